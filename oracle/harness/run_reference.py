@@ -1,0 +1,104 @@
+"""Run the UNMODIFIED reference (secastel/phaser, /root/reference/phaser/phaser.py) as an oracle.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under phaser_b200/ may import this module.  It exists to
+(1) pin oracle/port.py against the real reference and (2) generate the golden fixtures under
+tests/golden/ (see tests/golden/make_golden.py).  It needs /root/reference, which exists only in
+the build container -- never on the GPU box.
+
+How: the reference imports `pysam` without using it (phaser/phaser.py:15)
+and reaches samtools/bgzip/tabix/bedtools/bcftools only through bash pipelines
+(phaser/phaser.py:97-101, 1346, 1851), so a stub module on PYTHONPATH plus the PATH shims in
+oracle/harness/bin make it run end to end on SAM *text* passed as --bam.
+"""
+import gzip
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REFERENCE_DIR = os.environ.get("PHASER_REFERENCE_DIR", "/root/reference/phaser")
+
+OUTPUT_SUFFIXES = [
+    "haplotypic_counts.txt", "haplotypes.txt", "allele_config.txt",
+    "allelic_counts.txt", "variant_connections.txt", "vcf.gz",
+]
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(REFERENCE_DIR, "phaser.py"))
+
+
+def _env(hashseed):
+    env = dict(os.environ)
+    env["PATH"] = os.path.join(HERE, "bin") + os.pathsep + env.get("PATH", "")
+    env["PYTHONPATH"] = os.path.join(HERE, "stub") + os.pathsep + env.get("PYTHONPATH", "")
+    env["PYTHONHASHSEED"] = str(hashseed)
+    return env
+
+
+def run_mapper(sam_path, variant_table, out_path, baseq=10, isize_cutoff=0, hashseed=0):
+    """L1 oracle: reference call_read_variant_map.py on SAM text (phaser/call_read_variant_map.py:7-19)."""
+    cmd = [sys.executable, os.path.join(REFERENCE_DIR, "call_read_variant_map.py"),
+           "--variant_table", variant_table, "--o", out_path, "--baseq", str(baseq),
+           "--splice", "1", "--isize_cutoff", str(isize_cutoff)]
+    with open(sam_path, "rb") as fin:
+        subprocess.run(cmd, stdin=fin, stdout=subprocess.DEVNULL, check=True, env=_env(hashseed))
+    return out_path
+
+
+def run_reference(vcf_gz, bams, out_prefix, sample, mapq="255", baseq=10, paired_end="1",
+                  extra_args=(), hashseed=0, threads=1, quiet=True, timeout=None):
+    """L2/L3 oracle: the whole reference phaser.py (phaser/phaser.py:26-178).
+
+    `bams` are SAM text files (coordinate sorted, with @SQ lines).  Empty `.bai` / `.tbi` files are
+    created next to the inputs because the reference only checks that they exist
+    (phaser/phaser.py:124, 190).  Returns {suffix: path}.
+    """
+    if not reference_available():
+        raise RuntimeError("reference not found at %s" % REFERENCE_DIR)
+    if isinstance(bams, str):
+        bams = [bams]
+    for b in bams:
+        if not os.path.exists(b + ".bai"):
+            open(b + ".bai", "w").close()
+    if not os.path.exists(vcf_gz + ".tbi") and not os.path.exists(vcf_gz + ".csi"):
+        open(vcf_gz + ".tbi", "w").close()
+    cmd = [sys.executable, os.path.join(REFERENCE_DIR, "phaser.py"),
+           "--vcf", vcf_gz, "--bam", ",".join(bams), "--sample", sample,
+           "--mapq", str(mapq), "--baseq", str(baseq), "--paired_end", str(paired_end),
+           "--o", out_prefix, "--threads", str(threads)] + [str(a) for a in extra_args]
+    res = subprocess.run(cmd, env=_env(hashseed), stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                         timeout=timeout)
+    log = res.stdout.decode("utf-8", "replace")
+    if not quiet:
+        sys.stdout.write(log)
+    out = {"log": log, "returncode": res.returncode}
+    for suf in OUTPUT_SUFFIXES:
+        p = out_prefix + "." + suf
+        if os.path.exists(p):
+            out[suf] = p
+    return out
+
+
+def read_text(path):
+    if path.endswith(".gz"):
+        with gzip.open(path, "rt") as f:
+            return f.read()
+    with open(path) as f:
+        return f.read()
+
+
+if __name__ == "__main__":
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--vcf", required=True)
+    ap.add_argument("--bam", required=True)
+    ap.add_argument("--sample", required=True)
+    ap.add_argument("--o", required=True)
+    ap.add_argument("--mapq", default="255")
+    ap.add_argument("--paired_end", default="1")
+    ap.add_argument("rest", nargs="*")
+    a = ap.parse_args()
+    r = run_reference(a.vcf, a.bam.split(","), a.o, a.sample, a.mapq, 10, a.paired_end, a.rest, quiet=False)
+    sys.exit(r["returncode"])

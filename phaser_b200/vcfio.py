@@ -1,0 +1,137 @@
+"""VCF ingest (host): the het-site filter of the reference -> VariantTable.
+
+Mirrors, line for line in behaviour, the text pipeline + parser of the reference:
+  * `gunzip -c VCF | cut -f 1-9,<sample col> | grep -v '0|0\\|1|1'`      phaser/phaser.py:205-225
+  * the per-line het / PASS test                                           phaser/phaser.py:396-434
+  * the per-contig mapping table rows (ids, indel exclusion, maf)          phaser/phaser.py:1355-1413
+Fatal conditions keep the reference's messages (raised as PhaserFatal; the CLI prints
+"     FATAL ERROR: ..." and exits 1 like phaser/phaser.py:2032-2034).
+"""
+import gzip
+from collections import OrderedDict
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+from .layout import VariantTable, allele_code
+
+
+class PhaserFatal(Exception):
+    pass
+
+
+@dataclass
+class VcfStats:
+    het_count: int = 0
+    filter_count: int = 0
+    indels_excluded: int = 0
+    unphased_count: int = 0
+
+
+def sample_column_map(path, start_col=9, line_key="#CHR"):
+    """phaser/phaser.py:2326-2342"""
+    out = OrderedDict()
+    with gzip.open(path, "rt") as f:
+        for line in f:
+            if line_key in line:
+                cols = line.rstrip().rstrip("\n").split("\t")
+                for i in range(start_col, len(cols)):
+                    out[cols[i]] = i
+                break
+    return out
+
+
+def _annotation_to_dict(text, sep=";"):
+    out = OrderedDict()
+    for var in text.split(sep):
+        if "=" in var:
+            out[var.split("=")[0]] = var.split("=")[1]
+    return out
+
+
+def parse_vcf(path, sample_column: int, pass_only=1, chrom_of_interest="", chr_prefix="", id_separator="_",
+              include_indels=0, gw_phase_method=0, gw_af_field="AF"):
+    """Returns (VariantTable, VcfStats).  `sample_column` is the 0-based VCF column of the sample."""
+    if include_indels:
+        raise NotImplementedError("--include_indels 1 is not supported by the B200 mapper yet (multi-base alleles)")
+    contig_ban = [id_separator, ":"]
+    pool = OrderedDict()
+    st = VcfStats()
+    with gzip.open(path, "rt") as f:
+        for line in f:
+            cols = line.rstrip("\n").split("\t")
+            if line.startswith("#"):
+                continue
+            # cut -f 1-9,<col> ; grep -v '0|0\|1|1' acts on that cut line (anywhere in it)
+            cut = cols[0:9] + ([cols[sample_column]] if sample_column < len(cols) else [])
+            cut_line = "\t".join(cut)
+            if "0|0" in cut_line or "1|1" in cut_line:
+                continue
+            chrom = cut[0]
+            for item in contig_ban:
+                if item in chrom:
+                    raise PhaserFatal("Character '%s' must not be present in contig name. Please change id separtor "
+                                      "using --id_separator to a character not found in the contig names and try "
+                                      "again." % item)
+            if chrom_of_interest == "" or chrom_of_interest == chrom:
+                if chrom not in pool:
+                    pool[chrom] = []
+                fields = cut[8].split(":")
+                if "GT" in fields:
+                    geno_string = cut[9].split(":")[fields.index("GT")]
+                    xgeno = list(geno_string)
+                    unphased = False
+                    if "." not in xgeno:
+                        if "|" in xgeno:
+                            xgeno.remove("|")
+                        if "/" in xgeno:
+                            xgeno.remove("/")
+                            unphased = True
+                        if len(set(xgeno)) > 1:
+                            if pass_only == 0 or "PASS" in cut[6].split(";"):
+                                pool[chrom].append((cut, geno_string, xgeno))
+                                if unphased:
+                                    st.unphased_count += 1
+                            else:
+                                st.filter_count += 1
+    contigs: List[str] = []
+    off = [0]
+    pos, a0, a1, rl = [], [], [], []
+    ids, rsids, alls, gts, mafs = [], [], [], [], []
+    for chrom, rows in pool.items():
+        cname = chr_prefix + chrom
+        contigs.append(cname)
+        for cut, geno_string, xgeno in rows:
+            alt = cut[4].split(",")
+            all_alleles = [cut[3]] + alt
+            maf: Optional[float] = None
+            if gw_phase_method == 1:
+                info = _annotation_to_dict(cut[7])
+                if gw_af_field in info:
+                    afs = list(map(float, info[gw_af_field].split(",")))
+                    if len(afs) == len(alt):
+                        use = [int(a) - 1 for a in xgeno if a != "." and int(a) != 0]
+                        if use:
+                            maf = min(min(afs[x], 1 - afs[x]) for x in use)
+            if max(len(x) for x in all_alleles) == 1:
+                ind = [all_alleles[i] for i in range(len(all_alleles)) if str(i) in xgeno]
+                if len(ind) != 2 or len(xgeno) != 2:
+                    raise PhaserFatal("Variant %s:%s: only diploid genotypes with two distinct alleles are supported."
+                                      % (chrom, cut[1]))
+                pos.append(int(cut[1]))
+                a0.append(allele_code(ind[0])); a1.append(allele_code(ind[1]))
+                rl.append(len(cut[3]))
+                ids.append(cname + id_separator + cut[1] + id_separator + id_separator.join(all_alleles))
+                rsids.append(cut[2]); alls.append(all_alleles); gts.append(geno_string); mafs.append(str(maf))
+                st.het_count += 1
+            else:
+                st.indels_excluded += 1
+        off.append(len(pos))
+    vt = VariantTable(contigs, np.asarray(off, np.int64), np.asarray(pos, np.int32), np.asarray(a0, np.uint8),
+                      np.asarray(a1, np.uint8), np.asarray(rl, np.int32), ids, rsids, alls, gts, mafs)
+    for c in range(len(contigs)):
+        p = vt.pos[off[c]:off[c + 1]]
+        if p.shape[0] > 1 and np.any(np.diff(p) < 0):
+            raise PhaserFatal("VCF records of contig %s are not sorted by position." % contigs[c])
+    return vt, st
