@@ -1,0 +1,114 @@
+/* phz.h -- C ABI of the B200-native read -> variant -> haplotype path of phASER.
+ *
+ * This is the drop-in boundary.  The reference (secastel/phaser) has no FFI of its own: it is pure
+ * Python whose hot path is reached through (S1) the module function
+ * read_variant_map.do_read_variant_map (phaser/read_variant_map.py:3) -- which its README tells
+ * users to replace by a compiled read_variant_map.so (phaser/README.md:20-25) -- and (S2) the stage
+ * functions of phaser/phaser.py that process_vcf maps over contigs / pairs / blocks
+ * (phaser/phaser.py:442, 533, 556, 650, 680, 784, 808).  Each entry point below names the reference
+ * code it replaces.  INTEGRATION.md shows the ctypes stubs a maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes only.  `d_` pointers are DEVICE pointers (sm_100a build) --
+ * the caller owns them and keeps them alive until the stage that reads them has returned; `h_`
+ * pointers are host pointers.  Every function returns 0 on success and a negative code on error;
+ * phz_last_error() gives the message.  One context = one GPU = one CUDA stream; no internal threads.
+ */
+#ifndef PHZ_H
+#define PHZ_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct phz_ctx phz_ctx;
+
+#define PHZ_AS_BINS 65536          /* alignment-score histogram: bin = AS + 32768 */
+#define PHZ_AS_NONE INT32_MIN      /* as_cutoff value meaning "no cutoff" */
+
+/* Packed SoA of one BAM's records after the samtools-stage filters (phaser.py:505-513, 1346),
+ * grouped by contig in VCF order.  Replaces the SAM text stream read by read_variant_map.py:25-35. */
+typedef struct phz_reads {
+  int64_t n_records;
+  int64_t n_cigar_ops;             /* length of cigar[] */
+  int64_t n_bases;                 /* length of qual[]; seq[] holds (n_bases+1)/2 bytes */
+  const int64_t* h_contig_rec_off; /* HOST, n_contigs+1: records of contig c are [off[c], off[c+1]) */
+  const int32_t* pos;              /* 1-based leftmost position (SAM POS) */
+  const int32_t* tlen;             /* SAM TLEN */
+  const int16_t* aln_score;        /* AS:i, -32768 when the tag is absent */
+  const uint32_t* frag;            /* fragment id: one per distinct QNAME */
+  const uint32_t* cigar_off;       /* n_records+1 */
+  const uint32_t* cigar;           /* BAM encoding: len<<4 | op (MIDNSHP=X) */
+  const uint64_t* seq_off;         /* n_records+1, in bases */
+  const uint8_t* seq;              /* 4-bit BAM base codes, even base index = high nibble */
+  const uint8_t* qual;             /* phred, one byte per base */
+} phz_reads;
+
+const char* phz_last_error(void);
+/* "cuda-sm_100a" for the product library; the host logic-test double reports "hostsim". */
+const char* phz_backend_name(void);
+
+/* device: CUDA ordinal; stream: a cudaStream_t (0 = the legacy default stream). */
+phz_ctx* phz_create(int device, void* stream);
+void phz_destroy(phz_ctx* ctx);
+int phz_sync(phz_ctx* ctx);
+
+/* Het-site table of the sample, sorted by (contig, VCF order).  Replaces the per-contig mapping
+ * tables written by generate_mapping_table (phaser.py:1355-1413) and parsed by `variant`
+ * (read_variant_map.py:126-138).  a0/a1: 4-bit base codes of the two alleles the sample carries,
+ * in allele-index order (phaser.py:1431-1435); 0xFF = cannot equal a read base. */
+int phz_set_variants(phz_ctx* ctx, int n_contigs, const int64_t* h_contig_var_off, const int32_t* d_pos,
+                     const uint8_t* d_a0, const uint8_t* d_a1, int64_t n_variants);
+
+/* K1.  Replaces do_read_variant_map (read_variant_map.py:3-124) incl. split_read (:165-234) and
+ * identify_allele (:236-258) for one BAM: emits, in (record, segment, variant) order, one tuple per
+ * het SNV a spliced segment of a record covers.  All pointers of `reads` except h_contig_rec_off
+ * are device pointers.  Tuples stay inside the context (arrays "t_rec", "t_var", "t_misc"). */
+int phz_map_reads(phz_ctx* ctx, const phz_reads* reads, int baseq, double isize_cutoff, int64_t* n_candidates);
+/* Same with HOST arrays (pinned memory recommended): copies them to the device on the context's
+ * stream first.  This is the end-to-end entry point bench.py times. */
+int phz_map_reads_host(phz_ctx* ctx, const phz_reads* host_reads, int baseq, double isize_cutoff, int64_t* n_candidates);
+
+/* Exact histogram of the alignment scores of the tuples the reference mapper would print; the host
+ * derives numpy.percentile from it (phaser.py:545-553).  d_hist: PHZ_AS_BINS uint64 on the device. */
+int phz_as_histogram(phz_ctx* ctx, uint64_t* d_hist);
+
+/* Applies `int(AS) >= as_cutoff` (phaser.py:1304) and appends the surviving tuples of BAM
+ * `bam_index` to the run-wide store, i.e. process_mapping_result + the merge loops
+ * (phaser.py:1287-1328, 558-581).  d_frag: the BAM's fragment-id array (NULL after phz_map_reads_host). */
+int phz_commit_bam(phz_ctx* ctx, int bam_index, int32_t as_cutoff, const uint32_t* d_frag, int64_t* n_kept);
+
+/* Per-variant read lists/sets, noise sums (phaser.py:610-632), generate_connectivity_map
+ * (phaser.py:1265-1285), pair enumeration (:667-678) and the count part of test_variant_connection
+ * (:1594-1642).  h_noise[2] receives (base_match_count, base_mismatch_count). */
+int phz_build_graph(phz_ctx* ctx, uint64_t n_fragments, uint64_t bam_exclude_mask, uint64_t* h_noise,
+                    int64_t* n_edges, uint32_t* max_c_total);
+
+/* Edge drop (phaser.py:696-707) through the integer critical values h_kstar[c_total] computed on the
+ * host with scipy (so the binomial test of phaser.py:1649 agrees bit for bit), build_haplotypes
+ * (:1861-1882), phase_v3 (:2107-2324), block statistics and haplotypic counts (:876-931, 1048-1095).
+ * status_flags: bit0 = a sub-block larger than 24 variants needed exhaustive phasing (unsupported),
+ * bit1 = split_by_weak cannot reach max_block_size (the reference would not terminate). */
+int phz_phase(phz_ctx* ctx, const uint32_t* h_kstar, int64_t kstar_len, int max_block_size,
+              uint64_t bam_exclude_mask, int64_t* n_final_blocks, int* status_flags);
+
+/* The per-variant read lists behind the aReads/bReads columns (phaser.py:1105-1115). */
+int phz_read_lists(phz_ctx* ctx, uint64_t bam_exclude_mask, int64_t* n_entries);
+
+/* Result / intermediate arrays by name (DESIGN.md lists them). */
+int phz_array(phz_ctx* ctx, const char* name, const void** d_ptr, int64_t* count, int* elem_bytes);
+int phz_download(phz_ctx* ctx, const char* name, void* h_dst, int64_t dst_bytes);
+/* counters[16]: n_tuples, entries, groups, pairs, distinct pairs, edges, dropped, members, blocks,
+ * hard blocks, final blocks, read-list entries, n_candidates, n_bams, 0, 0 */
+int phz_counters(phz_ctx* ctx, int64_t* counters);
+/* CUDA-event timing of the K1 passes of the LAST phz_map_reads call on the context's stream:
+ * ms[0] = count pass, ms[1] = scan + size readback, ms[2] = emit pass (-1 when profiling is off). */
+int phz_set_profiling(phz_ctx* ctx, int on);
+int phz_map_times(phz_ctx* ctx, float* ms);
+/* kernels of this library launched so far / library (CUB) passes launched so far */
+int phz_launch_counts(phz_ctx* ctx, uint64_t* own, uint64_t* library);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,190 @@
+// extern "C" surface of include/phz.h over Pipeline<PHZ_BACKEND>.  Included by phz_api.cu (product,
+// DeviceBackend) and by tests/hostsim/hostsim.cpp (logic-test double, HostSimBackend).
+#include "../../include/phz.h"
+#include "phz_pipeline.h"
+#include <climits>
+#include <map>
+
+using namespace phz;
+
+struct phz_ctx {
+  Pipeline<PHZ_BACKEND> p;
+  // staging for phz_map_reads_host
+  Buf<PHZ_BACKEND, int32_t> st_pos, st_tlen; Buf<PHZ_BACKEND, int16_t> st_as; Buf<PHZ_BACKEND, u32> st_frag, st_coff, st_cig;
+  Buf<PHZ_BACKEND, u64> st_soff; Buf<PHZ_BACKEND, u8> st_seq, st_qual;
+  phz_ctx() {
+    PHZ_BACKEND* b = &p.be;
+    st_pos.bind(b); st_tlen.bind(b); st_as.bind(b); st_frag.bind(b); st_coff.bind(b); st_cig.bind(b); st_soff.bind(b);
+    st_seq.bind(b); st_qual.bind(b);
+  }
+};
+
+static thread_local std::string g_err;
+
+#define PHZ_TRY try {
+#define PHZ_CATCH                                                     \
+  }                                                                   \
+  catch (const std::exception& e) { g_err = e.what(); return -1; }    \
+  catch (...) { g_err = "unknown error"; return -2; }                 \
+  return 0;
+
+extern "C" {
+
+const char* phz_last_error(void) { return g_err.c_str(); }
+const char* phz_backend_name(void) { return PHZ_BACKEND_NAME; }
+
+phz_ctx* phz_create(int device, void* stream) {
+  try {
+#ifdef __CUDACC__
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { g_err = "no CUDA device available (this library has no CPU path)"; return nullptr; }
+    PHZ_CUDA(cudaSetDevice(device));
+#endif
+    phz_ctx* c = new phz_ctx();
+    c->p.be.device = device;
+#ifdef __CUDACC__
+    c->p.be.stream = (cudaStream_t)stream;
+#else
+    (void)stream;
+#endif
+    return c;
+  } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+
+void phz_destroy(phz_ctx* ctx) { delete ctx; }
+
+int phz_sync(phz_ctx* ctx) { PHZ_TRY ctx->p.be.sync(); PHZ_CATCH }
+
+int phz_set_variants(phz_ctx* ctx, int n_contigs, const int64_t* h_off, const int32_t* d_pos, const uint8_t* d_a0,
+                     const uint8_t* d_a1, int64_t n_variants) {
+  PHZ_TRY ctx->p.set_variants(n_contigs, h_off, d_pos, d_a0, d_a1, n_variants); PHZ_CATCH
+}
+
+static ReadsView view_of(const phz_reads* r, int nc) {
+  ReadsView v;
+  v.n_records = r->n_records; v.n_contigs = nc; v.contig_rec_off = nullptr;
+  v.pos = r->pos; v.tlen = r->tlen; v.aln_score = r->aln_score; v.frag = r->frag;
+  v.cigar_off = r->cigar_off; v.cigar = r->cigar; v.seq_off = (const u64*)r->seq_off; v.seq = r->seq; v.qual = r->qual;
+  return v;
+}
+
+int phz_map_reads(phz_ctx* ctx, const phz_reads* reads, int baseq, double isize_cutoff, int64_t* n_candidates) {
+  PHZ_TRY
+  ReadsView v = view_of(reads, ctx->p.nc);
+  *n_candidates = ctx->p.map_reads(v, reads->h_contig_rec_off, baseq, isize_cutoff);
+  PHZ_CATCH
+}
+
+int phz_map_reads_host(phz_ctx* ctx, const phz_reads* h, int baseq, double isize_cutoff, int64_t* n_candidates) {
+  PHZ_TRY
+  auto& be = ctx->p.be;
+  int64_t R = h->n_records;
+  phz_reads d = *h;
+  be.h2d(ctx->st_pos.ensure(R), h->pos, R * 4); d.pos = ctx->st_pos.p;
+  be.h2d(ctx->st_tlen.ensure(R), h->tlen, R * 4); d.tlen = ctx->st_tlen.p;
+  be.h2d(ctx->st_as.ensure(R), h->aln_score, R * 2); d.aln_score = ctx->st_as.p;
+  be.h2d(ctx->st_frag.ensure(R), h->frag, R * 4); d.frag = ctx->st_frag.p;
+  be.h2d(ctx->st_coff.ensure(R + 1), h->cigar_off, (R + 1) * 4); d.cigar_off = ctx->st_coff.p;
+  be.h2d(ctx->st_cig.ensure(h->n_cigar_ops), h->cigar, h->n_cigar_ops * 4); d.cigar = ctx->st_cig.p;
+  be.h2d(ctx->st_soff.ensure(R + 1), h->seq_off, (R + 1) * 8); d.seq_off = (const uint64_t*)ctx->st_soff.p;
+  be.h2d(ctx->st_seq.ensure((h->n_bases + 1) / 2), h->seq, (h->n_bases + 1) / 2); d.seq = ctx->st_seq.p;
+  be.h2d(ctx->st_qual.ensure(h->n_bases), h->qual, h->n_bases); d.qual = ctx->st_qual.p;
+  ReadsView v = view_of(&d, ctx->p.nc);
+  *n_candidates = ctx->p.map_reads(v, h->h_contig_rec_off, baseq, isize_cutoff);
+  PHZ_CATCH
+}
+
+int phz_as_histogram(phz_ctx* ctx, uint64_t* d_hist) { PHZ_TRY ctx->p.as_histogram((u64*)d_hist); PHZ_CATCH }
+
+int phz_commit_bam(phz_ctx* ctx, int bam_index, int32_t as_cutoff, const uint32_t* d_frag, int64_t* n_kept) {
+  PHZ_TRY
+  const u32* f = d_frag ? d_frag : ctx->st_frag.p;
+  if (!f) throw PhzError("phz_commit_bam: no fragment ids");
+  *n_kept = ctx->p.commit_bam(bam_index, as_cutoff, f);
+  PHZ_CATCH
+}
+
+int phz_build_graph(phz_ctx* ctx, uint64_t n_fragments, uint64_t excl, uint64_t* h_noise, int64_t* n_edges, uint32_t* max_c_total) {
+  PHZ_TRY
+  u64 nz[2] = {0, 0};
+  ctx->p.build_graph(n_fragments, excl, nz);
+  h_noise[0] = nz[0]; h_noise[1] = nz[1];
+  *n_edges = ctx->p.E; *max_c_total = ctx->p.max_tot;
+  PHZ_CATCH
+}
+
+int phz_phase(phz_ctx* ctx, const uint32_t* h_kstar, int64_t kstar_len, int max_block_size, uint64_t excl,
+              int64_t* n_final_blocks, int* status_flags) {
+  PHZ_TRY
+  int err = 0;
+  ctx->p.phase(h_kstar, kstar_len, max_block_size, excl, &err);
+  *n_final_blocks = ctx->p.NF; *status_flags = err;
+  PHZ_CATCH
+}
+
+int phz_read_lists(phz_ctx* ctx, uint64_t excl, int64_t* n_entries) {
+  PHZ_TRY *n_entries = ctx->p.read_lists(excl); PHZ_CATCH
+}
+
+struct ArrRef { const void* p; int64_t n; int eb; };
+
+static bool find_array(phz_ctx* ctx, const std::string& name, ArrRef* out) {
+  auto& p = ctx->p;
+  const int64_t nb = p.n_bams > 0 ? p.n_bams : 1;
+#define A(nm, buf, cnt) if (name == nm) { *out = ArrRef{(const void*)p.buf.p, (int64_t)(cnt), (int)sizeof(*p.buf.p)}; return true; }
+  A("t_rec", t_rec, p.n_cand) A("t_var", t_var, p.n_cand) A("t_misc", t_misc, p.n_cand)
+  A("g_frag", g_frag, p.n_tuples) A("g_var", g_var, p.n_tuples) A("g_cb", g_cb, p.n_tuples)
+  A("vfirst", vfirst, p.V) A("ncls", ncls, p.V * 3) A("setsize", setsize, p.V * 3) A("vb_cnt", vb_cnt, p.V * nb * 2)
+  A("vrank", vrank, p.V) A("cfirst", cfirst, p.nc) A("crank", crank, p.nc)
+  A("e_key", e_key, p.NE) A("e_bam", e_bam, p.NE) A("e_mask", e_mask, p.NE) A("e_tmin", e_tmin, p.NE) A("grp_off", grp_off, p.NG + 1)
+  A("ed_a", ed_a, p.E) A("ed_b", ed_b, p.E) A("ed_sup", ed_sup, p.E) A("ed_tot", ed_tot, p.E) A("ed_n9", ed_n9, p.E * 9)
+  A("ed_cfg", ed_cfg, p.E) A("ed_keep", ed_keep, p.E)
+  A("members", members, p.NM) A("blk_off", blk_off, p.NB + 1) A("blk_order", blk_order, p.NB) A("blk_status", blk_status, p.NB)
+  A("blk_nfinal", blk_nfinal, p.NB) A("blk_rank", blk_rank, p.NB)
+  A("fb_first", fb_first, p.NF) A("fb_len", fb_len, p.NF) A("fb_blk", fb_blk, p.NF) A("fb_sup", fb_sup, p.NF) A("fb_tot", fb_tot, p.NF)
+  A("fb_cnt", fb_cnt, p.NF * 2) A("fb_bcnt", fb_bcnt, p.NF * nb * 2) A("v_final", v_final, p.V) A("v_hap", v_hap, p.V)
+  A("rl_frag", rl_frag, p.NRL) A("rl_var", rl_var, p.NRL) A("rl_row", rl_row, p.NRL)
+#undef A
+  return false;
+}
+
+int phz_array(phz_ctx* ctx, const char* name, const void** d_ptr, int64_t* count, int* elem_bytes) {
+  PHZ_TRY
+  ArrRef r;
+  if (!find_array(ctx, name, &r)) throw PhzError(std::string("unknown array: ") + name);
+  *d_ptr = r.p; *count = r.n; *elem_bytes = r.eb;
+  PHZ_CATCH
+}
+
+int phz_download(phz_ctx* ctx, const char* name, void* h_dst, int64_t dst_bytes) {
+  PHZ_TRY
+  ArrRef r;
+  if (!find_array(ctx, name, &r)) throw PhzError(std::string("unknown array: ") + name);
+  if (r.n * r.eb > dst_bytes) throw PhzError(std::string("destination too small for array ") + name);
+  if (r.n > 0) ctx->p.be.d2h(h_dst, r.p, (size_t)(r.n * r.eb)); else ctx->p.be.sync();
+  PHZ_CATCH
+}
+
+int phz_counters(phz_ctx* ctx, int64_t* c) {
+  PHZ_TRY
+  auto& p = ctx->p;
+  int64_t v[16] = {p.n_tuples, p.NE, p.NG, p.NP, p.NX, p.E, (int64_t)p.n_dropped, p.NM, p.NB, p.NH, p.NF, p.NRL,
+                   p.n_cand, p.n_bams, 0, 0};
+  for (int i = 0; i < 16; ++i) c[i] = v[i];
+  PHZ_CATCH
+}
+
+int phz_set_profiling(phz_ctx* ctx, int on) { PHZ_TRY ctx->p.be.profiling = on != 0; PHZ_CATCH }
+
+int phz_map_times(phz_ctx* ctx, float* ms) {
+  PHZ_TRY
+  ms[0] = ctx->p.be.elapsed(0, 1); ms[1] = ctx->p.be.elapsed(1, 2); ms[2] = ctx->p.be.elapsed(2, 3);
+  PHZ_CATCH
+}
+
+int phz_launch_counts(phz_ctx* ctx, uint64_t* own, uint64_t* library) {
+  PHZ_TRY *own = ctx->p.be.launches; *library = ctx->p.be.lib_launches; PHZ_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,166 @@
+// K1 per-record logic: CIGAR walk -> spliced segments -> (record, segment, variant, allele class).
+//
+// Replaces read_variant_map.py of the reference: the streaming join (read_variant_map.py:25-123),
+// split_read (:165-234) and identify_allele (:236-258).  For coordinate-sorted input the join is a
+// pure predicate per (record, segment, variant) (SURVEY.md "K1 spec"): a het SNV at VCF position p is
+// tested against segment s of a record at POS iff 0 <= p-(POS+seg_start) < len(pseudo_read(s)).
+// Reference quirks kept on purpose: insertion keys are whole-read reference offsets but are looked
+// up with segment-relative offsets (Q3); an insertion right after the SNV base turns the allele into
+// a multi-base string (class "other", Q4); deletion placeholders and IUPAC 'D' are stripped (Q5).
+#pragma once
+#include "phz_backend.h"
+
+namespace phz {
+
+struct ReadsView {
+  int64_t n_records;
+  int n_contigs;
+  const int64_t* contig_rec_off;   // [n_contigs+1] (device)
+  const int32_t* pos;
+  const int32_t* tlen;
+  const int16_t* aln_score;
+  const u32* frag;
+  const u32* cigar_off;            // [R+1]
+  const u32* cigar;
+  const u64* seq_off;              // [R+1]
+  const u8* seq;                   // nibble packed
+  const u8* qual;
+};
+
+struct VariantsView {
+  int64_t n_variants;
+  int n_contigs;
+  const int64_t* contig_var_off;   // [n_contigs+1] (device)
+  const int32_t* pos;
+  const u8* a0;
+  const u8* a1;
+};
+
+enum { CLS_A0 = 0, CLS_A1 = 1, CLS_OTHER = 2, CLS_NONE = 3 };
+enum { OP_M = 0, OP_I = 1, OP_D = 2, OP_N = 3, OP_S = 4, OP_H = 5, OP_P = 6, OP_EQ = 7, OP_X = 8 };
+constexpr u8 BASE_N = 15, BASE_D = 13;
+
+// t_misc layout: bits 0-1 class, bit 2 multi-base string, bits 4-7 first base code, bits 8-15 segment, bits 16-31 AS
+PHZ_HD u32 pack_misc(int cls, int multi, int base, int seg, int as16) {
+  return (u32)cls | ((u32)multi << 2) | ((u32)(base & 15) << 4) | ((u32)(seg > 255 ? 255 : seg) << 8) | ((u32)(as16 & 0xFFFF) << 16);
+}
+PHZ_HD int misc_cls(u32 m) { return m & 3; }
+PHZ_HD int misc_as(u32 m) { return (int)(int16_t)(m >> 16); }
+
+PHZ_HD bool isize_ok(int32_t tlen, double cutoff) {
+  // read_variant_map.py:35,51: abs(TLEN) <= isize_cutoff unless the cutoff is 0
+  if (cutoff == 0.0) return true;
+  int64_t t = tlen; if (t < 0) t = -t;
+  return (double)t <= cutoff;
+}
+
+PHZ_HD u8 masked_base(const ReadsView& rv, u64 base_off, int q, int baseq) {
+  u64 i = base_off + (u64)q;
+  u8 b = rv.seq[i >> 1];
+  b = (i & 1) ? (b & 15) : (b >> 4);
+  return ((int)rv.qual[i] < baseq) ? BASE_N : b;    // read_variant_map.py:179-184
+}
+
+// Walks one record.  EMIT=false: returns the number of candidate (segment, variant) pairs.
+// EMIT=true: writes one tuple per candidate starting at out index `o` (class CLS_NONE when the
+// reference would print nothing) and returns the number written.
+template <bool EMIT>
+PHZ_HD u32 map_record(const ReadsView& rv, const VariantsView& vv, int64_t r, int contig, int baseq, double isize_cutoff,
+                      u64 o, u32* t_rec, u32* t_var, u32* t_misc) {
+  if (!isize_ok(rv.tlen[r], isize_cutoff)) return 0;
+  const int64_t v0 = vv.contig_var_off[contig], v1 = vv.contig_var_off[contig + 1];
+  if (v0 == v1) return 0;
+  const int32_t rpos = rv.pos[r];
+  const u32 c0 = rv.cigar_off[r], c1 = rv.cigar_off[r + 1];
+  const u64 boff = rv.seq_off[r];
+  const int as16 = rv.aln_score[r];
+  u32 n_out = 0;
+  int seg = 0;
+  u32 k = c0;
+  int64_t gp = 0;      // whole-read reference offset (genome_pos)
+  int64_t qp = 0;      // query offset (read_pos)
+  while (k <= c1) {
+    // one segment: ops [k, kend) up to (not including) the closing N or the end
+    const u32 kseg = k;
+    const int64_t seg_start = gp, q_start = qp;
+    int64_t seg_len = 0;
+    u32 kk = k;
+    for (; kk < c1; ++kk) {
+      u32 c = rv.cigar[kk]; int op = c & 15; int64_t n = c >> 4;
+      if (op == OP_N) break;
+      if (op == OP_M || op == OP_EQ || op == OP_X || op == OP_D) seg_len += n;
+    }
+    const u32 kend = kk;
+    if (seg_len > 0) {
+      // candidates: variants with seg_start <= pos-rpos and pos-rpos+1 <= seg_start+seg_len
+      int64_t lo_pos = (int64_t)rpos + seg_start, hi_pos = lo_pos + seg_len;   // [lo_pos, hi_pos)
+      if (lo_pos < 2147483647LL) {
+        int32_t hi32 = hi_pos > 2147483647LL ? 2147483647 : (int32_t)hi_pos;
+        int64_t lo = lower_bound_i32(vv.pos, v0, v1, (int32_t)lo_pos);
+        int64_t hi = lower_bound_i32(vv.pos, lo, v1, hi32);
+        if (!EMIT) {
+          n_out += (u32)(hi - lo);
+        } else {
+          for (int64_t j = lo; j < hi; ++j) {
+            const int64_t st = (int64_t)vv.pos[j] - lo_pos;      // offset in pseudo_read
+            // locate pseudo_read[st] and the insertion keyed st (keys are whole-read offsets: Q3)
+            int64_t g = seg_start, q = q_start;
+            int base = -1;            // -1: not found (cannot happen), 16: deletion placeholder
+            int64_t ins_q = -1, ins_n = 0;
+            for (u32 x = kseg; x < kend; ++x) {
+              u32 c = rv.cigar[x]; int op = c & 15; int64_t n = c >> 4;
+              if (op == OP_M || op == OP_EQ || op == OP_X) {
+                int64_t sp = g - seg_start;
+                if (st >= sp && st < sp + n) base = masked_base(rv, boff, (int)(q + (st - sp)), baseq);
+                g += n; q += n;
+              } else if (op == OP_D) {
+                int64_t sp = g - seg_start;
+                if (st >= sp && st < sp + n) base = 16;
+                g += n;
+              } else if (op == OP_I) {
+                if (g - 1 == st) { ins_q = q; ins_n = n; }       // later insertion with the same key wins
+                q += n;
+              } else if (op == OP_S) {
+                q += n;
+              }
+            }
+            // string = [base] + inserted bases, minus every 'D'
+            int n_chars = 0, first = 0;
+            if (base != 16 && base != BASE_D && base >= 0) { first = base; n_chars = 1; }
+            for (int64_t z = 0; z < ins_n; ++z) {
+              int b = masked_base(rv, boff, (int)(ins_q + z), baseq);
+              if (b != BASE_D) { if (n_chars == 0) first = b; n_chars++; }
+            }
+            int cls, multi = 0;
+            if (n_chars == 0) cls = CLS_NONE;                     // "" -> nothing written
+            else if (n_chars == 1) {
+              if (first == BASE_N) cls = CLS_NONE;                // "N" -> nothing written
+              else if (first == vv.a0[j]) cls = CLS_A0;
+              else if (first == vv.a1[j]) cls = CLS_A1;
+              else cls = CLS_OTHER;
+            } else { cls = CLS_OTHER; multi = 1; }
+            t_rec[o + n_out] = (u32)r;
+            t_var[o + n_out] = (u32)j;
+            t_misc[o + n_out] = pack_misc(cls, multi, first, seg, as16);
+            n_out++;
+          }
+        }
+      }
+    }
+    if (kend >= c1) break;
+    // closing N: advance reference, open the next segment
+    gp = seg_start; qp = q_start;
+    for (u32 x = kseg; x < kend; ++x) {
+      u32 c = rv.cigar[x]; int op = c & 15; int64_t n = c >> 4;
+      if (op == OP_M || op == OP_EQ || op == OP_X) { gp += n; qp += n; }
+      else if (op == OP_D) gp += n;
+      else if (op == OP_I || op == OP_S) qp += n;
+    }
+    gp += (int64_t)(rv.cigar[kend] >> 4);
+    k = kend + 1;
+    seg++;
+  }
+  return n_out;
+}
+
+}  // namespace phz

@@ -1,0 +1,608 @@
+// The read -> variant -> haplotype pipeline on packed SoA arrays (see DESIGN.md for the data layout).
+//
+// Stage map (reference file:line each stage replaces, all in /root/reference/phaser/):
+//   map_reads      read_variant_map.py:25-123,165-258  K1: one logical thread per record walks the CIGAR
+//   as_histogram   phaser.py:545-553                    exact AS histogram -> percentile on host
+//   commit_bam     phaser.py:1304                       AS cutoff filter, append to the run-wide tuple store
+//   build_graph    phaser.py:1287-1328, 558-581, 610-640, 1265-1285, 667-678, 1594-1642
+//                  per-variant lists/sets, noise sums, fragment->variant groups, pair table, edge table
+//   phase          phaser.py:686-726, 1861-1887, 2107-2324, 865-931, 1048-1095
+//                  edge drop (integer critical value), components, block order, phasing, counts
+//   read_lists     phaser.py:1105-1115                  per (block, BAM, haplotype, variant) read lists
+#pragma once
+#include "phz_map_core.h"
+#include "phz_phase_core.h"
+
+#ifdef __CUDACC__
+#define PHZ_LAMBDA [=] __host__ __device__
+#else
+#define PHZ_LAMBDA [=]
+#endif
+
+namespace phz {
+
+constexpr u32 NONE32 = 0xFFFFFFFFu;
+constexpr u64 NONE64 = 0xFFFFFFFFFFFFFFFFull;
+constexpr int AS_BINS = 65536;
+
+inline int ceil_log2_host(u64 x) { int b = 0; while (((u64)1 << b) < x && b < 63) b++; return b < 1 ? 1 : b; }
+
+#ifdef __CUDACC__
+// AS histogram with a shared-memory window: alignment scores cluster in a few dozen values, so
+// global atomics on them would serialise in L2.
+__global__ void __launch_bounds__(256) as_hist_kernel(const u32* __restrict__ t_misc, int64_t n, u64* __restrict__ hist) {
+  constexpr int W = 4096, LO = 32768 - 2048;        // window: AS in [-2048, 2047]
+  __shared__ u32 sh[W];
+  for (int i = threadIdx.x; i < W; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    u32 m = t_misc[i];
+    if ((m & 3) == CLS_NONE) continue;
+    int bin = (int)(int16_t)(m >> 16) + 32768;
+    int w = bin - LO;
+    if (w >= 0 && w < W) atomicAdd(&sh[w], 1u); else atomicAdd((unsigned long long*)&hist[bin], 1ull);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < W; i += blockDim.x) if (sh[i]) atomicAdd((unsigned long long*)&hist[LO + i], (unsigned long long)sh[i]);
+}
+#endif
+
+template <class B>
+struct Pipeline {
+  B be;
+  // ------------------------------------------------------------------ variants
+  int nc = 0; int64_t V = 0; int vbits = 1;
+  std::vector<int64_t> h_cvoff;
+  Buf<B, int64_t> d_cvoff, d_croff;
+  const int32_t* vpos = nullptr; const u8* va0 = nullptr; const u8* va1 = nullptr;
+  Buf<B, u32> vcontig;
+  // ------------------------------------------------------------------ K1 candidates of the current BAM
+  Buf<B, u32> cand_cnt, cand_off, t_rec, t_var, t_misc, keep_flag, keep_off;
+  int64_t n_cand = 0;
+  // ------------------------------------------------------------------ run-wide kept tuples
+  Buf<B, u32> g_frag, g_var; Buf<B, u8> g_cb;      // g_cb = class | bam << 2
+  int64_t n_tuples = 0; int n_bams = 0;
+  // ------------------------------------------------------------------ per-variant
+  Buf<B, u32> vfirst, ncls, setsize, vb_cnt, cfirst, crank;
+  Buf<B, u64> vrank, noise;
+  // ------------------------------------------------------------------ fragment x variant entries
+  Buf<B, u64> s_key, s_key2; Buf<B, u32> s_val, s_val2, s_flag, s_scan;
+  Buf<B, u64> e_key; Buf<B, u8> e_bam; Buf<B, u32> e_mask, e_tmin, e_flag, e_scan;
+  Buf<B, u32> grp_off, pair_cnt, pair_off;
+  int64_t NE = 0, NG = 0, NP = 0;
+  // ------------------------------------------------------------------ pairs / edges
+  Buf<B, u64> p_key, p_key2; Buf<B, u32> p_val, p_val2, p_flag, p_scan, pe_start;
+  Buf<B, u32> x_flag, x_scan;
+  Buf<B, u32> ed_a, ed_b, ed_sup, ed_tot, ed_n9; Buf<B, u8> ed_cfg, ed_keep;
+  Buf<B, u32> scalars, kstar_d;                     // scalars: [0]=max_tot [1]=err flags [2]=dropped
+  int64_t NX = 0, E = 0; u32 max_tot = 0;
+  // ------------------------------------------------------------------ blocks
+  Buf<B, u32> parent, deg, root, m_flag, m_scan, m_list, m_key, m_key2, m_val2, members;
+  Buf<B, u32> b_flag, b_scan, blk_off, blk_of, pos_in_blk, blk_contig_rank, blk_order, blk_pos;
+  Buf<B, u64> blk_rank, bs_key, bs_key2; Buf<B, u32> bs_val, bs_val2, bs_k32, bs_k32b;
+  Buf<B, u64> d_key, d_key2; Buf<B, u32> d_sign, d_sign2, adj_off;
+  Buf<B, u8> color, v_hap, blk_status; Buf<B, u32> bfsq, run_start, run_len, blk_nfinal, v_fin_local;
+  Buf<B, u32> ebk_cnt, ebk_off, ebk_key, ebk_key2, ebk_val, ebk_list;
+  Buf<B, u32> h_flag, h_scan, h_list, h_words, h_woff, h_scratch;
+  Buf<B, u32> nf_ord, fb_base, fb_first, fb_len, fb_blk, v_final, fb_sup, fb_tot, fb_cnt, fb_bcnt;
+  int64_t NM = 0, NB = 0, NH = 0, NF = 0; u32 n_dropped = 0;
+  // ------------------------------------------------------------------ read lists
+  Buf<B, u32> rl_flag, rl_scan, rl_k32, rl_k32b, rl_t, rl_t2; Buf<B, u64> rl_k64, rl_k64b;
+  Buf<B, u32> rl_frag, rl_var, rl_row;
+  int64_t NRL = 0;
+
+  Pipeline() {
+    B* b = &be;
+    d_cvoff.bind(b); d_croff.bind(b); vcontig.bind(b);
+    cand_cnt.bind(b); cand_off.bind(b); t_rec.bind(b); t_var.bind(b); t_misc.bind(b); keep_flag.bind(b); keep_off.bind(b);
+    g_frag.bind(b); g_var.bind(b); g_cb.bind(b);
+    vfirst.bind(b); ncls.bind(b); setsize.bind(b); vb_cnt.bind(b); cfirst.bind(b); crank.bind(b); vrank.bind(b); noise.bind(b);
+    s_key.bind(b); s_key2.bind(b); s_val.bind(b); s_val2.bind(b); s_flag.bind(b); s_scan.bind(b);
+    e_key.bind(b); e_bam.bind(b); e_mask.bind(b); e_tmin.bind(b); e_flag.bind(b); e_scan.bind(b);
+    grp_off.bind(b); pair_cnt.bind(b); pair_off.bind(b);
+    p_key.bind(b); p_key2.bind(b); p_val.bind(b); p_val2.bind(b); p_flag.bind(b); p_scan.bind(b); pe_start.bind(b);
+    x_flag.bind(b); x_scan.bind(b);
+    ed_a.bind(b); ed_b.bind(b); ed_sup.bind(b); ed_tot.bind(b); ed_n9.bind(b); ed_cfg.bind(b); ed_keep.bind(b); scalars.bind(b); kstar_d.bind(b);
+    parent.bind(b); deg.bind(b); root.bind(b); m_flag.bind(b); m_scan.bind(b); m_list.bind(b); m_key.bind(b); m_key2.bind(b);
+    m_val2.bind(b); members.bind(b);
+    b_flag.bind(b); b_scan.bind(b); blk_off.bind(b); blk_of.bind(b); pos_in_blk.bind(b); blk_contig_rank.bind(b);
+    blk_order.bind(b); blk_pos.bind(b); blk_rank.bind(b); bs_key.bind(b); bs_key2.bind(b); bs_val.bind(b); bs_val2.bind(b);
+    bs_k32.bind(b); bs_k32b.bind(b);
+    d_key.bind(b); d_key2.bind(b); d_sign.bind(b); d_sign2.bind(b); adj_off.bind(b);
+    color.bind(b); v_hap.bind(b); blk_status.bind(b); bfsq.bind(b); run_start.bind(b); run_len.bind(b); blk_nfinal.bind(b);
+    v_fin_local.bind(b);
+    ebk_cnt.bind(b); ebk_off.bind(b); ebk_key.bind(b); ebk_key2.bind(b); ebk_val.bind(b); ebk_list.bind(b);
+    h_flag.bind(b); h_scan.bind(b); h_list.bind(b); h_words.bind(b); h_woff.bind(b); h_scratch.bind(b);
+    nf_ord.bind(b); fb_base.bind(b); fb_first.bind(b); fb_len.bind(b); fb_blk.bind(b); v_final.bind(b); fb_sup.bind(b);
+    fb_tot.bind(b); fb_cnt.bind(b); fb_bcnt.bind(b);
+    rl_flag.bind(b); rl_scan.bind(b); rl_k32.bind(b); rl_k32b.bind(b); rl_t.bind(b); rl_t2.bind(b); rl_k64.bind(b);
+    rl_k64b.bind(b); rl_frag.bind(b); rl_var.bind(b); rl_row.bind(b);
+  }
+
+  u32 fetch_u32(const u32* p) { u32 v = 0; be.d2h(&v, p, sizeof(u32)); return v; }
+
+  // =================================================================== variants
+  void set_variants(int n_contigs, const int64_t* contig_var_off_host, const int32_t* d_pos, const u8* d_a0,
+                    const u8* d_a1, int64_t n_variants) {
+    nc = n_contigs; V = n_variants;
+    if (V >= (int64_t)0x7FFFFFFF) throw PhzError("too many variants for 32-bit variant ids");
+    vbits = ceil_log2_host((u64)(V > 1 ? V : 2));
+    h_cvoff.assign(contig_var_off_host, contig_var_off_host + nc + 1);
+    be.h2d(d_cvoff.ensure(nc + 1), h_cvoff.data(), (nc + 1) * sizeof(int64_t));
+    vpos = d_pos; va0 = d_a0; va1 = d_a1;
+    u32* vc = vcontig.ensure(V);
+    const int64_t* off = d_cvoff.p; int n = nc;
+    be.for_each(V, PHZ_LAMBDA(int64_t v) { vc[v] = (u32)upper_slot_i64(off, n, v); });
+    n_tuples = 0; n_bams = 0; n_cand = 0;
+  }
+
+  // =================================================================== K1
+  // Returns the number of candidate (record, segment, variant) triples of this BAM.
+  int64_t map_reads(ReadsView rv, const int64_t* contig_rec_off_host, int baseq, double isize_cutoff) {
+    if (rv.n_contigs != nc) throw PhzError("reads and variants disagree on the number of contigs");
+    be.h2d(d_croff.ensure(nc + 1), contig_rec_off_host, (nc + 1) * sizeof(int64_t));
+    rv.contig_rec_off = d_croff.p;
+    VariantsView vv{V, nc, d_cvoff.p, vpos, va0, va1};
+    const int64_t R = rv.n_records;
+    if (R >= (int64_t)0x7FFFFFFF) throw PhzError("more than 2^31-1 records in one map_reads call; split the BAM");
+    u32* cnt = cand_cnt.ensure(R + 1);
+    u32* off = cand_off.ensure(R + 2);
+    int ncg = nc;
+    be.mark(0);
+    be.for_each(R, PHZ_LAMBDA(int64_t r) {
+      int c = upper_slot_i64(rv.contig_rec_off, ncg, r);
+      cnt[r] = map_record<false>(rv, vv, r, c, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr);
+    });
+    be.mark(1);
+    be.exclusive_scan_u32(cnt, off, R);
+    n_cand = R > 0 ? (int64_t)fetch_u32(off + R) : 0;
+    u32* tr = t_rec.ensure(n_cand); u32* tv = t_var.ensure(n_cand); u32* tm = t_misc.ensure(n_cand);
+    be.mark(2);
+    be.for_each(R, PHZ_LAMBDA(int64_t r) {
+      if (cnt[r] == 0) return;
+      int c = upper_slot_i64(rv.contig_rec_off, ncg, r);
+      map_record<true>(rv, vv, r, c, baseq, isize_cutoff, off[r], tr, tv, tm);
+    });
+    be.mark(3);
+    return n_cand;
+  }
+
+  // hist: u64[65536] on the device, bin = AS + 32768, counts the tuples the reference would print
+  void as_histogram(u64* hist) {
+    be.memset0(hist, AS_BINS * sizeof(u64));
+    if (n_cand == 0) return;
+    const u32* tm = t_misc.p; int64_t n = n_cand;
+#ifdef __CUDACC__
+    int blocks = (int)((n + 256 * 16 - 1) / (256 * 16)); if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
+    as_hist_kernel<<<blocks, 256, 0, be.stream>>>(tm, n, hist);
+    PHZ_CUDA(cudaGetLastError());
+    be.launches++;
+#else
+    be.for_each(n, PHZ_LAMBDA(int64_t i) {
+      u32 m = tm[i];
+      if (misc_cls(m) != CLS_NONE) atomic_add((unsigned long long*)&hist[misc_as(m) + 32768], 1ull);
+    });
+#endif
+  }
+
+  // keep tuples with a printed allele and AS >= cutoff (phaser.py:1304); cutoff = INT32_MIN disables it
+  int64_t commit_bam(int bam, int32_t as_cutoff, const u32* frag) {
+    if (bam != n_bams) throw PhzError("commit_bam: BAMs must be committed in order");
+    if (bam >= 64) throw PhzError("at most 64 BAMs");
+    int64_t n = n_cand;
+    u32* kf = keep_flag.ensure(n + 1); u32* ko = keep_off.ensure(n + 2);
+    const u32* tr = t_rec.p; const u32* tv = t_var.p; const u32* tm = t_misc.p;
+    be.for_each(n, PHZ_LAMBDA(int64_t i) {
+      u32 m = tm[i];
+      kf[i] = (misc_cls(m) != CLS_NONE && misc_as(m) >= as_cutoff) ? 1u : 0u;
+    });
+    be.exclusive_scan_u32(kf, ko, n);
+    int64_t nk = n > 0 ? (int64_t)fetch_u32(ko + n) : 0;
+    if (n_tuples + nk >= (int64_t)0xFFFFFFF0ull) throw PhzError("more than 2^32 tuples");
+    u32* gf = g_frag.grow(n_tuples + nk, n_tuples); u32* gv = g_var.grow(n_tuples + nk, n_tuples);
+    u8* gc = g_cb.grow(n_tuples + nk, n_tuples);
+    int64_t base = n_tuples;
+    be.for_each(n, PHZ_LAMBDA(int64_t i) {
+      if (!kf[i]) return;
+      int64_t o = base + ko[i];
+      gf[o] = frag[tr[i]]; gv[o] = tv[i]; gc[o] = (u8)(misc_cls(tm[i]) | (bam << 2));
+    });
+    n_tuples += nk; n_bams = bam + 1; n_cand = 0;
+    return nk;
+  }
+
+  // =================================================================== graph
+  // n_frag: number of fragment ids (max id + 1).  excl_mask: bit b set = BAM b excluded from haplotypic counts.
+  void build_graph(u64 n_frag, u64 excl_mask, u64* noise_out /*host [2]: match, mismatch*/) {
+    const int64_t n = n_tuples; const int64_t Vn = V; const int nb = n_bams > 0 ? n_bams : 1;
+    const u32* gf = g_frag.p; const u32* gv = g_var.p; const u8* gc = g_cb.p; const u32* vc = vcontig.p;
+    // ---- per-variant lists: first-seen rank (phaser.py:1310), list lengths with duplicates (Q17)
+    u32* vf = vfirst.ensure(Vn); be.memset_ff(vf, Vn * sizeof(u32));
+    u32* nl = ncls.ensure(Vn * 3); be.memset0(nl, Vn * 3 * sizeof(u32));
+    be.for_each(n, PHZ_LAMBDA(int64_t t) {
+      u32 v = gv[t];
+      atomic_min(&vf[v], (u32)t);
+      atomic_add(&nl[(int64_t)v * 3 + (gc[t] & 3)], 1u);
+    });
+    u32* cf = cfirst.ensure(nc + 1); be.memset_ff(cf, (nc + 1) * sizeof(u32));
+    u64* nz = noise.ensure(2); be.memset0(nz, 2 * sizeof(u64));
+    be.for_each(Vn, PHZ_LAMBDA(int64_t v) {
+      if (vf[v] == NONE32) return;
+      atomic_min(&cf[vc[v]], vf[v]);
+      // noise estimate, phaser.py:614-624
+      u32 mis = nl[v * 3 + 2], mat = nl[v * 3] + nl[v * 3 + 1];
+      if (mat > 0 && ((double)mis / (double)(mis + mat)) < 0.05) {
+        atomic_add((unsigned long long*)&nz[0], (unsigned long long)mat);
+        atomic_add((unsigned long long*)&nz[1], (unsigned long long)mis);
+      }
+    });
+    be.d2h(noise_out, nz, 2 * sizeof(u64));
+    {   // contig order of first appearance (read_vars key order, phaser.py:573-574)
+      u32* cr = crank.ensure(nc + 1); int ncg = nc;
+      be.for_each(nc, PHZ_LAMBDA(int64_t c) {
+        u32 r = 0;
+        for (int o = 0; o < ncg; ++o) if (cf[o] < cf[c] || (cf[o] == cf[c] && o < c)) r++;
+        cr[c] = r;
+      });
+    }
+    // ---- (fragment, variant, bam) entries: sort tuples by (fragment, variant); t ascending inside
+    const int fb = ceil_log2_host(n_frag > 1 ? n_frag : 2); const int vb = vbits;
+    if (fb + vb > 64) throw PhzError("fragment/variant id space too large");
+    u64* k1 = s_key.ensure(n); u64* k2 = s_key2.ensure(n); u32* x1 = s_val.ensure(n); u32* x2 = s_val2.ensure(n);
+    be.for_each(n, PHZ_LAMBDA(int64_t t) { k1[t] = ((u64)gf[t] << vb) | (u64)gv[t]; x1[t] = (u32)t; });
+    be.sort_pairs(k1, k2, x1, x2, n, 0, fb + vb);
+    u32* sf = s_flag.ensure(n + 1); u32* ss = s_scan.ensure(n + 2);
+    be.for_each(n, PHZ_LAMBDA(int64_t i) {
+      sf[i] = (i == 0 || k2[i] != k2[i - 1] || (gc[x2[i]] >> 2) != (gc[x2[i - 1]] >> 2)) ? 1u : 0u;
+    });
+    be.exclusive_scan_u32(sf, ss, n);
+    NE = n > 0 ? (int64_t)fetch_u32(ss + n) : 0;
+    u64* ek = e_key.ensure(NE); u8* eb = e_bam.ensure(NE); u32* em = e_mask.ensure(NE); u32* et = e_tmin.ensure(NE);
+    be.memset0(em, NE * sizeof(u32)); be.memset_ff(et, NE * sizeof(u32));
+    be.for_each(n, PHZ_LAMBDA(int64_t i) {
+      u32 e = ss[i] + sf[i] - 1; u32 t = x2[i]; u32 cls = gc[t] & 3;
+      if (sf[i]) { ek[e] = k2[i]; eb[e] = gc[t] >> 2; }
+      atomic_or(&em[e], 1u << cls);
+      if (cls < 2) atomic_min(&et[e], t);
+    });
+    // ---- groups = (fragment, contig) runs of entries
+    u32* ef = e_flag.ensure(NE + 1); u32* es = e_scan.ensure(NE + 2);
+    const u64 vmask = (((u64)1) << vb) - 1;
+    be.for_each(NE, PHZ_LAMBDA(int64_t j) {
+      bool head = (j == 0) || ((ek[j] >> vb) != (ek[j - 1] >> vb)) || (vc[ek[j] & vmask] != vc[ek[j - 1] & vmask]);
+      ef[j] = head ? 1u : 0u;
+    });
+    be.exclusive_scan_u32(ef, es, NE);
+    NG = NE > 0 ? (int64_t)fetch_u32(es + NE) : 0;
+    u32* go = grp_off.ensure(NG + 1);
+    { int64_t ne = NE, ng = NG;
+      be.for_each(NE + 1, PHZ_LAMBDA(int64_t j) { if (j == ne) go[ng] = (u32)ne; else if (ef[j]) go[es[j]] = (u32)j; }); }
+    // ---- per group: sets, per-BAM allele counts, overlap rank, pair count
+    u32* sz = setsize.ensure(Vn * 3); be.memset0(sz, Vn * 3 * sizeof(u32));
+    u32* vbc = vb_cnt.ensure(Vn * nb * 2); be.memset0(vbc, Vn * nb * 2 * sizeof(u32));
+    u64* vr = vrank.ensure(Vn); be.memset_ff(vr, Vn * sizeof(u64));
+    u32* pc = pair_cnt.ensure(NG + 1); u32* po = pair_off.ensure(NG + 2);
+    be.for_each(NG, PHZ_LAMBDA(int64_t g) {
+      u32 j0 = go[g], j1 = go[g + 1];
+      int effbam = -1; u32 first_t = NONE32;
+      for (u32 j = j0; j < j1; ++j) if (em[j] & 3) { if ((int)eb[j] > effbam) effbam = eb[j]; if (et[j] < first_t) first_t = et[j]; }
+      u32 k = 0, kelig = 0;
+      for (u32 j = j0; j < j1;) {
+        u32 v = (u32)(ek[j] & vmask); u32 mask = 0; bool elig = false; u32 jj = j;
+        for (; jj < j1 && (u32)(ek[jj] & vmask) == v; ++jj) {
+          mask |= em[jj];
+          if ((em[jj] & 3) && (int)eb[jj] == effbam) elig = true;
+          if (!((excl_mask >> eb[jj]) & 1)) {          // haplo_reads, phaser.py:1320-1322 (Q25)
+            if (em[jj] & 1) atomic_add(&vbc[((int64_t)v * nb + eb[jj]) * 2], 1u);
+            if (em[jj] & 2) atomic_add(&vbc[((int64_t)v * nb + eb[jj]) * 2 + 1], 1u);
+          }
+        }
+        for (int x = 0; x < 3; ++x) if (mask & (1u << x)) atomic_add(&sz[(int64_t)v * 3 + x], 1u);
+        k++; if (elig) kelig++;
+        j = jj;
+      }
+      pc[g] = k * (k - 1) / 2;
+      if (kelig >= 2) {     // insertion order of dict_variant_overlap, phaser.py:1271-1283
+        for (u32 j = j0; j < j1; ++j)
+          if ((em[j] & 3) && (int)eb[j] == effbam)
+            atomic_min((unsigned long long*)&vr[ek[j] & vmask], ((unsigned long long)first_t << 32) | et[j]);
+      }
+    });
+    be.exclusive_scan_u32(pc, po, NG);
+    NP = NG > 0 ? (int64_t)fetch_u32(po + NG) : 0;
+    // ---- pairs: key (va, vb), value = 9 co-occurrence cells + eligibility
+    u64* pk = p_key.ensure(NP); u64* pk2 = p_key2.ensure(NP); u32* pv = p_val.ensure(NP); u32* pv2 = p_val2.ensure(NP);
+    be.for_each(NG, PHZ_LAMBDA(int64_t g) {
+      if (pc[g] == 0) return;
+      u32 j0 = go[g], j1 = go[g + 1];
+      int effbam = -1;
+      for (u32 j = j0; j < j1; ++j) if ((em[j] & 3) && (int)eb[j] > effbam) effbam = eb[j];
+      u64 o = po[g];
+      for (u32 a = j0; a < j1;) {
+        u32 va = (u32)(ek[a] & vmask); u32 ma = 0; bool ea = false; u32 a1 = a;
+        for (; a1 < j1 && (u32)(ek[a1] & vmask) == va; ++a1) { ma |= em[a1]; if ((em[a1] & 3) && (int)eb[a1] == effbam) ea = true; }
+        for (u32 b = a1; b < j1;) {
+          u32 vbb = (u32)(ek[b] & vmask); u32 mb = 0; bool ebb = false; u32 b1 = b;
+          for (; b1 < j1 && (u32)(ek[b1] & vmask) == vbb; ++b1) { mb |= em[b1]; if ((em[b1] & 3) && (int)eb[b1] == effbam) ebb = true; }
+          u32 cells = 0;
+          for (int x = 0; x < 3; ++x) for (int y = 0; y < 3; ++y) if (((ma >> x) & 1) && ((mb >> y) & 1)) cells |= 1u << (x * 3 + y);
+          if (ea && ebb) cells |= 1u << 9;
+          pk[o] = ((u64)va << vb) | vbb; pv[o] = cells; o++;
+          b = b1;
+        }
+        a = a1;
+      }
+    });
+    be.sort_pairs(pk, pk2, pv, pv2, NP, 0, 2 * vb);
+    u32* pf = p_flag.ensure(NP + 1); u32* ps = p_scan.ensure(NP + 2);
+    be.for_each(NP, PHZ_LAMBDA(int64_t i) { pf[i] = (i == 0 || pk2[i] != pk2[i - 1]) ? 1u : 0u; });
+    be.exclusive_scan_u32(pf, ps, NP);
+    NX = NP > 0 ? (int64_t)fetch_u32(ps + NP) : 0;
+    u32* pst = pe_start.ensure(NX + 1);
+    { int64_t np = NP, nx = NX;
+      be.for_each(NP + 1, PHZ_LAMBDA(int64_t i) { if (i == np) pst[nx] = (u32)np; else if (pf[i]) pst[ps[i]] = (u32)i; }); }
+    // ---- eligible pairs -> edge table (phaser.py:667-678, 1594-1642)
+    u32* xf = x_flag.ensure(NX + 1); u32* xs = x_scan.ensure(NX + 2);
+    be.for_each(NX, PHZ_LAMBDA(int64_t x) {
+      u32 f = 0;
+      for (u32 i = pst[x]; i < pst[x + 1]; ++i) if (pv2[i] & (1u << 9)) { f = 1; break; }
+      xf[x] = f;
+    });
+    be.exclusive_scan_u32(xf, xs, NX);
+    E = NX > 0 ? (int64_t)fetch_u32(xs + NX) : 0;
+    u32* ea_ = ed_a.ensure(E); u32* eb_ = ed_b.ensure(E); u32* esup = ed_sup.ensure(E); u32* etot = ed_tot.ensure(E);
+    u32* en9 = ed_n9.ensure(E * 9); u8* ecfg = ed_cfg.ensure(E); ed_keep.ensure(E);
+    u32* sc = scalars.ensure(8); be.memset0(sc, 8 * sizeof(u32));
+    be.for_each(NX, PHZ_LAMBDA(int64_t x) {
+      if (!xf[x]) return;
+      u32 e = xs[x];
+      u32 n9[9]; for (int c = 0; c < 9; ++c) n9[c] = 0;
+      for (u32 i = pst[x]; i < pst[x + 1]; ++i) { u32 cells = pv2[i]; for (int c = 0; c < 9; ++c) n9[c] += (cells >> c) & 1u; }
+      u64 key = pk2[pst[x]];
+      ea_[e] = (u32)(key >> vb); eb_[e] = (u32)(key & vmask);
+      for (int c = 0; c < 9; ++c) en9[(int64_t)e * 9 + c] = n9[c];
+      u32 cis = n9[0] + n9[4], trans = n9[3] + n9[1];          // n[x][y] at x*3+y
+      u32 other = n9[6] + n9[7] + n9[2] + n9[5] + n9[8];
+      u32 sup = cis > trans ? cis : trans, tot = cis + trans + other;
+      esup[e] = sup; etot[e] = tot;
+      ecfg[e] = (u8)(cis > trans ? EDGE_CIS : (cis < trans ? EDGE_TRANS : EDGE_TIE));
+      if (tot > load_volatile(&sc[0])) atomic_max(&sc[0], tot);
+    });
+    max_tot = E > 0 ? fetch_u32(sc) : 0;
+  }
+
+  // =================================================================== drop, blocks, phasing, counts
+  // kstar[n] (host, n in [0, max_tot]): smallest k with binom.cdf(k, n, p) >= cc_threshold; an edge is
+  // dropped iff c_supporting == 0 or (c_total > c_supporting and c_supporting < kstar[c_total])
+  // (phaser.py:1645-1652, 696).
+  void phase(const u32* kstar_host, int64_t kstar_len, int max_block_size, u64 excl_mask, int* err_out) {
+    if ((int64_t)max_tot >= kstar_len && E > 0) throw PhzError("critical-value table shorter than max c_total");
+    const int64_t Vn = V; const int nb = n_bams > 0 ? n_bams : 1; const int vb = vbits;
+    const u32* vc = vcontig.p;
+    u32* ks = kstar_d.ensure(kstar_len);
+    be.h2d(ks, kstar_host, kstar_len * sizeof(u32));
+    const u32* ea_ = ed_a.p; const u32* eb_ = ed_b.p; const u32* esup = ed_sup.p; const u32* etot = ed_tot.p;
+    const u8* ecfg = ed_cfg.p; u8* keep = ed_keep.p;
+    u32* par = parent.ensure(Vn); u32* dg = deg.ensure(Vn + 1); be.memset0(dg, (Vn + 1) * sizeof(u32));
+    u32* sc = scalars.p; be.memset0(sc, 8 * sizeof(u32));
+    be.for_each(Vn, PHZ_LAMBDA(int64_t v) { par[v] = (u32)v; });
+    be.for_each(E, PHZ_LAMBDA(int64_t e) {
+      u32 sup = esup[e], tot = etot[e];
+      bool drop = (sup == 0) || (tot > sup && sup < ks[tot]);
+      keep[e] = drop ? 0 : 1;
+      if (drop) { atomic_add(&sc[2], 1u); return; }
+      u32 a = ea_[e], b = eb_[e];
+      atomic_add(&dg[a], 1u); atomic_add(&dg[b], 1u);
+      // lock-free union: hook the larger root under the smaller one
+      while (true) {
+        while (true) { u32 p = load_volatile(&par[a]); if (p == a) break; a = p; }
+        while (true) { u32 p = load_volatile(&par[b]); if (p == b) break; b = p; }
+        if (a == b) break;
+        if (a > b) { u32 t = a; a = b; b = t; }
+        if (atomic_cas(&par[b], b, a) == b) break;
+      }
+    });
+    n_dropped = E > 0 ? fetch_u32(sc + 2) : 0;
+    // ---- members of the kept-edge graph, grouped by component root, ascending variant index inside
+    u32* rt = root.ensure(Vn); u32* mf = m_flag.ensure(Vn + 1); u32* ms = m_scan.ensure(Vn + 2);
+    be.for_each(Vn, PHZ_LAMBDA(int64_t v) {
+      if (dg[v] == 0) { mf[v] = 0; rt[v] = NONE32; return; }
+      u32 a = (u32)v; while (true) { u32 p = par[a]; if (p == a) break; a = p; }
+      rt[v] = a; mf[v] = 1;
+    });
+    be.exclusive_scan_u32(mf, ms, Vn);
+    NM = Vn > 0 ? (int64_t)fetch_u32(ms + Vn) : 0;
+    u32* ml = m_list.ensure(NM); u32* mk = m_key.ensure(NM); u32* mk2 = m_key2.ensure(NM); u32* mem = members.ensure(NM);
+    be.for_each(Vn, PHZ_LAMBDA(int64_t v) { if (mf[v]) { ml[ms[v]] = (u32)v; mk[ms[v]] = rt[v]; } });
+    be.sort_pairs32(mk, mk2, ml, mem, NM, 0, vb);
+    u32* bf = b_flag.ensure(NM + 1); u32* bs = b_scan.ensure(NM + 2);
+    be.for_each(NM, PHZ_LAMBDA(int64_t i) { bf[i] = (i == 0 || mk2[i] != mk2[i - 1]) ? 1u : 0u; });
+    be.exclusive_scan_u32(bf, bs, NM);
+    NB = NM > 0 ? (int64_t)fetch_u32(bs + NM) : 0;
+    u32* bo = blk_off.ensure(NB + 1); u32* bof = blk_of.ensure(Vn); u32* pib = pos_in_blk.ensure(Vn);
+    be.memset_ff(bof, Vn * sizeof(u32));
+    { int64_t nm = NM, nbk = NB;
+      be.for_each(NM + 1, PHZ_LAMBDA(int64_t i) { if (i == nm) bo[nbk] = (u32)nm; else if (bf[i]) bo[bs[i]] = (u32)i; }); }
+    u64* br = blk_rank.ensure(NB); be.memset_ff(br, NB * sizeof(u64));
+    const u64* vr = vrank.p;
+    be.for_each(NM, PHZ_LAMBDA(int64_t i) {
+      u32 b = bs[i] + bf[i] - 1; u32 v = mem[i];
+      bof[v] = b;
+      atomic_min((unsigned long long*)&br[b], (unsigned long long)vr[v]);
+    });
+    be.for_each(NM, PHZ_LAMBDA(int64_t i) { u32 v = mem[i]; pib[v] = (u32)i - bo[bof[v]]; });
+    // ---- block output order: contig first-appearance rank, then first remaining key (phaser.py:1870)
+    u64* bk = bs_key.ensure(NB); u64* bk2 = bs_key2.ensure(NB); u32* bv = bs_val.ensure(NB); u32* bv2 = bs_val2.ensure(NB);
+    u32* b32 = bs_k32.ensure(NB); u32* b32b = bs_k32b.ensure(NB); u32* bord = blk_order.ensure(NB); u32* bpos = blk_pos.ensure(NB);
+    const u32* cr = crank.p;
+    be.for_each(NB, PHZ_LAMBDA(int64_t b) { bk[b] = br[b]; bv[b] = (u32)b; });
+    be.sort_pairs(bk, bk2, bv, bv2, NB, 0, 64);
+    be.for_each(NB, PHZ_LAMBDA(int64_t i) { b32[i] = cr[vc[mem[bo[bv2[i]]]]]; });
+    be.sort_pairs32(b32, b32b, bv2, bord, NB, 0, ceil_log2_host((u64)(nc > 1 ? nc : 2)));
+    be.for_each(NB, PHZ_LAMBDA(int64_t i) { bpos[bord[i]] = (u32)i; });
+    // ---- adjacency (kept, non-tie) by source variant
+    u32* af = x_flag.ensure(E + 1 > NX + 1 ? E + 1 : NX + 1); u32* as_ = x_scan.ensure(E + 2 > NX + 2 ? E + 2 : NX + 2);
+    be.for_each(E, PHZ_LAMBDA(int64_t e) { af[e] = (keep[e] && ecfg[e] != EDGE_TIE) ? 2u : 0u; });
+    be.exclusive_scan_u32(af, as_, E);
+    int64_t ND = E > 0 ? (int64_t)fetch_u32(as_ + E) : 0;
+    u64* dk = d_key.ensure(ND); u64* dk2 = d_key2.ensure(ND); u32* dsg = d_sign.ensure(ND); u32* dsg2 = d_sign2.ensure(ND);
+    u32* ao = adj_off.ensure(Vn + 2);
+    u32* dcnt = m_flag.p;      // reuse: per-variant directed degree
+    be.memset0(dcnt, (Vn + 1) * sizeof(u32));
+    be.for_each(E, PHZ_LAMBDA(int64_t e) {
+      if (!af[e]) return;
+      u32 o = as_[e]; u32 a = ea_[e], b = eb_[e];
+      dk[o] = ((u64)a << vb) | b; dsg[o] = ecfg[e];
+      dk[o + 1] = ((u64)b << vb) | a; dsg[o + 1] = ecfg[e];
+      atomic_add(&dcnt[a], 1u); atomic_add(&dcnt[b], 1u);
+    });
+    be.sort_pairs(dk, dk2, dsg, dsg2, ND, 0, 2 * vb);
+    be.exclusive_scan_u32(dcnt, ao, Vn);
+    // ---- fast path: 2-colouring from the leftmost variant (resolve_phase, phaser.py:2172-2207)
+    u8* col = color.ensure(Vn); be.memset_ff(col, Vn);
+    u8* vh = v_hap.ensure(Vn); be.memset0(vh, Vn);
+    u32* q = bfsq.ensure(NM); u32* rs = run_start.ensure(NM); u32* rl = run_len.ensure(NM);
+    u8* bst = blk_status.ensure(NB); u32* bnf = blk_nfinal.ensure(NB + 1);
+    u32* vfl = v_fin_local.ensure(Vn); be.memset_ff(vfl, Vn * sizeof(u32));
+    const u64 vmask = (((u64)1) << vb) - 1;
+    be.for_each(NB, PHZ_LAMBDA(int64_t b) {
+      u32 o0 = bo[b], o1 = bo[b + 1]; u32 n = o1 - o0;
+      u32 seed = mem[o0];
+      col[seed] = 0; q[o0] = seed; u32 qh = 0, qt = 1; bool conflict = false;
+      while (qh < qt) {
+        u32 v = q[o0 + qh++]; u8 cv = col[v];
+        for (u32 k = ao[v]; k < ao[v + 1]; ++k) {
+          u32 w = (u32)(dk2[k] & vmask); u8 want = cv ^ (u8)dsg2[k];
+          if (col[w] == 0xFF) { col[w] = want; q[o0 + qt++] = w; }
+          else if (col[w] != want) conflict = true;
+        }
+      }
+      u32 m = qt;
+      if (!conflict && m == n) {
+        bst[b] = 0; bnf[b] = 1; rs[o0] = 0; rl[o0] = n;
+        for (u32 i = o0; i < o1; ++i) { u32 v = mem[i]; vh[v] = col[v]; vfl[v] = 0; }
+      } else if (conflict && 2 * m == n) {       // reaches n alleles on m variants: short all-zero string
+        bst[b] = 1; bnf[b] = 1; rs[o0] = 0; rl[o0] = m;
+        for (u32 i = o0; i < o0 + m; ++i) { u32 v = mem[i]; vh[v] = 0; vfl[v] = 0; }
+      } else { bst[b] = 2; bnf[b] = 0; }
+    });
+    // ---- hard path: phase_v3 proper, one logical thread per block
+    u32* hf = h_flag.ensure(NB + 1); u32* hs = h_scan.ensure(NB + 2);
+    be.for_each(NB, PHZ_LAMBDA(int64_t b) { hf[b] = bst[b] == 2 ? 1u : 0u; });
+    be.exclusive_scan_u32(hf, hs, NB);
+    NH = NB > 0 ? (int64_t)fetch_u32(hs + NB) : 0;
+    if (NH > 0) {
+      // per-block lists of kept edges (ties included: they count as connections in find_weak_points)
+      u32* ec = ebk_cnt.ensure(NB + 1); u32* eo = ebk_off.ensure(NB + 2); be.memset0(ec, (NB + 1) * sizeof(u32));
+      be.for_each(E, PHZ_LAMBDA(int64_t e) { af[e] = keep[e] ? 1u : 0u; if (keep[e]) atomic_add(&ec[bof[ea_[e]]], 1u); });
+      be.exclusive_scan_u32(ec, eo, NB);
+      be.exclusive_scan_u32(af, as_, E);
+      int64_t NK = E > 0 ? (int64_t)fetch_u32(as_ + E) : 0;
+      u32* kk = ebk_key.ensure(NK); u32* kk2 = ebk_key2.ensure(NK); u32* kv = ebk_val.ensure(NK); u32* kl = ebk_list.ensure(NK);
+      be.for_each(E, PHZ_LAMBDA(int64_t e) { if (af[e]) { kk[as_[e]] = bof[ea_[e]]; kv[as_[e]] = (u32)e; } });
+      be.sort_pairs32(kk, kk2, kv, kl, NK, 0, ceil_log2_host((u64)(NB > 1 ? NB : 2)));
+      u32* hl = h_list.ensure(NH); u32* hw = h_words.ensure(NH + 1); u32* hwo = h_woff.ensure(NH + 2);
+      be.for_each(NB, PHZ_LAMBDA(int64_t b) {
+        if (!hf[b]) return;
+        hl[hs[b]] = (u32)b; hw[hs[b]] = (u32)hard_scratch_words(bo[b + 1] - bo[b]);
+      });
+      be.exclusive_scan_u32(hw, hwo, NH);
+      u32 words = fetch_u32(hwo + NH);
+      u32* scr = h_scratch.ensure(words);
+      int mbs = max_block_size;
+      be.for_each(NH, PHZ_LAMBDA(int64_t h) {
+        u32 b = hl[h]; u32 o0 = bo[b]; int n = (int)(bo[b + 1] - o0);
+        BlockEdges bed{kl + eo[b], eo[b + 1] - eo[b], ea_, eb_, ecfg, pib};
+        // hap / fin_local are written through small local views over the member segment
+        u8* hap_loc = (u8*)(q + o0);           // n bytes inside this block's queue segment (n u32 words)
+        u32* fin_loc = scr + hwo[h] + hard_scratch_words(n) - n;   // tail of this block's scratch
+        for (int i = 0; i < n; ++i) { fin_loc[i] = NONE32; hap_loc[i] = 0; }
+        int err = 0;
+        int nr = phase_block_hard(bed, n, mbs, scr + hwo[h], rs + o0, rl + o0, hap_loc, fin_loc, &err);
+        bnf[b] = (u32)nr;
+        for (int i = 0; i < n; ++i) { u32 v = mem[o0 + i]; vfl[v] = fin_loc[i]; vh[v] = hap_loc[i]; }
+        if (err) atomic_or(&sc[1], (u32)err);
+      });
+    }
+    // ---- final blocks in output order (block_index of phaser.py:863-867)
+    u32* nfo = nf_ord.ensure(NB + 1); u32* fbb = fb_base.ensure(NB + 2);
+    be.for_each(NB, PHZ_LAMBDA(int64_t i) { nfo[i] = bnf[bord[i]]; });
+    be.exclusive_scan_u32(nfo, fbb, NB);
+    NF = NB > 0 ? (int64_t)fetch_u32(fbb + NB) : 0;
+    u32* ff = fb_first.ensure(NF); u32* fl = fb_len.ensure(NF); u32* fbk = fb_blk.ensure(NF);
+    u32* vfin = v_final.ensure(Vn); be.memset_ff(vfin, Vn * sizeof(u32));
+    be.for_each(NB, PHZ_LAMBDA(int64_t i) {
+      u32 b = bord[i]; u32 o0 = bo[b];
+      for (u32 r = 0; r < bnf[b]; ++r) { u32 f = fbb[i] + r; ff[f] = o0 + rs[o0 + r]; fl[f] = rl[o0 + r]; fbk[f] = b; }
+    });
+    be.for_each(NM, PHZ_LAMBDA(int64_t i) {
+      u32 v = mem[i]; if (vfl[v] != NONE32) vfin[v] = fbb[bpos[bof[v]]] + vfl[v];
+    });
+    // ---- edge support per final block (phaser.py:876-895)
+    u32* fsup = fb_sup.ensure(NF); u32* ftot = fb_tot.ensure(NF);
+    be.memset0(fsup, NF * sizeof(u32)); be.memset0(ftot, NF * sizeof(u32));
+    be.for_each(E, PHZ_LAMBDA(int64_t e) {
+      if (!keep[e] || ecfg[e] == EDGE_TIE) return;
+      u32 a = ea_[e], b = eb_[e]; u32 fa = vfin[a];
+      if (fa == NONE32 || fa != vfin[b]) return;
+      atomic_add(&ftot[fa], 1u);
+      if ((vh[a] ^ vh[b]) == ecfg[e]) atomic_add(&fsup[fa], 1u);
+    });
+    // ---- unique-fragment counts per final block x haplotype (all BAMs, and per counted BAM)
+    u32* fc = fb_cnt.ensure(NF * 2); u32* fbc = fb_bcnt.ensure(NF * nb * 2);
+    be.memset0(fc, NF * 2 * sizeof(u32)); be.memset0(fbc, NF * nb * 2 * sizeof(u32));
+    const u64* ek = e_key.p; const u8* eb = e_bam.p; const u32* em = e_mask.p; const u32* go = grp_off.p;
+    be.for_each(NG, PHZ_LAMBDA(int64_t g) {
+      u32 j0 = go[g], j1 = go[g + 1];
+      for (u32 j = j0; j < j1; ++j) {
+        u32 v = (u32)(ek[j] & vmask); u32 f = vfin[v];
+        if (f == NONE32) continue;
+        for (int h = 0; h < 2; ++h) {
+          if (!((em[j] >> (vh[v] ^ h)) & 1)) continue;
+          bool seen_any = false, seen_bam = false;
+          for (u32 i = j0; i < j; ++i) {
+            u32 w = (u32)(ek[i] & vmask);
+            if (vfin[w] != f || !((em[i] >> (vh[w] ^ h)) & 1)) continue;
+            seen_any = true; if (eb[i] == eb[j]) seen_bam = true;
+          }
+          if (!seen_any) atomic_add(&fc[(int64_t)f * 2 + h], 1u);
+          if (!seen_bam && !((excl_mask >> eb[j]) & 1)) atomic_add(&fbc[((int64_t)f * nb + eb[j]) * 2 + h], 1u);
+        }
+      }
+    });
+    u32 errf = fetch_u32(sc + 1);
+    *err_out = (int)errf;
+  }
+
+  // =================================================================== per-variant read lists of the rows
+  // Tuples (reference/alternative calls of counted BAMs) of variants inside final blocks, ordered by
+  // (final block, BAM, haplotype, variant, tuple order): the lists behind aReads/bReads (phaser.py:1105-1115).
+  int64_t read_lists(u64 excl_mask) {
+    const int64_t n = n_tuples; const int nb = n_bams > 0 ? n_bams : 1; const int vb = vbits;
+    const u32* gf = g_frag.p; const u32* gv = g_var.p; const u8* gc = g_cb.p; const u32* vfin = v_final.p; const u8* vh = v_hap.p;
+    u32* rf = rl_flag.ensure(n + 1); u32* rsn = rl_scan.ensure(n + 2);
+    be.for_each(n, PHZ_LAMBDA(int64_t t) {
+      u32 cls = gc[t] & 3; u32 bam = gc[t] >> 2;
+      rf[t] = (cls < 2 && vfin[gv[t]] != NONE32 && !((excl_mask >> bam) & 1)) ? 1u : 0u;
+    });
+    be.exclusive_scan_u32(rf, rsn, n);
+    NRL = n > 0 ? (int64_t)fetch_u32(rsn + n) : 0;
+    u32* k32 = rl_k32.ensure(NRL); u32* k32b = rl_k32b.ensure(NRL); u32* tt = rl_t.ensure(NRL); u32* tt2 = rl_t2.ensure(NRL);
+    u64* k64 = rl_k64.ensure(NRL); u64* k64b = rl_k64b.ensure(NRL);
+    be.for_each(n, PHZ_LAMBDA(int64_t t) { if (rf[t]) { k32[rsn[t]] = gv[t]; tt[rsn[t]] = (u32)t; } });
+    be.sort_pairs32(k32, k32b, tt, tt2, NRL, 0, vb);          // by variant, tuple order kept
+    int bb = ceil_log2_host((u64)(nb > 1 ? nb : 2));
+    int fbits = ceil_log2_host((u64)(NF > 1 ? NF : 2));
+    if (fbits + bb + 1 > 32) throw PhzError("row key of read_lists does not fit 32 bits");
+    be.for_each(NRL, PHZ_LAMBDA(int64_t i) {
+      u32 t = tt2[i]; u32 v = gv[t]; u32 hap = (gc[t] & 3) ^ vh[v];
+      k64[i] = ((((u64)vfin[v] << bb) | (gc[t] >> 2)) << 1) | hap;
+    });
+    be.sort_pairs(k64, k64b, tt2, tt, NRL, 0, fbits + bb + 1);
+    u32* of = rl_frag.ensure(NRL); u32* ov = rl_var.ensure(NRL); u32* orow = rl_row.ensure(NRL);
+    be.for_each(NRL, PHZ_LAMBDA(int64_t i) { u32 t = tt[i]; of[i] = gf[t]; ov[i] = gv[t]; orow[i] = (u32)k64b[i]; });
+    return NRL;
+  }
+};
+
+}  // namespace phz

@@ -1,0 +1,230 @@
+"""ctypes binding of the C ABI (include/phz.h) + device-memory plumbing through torch.
+
+The product library is phaser_b200/_phz.so (built by __graft_entry__.build() with nvcc for sm_100a).
+There is NO CPU path: without that library, or without a CUDA device, Engine() raises.  The `lib`
+argument exists for the build container's logic tests, which pass the host-simulation double built
+from the same pipeline source (tests/hostsim); product code never passes it.
+"""
+import ctypes
+import os
+from ctypes import c_int, c_int32, c_int64, c_uint32, c_uint64, c_double, c_void_p, c_char_p, POINTER, byref
+
+import numpy as np
+import torch
+
+from .layout import ReadBatch, VariantTable
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_phz.so")
+AS_BINS = 65536
+AS_NONE = -(2 ** 31)
+
+
+class PhzError(RuntimeError):
+    pass
+
+
+class phz_reads(ctypes.Structure):
+    _fields_ = [("n_records", c_int64), ("n_cigar_ops", c_int64), ("n_bases", c_int64),
+                ("h_contig_rec_off", c_void_p), ("pos", c_void_p), ("tlen", c_void_p), ("aln_score", c_void_p),
+                ("frag", c_void_p), ("cigar_off", c_void_p), ("cigar", c_void_p), ("seq_off", c_void_p),
+                ("seq", c_void_p), ("qual", c_void_p)]
+
+
+EXPORTS = ["phz_last_error", "phz_backend_name", "phz_create", "phz_destroy", "phz_sync", "phz_set_variants",
+           "phz_map_reads", "phz_map_reads_host", "phz_as_histogram", "phz_commit_bam", "phz_build_graph",
+           "phz_phase", "phz_read_lists", "phz_array", "phz_download", "phz_counters", "phz_launch_counts",
+           "phz_set_profiling", "phz_map_times"]
+
+
+def _declare(lib):
+    lib.phz_last_error.restype = c_char_p
+    lib.phz_backend_name.restype = c_char_p
+    lib.phz_create.restype = c_void_p
+    lib.phz_create.argtypes = [c_int, c_void_p]
+    lib.phz_destroy.argtypes = [c_void_p]
+    lib.phz_sync.argtypes = [c_void_p]
+    lib.phz_set_variants.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64]
+    lib.phz_map_reads.argtypes = [c_void_p, POINTER(phz_reads), c_int, c_double, POINTER(c_int64)]
+    lib.phz_map_reads_host.argtypes = [c_void_p, POINTER(phz_reads), c_int, c_double, POINTER(c_int64)]
+    lib.phz_as_histogram.argtypes = [c_void_p, c_void_p]
+    lib.phz_commit_bam.argtypes = [c_void_p, c_int, c_int32, c_void_p, POINTER(c_int64)]
+    lib.phz_build_graph.argtypes = [c_void_p, c_uint64, c_uint64, POINTER(c_uint64), POINTER(c_int64), POINTER(c_uint32)]
+    lib.phz_phase.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_uint64, POINTER(c_int64), POINTER(c_int)]
+    lib.phz_read_lists.argtypes = [c_void_p, c_uint64, POINTER(c_int64)]
+    lib.phz_array.argtypes = [c_void_p, c_char_p, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int)]
+    lib.phz_download.argtypes = [c_void_p, c_char_p, c_void_p, c_int64]
+    lib.phz_counters.argtypes = [c_void_p, POINTER(c_int64)]
+    lib.phz_launch_counts.argtypes = [c_void_p, POINTER(c_uint64), POINTER(c_uint64)]
+    lib.phz_set_profiling.argtypes = [c_void_p, c_int]
+    lib.phz_map_times.argtypes = [c_void_p, POINTER(ctypes.c_float)]
+    return lib
+
+
+def load_library(path=LIB_PATH):
+    if not os.path.isfile(path):
+        raise PhzError("CUDA library %s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(nvcc, sm_100a).  phaser_b200 has no CPU path." % path)
+    return _declare(ctypes.CDLL(path))
+
+
+_DT = {1: np.uint8, 2: np.int16, 4: np.uint32, 8: np.uint64}
+COUNTER_NAMES = ["n_tuples", "entries", "groups", "pairs", "distinct_pairs", "edges", "dropped", "members", "blocks",
+                 "hard_blocks", "final_blocks", "read_list_entries", "n_candidates", "n_bams"]
+
+
+def _as_torch(a: np.ndarray, device, pin=False):
+    """numpy -> torch on `device`; unsigned 32/64-bit arrays travel as same-width signed views."""
+    if a.dtype == np.uint32:
+        a = a.view(np.int32)
+    elif a.dtype == np.uint64:
+        a = a.view(np.int64)
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if pin and torch.cuda.is_available():
+        t = t.pin_memory()
+    return t.to(device, non_blocking=False) if device is not None else t
+
+
+class Engine:
+    def __init__(self, device="cuda:0", lib=None):
+        self.lib = lib if lib is not None else load_library()
+        self.backend = self.lib.phz_backend_name().decode()
+        self.device = torch.device(device)
+        if self.backend != "hostsim":
+            if self.device.type != "cuda" or not torch.cuda.is_available():
+                raise PhzError("phaser_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+            torch.cuda.set_device(self.device)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            index = self.device.index or 0
+        else:
+            if lib is None:
+                raise PhzError("the host-simulation backend is a test double and must be passed explicitly")
+            self.device = torch.device("cpu")
+            stream = 0
+            index = 0
+        self.ctx = self.lib.phz_create(index, c_void_p(stream))
+        if not self.ctx:
+            raise PhzError(self.lib.phz_last_error().decode())
+        self._keep = {}
+        self.n_contigs = 0
+        self._cur = None
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.phz_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PhzError(self.lib.phz_last_error().decode())
+
+    # ------------------------------------------------------------------ stages
+    def set_variants(self, vt: VariantTable):
+        d = self.device
+        self._keep["v"] = (_as_torch(vt.pos, d), _as_torch(vt.a0, d), _as_torch(vt.a1, d))
+        off = np.ascontiguousarray(vt.contig_var_off, np.int64)
+        self._keep["voff"] = off
+        self.n_contigs = len(vt.contigs)
+        p, a0, a1 = self._keep["v"]
+        self._check(self.lib.phz_set_variants(self.ctx, self.n_contigs, off.ctypes.data, p.data_ptr(), a0.data_ptr(),
+                                              a1.data_ptr(), vt.n_variants))
+
+    def upload_reads(self, batch: ReadBatch):
+        """ReadBatch (numpy) -> dict of device tensors (the 'inputs resident in HBM' form)."""
+        d = self.device
+        return dict(contig_rec_off=np.ascontiguousarray(batch.contig_rec_off, np.int64),
+                    pos=_as_torch(batch.pos, d), tlen=_as_torch(batch.tlen, d), aln_score=_as_torch(batch.aln_score, d),
+                    frag=_as_torch(batch.frag, d), cigar_off=_as_torch(batch.cigar_off, d), cigar=_as_torch(batch.cigar, d),
+                    seq_off=_as_torch(batch.seq_off, d), seq=_as_torch(batch.seq, d), qual=_as_torch(batch.qual, d))
+
+    @staticmethod
+    def _reads_struct(t):
+        def ptr(x):
+            return x.data_ptr() if torch.is_tensor(x) else x.ctypes.data
+        r = phz_reads()
+        r.n_records = int(t["pos"].shape[0]); r.n_cigar_ops = int(t["cigar"].shape[0]); r.n_bases = int(t["qual"].shape[0])
+        r.h_contig_rec_off = t["contig_rec_off"].ctypes.data
+        for k in ("pos", "tlen", "aln_score", "frag", "cigar_off", "cigar", "seq_off", "seq", "qual"):
+            setattr(r, k, ptr(t[k]))
+        return r
+
+    def map_reads(self, dev_reads, baseq, isize_cutoff):
+        """dev_reads: dict from upload_reads (device tensors)."""
+        self._cur = dev_reads
+        r = self._reads_struct(dev_reads)
+        n = c_int64(0)
+        self._check(self.lib.phz_map_reads(self.ctx, byref(r), int(baseq), float(isize_cutoff), byref(n)))
+        return n.value
+
+    def map_reads_host(self, host_reads, baseq, isize_cutoff):
+        """host_reads: dict of (pinned) CPU tensors / numpy arrays; H2D copies happen inside the call."""
+        self._cur = None
+        r = self._reads_struct(host_reads)
+        n = c_int64(0)
+        self._check(self.lib.phz_map_reads_host(self.ctx, byref(r), int(baseq), float(isize_cutoff), byref(n)))
+        return n.value
+
+    def as_histogram(self):
+        h = torch.zeros(AS_BINS, dtype=torch.int64, device=self.device)
+        self._check(self.lib.phz_as_histogram(self.ctx, h.data_ptr()))
+        return h
+
+    def commit_bam(self, bam_index, as_cutoff=None):
+        n = c_int64(0)
+        frag = self._cur["frag"].data_ptr() if self._cur is not None else None
+        self._check(self.lib.phz_commit_bam(self.ctx, int(bam_index), AS_NONE if as_cutoff is None else int(as_cutoff),
+                                            frag, byref(n)))
+        return n.value
+
+    def build_graph(self, n_fragments, exclude_mask=0):
+        noise = (c_uint64 * 2)(); e = c_int64(0); mt = c_uint32(0)
+        self._check(self.lib.phz_build_graph(self.ctx, int(n_fragments), int(exclude_mask), noise, byref(e), byref(mt)))
+        return int(noise[0]), int(noise[1]), e.value, mt.value
+
+    def phase(self, kstar: np.ndarray, max_block_size, exclude_mask=0):
+        k = np.ascontiguousarray(kstar, np.uint32)
+        nf = c_int64(0); fl = c_int(0)
+        self._check(self.lib.phz_phase(self.ctx, k.ctypes.data, k.shape[0], int(max_block_size), int(exclude_mask),
+                                       byref(nf), byref(fl)))
+        return nf.value, fl.value
+
+    def read_lists(self, exclude_mask=0):
+        n = c_int64(0)
+        self._check(self.lib.phz_read_lists(self.ctx, int(exclude_mask), byref(n)))
+        return n.value
+
+    # ------------------------------------------------------------------ results
+    def download(self, name, dtype=None):
+        p = c_void_p(); n = c_int64(0); eb = c_int(0)
+        self._check(self.lib.phz_array(self.ctx, name.encode(), byref(p), byref(n), byref(eb)))
+        out = np.empty(n.value, dtype or _DT[eb.value])
+        self._check(self.lib.phz_download(self.ctx, name.encode(), out.ctypes.data, out.nbytes))
+        return out
+
+    def counters(self):
+        c = (c_int64 * 16)()
+        self._check(self.lib.phz_counters(self.ctx, c))
+        return {k: int(c[i]) for i, k in enumerate(COUNTER_NAMES)}
+
+    def launch_counts(self):
+        a = c_uint64(0); b = c_uint64(0)
+        self._check(self.lib.phz_launch_counts(self.ctx, byref(a), byref(b)))
+        return a.value, b.value
+
+    def set_profiling(self, on=True):
+        self._check(self.lib.phz_set_profiling(self.ctx, 1 if on else 0))
+
+    def map_times(self):
+        """(count pass, scan + readback, emit pass) in ms for the last map_reads call; CUDA events."""
+        ms = (ctypes.c_float * 3)()
+        self._check(self.lib.phz_map_times(self.ctx, ms))
+        return float(ms[0]), float(ms[1]), float(ms[2])
+
+    def sync(self):
+        self._check(self.lib.phz_sync(self.ctx))

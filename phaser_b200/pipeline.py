@@ -1,0 +1,193 @@
+"""Host driver of the device pipeline: the stages of process_vcf between "het sites loaded" and
+"write the files" (phaser/phaser.py:463-831), with the three tiny floating-point pieces kept on the
+host so that they agree bit for bit with the reference's numpy / scipy calls:
+
+  * alignment-score cutoff   numpy.percentile semantics from an exact histogram  (phaser.py:545-553)
+  * noise level              one float64 division                                  (phaser.py:631)
+  * conflicting-config test  integer critical values from scipy's binom            (phaser.py:1649, 696)
+
+Multi-GPU: contigs are sharded over ranks (shard.py); `comm` carries the three exact reductions
+(histogram, noise sums, max c_total).  Everything else is rank-local.
+"""
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from .engine import Engine, AS_BINS
+from .layout import ReadBatch, VariantTable, AS_MISSING
+from .vcfio import PhaserFatal
+
+
+@dataclass
+class PhaseParams:
+    baseq: int = 10
+    isize: List[float] = field(default_factory=lambda: [0.0])
+    as_q_cutoff: float = 0.05
+    cc_threshold: float = 0.01
+    max_block_size: int = 15
+    haplo_count_bam_exclude: List[int] = field(default_factory=list)   # 0-based
+    want_read_lists: bool = True
+
+    def exclude_mask(self):
+        m = 0
+        for b in self.haplo_count_bam_exclude:
+            m |= 1 << b
+        return m
+
+
+class NullComm:
+    """Single-GPU stand-in for the cross-rank reductions."""
+    world_size = 1
+    rank = 0
+
+    def allreduce_sum(self, t):
+        return t
+
+    def allreduce_max_int(self, x):
+        return x
+
+    def allreduce_sum_ints(self, xs):
+        return list(xs)
+
+
+def percentile_from_histogram(hist: np.ndarray, q_fraction: float):
+    """numpy.percentile(values, q_fraction*100) (default 'linear' method) where `values` are the
+    integers whose exact histogram is `hist` (bin = value + 32768).  phaser.py:551."""
+    n = int(hist.sum())
+    if n == 0:
+        return None
+    q = np.true_divide(np.float64(q_fraction * 100), 100)
+    virtual = (n - 1) * q
+    prev = int(np.floor(virtual))
+    gamma = np.float64(virtual - prev)
+    nxt = min(prev + 1, n - 1)
+    prev = max(min(prev, n - 1), 0)
+    cum = np.cumsum(hist)
+    a = np.float64(int(np.searchsorted(cum, prev + 1, side="left")) - 32768)
+    b = np.float64(int(np.searchsorted(cum, nxt + 1, side="left")) - 32768)
+    diff = b - a
+    out = a + diff * gamma
+    if gamma >= 0.5:
+        out = b - diff * (1 - gamma)
+    return float(out)
+
+
+def noise_level(match: int, mismatch: int) -> float:
+    """phaser.py:631"""
+    return float(mismatch) / (float(match + mismatch) * 2)
+
+
+def critical_values(max_total: int, noise_e: float, cc_threshold: float) -> np.ndarray:
+    """kstar[n] = min{k : binom.cdf(k, n, p) >= cc_threshold}, p = 1-(6e+10e^2)  (phaser.py:1649, 696).
+    An edge with 0 < c_supporting < c_total is dropped iff c_supporting < kstar[c_total]; uses the same
+    scipy function as the reference so the comparison agrees with it exactly."""
+    from scipy.stats import binom
+    p = 1 - ((6 * noise_e) + (10 * math.pow(noise_e, 2)))
+    n = np.arange(0, max_total + 1, dtype=np.int64)
+    k = np.nan_to_num(binom.ppf(cc_threshold, n, p), nan=0.0).astype(np.int64)
+    k = np.clip(k, 0, n)
+    for _ in range(64):
+        low = binom.cdf(k, n, p) < cc_threshold            # k too small
+        k = np.where(low & (k < n), k + 1, k)
+        km = np.maximum(k - 1, 0)
+        high = (k > 0) & (binom.cdf(km, n, p) >= cc_threshold)   # k-1 already passes
+        k = np.where(high, km, k)
+        if not (low & (k < n)).any() and not high.any():
+            break
+    # cdf(n; n, p) = 1 >= threshold always, so k <= n
+    return k.astype(np.uint32)
+
+
+def edge_pvalues(sup: np.ndarray, tot: np.ndarray, noise_e: float):
+    """conflicting_config_p per edge as the reference prints it (phaser.py:1645-1652): python int 0 / 1 or
+    numpy float64 from binom.cdf."""
+    from scipy.stats import binom
+    p = 1 - ((6 * noise_e) + (10 * math.pow(noise_e, 2)))
+    out = np.empty(sup.shape[0], dtype=object)
+    test = (sup > 0) & (tot > sup)
+    out[sup == 0] = 0
+    out[(sup > 0) & ~test] = 1
+    if test.any():
+        pairs = np.stack([sup[test].astype(np.int64), tot[test].astype(np.int64)], 1)
+        uniq, inv = np.unique(pairs, axis=0, return_inverse=True)
+        vals = binom.cdf(uniq[:, 0], uniq[:, 1], p)
+        res = vals[inv.reshape(-1)]
+        idx = np.nonzero(test)[0]
+        for i, v in zip(idx.tolist(), res):
+            out[i] = v
+    return out
+
+
+@dataclass
+class PhaseResult:
+    n_bams: int
+    as_cutoff: List[Optional[float]]
+    tuples_per_bam: List[int]
+    candidates_per_bam: List[int]
+    noise_e: float
+    match: int
+    mismatch: int
+    counters: dict
+    status_flags: int
+    arrays: dict
+
+    def __getattr__(self, k):
+        a = self.__dict__.get("arrays", {})
+        if k in a:
+            return a[k]
+        raise AttributeError(k)
+
+
+RESULT_ARRAYS = ["vfirst", "ncls", "setsize", "vb_cnt", "ed_a", "ed_b", "ed_sup", "ed_tot", "ed_cfg", "ed_keep",
+                 "members", "fb_first", "fb_len", "fb_sup", "fb_tot", "fb_cnt", "fb_bcnt", "v_final", "v_hap"]
+
+
+def run_path(engine: Engine, vt: VariantTable, batches, params: PhaseParams, n_fragments: int, comm=None,
+             host_inputs=False, download=True) -> PhaseResult:
+    """`batches`: per BAM either a dict of device tensors (Engine.upload_reads) or, with host_inputs,
+    a dict of host arrays that phz_map_reads_host copies to the device itself."""
+    comm = comm or NullComm()
+    nb = len(batches)
+    isz = list(params.isize) * nb if len(params.isize) == 1 else list(params.isize)
+    excl = params.exclude_mask()
+    engine.set_variants(vt)
+    cutoffs, kept, cands = [], [], []
+    for b, reads in enumerate(batches):
+        n_cand = engine.map_reads_host(reads, params.baseq, isz[b]) if host_inputs else \
+            engine.map_reads(reads, params.baseq, isz[b])
+        cands.append(n_cand)
+        cutoff = None
+        if params.as_q_cutoff > 0:
+            hist = comm.allreduce_sum(engine.as_histogram()).cpu().numpy()
+            n_missing = int(hist[AS_MISSING + 32768]); hist[AS_MISSING + 32768] = 0
+            cutoff = percentile_from_histogram(hist, params.as_q_cutoff)     # None: no AS values at all
+            if cutoff is not None and n_missing > 0:
+                raise PhaserFatal("%d mapped reads carry no AS:i tag but an alignment-score cutoff is active "
+                                  "(the reference fails on int('') at phaser.py:1304); use --as_q_cutoff 0" % n_missing)
+        cutoffs.append(cutoff)
+        kept.append(engine.commit_bam(b, None if cutoff is None else int(math.ceil(cutoff))))
+    match, mism, n_edges, max_tot = engine.build_graph(n_fragments, excl)
+    match, mism = comm.allreduce_sum_ints([match, mism])
+    if match == 0:
+        raise PhaserFatal("No reads could be matched to variants. Please double check your settings and input files. "
+                          "Common reasons for this occurring include: 1) MAPQ or BASEQ set too conservatively 2) BAM "
+                          "and VCF have different chromosome names (IE 'chr1' vs '1').")
+    noise_e = noise_level(match, mism)
+    kstar = critical_values(int(max_tot), noise_e, params.cc_threshold)
+    nf, flags = engine.phase(kstar, params.max_block_size, excl)
+    if flags & 2:
+        raise PhaserFatal("a haplotype block cannot be split down to --max_block_size (the reference does not "
+                          "terminate on this input)")
+    if flags & 1:
+        raise PhaserFatal("a sub-block of more than 24 variants needs exhaustive phasing; lower --max_block_size")
+    arrays = {}
+    if download:
+        for name in RESULT_ARRAYS:
+            arrays[name] = engine.download(name)
+        if params.want_read_lists:
+            engine.read_lists(excl)
+            for name in ("rl_frag", "rl_var", "rl_row"):
+                arrays[name] = engine.download(name)
+    return PhaseResult(nb, cutoffs, kept, cands, noise_e, match, mism, engine.counters(), flags, arrays)

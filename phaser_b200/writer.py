@@ -1,0 +1,373 @@
+"""Text outputs from the device result arrays: the five .txt files and the annotated VCF.
+
+Formats, column orders and number formatting follow the reference's writers:
+  allelic_counts.txt       phaser/phaser.py:737-749
+  variant_connections.txt  phaser/phaser.py:683-695
+  haplotypes.txt           phaser/phaser.py:843, 865-1043, 1224-1239
+  haplotypic_counts.txt    phaser/phaser.py:836-839, 1048-1125, 1180-1221
+  allele_config.txt        phaser/phaser.py:847, 1160-1172
+  VCF                      phaser/phaser.py:1661-1845
+Fields whose order in the reference comes from CPython set iteration are written in a canonical
+order instead: singleton rows in first-seen order, variant_connections rows
+in edge-table order, aReads/bReads as first-occurrence indices.
+"""
+from collections import OrderedDict
+
+import numpy as np
+
+from .pipeline import PhaseResult, edge_pvalues
+
+NONE32 = 0xFFFFFFFF
+NAN = float("nan")
+
+
+class VariantMeta:
+    """generate_variant_dict (phaser.py:1418-1462): text-side view of one het site."""
+    __slots__ = ("id", "rsid", "ref", "alleles", "phase", "maf", "chrom", "pos")
+
+    def __init__(self, vt, v, chrom):
+        alls = vt.all_alleles[v]
+        g = list(vt.gt[v])
+        phased = "|" in g
+        if phased:
+            g.remove("|")
+        if "/" in g:
+            g.remove("/")
+        self.alleles = [alls[i] for i in range(len(alls)) if str(i) in g]
+        self.phase = [alls[int(i)] for i in g] if phased else ["-", "-"]
+        try:
+            self.maf = float(vt.maf[v])
+        except ValueError:
+            self.maf = 0
+        self.id = vt.ids[v]
+        self.rsid = vt.rsids[v] if vt.rsids[v] not in (".", "") else vt.ids[v]
+        self.ref = alls[0]
+        self.chrom = chrom
+        self.pos = int(vt.pos[v])
+
+
+class Outputs:
+    def __init__(self, res: PhaseResult, vt, bam_names, params, unphased_vars=1, gw_phase_method=0, unique_ids=0):
+        self.res = res; self.vt = vt; self.bam_names = bam_names; self.P = params
+        self.unphased_vars = unphased_vars; self.gw_phase_method = gw_phase_method; self.unique_ids = unique_ids
+        self._meta = {}
+        self.contig_of = np.zeros(vt.n_variants, np.int64)
+        for c in range(len(vt.contigs)):
+            self.contig_of[int(vt.contig_var_off[c]):int(vt.contig_var_off[c + 1])] = c
+        self.lookup = {}         # v -> (members, "a|b", block_index, max_maf)
+        self.gw_stat_of = {}
+        self.gw_phase = {}
+        self.all_variants = []
+
+    def meta(self, v) -> VariantMeta:
+        m = self._meta.get(v)
+        if m is None:
+            m = VariantMeta(self.vt, v, self.vt.contigs[self.contig_of[v]])
+            self._meta[v] = m
+        return m
+
+    # ------------------------------------------------------------------ simple tables
+    def first_seen_order(self):
+        vf = self.res.vfirst
+        seen = np.nonzero(vf != NONE32)[0]
+        return seen[np.argsort(vf[seen], kind="stable")]
+
+    def allelic_counts(self):
+        r = self.res
+        out = ["contig\tposition\tvariantID\trefAllele\taltAllele\trefCount\taltCount\ttotalCount\n"]
+        sz = r.setsize.reshape(-1, 3)
+        n = 0
+        for v in self.first_seen_order().tolist():
+            a, b = int(sz[v, 0]), int(sz[v, 1])
+            if a + b > 0:
+                m = self.meta(v)
+                out.append("\t".join([m.chrom, str(m.pos), m.id, m.alleles[0], m.alleles[1], str(a), str(b), str(a + b) + "\n"]))
+                n += 1
+        self.covered_count = n
+        return "".join(out)
+
+    def variant_connections(self):
+        r = self.res
+        out = ["variant_a\tvariant_b\tsupporting_connections\ttotal_connections\tconflicting_configuration_p\tphase_concordant\n"]
+        pv = edge_pvalues(r.ed_sup, r.ed_tot, r.noise_e)
+        for e in range(r.ed_a.shape[0]):
+            a = int(r.ed_a[e]); b = int(r.ed_b[e]); cfg = int(r.ed_cfg[e])
+            ma = self.meta(a); mb = self.meta(b)
+            pc = "."
+            if "-" not in ma.phase and "-" not in mb.phase:       # phaser.py:1609-1620
+                if cfg == 0:
+                    pc = 1 if ma.phase.index(ma.alleles[0]) == mb.phase.index(mb.alleles[0]) else 0
+                elif cfg == 1:
+                    pc = 1 if ma.phase.index(ma.alleles[1]) == mb.phase.index(mb.alleles[0]) else 0
+            out.append("\t".join(map(str, [ma.id, mb.id, int(r.ed_sup[e]), int(r.ed_tot[e]), pv[e], pc])) + "\n")
+        return "".join(out)
+
+    # ------------------------------------------------------------------ blocks
+    def _read_list_rows(self):
+        """(final block, bam, hap) -> list (one per variant, in variant order) of fragment lists"""
+        r = self.res
+        rows = {}
+        if "rl_row" not in r.arrays:
+            return rows
+        row = r.rl_row; var = r.rl_var; frag = r.rl_frag
+        n = row.shape[0]
+        if n == 0:
+            return rows
+        brk = np.nonzero((row[1:] != row[:-1]) | (var[1:] != var[:-1]))[0] + 1
+        starts = np.concatenate([[0], brk]); ends = np.concatenate([brk, [n]])
+        for s, e in zip(starts.tolist(), ends.tolist()):
+            rows.setdefault(int(row[s]), OrderedDict())[int(var[s])] = frag[s:e].tolist()
+        return rows
+
+    @staticmethod
+    def _relabel(lists):
+        ids = {}
+        out = []
+        for lst in lists:
+            cur = []
+            for f in lst:
+                i = ids.get(f)
+                if i is None:
+                    i = len(ids); ids[f] = i
+                cur.append(str(i))
+            out.append(",".join(cur))
+        return ";".join(out)
+
+    def block_tables(self):
+        """Returns (haplotypes.txt, haplotypic_counts.txt, allele_config.txt)."""
+        r = self.res; nb = r.n_bams
+        excl = set(self.P.haplo_count_bam_exclude)
+        hc = ["\t".join(["contig", "start", "stop", "variants", "variantCount", "variantsBlacklisted",
+                         "variantCountBlacklisted", "haplotypeA", "haplotypeB", "aCount", "bCount", "totalCount",
+                         "blockGWPhase", "gwStat", "max_haplo_maf", "bam", "aReads", "bReads"]) + "\n"]
+        hp = ["\t".join(['contig', 'start', 'stop', 'length', 'variants', 'variant_ids', 'variant_alleles',
+                         'reads_hap_a', 'reads_hap_b', 'reads_total', 'edges_supporting', 'edges_total',
+                         'annotated_phase', 'phase_concordant', 'gw_phase', 'gw_confidence']) + "\n"]
+        ac = ["\t".join(['variant_a', 'rsid_a', 'variant_b', 'rsid_b', 'configuration']) + "\n"]
+        rl = self._read_list_rows()
+        bb = max(1, int(np.ceil(np.log2(max(nb, 2)))))
+        fcnt = r.fb_cnt.reshape(-1, 2); fbc = r.fb_bcnt.reshape(-1, nb, 2) if r.fb_bcnt.size else r.fb_bcnt.reshape(0, nb, 2)
+        for f in range(r.fb_first.shape[0]):
+            block_index = f + 1
+            o = int(r.fb_first[f]); n = int(r.fb_len[f])
+            variants = r.members[o:o + n].tolist()
+            self.all_variants += variants
+            hap_a = [int(r.v_hap[v]) for v in variants]
+            ms = [self.meta(v) for v in variants]
+            sup = int(r.fb_sup[f]) * 2 / 2; tot = int(r.fb_tot[f]) * 2 / 2          # floats, phaser.py:894-895
+            rsids = [m.rsid for m in ms] if self.unique_ids == 0 else [m.id for m in ms]
+            positions = [m.pos for m in ms]
+            alleles = [[], []]; phases = [[], []]
+            for h in (0, 1):
+                for i, m in enumerate(ms):
+                    al = m.alleles[hap_a[i] ^ h]
+                    alleles[h].append(al)
+                    try:
+                        phases[h].append(m.phase.index(al))
+                    except ValueError:
+                        phases[h].append(NAN)
+            known = [x for x in phases[0] if x == x]
+            phase_concordant = 1 if len(set(known)) <= 1 else 0
+            ps = ["".join("-" if x != x else str(x) for x in phases[h]) for h in (0, 1)]
+            corrected = [phases[0], phases[1]]
+            stat = 0.5
+            mafs = [m.maf for m in ms]
+            if len(known) > 0:                                        # phaser.py:959-1025
+                n_nan = len(phases[0]) - len(known)
+                if len(set(known)) + n_nan == 1:                     # every float('nan') is its own set element (Q23)
+                    stat = 1
+                else:
+                    use_mean = self.gw_phase_method == 0
+                    if self.gw_phase_method == 1:
+                        support = [0, 0]
+                        for ph, maf in zip(phases[0], mafs):
+                            if ph == 0:
+                                support[0] += maf
+                            elif ph == 1:
+                                support[1] += maf
+                        if sum(support) > 0:
+                            stat = max(support) / sum(support)
+                            if support[0] > support[1]:
+                                corrected = [[0] * n, [1] * n]
+                            elif support[1] > support[0]:
+                                corrected = [[1] * n, [0] * n]
+                        else:
+                            use_mean = True
+                    if use_mean:
+                        stat = sum(known) / len(known)               # numpy.mean of small ints, phaser.py:970
+                        if stat < 0.5:
+                            corrected = [[0] * n, [1] * n]
+                        elif stat > 0.5:
+                            corrected = [[1] * n, [0] * n]
+                        stat = max([stat, 1 - stat])
+            max_maf = max(mafs)
+            self.gw_stat_of[block_index] = stat
+            for i, v in enumerate(variants):
+                self.lookup[v] = (variants, "%d|%d" % (hap_a[i], 1 - hap_a[i]), block_index, max_maf)
+                ai = ms[i].alleles.index(alleles[0][i])
+                g = [None, None]
+                g[ai] = corrected[0][i]; g[1 - ai] = corrected[1][i]
+                self.gw_phase[v] = g
+            cps = ["".join("-" if x != x else str(x) for x in corrected[h]) for h in (0, 1)]
+            ca, cb = int(fcnt[f, 0]), int(fcnt[f, 1])
+            hp.append("\t".join(map(str, [ms[0].chrom, min(positions), max(positions), max(positions) - min(positions),
+                                          n, ",".join(rsids), ",".join(alleles[0]) + "|" + ",".join(alleles[1]),
+                                          ca, cb, ca + cb, sup, tot, ps[0] + "|" + ps[1], phase_concordant,
+                                          cps[0] + "|" + cps[1], stat])) + "\n")
+            gwp = "0/1"
+            if corrected[0][0] == 0:
+                gwp = "0|1"
+            elif corrected[0][0] == 1:
+                gwp = "1|0"
+            for b in range(nb):
+                if b in excl:
+                    continue
+                a_cnt, b_cnt = int(fbc[f, b, 0]), int(fbc[f, b, 1])
+                if a_cnt + b_cnt > 0:
+                    cols = []
+                    for h in (0, 1):
+                        key = (((f << bb) | b) << 1) | h
+                        per_var = rl.get(key, {})
+                        cols.append(self._relabel([per_var.get(v, []) for v in variants]))
+                    hc.append("\t".join(map(str, [ms[0].chrom, min(positions), max(positions),
+                                                  ",".join(m.id for m in ms), n, "", 0, ",".join(alleles[0]),
+                                                  ",".join(alleles[1]), a_cnt, b_cnt, a_cnt + b_cnt, gwp, stat,
+                                                  str(max_maf), self.bam_names[b], cols[0], cols[1]])) + "\n")
+            for i, ma in enumerate(ms):
+                for j, mb in enumerate(ms):
+                    if i != j:
+                        cfg = "trans" if (ma.ref == alleles[0][i]) == (mb.ref == alleles[1][j]) else "cis"
+                        ac.append("\t".join([ma.id, ma.rsid, mb.id, mb.rsid, cfg]) + "\n")
+        # ---- singletons (phaser.py:1180-1239)
+        if self.unphased_vars == 1:
+            ncls = r.ncls.reshape(-1, 3); sz = r.setsize.reshape(-1, 3)
+            vbc = r.vb_cnt.reshape(-1, nb, 2)
+            singles = [v for v in self.first_seen_order().tolist()
+                       if int(ncls[v, 0]) + int(ncls[v, 1]) > 0 and r.v_final[v] == NONE32]
+            for v in singles:
+                m = self.meta(v)
+                for b in range(nb):
+                    if b in excl:
+                        continue
+                    ca, cb = int(vbc[v, b, 0]), int(vbc[v, b, 1])
+                    if ca + cb > 0:
+                        if "-" not in m.phase:
+                            pstr = str(m.phase.index(m.alleles[0])) + "|" + str(m.phase.index(m.alleles[1]))
+                        else:
+                            pstr = "0/1"
+                        hc.append("\t".join([m.chrom, str(m.pos), str(m.pos), m.id, "1", "", "0", m.alleles[0], m.alleles[1],
+                                             str(ca), str(cb), str(ca + cb), pstr, "1", str(m.maf), self.bam_names[b],
+                                             "", ""]) + "\n")
+            for v in singles:
+                m = self.meta(v)
+                if "-" not in m.phase:
+                    pstr = str(m.phase.index(m.alleles[0])) + "|" + str(m.phase.index(m.alleles[1]))
+                else:
+                    pstr = "-|-"
+                name = m.rsid if self.unique_ids == 0 else m.id
+                n0, n1 = int(sz[v, 0]), int(sz[v, 1])
+                hp.append("\t".join([m.chrom, str(m.pos - 1), str(m.pos), "1", "1", name, m.alleles[0] + "|" + m.alleles[1],
+                                     str(n0), str(n1), str(n0 + n1), "0", "0", pstr, "nan", pstr, "nan"]) + "\n")
+        return "".join(hp), "".join(hc), "".join(ac)
+
+    # ------------------------------------------------------------------ VCF
+    def vcf_text(self, vcf_lines, sample_column, id_separator="_", gw_phase_vcf=0, min_conf=0.90, chrom_of_interest=""):
+        """write_vcf (phaser.py:1661-1845).  Must run after block_tables().  Returns
+        (text, unphased_phased, phase_corrections)."""
+        id_to_v = {s: i for i, s in enumerate(self.vt.ids)}
+        out = []
+        fmt_text = ""
+        corrections = unphased_phased = 0
+        tags = ['PG', 'PB', 'PI', 'PW', 'PC', 'PM']
+        for line in vcf_lines:
+            cols = line.replace("\n", "").split("\t")
+            cols = cols[0:9] + ([cols[sample_column]] if len(cols) > sample_column else [])
+            line = "\t".join(cols) + "\n"
+            if "##FORMAT" in line:
+                fmt_text += line
+                out.append(line)
+            elif line.startswith("#CHROM"):
+                for t, d in (("PG", "phASER Local Genotype"), ("PB", "phASER Local Block"),
+                             ("PI", "phASER Local Block Index (unique for each block)"),
+                             ("PM", "phASER Local Block Maximum Variant MAF"), ("PW", "phASER Genome Wide Genotype"),
+                             ("PC", "phASER Genome Wide Confidence")):
+                    if "##FORMAT=<ID=%s," % t not in fmt_text:
+                        out.append('##FORMAT=<ID=%s,Number=1,Type=String,Description="%s">\n' % (t, d))
+                if gw_phase_vcf == 2 and "##FORMAT=<ID=PS," not in fmt_text:
+                    out.append('##FORMAT=<ID=PS,Number=1,Type=String,Description="Phase Set">\n')
+                out.append("\t".join(cols[0:9] + [cols[9]]) + "\n")
+            elif line[0:1] == "#":
+                out.append(line)
+            else:
+                chrom = cols[0]; pos = int(cols[1])
+                if chrom_of_interest == "" or chrom == chrom_of_interest:
+                    if "GT" in cols[8]:
+                        gt_index = cols[8].split(":").index("GT")
+                        genotype = list(cols[9].split(":")[gt_index])
+                        if "|" in genotype:
+                            genotype.remove("|")
+                        if "/" in genotype:
+                            genotype.remove("/")
+                        all_alleles = [cols[3]] + cols[4].split(",")
+                        n_fields = len(cols[8].split(":"))
+                        for i in range(9, len(cols)):
+                            sf = len(cols[i].split(":"))
+                            if sf != n_fields:
+                                cols[i] += ":" * (n_fields - sf)
+                        ff = cols[8].split(":")
+                        for t in tags:
+                            if t not in ff:
+                                ff.append(t)
+                        cols[8] = ":".join(ff)
+                        uid = chrom + id_separator + str(pos) + id_separator + id_separator.join(all_alleles)
+                        v = id_to_v.get(uid)
+                        if v is not None and v in self.lookup:
+                            members, ab, bidx, max_maf = self.lookup[v]
+                            m = self.meta(v)
+                            alleles_out = []; gw_out = ["", ""]
+                            for al in ab.split("|"):
+                                base = m.alleles[int(al)]
+                                vidx = all_alleles.index(base)
+                                g = self.gw_phase[v][int(al)]
+                                if isinstance(g, int):
+                                    gw_out[g] = str(vidx)
+                                alleles_out.append(str(vidx))
+                            names = [self.meta(x).rsid.replace(":", "_") for x in members]
+                            stat = self.gw_stat_of[bidx]
+                            if "-" not in gw_out:
+                                xf = cols[9].split(":")
+                                new_phase = "|".join(gw_out)
+                                if stat >= min_conf:
+                                    if "|" in xf[gt_index] and xf[gt_index] != new_phase:
+                                        corrections += 1
+                                    if "/" in xf[gt_index] and xf[gt_index] != "./." and xf[gt_index] != new_phase:
+                                        unphased_phased += 1
+                                    if gw_phase_vcf in (1, 2):
+                                        xf[gt_index] = new_phase
+                                        cols[9] = ":".join(xf)
+                                if gw_phase_vcf == 2 and stat < min_conf:
+                                    xf[gt_index] = "|".join(alleles_out)
+                                    cols[9] = ":".join(xf)
+                            sf = cols[9].split(":")
+                            sf += [''] * (len(ff) - len(sf))
+                            sf[ff.index('PG')] = "|".join(alleles_out)
+                            sf[ff.index('PB')] = ",".join(names)
+                            sf[ff.index('PI')] = str(bidx)
+                            sf[ff.index('PM')] = str(max_maf)
+                            sf[ff.index('PW')] = "|".join(gw_out)
+                            sf[ff.index('PC')] = str(stat)
+                            if gw_phase_vcf == 2 and stat < min_conf:
+                                if 'PS' not in ff:
+                                    cols[8] += ":PS"; ff.append("PS"); sf.append('')
+                                sf[ff.index('PS')] = str(bidx)
+                            cols[9] = ":".join(sf)
+                        else:
+                            sf = cols[9].split(":")
+                            sf += [''] * (len(ff) - len(sf))
+                            sf[ff.index('PG')] = "/".join(sorted(genotype))
+                            sf[ff.index('PB')] = '.'; sf[ff.index('PI')] = '.'; sf[ff.index('PM')] = '.'
+                            sf[ff.index('PW')] = cols[9].split(":")[gt_index]
+                            sf[ff.index('PC')] = '.'
+                            cols[9] = ":".join(sf)
+                    out.append("\t".join(cols[0:9] + [cols[9]]) + "\n")
+        return "".join(out), unphased_phased, corrections

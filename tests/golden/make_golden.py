@@ -1,0 +1,202 @@
+"""Generate the golden fixtures by running the UNMODIFIED reference (build container only).
+
+    python tests/golden/make_golden.py
+
+Needs /root/reference (read-only) and the harness in oracle/harness.  For every case it writes the
+inputs (VCF + SAM text named *.bam, as the harness serves them) and the reference's own outputs
+under tests/golden/cases/<case>/ : ref.<file> for the six outputs (VCF decompressed) plus, for the
+mapper-level cases, the reference mapper's TSV.  The reference was run with PYTHONHASHSEED=0.
+"""
+import gzip
+import json
+import os
+import shutil
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle.harness import run_reference as rr       # noqa: E402
+from phaser_b200 import synth                        # noqa: E402
+
+CASES = os.path.join(HERE, "cases")
+
+VCF_HEAD = ("##fileformat=VCFv4.2\n##contig=<ID=1,length=100000>\n##contig=<ID=2,length=100000>\n"
+            '##INFO=<ID=AF,Number=A,Type=Float,Description="Allele frequency">\n'
+            '##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">\n'
+            '##FORMAT=<ID=DP,Number=1,Type=Integer,Description="Depth">\n'
+            "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tOTHER\tS1\n")
+SAM_HEAD = "@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:1\tLN:100000\n@SQ\tSN:2\tLN:100000\n"
+
+
+def vline(chrom, pos, vid, ref, alt, gt, filt="PASS", af="0.2", fmt="GT:DP", other="0|0:5", extra=":7"):
+    # note: the OTHER sample's 0|0 is cut away before the grep (phaser.py:220-224 cuts first)
+    return "%s\t%d\t%s\t%s\t%s\t50\t%s\tAF=%s\t%s\t%s\t%s%s\n" % (chrom, pos, vid, ref, alt, filt, af, fmt, other, gt, extra)
+
+
+def sline(q, flag, chrom, pos, mapq, cigar, seq, qual=None, AS=140, tlen=0, tags=True):
+    qual = qual if qual is not None else "F" * len(seq)
+    t = "\tNH:i:1\tAS:i:%d" % AS if tags and AS is not None else ("\tNH:i:1" if tags else "")
+    return "%s\t%d\t%s\t%d\t%d\t%s\t=\t%d\t%d\t%s\t%s%s\n" % (q, flag, chrom, pos, mapq, cigar, pos, tlen, seq, qual, t)
+
+
+def quirk_case():
+    """Hand-written records, one per mapper quirk of SURVEY.md section 8a (Q3, Q4, Q5, Q27, clips, =/X,
+    D followed by I, IUPAC D, multi-allelic sites, duplicate positions, '.' ids) + a few clean pairs so
+    that phasing has something to do."""
+    V = []
+    V.append(vline("1", 105, "rs1", "A", "G", "0|1"))
+    V.append(vline("1", 112, "rs2", "C", "T", "1|0"))
+    V.append(vline("1", 120, ".", "G", "A", "0/1"))
+    V.append(vline("1", 139, "rs4", "T", "C", "0|1"))
+    V.append(vline("1", 144, "rs5", "A", "C", "0|1"))
+    V.append(vline("1", 150, "rs6", "A", "C,G", "1|2"))          # multi-allelic, sample carries both ALTs
+    V.append(vline("1", 150, "rs6b", "A", "T", "0|1"))           # same position again
+    V.append(vline("1", 160, "rs7", "G", "T", "1|1"))            # hom: removed by the grep
+    V.append(vline("1", 161, "rs8", "G", "T", "0|1", filt="q10"))  # not PASS
+    V.append(vline("1", 162, "rs9", "GA", "G", "0|1"))           # indel: excluded
+    V.append(vline("1", 170, "rs10", "C", "A", "0|1", fmt="GT", extra=""))
+    V.append(vline("1", 171, "rs11", "C", "A", "./."))
+    V.append(vline("1", 180, "rs:12", "T", "G", "0|1"))
+    V.append(vline("1", 190, "rs13", "T", "G", "1/0"))
+    V.append(vline("2", 50, "rs20", "A", "T", "0|1"))
+    V.append(vline("2", 60, "rs21", "C", "G", "0|1"))
+    V.append(vline("2", 300, "rs22", "C", "G", "0|1"))
+    S = []
+
+    def rd(name, flag, chrom, pos, cigar, edits=None, qual_edits=None, **kw):
+        n = 0; num = ""
+        for ch in cigar:
+            if ch.isdigit():
+                num += ch
+            else:
+                if ch in "MIS=X":
+                    n += int(num)
+                num = ""
+        seq = ["A"] * n
+        q = ["F"] * n
+        for k, b in (edits or {}).items():
+            seq[k] = b
+        for k, b in (qual_edits or {}).items():
+            q[k] = b
+        S.append((chrom, pos, sline(name, flag, chrom, pos, 255, cigar, "".join(seq), "".join(q), **kw)))
+
+    # contig 1
+    rd("q3", 99, "1", 95, "2M3N40M1I10M", {41: "C", 42: "G", 46: "C"})      # Q3: insertion lands on 144 not 139
+    rd("q4", 99, "1", 100, "6M2I22M", {5: "G", 6: "C", 7: "C", 14: "T"})     # Q4: G + CC at 105 -> other
+    rd("del", 99, "1", 100, "10M4D20M", {5: "G"})                            # deletion over 112 -> nothing
+    rd("lowq", 99, "1", 100, "30M", {5: "G", 12: "T"}, {5: "#"})             # low quality at 105 -> nothing
+    rd("di", 99, "1", 100, "12M1D1I10M", {5: "A", 12: "T"})                  # D then I: key 12 = the D itself -> "T"
+    rd("clipS", 99, "1", 102, "3S20M", {6: "G", 13: "T"})                    # soft clip: query offset shifts
+    rd("clipH", 99, "1", 102, "2H20M3H", {3: "G", 10: "T"})
+    rd("eqx", 99, "1", 100, "5=1X24=", {5: "G", 12: "C", 20: "A"})
+    rd("iupacD", 99, "1", 100, "30M", {5: "D", 12: "T"})                     # IUPAC D is stripped like a deletion
+    rd("nbase", 99, "1", 100, "30M", {5: "N", 12: "T"})
+    rd("multi", 99, "1", 140, "30M", {4: "C", 10: "C"})                      # 144:C alt ; 150:C = allele 0 of 1|2, other for rs6b
+    rd("multi2", 147, "1", 140, "30M", {4: "A", 10: "G"})
+    rd("multi3", 99, "1", 140, "30M", {4: "A", 10: "T"})
+    for i in range(6):                                                        # clean cis support 105-112-120
+        rd("c%d" % i, 99, "1", 100, "30M", {5: "G", 12: "C", 20: "A"} if i % 2 else {5: "A", 12: "T", 20: "G"})
+    rd("m1", 99, "1", 100, "15M", {5: "G", 12: "C"})                          # Q27: mates disagree at 112
+    rd("m1", 147, "1", 106, "20M", {6: "T", 14: "A"})
+    rd("far", 99, "1", 165, "30M", {5: "A", 15: "G", 25: "G"}, tlen=900)      # 170 alt, 180 alt, 190 alt
+    rd("far2", 99, "1", 165, "30M", {5: "C", 15: "T", 25: "T"}, tlen=-100)
+    rd("far3", 99, "1", 165, "30M", {5: "A", 15: "T", 25: "G"})               # conflicting with far/far2 on 170-180
+    rd("far4", 99, "1", 165, "30M", {5: "A", 15: "G", 25: "G"})
+    rd("dup", 99 | 0x400, "1", 100, "30M", {5: "G"})                          # duplicate: filtered
+    rd("unpaired", 65, "1", 100, "30M", {5: "G"})                             # not proper pair: filtered
+    # contig 2: spliced pair joining 50/60 with 300
+    rd("s1", 99, "2", 45, "20M230N20M", {5: "T", 15: "G", 25: "G"})
+    rd("s2", 99, "2", 45, "20M230N20M", {5: "A", 15: "C", 25: "C"})
+    rd("s3", 99, "2", 45, "20M230N20M", {5: "T", 15: "G", 25: "G"})
+    rd("s4", 99, "2", 55, "10M230N20M", {5: "C", 15: "C"})
+    S.sort(key=lambda t: (t[0], t[1]))
+    return VCF_HEAD + "".join(V), SAM_HEAD + "".join(x[2] for x in S)
+
+
+def run_case(name, vcf_text, sams, args, mapq="255", paired_end="1"):
+    d = os.path.join(CASES, name)
+    if os.path.isdir(d):
+        shutil.rmtree(d)
+    os.makedirs(d)
+    vcf = os.path.join(d, "in.vcf.gz")
+    with gzip.open(vcf, "wt") as f:
+        f.write(vcf_text)
+    paths = []
+    for bn, text in sams:
+        p = os.path.join(d, bn)
+        with open(p, "w") as f:
+            f.write(text)
+        paths.append(p)
+    tmp = tempfile.mkdtemp()
+    r = rr.run_reference(vcf, paths, os.path.join(tmp, "ref"), "S1", mapq=mapq, paired_end=paired_end,
+                         extra_args=args, hashseed=0)
+    if r["returncode"] != 0:
+        raise RuntimeError(r["log"][-2000:])
+    for suf in rr.OUTPUT_SUFFIXES:
+        text = rr.read_text(r[suf])
+        with open(os.path.join(d, "ref." + suf.replace(".gz", "")), "w") as f:
+            f.write(text)
+    for p in paths:
+        os.remove(p + ".bai")
+    os.remove(vcf + ".tbi")
+    with open(os.path.join(d, "case.json"), "w") as f:
+        json.dump(dict(bams=[bn for bn, _ in sams], args=[str(a) for a in args], mapq=mapq, paired_end=paired_end,
+                       sample="S1"), f, indent=1)
+    # mapper-level golden: the reference mapper on each BAM with the table the product's VCF parser yields
+    from phaser_b200 import vcfio
+    col = vcfio.sample_column_map(vcf)["S1"]
+    vt, _ = vcfio.parse_vcf(vcf, col)
+    table = os.path.join(tmp, "table.tsv")
+    with open(table, "w") as f:
+        for v in range(vt.n_variants):
+            c = [c for c in range(len(vt.contigs)) if vt.contig_var_off[c] <= v < vt.contig_var_off[c + 1]][0]
+            f.write("\t".join([vt.contigs[c], str(int(vt.pos[v])), vt.ids[v], vt.rsids[v], ",".join(vt.all_alleles[v]),
+                               str(int(vt.ref_len[v])), vt.gt[v], vt.maf[v]]) + "\n")
+    for p in paths:
+        # the mapper is fed what the two samtools stages would pass: here everything on the VCF's contigs
+        out = os.path.join(d, "ref.mapper." + os.path.basename(p) + ".tsv")
+        filt = os.path.join(tmp, "filt.sam")
+        with open(p) as fin, open(filt, "w") as fo:
+            for ln in fin:
+                if ln[0] == "@":
+                    fo.write(ln); continue
+                c = ln.split("\t")
+                fl = int(c[1])
+                if (fl & 0x400) or (paired_end == "1" and not fl & 2) or int(c[4]) < int(mapq.split(",")[0]):
+                    continue
+                fo.write(ln)
+        rr.run_mapper(filt, table, out, baseq=10, isize_cutoff=0)
+    shutil.rmtree(tmp)
+    print("golden case", name, "ok")
+
+
+def synth_case(name, seed, n_variants, n_pairs, n_bams, args, **read_kw):
+    g = synth.make_genome(seed, n_variants, contigs=[("21", 120000), ("22", 80000)], n_genes=max(2, n_variants // 8))
+    tmp = tempfile.mkdtemp()
+    vcf = synth.write_vcf(g, os.path.join(tmp, "x.vcf.gz"))
+    sams = []
+    for b in range(n_bams):
+        rec = synth.make_reads(g, seed * 100 + b, n_pairs, dup_frac=0.05, **read_kw)
+        p = synth.write_sam(rec, g, os.path.join(tmp, "b%d.bam" % b), bam_name="b%d" % b)
+        sams.append(("b%d.bam" % b, open(p).read()))
+    with gzip.open(vcf, "rt") as f:
+        vt = f.read()
+    shutil.rmtree(tmp)
+    run_case(name, vt, sams, args)
+
+
+def main():
+    os.makedirs(CASES, exist_ok=True)
+    v, s = quirk_case()
+    run_case("quirks", v, [("quirks.bam", s)], ["--as_q_cutoff", "0"])
+    run_case("quirks_isize", v, [("quirks.bam", s)], ["--as_q_cutoff", "0", "--isize", "500"])
+    synth_case("rna_small", 21, 160, 900, 1, [])
+    synth_case("rna_two_bams", 22, 160, 700, 2, ["--haplo_count_bam_exclude", "2"])
+    synth_case("rna_conflict", 23, 120, 1500, 1, ["--max_block_size", "4"], switch_per_base=0.03)
+
+
+if __name__ == "__main__":
+    main()

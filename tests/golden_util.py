@@ -1,0 +1,41 @@
+"""Load the committed golden cases (tests/golden/cases, produced by tests/golden/make_golden.py)."""
+import json
+import os
+
+CASES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cases")
+FILES = {"allelic_counts": "ref.allelic_counts.txt", "allele_config": "ref.allele_config.txt",
+         "haplotypes": "ref.haplotypes.txt", "haplotypic_counts": "ref.haplotypic_counts.txt",
+         "variant_connections": "ref.variant_connections.txt", "vcf": "ref.vcf"}
+
+
+def case_names():
+    return sorted(d for d in os.listdir(CASES) if os.path.isdir(os.path.join(CASES, d)))
+
+
+def load_case(name):
+    d = os.path.join(CASES, name)
+    with open(os.path.join(d, "case.json")) as f:
+        meta = json.load(f)
+    ref = {k: open(os.path.join(d, fn)).read() for k, fn in FILES.items()}
+    sams = [os.path.join(d, b) for b in meta["bams"]]
+    mapper = {b: open(os.path.join(d, "ref.mapper.%s.tsv" % b)).read() for b in meta["bams"]}
+    return dict(dir=d, vcf=os.path.join(d, "in.vcf.gz"), sams=sams, meta=meta, ref=ref, mapper=mapper)
+
+
+def args_to_kw(args):
+    """reference CLI flags of a case -> keyword arguments understood by tests.util helpers"""
+    kw = {}
+    it = iter(args)
+    for a in it:
+        v = next(it)
+        if a == "--as_q_cutoff":
+            kw["as_q_cutoff"] = float(v)
+        elif a == "--isize":
+            kw["isize"] = [float(x) for x in v.split(",")]
+        elif a == "--max_block_size":
+            kw["max_block_size"] = int(v)
+        elif a == "--haplo_count_bam_exclude":
+            kw["exclude"] = [int(x) - 1 for x in v.split(",")]
+        else:
+            raise KeyError(a)
+    return kw

@@ -1,0 +1,86 @@
+"""Parity tests proper: the CUDA library (phaser_b200/_phz.so, sm_100a) through the C ABI against the
+reference fixtures and the oracle.  Run on the B200 box:  python -m pytest tests -m gpu"""
+import numpy as np
+import pytest
+
+from oracle import compare, port
+from tests import util, golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+
+def test_backend_is_the_cuda_library(gpu):
+    assert gpu.backend == "cuda-sm_100a"
+
+
+@pytest.mark.parametrize("name", G.case_names())
+def test_files_match_reference(gpu, name):
+    c = G.load_case(name)
+    kw = G.args_to_kw(c["meta"]["args"])
+    got, res, _ = util.product_outputs(gpu, c["vcf"], c["sams"], **kw)
+    bad = compare.diff_outputs(c["ref"], got)
+    assert not bad, "\n".join(bad)
+    own, lib = gpu.launch_counts()
+    assert own > 0
+
+
+@pytest.mark.parametrize("name", G.case_names())
+def test_mapper_tuples_match_oracle(gpu, name):
+    c = G.load_case(name)
+    vt, st, batches, col, fd = util.load_inputs(c["vcf"], c["sams"])
+    for batch in batches:
+        got, exp = util.compare_tuples(gpu, vt, batch)
+        assert got == exp
+
+
+@pytest.mark.parametrize("seed,n_bams,switch,mbs", [(31, 1, 0.002, 15), (32, 2, 0.01, 15), (33, 1, 0.03, 4),
+                                                     (34, 2, 0.05, 3), (35, 1, 0.03, 5), (36, 3, 0.01, 15)])
+def test_seeded_cases_match_oracle(gpu, tmp_path, seed, n_bams, switch, mbs):
+    vcf, sams = util.make_case(tmp_path, seed, 250, 2500, n_bams=n_bams, switch_per_base=switch)
+    got, res, _ = util.product_outputs(gpu, vcf, sams, max_block_size=mbs)
+    exp, ores = util.oracle_outputs(vcf, sams, max_block_size=mbs)
+    bad = compare.diff_outputs(exp, got)
+    assert not bad, "\n".join(bad)
+    assert res.counters["n_tuples"] == ores.total_tuples
+    assert res.noise_e == ores.noise_e
+
+
+def test_larger_case_matches_oracle(gpu, tmp_path):
+    """~40k records over 3 contigs: long enough for multi-block grids, short enough for the Python oracle."""
+    vcf, sams = util.make_case(tmp_path, 41, 2500, 20000, contigs=[("20", 900000), ("21", 700000), ("22", 500000)],
+                               switch_per_base=0.004)
+    got, res, _ = util.product_outputs(gpu, vcf, sams)
+    exp, ores = util.oracle_outputs(vcf, sams)
+    bad = compare.diff_outputs(exp, got)
+    assert not bad, "\n".join(bad)
+
+
+def test_full_path_is_deterministic_and_consistent(gpu, tmp_path):
+    """Size-independent properties on a case too big for the oracle: two runs give identical arrays;
+    list lengths add up to the tuple count; every final block has >= 2 variants on one contig, sorted;
+    per-BAM haplotype counts never exceed the all-BAM counts."""
+    from phaser_b200 import synth, pipeline
+    g = synth.make_genome(51, 40000, contigs=synth.GRCH38[18:22], n_genes=5000)
+    vt = synth.to_variant_table(g)
+    recs = [synth.filter_raw(synth.make_reads(g, 5100 + b, 300000), True, True, 0) for b in range(2)]
+    P = pipeline.PhaseParams()
+    outs = []
+    for rep in range(2):
+        batches = []
+        nfrag = 0
+        for b, rec in enumerate(recs):
+            rb = synth.to_read_batch(rec, len(vt.contigs), "b%d" % b)
+            rb.frag = (rb.frag + nfrag).astype(np.uint32); nfrag += len(rb.qnames)
+            batches.append(gpu.upload_reads(rb))
+        outs.append(pipeline.run_path(gpu, vt, batches, P, n_fragments=nfrag))
+    a, b = outs
+    for k in a.arrays:
+        assert np.array_equal(a.arrays[k], b.arrays[k]), k
+    assert int(a.ncls.sum()) == a.counters["n_tuples"]
+    assert a.counters["final_blocks"] > 100
+    contig_of = np.searchsorted(vt.contig_var_off, np.arange(vt.n_variants), side="right") - 1
+    for f in range(a.fb_first.shape[0]):
+        m = a.members[a.fb_first[f]:a.fb_first[f] + a.fb_len[f]]
+        assert m.shape[0] >= 2 and (np.diff(m.astype(np.int64)) > 0).all() and len(set(contig_of[m].tolist())) == 1
+    fc = a.fb_cnt.reshape(-1, 2); fbc = a.fb_bcnt.reshape(-1, 2, 2)
+    assert (fbc.sum(1) >= fc).all() and (fbc.max(1) <= fc).all()

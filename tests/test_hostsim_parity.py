@@ -1,0 +1,37 @@
+"""Build-container logic tests: the product's pipeline source compiled against the host-simulation
+backend (tests/hostsim) must reproduce the reference fixtures and the oracle on seeded inputs.
+The same assertions run on the real CUDA library in tests/test_gpu_parity.py."""
+import pytest
+
+from oracle import compare
+from tests import util, golden_util as G
+
+
+@pytest.mark.parametrize("name", G.case_names())
+def test_files_match_reference(hostsim, name):
+    c = G.load_case(name)
+    kw = G.args_to_kw(c["meta"]["args"])
+    got, res, _ = util.product_outputs(hostsim, c["vcf"], c["sams"], **kw)
+    bad = compare.diff_outputs(c["ref"], got)
+    assert not bad, "\n".join(bad)
+
+
+@pytest.mark.parametrize("name", G.case_names())
+def test_mapper_tuples_match_oracle(hostsim, name):
+    c = G.load_case(name)
+    vt, st, batches, col, fd = util.load_inputs(c["vcf"], c["sams"])
+    for batch in batches:
+        got, exp = util.compare_tuples(hostsim, vt, batch)
+        assert got == exp
+
+
+@pytest.mark.parametrize("seed,n_bams,switch,mbs", [(31, 1, 0.002, 15), (32, 2, 0.01, 15), (33, 1, 0.03, 4),
+                                                     (34, 2, 0.05, 3), (35, 1, 0.03, 5)])
+def test_seeded_cases_match_oracle(hostsim, tmp_path, seed, n_bams, switch, mbs):
+    vcf, sams = util.make_case(tmp_path, seed, 250, 2500, n_bams=n_bams, switch_per_base=switch)
+    got, res, _ = util.product_outputs(hostsim, vcf, sams, max_block_size=mbs)
+    exp, ores = util.oracle_outputs(vcf, sams, max_block_size=mbs)
+    bad = compare.diff_outputs(exp, got)
+    assert not bad, "\n".join(bad)
+    assert res.counters["n_tuples"] == ores.total_tuples
+    assert abs(res.noise_e - ores.noise_e) == 0.0
