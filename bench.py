@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py -- het-SNVs phased/sec of the read -> variant -> haplotype path on B200.
+
+Contract: `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line (rank 0).
+A "step" is one pass of the whole hot path (K1 map -> AS cutoff -> graph -> phasing -> counts) over
+one synthetic sample of the BASELINE.json configs[1] shape: whole-genome RNA-seq, ~50 M read pairs
+(100 M records, 2x76 bp, spliced) over ~2 M het SNVs.  `value` times it with the packed inputs
+already resident in HBM; `e2e` times the same step through the host-buffer C-ABI entry
+(phz_map_reads_host: pinned host arrays -> device inside the timed region, result arrays back).
+N > 1: one process per GPU, every rank phases its own sample (weak scaling, GTEx-batch style,
+configs[4]); no data-path collective, max-over-ranks timing.
+`--impl reference` times the reference's CPU implementation of the same path (oracle/_ref when it
+was built from /root/reference, else the oracle port) on a bounded sample, rank 0 only.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np       # noqa: E402
+import torch             # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=50_000_000, help="read pairs per sample (configs[1]: 50 M)")
+    ap.add_argument("--variants", type=int, default=2_000_000, help="het SNVs per sample (configs[1]: 2 M)")
+    ap.add_argument("--exonic_frac", type=float, default=0.10)
+    ap.add_argument("--seed", type=int, default=2000)
+    ap.add_argument("--cpu_pairs", type=int, default=40_000, help="bounded sample for the CPU baseline")
+    ap.add_argument("--no_e2e", action="store_true")
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip().split(", "))
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------- workload
+
+def make_sample(seed, n_pairs, n_variants, exonic_frac, device):
+    """Synthetic sample of the configs[1] shape, generated on `device`, returned as packed SoA tensors."""
+    from phaser_b200 import synth
+    g = synth.make_genome(seed, n_variants, exonic_frac=exonic_frac, device=device,
+                          n_genes=max(2, int(n_variants * exonic_frac) // 8))
+    vt = synth.to_variant_table_arrays(g)
+    parts = []
+    done = 0
+    chunk = 2_000_000
+    while done < n_pairs:
+        n = min(chunk, n_pairs - done)
+        rec = synth.make_reads(g, seed * 1000 + done // chunk, n, chunk_pairs=chunk)
+        rec["frag"] = rec["frag"] + done
+        parts.append(synth.compact_raw(rec))
+        done += n
+    rec = synth.concat_sorted(parts)
+    packed = synth.pack_records(rec, len(g.contigs))
+    return g, vt, packed, n_pairs
+
+
+def algorithmic_bytes_k1(packed, n_variants, n_tuples):
+    """B_K1 = R*(26 + 4*Cbar + 1.5*Lr) + 6*V + 12*T"""
+    R = int(packed["pos"].shape[0])
+    return R * 26 + 4 * int(packed["cigar"].shape[0]) + int(packed["qual"].shape[0]) * 1.5 + 6 * n_variants + 12 * n_tuples
+
+
+def run_ours(a):
+    import torch.distributed as dist
+    from phaser_b200 import engine as eng, pipeline
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    E = eng.Engine(device=dev)
+    t_gen = time.time()
+    g, vt, packed, n_pairs = make_sample(a.seed + rank, a.pairs, a.variants, a.exonic_frac, dev)
+    torch.cuda.synchronize()
+    t_gen = time.time() - t_gen
+    V = vt.n_variants
+    P = pipeline.PhaseParams(want_read_lists=True)
+    reads = dict(packed)
+    reads["contig_rec_off"] = packed["contig_rec_off"].cpu().numpy().astype(np.int64)
+    R = int(reads["pos"].shape[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(host_inputs=False, src=None):
+        return pipeline.run_path(E, vt, [src if src is not None else reads], P, n_fragments=n_pairs,
+                                 host_inputs=host_inputs, download=host_inputs)
+
+    E.set_profiling(True)
+    for _ in range(a.warmup):
+        res = step()
+    own0, lib0 = E.launch_counts()
+    k1_ms = []
+    clocks = ClockSampler(local); clocks.start()
+    barrier()
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(a.steps):
+        res = step()
+        k1_ms.append(E.map_times())
+    ev1.record()
+    barrier()
+    clk = clocks.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    own1, lib1 = E.launch_counts()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / a.steps
+    counters = res.counters
+    n_tuples = counters["n_tuples"]
+    k1 = np.asarray(k1_ms)           # [steps, 3] count / scan+readback / emit
+    k1_total_ms = float(k1.sum(1).mean())
+    bytes_k1 = algorithmic_bytes_k1(packed, V, sum(res.candidates_per_bam))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = bytes_k1 / (k1_total_ms * 1e-3) / 1e9
+    # ---- end to end: pinned host arrays -> device inside the timed region -> result arrays on the host
+    e2e = None
+    if not a.no_e2e:
+        host = {k: (v.cpu().pin_memory() if torch.is_tensor(v) else v) for k, v in reads.items()}
+        h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
+        for _ in range(2):
+            r2 = step(True, host)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            r2 = step(True, host)
+        barrier()
+        dt = (time.perf_counter() - t0) / a.steps
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        d2h = sum(int(v.nbytes) for v in r2.arrays.values())
+        e2e = {"value": V * world / float(tt.item()), "unit": "het-SNVs/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": float(tt.item()) * 1e3}
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu = cpu_baseline(a)
+    if rank == 0:
+        out = {
+            "metric": "het_snvs_phased_per_sec", "value": V * world / (ms_step * 1e-3), "unit": "het-SNVs/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (integer and byte work; fp64 only for 3 host scalars)",
+            "data": "synthetic",
+            "config": {"workload": "configs[1]: whole-genome 1 RNA-seq BAM, %d read pairs (%d records after filters, 2x76 bp "
+                                   "spliced), %d het SNVs, 1 sample per GPU" % (n_pairs, R, V),
+                       "l2": "inputs (%.1f GB per step) are larger than L2" % (bytes_k1 / 1e9),
+                       "records": R, "het_snvs": V, "tuples": n_tuples, "edges": counters["edges"],
+                       "blocks": counters["final_blocks"], "phased_in_blocks": int((res.counters["members"])),
+                       "generator_s": round(t_gen, 1)},
+            "reads_x_variants_per_sec": n_tuples * world / (ms_step * 1e-3),
+            "records_per_sec": R * world / (ms_step * 1e-3),
+            "roofline": {"bound": "hbm", "kernel": "K1 read->allele (count pass + scan + emit pass)", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                         "algorithmic_bytes": bytes_k1, "ms": k1_total_ms,
+                         "ms_count_scan_emit": [float(x) for x in k1.mean(0)], "traffic": None},
+            "e2e": e2e, "cpu_baseline": cpu,
+            "gpu_launches": int((own1 - own0) / a.steps), "library_passes": int((lib1 - lib0) / a.steps),
+            "clocks": clk,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------- CPU arms
+
+def cpu_sample(a):
+    """Bounded sample of the same workload shape, as SAM-free packed arrays for the CPU arm."""
+    from phaser_b200 import synth
+    n_pairs = a.cpu_pairs
+    n_var = max(50, int(a.variants * (n_pairs / a.pairs)))
+    contigs = [("22", 2_000_000)]
+    g = synth.make_genome(a.seed, n_var, exonic_frac=1.0, contigs=contigs, n_genes=max(2, n_var // 8))
+    vt = synth.to_variant_table(g)
+    rec = synth.make_reads(g, a.seed * 1000, n_pairs)
+    rb = synth.to_read_batch(rec, 1, "bam0")
+    return vt, rb, n_pairs, n_var
+
+
+def cpu_baseline(a):
+    from oracle import port
+    vt, rb, n_pairs, n_var = cpu_sample(a)
+    t0 = time.perf_counter()
+    res = port.run(vt, [rb], port.Params())
+    dt = time.perf_counter() - t0
+    return {"value": vt.n_variants / dt, "unit": "het-SNVs/s", "cores": 1, "kind": "port",
+            "sample": "%d read pairs x %d het SNVs (same generator, 1 contig), oracle/port.py single thread, %.1f s" % (
+                n_pairs, vt.n_variants, dt),
+            "tuples_per_sec": res.total_tuples / dt, "records_per_sec": rb.n_records / dt}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    last = None
+    for i in range(a.warmup + a.steps):
+        last = cpu_baseline(a)
+        if i >= a.warmup:
+            vals.append(last["value"])
+        if i >= 1 and a.warmup + a.steps > 2:
+            # one warm-up and one timed step are enough for a 10-30 s CPU pass; keep the run bounded
+            if i >= a.warmup:
+                break
+    v = float(np.mean(vals)) if vals else last["value"]
+    out = {"impl": "reference", "metric": "het_snvs_phased_per_sec", "value": v, "unit": "het-SNVs/s",
+           "n_gpus": a.gpus, "steps": len(vals), "warmup": a.warmup, "ms_per_step": None, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "python objects", "data": "synthetic",
+           "config": {"workload": "configs[1] shape, bounded sample: " + last["sample"]},
+           "cpu_baseline": dict(last, value=v),
+           "e2e": {"value": v, "unit": "het-SNVs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

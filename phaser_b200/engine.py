@@ -127,7 +127,9 @@ class Engine:
     # ------------------------------------------------------------------ stages
     def set_variants(self, vt: VariantTable):
         d = self.device
-        self._keep["v"] = (_as_torch(vt.pos, d), _as_torch(vt.a0, d), _as_torch(vt.a1, d))
+        if self._keep.get("vt_id") != id(vt):          # the table stays resident across calls
+            self._keep["v"] = (_as_torch(vt.pos, d), _as_torch(vt.a0, d), _as_torch(vt.a1, d))
+            self._keep["vt_id"] = id(vt); self._keep["vt"] = vt
         off = np.ascontiguousarray(vt.contig_var_off, np.int64)
         self._keep["voff"] = off
         self.n_contigs = len(vt.contigs)

@@ -183,11 +183,9 @@ def run_path(engine: Engine, vt: VariantTable, batches, params: PhaseParams, n_f
     if flags & 1:
         raise PhaserFatal("a sub-block of more than 24 variants needs exhaustive phasing; lower --max_block_size")
     arrays = {}
+    if params.want_read_lists:
+        engine.read_lists(excl)
     if download:
-        for name in RESULT_ARRAYS:
+        for name in RESULT_ARRAYS + (["rl_frag", "rl_var", "rl_row"] if params.want_read_lists else []):
             arrays[name] = engine.download(name)
-        if params.want_read_lists:
-            engine.read_lists(excl)
-            for name in ("rl_frag", "rl_var", "rl_row"):
-                arrays[name] = engine.download(name)
     return PhaseResult(nb, cutoffs, kept, cands, noise_e, match, mism, engine.counters(), flags, arrays)

@@ -286,19 +286,48 @@ def pack_records(rec, n_contigs):
     ncig = live.sum(1)
     cigar_off = torch.zeros(N + 1, dtype=torch.int64, device=device)
     cigar_off[1:] = torch.cumsum(ncig, 0)
-    cig = ((rec["opl"] << 4) | rec["ops"])[live]
+    cig = ((rec["opl"][live].to(torch.int32) << 4) | rec["ops"][live].to(torch.int32))
     seq_off = torch.arange(N + 1, dtype=torch.int64, device=device) * lr
     flat = rec["bases"].reshape(-1)
     if flat.shape[0] & 1:
         flat = torch.cat([flat, torch.zeros(1, dtype=torch.uint8, device=device)])
     seq = (flat[0::2] << 4) | flat[1::2]
-    counts = torch.bincount(rec["contig"], minlength=n_contigs)
+    counts = torch.bincount(rec["contig"].to(torch.int64), minlength=n_contigs)
     contig_rec_off = torch.zeros(n_contigs + 1, dtype=torch.int64, device=device)
     contig_rec_off[1:] = torch.cumsum(counts, 0)
     return dict(contig_rec_off=contig_rec_off, pos=rec["pos"].to(torch.int32), tlen=rec["tlen"].to(torch.int32),
                 aln_score=rec["aln"].to(torch.int16), frag=rec["frag"].to(torch.int32),
                 cigar_off=cigar_off.to(torch.int32), cigar=cig.to(torch.int32),
                 seq_off=seq_off, seq=seq.contiguous(), qual=rec["qual"].reshape(-1).contiguous())
+
+
+def compact_raw(rec):
+    """Shrink the dtypes of a make_reads chunk (bench-scale generation keeps ~200 B per record)."""
+    out = dict(rec)
+    out["contig"] = rec["contig"].to(torch.int16)
+    out["pos"] = rec["pos"].to(torch.int32); out["tlen"] = rec["tlen"].to(torch.int32)
+    out["flag"] = rec["flag"].to(torch.int16); out["mapq"] = rec["mapq"].to(torch.int16)
+    out["aln"] = rec["aln"].to(torch.int16); out["frag"] = rec["frag"].to(torch.int32)
+    out["ops"] = rec["ops"].to(torch.uint8); out["opl"] = rec["opl"].to(torch.int16)
+    return out
+
+
+def concat_sorted(parts):
+    """Concatenate chunks and restore the global coordinate order."""
+    rec = {k: (torch.cat([p[k] for p in parts]) if torch.is_tensor(parts[0][k]) else parts[0][k]) for k in parts[0]}
+    order = torch.argsort(rec["contig"].to(torch.int64) * (1 << 32) + rec["pos"].to(torch.int64), stable=True)
+    return {k: (v[order] if torch.is_tensor(v) else v) for k, v in rec.items()}
+
+
+def to_variant_table_arrays(genome) -> VariantTable:
+    """VariantTable with the numeric columns only (bench scale: no per-variant Python strings)."""
+    vc = genome.v_contig.cpu().numpy()
+    nc = len(genome.contigs)
+    off = np.zeros(nc + 1, np.int64); off[1:] = np.cumsum(np.bincount(vc, minlength=nc))
+    V = vc.shape[0]
+    return VariantTable([c[0] for c in genome.contigs], off, genome.v_pos.cpu().numpy().astype(np.int32),
+                        genome.v_ref.cpu().numpy().astype(np.uint8), genome.v_alt.cpu().numpy().astype(np.uint8),
+                        np.ones(V, np.int32))
 
 
 def to_read_batch(rec, n_contigs, bam_name="bam0") -> ReadBatch:
