@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--cpu_pairs", type=int, default=40_000, help="bounded sample for the CPU baseline")
     ap.add_argument("--no_e2e", action="store_true")
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="add per-stage CUDA-event times of one extra step")
     return ap.parse_args()
 
 
@@ -148,7 +149,7 @@ def run_ours(a):
         return pipeline.run_path(E, vt, [src if src is not None else reads], P, n_fragments=n_pairs,
                                  host_inputs=host_inputs, download=host_inputs)
 
-    E.set_profiling(True)
+    E.set_profiling(1)
     for _ in range(a.warmup):
         res = step()
     own0, lib0 = E.launch_counts()
@@ -200,6 +201,13 @@ def run_ours(a):
         d2h = sum(int(v.nbytes) for v in r2.arrays.values())
         e2e = {"value": V * world / float(tt.item()), "unit": "het-SNVs/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(tt.item()) * 1e3}
+    stages = None
+    if a.profile:
+        E.set_profiling(2)
+        t0 = time.perf_counter(); step(); torch.cuda.synchronize(); wall = (time.perf_counter() - t0) * 1e3
+        stages = {k: round(v, 3) for k, v in E.stage_report().items()}
+        stages["wall_ms"] = round(wall, 3)
+        E.set_profiling(1)
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu = cpu_baseline(a)
@@ -226,6 +234,8 @@ def run_ours(a):
             "gpu_launches": int((own1 - own0) / a.steps), "library_passes": int((lib1 - lib0) / a.steps),
             "clocks": clk,
         }
+        if stages is not None:
+            out["stages_ms"] = stages
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

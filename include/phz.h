@@ -103,8 +103,10 @@ int phz_download(phz_ctx* ctx, const char* name, void* h_dst, int64_t dst_bytes)
 int phz_counters(phz_ctx* ctx, int64_t* counters);
 /* CUDA-event timing of the K1 passes of the LAST phz_map_reads call on the context's stream:
  * ms[0] = count pass, ms[1] = scan + size readback, ms[2] = emit pass (-1 when profiling is off). */
-int phz_set_profiling(phz_ctx* ctx, int on);
+int phz_set_profiling(phz_ctx* ctx, int level);   /* 0 off, 1 K1 pass events, 2 + named stage marks */
 int phz_map_times(phz_ctx* ctx, float* ms);
+/* "stage<TAB>milliseconds" lines for the stages run since the last report (profiling on); clears them. */
+int phz_stage_report(phz_ctx* ctx, char* buf, int64_t buf_len);
 /* kernels of this library launched so far / library (CUB) passes launched so far */
 int phz_launch_counts(phz_ctx* ctx, uint64_t* own, uint64_t* library);
 

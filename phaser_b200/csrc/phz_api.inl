@@ -175,11 +175,19 @@ int phz_counters(phz_ctx* ctx, int64_t* c) {
   PHZ_CATCH
 }
 
-int phz_set_profiling(phz_ctx* ctx, int on) { PHZ_TRY ctx->p.be.profiling = on != 0; PHZ_CATCH }
+int phz_set_profiling(phz_ctx* ctx, int on) { PHZ_TRY ctx->p.be.profiling = on; PHZ_CATCH }
 
 int phz_map_times(phz_ctx* ctx, float* ms) {
   PHZ_TRY
   ms[0] = ctx->p.be.elapsed(0, 1); ms[1] = ctx->p.be.elapsed(1, 2); ms[2] = ctx->p.be.elapsed(2, 3);
+  PHZ_CATCH
+}
+
+int phz_stage_report(phz_ctx* ctx, char* buf, int64_t buf_len) {
+  PHZ_TRY
+  std::string r = ctx->p.be.stage_report();
+  if ((int64_t)r.size() + 1 > buf_len) r.resize(buf_len > 0 ? buf_len - 1 : 0);
+  std::memcpy(buf, r.c_str(), r.size() + 1);
   PHZ_CATCH
 }
 

@@ -101,7 +101,7 @@ struct DeviceBackend {
   void* cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
   // optional per-stage CUDA-event timing on this stream (phz_set_profiling)
-  bool profiling = false;
+  int profiling = 0;          // 1: K1 pass events, 2: + named stage marks
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   void mark(int i) {
     if (!profiling) return;
@@ -114,6 +114,25 @@ struct DeviceBackend {
     PHZ_CUDA(cudaEventSynchronize(ev[b]));
     PHZ_CUDA(cudaEventElapsedTime(&ms, ev[a], ev[b]));
     return ms;
+  }
+  // named stage marks: stage(name) closes the previous stage and opens `name`
+  std::vector<std::pair<std::string, cudaEvent_t>> marks;
+  void stage(const char* name) {
+    if (profiling < 2) return;
+    cudaEvent_t e; PHZ_CUDA(cudaEventCreate(&e)); PHZ_CUDA(cudaEventRecord(e, stream));
+    marks.emplace_back(name, e);
+  }
+  std::string stage_report() {
+    std::string out;
+    if (marks.empty()) return out;
+    PHZ_CUDA(cudaEventSynchronize(marks.back().second));
+    for (size_t i = 0; i + 1 < marks.size(); ++i) {
+      float ms = 0.f; cudaEventElapsedTime(&ms, marks[i].second, marks[i + 1].second);
+      out += marks[i].first + "\t" + std::to_string(ms) + "\n";
+    }
+    for (auto& m : marks) cudaEventDestroy(m.second);
+    marks.clear();
+    return out;
   }
 
   void* alloc(size_t bytes) {
@@ -201,9 +220,11 @@ struct HostSimBackend {
   int device = -1;
   u64 launches = 0;
   u64 lib_launches = 0;
-  bool profiling = false;
+  int profiling = 0;
   void mark(int) {}
   float elapsed(int, int) { return -1.f; }
+  void stage(const char*) {}
+  std::string stage_report() { return std::string(); }
 
   void* alloc(size_t bytes) { if (bytes == 0) bytes = 16; void* p = std::malloc(bytes); if (!p) throw PhzError("host alloc failed"); return p; }
   void free(void* p) { std::free(p); }

@@ -191,6 +191,7 @@ struct Pipeline {
     if (bam >= 64) throw PhzError("at most 64 BAMs");
     int64_t n = n_cand;
     u32* kf = keep_flag.ensure(n + 1); u32* ko = keep_off.ensure(n + 2);
+    be.stage("commit_bam");
     const u32* tr = t_rec.p; const u32* tv = t_var.p; const u32* tm = t_misc.p;
     be.for_each(n, PHZ_LAMBDA(int64_t i) {
       u32 m = tm[i];
@@ -208,6 +209,7 @@ struct Pipeline {
       gf[o] = frag[tr[i]]; gv[o] = tv[i]; gc[o] = (u8)(misc_cls(tm[i]) | (bam << 2));
     });
     n_tuples += nk; n_bams = bam + 1; n_cand = 0;
+    be.stage("commit_bam.end");
     return nk;
   }
 
@@ -216,6 +218,7 @@ struct Pipeline {
   void build_graph(u64 n_frag, u64 excl_mask, u64* noise_out /*host [2]: match, mismatch*/) {
     const int64_t n = n_tuples; const int64_t Vn = V; const int nb = n_bams > 0 ? n_bams : 1;
     const u32* gf = g_frag.p; const u32* gv = g_var.p; const u8* gc = g_cb.p; const u32* vc = vcontig.p;
+    be.stage("graph.variant_lists");
     // ---- per-variant lists: first-seen rank (phaser.py:1310), list lengths with duplicates (Q17)
     u32* vf = vfirst.ensure(Vn); be.memset_ff(vf, Vn * sizeof(u32));
     u32* nl = ncls.ensure(Vn * 3); be.memset0(nl, Vn * 3 * sizeof(u32));
@@ -245,12 +248,14 @@ struct Pipeline {
         cr[c] = r;
       });
     }
+    be.stage("graph.sort_tuples");
     // ---- (fragment, variant, bam) entries: sort tuples by (fragment, variant); t ascending inside
     const int fb = ceil_log2_host(n_frag > 1 ? n_frag : 2); const int vb = vbits;
     if (fb + vb > 64) throw PhzError("fragment/variant id space too large");
     u64* k1 = s_key.ensure(n); u64* k2 = s_key2.ensure(n); u32* x1 = s_val.ensure(n); u32* x2 = s_val2.ensure(n);
     be.for_each(n, PHZ_LAMBDA(int64_t t) { k1[t] = ((u64)gf[t] << vb) | (u64)gv[t]; x1[t] = (u32)t; });
     be.sort_pairs(k1, k2, x1, x2, n, 0, fb + vb);
+    be.stage("graph.entries");
     u32* sf = s_flag.ensure(n + 1); u32* ss = s_scan.ensure(n + 2);
     be.for_each(n, PHZ_LAMBDA(int64_t i) {
       sf[i] = (i == 0 || k2[i] != k2[i - 1] || (gc[x2[i]] >> 2) != (gc[x2[i - 1]] >> 2)) ? 1u : 0u;
@@ -265,6 +270,7 @@ struct Pipeline {
       atomic_or(&em[e], 1u << cls);
       if (cls < 2) atomic_min(&et[e], t);
     });
+    be.stage("graph.groups");
     // ---- groups = (fragment, contig) runs of entries
     u32* ef = e_flag.ensure(NE + 1); u32* es = e_scan.ensure(NE + 2);
     const u64 vmask = (((u64)1) << vb) - 1;
@@ -277,6 +283,7 @@ struct Pipeline {
     u32* go = grp_off.ensure(NG + 1);
     { int64_t ne = NE, ng = NG;
       be.for_each(NE + 1, PHZ_LAMBDA(int64_t j) { if (j == ne) go[ng] = (u32)ne; else if (ef[j]) go[es[j]] = (u32)j; }); }
+    be.stage("graph.group_stats");
     // ---- per group: sets, per-BAM allele counts, overlap rank, pair count
     u32* sz = setsize.ensure(Vn * 3); be.memset0(sz, Vn * 3 * sizeof(u32));
     u32* vbc = vb_cnt.ensure(Vn * nb * 2); be.memset0(vbc, Vn * nb * 2 * sizeof(u32));
@@ -310,6 +317,7 @@ struct Pipeline {
     });
     be.exclusive_scan_u32(pc, po, NG);
     NP = NG > 0 ? (int64_t)fetch_u32(po + NG) : 0;
+    be.stage("graph.emit_pairs");
     // ---- pairs: key (va, vb), value = 9 co-occurrence cells + eligibility
     u64* pk = p_key.ensure(NP); u64* pk2 = p_key2.ensure(NP); u32* pv = p_val.ensure(NP); u32* pv2 = p_val2.ensure(NP);
     be.for_each(NG, PHZ_LAMBDA(int64_t g) {
@@ -333,7 +341,9 @@ struct Pipeline {
         a = a1;
       }
     });
+    be.stage("graph.sort_pairs");
     be.sort_pairs(pk, pk2, pv, pv2, NP, 0, 2 * vb);
+    be.stage("graph.edge_table");
     u32* pf = p_flag.ensure(NP + 1); u32* ps = p_scan.ensure(NP + 2);
     be.for_each(NP, PHZ_LAMBDA(int64_t i) { pf[i] = (i == 0 || pk2[i] != pk2[i - 1]) ? 1u : 0u; });
     be.exclusive_scan_u32(pf, ps, NP);
@@ -369,6 +379,7 @@ struct Pipeline {
       if (tot > load_volatile(&sc[0])) atomic_max(&sc[0], tot);
     });
     max_tot = E > 0 ? fetch_u32(sc) : 0;
+    be.stage("graph.end");
   }
 
   // =================================================================== drop, blocks, phasing, counts
@@ -379,6 +390,7 @@ struct Pipeline {
     if ((int64_t)max_tot >= kstar_len && E > 0) throw PhzError("critical-value table shorter than max c_total");
     const int64_t Vn = V; const int nb = n_bams > 0 ? n_bams : 1; const int vb = vbits;
     const u32* vc = vcontig.p;
+    be.stage("phase.drop_union");
     u32* ks = kstar_d.ensure(kstar_len);
     be.h2d(ks, kstar_host, kstar_len * sizeof(u32));
     const u32* ea_ = ed_a.p; const u32* eb_ = ed_b.p; const u32* esup = ed_sup.p; const u32* etot = ed_tot.p;
@@ -403,6 +415,7 @@ struct Pipeline {
       }
     });
     n_dropped = E > 0 ? fetch_u32(sc + 2) : 0;
+    be.stage("phase.members");
     // ---- members of the kept-edge graph, grouped by component root, ascending variant index inside
     u32* rt = root.ensure(Vn); u32* mf = m_flag.ensure(Vn + 1); u32* ms = m_scan.ensure(Vn + 2);
     be.for_each(Vn, PHZ_LAMBDA(int64_t v) {
@@ -431,6 +444,7 @@ struct Pipeline {
       atomic_min((unsigned long long*)&br[b], (unsigned long long)vr[v]);
     });
     be.for_each(NM, PHZ_LAMBDA(int64_t i) { u32 v = mem[i]; pib[v] = (u32)i - bo[bof[v]]; });
+    be.stage("phase.block_order");
     // ---- block output order: contig first-appearance rank, then first remaining key (phaser.py:1870)
     u64* bk = bs_key.ensure(NB); u64* bk2 = bs_key2.ensure(NB); u32* bv = bs_val.ensure(NB); u32* bv2 = bs_val2.ensure(NB);
     u32* b32 = bs_k32.ensure(NB); u32* b32b = bs_k32b.ensure(NB); u32* bord = blk_order.ensure(NB); u32* bpos = blk_pos.ensure(NB);
@@ -440,6 +454,7 @@ struct Pipeline {
     be.for_each(NB, PHZ_LAMBDA(int64_t i) { b32[i] = cr[vc[mem[bo[bv2[i]]]]]; });
     be.sort_pairs32(b32, b32b, bv2, bord, NB, 0, ceil_log2_host((u64)(nc > 1 ? nc : 2)));
     be.for_each(NB, PHZ_LAMBDA(int64_t i) { bpos[bord[i]] = (u32)i; });
+    be.stage("phase.adjacency");
     // ---- adjacency (kept, non-tie) by source variant
     u32* af = x_flag.ensure(E + 1 > NX + 1 ? E + 1 : NX + 1); u32* as_ = x_scan.ensure(E + 2 > NX + 2 ? E + 2 : NX + 2);
     be.for_each(E, PHZ_LAMBDA(int64_t e) { af[e] = (keep[e] && ecfg[e] != EDGE_TIE) ? 2u : 0u; });
@@ -458,6 +473,7 @@ struct Pipeline {
     });
     be.sort_pairs(dk, dk2, dsg, dsg2, ND, 0, 2 * vb);
     be.exclusive_scan_u32(dcnt, ao, Vn);
+    be.stage("phase.fast_bfs");
     // ---- fast path: 2-colouring from the leftmost variant (resolve_phase, phaser.py:2172-2207)
     u8* col = color.ensure(Vn); be.memset_ff(col, Vn);
     u8* vh = v_hap.ensure(Vn); be.memset0(vh, Vn);
@@ -486,6 +502,7 @@ struct Pipeline {
         for (u32 i = o0; i < o0 + m; ++i) { u32 v = mem[i]; vh[v] = 0; vfl[v] = 0; }
       } else { bst[b] = 2; bnf[b] = 0; }
     });
+    be.stage("phase.hard_prepare");
     // ---- hard path: phase_v3 proper, one logical thread per block
     u32* hf = h_flag.ensure(NB + 1); u32* hs = h_scan.ensure(NB + 2);
     be.for_each(NB, PHZ_LAMBDA(int64_t b) { hf[b] = bst[b] == 2 ? 1u : 0u; });
@@ -510,6 +527,7 @@ struct Pipeline {
       u32 words = fetch_u32(hwo + NH);
       u32* scr = h_scratch.ensure(words);
       int mbs = max_block_size;
+      be.stage("phase.hard_kernel");
       be.for_each(NH, PHZ_LAMBDA(int64_t h) {
         u32 b = hl[h]; u32 o0 = bo[b]; int n = (int)(bo[b + 1] - o0);
         BlockEdges bed{kl + eo[b], eo[b + 1] - eo[b], ea_, eb_, ecfg, pib};
@@ -524,6 +542,7 @@ struct Pipeline {
         if (err) atomic_or(&sc[1], (u32)err);
       });
     }
+    be.stage("phase.final_table");
     // ---- final blocks in output order (block_index of phaser.py:863-867)
     u32* nfo = nf_ord.ensure(NB + 1); u32* fbb = fb_base.ensure(NB + 2);
     be.for_each(NB, PHZ_LAMBDA(int64_t i) { nfo[i] = bnf[bord[i]]; });
@@ -538,6 +557,7 @@ struct Pipeline {
     be.for_each(NM, PHZ_LAMBDA(int64_t i) {
       u32 v = mem[i]; if (vfl[v] != NONE32) vfin[v] = fbb[bpos[bof[v]]] + vfl[v];
     });
+    be.stage("phase.edge_support");
     // ---- edge support per final block (phaser.py:876-895)
     u32* fsup = fb_sup.ensure(NF); u32* ftot = fb_tot.ensure(NF);
     be.memset0(fsup, NF * sizeof(u32)); be.memset0(ftot, NF * sizeof(u32));
@@ -548,6 +568,7 @@ struct Pipeline {
       atomic_add(&ftot[fa], 1u);
       if ((vh[a] ^ vh[b]) == ecfg[e]) atomic_add(&fsup[fa], 1u);
     });
+    be.stage("phase.hap_counts");
     // ---- unique-fragment counts per final block x haplotype (all BAMs, and per counted BAM)
     u32* fc = fb_cnt.ensure(NF * 2); u32* fbc = fb_bcnt.ensure(NF * nb * 2);
     be.memset0(fc, NF * 2 * sizeof(u32)); be.memset0(fbc, NF * nb * 2 * sizeof(u32));
@@ -572,6 +593,7 @@ struct Pipeline {
     });
     u32 errf = fetch_u32(sc + 1);
     *err_out = (int)errf;
+    be.stage("phase.end");
   }
 
   // =================================================================== per-variant read lists of the rows
@@ -581,6 +603,7 @@ struct Pipeline {
     const int64_t n = n_tuples; const int nb = n_bams > 0 ? n_bams : 1; const int vb = vbits;
     const u32* gf = g_frag.p; const u32* gv = g_var.p; const u8* gc = g_cb.p; const u32* vfin = v_final.p; const u8* vh = v_hap.p;
     u32* rf = rl_flag.ensure(n + 1); u32* rsn = rl_scan.ensure(n + 2);
+    be.stage("read_lists");
     be.for_each(n, PHZ_LAMBDA(int64_t t) {
       u32 cls = gc[t] & 3; u32 bam = gc[t] >> 2;
       rf[t] = (cls < 2 && vfin[gv[t]] != NONE32 && !((excl_mask >> bam) & 1)) ? 1u : 0u;
@@ -601,6 +624,7 @@ struct Pipeline {
     be.sort_pairs(k64, k64b, tt2, tt, NRL, 0, fbits + bb + 1);
     u32* of = rl_frag.ensure(NRL); u32* ov = rl_var.ensure(NRL); u32* orow = rl_row.ensure(NRL);
     be.for_each(NRL, PHZ_LAMBDA(int64_t i) { u32 t = tt[i]; of[i] = gf[t]; ov[i] = gv[t]; orow[i] = (u32)k64b[i]; });
+    be.stage("read_lists.end");
     return NRL;
   }
 };

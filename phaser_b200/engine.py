@@ -34,7 +34,7 @@ class phz_reads(ctypes.Structure):
 EXPORTS = ["phz_last_error", "phz_backend_name", "phz_create", "phz_destroy", "phz_sync", "phz_set_variants",
            "phz_map_reads", "phz_map_reads_host", "phz_as_histogram", "phz_commit_bam", "phz_build_graph",
            "phz_phase", "phz_read_lists", "phz_array", "phz_download", "phz_counters", "phz_launch_counts",
-           "phz_set_profiling", "phz_map_times"]
+           "phz_set_profiling", "phz_map_times", "phz_stage_report"]
 
 
 def _declare(lib):
@@ -58,6 +58,7 @@ def _declare(lib):
     lib.phz_launch_counts.argtypes = [c_void_p, POINTER(c_uint64), POINTER(c_uint64)]
     lib.phz_set_profiling.argtypes = [c_void_p, c_int]
     lib.phz_map_times.argtypes = [c_void_p, POINTER(ctypes.c_float)]
+    lib.phz_stage_report.argtypes = [c_void_p, c_char_p, c_int64]
     return lib
 
 
@@ -219,14 +220,27 @@ class Engine:
         self._check(self.lib.phz_launch_counts(self.ctx, byref(a), byref(b)))
         return a.value, b.value
 
-    def set_profiling(self, on=True):
-        self._check(self.lib.phz_set_profiling(self.ctx, 1 if on else 0))
+    def set_profiling(self, level=1):
+        """0 off, 1 CUDA events around the K1 passes, 2 additionally named stage marks."""
+        self._check(self.lib.phz_set_profiling(self.ctx, int(level)))
 
     def map_times(self):
         """(count pass, scan + readback, emit pass) in ms for the last map_reads call; CUDA events."""
         ms = (ctypes.c_float * 3)()
         self._check(self.lib.phz_map_times(self.ctx, ms))
         return float(ms[0]), float(ms[1]), float(ms[2])
+
+    def stage_report(self):
+        """{stage: ms} accumulated since the last call (CUDA events; needs set_profiling(True))."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        self._check(self.lib.phz_stage_report(self.ctx, buf, len(buf)))
+        out = {}
+        for ln in buf.value.decode().splitlines():
+            k, v = ln.split("\t")
+            if k.endswith(".end"):
+                k = "host_gap_after." + k[:-4]      # time until the next API call: host-side work
+            out[k] = out.get(k, 0.0) + float(v)
+        return out
 
     def sync(self):
         self._check(self.lib.phz_sync(self.ctx))

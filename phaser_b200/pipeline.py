@@ -79,13 +79,25 @@ def noise_level(match: int, mismatch: int) -> float:
     return float(mismatch) / (float(match + mismatch) * 2)
 
 
-def critical_values(max_total: int, noise_e: float, cc_threshold: float) -> np.ndarray:
+def critical_values(max_total: int, noise_e: float, cc_threshold: float, totals=None) -> np.ndarray:
     """kstar[n] = min{k : binom.cdf(k, n, p) >= cc_threshold}, p = 1-(6e+10e^2)  (phaser.py:1649, 696).
     An edge with 0 < c_supporting < c_total is dropped iff c_supporting < kstar[c_total]; uses the same
-    scipy function as the reference so the comparison agrees with it exactly."""
+    scipy function as the reference so the comparison agrees with it exactly.  With `totals` (the
+    c_total values that actually occur) only those entries of the table are computed."""
     from scipy.stats import binom
     p = 1 - ((6 * noise_e) + (10 * math.pow(noise_e, 2)))
+    if totals is not None:
+        n = np.unique(np.asarray(totals, dtype=np.int64))
+        table = np.zeros(max_total + 1, np.uint32)
+        if n.shape[0]:
+            table[n] = _critical_values_at(n, p, cc_threshold)
+        return table
     n = np.arange(0, max_total + 1, dtype=np.int64)
+    return _critical_values_at(n, p, cc_threshold)
+
+
+def _critical_values_at(n, p, cc_threshold):
+    from scipy.stats import binom
     k = np.nan_to_num(binom.ppf(cc_threshold, n, p), nan=0.0).astype(np.int64)
     k = np.clip(k, 0, n)
     for _ in range(64):
@@ -175,7 +187,8 @@ def run_path(engine: Engine, vt: VariantTable, batches, params: PhaseParams, n_f
                           "Common reasons for this occurring include: 1) MAPQ or BASEQ set too conservatively 2) BAM "
                           "and VCF have different chromosome names (IE 'chr1' vs '1').")
     noise_e = noise_level(match, mism)
-    kstar = critical_values(int(max_tot), noise_e, params.cc_threshold)
+    totals = engine.download("ed_tot") if n_edges > 0 else np.zeros(0, np.uint32)
+    kstar = critical_values(int(max_tot), noise_e, params.cc_threshold, totals=totals)
     nf, flags = engine.phase(kstar, params.max_block_size, excl)
     if flags & 2:
         raise PhaserFatal("a haplotype block cannot be split down to --max_block_size (the reference does not "
