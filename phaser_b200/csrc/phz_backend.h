@@ -92,6 +92,13 @@ __global__ void __launch_bounds__(256) for_each_kernel(int64_t n, F f) {
   if (i < n) f(i);
 }
 
+// one warp per item: f(item, lane, 32)
+template <class F>
+__global__ void __launch_bounds__(256) for_each_warp_kernel(int64_t n, F f) {
+  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w < n) f(w, (int)(threadIdx.x & 31), 32);
+}
+
 struct DeviceBackend {
   static constexpr bool kIsDevice = true;
   cudaStream_t stream = nullptr;
@@ -161,6 +168,15 @@ struct DeviceBackend {
     if (n <= 0) return;
     int64_t blocks = (n + 255) / 256;
     for_each_kernel<<<(unsigned)blocks, 256, 0, stream>>>(n, f);
+    PHZ_CUDA(cudaGetLastError());
+    launches++;
+  }
+
+  template <class F>
+  void for_each_warp(int64_t n, F f) {
+    if (n <= 0) return;
+    int64_t blocks = (n * 32 + 255) / 256;
+    for_each_warp_kernel<<<(unsigned)blocks, 256, 0, stream>>>(n, f);
     PHZ_CUDA(cudaGetLastError());
     launches++;
   }
@@ -238,6 +254,11 @@ struct HostSimBackend {
   template <class F>
   void for_each(int64_t n, F f) {
     for (int64_t i = 0; i < n; ++i) f(i);
+    launches++;
+  }
+  template <class F>
+  void for_each_warp(int64_t n, F f) {
+    for (int64_t i = 0; i < n; ++i) f(i, 0, 1);
     launches++;
   }
   void exclusive_scan_u32(const u32* in, u32* out, int64_t n) {

@@ -14,6 +14,23 @@
 
 namespace phz {
 
+// A block is phased by `n` cooperating lanes (one warp on the device, a single lane in the host
+// simulation): lane 0 runs the serial control flow, all lanes share the 2^n enumeration.
+struct Coop { int lane; int n; };
+PHZ_HD void coop_sync(const Coop& c) {
+#if defined(__CUDA_ARCH__)
+  if (c.n > 1) __syncwarp();
+#endif
+  (void)c;
+}
+PHZ_HD int coop_bcast(const Coop& c, int v) {
+#if defined(__CUDA_ARCH__)
+  if (c.n > 1) return __shfl_sync(0xffffffffu, v, 0);
+#endif
+  (void)c;
+  return v;
+}
+
 constexpr u8 CH_DASH = 2;
 constexpr int EDGE_CIS = 0, EDGE_TRANS = 1, EDGE_TIE = 2;
 constexpr int MAX_ENUM = 24;
@@ -67,11 +84,16 @@ PHZ_HD int resolve_range(const BlockEdges& be, int lo, int hi, u8* color, u8* ou
   return -1;
 }
 
-// 2^n enumeration of sub_block_phase on local range [lo, hi).  Returns length n; out is the unique
-// best configuration or all dashes.  n > MAX_ENUM sets *err.
-PHZ_HD int enumerate_range(const BlockEdges& be, int lo, int hi, u8* out, int* err) {
+// 2^n enumeration of sub_block_phase on local range [lo, hi), shared by the cooperating lanes.
+// Returns length n (on every lane); out is the unique best configuration or all dashes (written by
+// lane 0).  n > MAX_ENUM sets *err.
+PHZ_HD int enumerate_range(const BlockEdges& be, int lo, int hi, u8* out, int* err, const Coop& cp) {
   int n = hi - lo;
-  if (n > MAX_ENUM) { *err = 1; for (int i = 0; i < n; ++i) out[i] = CH_DASH; return n; }
+  if (n > MAX_ENUM) {
+    if (cp.lane == 0) { *err |= 1; for (int i = 0; i < n; ++i) out[i] = CH_DASH; }
+    coop_sync(cp);
+    return n;
+  }
   u32 cis[MAX_ENUM], trans[MAX_ENUM];
   for (int i = 0; i < n; ++i) { cis[i] = 0; trans[i] = 0; }
   for (u32 k = 0; k < be.n_edges; ++k) {
@@ -83,10 +105,10 @@ PHZ_HD int enumerate_range(const BlockEdges& be, int lo, int hi, u8* out, int* e
   }
   // variant i <-> bit i; only configurations with allele 0 at variant 0 are scored (the complement of
   // every other one was scored earlier in lexicographic order, phaser.py:2226-2234)
-  u32 full = (n == 32) ? 0xFFFFFFFFu : ((1u << n) - 1);
+  u32 full = (1u << n) - 1;
   int best = -1; u32 best_w = 0; u32 n_best = 0;
   u32 total = 1u << (n - 1);
-  for (u32 y = 0; y < total; ++y) {
+  for (u32 y = (u32)cp.lane; y < total; y += (u32)cp.n) {
     u32 w = y << 1;
     int s = 0;
     for (int i = 0; i < n; ++i) {
@@ -100,8 +122,23 @@ PHZ_HD int enumerate_range(const BlockEdges& be, int lo, int hi, u8* out, int* e
     if (s > best) { best = s; best_w = w; n_best = 1; }
     else if (s == best) n_best++;
   }
-  if (n_best == 1) { for (int i = 0; i < n; ++i) out[i] = (best_w >> i) & 1u; }
-  else { for (int i = 0; i < n; ++i) out[i] = CH_DASH; }
+#if defined(__CUDA_ARCH__)
+  if (cp.n > 1) {
+    int gbest = best;
+    for (int o = 16; o > 0; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, gbest, o); gbest = t > gbest ? t : gbest; }
+    u32 mine = (best == gbest) ? n_best : 0u;
+    u32 cnt = mine;
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    unsigned holders = __ballot_sync(0xffffffffu, best == gbest);
+    u32 w0 = __shfl_sync(0xffffffffu, best_w, __ffs(holders) - 1);
+    best = gbest; n_best = cnt; best_w = w0;
+  }
+#endif
+  if (cp.lane == 0) {
+    if (n_best == 1) { for (int i = 0; i < n; ++i) out[i] = (best_w >> i) & 1u; }
+    else { for (int i = 0; i < n; ++i) out[i] = CH_DASH; }
+  }
+  coop_sync(cp);
   return n;
 }
 
@@ -138,8 +175,9 @@ PHZ_HD size_t hard_scratch_words(size_t n) { return 7 * n + 16; }
 // hard_scratch_words(n) u32 words.  Output: runs (run_start[k], run_len[k]) of consecutive local
 // variants that form the final blocks (k < returned count), hap[i] = allele of haplotype A for local
 // variant i (meaningful inside runs), fin_local[i] = run index (caller pre-fills 0xFFFFFFFF).
+// Called by every cooperating lane; the return value is the same on all of them.
 PHZ_HD int phase_block_hard(const BlockEdges& be, int n, int max_block_size, u32* w,
-                            u32* run_start, u32* run_len, u8* hap, u32* fin_local, int* err) {
+                            u32* run_start, u32* run_len, u8* hap, u32* fin_local, int* err, const Coop& cp) {
   int* cnt = (int*)w;                       // [n+1] crossing counts
   u32* sub_off = w + (n + 1);               // [n+1] variant offsets of sub-blocks
   u32* sub_len = sub_off + (n + 1);         // [n]   string length of each sub-block phase
@@ -149,78 +187,90 @@ PHZ_HD int phase_block_hard(const BlockEdges& be, int n, int max_block_size, u32
   u8* sub = color + n;                      // [n] concatenated sub-block phase strings
   u8* fin = sub + n;                        // [n] current final_phase string
   u8* cand = fin + n;                       // [n] candidate
-  // ---- find_weak_points (phaser.py:2309-2324): edge (i<j) crosses cut p iff i < p <= j
-  for (int p = 0; p <= n; ++p) { cnt[p] = 0; chosen[p] = 0; }
-  for (u32 k = 0; k < be.n_edges; ++k) {
-    int i, j, s; be.get(k, i, j, s);
-    if (i > j) { int t = i; i = j; j = t; }
-    if (i == j) continue;
-    cnt[i + 1] += 1; cnt[j + 1] -= 1;      // j <= n-1
-  }
-  for (int p = 1; p <= n; ++p) cnt[p] += cnt[p - 1];
-  // ---- split_by_weak (phaser.py:2271-2294)
-  int xmax = (max_block_size == 0) ? n : max_block_size;
-  int split_at = 1;
-  while (true) {
-    for (int p = 2; p <= n - 2; ++p)
-      if (cnt[p] == split_at && !chosen[p + 1] && !chosen[p - 1]) chosen[p] = 1;
-    int last = 0, max_frag = 0;
-    for (int p = 1; p <= n; ++p)
-      if (p == n || chosen[p]) { if (p - last > max_frag) max_frag = p - last; last = p; }
-    split_at++;
-    if (!(max_frag > xmax)) break;
-    int next = 0x7FFFFFFF;       // levels without positions change nothing: jump to the next one
-    for (int p = 2; p <= n - 2; ++p) if (cnt[p] >= split_at && cnt[p] < next) next = cnt[p];
-    if (next == 0x7FFFFFFF) { *err = 2; break; }     // the reference would loop forever here
-    split_at = next;
-  }
   int n_sub = 0;
-  {
+  if (cp.lane == 0) {
+    // ---- find_weak_points (phaser.py:2309-2324): edge (i<j) crosses cut p iff i < p <= j
+    for (int p = 0; p <= n; ++p) { cnt[p] = 0; chosen[p] = 0; }
+    for (u32 k = 0; k < be.n_edges; ++k) {
+      int i, j, s; be.get(k, i, j, s);
+      if (i > j) { int t = i; i = j; j = t; }
+      if (i == j) continue;
+      cnt[i + 1] += 1; cnt[j + 1] -= 1;      // j <= n-1
+    }
+    for (int p = 1; p <= n; ++p) cnt[p] += cnt[p - 1];
+    // ---- split_by_weak (phaser.py:2271-2294)
+    int xmax = (max_block_size == 0) ? n : max_block_size;
+    int split_at = 1;
+    while (true) {
+      for (int p = 2; p <= n - 2; ++p)
+        if (cnt[p] == split_at && !chosen[p + 1] && !chosen[p - 1]) chosen[p] = 1;
+      int last = 0, max_frag = 0;
+      for (int p = 1; p <= n; ++p)
+        if (p == n || chosen[p]) { if (p - last > max_frag) max_frag = p - last; last = p; }
+      split_at++;
+      if (!(max_frag > xmax)) break;
+      int next = 0x7FFFFFFF;       // levels without positions change nothing: jump to the next one
+      for (int p = 2; p <= n - 2; ++p) if (cnt[p] >= split_at && cnt[p] < next) next = cnt[p];
+      if (next == 0x7FFFFFFF) { *err |= 2; break; }     // the reference would loop forever here
+      split_at = next;
+    }
     int last = 0;
     for (int p = 1; p <= n; ++p) if (p == n || chosen[p]) { sub_off[n_sub++] = (u32)last; last = p; }
     sub_off[n_sub] = (u32)n;
   }
+  n_sub = coop_bcast(cp, n_sub);
+  coop_sync(cp);
   // ---- phase every sub-block (phaser.py:2133-2136)
   u32 used_chars = 0;
   for (int s = 0; s < n_sub; ++s) {
     int lo = (int)sub_off[s], hi = (int)sub_off[s + 1];
     int len = -1;
-    if (n_sub > 1) len = resolve_range(be, lo, hi, color, sub + used_chars);
-    if (len < 0) len = enumerate_range(be, lo, hi, sub + used_chars, err);
-    sub_pos[s] = used_chars; sub_len[s] = (u32)len; used_chars += (u32)len;
+    if (n_sub > 1) {
+      if (cp.lane == 0) len = resolve_range(be, lo, hi, color, sub + used_chars);
+      len = coop_bcast(cp, len);
+    }
+    if (len < 0) len = enumerate_range(be, lo, hi, sub + used_chars, err, cp);
+    if (cp.lane == 0) { sub_pos[s] = used_chars; sub_len[s] = (u32)len; }
+    used_chars += (u32)len;
   }
+  coop_sync(cp);
   // ---- merge left to right (phaser.py:2140-2157).  A and B are each all digits or all dashes, so
   // of the four concatenations only A+B and A+B' are scored (the other two are their complements,
   // phaser.py:2234) and the merge succeeds iff both are digits and the two supports differ.
-  int n_runs = 0, consumed = 0;
-  int fin_len = (int)sub_len[0];
-  for (int i = 0; i < fin_len; ++i) fin[i] = sub[sub_pos[0] + i];
-  int split_start = 0;
-  for (int s = 1; s < n_sub; ++s) {
-    const u8* nb = sub + sub_pos[s];
-    int nb_len = (int)sub_len[s];
-    int used = fin_len + nb_len;
-    bool a_dash = (fin_len > 0 && fin[0] == CH_DASH), b_dash = (nb_len > 0 && nb[0] == CH_DASH);
-    bool ok = false, flip_b = false;
-    if (!a_dash && !b_dash) {
-      for (int i = 0; i < fin_len; ++i) cand[i] = fin[i];
-      for (int i = 0; i < nb_len; ++i) cand[fin_len + i] = nb[i];
-      int s0 = score_config(be, n, split_start, cand, used);
-      for (int i = 0; i < nb_len; ++i) cand[fin_len + i] = nb[i] ^ 1;
-      int s1 = score_config(be, n, split_start, cand, used);
-      if (s0 > s1) { ok = true; flip_b = false; } else if (s1 > s0) { ok = true; flip_b = true; }
+  int n_runs = 0;
+  if (cp.lane == 0) {
+    int consumed = 0;
+    int fin_len = (int)sub_len[0];
+    for (int i = 0; i < fin_len; ++i) fin[i] = sub[sub_pos[0] + i];
+    int split_start = 0;
+    for (int s = 1; s < n_sub; ++s) {
+      const u8* nb = sub + sub_pos[s];
+      int nb_len = (int)sub_len[s];
+      int used = fin_len + nb_len;
+      bool a_dash = (fin_len > 0 && fin[0] == CH_DASH), b_dash = (nb_len > 0 && nb[0] == CH_DASH);
+      bool ok = false, flip_b = false;
+      if (!a_dash && !b_dash) {
+        for (int i = 0; i < fin_len; ++i) cand[i] = fin[i];
+        for (int i = 0; i < nb_len; ++i) cand[fin_len + i] = nb[i];
+        int s0 = score_config(be, n, split_start, cand, used);
+        for (int i = 0; i < nb_len; ++i) cand[fin_len + i] = nb[i] ^ 1;
+        int s1 = score_config(be, n, split_start, cand, used);
+        if (s0 > s1) { ok = true; flip_b = false; } else if (s1 > s0) { ok = true; flip_b = true; }
+      }
+      if (ok) {
+        for (int i = 0; i < nb_len; ++i) fin[fin_len + i] = flip_b ? (u8)(nb[i] ^ 1) : nb[i];
+        fin_len = used;
+      } else {
+        close_final_block(fin, fin_len, n, &consumed, &n_runs, run_start, run_len, hap, fin_local);
+        split_start = used;                 // Q14: not an offset sum
+        fin_len = nb_len;
+        for (int i = 0; i < nb_len; ++i) fin[i] = nb[i];
+      }
     }
-    if (ok) {
-      for (int i = 0; i < nb_len; ++i) fin[fin_len + i] = flip_b ? (u8)(nb[i] ^ 1) : nb[i];
-      fin_len = used;
-    } else {
-      close_final_block(fin, fin_len, n, &consumed, &n_runs, run_start, run_len, hap, fin_local);
-      split_start = used;                 // Q14: not an offset sum
-      fin_len = nb_len;
-      for (int i = 0; i < nb_len; ++i) fin[i] = nb[i];
-    }
+    close_final_block(fin, fin_len, n, &consumed, &n_runs, run_start, run_len, hap, fin_local);
   }
-  close_final_block(fin, fin_len, n, &consumed, &n_runs, run_start, run_len, hap, fin_local);
+  n_runs = coop_bcast(cp, n_runs);
+  coop_sync(cp);
   return n_runs;
 }
 

@@ -15,8 +15,10 @@
 
 #ifdef __CUDACC__
 #define PHZ_LAMBDA [=] __host__ __device__
+#define PHZ_LAMBDA_WARP [=] __host__ __device__
 #else
 #define PHZ_LAMBDA [=]
+#define PHZ_LAMBDA_WARP [=]
 #endif
 
 namespace phz {
@@ -72,7 +74,7 @@ struct Pipeline {
   int64_t NE = 0, NG = 0, NP = 0;
   // ------------------------------------------------------------------ pairs / edges
   Buf<B, u64> p_key, p_key2; Buf<B, u32> p_val, p_val2, p_flag, p_scan, pe_start;
-  Buf<B, u32> x_flag, x_scan;
+  Buf<B, u32> x_flag, x_scan, x_acc;
   Buf<B, u32> ed_a, ed_b, ed_sup, ed_tot, ed_n9; Buf<B, u8> ed_cfg, ed_keep;
   Buf<B, u32> scalars, kstar_d;                     // scalars: [0]=max_tot [1]=err flags [2]=dropped
   int64_t NX = 0, E = 0; u32 max_tot = 0;
@@ -101,7 +103,7 @@ struct Pipeline {
     e_key.bind(b); e_bam.bind(b); e_mask.bind(b); e_tmin.bind(b); e_flag.bind(b); e_scan.bind(b);
     grp_off.bind(b); pair_cnt.bind(b); pair_off.bind(b);
     p_key.bind(b); p_key2.bind(b); p_val.bind(b); p_val2.bind(b); p_flag.bind(b); p_scan.bind(b); pe_start.bind(b);
-    x_flag.bind(b); x_scan.bind(b);
+    x_flag.bind(b); x_scan.bind(b); x_acc.bind(b);
     ed_a.bind(b); ed_b.bind(b); ed_sup.bind(b); ed_tot.bind(b); ed_n9.bind(b); ed_cfg.bind(b); ed_keep.bind(b); scalars.bind(b); kstar_d.bind(b);
     parent.bind(b); deg.bind(b); root.bind(b); m_flag.bind(b); m_scan.bind(b); m_list.bind(b); m_key.bind(b); m_key2.bind(b);
     m_val2.bind(b); members.bind(b);
@@ -223,9 +225,23 @@ struct Pipeline {
     u32* vf = vfirst.ensure(Vn); be.memset_ff(vf, Vn * sizeof(u32));
     u32* nl = ncls.ensure(Vn * 3); be.memset0(nl, Vn * 3 * sizeof(u32));
     be.for_each(n, PHZ_LAMBDA(int64_t t) {
-      u32 v = gv[t];
+      u32 v = gv[t]; u32 cls = gc[t] & 3;
+#if defined(__CUDA_ARCH__)
+      // reads of one locus are neighbours in tuple order: combine the lanes that hit the same variant
+      unsigned act = __activemask();
+      unsigned peers = __match_any_sync(act, v);
+      unsigned b0 = __ballot_sync(act, cls == 0) & peers, b1 = __ballot_sync(act, cls == 1) & peers,
+               b2 = __ballot_sync(act, cls == 2) & peers;
+      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {          // lowest lane = smallest t of the group
+        atomic_min(&vf[v], (u32)t);
+        if (b0) atomic_add(&nl[(int64_t)v * 3], (u32)__popc(b0));
+        if (b1) atomic_add(&nl[(int64_t)v * 3 + 1], (u32)__popc(b1));
+        if (b2) atomic_add(&nl[(int64_t)v * 3 + 2], (u32)__popc(b2));
+      }
+#else
       atomic_min(&vf[v], (u32)t);
-      atomic_add(&nl[(int64_t)v * 3 + (gc[t] & 3)], 1u);
+      atomic_add(&nl[(int64_t)v * 3 + cls], 1u);
+#endif
     });
     u32* cf = cfirst.ensure(nc + 1); be.memset_ff(cf, (nc + 1) * sizeof(u32));
     u64* nz = noise.ensure(2); be.memset0(nz, 2 * sizeof(u64));
@@ -351,13 +367,31 @@ struct Pipeline {
     u32* pst = pe_start.ensure(NX + 1);
     { int64_t np = NP, nx = NX;
       be.for_each(NP + 1, PHZ_LAMBDA(int64_t i) { if (i == np) pst[nx] = (u32)np; else if (pf[i]) pst[ps[i]] = (u32)i; }); }
+    // ---- distinct pairs: 9 cell sums + eligibility.  One logical thread per fixed chunk of the sorted
+    // pair array accumulates its runs locally and flushes one atomic per (run, non-zero cell), so a pair
+    // supported by a million fragments costs the same per thread as any other.
+    u32* xacc = x_acc.ensure((NX + 1) * 10); be.memset0(xacc, (NX + 1) * 10 * sizeof(u32));
+    {
+      const int64_t CH = 32; int64_t np = NP; int64_t nchunks = (NP + CH - 1) / CH;
+      be.for_each(nchunks, PHZ_LAMBDA(int64_t c) {
+        int64_t i0 = c * CH, i1 = i0 + CH; if (i1 > np) i1 = np;
+        u32 acc[10]; for (int k = 0; k < 10; ++k) acc[k] = 0;
+        u32 cur = ps[i0] + pf[i0] - 1;
+        for (int64_t i = i0; i < i1; ++i) {
+          u32 x = ps[i] + pf[i] - 1;
+          if (x != cur) {
+            for (int k = 0; k < 10; ++k) if (acc[k]) { atomic_add(&xacc[(int64_t)cur * 10 + k], acc[k]); acc[k] = 0; }
+            cur = x;
+          }
+          u32 cells = pv2[i];
+          for (int k = 0; k < 10; ++k) acc[k] += (cells >> k) & 1u;
+        }
+        for (int k = 0; k < 10; ++k) if (acc[k]) atomic_add(&xacc[(int64_t)cur * 10 + k], acc[k]);
+      });
+    }
     // ---- eligible pairs -> edge table (phaser.py:667-678, 1594-1642)
     u32* xf = x_flag.ensure(NX + 1); u32* xs = x_scan.ensure(NX + 2);
-    be.for_each(NX, PHZ_LAMBDA(int64_t x) {
-      u32 f = 0;
-      for (u32 i = pst[x]; i < pst[x + 1]; ++i) if (pv2[i] & (1u << 9)) { f = 1; break; }
-      xf[x] = f;
-    });
+    be.for_each(NX, PHZ_LAMBDA(int64_t x) { xf[x] = xacc[x * 10 + 9] ? 1u : 0u; });
     be.exclusive_scan_u32(xf, xs, NX);
     E = NX > 0 ? (int64_t)fetch_u32(xs + NX) : 0;
     u32* ea_ = ed_a.ensure(E); u32* eb_ = ed_b.ensure(E); u32* esup = ed_sup.ensure(E); u32* etot = ed_tot.ensure(E);
@@ -366,8 +400,7 @@ struct Pipeline {
     be.for_each(NX, PHZ_LAMBDA(int64_t x) {
       if (!xf[x]) return;
       u32 e = xs[x];
-      u32 n9[9]; for (int c = 0; c < 9; ++c) n9[c] = 0;
-      for (u32 i = pst[x]; i < pst[x + 1]; ++i) { u32 cells = pv2[i]; for (int c = 0; c < 9; ++c) n9[c] += (cells >> c) & 1u; }
+      u32 n9[9]; for (int c = 0; c < 9; ++c) n9[c] = xacc[x * 10 + c];
       u64 key = pk2[pst[x]];
       ea_[e] = (u32)(key >> vb); eb_[e] = (u32)(key & vmask);
       for (int c = 0; c < 9; ++c) en9[(int64_t)e * 9 + c] = n9[c];
@@ -528,21 +561,22 @@ struct Pipeline {
       u32* scr = h_scratch.ensure(words);
       int mbs = max_block_size;
       be.stage("phase.hard_kernel");
-      be.for_each(NH, PHZ_LAMBDA(int64_t h) {
+      be.for_each_warp(NH, PHZ_LAMBDA_WARP(int64_t h, int lane, int nlanes) {
         u32 b = hl[h]; u32 o0 = bo[b]; int n = (int)(bo[b + 1] - o0);
         BlockEdges bed{kl + eo[b], eo[b + 1] - eo[b], ea_, eb_, ecfg, pib};
+        Coop cp{lane, nlanes};
         // hap / fin_local are written through small local views over the member segment
         u8* hap_loc = (u8*)(q + o0);           // n bytes inside this block's queue segment (n u32 words)
         u32* fin_loc = scr + hwo[h] + hard_scratch_words(n) - n;   // tail of this block's scratch
-        for (int i = 0; i < n; ++i) { fin_loc[i] = NONE32; hap_loc[i] = 0; }
+        for (int i = lane; i < n; i += nlanes) { fin_loc[i] = NONE32; hap_loc[i] = 0; }
+        coop_sync(cp);
         int err = 0;
-        int nr = phase_block_hard(bed, n, mbs, scr + hwo[h], rs + o0, rl + o0, hap_loc, fin_loc, &err);
-        bnf[b] = (u32)nr;
-        for (int i = 0; i < n; ++i) { u32 v = mem[o0 + i]; vfl[v] = fin_loc[i]; vh[v] = hap_loc[i]; }
-        if (err) atomic_or(&sc[1], (u32)err);
+        int nr = phase_block_hard(bed, n, mbs, scr + hwo[h], rs + o0, rl + o0, hap_loc, fin_loc, &err, cp);
+        if (lane == 0) bnf[b] = (u32)nr;
+        for (int i = lane; i < n; i += nlanes) { u32 v = mem[o0 + i]; vfl[v] = fin_loc[i]; vh[v] = hap_loc[i]; }
+        if (err && lane == 0) atomic_or(&sc[1], (u32)err);
       });
     }
-    be.stage("phase.final_table");
     // ---- final blocks in output order (block_index of phaser.py:863-867)
     u32* nfo = nf_ord.ensure(NB + 1); u32* fbb = fb_base.ensure(NB + 2);
     be.for_each(NB, PHZ_LAMBDA(int64_t i) { nfo[i] = bnf[bord[i]]; });
