@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--cpu_pairs", type=int, default=40_000, help="bounded sample for the CPU baseline")
     ap.add_argument("--no_e2e", action="store_true")
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--k1_mode", type=int, default=1, help="1 windowed K1 (default), 0 generic K1")
     ap.add_argument("--profile", action="store_true", help="add per-stage CUDA-event times of one extra step")
     return ap.parse_args()
 
@@ -130,6 +131,7 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     E = eng.Engine(device=dev)
+    E.set_option("k1_mode", a.k1_mode)
     t_gen = time.time()
     g, vt, packed, n_pairs = make_sample(a.seed + rank, a.pairs, a.variants, a.exonic_frac, dev)
     torch.cuda.synchronize()

@@ -175,6 +175,14 @@ int phz_counters(phz_ctx* ctx, int64_t* c) {
   PHZ_CATCH
 }
 
+int phz_set_option(phz_ctx* ctx, const char* name, int64_t value) {
+  PHZ_TRY
+  std::string n(name);
+  if (n == "k1_mode") ctx->p.k1_mode = (int)value;
+  else throw PhzError("unknown option: " + n);
+  PHZ_CATCH
+}
+
 int phz_set_profiling(phz_ctx* ctx, int on) { PHZ_TRY ctx->p.be.profiling = on; PHZ_CATCH }
 
 int phz_map_times(phz_ctx* ctx, float* ms) {

@@ -61,12 +61,49 @@ PHZ_HD u8 masked_base(const ReadsView& rv, u64 base_off, int q, int baseq) {
   return ((int)rv.qual[i] < baseq) ? BASE_N : b;    // read_variant_map.py:179-184
 }
 
+// Variant-position providers: where the per-segment range search reads the sorted het-site positions.
+struct GlobalVP {
+  const int32_t* g;
+  PHZ_HD int32_t at(int64_t j) const { return g[j]; }
+  // lower bounds of lo_key / hi_key inside the contig's range [v0, v1)
+  PHZ_HD void range(int32_t lo_key, int32_t hi_key, int64_t v0, int64_t v1, int64_t& lo, int64_t& hi) const {
+    lo = lower_bound_i32(g, v0, v1, lo_key);
+    hi = lower_bound_i32(g, lo, v1, hi_key);
+  }
+};
+
+// A slab of the position array staged in shared memory (global indices [wbase, wbase+wn)); searches
+// that fall outside it go back to global memory.
+struct WindowVP {
+  const int32_t* g;
+  const int32_t* s;
+  int64_t wbase;
+  int wn;
+  PHZ_HD int32_t at(int64_t j) const {
+    int64_t k = j - wbase;
+    return (k >= 0 && k < wn) ? s[k] : g[j];
+  }
+  PHZ_HD void range(int32_t lo_key, int32_t hi_key, int64_t v0, int64_t v1, int64_t& lo, int64_t& hi) const {
+    int64_t a = v0 > wbase ? v0 : wbase, b = v1 < wbase + wn ? v1 : wbase + wn;
+    if (a < b) {
+      int64_t l = lower_bound_i32(s, a - wbase, b - wbase, lo_key) + wbase;
+      if ((l > a || a == v0) && (l < b || b == v1)) {
+        int64_t h = lower_bound_i32(s, l - wbase, b - wbase, hi_key) + wbase;
+        if (h < b || b == v1) { lo = l; hi = h; return; }
+        lo = l; hi = lower_bound_i32(g, b, v1, hi_key); return;
+      }
+    }
+    lo = lower_bound_i32(g, v0, v1, lo_key);
+    hi = lower_bound_i32(g, lo, v1, hi_key);
+  }
+};
+
 // Walks one record.  EMIT=false: returns the number of candidate (segment, variant) pairs.
 // EMIT=true: writes one tuple per candidate starting at out index `o` (class CLS_NONE when the
 // reference would print nothing) and returns the number written.
-template <bool EMIT>
-PHZ_HD u32 map_record(const ReadsView& rv, const VariantsView& vv, int64_t r, int contig, int baseq, double isize_cutoff,
-                      u64 o, u32* t_rec, u32* t_var, u32* t_misc) {
+template <bool EMIT, class VP>
+PHZ_HD u32 map_record(const ReadsView& rv, const VariantsView& vv, const VP& vp, int64_t r, int contig, int baseq,
+                      double isize_cutoff, u64 o, u32* t_rec, u32* t_var, u32* t_misc) {
   if (!isize_ok(rv.tlen[r], isize_cutoff)) return 0;
   const int64_t v0 = vv.contig_var_off[contig], v1 = vv.contig_var_off[contig + 1];
   if (v0 == v1) return 0;
@@ -96,13 +133,13 @@ PHZ_HD u32 map_record(const ReadsView& rv, const VariantsView& vv, int64_t r, in
       int64_t lo_pos = (int64_t)rpos + seg_start, hi_pos = lo_pos + seg_len;   // [lo_pos, hi_pos)
       if (lo_pos < 2147483647LL) {
         int32_t hi32 = hi_pos > 2147483647LL ? 2147483647 : (int32_t)hi_pos;
-        int64_t lo = lower_bound_i32(vv.pos, v0, v1, (int32_t)lo_pos);
-        int64_t hi = lower_bound_i32(vv.pos, lo, v1, hi32);
+        int64_t lo, hi;
+        vp.range((int32_t)lo_pos, hi32, v0, v1, lo, hi);
         if (!EMIT) {
           n_out += (u32)(hi - lo);
         } else {
           for (int64_t j = lo; j < hi; ++j) {
-            const int64_t st = (int64_t)vv.pos[j] - lo_pos;      // offset in pseudo_read
+            const int64_t st = (int64_t)vp.at(j) - lo_pos;       // offset in pseudo_read
             // locate pseudo_read[st] and the insertion keyed st (keys are whole-read offsets: Q3)
             int64_t g = seg_start, q = q_start;
             int base = -1;            // -1: not found (cannot happen), 16: deletion placeholder

@@ -49,9 +49,104 @@ __global__ void __launch_bounds__(256) as_hist_kernel(const u32* __restrict__ t_
 }
 #endif
 
+// ----------------------------------------------------------------------------- K1, windowed
+// Records are coordinate sorted, so the het sites a tile of consecutive records can touch form a
+// short contiguous slab of the position array.  A CTA walks a strip of K1_TILES tiles of K1_THREADS
+// records; the slab [wbase, wbase+wn) lives in shared memory (one TMA bulk copy, re-armed only when
+// the strip has advanced past the middle of the slab), and the per-segment range searches run there.
+constexpr int K1_THREADS = 256;
+constexpr int K1_TILES = 8;
+constexpr int K1_WIN = 2048;          // het-site positions per slab (8 KB)
+
+struct WindowState { int contig; int64_t wbase; int wn; };
+
+// Decides whether the slab must be (re)loaded for the tile starting at record r0.  `win` is the
+// current slab (shared memory on the device).  Returns true when st was changed.
+PHZ_HD bool window_for_tile(const ReadsView& rv, const VariantsView& vv, int64_t r0, const int32_t* win, WindowState& st) {
+  int c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r0);
+  int64_t v0 = vv.contig_var_off[c], v1 = vv.contig_var_off[c + 1];
+  int32_t p0 = rv.pos[r0];
+  if (c == st.contig && st.wn > 0) {
+    bool reaches_end = st.wbase + st.wn >= v1;
+    if (reaches_end || p0 <= win[st.wn / 2]) return false;      // still in the first half: keep
+  }
+  int64_t wlo = lower_bound_i32(vv.pos, v0, v1, p0);
+  int64_t wbase = wlo & ~(int64_t)3;                              // 16-byte aligned source for the bulk copy
+  int64_t wn = vv.n_variants - wbase; if (wn > K1_WIN) wn = K1_WIN;
+  st.contig = c; st.wbase = wbase; st.wn = (int)wn;
+  return true;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+template <bool EMIT>
+__global__ void __launch_bounds__(K1_THREADS) k1_window_kernel(ReadsView rv, VariantsView vv, int baseq, double isize_cutoff,
+                                                             u32* __restrict__ cnt, const u32* __restrict__ off,
+                                                             u32* __restrict__ t_rec, u32* __restrict__ t_var,
+                                                             u32* __restrict__ t_misc) {
+  __shared__ __align__(128) int32_t win[K1_WIN];
+  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ WindowState st;
+  __shared__ int s_bulk;                  // bytes in flight for this tile's reload (0 = no reload)
+  const int tid = threadIdx.x;
+  const int64_t R = rv.n_records;
+  const int64_t strip0 = (int64_t)blockIdx.x * (K1_THREADS * K1_TILES);
+  if (tid == 0) {
+    st.contig = -1; st.wbase = 0; st.wn = 0; s_bulk = 0;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  u32 parity = 0;
+  for (int t = 0; t < K1_TILES; ++t) {
+    const int64_t r0 = strip0 + (int64_t)t * K1_THREADS;
+    if (r0 >= R) break;
+    __syncthreads();                      // everyone is done with the slab of the previous tile
+    if (tid == 0) {
+      WindowState ns = st;
+      int bytes = 0;
+      if (window_for_tile(rv, vv, r0, win, ns)) {
+        st = ns;
+        int nb = ns.wn & ~3;              // elements moved by the bulk copy (16-byte granules)
+        bytes = nb * 4;
+        if (bytes > 0) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(smem_u32(win)), "l"(vv.pos + ns.wbase), "r"(bytes), "r"(smem_u32(&mbar)) : "memory");
+        }
+        for (int i = nb; i < ns.wn; ++i) win[i] = vv.pos[ns.wbase + i];     // < 4 tail elements
+      }
+      s_bulk = bytes;
+    }
+    __syncthreads();
+    if (s_bulk > 0) {
+      u32 done = 0;
+      while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(&mbar)), "r"(parity) : "memory");
+      }
+      parity ^= 1;
+    }
+    const int64_t r = r0 + tid;
+    if (r < R) {
+      WindowVP vp{vv.pos, win, st.wbase, st.wn};
+      int c = st.contig;
+      if (r >= rv.contig_rec_off[c + 1]) c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r);
+      if (!EMIT) {
+        cnt[r] = map_record<false>(rv, vv, vp, r, c, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr);
+      } else if (cnt[r] != 0) {
+        map_record<true>(rv, vv, vp, r, c, baseq, isize_cutoff, off[r], t_rec, t_var, t_misc);
+      }
+    }
+  }
+}
+#endif
+
 template <class B>
 struct Pipeline {
   B be;
+  int k1_mode = 1;            // 1: windowed K1 (shared-memory slab), 0: generic one-thread-per-record K1
   // ------------------------------------------------------------------ variants
   int nc = 0; int64_t V = 0; int vbits = 1;
   std::vector<int64_t> h_cvoff;
@@ -149,24 +244,60 @@ struct Pipeline {
     if (R >= (int64_t)0x7FFFFFFF) throw PhzError("more than 2^31-1 records in one map_reads call; split the BAM");
     u32* cnt = cand_cnt.ensure(R + 1);
     u32* off = cand_off.ensure(R + 2);
-    int ncg = nc;
     be.mark(0);
-    be.for_each(R, PHZ_LAMBDA(int64_t r) {
-      int c = upper_slot_i64(rv.contig_rec_off, ncg, r);
-      cnt[r] = map_record<false>(rv, vv, r, c, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr);
-    });
+    run_k1<false>(rv, vv, baseq, isize_cutoff, cnt, off, nullptr, nullptr, nullptr);
     be.mark(1);
     be.exclusive_scan_u32(cnt, off, R);
     n_cand = R > 0 ? (int64_t)fetch_u32(off + R) : 0;
     u32* tr = t_rec.ensure(n_cand); u32* tv = t_var.ensure(n_cand); u32* tm = t_misc.ensure(n_cand);
     be.mark(2);
-    be.for_each(R, PHZ_LAMBDA(int64_t r) {
-      if (cnt[r] == 0) return;
-      int c = upper_slot_i64(rv.contig_rec_off, ncg, r);
-      map_record<true>(rv, vv, r, c, baseq, isize_cutoff, off[r], tr, tv, tm);
-    });
+    run_k1<true>(rv, vv, baseq, isize_cutoff, cnt, off, tr, tv, tm);
     be.mark(3);
     return n_cand;
+  }
+
+  template <bool EMIT>
+  void run_k1(const ReadsView& rv, const VariantsView& vv, int baseq, double isize_cutoff, u32* cnt, const u32* off,
+              u32* tr, u32* tv, u32* tm) {
+    const int64_t R = rv.n_records;
+    if (R <= 0) return;
+    if (k1_mode == 1) {
+#ifdef __CUDACC__
+      int64_t strips = (R + (int64_t)K1_THREADS * K1_TILES - 1) / ((int64_t)K1_THREADS * K1_TILES);
+      k1_window_kernel<EMIT><<<(unsigned)strips, K1_THREADS, 0, be.stream>>>(rv, vv, baseq, isize_cutoff, cnt, off, tr, tv, tm);
+      PHZ_CUDA(cudaGetLastError());
+      be.launches++;
+#else
+      // host simulation of the same tiling / slab logic (the slab is a view of the array itself)
+      WindowState st{-1, 0, 0};
+      const int64_t strip = (int64_t)K1_THREADS * K1_TILES;
+      for (int64_t s0 = 0; s0 < R; s0 += strip) {
+        st = WindowState{-1, 0, 0};
+        for (int t = 0; t < K1_TILES; ++t) {
+          int64_t r0 = s0 + (int64_t)t * K1_THREADS;
+          if (r0 >= R) break;
+          window_for_tile(rv, vv, r0, vv.pos + st.wbase, st);
+          for (int64_t r = r0; r < r0 + K1_THREADS && r < R; ++r) {
+            WindowVP vp{vv.pos, vv.pos + st.wbase, st.wbase, st.wn};
+            int c = st.contig;
+            if (r >= rv.contig_rec_off[c + 1]) c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r);
+            if (!EMIT) cnt[r] = map_record<false>(rv, vv, vp, r, c, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr);
+            else if (cnt[r] != 0) map_record<true>(rv, vv, vp, r, c, baseq, isize_cutoff, off[r], tr, tv, tm);
+          }
+        }
+      }
+      be.launches++;
+#endif
+      return;
+    }
+    int ncg = nc;
+    be.for_each(R, PHZ_LAMBDA(int64_t r) {
+      if (EMIT && cnt[r] == 0) return;
+      int c = upper_slot_i64(rv.contig_rec_off, ncg, r);
+      GlobalVP vp{vv.pos};
+      if (!EMIT) cnt[r] = map_record<false>(rv, vv, vp, r, c, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr);
+      else map_record<true>(rv, vv, vp, r, c, baseq, isize_cutoff, off[r], tr, tv, tm);
+    });
   }
 
   // hist: u64[65536] on the device, bin = AS + 32768, counts the tuples the reference would print

@@ -34,7 +34,7 @@ class phz_reads(ctypes.Structure):
 EXPORTS = ["phz_last_error", "phz_backend_name", "phz_create", "phz_destroy", "phz_sync", "phz_set_variants",
            "phz_map_reads", "phz_map_reads_host", "phz_as_histogram", "phz_commit_bam", "phz_build_graph",
            "phz_phase", "phz_read_lists", "phz_array", "phz_download", "phz_counters", "phz_launch_counts",
-           "phz_set_profiling", "phz_map_times", "phz_stage_report"]
+           "phz_set_profiling", "phz_map_times", "phz_stage_report", "phz_set_option"]
 
 
 def _declare(lib):
@@ -59,6 +59,7 @@ def _declare(lib):
     lib.phz_set_profiling.argtypes = [c_void_p, c_int]
     lib.phz_map_times.argtypes = [c_void_p, POINTER(ctypes.c_float)]
     lib.phz_stage_report.argtypes = [c_void_p, c_char_p, c_int64]
+    lib.phz_set_option.argtypes = [c_void_p, c_char_p, c_int64]
     return lib
 
 
@@ -229,6 +230,9 @@ class Engine:
         ms = (ctypes.c_float * 3)()
         self._check(self.lib.phz_map_times(self.ctx, ms))
         return float(ms[0]), float(ms[1]), float(ms[2])
+
+    def set_option(self, name, value):
+        self._check(self.lib.phz_set_option(self.ctx, name.encode(), int(value)))
 
     def stage_report(self):
         """{stage: ms} accumulated since the last call (CUDA events; needs set_profiling(True))."""

@@ -1,4 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee gpurun_out/pytest_gpu.log
-timeout 1200 python bench.py --steps 3 --warmup 3 --no_cpu_baseline --profile > gpurun_out/prof_full.json 2> gpurun_out/prof_full.err; tail -c 2800 gpurun_out/prof_full.json; tail -3 gpurun_out/prof_full.err
+for m in 0 1; do
+timeout 1200 python bench.py --steps 3 --warmup 3 --no_cpu_baseline --no_e2e --k1_mode $m > gpurun_out/k1_mode$m.json 2> gpurun_out/k1_mode$m.err; python -c "
+import json;d=json.load(open('gpurun_out/k1_mode$m.json'));print('k1_mode',$m,d['ms_per_step'],d['roofline']['ms_count_scan_emit'],d['roofline']['frac'])"; tail -3 gpurun_out/k1_mode$m.err
+done

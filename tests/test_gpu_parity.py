@@ -84,3 +84,26 @@ def test_full_path_is_deterministic_and_consistent(gpu, tmp_path):
         assert m.shape[0] >= 2 and (np.diff(m.astype(np.int64)) > 0).all() and len(set(contig_of[m].tolist())) == 1
     fc = a.fb_cnt.reshape(-1, 2); fbc = a.fb_bcnt.reshape(-1, 2, 2)
     assert (fbc.sum(1) >= fc).all() and (fbc.max(1) <= fc).all()
+
+
+def test_windowed_k1_equals_generic_k1(gpu):
+    """The shared-memory/TMA K1 and the plain one-thread-per-record K1 must emit identical tuples
+    (whole-genome contig layout, ~1.2 M records, spliced + indels + clips)."""
+    from phaser_b200 import synth
+    g = synth.make_genome(61, 60000, exonic_frac=0.3, n_genes=4000)
+    vt = synth.to_variant_table_arrays(g)
+    rec = synth.make_reads(g, 6100, 600000)
+    rb = synth.to_read_batch(rec, len(vt.contigs), "b0")
+    d = gpu.upload_reads(rb)
+    out = {}
+    try:
+        for mode in (0, 1):
+            gpu.set_option("k1_mode", mode)
+            gpu.set_variants(vt)
+            n = gpu.map_reads(d, 10, 0.0)
+            out[mode] = (n, gpu.download("t_rec"), gpu.download("t_var"), gpu.download("t_misc"))
+    finally:
+        gpu.set_option("k1_mode", 1)
+    assert out[0][0] == out[1][0] and out[0][0] > 100000
+    for a, b in zip(out[0][1:], out[1][1:]):
+        assert np.array_equal(a, b)

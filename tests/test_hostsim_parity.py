@@ -35,3 +35,25 @@ def test_seeded_cases_match_oracle(hostsim, tmp_path, seed, n_bams, switch, mbs)
     assert not bad, "\n".join(bad)
     assert res.counters["n_tuples"] == ores.total_tuples
     assert abs(res.noise_e - ores.noise_e) == 0.0
+
+
+def test_windowed_k1_logic_equals_generic(hostsim):
+    """Slab selection + in-slab range search (shared with the CUDA kernel) against plain global search."""
+    import numpy as np
+    from phaser_b200 import synth
+    g = synth.make_genome(61, 6000, exonic_frac=0.3, n_genes=400, contigs=synth.GRCH38[19:22])
+    vt = synth.to_variant_table_arrays(g)
+    rb = synth.to_read_batch(synth.make_reads(g, 6100, 40000), len(vt.contigs), "b0")
+    d = hostsim.upload_reads(rb)
+    out = {}
+    try:
+        for mode in (0, 1):
+            hostsim.set_option("k1_mode", mode)
+            hostsim.set_variants(vt)
+            n = hostsim.map_reads(d, 10, 0.0)
+            out[mode] = (n, hostsim.download("t_rec"), hostsim.download("t_var"), hostsim.download("t_misc"))
+    finally:
+        hostsim.set_option("k1_mode", 1)
+    assert out[0][0] == out[1][0] and out[0][0] > 5000
+    for a, b in zip(out[0][1:], out[1][1:]):
+        assert np.array_equal(a, b)
