@@ -73,7 +73,8 @@ struct GlobalVP {
 };
 
 // A slab of the position array staged in shared memory (global indices [wbase, wbase+wn)); searches
-// that fall outside it go back to global memory.
+// that fall outside it go back to global memory.  32-bit local indices, branch-free halving (the trip
+// count is the same for every lane of a tile), short linear scan for the upper end.
 struct WindowVP {
   const int32_t* g;
   const int32_t* s;
@@ -84,13 +85,22 @@ struct WindowVP {
     return (k >= 0 && k < wn) ? s[k] : g[j];
   }
   PHZ_HD void range(int32_t lo_key, int32_t hi_key, int64_t v0, int64_t v1, int64_t& lo, int64_t& hi) const {
-    int64_t a = v0 > wbase ? v0 : wbase, b = v1 < wbase + wn ? v1 : wbase + wn;
+    int64_t a64 = v0 - wbase, b64 = v1 - wbase;
+    int a = a64 > 0 ? (int)a64 : 0, b = b64 < wn ? (int)b64 : wn;
     if (a < b) {
-      int64_t l = lower_bound_i32(s, a - wbase, b - wbase, lo_key) + wbase;
-      if ((l > a || a == v0) && (l < b || b == v1)) {
-        int64_t h = lower_bound_i32(s, l - wbase, b - wbase, hi_key) + wbase;
-        if (h < b || b == v1) { lo = l; hi = h; return; }
-        lo = l; hi = lower_bound_i32(g, b, v1, hi_key); return;
+      int l = a, len = b - a;
+      while (len > 0) {
+        int half = len >> 1, mid = l + half;
+        bool p = s[mid] < lo_key;
+        l = p ? mid + 1 : l;
+        len = p ? len - half - 1 : half;
+      }
+      if ((l > a || wbase + a == v0) && (l < b || wbase + b == v1)) {
+        int h = l;
+        while (h < b && s[h] < hi_key) ++h;
+        lo = wbase + l;
+        hi = (h < b || wbase + b == v1) ? wbase + h : lower_bound_i32(g, wbase + b, v1, hi_key);
+        return;
       }
     }
     lo = lower_bound_i32(g, v0, v1, lo_key);
@@ -109,49 +119,51 @@ PHZ_HD u32 map_record(const ReadsView& rv, const VariantsView& vv, const VP& vp,
   if (v0 == v1) return 0;
   const int32_t rpos = rv.pos[r];
   const u32 c0 = rv.cigar_off[r], c1 = rv.cigar_off[r + 1];
-  const u64 boff = rv.seq_off[r];
-  const int as16 = rv.aln_score[r];
   u32 n_out = 0;
   int seg = 0;
   u32 k = c0;
-  int64_t gp = 0;      // whole-read reference offset (genome_pos)
-  int64_t qp = 0;      // query offset (read_pos)
-  while (k <= c1) {
-    // one segment: ops [k, kend) up to (not including) the closing N or the end
+  int32_t gp = 0;      // whole-read reference offset (genome_pos)
+  int32_t qp = 0;      // query offset (read_pos)
+  while (true) {
+    // one segment: ops [kseg, kend) up to (not including) the closing N or the end
     const u32 kseg = k;
-    const int64_t seg_start = gp, q_start = qp;
-    int64_t seg_len = 0;
-    u32 kk = k;
-    for (; kk < c1; ++kk) {
-      u32 c = rv.cigar[kk]; int op = c & 15; int64_t n = c >> 4;
+    const int32_t seg_start = gp, q_start = qp;
+    int32_t g_end = gp, q_end = qp;
+    for (; k < c1; ++k) {
+      u32 c = rv.cigar[k]; int op = c & 15; int32_t n = (int32_t)(c >> 4);
       if (op == OP_N) break;
-      if (op == OP_M || op == OP_EQ || op == OP_X || op == OP_D) seg_len += n;
+      if (op == OP_M || op == OP_EQ || op == OP_X) { g_end += n; q_end += n; }
+      else if (op == OP_D) g_end += n;
+      else if (op == OP_I || op == OP_S) q_end += n;
     }
-    const u32 kend = kk;
+    const u32 kend = k;
+    const int32_t seg_len = g_end - seg_start;           // len(pseudo_read): M/=/X and D
     if (seg_len > 0) {
-      // candidates: variants with seg_start <= pos-rpos and pos-rpos+1 <= seg_start+seg_len
-      int64_t lo_pos = (int64_t)rpos + seg_start, hi_pos = lo_pos + seg_len;   // [lo_pos, hi_pos)
+      // candidates: het sites with 0 <= pos-(rpos+seg_start) < seg_len
+      const int64_t lo_pos = (int64_t)rpos + seg_start, hi_pos = lo_pos + seg_len;
       if (lo_pos < 2147483647LL) {
-        int32_t hi32 = hi_pos > 2147483647LL ? 2147483647 : (int32_t)hi_pos;
+        const int32_t hi32 = hi_pos > 2147483647LL ? 2147483647 : (int32_t)hi_pos;
         int64_t lo, hi;
         vp.range((int32_t)lo_pos, hi32, v0, v1, lo, hi);
         if (!EMIT) {
           n_out += (u32)(hi - lo);
-        } else {
+        } else if (hi > lo) {
+          const u64 boff = rv.seq_off[r];
+          const int as16 = rv.aln_score[r];
           for (int64_t j = lo; j < hi; ++j) {
-            const int64_t st = (int64_t)vp.at(j) - lo_pos;       // offset in pseudo_read
+            const int32_t st = (int32_t)((int64_t)vp.at(j) - lo_pos);       // offset in pseudo_read
             // locate pseudo_read[st] and the insertion keyed st (keys are whole-read offsets: Q3)
-            int64_t g = seg_start, q = q_start;
-            int base = -1;            // -1: not found (cannot happen), 16: deletion placeholder
-            int64_t ins_q = -1, ins_n = 0;
+            int32_t g = seg_start, q = q_start;
+            int base = -1;            // 16: deletion placeholder
+            int32_t ins_q = -1, ins_n = 0;
             for (u32 x = kseg; x < kend; ++x) {
-              u32 c = rv.cigar[x]; int op = c & 15; int64_t n = c >> 4;
+              u32 c = rv.cigar[x]; int op = c & 15; int32_t n = (int32_t)(c >> 4);
               if (op == OP_M || op == OP_EQ || op == OP_X) {
-                int64_t sp = g - seg_start;
-                if (st >= sp && st < sp + n) base = masked_base(rv, boff, (int)(q + (st - sp)), baseq);
+                int32_t sp = g - seg_start;
+                if (st >= sp && st < sp + n) base = masked_base(rv, boff, q + (st - sp), baseq);
                 g += n; q += n;
               } else if (op == OP_D) {
-                int64_t sp = g - seg_start;
+                int32_t sp = g - seg_start;
                 if (st >= sp && st < sp + n) base = 16;
                 g += n;
               } else if (op == OP_I) {
@@ -164,8 +176,8 @@ PHZ_HD u32 map_record(const ReadsView& rv, const VariantsView& vv, const VP& vp,
             // string = [base] + inserted bases, minus every 'D'
             int n_chars = 0, first = 0;
             if (base != 16 && base != BASE_D && base >= 0) { first = base; n_chars = 1; }
-            for (int64_t z = 0; z < ins_n; ++z) {
-              int b = masked_base(rv, boff, (int)(ins_q + z), baseq);
+            for (int32_t z = 0; z < ins_n; ++z) {
+              int b = masked_base(rv, boff, ins_q + z, baseq);
               if (b != BASE_D) { if (n_chars == 0) first = b; n_chars++; }
             }
             int cls, multi = 0;
@@ -185,15 +197,9 @@ PHZ_HD u32 map_record(const ReadsView& rv, const VariantsView& vv, const VP& vp,
       }
     }
     if (kend >= c1) break;
-    // closing N: advance reference, open the next segment
-    gp = seg_start; qp = q_start;
-    for (u32 x = kseg; x < kend; ++x) {
-      u32 c = rv.cigar[x]; int op = c & 15; int64_t n = c >> 4;
-      if (op == OP_M || op == OP_EQ || op == OP_X) { gp += n; qp += n; }
-      else if (op == OP_D) gp += n;
-      else if (op == OP_I || op == OP_S) qp += n;
-    }
-    gp += (int64_t)(rv.cigar[kend] >> 4);
+    // closing N: advance the reference, open the next segment
+    gp = g_end + (int32_t)(rv.cigar[kend] >> 4);
+    qp = q_end;
     k = kend + 1;
     seg++;
   }

@@ -143,10 +143,127 @@ __global__ void __launch_bounds__(K1_THREADS) k1_window_kernel(ReadsView rv, Var
 }
 #endif
 
+// ----------------------------------------------------------------------------- K1, fused single pass
+// One CTA = one tile of KF_THREADS consecutive records.  A tiny pre-pass stores, per tile, where its
+// het-site slab starts; the CTA's first thread turns that into one TMA bulk copy while the others are
+// already loading their records.  Every thread counts its candidates in the slab, the CTA scans the
+// counts, a decoupled look-back over per-tile status words (aggregate / inclusive prefix) yields the
+// tile's global output offset, and the threads that have candidates emit them -- in (record, segment,
+// variant) order, without a second kernel, without per-record count/offset arrays in HBM.
+constexpr int KF_THREADS = 256;
+constexpr int KF_WIN = 1024;                      // het-site positions per slab (4 KB)
+constexpr u64 KF_FLAG_AGG = 1ull << 62, KF_FLAG_PREFIX = 2ull << 62, KF_VALUE_MASK = (1ull << 62) - 1;
+
+struct TileInfo { u32 wbase; u32 contig_wn; };    // contig << 16 | wn
+
+PHZ_HD TileInfo tile_info_for(const ReadsView& rv, const VariantsView& vv, int64_t r0) {
+  int c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r0);
+  int64_t v0 = vv.contig_var_off[c], v1 = vv.contig_var_off[c + 1];
+  int64_t wlo = lower_bound_i32(vv.pos, v0, v1, rv.pos[r0]);
+  int64_t wbase = wlo & ~(int64_t)3;              // 16-byte aligned source for the bulk copy
+  int64_t wn = vv.n_variants - wbase; if (wn > KF_WIN) wn = KF_WIN;
+  TileInfo ti; ti.wbase = (u32)wbase; ti.contig_wn = ((u32)c << 16) | (u32)wn;
+  return ti;
+}
+
+#ifdef __CUDACC__
+__global__ void __launch_bounds__(KF_THREADS) k1_fused_kernel(ReadsView rv, VariantsView vv, const TileInfo* __restrict__ tiles,
+                                                             int baseq, double isize_cutoff, u32* __restrict__ t_rec,
+                                                             u32* __restrict__ t_var, u32* __restrict__ t_misc, u64 capacity,
+                                                             unsigned long long* tile_status, u32* ticket,
+                                                             unsigned long long* total_out, int64_t n_tiles) {
+  __shared__ __align__(128) int32_t win[KF_WIN];
+  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ u32 warp_sum[KF_THREADS / 32];
+  __shared__ unsigned long long s_base;
+  __shared__ u32 s_tile, s_wbase, s_cwn;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    u32 t = atomicAdd(ticket, 1u);                // tiles are taken in launch order: predecessors are running
+    TileInfo ti = tiles[t];
+    s_tile = t; s_wbase = ti.wbase; s_cwn = ti.contig_wn;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    int wn = (int)(ti.contig_wn & 0xFFFF), nb = wn & ~3, bytes = nb * 4;
+    if (bytes > 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(win)), "l"(vv.pos + ti.wbase), "r"(bytes), "r"(smem_u32(&mbar)) : "memory");
+    }
+    for (int i = nb; i < wn; ++i) win[i] = vv.pos[(int64_t)ti.wbase + i];
+  }
+  __syncthreads();
+  const int64_t tile = s_tile;
+  const int wn = (int)(s_cwn & 0xFFFF);
+  int contig = (int)(s_cwn >> 16);
+  const int64_t r = tile * KF_THREADS + tid;
+  const bool live = r < rv.n_records;
+  if (live && r >= rv.contig_rec_off[contig + 1]) contig = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r);
+  if ((wn & ~3) > 0) {
+    u32 done = 0;
+    while (!done) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0) : "memory");
+    }
+  }
+  WindowVP vp{vv.pos, win, (int64_t)s_wbase, wn};
+  u32 cnt = live ? map_record<false>(rv, vv, vp, r, contig, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr) : 0u;
+  // ---- CTA exclusive scan of the counts
+  u32 incl = cnt;
+  #pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) warp_sum[warp] = incl;
+  __syncthreads();
+  u32 warp_base = 0, cta_total = 0;
+  #pragma unroll
+  for (int w = 0; w < KF_THREADS / 32; ++w) { u32 v = warp_sum[w]; if (w < warp) warp_base += v; cta_total += v; }
+  const u32 excl_in_cta = warp_base + incl - cnt;
+  // ---- decoupled look-back: global offset of this tile
+  if (warp == 0) {
+    volatile unsigned long long* st = tile_status;
+    if (lane == 0) st[tile] = (tile == 0 ? KF_FLAG_PREFIX : KF_FLAG_AGG) | (unsigned long long)cta_total;
+    unsigned long long excl = 0;
+    if (tile > 0) {
+      int64_t idx = tile - 1;
+      while (true) {
+        int64_t j = idx - lane;
+        unsigned long long sw = KF_FLAG_PREFIX;                  // before tile 0: prefix 0
+        if (j >= 0) {
+          u32 spins = 0;
+          do {
+            sw = st[j];
+            if (++spins > (1u << 24)) { atomicOr(&ticket[1], 1u); sw = KF_FLAG_PREFIX; }   // never hang the GPU
+          } while ((sw >> 62) == 0);
+        }
+        unsigned pm = __ballot_sync(0xffffffffu, (sw >> 62) == 2);
+        unsigned long long val = sw & KF_VALUE_MASK;
+        if (pm) { int first = __ffs(pm) - 1; if (lane > first) val = 0; }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        excl += val;
+        if (pm) break;
+        idx -= 32;
+      }
+      if (lane == 0) st[tile] = KF_FLAG_PREFIX | (excl + cta_total);
+    }
+    if (lane == 0) {
+      s_base = excl;
+      if (tile == n_tiles - 1) *total_out = excl + cta_total;
+    }
+  }
+  __syncthreads();
+  if (cnt != 0) {
+    const u64 o = s_base + excl_in_cta;
+    if (o + cnt <= capacity) map_record<true>(rv, vv, vp, r, contig, baseq, isize_cutoff, o, t_rec, t_var, t_misc);
+  }
+}
+#endif
+
 template <class B>
 struct Pipeline {
   B be;
-  int k1_mode = 1;            // 1: windowed K1 (shared-memory slab), 0: generic one-thread-per-record K1
+  int k1_mode = 2;            // 2: fused single-pass K1 (default), 1: windowed two-pass K1, 0: generic two-pass K1
+  Buf<B, TileInfo> tile_info; Buf<B, u64> tile_status; Buf<B, u32> k1_ticket;
   // ------------------------------------------------------------------ variants
   int nc = 0; int64_t V = 0; int vbits = 1;
   std::vector<int64_t> h_cvoff;
@@ -190,7 +307,7 @@ struct Pipeline {
 
   Pipeline() {
     B* b = &be;
-    d_cvoff.bind(b); d_croff.bind(b); vcontig.bind(b);
+    d_cvoff.bind(b); d_croff.bind(b); vcontig.bind(b); tile_info.bind(b); tile_status.bind(b); k1_ticket.bind(b);
     cand_cnt.bind(b); cand_off.bind(b); t_rec.bind(b); t_var.bind(b); t_misc.bind(b); keep_flag.bind(b); keep_off.bind(b);
     g_frag.bind(b); g_var.bind(b); g_cb.bind(b);
     vfirst.bind(b); ncls.bind(b); setsize.bind(b); vb_cnt.bind(b); cfirst.bind(b); crank.bind(b); vrank.bind(b); noise.bind(b);
@@ -242,6 +359,7 @@ struct Pipeline {
     VariantsView vv{V, nc, d_cvoff.p, vpos, va0, va1};
     const int64_t R = rv.n_records;
     if (R >= (int64_t)0x7FFFFFFF) throw PhzError("more than 2^31-1 records in one map_reads call; split the BAM");
+    if (k1_mode == 2) return map_reads_fused(rv, vv, baseq, isize_cutoff);
     u32* cnt = cand_cnt.ensure(R + 1);
     u32* off = cand_off.ensure(R + 2);
     be.mark(0);
@@ -253,6 +371,54 @@ struct Pipeline {
     be.mark(2);
     run_k1<true>(rv, vv, baseq, isize_cutoff, cnt, off, tr, tv, tm);
     be.mark(3);
+    return n_cand;
+  }
+
+  // Fused single-pass K1.  Output capacity is what the buffers already hold (or a first guess); if the
+  // exact total turns out larger the buffers grow and the kernel runs once more.
+  int64_t map_reads_fused(const ReadsView& rv, const VariantsView& vv, int baseq, double isize_cutoff) {
+    const int64_t R = rv.n_records;
+    if (R <= 0) { n_cand = 0; be.mark(0); be.mark(1); be.mark(2); be.mark(3); return 0; }
+    const int64_t n_tiles = (R + KF_THREADS - 1) / KF_THREADS;
+    TileInfo* ti = tile_info.ensure(n_tiles);
+    be.mark(0);
+    be.for_each(n_tiles, PHZ_LAMBDA(int64_t t) { ti[t] = tile_info_for(rv, vv, t * KF_THREADS); });
+    be.mark(1); be.mark(2);
+    size_t cap = t_rec.cap < t_var.cap ? t_rec.cap : t_var.cap; if (t_misc.cap < cap) cap = t_misc.cap;
+    if (cap == 0) cap = (size_t)(R / 2 + (1 << 20));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      u32* tr = t_rec.ensure(cap); u32* tv = t_var.ensure(cap); u32* tm = t_misc.ensure(cap);
+      u64 total = 0;
+#ifdef __CUDACC__
+      u64* st = tile_status.ensure(n_tiles + 1); be.memset0(st, (n_tiles + 1) * sizeof(u64));
+      u32* tk = k1_ticket.ensure(4); be.memset0(tk, 4 * sizeof(u32));
+      k1_fused_kernel<<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, tr, tv, tm, (u64)cap,
+                                                                      st, tk, st + n_tiles, n_tiles);
+      PHZ_CUDA(cudaGetLastError());
+      be.launches++;
+      be.mark(3);
+      be.d2h(&total, st + n_tiles, sizeof(u64));
+      if (fetch_u32(tk + 1) != 0) throw PhzError("K1 look-back timed out (a predecessor tile never published its prefix)");
+#else
+      // host simulation: same tile descriptors, slab logic and emission order, tiles in sequence
+      for (int64_t t = 0; t < n_tiles; ++t) {
+        int wn = (int)(ti[t].contig_wn & 0xFFFF); int c0 = (int)(ti[t].contig_wn >> 16);
+        WindowVP vp{vv.pos, vv.pos + ti[t].wbase, (int64_t)ti[t].wbase, wn};
+        for (int64_t r = t * KF_THREADS; r < (t + 1) * KF_THREADS && r < R; ++r) {
+          int c = c0;
+          if (r >= rv.contig_rec_off[c + 1]) c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r);
+          u32 cnt = map_record<false>(rv, vv, vp, r, c, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr);
+          if (cnt && total + cnt <= cap) map_record<true>(rv, vv, vp, r, c, baseq, isize_cutoff, total, tr, tv, tm);
+          total += cnt;
+        }
+      }
+      be.launches++;
+#endif
+      if (total >= 0xFFFFFFF0ull) throw PhzError("more than 2^32 candidate tuples in one map_reads call; split the BAM");
+      n_cand = (int64_t)total;
+      if (total <= cap) break;
+      cap = (size_t)total;
+    }
     return n_cand;
   }
 
