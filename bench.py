@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--cpu_pairs", type=int, default=40_000, help="bounded sample for the CPU baseline")
     ap.add_argument("--no_e2e", action="store_true")
     ap.add_argument("--no_cpu_baseline", action="store_true")
-    ap.add_argument("--k1_mode", type=int, default=2, help="2 fused single-pass K1 (default), 1 windowed two-pass, 0 generic two-pass")
+    ap.add_argument("--k1_mode", type=int, default=3, help="3 tile kernel + permute (default), 2 fused look-back, 1 windowed two-pass, 0 generic two-pass")
     ap.add_argument("--profile", action="store_true", help="add per-stage CUDA-event times of one extra step")
     return ap.parse_args()
 

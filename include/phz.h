@@ -101,9 +101,10 @@ int phz_download(phz_ctx* ctx, const char* name, void* h_dst, int64_t dst_bytes)
 /* counters[16]: n_tuples, entries, groups, pairs, distinct pairs, edges, dropped, members, blocks,
  * hard blocks, final blocks, read-list entries, n_candidates, n_bams, 0, 0 */
 int phz_counters(phz_ctx* ctx, int64_t* counters);
-/* Tuning / A-B switches.  "k1_mode": 2 = fused single-pass K1 (het-site slab staged in shared memory by
- * a TMA bulk copy, CTA scan + decoupled look-back for the output offsets; default), 1 = windowed
- * two-pass K1 (count, scan, emit), 0 = generic two-pass K1 (searches in global memory). */
+/* Tuning / A-B switches.  "k1_mode": 3 = tile kernel (het-site slab staged in shared memory by a TMA
+ * bulk copy, CTA scan, one atomic cursor per tile, dense coalesced emission) + streaming permute into
+ * canonical order (default); 2 = fused single pass with decoupled look-back; 1 = windowed two-pass
+ * (count, scan, emit); 0 = generic two-pass (searches in global memory).  All four emit identical tuples. */
 int phz_set_option(phz_ctx* ctx, const char* name, int64_t value);
 /* CUDA-event timing of the K1 passes of the LAST phz_map_reads call on the context's stream:
  * ms[0] = count pass, ms[1] = scan + size readback, ms[2] = emit pass (-1 when profiling is off). */

@@ -108,12 +108,15 @@ struct WindowVP {
   }
 };
 
-// Walks one record.  EMIT=false: returns the number of candidate (segment, variant) pairs.
-// EMIT=true: writes one tuple per candidate starting at out index `o` (class CLS_NONE when the
-// reference would print nothing) and returns the number written.
-template <bool EMIT, class VP>
+// Walks one record.
+// MODE 0 (count): returns the number of candidate (segment, variant) pairs.
+// MODE 1 (emit):  writes one tuple per candidate starting at out index `o` (class CLS_NONE when the
+//                 reference would print nothing) and returns the number written.
+// MODE 2 (k-th):  `o` is the ordinal of ONE candidate of this record; writes that tuple at out index 0.
+template <int MODE, class VP>
 PHZ_HD u32 map_record(const ReadsView& rv, const VariantsView& vv, const VP& vp, int64_t r, int contig, int baseq,
                       double isize_cutoff, u64 o, u32* t_rec, u32* t_var, u32* t_misc) {
+  constexpr bool EMIT = MODE != 0;
   if (!isize_ok(rv.tlen[r], isize_cutoff)) return 0;
   const int64_t v0 = vv.contig_var_off[contig], v1 = vv.contig_var_off[contig + 1];
   if (v0 == v1) return 0;
@@ -147,9 +150,12 @@ PHZ_HD u32 map_record(const ReadsView& rv, const VariantsView& vv, const VP& vp,
         vp.range((int32_t)lo_pos, hi32, v0, v1, lo, hi);
         if (!EMIT) {
           n_out += (u32)(hi - lo);
+        } else if (MODE == 2 && (u64)n_out + (u64)(hi - lo) <= o) {
+          n_out += (u32)(hi - lo);                 // the wanted candidate is in a later segment
         } else if (hi > lo) {
           const u64 boff = rv.seq_off[r];
           const int as16 = rv.aln_score[r];
+          if (MODE == 2) { lo += (int64_t)(o - n_out); hi = lo + 1; }
           for (int64_t j = lo; j < hi; ++j) {
             const int32_t st = (int32_t)((int64_t)vp.at(j) - lo_pos);       // offset in pseudo_read
             // locate pseudo_read[st] and the insertion keyed st (keys are whole-read offsets: Q3)
@@ -188,11 +194,13 @@ PHZ_HD u32 map_record(const ReadsView& rv, const VariantsView& vv, const VP& vp,
               else if (first == vv.a1[j]) cls = CLS_A1;
               else cls = CLS_OTHER;
             } else { cls = CLS_OTHER; multi = 1; }
-            t_rec[o + n_out] = (u32)r;
-            t_var[o + n_out] = (u32)j;
-            t_misc[o + n_out] = pack_misc(cls, multi, first, seg, as16);
+            const u64 w = (MODE == 2) ? 0 : o + n_out;
+            t_rec[w] = (u32)r;
+            t_var[w] = (u32)j;
+            t_misc[w] = pack_misc(cls, multi, first, seg, as16);
             n_out++;
           }
+          if (MODE == 2) return 1;
         }
       }
     }

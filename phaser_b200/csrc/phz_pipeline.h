@@ -134,9 +134,9 @@ __global__ void __launch_bounds__(K1_THREADS) k1_window_kernel(ReadsView rv, Var
       int c = st.contig;
       if (r >= rv.contig_rec_off[c + 1]) c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r);
       if (!EMIT) {
-        cnt[r] = map_record<false>(rv, vv, vp, r, c, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr);
+        cnt[r] = map_record<0>(rv, vv, vp, r, c, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr);
       } else if (cnt[r] != 0) {
-        map_record<true>(rv, vv, vp, r, c, baseq, isize_cutoff, off[r], t_rec, t_var, t_misc);
+        map_record<1>(rv, vv, vp, r, c, baseq, isize_cutoff, off[r], t_rec, t_var, t_misc);
       }
     }
   }
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(KF_THREADS) k1_fused_kernel(ReadsView rv, Vari
     }
   }
   WindowVP vp{vv.pos, win, (int64_t)s_wbase, wn};
-  u32 cnt = live ? map_record<false>(rv, vv, vp, r, contig, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr) : 0u;
+  u32 cnt = live ? map_record<0>(rv, vv, vp, r, contig, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr) : 0u;
   // ---- CTA exclusive scan of the counts
   u32 incl = cnt;
   #pragma unroll
@@ -254,7 +254,89 @@ __global__ void __launch_bounds__(KF_THREADS) k1_fused_kernel(ReadsView rv, Vari
   __syncthreads();
   if (cnt != 0) {
     const u64 o = s_base + excl_in_cta;
-    if (o + cnt <= capacity) map_record<true>(rv, vv, vp, r, contig, baseq, isize_cutoff, o, t_rec, t_var, t_misc);
+    if (o + cnt <= capacity) map_record<1>(rv, vv, vp, r, contig, baseq, isize_cutoff, o, t_rec, t_var, t_misc);
+  }
+}
+#endif
+
+// ----------------------------------------------------------------------------- K1, tile kernel
+// Same slab / count / CTA scan as the fused kernel, but (a) a tile takes its output range from ONE
+// atomic cursor (no waiting on other tiles) and records (base, count) in a tile table, and (b) the
+// emission is DENSE: candidate i of the tile goes to thread i (binary search over the tile's 256
+// running offsets in shared memory), so all lanes gather SEQ/QUAL bytes and the stores are fully
+// coalesced.  A scan over the tile table then gives the canonical offsets and a streaming permute
+// moves each tile's block into (record, segment, variant) order.
+#ifdef __CUDACC__
+__global__ void __launch_bounds__(KF_THREADS) k1_tile_kernel(ReadsView rv, VariantsView vv, const TileInfo* __restrict__ tiles,
+                                                            int baseq, double isize_cutoff, u32* __restrict__ s_rec,
+                                                            u32* __restrict__ s_var, u32* __restrict__ s_misc, u64 capacity,
+                                                            unsigned long long* cursor, u32* __restrict__ tile_base,
+                                                            u32* __restrict__ tile_cnt) {
+  __shared__ __align__(128) int32_t win[KF_WIN];
+  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ u32 warp_sum[KF_THREADS / 32];
+  __shared__ u32 excl_of[KF_THREADS + 1];
+  __shared__ unsigned long long s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t tile = blockIdx.x;
+  const TileInfo ti = tiles[tile];
+  const int wn = (int)(ti.contig_wn & 0xFFFF);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    int nb = wn & ~3, bytes = nb * 4;
+    if (bytes > 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(win)), "l"(vv.pos + ti.wbase), "r"(bytes), "r"(smem_u32(&mbar)) : "memory");
+    }
+    for (int i = nb; i < wn; ++i) win[i] = vv.pos[(int64_t)ti.wbase + i];
+  }
+  const int64_t r0 = tile * KF_THREADS;
+  const int64_t r = r0 + tid;
+  const bool live = r < rv.n_records;
+  const int contig0 = (int)(ti.contig_wn >> 16);
+  const int64_t contig0_end = rv.contig_rec_off[contig0 + 1];
+  int contig = contig0;
+  if (live && r >= contig0_end) contig = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r);
+  __syncthreads();                                   // mbarrier initialised, tail elements visible
+  if ((wn & ~3) > 0) {
+    u32 done = 0;
+    while (!done) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0) : "memory");
+    }
+  }
+  WindowVP vp{vv.pos, win, (int64_t)ti.wbase, wn};
+  const u32 cnt = live ? map_record<0>(rv, vv, vp, r, contig, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr) : 0u;
+  // ---- CTA exclusive scan of the counts
+  u32 incl = cnt;
+  #pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) warp_sum[warp] = incl;
+  __syncthreads();
+  u32 warp_base = 0, cta_total = 0;
+  #pragma unroll
+  for (int w = 0; w < KF_THREADS / 32; ++w) { u32 v = warp_sum[w]; if (w < warp) warp_base += v; cta_total += v; }
+  excl_of[tid] = warp_base + incl - cnt;
+  if (tid == 0) {
+    excl_of[KF_THREADS] = cta_total;
+    unsigned long long b = cta_total ? atomicAdd(cursor, (unsigned long long)cta_total) : 0ull;
+    s_base = b;
+    tile_base[tile] = (u32)b; tile_cnt[tile] = cta_total;
+  }
+  __syncthreads();
+  const u64 base = s_base;
+  if (cta_total == 0 || base + cta_total > capacity) return;
+  // ---- dense emission: candidate i of the tile -> thread i
+  for (u32 i = (u32)tid; i < cta_total; i += KF_THREADS) {
+    int lo = 0, hi = KF_THREADS;                      // last record index with excl_of <= i
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (excl_of[mid] <= i) lo = mid; else hi = mid; }
+    const int64_t rr = r0 + lo;
+    int c = contig0;
+    if (rr >= contig0_end) c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, rr);
+    map_record<2>(rv, vv, vp, rr, c, baseq, isize_cutoff, (u64)(i - excl_of[lo]), s_rec + base + i, s_var + base + i,
+                  s_misc + base + i);
   }
 }
 #endif
@@ -262,7 +344,8 @@ __global__ void __launch_bounds__(KF_THREADS) k1_fused_kernel(ReadsView rv, Vari
 template <class B>
 struct Pipeline {
   B be;
-  int k1_mode = 2;            // 2: fused single-pass K1 (default), 1: windowed two-pass K1, 0: generic two-pass K1
+  int k1_mode = 3;            // 3: tile kernel + permute (default), 2: fused look-back, 1: windowed two-pass, 0: generic two-pass
+  Buf<B, u32> s_rec, s_var, s_misc, tile_base, tile_cnt, tile_canon;
   Buf<B, TileInfo> tile_info; Buf<B, u64> tile_status; Buf<B, u32> k1_ticket;
   // ------------------------------------------------------------------ variants
   int nc = 0; int64_t V = 0; int vbits = 1;
@@ -308,6 +391,7 @@ struct Pipeline {
   Pipeline() {
     B* b = &be;
     d_cvoff.bind(b); d_croff.bind(b); vcontig.bind(b); tile_info.bind(b); tile_status.bind(b); k1_ticket.bind(b);
+    s_rec.bind(b); s_var.bind(b); s_misc.bind(b); tile_base.bind(b); tile_cnt.bind(b); tile_canon.bind(b);
     cand_cnt.bind(b); cand_off.bind(b); t_rec.bind(b); t_var.bind(b); t_misc.bind(b); keep_flag.bind(b); keep_off.bind(b);
     g_frag.bind(b); g_var.bind(b); g_cb.bind(b);
     vfirst.bind(b); ncls.bind(b); setsize.bind(b); vb_cnt.bind(b); cfirst.bind(b); crank.bind(b); vrank.bind(b); noise.bind(b);
@@ -359,6 +443,7 @@ struct Pipeline {
     VariantsView vv{V, nc, d_cvoff.p, vpos, va0, va1};
     const int64_t R = rv.n_records;
     if (R >= (int64_t)0x7FFFFFFF) throw PhzError("more than 2^31-1 records in one map_reads call; split the BAM");
+    if (k1_mode == 3) return map_reads_tiles(rv, vv, baseq, isize_cutoff);
     if (k1_mode == 2) return map_reads_fused(rv, vv, baseq, isize_cutoff);
     u32* cnt = cand_cnt.ensure(R + 1);
     u32* off = cand_off.ensure(R + 2);
@@ -370,6 +455,69 @@ struct Pipeline {
     u32* tr = t_rec.ensure(n_cand); u32* tv = t_var.ensure(n_cand); u32* tm = t_misc.ensure(n_cand);
     be.mark(2);
     run_k1<true>(rv, vv, baseq, isize_cutoff, cnt, off, tr, tv, tm);
+    be.mark(3);
+    return n_cand;
+  }
+
+  // Tile kernel + permute (see k1_tile_kernel).  Scratch capacity is what the buffers already hold (or a
+  // first guess); if the exact total turns out larger the buffers grow and the kernel runs once more.
+  int64_t map_reads_tiles(const ReadsView& rv, const VariantsView& vv, int baseq, double isize_cutoff) {
+    const int64_t R = rv.n_records;
+    if (R <= 0) { n_cand = 0; be.mark(0); be.mark(1); be.mark(2); be.mark(3); return 0; }
+    const int64_t n_tiles = (R + KF_THREADS - 1) / KF_THREADS;
+    TileInfo* ti = tile_info.ensure(n_tiles);
+    u32* tb = tile_base.ensure(n_tiles + 1); u32* tc = tile_cnt.ensure(n_tiles + 1); u32* tn = tile_canon.ensure(n_tiles + 2);
+    be.mark(0);
+    be.for_each(n_tiles, PHZ_LAMBDA(int64_t t) { ti[t] = tile_info_for(rv, vv, t * KF_THREADS); });
+    be.mark(1);
+    size_t cap = s_rec.cap < s_var.cap ? s_rec.cap : s_var.cap; if (s_misc.cap < cap) cap = s_misc.cap;
+    if (cap == 0) cap = (size_t)(R / 2 + (1 << 20));
+    u64 total = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      u32* sr = s_rec.ensure(cap); u32* sv = s_var.ensure(cap); u32* sm = s_misc.ensure(cap);
+      total = 0;
+#ifdef __CUDACC__
+      u64* cur = tile_status.ensure(2); be.memset0(cur, 2 * sizeof(u64));
+      k1_tile_kernel<<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, sr, sv, sm, (u64)cap,
+                                                                     cur, tb, tc);
+      PHZ_CUDA(cudaGetLastError());
+      be.launches++;
+      be.d2h(&total, cur, sizeof(u64));
+#else
+      // host simulation: same tile descriptors, slab logic and k-th candidate emission, tiles in sequence
+      for (int64_t t = 0; t < n_tiles; ++t) {
+        int wn = (int)(ti[t].contig_wn & 0xFFFF); int c0 = (int)(ti[t].contig_wn >> 16);
+        WindowVP vp{vv.pos, vv.pos + ti[t].wbase, (int64_t)ti[t].wbase, wn};
+        u32 tile_total = 0;
+        for (int64_t r = t * KF_THREADS; r < (t + 1) * KF_THREADS && r < R; ++r) {
+          int c = c0;
+          if (r >= rv.contig_rec_off[c + 1]) c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r);
+          u32 cnt = map_record<0>(rv, vv, vp, r, c, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr);
+          if (total + tile_total + cnt <= cap)
+            for (u32 k = 0; k < cnt; ++k) {
+              u64 w = total + tile_total + k;
+              map_record<2>(rv, vv, vp, r, c, baseq, isize_cutoff, k, sr + w, sv + w, sm + w);
+            }
+          tile_total += cnt;
+        }
+        tb[t] = (u32)total; tc[t] = tile_total; total += tile_total;
+      }
+      be.launches++;
+#endif
+      if (total >= 0xFFFFFFF0ull) throw PhzError("more than 2^32 candidate tuples in one map_reads call; split the BAM");
+      if (total <= cap) break;
+      cap = (size_t)total;
+    }
+    n_cand = (int64_t)total;
+    be.mark(2);
+    // canonical order: tile t's block moves from tile_base[t] (arrival order) to the running sum of counts
+    be.exclusive_scan_u32(tc, tn, n_tiles);
+    u32* tr = t_rec.ensure(n_cand); u32* tv = t_var.ensure(n_cand); u32* tm = t_misc.ensure(n_cand);
+    const u32* sr = s_rec.p; const u32* sv = s_var.p; const u32* sm = s_misc.p;
+    be.for_each_warp(n_tiles, PHZ_LAMBDA_WARP(int64_t t, int lane, int nlanes) {
+      u32 n = tc[t]; u32 src = tb[t], dst = tn[t];
+      for (u32 i = (u32)lane; i < n; i += (u32)nlanes) { tr[dst + i] = sr[src + i]; tv[dst + i] = sv[src + i]; tm[dst + i] = sm[src + i]; }
+    });
     be.mark(3);
     return n_cand;
   }
@@ -407,8 +555,8 @@ struct Pipeline {
         for (int64_t r = t * KF_THREADS; r < (t + 1) * KF_THREADS && r < R; ++r) {
           int c = c0;
           if (r >= rv.contig_rec_off[c + 1]) c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r);
-          u32 cnt = map_record<false>(rv, vv, vp, r, c, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr);
-          if (cnt && total + cnt <= cap) map_record<true>(rv, vv, vp, r, c, baseq, isize_cutoff, total, tr, tv, tm);
+          u32 cnt = map_record<0>(rv, vv, vp, r, c, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr);
+          if (cnt && total + cnt <= cap) map_record<1>(rv, vv, vp, r, c, baseq, isize_cutoff, total, tr, tv, tm);
           total += cnt;
         }
       }
@@ -447,8 +595,8 @@ struct Pipeline {
             WindowVP vp{vv.pos, vv.pos + st.wbase, st.wbase, st.wn};
             int c = st.contig;
             if (r >= rv.contig_rec_off[c + 1]) c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r);
-            if (!EMIT) cnt[r] = map_record<false>(rv, vv, vp, r, c, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr);
-            else if (cnt[r] != 0) map_record<true>(rv, vv, vp, r, c, baseq, isize_cutoff, off[r], tr, tv, tm);
+            if (!EMIT) cnt[r] = map_record<0>(rv, vv, vp, r, c, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr);
+            else if (cnt[r] != 0) map_record<1>(rv, vv, vp, r, c, baseq, isize_cutoff, off[r], tr, tv, tm);
           }
         }
       }
@@ -461,8 +609,8 @@ struct Pipeline {
       if (EMIT && cnt[r] == 0) return;
       int c = upper_slot_i64(rv.contig_rec_off, ncg, r);
       GlobalVP vp{vv.pos};
-      if (!EMIT) cnt[r] = map_record<false>(rv, vv, vp, r, c, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr);
-      else map_record<true>(rv, vv, vp, r, c, baseq, isize_cutoff, off[r], tr, tv, tm);
+      if (!EMIT) cnt[r] = map_record<0>(rv, vv, vp, r, c, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr);
+      else map_record<1>(rv, vv, vp, r, c, baseq, isize_cutoff, off[r], tr, tv, tm);
     });
   }
 

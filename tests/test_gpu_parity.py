@@ -97,14 +97,14 @@ def test_windowed_k1_equals_generic_k1(gpu):
     d = gpu.upload_reads(rb)
     out = {}
     try:
-        for mode in (0, 1, 2):
+        for mode in (0, 1, 2, 3):
             gpu.set_option("k1_mode", mode)
             gpu.set_variants(vt)
             n = gpu.map_reads(d, 10, 0.0)
             out[mode] = (n, gpu.download("t_rec"), gpu.download("t_var"), gpu.download("t_misc"))
     finally:
-        gpu.set_option("k1_mode", 2)
-    assert out[0][0] == out[1][0] == out[2][0] and out[0][0] > 100000
-    for m in (1, 2):
+        gpu.set_option("k1_mode", 3)
+    assert out[0][0] == out[1][0] == out[2][0] == out[3][0] and out[0][0] > 100000
+    for m in (1, 2, 3):
         for a, b in zip(out[0][1:], out[m][1:]):
             assert np.array_equal(a, b), m
