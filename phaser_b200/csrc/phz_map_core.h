@@ -66,36 +66,49 @@ struct GlobalVP {
   const int32_t* g;
   PHZ_HD int32_t at(int64_t j) const { return g[j]; }
   // lower bounds of lo_key / hi_key inside the contig's range [v0, v1)
-  PHZ_HD void range(int32_t lo_key, int32_t hi_key, int64_t v0, int64_t v1, int64_t& lo, int64_t& hi) const {
+  PHZ_HD void range(int32_t lo_key, int32_t hi_key, int64_t v0, int64_t v1, bool, int64_t& lo, int64_t& hi) const {
     lo = lower_bound_i32(g, v0, v1, lo_key);
     hi = lower_bound_i32(g, lo, v1, hi_key);
   }
 };
 
 // A slab of the position array staged in shared memory (global indices [wbase, wbase+wn)); searches
-// that fall outside it go back to global memory.  32-bit local indices, branch-free halving (the trip
-// count is the same for every lane of a tile), short linear scan for the upper end.
+// that fall outside it go back to global memory.  32-bit local indices, branch-free halving, short
+// linear scan for the upper end.  [hint_lo, hint_hi] (local, inclusive) brackets the lower bound of the
+// POS of every record of the tile on the tile's first contig (records are coordinate sorted), so the
+// first-segment search of such a record only looks there; hint_hi < 0 disables it.
 struct WindowVP {
   const int32_t* g;
   const int32_t* s;
   int64_t wbase;
   int wn;
+  int hint_lo, hint_hi;
   PHZ_HD int32_t at(int64_t j) const {
     int64_t k = j - wbase;
     return (k >= 0 && k < wn) ? s[k] : g[j];
   }
-  PHZ_HD void range(int32_t lo_key, int32_t hi_key, int64_t v0, int64_t v1, int64_t& lo, int64_t& hi) const {
+  PHZ_HD int lower(int l, int len, int32_t key) const {
+    while (len > 0) {
+      int half = len >> 1, mid = l + half;
+      bool p = s[mid] < key;
+      l = p ? mid + 1 : l;
+      len = p ? len - half - 1 : half;
+    }
+    return l;
+  }
+  PHZ_HD void range(int32_t lo_key, int32_t hi_key, int64_t v0, int64_t v1, bool use_hint, int64_t& lo, int64_t& hi) const {
     int64_t a64 = v0 - wbase, b64 = v1 - wbase;
     int a = a64 > 0 ? (int)a64 : 0, b = b64 < wn ? (int)b64 : wn;
     if (a < b) {
-      int l = a, len = b - a;
-      while (len > 0) {
-        int half = len >> 1, mid = l + half;
-        bool p = s[mid] < lo_key;
-        l = p ? mid + 1 : l;
-        len = p ? len - half - 1 : half;
+      int l; bool ok;
+      if (use_hint && hint_hi >= 0) {
+        l = lower(hint_lo, hint_hi - hint_lo, lo_key);      // the true lower bound is inside the bracket
+        ok = true;
+      } else {
+        l = lower(a, b - a, lo_key);
+        ok = (l > a || wbase + a == v0) && (l < b || wbase + b == v1);
       }
-      if ((l > a || wbase + a == v0) && (l < b || wbase + b == v1)) {
+      if (ok) {
         int h = l;
         while (h < b && s[h] < hi_key) ++h;
         lo = wbase + l;
@@ -147,7 +160,7 @@ PHZ_HD u32 map_record(const ReadsView& rv, const VariantsView& vv, const VP& vp,
       if (lo_pos < 2147483647LL) {
         const int32_t hi32 = hi_pos > 2147483647LL ? 2147483647 : (int32_t)hi_pos;
         int64_t lo, hi;
-        vp.range((int32_t)lo_pos, hi32, v0, v1, lo, hi);
+        vp.range((int32_t)lo_pos, hi32, v0, v1, seg == 0, lo, hi);
         if (!EMIT) {
           n_out += (u32)(hi - lo);
         } else if (MODE == 2 && (u64)n_out + (u64)(hi - lo) <= o) {

@@ -71,7 +71,7 @@ PHZ_HD bool window_for_tile(const ReadsView& rv, const VariantsView& vv, int64_t
     if (reaches_end || p0 <= win[st.wn / 2]) return false;      // still in the first half: keep
   }
   int64_t wlo = lower_bound_i32(vv.pos, v0, v1, p0);
-  int64_t wbase = wlo & ~(int64_t)3;                              // 16-byte aligned source for the bulk copy
+  int64_t wbase = (wlo > 0 ? wlo - 1 : 0) & ~(int64_t)3;         // one element of slack, 16-byte aligned source
   int64_t wn = vv.n_variants - wbase; if (wn > K1_WIN) wn = K1_WIN;
   st.contig = c; st.wbase = wbase; st.wn = (int)wn;
   return true;
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_window_kernel(ReadsView rv, Var
     }
     const int64_t r = r0 + tid;
     if (r < R) {
-      WindowVP vp{vv.pos, win, st.wbase, st.wn};
+      WindowVP vp{vv.pos, win, st.wbase, st.wn, 0, -1};
       int c = st.contig;
       if (r >= rv.contig_rec_off[c + 1]) c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r);
       if (!EMIT) {
@@ -154,16 +154,32 @@ constexpr int KF_THREADS = 256;
 constexpr int KF_WIN = 1024;                      // het-site positions per slab (4 KB)
 constexpr u64 KF_FLAG_AGG = 1ull << 62, KF_FLAG_PREFIX = 2ull << 62, KF_VALUE_MASK = (1ull << 62) - 1;
 
-struct TileInfo { u32 wbase; u32 contig_wn; };    // contig << 16 | wn
+struct TileInfo { u32 wbase; u32 contig_wn; u32 hint; };    // contig << 16 | wn ; hint_lo << 16 | bracket length (0xFFFF = none)
 
 PHZ_HD TileInfo tile_info_for(const ReadsView& rv, const VariantsView& vv, int64_t r0) {
   int c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r0);
   int64_t v0 = vv.contig_var_off[c], v1 = vv.contig_var_off[c + 1];
   int64_t wlo = lower_bound_i32(vv.pos, v0, v1, rv.pos[r0]);
-  int64_t wbase = wlo & ~(int64_t)3;              // 16-byte aligned source for the bulk copy
+  // one element of slack in front (so an in-slab result equal to the slab start is never ambiguous),
+  // rounded down to a 16-byte aligned source for the bulk copy
+  int64_t wbase = (wlo > 0 ? wlo - 1 : 0) & ~(int64_t)3;
   int64_t wn = vv.n_variants - wbase; if (wn > KF_WIN) wn = KF_WIN;
+  // bracket of lower_bound(POS) over the tile's records that lie on contig c
+  int64_t r_last = r0 + KF_THREADS - 1;
+  if (r_last >= rv.n_records) r_last = rv.n_records - 1;
+  if (r_last >= rv.contig_rec_off[c + 1]) r_last = rv.contig_rec_off[c + 1] - 1;
+  int64_t wlast = lower_bound_i32(vv.pos, wlo, v1, rv.pos[r_last]);
+  int64_t hint_lo = wlo - wbase, nfirst = wlast - wlo;
   TileInfo ti; ti.wbase = (u32)wbase; ti.contig_wn = ((u32)c << 16) | (u32)wn;
+  ti.hint = (hint_lo + nfirst <= wn && nfirst < 0xFFFF) ? (((u32)hint_lo << 16) | (u32)nfirst) : 0xFFFFu;
   return ti;
+}
+
+PHZ_HD WindowVP window_of(const TileInfo& ti, const int32_t* g, const int32_t* slab, bool same_contig) {
+  WindowVP vp; vp.g = g; vp.s = slab; vp.wbase = (int64_t)ti.wbase; vp.wn = (int)(ti.contig_wn & 0xFFFF);
+  u32 n = ti.hint & 0xFFFFu;
+  vp.hint_lo = (int)(ti.hint >> 16); vp.hint_hi = (n != 0xFFFFu && same_contig) ? vp.hint_lo + (int)n : -1;
+  return vp;
 }
 
 #ifdef __CUDACC__
@@ -176,12 +192,12 @@ __global__ void __launch_bounds__(KF_THREADS) k1_fused_kernel(ReadsView rv, Vari
   __shared__ __align__(8) unsigned long long mbar;
   __shared__ u32 warp_sum[KF_THREADS / 32];
   __shared__ unsigned long long s_base;
-  __shared__ u32 s_tile, s_wbase, s_cwn;
+  __shared__ u32 s_tile; __shared__ TileInfo s_ti;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     u32 t = atomicAdd(ticket, 1u);                // tiles are taken in launch order: predecessors are running
     TileInfo ti = tiles[t];
-    s_tile = t; s_wbase = ti.wbase; s_cwn = ti.contig_wn;
+    s_tile = t; s_ti = ti;
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     int wn = (int)(ti.contig_wn & 0xFFFF), nb = wn & ~3, bytes = nb * 4;
@@ -194,8 +210,10 @@ __global__ void __launch_bounds__(KF_THREADS) k1_fused_kernel(ReadsView rv, Vari
   }
   __syncthreads();
   const int64_t tile = s_tile;
-  const int wn = (int)(s_cwn & 0xFFFF);
-  int contig = (int)(s_cwn >> 16);
+  const TileInfo ti = s_ti;
+  const int wn = (int)(ti.contig_wn & 0xFFFF);
+  const int contig0 = (int)(ti.contig_wn >> 16);
+  int contig = contig0;
   const int64_t r = tile * KF_THREADS + tid;
   const bool live = r < rv.n_records;
   if (live && r >= rv.contig_rec_off[contig + 1]) contig = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r);
@@ -206,7 +224,7 @@ __global__ void __launch_bounds__(KF_THREADS) k1_fused_kernel(ReadsView rv, Vari
                    : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0) : "memory");
     }
   }
-  WindowVP vp{vv.pos, win, (int64_t)s_wbase, wn};
+  const WindowVP vp = window_of(ti, vv.pos, win, contig == contig0);
   u32 cnt = live ? map_record<0>(rv, vv, vp, r, contig, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr) : 0u;
   // ---- CTA exclusive scan of the counts
   u32 incl = cnt;
@@ -307,7 +325,7 @@ __global__ void __launch_bounds__(KF_THREADS) k1_tile_kernel(ReadsView rv, Varia
                    : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0) : "memory");
     }
   }
-  WindowVP vp{vv.pos, win, (int64_t)ti.wbase, wn};
+  const WindowVP vp = window_of(ti, vv.pos, win, contig == contig0);
   const u32 cnt = live ? map_record<0>(rv, vv, vp, r, contig, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr) : 0u;
   // ---- CTA exclusive scan of the counts
   u32 incl = cnt;
@@ -335,7 +353,8 @@ __global__ void __launch_bounds__(KF_THREADS) k1_tile_kernel(ReadsView rv, Varia
     const int64_t rr = r0 + lo;
     int c = contig0;
     if (rr >= contig0_end) c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, rr);
-    map_record<2>(rv, vv, vp, rr, c, baseq, isize_cutoff, (u64)(i - excl_of[lo]), s_rec + base + i, s_var + base + i,
+    const WindowVP vpk = window_of(ti, vv.pos, win, c == contig0);
+    map_record<2>(rv, vv, vpk, rr, c, baseq, isize_cutoff, (u64)(i - excl_of[lo]), s_rec + base + i, s_var + base + i,
                   s_misc + base + i);
   }
 }
@@ -486,12 +505,12 @@ struct Pipeline {
 #else
       // host simulation: same tile descriptors, slab logic and k-th candidate emission, tiles in sequence
       for (int64_t t = 0; t < n_tiles; ++t) {
-        int wn = (int)(ti[t].contig_wn & 0xFFFF); int c0 = (int)(ti[t].contig_wn >> 16);
-        WindowVP vp{vv.pos, vv.pos + ti[t].wbase, (int64_t)ti[t].wbase, wn};
+        int c0 = (int)(ti[t].contig_wn >> 16);
         u32 tile_total = 0;
         for (int64_t r = t * KF_THREADS; r < (t + 1) * KF_THREADS && r < R; ++r) {
           int c = c0;
           if (r >= rv.contig_rec_off[c + 1]) c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r);
+          const WindowVP vp = window_of(ti[t], vv.pos, vv.pos + ti[t].wbase, c == c0);
           u32 cnt = map_record<0>(rv, vv, vp, r, c, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr);
           if (total + tile_total + cnt <= cap)
             for (u32 k = 0; k < cnt; ++k) {
@@ -550,11 +569,11 @@ struct Pipeline {
 #else
       // host simulation: same tile descriptors, slab logic and emission order, tiles in sequence
       for (int64_t t = 0; t < n_tiles; ++t) {
-        int wn = (int)(ti[t].contig_wn & 0xFFFF); int c0 = (int)(ti[t].contig_wn >> 16);
-        WindowVP vp{vv.pos, vv.pos + ti[t].wbase, (int64_t)ti[t].wbase, wn};
+        int c0 = (int)(ti[t].contig_wn >> 16);
         for (int64_t r = t * KF_THREADS; r < (t + 1) * KF_THREADS && r < R; ++r) {
           int c = c0;
           if (r >= rv.contig_rec_off[c + 1]) c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r);
+          const WindowVP vp = window_of(ti[t], vv.pos, vv.pos + ti[t].wbase, c == c0);
           u32 cnt = map_record<0>(rv, vv, vp, r, c, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr);
           if (cnt && total + cnt <= cap) map_record<1>(rv, vv, vp, r, c, baseq, isize_cutoff, total, tr, tv, tm);
           total += cnt;
@@ -592,7 +611,7 @@ struct Pipeline {
           if (r0 >= R) break;
           window_for_tile(rv, vv, r0, vv.pos + st.wbase, st);
           for (int64_t r = r0; r < r0 + K1_THREADS && r < R; ++r) {
-            WindowVP vp{vv.pos, vv.pos + st.wbase, st.wbase, st.wn};
+            WindowVP vp{vv.pos, vv.pos + st.wbase, st.wbase, st.wn, 0, -1};
             int c = st.contig;
             if (r >= rv.contig_rec_off[c + 1]) c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r);
             if (!EMIT) cnt[r] = map_record<0>(rv, vv, vp, r, c, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr);
