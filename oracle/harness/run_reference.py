@@ -25,8 +25,16 @@ OUTPUT_SUFFIXES = [
 ]
 
 
+COMPILED_DIR = os.path.join(os.path.dirname(HERE), "_ref")
+
+
 def reference_available():
     return os.path.isfile(os.path.join(REFERENCE_DIR, "phaser.py"))
+
+
+def compiled_available():
+    """oracle/_ref: the reference compiled as-is by oracle/build_ref.py (travels to the GPU box)."""
+    return all(os.path.isfile(os.path.join(COMPILED_DIR, f)) for f in ("phaser.so", "read_variant_map.so", "run_phaser.py"))
 
 
 def _env(hashseed):
@@ -48,15 +56,21 @@ def run_mapper(sam_path, variant_table, out_path, baseq=10, isize_cutoff=0, hash
 
 
 def run_reference(vcf_gz, bams, out_prefix, sample, mapq="255", baseq=10, paired_end="1",
-                  extra_args=(), hashseed=0, threads=1, quiet=True, timeout=None):
+                  extra_args=(), hashseed=0, threads=1, quiet=True, timeout=None, compiled=False):
     """L2/L3 oracle: the whole reference phaser.py (phaser/phaser.py:26-178).
 
     `bams` are SAM text files (coordinate sorted, with @SQ lines).  Empty `.bai` / `.tbi` files are
     created next to the inputs because the reference only checks that they exist
     (phaser/phaser.py:124, 190).  Returns {suffix: path}.
     """
-    if not reference_available():
-        raise RuntimeError("reference not found at %s" % REFERENCE_DIR)
+    if compiled:
+        if not compiled_available():
+            raise RuntimeError("compiled reference not found in %s (run oracle/build_ref.py)" % COMPILED_DIR)
+        script = os.path.join(COMPILED_DIR, "run_phaser.py")
+    else:
+        if not reference_available():
+            raise RuntimeError("reference not found at %s" % REFERENCE_DIR)
+        script = os.path.join(REFERENCE_DIR, "phaser.py")
     if isinstance(bams, str):
         bams = [bams]
     for b in bams:
@@ -64,7 +78,7 @@ def run_reference(vcf_gz, bams, out_prefix, sample, mapq="255", baseq=10, paired
             open(b + ".bai", "w").close()
     if not os.path.exists(vcf_gz + ".tbi") and not os.path.exists(vcf_gz + ".csi"):
         open(vcf_gz + ".tbi", "w").close()
-    cmd = [sys.executable, os.path.join(REFERENCE_DIR, "phaser.py"),
+    cmd = [sys.executable, script,
            "--vcf", vcf_gz, "--bam", ",".join(bams), "--sample", sample,
            "--mapq", str(mapq), "--baseq", str(baseq), "--paired_end", str(paired_end),
            "--o", out_prefix, "--threads", str(threads)] + [str(a) for a in extra_args]
