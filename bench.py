@@ -38,10 +38,11 @@ def parse_args():
     ap.add_argument("--variants", type=int, default=2_000_000, help="het SNVs per sample (configs[1]: 2 M)")
     ap.add_argument("--exonic_frac", type=float, default=0.10)
     ap.add_argument("--seed", type=int, default=2000)
-    ap.add_argument("--cpu_pairs", type=int, default=250_000, help="read pairs of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu_pairs", type=int, default=750_000, help="read pairs of the bounded CPU-baseline sample")
     ap.add_argument("--no_e2e", action="store_true")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--k1_mode", type=int, default=3, help="3 tile kernel + permute (default), 2 fused look-back, 1 windowed two-pass, 0 generic two-pass")
+    ap.add_argument("--profiler_range", action="store_true", help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)")
     ap.add_argument("--profile", action="store_true", help="add per-stage CUDA-event times of one extra step")
     return ap.parse_args()
 
@@ -159,11 +160,15 @@ def run_ours(a):
     clocks = ClockSampler(local); clocks.start()
     barrier()
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    if a.profiler_range:
+        torch.cuda.cudart().cudaProfilerStart()
     ev0.record()
     for _ in range(a.steps):
         res = step()
         k1_ms.append(E.map_times())
     ev1.record()
+    if a.profiler_range:
+        torch.cuda.synchronize(); torch.cuda.cudart().cudaProfilerStop()
     barrier()
     clk = clocks.stop()
     ms_total = ev0.elapsed_time(ev1)
@@ -270,6 +275,9 @@ def cpu_sample_files(a, tmp):
     return g, rec, vcf, sam, n_pairs, int(g.v_pos.shape[0])
 
 
+_CPU_FILES = {}
+
+
 def cpu_baseline(a):
     """The reference CPU path on this box's host cores.  kind "reference": the unmodified reference
     compiled as-is into oracle/_ref (oracle/build_ref.py), run end to end with --threads = host cores
@@ -278,8 +286,12 @@ def cpu_baseline(a):
     from oracle.harness import run_reference as rr
     tmp = tempfile.mkdtemp(prefix="phz_cpu_")
     try:
-        g, rec, vcf, sam, n_pairs, n_var = cpu_sample_files(a, tmp)
-        n_rec = int(rec["pos"].shape[0])
+        key = (a.seed, a.cpu_pairs, a.variants, a.pairs)
+        if key not in _CPU_FILES:            # the sample files are written once per run, outside any timing
+            keep = tempfile.mkdtemp(prefix="phz_cpu_in_")
+            g, rec, vcf, sam, n_pairs, n_var = cpu_sample_files(a, keep)
+            _CPU_FILES[key] = (vcf, sam, n_pairs, n_var, int(rec["pos"].shape[0]))
+        vcf, sam, n_pairs, n_var, n_rec = _CPU_FILES[key]
         cores = os.cpu_count() or 1
         if rr.compiled_available():
             t0 = time.perf_counter()
