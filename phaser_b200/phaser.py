@@ -1,0 +1,250 @@
+#!/usr/bin/env python
+"""phaser.py -- drop-in command line for the read -> variant -> haplotype path of phASER on B200.
+
+Same flags, file formats and fatal-error behaviour as the reference CLI (phaser/phaser.py:26-178);
+the work between "het sites loaded" and "files written" runs on the GPU through the C ABI
+(include/phz.h).  Differences a user can see:
+  * no samtools / bgzip / tabix / bedtools / bcftools are needed (BAM or SAM text is read directly);
+  * options that only exist to drive those tools are rejected with a FATAL ERROR instead of being
+    silently ignored: --blacklist, --haplo_count_blacklist, --include_indels 1, --process_slow 1,
+    --output_network, --output_read_ids 1 ("next" rows);
+  * fields the reference prints in CPython-set order come out in a canonical order
+    (SURVEY.md section 8c).
+"""
+import argparse
+import datetime
+import gzip
+import os
+import sys
+import time
+
+if __package__ in (None, ""):
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from phaser_b200 import vcfio, samio, pipeline, writer, bgzf    # noqa: E402
+from phaser_b200.vcfio import PhaserFatal                        # noqa: E402
+
+VERSION = "1.2.0"
+
+
+def build_parser():
+    p = argparse.ArgumentParser()
+    # required (phaser.py:30-36)
+    p.add_argument("--bam", required=False, default='', help="Indexed BAMs (comma separated) containing aligned reads")
+    p.add_argument("--vcf", required=True, default='', help="VCF for the sample, must be gzipped and tabix indexed.")
+    p.add_argument("--sample", required=False, default='', help="Sample name in VCF")
+    p.add_argument("--mapq", required=True, help="Minimum MAPQ for reads to be used for phasing (comma separated list allowed).")
+    p.add_argument("--baseq", type=int, required=True, help="Minimum baseq for bases to be used for phasing")
+    p.add_argument("--paired_end", required=True, help="Sequencing data comes from a paired end assay (0,1; comma separated list allowed).")
+    p.add_argument("--o", required=True, help="Out prefix")
+    # optional (phaser.py:40-53)
+    p.add_argument("--python_string", default="python3")
+    p.add_argument("--haplo_count_bam_exclude", default="")
+    p.add_argument("--haplo_count_blacklist", default="")
+    p.add_argument("--cc_threshold", type=float, default=0.01)
+    p.add_argument("--isize", default="0")
+    p.add_argument("--as_q_cutoff", type=float, default=0.05)
+    p.add_argument("--blacklist", default="")
+    p.add_argument("--write_vcf", type=int, default=1)
+    p.add_argument("--include_indels", type=int, default=0)
+    p.add_argument("--output_read_ids", type=int, default=0)
+    p.add_argument("--remove_dups", type=int, default=1)
+    p.add_argument("--pass_only", type=int, default=1)
+    p.add_argument("--unphased_vars", type=int, default=1)
+    p.add_argument("--chr_prefix", type=str, default="")
+    # genome wide phasing (phaser.py:56-59)
+    p.add_argument("--gw_phase_method", type=int, default=0)
+    p.add_argument("--gw_af_field", default="AF")
+    p.add_argument("--gw_phase_vcf", type=int, default=0)
+    p.add_argument("--gw_phase_vcf_min_confidence", type=float, default=0.90)
+    # performance (phaser.py:62-65)
+    p.add_argument("--threads", type=int, default=1, help="accepted for compatibility; the GPU path does not use host threads")
+    p.add_argument("--max_block_size", type=int, default=15)
+    p.add_argument("--temp_dir", default="")
+    p.add_argument("--max_items_per_thread", type=int, default=100000)
+    # debug / reporting (phaser.py:68-78)
+    p.add_argument("--show_warning", type=int, default=0)
+    p.add_argument("--debug", type=int, default=0)
+    p.add_argument("--chr", default="")
+    p.add_argument("--unique_ids", type=int, default=0)
+    p.add_argument("--id_separator", default="_")
+    p.add_argument("--output_network", default="")
+    p.add_argument("--process_slow", type=int, default=0, required=False)
+    # this implementation only
+    p.add_argument("--device", default="cuda:0", help="CUDA device to run on")
+    return p
+
+
+def say(text=""):
+    print(text)
+    sys.stdout.flush()
+
+
+def fatal_error(text):
+    """phaser.py:2032-2034"""
+    say("     FATAL ERROR: " + text)
+    sys.exit(1)
+
+
+def bam_display_names(bam_list):
+    """phaser.py:469-480"""
+    file_names = [os.path.basename(x).replace(".bam", "") for x in bam_list]
+    out, counter = [], {}
+    for x in file_names:
+        if file_names.count(x) > 1:
+            counter[x] = counter.get(x, 0) + 1
+            out.append(x + "." + str(counter[x]))
+        else:
+            out.append(x)
+    return out
+
+
+def per_bam_lists(args, bam_list):
+    """phaser.py:482-513"""
+    mapq = args.mapq.split(",")
+    if len(mapq) == 1 and len(bam_list) > 1:
+        mapq = mapq * len(bam_list)
+    elif len(mapq) != len(bam_list):
+        fatal_error("Number of mapq values and input BAMs does not match. Supply either one mapq to be used for all BAMs or one mapq per input BAM.")
+    isize = args.isize.split(",")
+    if len(isize) == 1 and len(bam_list) > 1:
+        isize = isize * len(bam_list)
+    elif len(mapq) != len(isize):
+        fatal_error("Number of isize values and input BAMs does not match. Supply either one isize to be used for all BAMs or one isize per input BAM.")
+    isize = list(map(float, isize))
+    paired = args.paired_end.split(",")
+    if len(paired) == 1 and len(bam_list) > 1:
+        paired = paired * len(bam_list)
+    elif len(paired) != len(bam_list):
+        fatal_error("Number of paired_end values and input BAMs does not match. Supply either one paired_end to be used for all BAMs or one paired_end per input BAM.")
+    return [int(x) for x in mapq], isize, [int(x) for x in paired]
+
+
+def run(args, engine=None):
+    say("")
+    say("##################################################")
+    say("              Welcome to phASER v%s" % VERSION)
+    say("  Author: Stephane Castel (stephanecastel@gmail.com)")
+    say("  Updated by: Bishwa K. Giri (bkgiri@uncg.edu)")
+    say("  B200-native read->variant->haplotype path (phaser_b200)")
+    say("##################################################")
+    say("")
+    for flag, bad, why in (("--blacklist", args.blacklist != "", "needs a BED interval join"),
+                           ("--haplo_count_blacklist", args.haplo_count_blacklist != "", "needs a BED interval join"),
+                           ("--include_indels 1", args.include_indels == 1, "multi-base alleles"),
+                           ("--process_slow 1", args.process_slow == 1, "per-contig mode changes results in the reference"),
+                           ("--output_network", args.output_network != "", "debug dump"),
+                           ("--output_read_ids 1", args.output_read_ids == 1, "read-id columns")):
+        if bad:
+            fatal_error("%s is not supported by the B200 path yet (%s)." % (flag, why))
+    if args.id_separator == ":" or args.id_separator == "":
+        fatal_error("ID separator must not be ':' or blank. Please choose another separator that is not found in the contig names.")
+    if os.path.isfile(args.vcf) is False:
+        fatal_error("VCF file does not exist.")
+    if args.vcf.endswith(".gz") is False and args.vcf.endswith(".bgz") is False:
+        fatal_error("VCF must be gzipped.")
+    bam_list = [b for b in args.bam.split(",")]
+    for b in bam_list:
+        if b != "" and os.path.isfile(b) is False:
+            fatal_error("File: %s not found." % b)
+    cols = vcfio.sample_column_map(args.vcf)
+    if args.sample not in cols:
+        fatal_error("Sample '%s' not found in the input VCF file." % args.sample)
+    sample_column = cols[args.sample]
+    if args.haplo_count_bam_exclude != "":
+        exclude = [x - 1 for x in map(int, args.haplo_count_bam_exclude.split(","))]
+    else:
+        exclude = []
+    start_time = time.time()
+    say('STARTED "Read backed phasing and ASE/haplotype analyses" ... ')
+    say("    DATE, TIME : %s" % datetime.datetime.now().strftime('%Y-%m-%d, %H:%M:%S'))
+    say("#1. Loading heterozygous variants into intervals...")
+    try:
+        vt, st = vcfio.parse_vcf(args.vcf, sample_column, pass_only=args.pass_only, chrom_of_interest=args.chr,
+                                 chr_prefix=args.chr_prefix, id_separator=args.id_separator,
+                                 include_indels=args.include_indels, gw_phase_method=args.gw_phase_method,
+                                 gw_af_field=args.gw_af_field)
+    except PhaserFatal as e:
+        fatal_error(str(e))
+    say("          %d heterozygous sites being used for phasing (%d filtered, %d indels excluded, %d unphased)" % (
+        st.het_count, st.filter_count, st.indels_excluded, st.unphased_count))
+    say()
+    if st.het_count == 0:
+        fatal_error("No heterozygous sites that passed all filters were included in the analysis, phASER cannot continue. Check blacklist and pass_only arguments.")
+    say("#2. Retrieving reads that overlap heterozygous sites...")
+    mapq, isize, paired = per_bam_lists(args, bam_list)
+    bam_names = bam_display_names(bam_list)
+    if engine is None:
+        from phaser_b200.engine import Engine
+        engine = Engine(device=args.device)
+    fd = samio.FragmentDictionary()
+    batches = []
+    for i, bam in enumerate(bam_list):
+        say("     file: %s" % bam)
+        say("          minimum mapq: %s" % mapq[i])
+        rb = samio.read_alignments(bam, vt.contigs, fd, remove_dups=(args.remove_dups == 1), proper_pair=(paired[i] == 1),
+                                   min_mapq=mapq[i])
+        batches.append(engine.upload_reads(rb))
+    P = pipeline.PhaseParams(baseq=args.baseq, isize=isize, as_q_cutoff=args.as_q_cutoff, cc_threshold=args.cc_threshold,
+                             max_block_size=args.max_block_size, haplo_count_bam_exclude=exclude)
+    try:
+        res = pipeline.run_path(engine, vt, batches, P, n_fragments=len(fd.names))
+    except PhaserFatal as e:
+        fatal_error(str(e))
+    for i, bam in enumerate(bam_list):
+        if res.as_cutoff[i] is not None:
+            say("          using alignment score cutoff of %d" % res.as_cutoff[i])
+        say("          retrieved %d reads" % res.tuples_per_bam[i])
+    say("#3. Identifying connected variants...")
+    say("     sequencing noise level estimated at %f" % res.noise_e)
+    out = writer.Outputs(res, vt, bam_names, P, unphased_vars=args.unphased_vars, gw_phase_method=args.gw_phase_method,
+                         unique_ids=args.unique_ids)
+    with open(args.o + ".variant_connections.txt", "w") as f:
+        f.write(out.variant_connections())
+    say("     %d variant connections dropped because of conflicting configurations (threshold = %f)" % (
+        res.counters["dropped"], args.cc_threshold))
+    with open(args.o + ".allelic_counts.txt", "w") as f:
+        f.write(out.allelic_counts())
+    say("     %d variants covered by at least 1 read" % out.covered_count)
+    say("#4. Identifying haplotype blocks...")
+    say("#5. Phasing blocks...")
+    say("#6. Outputting haplotypes...")
+    hp, hc, cfg = out.block_tables()
+    with open(args.o + ".haplotypes.txt", "w") as f:
+        f.write(hp)
+    with open(args.o + ".haplotypic_counts.txt", "w") as f:
+        f.write(hc)
+    with open(args.o + ".allele_config.txt", "w") as f:
+        f.write(cfg)
+    unphased_phased = phase_corrected = 0
+    if args.write_vcf == 1:
+        say("#7. Outputting phased VCF...")
+        with gzip.open(args.vcf, "rt") as f:
+            text, unphased_phased, phase_corrected = out.vcf_text(
+                f, sample_column, id_separator=args.id_separator, gw_phase_vcf=args.gw_phase_vcf,
+                min_conf=args.gw_phase_vcf_min_confidence, chrom_of_interest=args.chr)
+        with bgzf.BGZFWriter(args.o + ".vcf.gz") as f:       # what `bgzip -f` writes (phaser.py:1851)
+            f.write(text)
+    total_time = time.time() - start_time
+    say('')
+    say("     COMPLETED using %d reads in %d seconds on %s" % (sum(res.tuples_per_bam), total_time, engine.backend))
+    n_phased = len(out.all_variants)
+    say("     PHASED  %d of %d all variants (= %f) with at least one other variant" % (
+        n_phased, st.het_count, float(n_phased) / float(st.het_count)))
+    if args.write_vcf == 1:
+        if st.unphased_count > 0:
+            say("     GENOME WIDE PHASED  %d of %d unphased variants (= %f)" % (
+                unphased_phased, st.unphased_count, float(unphased_phased) / float(st.unphased_count)))
+        say("     GENOME WIDE PHASE CORRECTED  %d of %d variants (= %f)" % (
+            phase_corrected, st.het_count, float(phase_corrected) / float(st.het_count)))
+    say('The End.')
+    return res
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    run(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -106,3 +106,24 @@ def parse_sam(path, contigs: List[str], fragdict: FragmentDictionary, remove_dup
     qual = (np.frombuffer(bytes(quals), np.uint8).astype(np.int16) - 33).clip(0, 255).astype(np.uint8)
     return ReadBatch(nc, off, pos, tlen, aln, frag, cig_off, np.asarray(cig, np.uint32), seq_off, seq, qual,
                      fragdict.names)
+
+
+def read_alignments(path, contigs, fragdict, remove_dups=True, proper_pair=True, min_mapq=0) -> ReadBatch:
+    """BAM (BGZF, magic "BAM\\1" after inflate) or SAM text (optionally gzipped), by content."""
+    with open(path, "rb") as f:
+        magic = f.read(18)
+    if magic[:2] == b"\x1f\x8b" and len(magic) >= 14 and magic[3] & 4 and magic[12:14] == b"BC":
+        from . import bamio
+        rb = bamio.read_bam(path, contigs, fragdict, remove_dups, proper_pair, min_mapq)
+    else:
+        rb = parse_sam(path, contigs, fragdict, remove_dups, proper_pair, min_mapq)
+    check_sorted(rb, path)
+    return rb
+
+
+def check_sorted(rb: ReadBatch, path=""):
+    """The kernels (like the reference's streaming mapper) need coordinate-sorted records."""
+    for c in range(rb.n_contigs):
+        p = rb.pos[int(rb.contig_rec_off[c]):int(rb.contig_rec_off[c + 1])]
+        if p.shape[0] > 1 and np.any(np.diff(p.astype(np.int64)) < 0):
+            raise ValueError("%s: records are not sorted by coordinate" % path)

@@ -1,0 +1,82 @@
+"""CLI drop-in behaviour and BAM/BGZF ingest (host-simulation backend in the build container)."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from oracle import compare
+from phaser_b200 import phaser as cli, bamio, bgzf, samio
+from tests import util, golden_util as G
+
+
+def _run_cli(engine, case, tmp_path, extra=()):
+    c = G.load_case(case)
+    o = str(tmp_path / "out")
+    argv = ["--vcf", c["vcf"], "--bam", ",".join(c["sams"]), "--sample", "S1", "--mapq", c["meta"]["mapq"], "--baseq", "10",
+            "--paired_end", c["meta"]["paired_end"], "--o", o] + list(c["meta"]["args"]) + list(extra)
+    cli.run(cli.build_parser().parse_args(argv), engine=engine)
+    got = {k: open(o + "." + k + ".txt").read() for k in ("allelic_counts", "allele_config", "haplotypes", "haplotypic_counts",
+                                                          "variant_connections")}
+    got["vcf"] = gzip.open(o + ".vcf.gz", "rt").read()
+    return c, got
+
+
+@pytest.mark.parametrize("case", ["quirks", "rna_two_bams"])
+def test_cli_writes_reference_identical_files(hostsim, tmp_path, case):
+    c, got = _run_cli(hostsim, case, tmp_path)
+    bad = compare.diff_outputs(c["ref"], got)
+    assert not bad, "\n".join(bad)
+
+
+def test_cli_fatal_errors_exit_1(hostsim, tmp_path, capsys):
+    c = G.load_case("quirks")
+    base = ["--vcf", c["vcf"], "--bam", c["sams"][0], "--mapq", "255", "--baseq", "10", "--paired_end", "1", "--o", str(tmp_path / "x")]
+    for extra, msg in ((["--sample", "NOPE"], "Sample 'NOPE' not found"),
+                       (["--sample", "S1", "--id_separator", ":"], "ID separator must not be"),
+                       (["--sample", "S1", "--mapq", "1,2"], "Number of mapq values"),
+                       (["--sample", "S1", "--blacklist", "x.bed"], "not supported")):
+        with pytest.raises(SystemExit) as e:
+            cli.run(cli.build_parser().parse_args(base + extra), engine=hostsim)
+        assert e.value.code == 1
+        assert "FATAL ERROR: " in capsys.readouterr().out
+
+
+def test_bam_reader_equals_sam_reader(tmp_path):
+    """Write the golden SAM text as BAM with our writer, read it back: identical packed arrays."""
+    c = G.load_case("rna_small")
+    sam = c["sams"][0]
+    refs = []; recs = []
+    for ln in open(sam):
+        f = ln.rstrip("\n").split("\t")
+        if ln.startswith("@SQ"):
+            refs.append((f[1][3:], int(f[2][3:])))
+        elif not ln.startswith("@"):
+            cig = []; n = ""
+            for ch in f[5]:
+                if ch.isdigit():
+                    n += ch
+                else:
+                    cig.append((int(n), ch)); n = ""
+            a = [int(t[5:]) for t in f[11:] if t.startswith("AS:i:")]
+            recs.append((f[0], int(f[1]), [r[0] for r in refs].index(f[2]), int(f[3]), int(f[4]), cig, f[9],
+                         bytes(ord(q) - 33 for q in f[10]), int(f[8]), a[0] if a else None))
+    bam = str(tmp_path / "x.bam")
+    bamio.write_bam(bam, refs, recs)
+    contigs = [r[0] for r in refs]
+    a = samio.read_alignments(sam, contigs, samio.FragmentDictionary(), True, True, 255)
+    b = samio.read_alignments(bam, contigs, samio.FragmentDictionary(), True, True, 255)
+    for k in ("contig_rec_off", "pos", "tlen", "aln_score", "frag", "cigar_off", "cigar", "seq_off", "seq", "qual"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert a.qnames == b.qnames
+
+
+def test_bgzf_roundtrip_and_gzip_compat(tmp_path):
+    p = str(tmp_path / "t.gz")
+    payload = (b"line\tof\ttext\n" * 20000)
+    with bgzf.BGZFWriter(p) as w:
+        w.write(payload[:100000]); w.write(payload[100000:])
+    assert gzip.open(p).read() == payload            # plain gzip readers accept BGZF
+    assert bgzf.read_all(p) == payload
+    raw = open(p, "rb").read()
+    assert raw.endswith(bgzf.EOF_BLOCK) and raw[12:14] == b"BC"
