@@ -43,10 +43,16 @@ def _open_text(path):
 
 def parse_sam(path, contigs: List[str], fragdict: FragmentDictionary, remove_dups=True, proper_pair=True,
               min_mapq=0) -> ReadBatch:
+    with _open_text(path) as f:
+        return parse_sam_stream(f, contigs, fragdict, remove_dups, proper_pair, min_mapq)
+
+
+def parse_sam_stream(f, contigs: List[str], fragdict: FragmentDictionary, remove_dups=True, proper_pair=True,
+                     min_mapq=0) -> ReadBatch:
     cidx = {c: i for i, c in enumerate(contigs)}
     nc = len(contigs)
     per = [[] for _ in range(nc)]
-    with _open_text(path) as f:
+    if True:
         for line in f:
             if line[0] == "@":
                 continue

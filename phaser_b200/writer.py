@@ -69,7 +69,7 @@ class Outputs:
     # ------------------------------------------------------------------ simple tables
     def first_seen_order(self):
         vf = self.res.vfirst
-        seen = np.nonzero(vf != NONE32)[0]
+        seen = np.nonzero(vf != np.iinfo(vf.dtype).max)[0]     # u32 tuple index, or u64 merged key (shard.py)
         return seen[np.argsort(vf[seen], kind="stable")]
 
     def allelic_counts(self):

@@ -1,0 +1,46 @@
+"""One rank of the world_size-2 gloo test (tests/test_shard_gloo.py): contig-sharded run on the
+host-simulation backend, rank 0 merges, writes the files and diffs them against the reference fixture."""
+import gzip
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch.distributed as dist      # noqa: E402
+
+from oracle import compare            # noqa: E402
+from phaser_b200 import pipeline, shard, writer   # noqa: E402
+from tests import util, golden_util as G           # noqa: E402
+
+
+def main():
+    case = sys.argv[1]
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["MASTER_PORT"],
+                            rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+    c = G.load_case(case)
+    kw = G.args_to_kw(c["meta"]["args"])
+    vt, st, batches, col, fd = util.load_inputs(c["vcf"], c["sams"])
+    P = pipeline.PhaseParams(as_q_cutoff=kw.get("as_q_cutoff", 0.05), max_block_size=kw.get("max_block_size", 15),
+                             haplo_count_bam_exclude=kw.get("exclude", []), isize=kw.get("isize", [0.0]))
+    e = util.hostsim_engine()
+    res = shard.run_sharded(e, vt, batches, P, n_fragments=len(fd.names))
+    rc = 0
+    if dist.get_rank() == 0:
+        o = writer.Outputs(res, vt, util.bam_display_names(c["sams"]), P)
+        got = dict(allelic_counts=o.allelic_counts(), variant_connections=o.variant_connections())
+        got["haplotypes"], got["haplotypic_counts"], got["allele_config"] = o.block_tables()
+        with gzip.open(c["vcf"], "rt") as f:
+            got["vcf"], _, _ = o.vcf_text(f.readlines(), col)
+        bad = compare.diff_outputs(c["ref"], got)
+        if bad:
+            print("\n".join(bad)); rc = 1
+        else:
+            print("SHARDED PARITY OK", case, res.counters)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(rc)
+
+
+if __name__ == "__main__":
+    main()

@@ -80,3 +80,32 @@ def test_bgzf_roundtrip_and_gzip_compat(tmp_path):
     assert bgzf.read_all(p) == payload
     raw = open(p, "rb").read()
     assert raw.endswith(bgzf.EOF_BLOCK) and raw[12:14] == b"BC"
+
+
+@pytest.mark.parametrize("case", ["quirks", "rna_small"])
+def test_read_variant_map_seam_writes_the_reference_tsv(hostsim, tmp_path, monkeypatch, case):
+    """Seam S1: do_read_variant_map(variant_table, baseq, o, splice, isize_cutoff) with SAM text on stdin
+    produces byte for byte the TSV of the reference mapper (committed golden)."""
+    import io
+    from phaser_b200 import read_variant_map as rvm, vcfio
+    c = G.load_case(case)
+    col = vcfio.sample_column_map(c["vcf"])["S1"]
+    vt, _ = vcfio.parse_vcf(c["vcf"], col)
+    table = tmp_path / "table.tsv"
+    with open(table, "w") as f:
+        for v in range(vt.n_variants):
+            ci = int(np.searchsorted(vt.contig_var_off, v, side="right") - 1)
+            f.write("\t".join([vt.contigs[ci], str(int(vt.pos[v])), vt.ids[v], vt.rsids[v], ",".join(vt.all_alleles[v]),
+                               "1", vt.gt[v], vt.maf[v]]) + "\n")
+    lines = []
+    for ln in open(c["sams"][0]):          # what the two samtools stages would let through
+        if ln[0] != "@":
+            f_ = ln.split("\t")
+            if int(f_[1]) & 0x400 or not int(f_[1]) & 2 or int(f_[4]) < 255:
+                continue
+        lines.append(ln)
+    monkeypatch.setattr("sys.stdin", io.StringIO("".join(lines)))
+    rvm.set_engine(hostsim)
+    out = tmp_path / "out.tsv"
+    rvm.do_read_variant_map(str(table), 10, str(out), 1, 0.0)
+    assert open(out).read() == c["mapper"][c["meta"]["bams"][0]]
