@@ -16,14 +16,22 @@ from tests import util, golden_util as G           # noqa: E402
 
 def main():
     case = sys.argv[1]
-    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["MASTER_PORT"],
+    on_gpu = os.environ.get("PHZ_ENGINE", "hostsim") == "gpu"
+    if on_gpu:
+        import torch
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", os.environ["RANK"])))
+    dist.init_process_group("nccl" if on_gpu else "gloo", init_method="tcp://127.0.0.1:%s" % os.environ["MASTER_PORT"],
                             rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
     c = G.load_case(case)
     kw = G.args_to_kw(c["meta"]["args"])
     vt, st, batches, col, fd = util.load_inputs(c["vcf"], c["sams"])
     P = pipeline.PhaseParams(as_q_cutoff=kw.get("as_q_cutoff", 0.05), max_block_size=kw.get("max_block_size", 15),
                              haplo_count_bam_exclude=kw.get("exclude", []), isize=kw.get("isize", [0.0]))
-    e = util.hostsim_engine()
+    if on_gpu:
+        from phaser_b200.engine import Engine
+        e = Engine(device="cuda:%d" % int(os.environ.get("LOCAL_RANK", os.environ["RANK"])))
+    else:
+        e = util.hostsim_engine()
     res = shard.run_sharded(e, vt, batches, P, n_fragments=len(fd.names))
     rc = 0
     if dist.get_rank() == 0:
