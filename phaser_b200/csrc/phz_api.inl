@@ -66,6 +66,7 @@ static ReadsView view_of(const phz_reads* r, int nc) {
   v.n_records = r->n_records; v.n_contigs = nc; v.contig_rec_off = nullptr;
   v.pos = r->pos; v.tlen = r->tlen; v.aln_score = r->aln_score; v.frag = r->frag;
   v.cigar_off = r->cigar_off; v.cigar = r->cigar; v.seq_off = (const u64*)r->seq_off; v.seq = r->seq; v.qual = r->qual;
+  v.n_cigar_ops = r->n_cigar_ops;
   return v;
 }
 

@@ -25,6 +25,31 @@ struct ReadsView {
   const u64* seq_off;              // [R+1]
   const u8* seq;                   // nibble packed
   const u8* qual;
+  int64_t n_cigar_ops;
+  // field accessors (the tile kernel substitutes a view whose slabs live in shared memory)
+  PHZ_HD int32_t pos_at(int64_t r) const { return pos[r]; }
+  PHZ_HD int32_t tlen_at(int64_t r) const { return tlen[r]; }
+  PHZ_HD u32 cig_lo(int64_t r) const { return cigar_off[r]; }
+  PHZ_HD u32 cig_hi(int64_t r) const { return cigar_off[r + 1]; }
+  PHZ_HD u32 cigar_at(u32 k) const { return cigar[k]; }
+  PHZ_HD u64 seq_off_at(int64_t r) const { return seq_off[r]; }
+  PHZ_HD int aln_at(int64_t r) const { return aln_score[r]; }
+};
+
+// The same record fields, served from the shared-memory slabs a tile's TMA bulk copies filled
+// (records [r0, r0+256)); CIGAR words beyond the staged slab fall back to global memory.
+struct TileRV {
+  int64_t r0;
+  const int32_t* s_pos; const int32_t* s_tlen; const u32* s_coff; const u32* s_cig; const u64* s_soff; const int16_t* s_as;
+  u32 cig_base, cig_n;
+  const u32* cigar; const u8* seq; const u8* qual;
+  PHZ_HD int32_t pos_at(int64_t r) const { return s_pos[r - r0]; }
+  PHZ_HD int32_t tlen_at(int64_t r) const { return s_tlen[r - r0]; }
+  PHZ_HD u32 cig_lo(int64_t r) const { return s_coff[r - r0]; }
+  PHZ_HD u32 cig_hi(int64_t r) const { return s_coff[r - r0 + 1]; }
+  PHZ_HD u32 cigar_at(u32 k) const { u32 i = k - cig_base; return i < cig_n ? s_cig[i] : cigar[k]; }
+  PHZ_HD u64 seq_off_at(int64_t r) const { return s_soff[r - r0]; }
+  PHZ_HD int aln_at(int64_t r) const { return s_as[r - r0]; }
 };
 
 struct VariantsView {
@@ -54,7 +79,8 @@ PHZ_HD bool isize_ok(int32_t tlen, double cutoff) {
   return (double)t <= cutoff;
 }
 
-PHZ_HD u8 masked_base(const ReadsView& rv, u64 base_off, int q, int baseq) {
+template <class RV>
+PHZ_HD u8 masked_base(const RV& rv, u64 base_off, int q, int baseq) {
   u64 i = base_off + (u64)q;
   u8 b = rv.seq[i >> 1];
   b = (i & 1) ? (b & 15) : (b >> 4);
@@ -126,15 +152,15 @@ struct WindowVP {
 // MODE 1 (emit):  writes one tuple per candidate starting at out index `o` (class CLS_NONE when the
 //                 reference would print nothing) and returns the number written.
 // MODE 2 (k-th):  `o` is the ordinal of ONE candidate of this record; writes that tuple at out index 0.
-template <int MODE, class VP>
-PHZ_HD u32 map_record(const ReadsView& rv, const VariantsView& vv, const VP& vp, int64_t r, int contig, int baseq,
+template <int MODE, class RV, class VP>
+PHZ_HD u32 map_record(const RV& rv, const VariantsView& vv, const VP& vp, int64_t r, int contig, int baseq,
                       double isize_cutoff, u64 o, u32* t_rec, u32* t_var, u32* t_misc) {
   constexpr bool EMIT = MODE != 0;
-  if (!isize_ok(rv.tlen[r], isize_cutoff)) return 0;
+  if (!isize_ok(rv.tlen_at(r), isize_cutoff)) return 0;
   const int64_t v0 = vv.contig_var_off[contig], v1 = vv.contig_var_off[contig + 1];
   if (v0 == v1) return 0;
-  const int32_t rpos = rv.pos[r];
-  const u32 c0 = rv.cigar_off[r], c1 = rv.cigar_off[r + 1];
+  const int32_t rpos = rv.pos_at(r);
+  const u32 c0 = rv.cig_lo(r), c1 = rv.cig_hi(r);
   u32 n_out = 0;
   int seg = 0;
   u32 k = c0;
@@ -146,7 +172,7 @@ PHZ_HD u32 map_record(const ReadsView& rv, const VariantsView& vv, const VP& vp,
     const int32_t seg_start = gp, q_start = qp;
     int32_t g_end = gp, q_end = qp;
     for (; k < c1; ++k) {
-      u32 c = rv.cigar[k]; int op = c & 15; int32_t n = (int32_t)(c >> 4);
+      u32 c = rv.cigar_at(k); int op = c & 15; int32_t n = (int32_t)(c >> 4);
       if (op == OP_N) break;
       if (op == OP_M || op == OP_EQ || op == OP_X) { g_end += n; q_end += n; }
       else if (op == OP_D) g_end += n;
@@ -166,8 +192,8 @@ PHZ_HD u32 map_record(const ReadsView& rv, const VariantsView& vv, const VP& vp,
         } else if (MODE == 2 && (u64)n_out + (u64)(hi - lo) <= o) {
           n_out += (u32)(hi - lo);                 // the wanted candidate is in a later segment
         } else if (hi > lo) {
-          const u64 boff = rv.seq_off[r];
-          const int as16 = rv.aln_score[r];
+          const u64 boff = rv.seq_off_at(r);
+          const int as16 = rv.aln_at(r);
           if (MODE == 2) { lo += (int64_t)(o - n_out); hi = lo + 1; }
           for (int64_t j = lo; j < hi; ++j) {
             const int32_t st = (int32_t)((int64_t)vp.at(j) - lo_pos);       // offset in pseudo_read
@@ -176,7 +202,7 @@ PHZ_HD u32 map_record(const ReadsView& rv, const VariantsView& vv, const VP& vp,
             int base = -1;            // 16: deletion placeholder
             int32_t ins_q = -1, ins_n = 0;
             for (u32 x = kseg; x < kend; ++x) {
-              u32 c = rv.cigar[x]; int op = c & 15; int32_t n = (int32_t)(c >> 4);
+              u32 c = rv.cigar_at(x); int op = c & 15; int32_t n = (int32_t)(c >> 4);
               if (op == OP_M || op == OP_EQ || op == OP_X) {
                 int32_t sp = g - seg_start;
                 if (st >= sp && st < sp + n) base = masked_base(rv, boff, q + (st - sp), baseq);
@@ -219,7 +245,7 @@ PHZ_HD u32 map_record(const ReadsView& rv, const VariantsView& vv, const VP& vp,
     }
     if (kend >= c1) break;
     // closing N: advance the reference, open the next segment
-    gp = g_end + (int32_t)(rv.cigar[kend] >> 4);
+    gp = g_end + (int32_t)(rv.cigar_at(kend) >> 4);
     qp = q_end;
     k = kend + 1;
     seg++;

@@ -154,7 +154,7 @@ constexpr int KF_THREADS = 256;
 constexpr int KF_WIN = 1024;                      // het-site positions per slab (4 KB)
 constexpr u64 KF_FLAG_AGG = 1ull << 62, KF_FLAG_PREFIX = 2ull << 62, KF_VALUE_MASK = (1ull << 62) - 1;
 
-struct TileInfo { u32 wbase; u32 contig_wn; u32 hint; };    // contig << 16 | wn ; hint_lo << 16 | bracket length (0xFFFF = none)
+struct TileInfo { u32 wbase; u32 contig_wn; u32 hint; u32 cig0; };    // contig << 16 | wn ; hint_lo << 16 | bracket length (0xFFFF = none) ; first CIGAR word of the tile
 
 PHZ_HD TileInfo tile_info_for(const ReadsView& rv, const VariantsView& vv, int64_t r0) {
   int c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r0);
@@ -170,7 +170,7 @@ PHZ_HD TileInfo tile_info_for(const ReadsView& rv, const VariantsView& vv, int64
   if (r_last >= rv.contig_rec_off[c + 1]) r_last = rv.contig_rec_off[c + 1] - 1;
   int64_t wlast = lower_bound_i32(vv.pos, wlo, v1, rv.pos[r_last]);
   int64_t hint_lo = wlo - wbase, nfirst = wlast - wlo;
-  TileInfo ti; ti.wbase = (u32)wbase; ti.contig_wn = ((u32)c << 16) | (u32)wn;
+  TileInfo ti; ti.wbase = (u32)wbase; ti.contig_wn = ((u32)c << 16) | (u32)wn; ti.cig0 = rv.cigar_off[r0];
   ti.hint = (hint_lo + nfirst <= wn && nfirst < 0xFFFF) ? (((u32)hint_lo << 16) | (u32)nfirst) : 0xFFFFu;
   return ti;
 }
@@ -285,12 +285,25 @@ __global__ void __launch_bounds__(KF_THREADS) k1_fused_kernel(ReadsView rv, Vari
 // coalesced.  A scan over the tile table then gives the canonical offsets and a streaming permute
 // moves each tile's block into (record, segment, variant) order.
 #ifdef __CUDACC__
+constexpr int KT_CIG = 1024;          // CIGAR words staged per tile (4 KB); tiles with more fall back to global loads
+
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, int bytes, unsigned long long* mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
+
 __global__ void __launch_bounds__(KF_THREADS) k1_tile_kernel(ReadsView rv, VariantsView vv, const TileInfo* __restrict__ tiles,
                                                             int baseq, double isize_cutoff, u32* __restrict__ s_rec,
                                                             u32* __restrict__ s_var, u32* __restrict__ s_misc, u64 capacity,
                                                             unsigned long long* cursor, u32* __restrict__ tile_base,
                                                             u32* __restrict__ tile_cnt) {
   __shared__ __align__(128) int32_t win[KF_WIN];
+  __shared__ __align__(128) int32_t sh_pos[KF_THREADS];
+  __shared__ __align__(128) int32_t sh_tlen[KF_THREADS];
+  __shared__ __align__(128) u32 sh_coff[KF_THREADS + 4];
+  __shared__ __align__(128) u32 sh_cig[KT_CIG];
+  __shared__ __align__(128) u64 sh_soff[KF_THREADS];
+  __shared__ __align__(128) int16_t sh_as[KF_THREADS];
   __shared__ __align__(8) unsigned long long mbar;
   __shared__ u32 warp_sum[KF_THREADS / 32];
   __shared__ u32 excl_of[KF_THREADS + 1];
@@ -299,34 +312,55 @@ __global__ void __launch_bounds__(KF_THREADS) k1_tile_kernel(ReadsView rv, Varia
   const int64_t tile = blockIdx.x;
   const TileInfo ti = tiles[tile];
   const int wn = (int)(ti.contig_wn & 0xFFFF);
+  const int64_t r0 = tile * KF_THREADS;
+  const int nrec = (int)((rv.n_records - r0) < KF_THREADS ? (rv.n_records - r0) : KF_THREADS);
+  // CIGAR slab: words [cig_al, cig_al + cig_n) with a 16-byte aligned start
+  const u32 cig_al = ti.cig0 & ~3u;
+  int64_t cig_left = rv.n_cigar_ops - (int64_t)cig_al;
+  const u32 cig_n = (u32)(cig_left < KT_CIG ? cig_left : KT_CIG);
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    int nb = wn & ~3, bytes = nb * 4;
+    // every slab is [multiple of 16 bytes] by TMA + a short tail by plain loads
+    const int n4 = nrec & ~3, n2 = nrec & ~1, n8 = nrec & ~7, nw = wn & ~3, nc4 = (int)(cig_n & ~3u);
+    const int bytes = nw * 4 + n4 * 4 + n4 * 4 + n4 * 4 + nc4 * 4 + n2 * 8 + n8 * 2;
     if (bytes > 0) {
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(smem_u32(win)), "l"(vv.pos + ti.wbase), "r"(bytes), "r"(smem_u32(&mbar)) : "memory");
+      if (nw) tma_load_1d(win, vv.pos + ti.wbase, nw * 4, &mbar);
+      if (n4) {
+        tma_load_1d(sh_pos, rv.pos + r0, n4 * 4, &mbar);
+        tma_load_1d(sh_tlen, rv.tlen + r0, n4 * 4, &mbar);
+        tma_load_1d(sh_coff, rv.cigar_off + r0, n4 * 4, &mbar);
+      }
+      if (nc4) tma_load_1d(sh_cig, rv.cigar + cig_al, nc4 * 4, &mbar);
+      if (n2) tma_load_1d(sh_soff, rv.seq_off + r0, n2 * 8, &mbar);
+      if (n8) tma_load_1d(sh_as, rv.aln_score + r0, n8 * 2, &mbar);
     }
-    for (int i = nb; i < wn; ++i) win[i] = vv.pos[(int64_t)ti.wbase + i];
+    for (int i = nw; i < wn; ++i) win[i] = vv.pos[(int64_t)ti.wbase + i];
+    for (int i = n4; i < nrec; ++i) { sh_pos[i] = rv.pos[r0 + i]; sh_tlen[i] = rv.tlen[r0 + i]; sh_coff[i] = rv.cigar_off[r0 + i]; }
+    sh_coff[nrec] = rv.cigar_off[r0 + nrec];
+    for (u32 i = (u32)nc4; i < cig_n; ++i) sh_cig[i] = rv.cigar[cig_al + i];
+    for (int i = n2; i < nrec; ++i) sh_soff[i] = rv.seq_off[r0 + i];
+    for (int i = n8; i < nrec; ++i) sh_as[i] = rv.aln_score[r0 + i];
+    s_base = (unsigned long long)bytes;
   }
-  const int64_t r0 = tile * KF_THREADS;
   const int64_t r = r0 + tid;
-  const bool live = r < rv.n_records;
+  const bool live = tid < nrec;
   const int contig0 = (int)(ti.contig_wn >> 16);
   const int64_t contig0_end = rv.contig_rec_off[contig0 + 1];
   int contig = contig0;
   if (live && r >= contig0_end) contig = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r);
   __syncthreads();                                   // mbarrier initialised, tail elements visible
-  if ((wn & ~3) > 0) {
+  if (s_base > 0) {
     u32 done = 0;
     while (!done) {
       asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                    : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0) : "memory");
     }
   }
+  const TileRV trv{r0, sh_pos, sh_tlen, sh_coff, sh_cig, sh_soff, sh_as, cig_al, cig_n, rv.cigar, rv.seq, rv.qual};
   const WindowVP vp = window_of(ti, vv.pos, win, contig == contig0);
-  const u32 cnt = live ? map_record<0>(rv, vv, vp, r, contig, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr) : 0u;
+  const u32 cnt = live ? map_record<0>(trv, vv, vp, r, contig, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr) : 0u;
   // ---- CTA exclusive scan of the counts
   u32 incl = cnt;
   #pragma unroll
@@ -354,7 +388,7 @@ __global__ void __launch_bounds__(KF_THREADS) k1_tile_kernel(ReadsView rv, Varia
     int c = contig0;
     if (rr >= contig0_end) c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, rr);
     const WindowVP vpk = window_of(ti, vv.pos, win, c == contig0);
-    map_record<2>(rv, vv, vpk, rr, c, baseq, isize_cutoff, (u64)(i - excl_of[lo]), s_rec + base + i, s_var + base + i,
+    map_record<2>(trv, vv, vpk, rr, c, baseq, isize_cutoff, (u64)(i - excl_of[lo]), s_rec + base + i, s_var + base + i,
                   s_misc + base + i);
   }
 }
