@@ -139,6 +139,8 @@ class Params:
         self.id_separator = "_"
         self.unique_ids = 0
         self.output_read_ids = 0
+        self.pass_only = 1
+        self.remove_dups = 1
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise AttributeError(k)

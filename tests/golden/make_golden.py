@@ -188,6 +188,22 @@ def synth_case(name, seed, n_variants, n_pairs, n_bams, args, **read_kw):
     run_case(name, vt, sams, args)
 
 
+def option_case(name, base, args, mapq="255", paired_end="1"):
+    """Same inputs as case `base` (not stored twice), other command-line options."""
+    b = os.path.join(CASES, base)
+    meta = json.load(open(os.path.join(b, "case.json")))
+    vcf_text = gzip.open(os.path.join(b, "in.vcf.gz"), "rt").read()
+    sams = [(bn, open(os.path.join(b, bn)).read()) for bn in meta["bams"]]
+    run_case(name, vcf_text, sams, args, mapq=mapq, paired_end=paired_end)
+    d = os.path.join(CASES, name)
+    for bn in meta["bams"]:
+        os.remove(os.path.join(d, bn))
+    os.remove(os.path.join(d, "in.vcf.gz"))
+    m = json.load(open(os.path.join(d, "case.json")))
+    m["inputs"] = base
+    json.dump(m, open(os.path.join(d, "case.json"), "w"), indent=1)
+
+
 def main():
     os.makedirs(CASES, exist_ok=True)
     v, s = quirk_case()
@@ -196,6 +212,12 @@ def main():
     synth_case("rna_small", 21, 160, 900, 1, [])
     synth_case("rna_two_bams", 22, 160, 700, 2, ["--haplo_count_bam_exclude", "2"])
     synth_case("rna_conflict", 23, 120, 1500, 1, ["--max_block_size", "4"], switch_per_base=0.03)
+    option_case("opt_maf_gwvcf2", "rna_conflict", ["--gw_phase_method", "1", "--gw_phase_vcf", "2", "--max_block_size", "4"])
+    option_case("opt_gwvcf1", "rna_small", ["--gw_phase_vcf", "1", "--gw_phase_vcf_min_confidence", "0.6"])
+    option_case("opt_nounphased_uid", "rna_two_bams", ["--unphased_vars", "0", "--unique_ids", "1", "--id_separator", "-"])
+    option_case("opt_filters", "rna_small", ["--pass_only", "0", "--remove_dups", "0", "--cc_threshold", "0.05", "--as_q_cutoff", "0.2"],
+                paired_end="0")
+    option_case("opt_quirks_baseq", "quirks", ["--as_q_cutoff", "0", "--max_block_size", "3"], mapq="0")
 
 
 if __name__ == "__main__":

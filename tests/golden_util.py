@@ -17,9 +17,10 @@ def load_case(name):
     with open(os.path.join(d, "case.json")) as f:
         meta = json.load(f)
     ref = {k: open(os.path.join(d, fn)).read() for k, fn in FILES.items()}
-    sams = [os.path.join(d, b) for b in meta["bams"]]
+    src = os.path.join(CASES, meta["inputs"]) if "inputs" in meta else d
+    sams = [os.path.join(src, b) for b in meta["bams"]]
     mapper = {b: open(os.path.join(d, "ref.mapper.%s.tsv" % b)).read() for b in meta["bams"]}
-    return dict(dir=d, vcf=os.path.join(d, "in.vcf.gz"), sams=sams, meta=meta, ref=ref, mapper=mapper)
+    return dict(dir=d, vcf=os.path.join(src, "in.vcf.gz"), sams=sams, meta=meta, ref=ref, mapper=mapper)
 
 
 def args_to_kw(args):
@@ -36,6 +37,12 @@ def args_to_kw(args):
             kw["max_block_size"] = int(v)
         elif a == "--haplo_count_bam_exclude":
             kw["exclude"] = [int(x) - 1 for x in v.split(",")]
+        elif a in ("--gw_phase_method", "--gw_phase_vcf", "--unphased_vars", "--unique_ids", "--pass_only", "--remove_dups"):
+            kw[a[2:]] = int(v)
+        elif a in ("--gw_phase_vcf_min_confidence", "--cc_threshold"):
+            kw[a[2:]] = float(v)
+        elif a == "--id_separator":
+            kw["id_separator"] = v
         else:
             raise KeyError(a)
     return kw

@@ -17,7 +17,7 @@ def test_backend_is_the_cuda_library(gpu):
 def test_files_match_reference(gpu, name):
     c = G.load_case(name)
     kw = G.args_to_kw(c["meta"]["args"])
-    got, res, _ = util.product_outputs(gpu, c["vcf"], c["sams"], **kw)
+    got, res, _ = util.product_outputs(gpu, c["vcf"], c["sams"], mapq=c["meta"]["mapq"], paired_end=c["meta"]["paired_end"], **kw)
     bad = compare.diff_outputs(c["ref"], got)
     assert not bad, "\n".join(bad)
     own, lib = gpu.launch_counts()
@@ -27,7 +27,10 @@ def test_files_match_reference(gpu, name):
 @pytest.mark.parametrize("name", G.case_names())
 def test_mapper_tuples_match_oracle(gpu, name):
     c = G.load_case(name)
-    vt, st, batches, col, fd = util.load_inputs(c["vcf"], c["sams"])
+    kw = G.args_to_kw(c["meta"]["args"])
+    vt, st, batches, col, fd = util.load_inputs(c["vcf"], c["sams"], mapq=c["meta"]["mapq"], paired_end=c["meta"]["paired_end"],
+                                                remove_dups=kw.get("remove_dups", 1), pass_only=kw.get("pass_only", 1),
+                                                id_separator=kw.get("id_separator", "_"), gw_phase_method=kw.get("gw_phase_method", 0))
     for batch in batches:
         got, exp = util.compare_tuples(gpu, vt, batch)
         assert got == exp

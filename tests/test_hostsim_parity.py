@@ -11,7 +11,7 @@ from tests import util, golden_util as G
 def test_files_match_reference(hostsim, name):
     c = G.load_case(name)
     kw = G.args_to_kw(c["meta"]["args"])
-    got, res, _ = util.product_outputs(hostsim, c["vcf"], c["sams"], **kw)
+    got, res, _ = util.product_outputs(hostsim, c["vcf"], c["sams"], mapq=c["meta"]["mapq"], paired_end=c["meta"]["paired_end"], **kw)
     bad = compare.diff_outputs(c["ref"], got)
     assert not bad, "\n".join(bad)
 
@@ -19,7 +19,10 @@ def test_files_match_reference(hostsim, name):
 @pytest.mark.parametrize("name", G.case_names())
 def test_mapper_tuples_match_oracle(hostsim, name):
     c = G.load_case(name)
-    vt, st, batches, col, fd = util.load_inputs(c["vcf"], c["sams"])
+    kw = G.args_to_kw(c["meta"]["args"])
+    vt, st, batches, col, fd = util.load_inputs(c["vcf"], c["sams"], mapq=c["meta"]["mapq"], paired_end=c["meta"]["paired_end"],
+                                                remove_dups=kw.get("remove_dups", 1), pass_only=kw.get("pass_only", 1),
+                                                id_separator=kw.get("id_separator", "_"), gw_phase_method=kw.get("gw_phase_method", 0))
     for batch in batches:
         got, exp = util.compare_tuples(hostsim, vt, batch)
         assert got == exp

@@ -59,9 +59,10 @@ def bam_display_names(paths):
     return out
 
 
-def load_inputs(vcf_gz, sams, sample="S1", mapq="255", paired_end="1", remove_dups=1, pass_only=1):
+def load_inputs(vcf_gz, sams, sample="S1", mapq="255", paired_end="1", remove_dups=1, pass_only=1, id_separator="_",
+                gw_phase_method=0):
     col = vcfio.sample_column_map(vcf_gz)[sample]
-    vt, st = vcfio.parse_vcf(vcf_gz, col, pass_only=pass_only)
+    vt, st = vcfio.parse_vcf(vcf_gz, col, pass_only=pass_only, id_separator=id_separator, gw_phase_method=gw_phase_method)
     fd = samio.FragmentDictionary()
     mq = [int(x) for x in str(mapq).split(",")]; pe = [int(x) for x in str(paired_end).split(",")]
     if len(mq) == 1:
@@ -74,23 +75,30 @@ def load_inputs(vcf_gz, sams, sample="S1", mapq="255", paired_end="1", remove_du
 
 def product_outputs(engine, vcf_gz, sams, sample="S1", mapq="255", paired_end="1", max_block_size=15,
                     as_q_cutoff=0.05, cc_threshold=0.01, exclude=(), isize=(0.0,), baseq=10, unphased_vars=1,
-                    gw_phase_vcf=0):
-    vt, st, batches, col, fd = load_inputs(vcf_gz, sams, sample, mapq, paired_end)
+                    gw_phase_vcf=0, gw_phase_method=0, gw_phase_vcf_min_confidence=0.90, unique_ids=0, pass_only=1,
+                    remove_dups=1, id_separator="_"):
+    vt, st, batches, col, fd = load_inputs(vcf_gz, sams, sample, mapq, paired_end, remove_dups, pass_only, id_separator,
+                                           gw_phase_method)
     P = pipeline.PhaseParams(baseq=baseq, isize=list(isize), as_q_cutoff=as_q_cutoff, cc_threshold=cc_threshold,
                              max_block_size=max_block_size, haplo_count_bam_exclude=list(exclude))
     dev = [engine.upload_reads(b) for b in batches]
     res = pipeline.run_path(engine, vt, dev, P, n_fragments=len(fd.names))
-    o = writer.Outputs(res, vt, bam_display_names(sams), P, unphased_vars=unphased_vars)
+    o = writer.Outputs(res, vt, bam_display_names(sams), P, unphased_vars=unphased_vars, gw_phase_method=gw_phase_method,
+                       unique_ids=unique_ids)
     ac = o.allelic_counts(); vc = o.variant_connections()
     hp, hc, cfg = o.block_tables()
     with gzip.open(vcf_gz, "rt") as f:
-        vcf_text, _, _ = o.vcf_text(f.readlines(), col, gw_phase_vcf=gw_phase_vcf)
+        vcf_text, _, _ = o.vcf_text(f.readlines(), col, id_separator=id_separator, gw_phase_vcf=gw_phase_vcf,
+                                    min_conf=gw_phase_vcf_min_confidence)
     return dict(allelic_counts=ac, allele_config=cfg, haplotypes=hp, haplotypic_counts=hc, variant_connections=vc,
                 vcf=vcf_text), res, (vt, batches)
 
 
-def oracle_outputs(vcf_gz, sams, sample="S1", mapq="255", paired_end="1", **kw):
-    vt, st, batches, col, fd = load_inputs(vcf_gz, sams, sample, mapq, paired_end)
+def oracle_outputs(vcf_gz, sams, sample="S1", mapq="255", paired_end="1", pass_only=1, remove_dups=1, exclude=None, **kw):
+    vt, st, batches, col, fd = load_inputs(vcf_gz, sams, sample, mapq, paired_end, remove_dups, pass_only,
+                                           kw.get("id_separator", "_"), kw.get("gw_phase_method", 0))
+    if exclude is not None:
+        kw["haplo_count_bam_exclude"] = list(exclude)
     P = port.Params(bam_names=bam_display_names(sams), **kw)
     res = port.run(vt, batches, P)
     with gzip.open(vcf_gz, "rt") as f:
