@@ -115,6 +115,22 @@ int phz_stage_report(phz_ctx* ctx, char* buf, int64_t buf_len);
 /* kernels of this library launched so far / library (CUB) passes launched so far */
 int phz_launch_counts(phz_ctx* ctx, uint64_t* own, uint64_t* library);
 
+/* ---- native host ingest (no GPU involved): BAM (BGZF, parallel inflate) or SAM text -> phz_reads with
+ * HOST pointers.  Replaces `samtools view -h BAM chr: | samtools view -Sh [-F 0x400] [-f 2] -q MAPQ`
+ * (phaser.py:1346) and the mapper's per-line parsing (read_variant_map.py:25-64).  Records come out
+ * grouped by contig in the order of `contigs` (the VCF's), file order inside a contig.  A fragment
+ * dictionary gives one id per distinct QNAME and is shared by all BAMs of a run. */
+typedef struct phz_fragdict phz_fragdict;
+typedef struct phz_host_reads phz_host_reads;
+phz_fragdict* phz_fragdict_create(void);
+void phz_fragdict_destroy(phz_fragdict* d);
+int64_t phz_fragdict_size(phz_fragdict* d);
+int64_t phz_fragdict_name(phz_fragdict* d, int64_t id, char* buf, int64_t buflen);
+phz_host_reads* phz_read_alignments(const char* path, const char* const* contigs, int n_contigs, phz_fragdict* d,
+                                    int remove_dups, int proper_pair, int min_mapq, int n_threads);
+int phz_host_reads_view(phz_host_reads* r, phz_reads* out, int* sorted_by_coordinate);
+void phz_host_reads_free(phz_host_reads* r);
+
 #ifdef __cplusplus
 }
 #endif

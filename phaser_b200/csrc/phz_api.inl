@@ -205,3 +205,5 @@ int phz_launch_counts(phz_ctx* ctx, uint64_t* own, uint64_t* library) {
 }
 
 }  // extern "C"
+
+#include "phz_io.inl"

@@ -1,0 +1,368 @@
+// Native host ingest: BAM (BGZF) or SAM text -> the packed SoA layout of include/phz.h.
+//
+// Replaces the two `samtools view` stages of the reference pipeline and the per-line parsing of its
+// mapper (phaser/phaser.py:1346, read_variant_map.py:25-64) -- SURVEY.md section 8f row N2.  BGZF
+// blocks are inflated in parallel (zlib, one raw-deflate stream per block), records are decoded
+// straight into the device layout (BAM's 4-bit bases / len<<4|op CIGAR words / phred bytes ARE that
+// layout), filters as the reference's samtools arguments (phaser.py:505-513): contig named by the
+// VCF, -F 0x400 iff remove_dups, -f 2 iff paired_end, -q MAPQ.  Fragment ids: one per distinct QNAME,
+// shared by all BAMs of a run (exact: names are compared, not just hashed).
+#include <zlib.h>
+#include <thread>
+#include <atomic>
+#include <fstream>
+
+namespace phzio {
+
+using phz::u64; using phz::u32; using phz::u8; using phz::PhzError;
+
+struct FragDict {
+  // open addressing over (hash, arena offset); names live in one arena
+  std::vector<u64> slot_hash; std::vector<u32> slot_id;
+  std::vector<u64> name_off; std::string arena;
+  size_t mask = 0, count = 0;
+  FragDict() { resize(1 << 16); }
+  void resize(size_t n) {
+    std::vector<u64> oh(n, 0); std::vector<u32> oi(n, 0xFFFFFFFFu);
+    for (size_t i = 0; i < slot_hash.size(); ++i)
+      if (slot_id[i] != 0xFFFFFFFFu) { size_t p = slot_hash[i] & (n - 1); while (oi[p] != 0xFFFFFFFFu) p = (p + 1) & (n - 1); oh[p] = slot_hash[i]; oi[p] = slot_id[i]; }
+    slot_hash.swap(oh); slot_id.swap(oi); mask = n - 1;
+  }
+  static u64 hash(const char* s, size_t n) {
+    u64 h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; ++i) { h ^= (u8)s[i]; h *= 1099511628211ull; }
+    h ^= h >> 29; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 32;
+    return h;
+  }
+  u32 get(const char* s, size_t n) {
+    u64 h = hash(s, n);
+    size_t p = h & mask;
+    while (slot_id[p] != 0xFFFFFFFFu) {
+      if (slot_hash[p] == h) {
+        u32 id = slot_id[p]; u64 o = name_off[id]; size_t len = (size_t)(name_off[id + 1] - o);
+        if (len == n && std::memcmp(arena.data() + o, s, n) == 0) return id;
+      }
+      p = (p + 1) & mask;
+    }
+    u32 id = (u32)count++;
+    if (name_off.empty()) name_off.push_back(0);
+    arena.append(s, n); name_off.push_back(arena.size());
+    slot_hash[p] = h; slot_id[p] = id;
+    if (count * 2 > mask + 1) resize((mask + 1) * 2);
+    return id;
+  }
+};
+
+struct HostReads {
+  int n_contigs = 0;
+  std::vector<int64_t> contig_rec_off;
+  std::vector<int32_t> pos, tlen; std::vector<int16_t> aln; std::vector<u32> frag, cigar_off, cigar;
+  std::vector<u64> seq_off; std::vector<u8> seq, qual;
+  int sorted = 1;
+  std::string error;
+};
+
+static bool read_file(const char* path, std::vector<u8>& out) {
+  std::ifstream f(path, std::ios::binary | std::ios::ate);
+  if (!f) return false;
+  std::streamsize n = f.tellg(); f.seekg(0);
+  out.resize((size_t)n);
+  return n == 0 || (bool)f.read((char*)out.data(), n);
+}
+
+// ---- BGZF: index the blocks, inflate them in parallel into one buffer
+static void inflate_bgzf(const std::vector<u8>& in, std::vector<u8>& out, int n_threads) {
+  struct Blk { size_t in_off, in_len, out_off, out_len; };
+  std::vector<Blk> blks;
+  size_t p = 0, total = 0;
+  while (p + 18 <= in.size()) {
+    if (in[p] != 0x1f || in[p + 1] != 0x8b) throw PhzError("corrupt BGZF block header");
+    u32 xlen = in[p + 10] | (in[p + 11] << 8);
+    size_t q = p + 12, xe = q + xlen; u32 bsize = 0; bool found = false;
+    while (q + 4 <= xe) {
+      u32 slen = in[q + 2] | (in[q + 3] << 8);
+      if (in[q] == 'B' && in[q + 1] == 'C' && slen == 2) { bsize = (in[q + 4] | (in[q + 5] << 8)) + 1; found = true; }
+      q += 4 + slen;
+    }
+    if (!found || p + bsize > in.size()) throw PhzError("BGZF block without BC field or truncated file");
+    u32 isize = in[p + bsize - 4] | (in[p + bsize - 3] << 8) | (in[p + bsize - 2] << 16) | ((u32)in[p + bsize - 1] << 24);
+    blks.push_back(Blk{xe, p + bsize - 8 - xe, total, isize});
+    total += isize; p += bsize;
+  }
+  out.resize(total);
+  std::atomic<size_t> next(0); std::atomic<int> bad(0);
+  auto work = [&]() {
+    z_stream zs;
+    while (true) {
+      size_t i = next.fetch_add(1);
+      if (i >= blks.size()) break;
+      const Blk& b = blks[i];
+      if (b.out_len == 0) continue;
+      std::memset(&zs, 0, sizeof(zs));
+      if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; break; }
+      zs.next_in = (Bytef*)(in.data() + b.in_off); zs.avail_in = (uInt)b.in_len;
+      zs.next_out = out.data() + b.out_off; zs.avail_out = (uInt)b.out_len;
+      int rc = inflate(&zs, Z_FINISH);
+      inflateEnd(&zs);
+      if (rc != Z_STREAM_END) { bad = 1; break; }
+    }
+  };
+  if (n_threads < 1) n_threads = 1;
+  std::vector<std::thread> th;
+  for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+  if (bad) throw PhzError("BGZF inflate failed");
+}
+
+static void inflate_gzip_stream(const std::vector<u8>& in, std::vector<u8>& out) {
+  z_stream zs; std::memset(&zs, 0, sizeof(zs));
+  if (inflateInit2(&zs, 31) != Z_OK) throw PhzError("zlib init failed");
+  out.clear(); std::vector<u8> buf(1 << 20);
+  zs.next_in = (Bytef*)in.data(); zs.avail_in = (uInt)in.size();
+  while (true) {
+    zs.next_out = buf.data(); zs.avail_out = (uInt)buf.size();
+    int rc = inflate(&zs, Z_NO_FLUSH);
+    out.insert(out.end(), buf.data(), buf.data() + (buf.size() - zs.avail_out));
+    if (rc == Z_STREAM_END) { if (zs.avail_in == 0) break; if (inflateReset(&zs) != Z_OK) break; continue; }
+    if (rc != Z_OK) { inflateEnd(&zs); throw PhzError("gzip inflate failed"); }
+  }
+  inflateEnd(&zs);
+}
+
+struct Rec {              // one alignment that passed the filters, as offsets into the raw buffer
+  int contig; int32_t pos, tlen; int16_t aln; u32 frag;
+  const u8* cig; u32 n_cig;        // BAM: packed words; SAM: text
+  const u8* seq; const u8* qual; u32 l_seq;
+  bool text;
+};
+
+struct BaseTable {
+  u8 t[256];
+  BaseTable() {
+    const char* alpha = "=ACMGRSVTWYHKDBN";      // BAM 4-bit codes; anything else encodes as N, like samtools
+    for (int i = 0; i < 256; ++i) t[i] = 15;
+    for (int i = 0; i < 16; ++i) t[(u8)alpha[i]] = (u8)i;
+  }
+};
+static const BaseTable BASE_OF_TABLE;
+
+static int16_t as_from_aux(const u8* p, const u8* end, std::string& err) {
+  while (p + 3 <= end) {
+    char t0 = p[0], t1 = p[1], ty = p[2]; p += 3;
+    bool is_as = (t0 == 'A' && t1 == 'S');
+    int64_t v = 0; bool have = false;
+    switch (ty) {
+      case 'A': p += 1; break;
+      case 'c': v = (int8_t)p[0]; have = true; p += 1; break;
+      case 'C': v = p[0]; have = true; p += 1; break;
+      case 's': v = (int16_t)(p[0] | (p[1] << 8)); have = true; p += 2; break;
+      case 'S': v = (uint16_t)(p[0] | (p[1] << 8)); have = true; p += 2; break;
+      case 'i': v = (int32_t)(p[0] | (p[1] << 8) | (p[2] << 16) | ((u32)p[3] << 24)); have = true; p += 4; break;
+      case 'I': v = (u32)(p[0] | (p[1] << 8) | (p[2] << 16) | ((u32)p[3] << 24)); have = true; p += 4; break;
+      case 'f': p += 4; break;
+      case 'Z': case 'H': while (p < end && *p) ++p; ++p; break;
+      case 'B': { char st = p[0]; u32 n = p[1] | (p[2] << 8) | (p[3] << 16) | ((u32)p[4] << 24); p += 5;
+                  int w = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4; p += (size_t)n * w; break; }
+      default: return -32768;
+    }
+    if (is_as && have) {
+      if (v < -32767 || v > 32767) { err = "AS:i value outside the int16 range of the packed layout"; return -32768; }
+      return (int16_t)v;
+    }
+  }
+  return -32768;
+}
+
+static HostReads* build(std::vector<Rec>& recs, int nc) {
+  HostReads* H = new HostReads();
+  H->n_contigs = nc;
+  size_t R = recs.size();
+  std::vector<int64_t> cnt(nc + 1, 0);
+  for (auto& r : recs) cnt[r.contig + 1]++;
+  H->contig_rec_off.assign(nc + 1, 0);
+  for (int c = 0; c < nc; ++c) H->contig_rec_off[c + 1] = H->contig_rec_off[c] + cnt[c + 1];
+  std::vector<int64_t> cur(H->contig_rec_off.begin(), H->contig_rec_off.end() - 1);
+  std::vector<u32> order(R);
+  for (size_t i = 0; i < R; ++i) order[cur[recs[i].contig]++] = (u32)i;      // stable: file order inside a contig
+  H->pos.resize(R); H->tlen.resize(R); H->aln.resize(R); H->frag.resize(R);
+  H->cigar_off.assign(R + 1, 0); H->seq_off.assign(R + 1, 0);
+  // sizes
+  for (size_t k = 0; k < R; ++k) {
+    const Rec& r = recs[order[k]];
+    u32 nops = r.n_cig;
+    if (r.text) { nops = 0; for (u32 i = 0; i < r.n_cig; ++i) if (r.cig[i] < '0' || r.cig[i] > '9') nops++; if (r.n_cig == 1 && r.cig[0] == '*') nops = 0; }
+    H->cigar_off[k + 1] = H->cigar_off[k] + nops;
+    H->seq_off[k + 1] = H->seq_off[k] + r.l_seq;
+  }
+  H->cigar.resize(H->cigar_off[R]);
+  u64 nb = H->seq_off[R];
+  H->qual.resize(nb); H->seq.assign((nb + 1) / 2, 0);
+  static const char* OPS = "MIDNSHP=X";
+  for (size_t k = 0; k < R; ++k) {
+    const Rec& r = recs[order[k]];
+    H->pos[k] = r.pos; H->tlen[k] = r.tlen; H->aln[k] = r.aln; H->frag[k] = r.frag;
+    u32* co = H->cigar.data() + H->cigar_off[k];
+    if (!r.text) {
+      std::memcpy(co, r.cig, (size_t)r.n_cig * 4);
+    } else if (!(r.n_cig == 1 && r.cig[0] == '*')) {
+      u32 n = 0, w = 0;
+      for (u32 i = 0; i < r.n_cig; ++i) {
+        u8 ch = r.cig[i];
+        if (ch >= '0' && ch <= '9') n = n * 10 + (ch - '0');
+        else { const char* q = std::strchr(OPS, ch); co[w++] = (n << 4) | (u32)(q ? q - OPS : 0); n = 0; }
+      }
+    }
+    u64 b0 = H->seq_off[k];
+    for (u32 j = 0; j < r.l_seq; ++j) {
+      u8 code = r.text ? BASE_OF_TABLE.t[r.seq[j]] : ((j & 1) ? (r.seq[j >> 1] & 15) : (r.seq[j >> 1] >> 4));
+      u64 i = b0 + j;
+      H->seq[i >> 1] |= (i & 1) ? code : (u8)(code << 4);
+      int q = r.text ? (int)r.qual[j] - 33 : (int)r.qual[j];
+      H->qual[i] = (u8)(q < 0 ? 0 : q);
+    }
+  }
+  for (int c = 0; c < nc; ++c)
+    for (int64_t k = H->contig_rec_off[c] + 1; k < H->contig_rec_off[c + 1]; ++k)
+      if (H->pos[k] < H->pos[k - 1]) { H->sorted = 0; break; }
+  return H;
+}
+
+static HostReads* parse_bam(const std::vector<u8>& d, const char* const* contigs, int nc, FragDict* fd, int remove_dups,
+                            int proper_pair, int min_mapq) {
+  auto rd32 = [&](size_t o) { return (int32_t)(d[o] | (d[o + 1] << 8) | (d[o + 2] << 16) | ((u32)d[o + 3] << 24)); };
+  if (d.size() < 12 || std::memcmp(d.data(), "BAM\1", 4) != 0) throw PhzError("not a BAM file");
+  size_t p = 8 + (size_t)rd32(4);
+  int n_ref = rd32(p); p += 4;
+  std::vector<int> ref_to_contig(n_ref, -1);
+  for (int i = 0; i < n_ref; ++i) {
+    int ln = rd32(p); p += 4;
+    std::string name((const char*)d.data() + p, ln > 0 ? ln - 1 : 0); p += ln + 4;
+    for (int c = 0; c < nc; ++c) if (name == contigs[c]) ref_to_contig[i] = c;
+  }
+  std::vector<Rec> recs;
+  std::string err;
+  while (p + 4 <= d.size()) {
+    int32_t bs = rd32(p); size_t s = p + 4; p = s + (size_t)bs;
+    if (p > d.size()) throw PhzError("truncated BAM record");
+    int ref = rd32(s); if (ref < 0 || ref >= n_ref) continue;
+    int ci = ref_to_contig[ref]; if (ci < 0) continue;
+    u32 l_rn = d[s + 8], mapq = d[s + 9], n_cig = d[s + 12] | (d[s + 13] << 8), flag = d[s + 14] | (d[s + 15] << 8);
+    int32_t l_seq = rd32(s + 16);
+    if (remove_dups && (flag & 0x400)) continue;
+    if (proper_pair && !(flag & 2)) continue;
+    if ((int)mapq < min_mapq) continue;
+    size_t o = s + 32;
+    Rec r; r.text = false; r.contig = ci; r.pos = rd32(s + 4) + 1; r.tlen = rd32(s + 28);
+    r.frag = fd->get((const char*)d.data() + o, l_rn ? l_rn - 1 : 0); o += l_rn;
+    r.cig = d.data() + o; r.n_cig = n_cig; o += (size_t)n_cig * 4;
+    r.seq = d.data() + o; o += ((size_t)l_seq + 1) / 2; r.qual = d.data() + o; r.l_seq = (u32)l_seq; o += l_seq;
+    if (l_seq > 0 && r.qual[0] == 0xFF) throw PhzError("record without QUAL (unsupported)");
+    r.aln = as_from_aux(d.data() + o, d.data() + p, err);
+    if (!err.empty()) throw PhzError(err);
+    recs.push_back(r);
+  }
+  return build(recs, nc);
+}
+
+static HostReads* parse_sam(const std::vector<u8>& d, const char* const* contigs, int nc, FragDict* fd, int remove_dups,
+                            int proper_pair, int min_mapq) {
+  std::vector<Rec> recs;
+  const u8* p = d.data(); const u8* end = p + d.size();
+  while (p < end) {
+    const u8* eol = (const u8*)std::memchr(p, '\n', end - p); if (!eol) eol = end;
+    const u8* le = eol; if (le > p && le[-1] == '\r') --le;
+    if (p < le && *p != '@') {
+      const u8* f[12]; int nf = 0; const u8* q = p; f[nf++] = q;
+      while (q < le && nf < 12) { if (*q == '\t') f[nf++] = q + 1; ++q; }
+      if (nf >= 11) {
+        auto len = [&](int i) { return (size_t)((i + 1 < nf ? f[i + 1] - 1 : le) - f[i]); };
+        auto toint = [&](int i) { return std::strtol(std::string((const char*)f[i], len(i)).c_str(), nullptr, 10); };
+        std::string rname((const char*)f[2], len(2));
+        int ci = -1; for (int c = 0; c < nc; ++c) if (rname == contigs[c]) { ci = c; break; }
+        long flag = toint(1), mapq = toint(4);
+        if (ci >= 0 && !(remove_dups && (flag & 0x400)) && !(proper_pair && !(flag & 2)) && mapq >= min_mapq) {
+          Rec r; r.text = true; r.contig = ci; r.pos = (int32_t)toint(3); r.tlen = (int32_t)toint(8);
+          r.frag = fd->get((const char*)f[0], len(0));
+          r.cig = f[5]; r.n_cig = (u32)len(5);
+          r.seq = f[9]; r.l_seq = (u32)len(9);
+          const u8* qe = le; if (nf > 11) qe = f[11] - 1;
+          r.qual = f[10]; size_t lq = (size_t)(qe - f[10]);
+          if (r.l_seq == 1 && r.seq[0] == '*') r.l_seq = 0;
+          if (lq != r.l_seq) throw PhzError("SAM record with QUAL missing or not the length of SEQ (unsupported)");
+          r.aln = -32768;
+          if (nf > 11) {          // first AS: tag from column 12 on (read_variant_map.py:56-59)
+            const u8* t = f[11];
+            while (t < le) {
+              const u8* te = (const u8*)std::memchr(t, '\t', le - t); if (!te) te = le;
+              if (te - t > 5 && t[0] == 'A' && t[1] == 'S' && t[2] == ':') {
+                const u8* c2 = (const u8*)std::memchr(t + 3, ':', te - t - 3);
+                if (c2) { long v = std::strtol(std::string((const char*)c2 + 1, te - c2 - 1).c_str(), nullptr, 10);
+                          if (v < -32767 || v > 32767) throw PhzError("AS:i value outside the int16 range of the packed layout");
+                          r.aln = (int16_t)v; break; }
+              }
+              t = te + 1;
+            }
+          }
+          recs.push_back(r);
+        }
+      }
+    }
+    p = eol + 1;
+  }
+  return build(recs, nc);
+}
+
+}  // namespace phzio
+
+struct phz_fragdict { phzio::FragDict d; };
+struct phz_host_reads { phzio::HostReads* h; };
+
+extern "C" {
+
+phz_fragdict* phz_fragdict_create(void) { return new phz_fragdict(); }
+void phz_fragdict_destroy(phz_fragdict* d) { delete d; }
+int64_t phz_fragdict_size(phz_fragdict* d) { return (int64_t)d->d.count; }
+int64_t phz_fragdict_name(phz_fragdict* d, int64_t id, char* buf, int64_t buflen) {
+  if (id < 0 || (size_t)id >= d->d.count) return -1;
+  u64 o = d->d.name_off[id]; int64_t n = (int64_t)(d->d.name_off[id + 1] - o);
+  if (n + 1 > buflen) return -(n + 1);
+  std::memcpy(buf, d->d.arena.data() + o, n); buf[n] = 0;
+  return n;
+}
+
+phz_host_reads* phz_read_alignments(const char* path, const char* const* contigs, int n_contigs, phz_fragdict* fd,
+                                    int remove_dups, int proper_pair, int min_mapq, int n_threads) {
+  try {
+    std::vector<u8> raw;
+    if (!phzio::read_file(path, raw)) throw PhzError(std::string("cannot read ") + path);
+    std::vector<u8> data;
+    bool gz = raw.size() >= 18 && raw[0] == 0x1f && raw[1] == 0x8b;
+    bool bgzf = gz && (raw[3] & 4) && raw[12] == 'B' && raw[13] == 'C';
+    if (bgzf) phzio::inflate_bgzf(raw, data, n_threads);
+    else if (gz) phzio::inflate_gzip_stream(raw, data);
+    else data.swap(raw);
+    phz_host_reads* out = new phz_host_reads();
+    if (data.size() >= 4 && std::memcmp(data.data(), "BAM\1", 4) == 0)
+      out->h = phzio::parse_bam(data, contigs, n_contigs, &fd->d, remove_dups, proper_pair, min_mapq);
+    else
+      out->h = phzio::parse_sam(data, contigs, n_contigs, &fd->d, remove_dups, proper_pair, min_mapq);
+    return out;
+  } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+
+int phz_host_reads_view(phz_host_reads* r, phz_reads* out, int* sorted) {
+  PHZ_TRY
+  phzio::HostReads* h = r->h;
+  out->n_records = (int64_t)h->pos.size(); out->n_cigar_ops = (int64_t)h->cigar.size(); out->n_bases = (int64_t)h->qual.size();
+  out->h_contig_rec_off = h->contig_rec_off.data();
+  out->pos = h->pos.data(); out->tlen = h->tlen.data(); out->aln_score = h->aln.data(); out->frag = h->frag.data();
+  out->cigar_off = h->cigar_off.data(); out->cigar = h->cigar.data(); out->seq_off = (const uint64_t*)h->seq_off.data();
+  out->seq = h->seq.data(); out->qual = h->qual.data();
+  *sorted = h->sorted;
+  PHZ_CATCH
+}
+
+void phz_host_reads_free(phz_host_reads* r) { if (r) { delete r->h; delete r; } }
+
+}  // extern "C"

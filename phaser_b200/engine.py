@@ -34,7 +34,9 @@ class phz_reads(ctypes.Structure):
 EXPORTS = ["phz_last_error", "phz_backend_name", "phz_create", "phz_destroy", "phz_sync", "phz_set_variants",
            "phz_map_reads", "phz_map_reads_host", "phz_as_histogram", "phz_commit_bam", "phz_build_graph",
            "phz_phase", "phz_read_lists", "phz_array", "phz_download", "phz_counters", "phz_launch_counts",
-           "phz_set_profiling", "phz_map_times", "phz_stage_report", "phz_set_option"]
+           "phz_set_profiling", "phz_map_times", "phz_stage_report", "phz_set_option",
+           "phz_fragdict_create", "phz_fragdict_destroy", "phz_fragdict_size", "phz_fragdict_name", "phz_read_alignments",
+           "phz_host_reads_view", "phz_host_reads_free"]
 
 
 def _declare(lib):
@@ -60,6 +62,16 @@ def _declare(lib):
     lib.phz_map_times.argtypes = [c_void_p, POINTER(ctypes.c_float)]
     lib.phz_stage_report.argtypes = [c_void_p, c_char_p, c_int64]
     lib.phz_set_option.argtypes = [c_void_p, c_char_p, c_int64]
+    lib.phz_fragdict_create.restype = c_void_p
+    lib.phz_fragdict_destroy.argtypes = [c_void_p]
+    lib.phz_fragdict_size.restype = c_int64
+    lib.phz_fragdict_size.argtypes = [c_void_p]
+    lib.phz_fragdict_name.restype = c_int64
+    lib.phz_fragdict_name.argtypes = [c_void_p, c_int64, c_char_p, c_int64]
+    lib.phz_read_alignments.restype = c_void_p
+    lib.phz_read_alignments.argtypes = [c_char_p, POINTER(c_char_p), c_int, c_void_p, c_int, c_int, c_int, c_int]
+    lib.phz_host_reads_view.argtypes = [c_void_p, POINTER(phz_reads), POINTER(c_int)]
+    lib.phz_host_reads_free.argtypes = [c_void_p]
     return lib
 
 
@@ -84,7 +96,81 @@ def _as_torch(a: np.ndarray, device, pin=False):
     t = torch.from_numpy(np.ascontiguousarray(a))
     if pin and torch.cuda.is_available():
         t = t.pin_memory()
-    return t.to(device, non_blocking=False) if device is not None else t
+    if device is None:
+        return t
+    if torch.device(device).type == "cpu":
+        return t.clone()          # never alias caller memory (the native reader's buffers are freed with the batch)
+    return t.to(device, non_blocking=False)
+
+
+class NativeFragmentDictionary:
+    """QNAME -> fragment id kept by the native reader (one namespace for all BAMs of a run)."""
+
+    def __init__(self, lib=None):
+        self.lib = lib if lib is not None else load_library()
+        self.h = self.lib.phz_fragdict_create()
+
+    def __len__(self):
+        return int(self.lib.phz_fragdict_size(self.h))
+
+    @property
+    def names(self):
+        buf = ctypes.create_string_buffer(4096)
+        out = []
+        for i in range(len(self)):
+            n = self.lib.phz_fragdict_name(self.h, i, buf, len(buf))
+            out.append(buf.raw[:n].decode())
+        return out
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.phz_fragdict_destroy(self.h); self.h = None
+        except Exception:
+            pass
+
+
+class _NativeReads:
+    def __init__(self, lib, h):
+        self.lib = lib; self.h = h
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.phz_host_reads_free(self.h); self.h = None
+        except Exception:
+            pass
+
+
+def read_alignments_native(path, contigs, fragdict: NativeFragmentDictionary, remove_dups=True, proper_pair=True,
+                           min_mapq=0, threads=0, lib=None) -> ReadBatch:
+    """BAM (BGZF) or SAM text -> ReadBatch through the native reader (phz_read_alignments).  The arrays are
+    views of native memory owned by the returned batch."""
+    lib = lib if lib is not None else fragdict.lib
+    arr = (c_char_p * len(contigs))(*[c.encode() for c in contigs])
+    h = lib.phz_read_alignments(path.encode(), arr, len(contigs), fragdict.h, int(remove_dups), int(proper_pair),
+                                int(min_mapq), int(threads or (os.cpu_count() or 1)))
+    if not h:
+        raise PhzError(lib.phz_last_error().decode())
+    owner = _NativeReads(lib, h)
+    v = phz_reads(); srt = c_int(0)
+    if lib.phz_host_reads_view(h, byref(v), byref(srt)) != 0:
+        raise PhzError(lib.phz_last_error().decode())
+    if not srt.value:
+        raise PhzError("%s: records are not sorted by coordinate" % path)
+
+    def view(ptr, n, dt):
+        if n == 0 or not ptr:
+            return np.zeros(0, dt)
+        return np.ctypeslib.as_array(ctypes.cast(ptr, POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n,))
+
+    R = v.n_records; nc = len(contigs)
+    rb = ReadBatch(nc, view(v.h_contig_rec_off, nc + 1, np.int64), view(v.pos, R, np.int32), view(v.tlen, R, np.int32),
+                   view(v.aln_score, R, np.int16), view(v.frag, R, np.uint32), view(v.cigar_off, R + 1, np.uint32),
+                   view(v.cigar, v.n_cigar_ops, np.uint32), view(v.seq_off, R + 1, np.uint64),
+                   view(v.seq, (v.n_bases + 1) // 2, np.uint8), view(v.qual, v.n_bases, np.uint8), None)
+    rb._owner = owner
+    return rb
 
 
 class Engine:

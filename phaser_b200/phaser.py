@@ -58,7 +58,7 @@ def build_parser():
     p.add_argument("--gw_phase_vcf", type=int, default=0)
     p.add_argument("--gw_phase_vcf_min_confidence", type=float, default=0.90)
     # performance (phaser.py:62-65)
-    p.add_argument("--threads", type=int, default=1, help="accepted for compatibility; the GPU path does not use host threads")
+    p.add_argument("--threads", type=int, default=1, help="host threads for BAM decompression")
     p.add_argument("--max_block_size", type=int, default=15)
     p.add_argument("--temp_dir", default="")
     p.add_argument("--max_items_per_thread", type=int, default=100000)
@@ -177,18 +177,23 @@ def run(args, engine=None):
     if engine is None:
         from phaser_b200.engine import Engine
         engine = Engine(device=args.device)
-    fd = samio.FragmentDictionary()
+    from phaser_b200.engine import NativeFragmentDictionary, read_alignments_native, PhzError
+    fd = NativeFragmentDictionary(engine.lib)
     batches = []
     for i, bam in enumerate(bam_list):
         say("     file: %s" % bam)
         say("          minimum mapq: %s" % mapq[i])
-        rb = samio.read_alignments(bam, vt.contigs, fd, remove_dups=(args.remove_dups == 1), proper_pair=(paired[i] == 1),
-                                   min_mapq=mapq[i])
+        try:        # native reader: BGZF blocks inflated on --threads host threads, records decoded straight into SoA
+            rb = read_alignments_native(bam, vt.contigs, fd, remove_dups=(args.remove_dups == 1), proper_pair=(paired[i] == 1),
+                                        min_mapq=mapq[i], threads=max(1, args.threads), lib=engine.lib)
+        except PhzError as e:
+            fatal_error(str(e))
         batches.append(engine.upload_reads(rb))
+        del rb
     P = pipeline.PhaseParams(baseq=args.baseq, isize=isize, as_q_cutoff=args.as_q_cutoff, cc_threshold=args.cc_threshold,
                              max_block_size=args.max_block_size, haplo_count_bam_exclude=exclude)
     try:
-        res = pipeline.run_path(engine, vt, batches, P, n_fragments=len(fd.names))
+        res = pipeline.run_path(engine, vt, batches, P, n_fragments=len(fd))
     except PhaserFatal as e:
         fatal_error(str(e))
     for i, bam in enumerate(bam_list):

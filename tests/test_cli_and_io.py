@@ -109,3 +109,41 @@ def test_read_variant_map_seam_writes_the_reference_tsv(hostsim, tmp_path, monke
     out = tmp_path / "out.tsv"
     rvm.do_read_variant_map(str(table), 10, str(out), 1, 0.0)
     assert open(out).read() == c["mapper"][c["meta"]["bams"][0]]
+
+
+def test_native_reader_equals_python_readers(tmp_path):
+    """phz_read_alignments (C++, parallel BGZF inflate) == the Python SAM / BAM readers, array for array,
+    on SAM text, gzipped SAM and BAM, with and without filters."""
+    import ctypes
+    from phaser_b200 import engine as eng
+    lib = eng._declare(ctypes.CDLL(util.build_hostsim()))
+    c = G.load_case("rna_two_bams")
+    contigs = ["21", "22"]
+    refs = [("21", 120000), ("22", 80000)]
+    for sam in c["sams"]:
+        recs = []
+        for ln in open(sam):
+            f = ln.rstrip("\n").split("\t")
+            if not ln.startswith("@"):
+                cig = []; n = ""
+                for ch in f[5]:
+                    if ch.isdigit():
+                        n += ch
+                    else:
+                        cig.append((int(n), ch)); n = ""
+                a = [int(t[5:]) for t in f[11:] if t.startswith("AS:i:")]
+                recs.append((f[0], int(f[1]), contigs.index(f[2]), int(f[3]), int(f[4]), cig, f[9],
+                             bytes(ord(q) - 33 for q in f[10]), int(f[8]), a[0] if a else None))
+        bam = str(tmp_path / (os.path.basename(sam) + ".real.bam"))
+        bamio.write_bam(bam, refs, recs)
+        gz = str(tmp_path / (os.path.basename(sam) + ".sam.gz"))
+        with gzip.open(gz, "wt") as f:
+            f.write(open(sam).read())
+        for (rd, pp, mq) in ((True, True, 255), (False, False, 0)):
+            ref_batch = samio.parse_sam(sam, contigs, samio.FragmentDictionary(), rd, pp, mq)
+            for path in (sam, gz, bam):
+                fd = eng.NativeFragmentDictionary(lib)
+                b = eng.read_alignments_native(path, contigs, fd, rd, pp, mq, threads=3, lib=lib)
+                for k in ("contig_rec_off", "pos", "tlen", "aln_score", "frag", "cigar_off", "cigar", "seq_off", "seq", "qual"):
+                    assert np.array_equal(getattr(ref_batch, k), getattr(b, k)), (path, k)
+                assert fd.names == ref_batch.qnames

@@ -23,7 +23,7 @@ def build_hostsim():
     deps = [src] + [os.path.join(ROOT, "phaser_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "phaser_b200", "csrc"))]
     if os.path.exists(HOSTSIM_SO) and all(os.path.getmtime(HOSTSIM_SO) >= os.path.getmtime(d) for d in deps):
         return HOSTSIM_SO
-    subprocess.check_call(["g++", "-std=c++20", "-O2", "-shared", "-fPIC", "-o", HOSTSIM_SO, src])
+    subprocess.check_call(["g++", "-std=c++20", "-O2", "-shared", "-fPIC", "-o", HOSTSIM_SO, src, "-lz", "-lpthread"])
     return HOSTSIM_SO
 
 
