@@ -228,7 +228,7 @@ class Engine:
     def upload_reads(self, batch: ReadBatch):
         """ReadBatch (numpy) -> dict of device tensors (the 'inputs resident in HBM' form)."""
         d = self.device
-        return dict(contig_rec_off=np.ascontiguousarray(batch.contig_rec_off, np.int64),
+        return dict(contig_rec_off=np.array(batch.contig_rec_off, dtype=np.int64, copy=True),
                     pos=_as_torch(batch.pos, d), tlen=_as_torch(batch.tlen, d), aln_score=_as_torch(batch.aln_score, d),
                     frag=_as_torch(batch.frag, d), cigar_off=_as_torch(batch.cigar_off, d), cigar=_as_torch(batch.cigar, d),
                     seq_off=_as_torch(batch.seq_off, d), seq=_as_torch(batch.seq, d), qual=_as_torch(batch.qual, d))
