@@ -60,6 +60,10 @@ int phz_sync(phz_ctx* ctx);
 int phz_set_variants(phz_ctx* ctx, int n_contigs, const int64_t* h_contig_var_off, const int32_t* d_pos,
                      const uint8_t* d_a0, const uint8_t* d_a1, int64_t n_variants);
 
+/* Optional, after phz_set_variants: one byte per het site, 1 = the site lies in a --haplo_count_blacklist
+ * interval and is left out of the per-BAM haplotypic counts and read lists (phaser.py:1070, 1189).  NULL clears. */
+int phz_set_haplo_blacklist(phz_ctx* ctx, const uint8_t* d_flags);
+
 /* K1.  Replaces do_read_variant_map (read_variant_map.py:3-124) incl. split_read (:165-234) and
  * identify_allele (:236-258) for one BAM: emits, in (record, segment, variant) order, one tuple per
  * het SNV a spliced segment of a record covers.  All pointers of `reads` except h_contig_rec_off

@@ -39,9 +39,10 @@ def canon_haplotypic_counts(text):
         c = ln.split("\t")
         if len(c) >= 18:
             c[16] = _relabel(c[16]); c[17] = _relabel(c[17])
+        c[5] = ",".join(sorted(c[5].split(","))) if c[5] else c[5]     # variantsBlacklisted is printed from a set (phaser.py:1119)
         row = "\t".join(c)
-        # singleton rows: variantCount == 1 and empty aReads/bReads (phaser.py:1214-1220)
-        if c[4] == "1" and c[16] == "" and c[17] == "" and c[13] == "1" and "," not in c[3]:
+        # singleton rows: variantCount == 1, nothing blacklisted, empty aReads/bReads (phaser.py:1214-1220)
+        if c[4] == "1" and c[6] == "0" and c[16] == "" and c[17] == "" and c[13] == "1" and "," not in c[3]:
             singles.append(row)
         else:
             blocks.append(row)

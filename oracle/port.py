@@ -639,6 +639,9 @@ def _outputs(res, vt, var, sets, links, final, contig_of, vinfo, P, nb):
                                       hap_counts[0], hap_counts[1], sum(hap_counts), sup, tot, ps[0] + "|" + ps[1],
                                       phase_concordant, cps[0] + "|" + cps[1], stat])) + "\n")
         res.block_rows.append(dict(variants=variants, hap_a=hap_a, counts=hap_counts, sup=sup, tot=tot, stat=stat))
+        black = getattr(vt, "haplo_blacklisted", None)
+        used = [i for i, v in enumerate(variants) if black is None or not black[v]]      # phaser.py:1070
+        blacklisted = [vt.ids[v] for i, v in enumerate(variants) if i not in used]
         for b in range(nb):
             if b in P.haplo_count_bam_exclude:
                 continue
@@ -646,7 +649,8 @@ def _outputs(res, vt, var, sets, links, final, contig_of, vinfo, P, nb):
             for h in (0, 1):
                 hx = (hap_a, hap_b)[h]
                 u = set()
-                for i, v in enumerate(variants):
+                for i in used:
+                    v = variants[i]
                     ai = vis[i]["alleles"].index(vis[i]["alleles"][int(hx[i])])
                     lst = var[v]["haplo"][ai].get(b, [])
                     vreads[h].append(lst)
@@ -658,8 +662,9 @@ def _outputs(res, vt, var, sets, links, final, contig_of, vinfo, P, nb):
             elif corrected[0][0] == 1:
                 gwp = "1|0"
             if sum(cnt) > 0:
-                hc.append("\t".join(map(str, [chrom, min(positions), max(positions), _lts(vt.ids[v] for v in variants),
-                                              len(variants), "", 0, _lts(alleles[0]), _lts(alleles[1]), cnt[0], cnt[1],
+                hc.append("\t".join(map(str, [chrom, min(positions), max(positions), _lts(vt.ids[variants[i]] for i in used),
+                                              len(used), _lts(sorted(blacklisted)), len(blacklisted),
+                                              _lts(alleles[0][i] for i in used), _lts(alleles[1][i] for i in used), cnt[0], cnt[1],
                                               sum(cnt), gwp, stat, str(max_maf), P.bam_names[b],
                                               _relabel_first_occurrence(vreads[0]),
                                               _relabel_first_occurrence(vreads[1])])) + "\n")
@@ -676,6 +681,8 @@ def _outputs(res, vt, var, sets, links, final, contig_of, vinfo, P, nb):
         res.singletons = singles
         for v in singles:
             vi = vinfo(v)
+            if getattr(vt, "haplo_blacklisted", None) is not None and vt.haplo_blacklisted[v]:
+                continue                                   # phaser.py:1189
             for b in range(nb):
                 if b in P.haplo_count_bam_exclude:
                     continue

@@ -61,6 +61,8 @@ int phz_set_variants(phz_ctx* ctx, int n_contigs, const int64_t* h_off, const in
   PHZ_TRY ctx->p.set_variants(n_contigs, h_off, d_pos, d_a0, d_a1, n_variants); PHZ_CATCH
 }
 
+int phz_set_haplo_blacklist(phz_ctx* ctx, const uint8_t* d_flags) { PHZ_TRY ctx->p.vblack = d_flags; PHZ_CATCH }
+
 static ReadsView view_of(const phz_reads* r, int nc) {
   ReadsView v;
   v.n_records = r->n_records; v.n_contigs = nc; v.contig_rec_off = nullptr;

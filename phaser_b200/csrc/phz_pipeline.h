@@ -405,6 +405,7 @@ struct Pipeline {
   std::vector<int64_t> h_cvoff;
   Buf<B, int64_t> d_cvoff, d_croff;
   const int32_t* vpos = nullptr; const u8* va0 = nullptr; const u8* va1 = nullptr;
+  const u8* vblack = nullptr;      // per het site: 1 = left out of the haplotypic counts (phaser.py:1070)
   Buf<B, u32> vcontig;
   // ------------------------------------------------------------------ K1 candidates of the current BAM
   Buf<B, u32> cand_cnt, cand_off, t_rec, t_var, t_misc, keep_flag, keep_off;
@@ -480,7 +481,7 @@ struct Pipeline {
     vbits = ceil_log2_host((u64)(V > 1 ? V : 2));
     h_cvoff.assign(contig_var_off_host, contig_var_off_host + nc + 1);
     be.h2d(d_cvoff.ensure(nc + 1), h_cvoff.data(), (nc + 1) * sizeof(int64_t));
-    vpos = d_pos; va0 = d_a0; va1 = d_a1;
+    vpos = d_pos; va0 = d_a0; va1 = d_a1; vblack = nullptr;
     u32* vc = vcontig.ensure(V);
     const int64_t* off = d_cvoff.p; int n = nc;
     be.for_each(V, PHZ_LAMBDA(int64_t v) { vc[v] = (u32)upper_slot_i64(off, n, v); });
@@ -1105,6 +1106,7 @@ struct Pipeline {
     u32* fc = fb_cnt.ensure(NF * 2); u32* fbc = fb_bcnt.ensure(NF * nb * 2);
     be.memset0(fc, NF * 2 * sizeof(u32)); be.memset0(fbc, NF * nb * 2 * sizeof(u32));
     const u64* ek = e_key.p; const u8* eb = e_bam.p; const u32* em = e_mask.p; const u32* go = grp_off.p;
+    const u8* vbl = vblack;
     be.for_each(NG, PHZ_LAMBDA(int64_t g) {
       u32 j0 = go[g], j1 = go[g + 1];
       for (u32 j = j0; j < j1; ++j) {
@@ -1116,10 +1118,11 @@ struct Pipeline {
           for (u32 i = j0; i < j; ++i) {
             u32 w = (u32)(ek[i] & vmask);
             if (vfin[w] != f || !((em[i] >> (vh[w] ^ h)) & 1)) continue;
-            seen_any = true; if (eb[i] == eb[j]) seen_bam = true;
+            seen_any = true; if (eb[i] == eb[j] && !(vbl && vbl[w])) seen_bam = true;
           }
           if (!seen_any) atomic_add(&fc[(int64_t)f * 2 + h], 1u);
-          if (!seen_bam && !((excl_mask >> eb[j]) & 1)) atomic_add(&fbc[((int64_t)f * nb + eb[j]) * 2 + h], 1u);
+          if (!seen_bam && !((excl_mask >> eb[j]) & 1) && !(vbl && vbl[v]))
+            atomic_add(&fbc[((int64_t)f * nb + eb[j]) * 2 + h], 1u);
         }
       }
     });
@@ -1135,10 +1138,11 @@ struct Pipeline {
     const int64_t n = n_tuples; const int nb = n_bams > 0 ? n_bams : 1; const int vb = vbits;
     const u32* gf = g_frag.p; const u32* gv = g_var.p; const u8* gc = g_cb.p; const u32* vfin = v_final.p; const u8* vh = v_hap.p;
     u32* rf = rl_flag.ensure(n + 1); u32* rsn = rl_scan.ensure(n + 2);
+    const u8* vbl = vblack;
     be.stage("read_lists");
     be.for_each(n, PHZ_LAMBDA(int64_t t) {
       u32 cls = gc[t] & 3; u32 bam = gc[t] >> 2;
-      rf[t] = (cls < 2 && vfin[gv[t]] != NONE32 && !((excl_mask >> bam) & 1)) ? 1u : 0u;
+      rf[t] = (cls < 2 && vfin[gv[t]] != NONE32 && !((excl_mask >> bam) & 1) && !(vbl && vbl[gv[t]])) ? 1u : 0u;
     });
     be.exclusive_scan_u32(rf, rsn, n);
     NRL = n > 0 ? (int64_t)fetch_u32(rsn + n) : 0;

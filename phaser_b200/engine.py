@@ -36,7 +36,7 @@ EXPORTS = ["phz_last_error", "phz_backend_name", "phz_create", "phz_destroy", "p
            "phz_phase", "phz_read_lists", "phz_array", "phz_download", "phz_counters", "phz_launch_counts",
            "phz_set_profiling", "phz_map_times", "phz_stage_report", "phz_set_option",
            "phz_fragdict_create", "phz_fragdict_destroy", "phz_fragdict_size", "phz_fragdict_name", "phz_read_alignments",
-           "phz_host_reads_view", "phz_host_reads_free"]
+           "phz_host_reads_view", "phz_host_reads_free", "phz_set_haplo_blacklist"]
 
 
 def _declare(lib):
@@ -72,6 +72,7 @@ def _declare(lib):
     lib.phz_read_alignments.argtypes = [c_char_p, POINTER(c_char_p), c_int, c_void_p, c_int, c_int, c_int, c_int]
     lib.phz_host_reads_view.argtypes = [c_void_p, POINTER(phz_reads), POINTER(c_int)]
     lib.phz_host_reads_free.argtypes = [c_void_p]
+    lib.phz_set_haplo_blacklist.argtypes = [c_void_p, c_void_p]
     return lib
 
 
@@ -224,6 +225,10 @@ class Engine:
         p, a0, a1 = self._keep["v"]
         self._check(self.lib.phz_set_variants(self.ctx, self.n_contigs, off.ctypes.data, p.data_ptr(), a0.data_ptr(),
                                               a1.data_ptr(), vt.n_variants))
+        bl = getattr(vt, "haplo_blacklisted", None)
+        if bl is not None and bl.any():
+            self._keep["vblack"] = _as_torch(np.ascontiguousarray(bl, np.uint8), d)
+            self._check(self.lib.phz_set_haplo_blacklist(self.ctx, self._keep["vblack"].data_ptr()))
 
     def upload_reads(self, batch: ReadBatch):
         """ReadBatch (numpy) -> dict of device tensors (the 'inputs resident in HBM' form)."""

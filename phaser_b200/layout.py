@@ -74,6 +74,7 @@ class VariantTable:
     all_alleles: List[List[str]] = field(default_factory=list)
     gt: List[str] = field(default_factory=list)         # GT string verbatim (e.g. "0|1")
     maf: List[str] = field(default_factory=list)        # str(maf) as the mapping table carries it
+    haplo_blacklisted: Optional[np.ndarray] = None      # u8[V] 1 = left out of haplotypic counts (phaser.py:1070)
 
     @property
     def n_variants(self) -> int:

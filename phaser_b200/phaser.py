@@ -5,9 +5,8 @@ Same flags, file formats and fatal-error behaviour as the reference CLI (phaser/
 the work between "het sites loaded" and "files written" runs on the GPU through the C ABI
 (include/phz.h).  Differences a user can see:
   * no samtools / bgzip / tabix / bedtools / bcftools are needed (BAM or SAM text is read directly);
-  * options that only exist to drive those tools are rejected with a FATAL ERROR instead of being
-    silently ignored: --blacklist, --haplo_count_blacklist, --include_indels 1, --process_slow 1,
-    --output_network, --output_read_ids 1 (SURVEY.md section 8f, "next" rows);
+  * not yet supported, rejected with a FATAL ERROR instead of being silently ignored: --include_indels 1,
+    --process_slow 1, --output_network, --output_read_ids 1 (SURVEY.md section 8f, "next" rows);
   * fields the reference prints in CPython-set order come out in a canonical order
     (SURVEY.md section 8c).
 """
@@ -129,9 +128,7 @@ def run(args, engine=None):
     say("  B200-native read->variant->haplotype path (phaser_b200)")
     say("##################################################")
     say("")
-    for flag, bad, why in (("--blacklist", args.blacklist != "", "needs a BED interval join"),
-                           ("--haplo_count_blacklist", args.haplo_count_blacklist != "", "needs a BED interval join"),
-                           ("--include_indels 1", args.include_indels == 1, "multi-base alleles"),
+    for flag, bad, why in (("--include_indels 1", args.include_indels == 1, "multi-base alleles"),
                            ("--process_slow 1", args.process_slow == 1, "per-contig mode changes results in the reference"),
                            ("--output_network", args.output_network != "", "debug dump"),
                            ("--output_read_ids 1", args.output_read_ids == 1, "read-id columns")):
@@ -143,6 +140,9 @@ def run(args, engine=None):
         fatal_error("VCF file does not exist.")
     if args.vcf.endswith(".gz") is False and args.vcf.endswith(".bgz") is False:
         fatal_error("VCF must be gzipped.")
+    for xfile in (args.blacklist, args.haplo_count_blacklist):
+        if xfile != "" and os.path.isfile(xfile) is False:
+            fatal_error("File: %s not found." % xfile)
     bam_list = [b for b in args.bam.split(",")]
     for b in bam_list:
         if b != "" and os.path.isfile(b) is False:
@@ -163,7 +163,8 @@ def run(args, engine=None):
         vt, st = vcfio.parse_vcf(args.vcf, sample_column, pass_only=args.pass_only, chrom_of_interest=args.chr,
                                  chr_prefix=args.chr_prefix, id_separator=args.id_separator,
                                  include_indels=args.include_indels, gw_phase_method=args.gw_phase_method,
-                                 gw_af_field=args.gw_af_field)
+                                 gw_af_field=args.gw_af_field, blacklist=args.blacklist,
+                                 haplo_count_blacklist=args.haplo_count_blacklist)
     except PhaserFatal as e:
         fatal_error(str(e))
     say("          %d heterozygous sites being used for phasing (%d filtered, %d indels excluded, %d unphased)" % (

@@ -50,9 +50,46 @@ def _annotation_to_dict(text, sep=";"):
     return out
 
 
+class BedIntervals:
+    """Interval overlap as `bedtools intersect` answers it for the two uses in phaser.py:220, 234: a VCF
+    record occupies [POS-1, POS-1+len(REF)), BED intervals are [start, end) 0-based."""
+
+    def __init__(self, path):
+        import bisect
+        self._bisect = bisect
+        iv = {}
+        with open(path) as f:
+            for line in f:
+                c = line.rstrip("\n").split("\t")
+                if len(c) >= 3 and not line.startswith(("#", "track", "browser")):
+                    iv.setdefault(c[0], []).append((int(c[1]), int(c[2])))
+        self.starts = {}; self.maxend = {}
+        for k, v in iv.items():
+            v.sort()
+            self.starts[k] = [a for a, _ in v]
+            m = []; cur = -1
+            for _, b in v:
+                cur = max(cur, b); m.append(cur)
+            self.maxend[k] = m
+
+    def overlaps(self, chrom, pos, ref_len):
+        s = pos - 1; e = s + ref_len
+        st = self.starts.get(chrom)
+        if not st:
+            return False
+        j = self._bisect.bisect_left(st, e)        # intervals with start < e
+        return j > 0 and self.maxend[chrom][j - 1] > s
+
+
 def parse_vcf(path, sample_column: int, pass_only=1, chrom_of_interest="", chr_prefix="", id_separator="_",
-              include_indels=0, gw_phase_method=0, gw_af_field="AF"):
-    """Returns (VariantTable, VcfStats).  `sample_column` is the 0-based VCF column of the sample."""
+              include_indels=0, gw_phase_method=0, gw_af_field="AF", blacklist="", haplo_count_blacklist=""):
+    """Returns (VariantTable, VcfStats).  `sample_column` is the 0-based VCF column of the sample.
+    `blacklist`: BED of intervals whose variants are dropped before anything else (phaser.py:218-221);
+    `haplo_count_blacklist`: BED whose variants are kept for phasing but left out of the haplotypic counts
+    (phaser.py:231-243) -- the table's `haplo_blacklisted` flags."""
+    bl = BedIntervals(blacklist) if blacklist else None
+    hbl = BedIntervals(haplo_count_blacklist) if haplo_count_blacklist else None
+    haplo_set = set()
     if include_indels:
         raise NotImplementedError("--include_indels 1 is not supported by the B200 mapper yet (multi-base alleles)")
     contig_ban = [id_separator, ":"]
@@ -68,7 +105,11 @@ def parse_vcf(path, sample_column: int, pass_only=1, chrom_of_interest="", chr_p
             cut_line = "\t".join(cut)
             if "0|0" in cut_line or "1|1" in cut_line:
                 continue
+            if bl is not None and bl.overlaps(cut[0], int(cut[1]), len(cut[3])):
+                continue
             chrom = cut[0]
+            if hbl is not None and hbl.overlaps(chrom, int(cut[1]), len(cut[3])) and (chrom_of_interest == "" or chrom_of_interest == chrom):
+                haplo_set.add(chrom + "_" + cut[1])
             for item in contig_ban:
                 if item in chrom:
                     raise PhaserFatal("Character '%s' must not be present in contig name. Please change id separtor "
@@ -130,6 +171,13 @@ def parse_vcf(path, sample_column: int, pass_only=1, chrom_of_interest="", chr_p
         off.append(len(pos))
     vt = VariantTable(contigs, np.asarray(off, np.int64), np.asarray(pos, np.int32), np.asarray(a0, np.uint8),
                       np.asarray(a1, np.uint8), np.asarray(rl, np.int32), ids, rsids, alls, gts, mafs)
+    # phaser.py:1070: key = contig name as in the ids (chr_prefix applied) + "_" + pos, against raw VCF names
+    vt.haplo_blacklisted = np.zeros(len(pos), np.uint8)
+    if haplo_set:
+        for c in range(len(contigs)):
+            for v in range(off[c], off[c + 1]):
+                if contigs[c] + "_" + str(int(vt.pos[v])) in haplo_set:
+                    vt.haplo_blacklisted[v] = 1
     for c in range(len(contigs)):
         p = vt.pos[off[c]:off[c + 1]]
         if p.shape[0] > 1 and np.any(np.diff(p) < 0):

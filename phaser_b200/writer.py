@@ -219,6 +219,9 @@ class Outputs:
                 gwp = "0|1"
             elif corrected[0][0] == 1:
                 gwp = "1|0"
+            black = getattr(self.vt, "haplo_blacklisted", None)
+            used = [i for i, v in enumerate(variants) if black is None or not black[v]]        # phaser.py:1070
+            blacklisted = sorted(ms[i].id for i in range(n) if i not in used)
             for b in range(nb):
                 if b in excl:
                     continue
@@ -228,10 +231,11 @@ class Outputs:
                     for h in (0, 1):
                         key = (((f << bb) | b) << 1) | h
                         per_var = rl.get(key, {})
-                        cols.append(self._relabel([per_var.get(v, []) for v in variants]))
+                        cols.append(self._relabel([per_var.get(variants[i], []) for i in used]))
                     hc.append("\t".join(map(str, [ms[0].chrom, min(positions), max(positions),
-                                                  ",".join(m.id for m in ms), n, "", 0, ",".join(alleles[0]),
-                                                  ",".join(alleles[1]), a_cnt, b_cnt, a_cnt + b_cnt, gwp, stat,
+                                                  ",".join(ms[i].id for i in used), len(used), ",".join(blacklisted),
+                                                  len(blacklisted), ",".join(alleles[0][i] for i in used),
+                                                  ",".join(alleles[1][i] for i in used), a_cnt, b_cnt, a_cnt + b_cnt, gwp, stat,
                                                   str(max_maf), self.bam_names[b], cols[0], cols[1]])) + "\n")
             for i, ma in enumerate(ms):
                 for j, mb in enumerate(ms):
@@ -244,8 +248,11 @@ class Outputs:
             vbc = r.vb_cnt.reshape(-1, nb, 2)
             singles = [v for v in self.first_seen_order().tolist()
                        if int(ncls[v, 0]) + int(ncls[v, 1]) > 0 and r.v_final[v] == NONE32]
+            black = getattr(self.vt, "haplo_blacklisted", None)
             for v in singles:
                 m = self.meta(v)
+                if black is not None and black[v]:
+                    continue                                     # phaser.py:1189
                 for b in range(nb):
                     if b in excl:
                         continue

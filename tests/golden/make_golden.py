@@ -204,6 +204,25 @@ def option_case(name, base, args, mapq="255", paired_end="1"):
     json.dump(m, open(os.path.join(d, "case.json"), "w"), indent=1)
 
 
+def blacklist_cases():
+    """--blacklist / --haplo_count_blacklist (phaser.py:218-243): BED files derived from the case's own variants."""
+    b = os.path.join(CASES, "rna_two_bams")
+    lines = [l for l in gzip.open(os.path.join(b, "in.vcf.gz"), "rt") if not l.startswith("#")]
+    pos = [(l.split("\t")[0], int(l.split("\t")[1])) for l in lines]
+    os.makedirs(os.path.join(HERE, "beds"), exist_ok=True)
+    bl = os.path.join(HERE, "beds", "blacklist.bed"); hbl = os.path.join(HERE, "beds", "haplo_blacklist.bed")
+    with open(bl, "w") as f:          # drops every 9th variant from phasing altogether
+        for c, p_ in pos[4::9]:
+            f.write("%s\t%d\t%d\n" % (c, p_ - 1, p_))
+    with open(hbl, "w") as f:         # a few wider intervals: blocks lose members from the haplotypic counts
+        for c, p_ in pos[2::7]:
+            f.write("%s\t%d\t%d\n" % (c, max(0, p_ - 40), p_ + 40))
+    option_case("opt_blacklists", "rna_two_bams", ["--blacklist", bl, "--haplo_count_blacklist", hbl])
+    m = json.load(open(os.path.join(CASES, "opt_blacklists", "case.json")))
+    m["args"] = ["--blacklist", "beds/blacklist.bed", "--haplo_count_blacklist", "beds/haplo_blacklist.bed"]
+    json.dump(m, open(os.path.join(CASES, "opt_blacklists", "case.json"), "w"), indent=1)
+
+
 def main():
     os.makedirs(CASES, exist_ok=True)
     v, s = quirk_case()
@@ -218,6 +237,7 @@ def main():
     option_case("opt_filters", "rna_small", ["--pass_only", "0", "--remove_dups", "0", "--cc_threshold", "0.05", "--as_q_cutoff", "0.2"],
                 paired_end="0")
     option_case("opt_quirks_baseq", "quirks", ["--as_q_cutoff", "0", "--max_block_size", "3"], mapq="0")
+    blacklist_cases()
 
 
 if __name__ == "__main__":

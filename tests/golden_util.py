@@ -43,6 +43,8 @@ def args_to_kw(args):
             kw[a[2:]] = float(v)
         elif a == "--id_separator":
             kw["id_separator"] = v
+        elif a in ("--blacklist", "--haplo_count_blacklist"):
+            kw[a[2:]] = os.path.join(os.path.dirname(CASES), v)
         else:
             raise KeyError(a)
     return kw

@@ -13,8 +13,9 @@ from tests import util, golden_util as G
 def _run_cli(engine, case, tmp_path, extra=()):
     c = G.load_case(case)
     o = str(tmp_path / "out")
+    args = [os.path.join(os.path.dirname(G.CASES), a) if a.startswith("beds/") else a for a in c["meta"]["args"]]
     argv = ["--vcf", c["vcf"], "--bam", ",".join(c["sams"]), "--sample", "S1", "--mapq", c["meta"]["mapq"], "--baseq", "10",
-            "--paired_end", c["meta"]["paired_end"], "--o", o] + list(c["meta"]["args"]) + list(extra)
+            "--paired_end", c["meta"]["paired_end"], "--o", o] + args + list(extra)
     cli.run(cli.build_parser().parse_args(argv), engine=engine)
     got = {k: open(o + "." + k + ".txt").read() for k in ("allelic_counts", "allele_config", "haplotypes", "haplotypic_counts",
                                                           "variant_connections")}
@@ -22,7 +23,7 @@ def _run_cli(engine, case, tmp_path, extra=()):
     return c, got
 
 
-@pytest.mark.parametrize("case", ["quirks", "rna_two_bams"])
+@pytest.mark.parametrize("case", ["quirks", "rna_two_bams", "opt_blacklists", "opt_maf_gwvcf2", "opt_nounphased_uid", "opt_filters"])
 def test_cli_writes_reference_identical_files(hostsim, tmp_path, case):
     c, got = _run_cli(hostsim, case, tmp_path)
     bad = compare.diff_outputs(c["ref"], got)
@@ -35,7 +36,8 @@ def test_cli_fatal_errors_exit_1(hostsim, tmp_path, capsys):
     for extra, msg in ((["--sample", "NOPE"], "Sample 'NOPE' not found"),
                        (["--sample", "S1", "--id_separator", ":"], "ID separator must not be"),
                        (["--sample", "S1", "--mapq", "1,2"], "Number of mapq values"),
-                       (["--sample", "S1", "--blacklist", "x.bed"], "not supported")):
+                       (["--sample", "S1", "--blacklist", "x.bed"], "File: x.bed not found"),
+                       (["--sample", "S1", "--include_indels", "1"], "not supported")):
         with pytest.raises(SystemExit) as e:
             cli.run(cli.build_parser().parse_args(base + extra), engine=hostsim)
         assert e.value.code == 1

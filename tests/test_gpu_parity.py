@@ -111,3 +111,21 @@ def test_windowed_k1_equals_generic_k1(gpu):
     for m in (1, 2, 3):
         for a, b in zip(out[0][1:], out[m][1:]):
             assert np.array_equal(a, b), m
+
+
+def test_wgs_plus_rna_joint_matches_oracle(gpu, tmp_path):
+    """configs[3] shape at oracle scale: a WGS BAM (2x150, unspliced, MAPQ filter 20) + an RNA BAM, per-BAM
+    mapq / paired_end lists, haplotypic counts only for the RNA BAM."""
+    from phaser_b200 import synth
+    contigs = [("21", 200000), ("22", 150000)]
+    g = synth.make_genome(71, 500, contigs=contigs, n_genes=40)
+    vcf = synth.write_vcf(g, str(tmp_path / "j.vcf.gz"))
+    wgs = synth.make_wgs_reads(g, 7100, 6000, mapq=60, lowmapq_frac=0.05, dup_frac=0.03)
+    rna = synth.make_reads(g, 7101, 3000, dup_frac=0.05)
+    sams = [synth.write_sam(wgs, g, str(tmp_path / "wgs.bam"), "w"), synth.write_sam(rna, g, str(tmp_path / "rna.bam"), "r")]
+    kw = dict(mapq="20,255", paired_end="1,1", exclude=[0])
+    got, res, _ = util.product_outputs(gpu, vcf, sams, **kw)
+    exp, ores = util.oracle_outputs(vcf, sams, **kw)
+    bad = compare.diff_outputs(exp, got)
+    assert not bad, "\n".join(bad)
+    assert res.counters["n_tuples"] == ores.total_tuples > 3000
