@@ -271,7 +271,8 @@ def cpu_sample_files(a, tmp):
     g = synth.make_genome(a.seed, n_var, exonic_frac=a.exonic_frac, n_genes=max(2, int(n_var * a.exonic_frac) // 8))
     rec = synth.make_reads(g, a.seed * 1000, n_pairs)
     vcf = synth.write_vcf(g, os.path.join(tmp, "sample.vcf.gz"))
-    sam = synth.write_sam(rec, g, os.path.join(tmp, "sample.bam"), bam_name="bam0")
+    from phaser_b200 import engine as eng
+    sam = eng.write_sam_native(rec, g.contigs, os.path.join(tmp, "sample.bam"), bam_name="bam0")
     return g, rec, vcf, sam, n_pairs, int(g.v_pos.shape[0])
 
 

@@ -134,6 +134,11 @@ phz_host_reads* phz_read_alignments(const char* path, const char* const* contigs
                                     int remove_dups, int proper_pair, int min_mapq, int n_threads);
 int phz_host_reads_view(phz_host_reads* r, phz_reads* out, int* sorted_by_coordinate);
 void phz_host_reads_free(phz_host_reads* r);
+/* SAM text twin of generated records: input for the reference baseline (test / bench infrastructure). */
+int phz_write_sam(const char* path, const char* const* contig_names, const int64_t* contig_lengths, int n_contigs, int64_t n,
+                  const int64_t* contig, const int64_t* pos, const int64_t* tlen, const int64_t* flag, const int64_t* mapq,
+                  const int64_t* aln, const int64_t* frag, const int64_t* ops, const int64_t* opl, int n_ops,
+                  const uint8_t* bases, const uint8_t* qual, int read_len, const char* bam_name);
 
 #ifdef __cplusplus
 }

@@ -365,4 +365,32 @@ int phz_host_reads_view(phz_host_reads* r, phz_reads* out, int* sorted) {
 
 void phz_host_reads_free(phz_host_reads* r) { if (r) { delete r->h; delete r; } }
 
+// SAM text twin of generated records (test / baseline input for the reference, which reads SAM text
+// through the harness).  ops/opl: n x n_ops padded CIGAR table (len 0 = unused); bases: 4-bit codes.
+int phz_write_sam(const char* path, const char* const* contig_names, const int64_t* contig_lengths, int n_contigs, int64_t n,
+                  const int64_t* contig, const int64_t* pos, const int64_t* tlen, const int64_t* flag, const int64_t* mapq,
+                  const int64_t* aln, const int64_t* frag, const int64_t* ops, const int64_t* opl, int n_ops,
+                  const uint8_t* bases, const uint8_t* qual, int read_len, const char* bam_name) {
+  PHZ_TRY
+  FILE* f = std::fopen(path, "w");
+  if (!f) throw PhzError(std::string("cannot write ") + path);
+  static const char* ALPHA = "=ACMGRSVTWYHKDBN"; static const char* OPS = "MIDNSHP=X";
+  std::fprintf(f, "@HD\tVN:1.6\tSO:coordinate\n");
+  for (int c = 0; c < n_contigs; ++c) std::fprintf(f, "@SQ\tSN:%s\tLN:%lld\n", contig_names[c], (long long)contig_lengths[c]);
+  std::string line; std::vector<char> sq(read_len + 1), ql(read_len + 1);
+  for (int64_t i = 0; i < n; ++i) {
+    char cig[512]; int w = 0;
+    for (int j = 0; j < n_ops; ++j) if (opl[i * n_ops + j] > 0) w += std::snprintf(cig + w, sizeof(cig) - w, "%lld%c", (long long)opl[i * n_ops + j], OPS[ops[i * n_ops + j]]);
+    cig[w] = 0;
+    for (int j = 0; j < read_len; ++j) { sq[j] = ALPHA[bases[i * read_len + j] & 15]; ql[j] = (char)(qual[i * read_len + j] + 33); }
+    sq[read_len] = 0; ql[read_len] = 0;
+    long long pn = tlen[i] > 0 ? (pos[i] + tlen[i] > 1 ? pos[i] + tlen[i] : 1) : pos[i];
+    std::fprintf(f, "%s.%lld\t%lld\t%s\t%lld\t%lld\t%s\t=\t%lld\t%lld\t%s\t%s\tNH:i:1\tAS:i:%lld\n", bam_name, (long long)frag[i],
+                 (long long)flag[i], contig_names[contig[i]], (long long)pos[i], (long long)mapq[i], cig, pn, (long long)tlen[i],
+                 sq.data(), ql.data(), (long long)aln[i]);
+  }
+  std::fclose(f);
+  PHZ_CATCH
+}
+
 }  // extern "C"
