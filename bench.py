@@ -112,6 +112,12 @@ def make_sample(seed, n_pairs, n_variants, exonic_frac, device):
         parts.append(synth.compact_raw(rec))
         done += n
     rec = synth.concat_sorted(parts)
+    # fragment ids as the ingest assigns them: dense, in order of first appearance in the sorted BAM
+    fr = rec["frag"].to(torch.int64)
+    first = torch.full((n_pairs,), fr.shape[0], dtype=torch.int64, device=fr.device)
+    first.scatter_reduce_(0, fr, torch.arange(fr.shape[0], device=fr.device), "amin")
+    rank = torch.empty_like(first); rank[torch.argsort(first)] = torch.arange(n_pairs, device=fr.device)
+    rec["frag"] = rank[fr].to(torch.int32)
     packed = synth.pack_records(rec, len(g.contigs))
     return g, vt, packed, n_pairs
 

@@ -47,6 +47,19 @@ typedef unsigned long long u64;
 typedef uint32_t u32;
 typedef uint8_t u8;
 
+// counter[key] += 1 for every lane with `active`; lanes of a warp that hit the same key are combined
+// into one atomic (neighbouring items of the sorted arrays mostly belong to the same locus).  Must be
+// reached by all lanes that are active at the call site.
+PHZ_HD void warp_agg_inc(u32* counter, u32 key, bool active) {
+#if defined(__CUDA_ARCH__)
+  unsigned act = __activemask();
+  unsigned peers = __match_any_sync(act, active ? key : 0xFFFFFFFFu);
+  if (active && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&counter[key], (u32)__popc(peers));
+#else
+  if (active) counter[key] += 1;
+#endif
+}
+
 // lower_bound on a sorted int32 array: first index in [lo, hi) with a[idx] >= key
 PHZ_HD int64_t lower_bound_i32(const int32_t* a, int64_t lo, int64_t hi, int32_t key) {
   while (lo < hi) {

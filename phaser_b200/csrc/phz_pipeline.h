@@ -804,30 +804,41 @@ struct Pipeline {
     u32* vbc = vb_cnt.ensure(Vn * nb * 2); be.memset0(vbc, Vn * nb * 2 * sizeof(u32));
     u64* vr = vrank.ensure(Vn); be.memset_ff(vr, Vn * sizeof(u64));
     u32* pc = pair_cnt.ensure(NG + 1); u32* po = pair_off.ensure(NG + 2);
+    // (a) one logical thread per entry: unique-set sizes (at the first entry of a (fragment, variant) run) and
+    //     per-BAM allele counts, warp-aggregated because neighbouring entries sit on the same locus
+    { int64_t ne = NE;
+      be.for_each(NE, PHZ_LAMBDA(int64_t j) {
+        u32 v = (u32)(ek[j] & vmask);
+        bool first = (j == 0) || (ek[j] != ek[j - 1]);
+        u32 mask = 0;
+        if (first) for (int64_t jj = j; jj < ne && ek[jj] == ek[j]; ++jj) mask |= em[jj];
+        for (int x = 0; x < 3; ++x) warp_agg_inc(sz, v * 3 + (u32)x, first && ((mask >> x) & 1));
+        bool counted = !((excl_mask >> eb[j]) & 1);          // haplo_reads, phaser.py:1320-1322 (Q25)
+        u32 kb = (v * (u32)nb + eb[j]) * 2;
+        warp_agg_inc(vbc, kb, counted && (em[j] & 1));
+        warp_agg_inc(vbc, kb + 1, counted && (em[j] & 2));
+      }); }
+    // (b) one logical thread per (fragment, contig) group: effective BAM, overlap rank, pair count
     be.for_each(NG, PHZ_LAMBDA(int64_t g) {
       u32 j0 = go[g], j1 = go[g + 1];
       int effbam = -1; u32 first_t = NONE32;
       for (u32 j = j0; j < j1; ++j) if (em[j] & 3) { if ((int)eb[j] > effbam) effbam = eb[j]; if (et[j] < first_t) first_t = et[j]; }
       u32 k = 0, kelig = 0;
       for (u32 j = j0; j < j1;) {
-        u32 v = (u32)(ek[j] & vmask); u32 mask = 0; bool elig = false; u32 jj = j;
-        for (; jj < j1 && (u32)(ek[jj] & vmask) == v; ++jj) {
-          mask |= em[jj];
+        u32 v = (u32)(ek[j] & vmask); bool elig = false; u32 jj = j;
+        for (; jj < j1 && (u32)(ek[jj] & vmask) == v; ++jj)
           if ((em[jj] & 3) && (int)eb[jj] == effbam) elig = true;
-          if (!((excl_mask >> eb[jj]) & 1)) {          // haplo_reads, phaser.py:1320-1322 (Q25)
-            if (em[jj] & 1) atomic_add(&vbc[((int64_t)v * nb + eb[jj]) * 2], 1u);
-            if (em[jj] & 2) atomic_add(&vbc[((int64_t)v * nb + eb[jj]) * 2 + 1], 1u);
-          }
-        }
-        for (int x = 0; x < 3; ++x) if (mask & (1u << x)) atomic_add(&sz[(int64_t)v * 3 + x], 1u);
         k++; if (elig) kelig++;
         j = jj;
       }
       pc[g] = k * (k - 1) / 2;
       if (kelig >= 2) {     // insertion order of dict_variant_overlap, phaser.py:1271-1283
         for (u32 j = j0; j < j1; ++j)
-          if ((em[j] & 3) && (int)eb[j] == effbam)
-            atomic_min((unsigned long long*)&vr[ek[j] & vmask], ((unsigned long long)first_t << 32) | et[j]);
+          if ((em[j] & 3) && (int)eb[j] == effbam) {
+            unsigned long long key = ((unsigned long long)first_t << 32) | et[j];
+            unsigned long long* slot = (unsigned long long*)&vr[ek[j] & vmask];
+            if (key < *(volatile unsigned long long*)slot) atomic_min(slot, key);     // the minimum settles early
+          }
       }
     });
     be.exclusive_scan_u32(pc, po, NG);

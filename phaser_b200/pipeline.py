@@ -84,27 +84,41 @@ def critical_values(max_total: int, noise_e: float, cc_threshold: float, totals=
     An edge with 0 < c_supporting < c_total is dropped iff c_supporting < kstar[c_total]; uses the same
     scipy function as the reference so the comparison agrees with it exactly.  With `totals` (the
     c_total values that actually occur) only those entries of the table are computed."""
-    from scipy.stats import binom
     p = 1 - ((6 * noise_e) + (10 * math.pow(noise_e, 2)))
     if totals is not None:
-        n = np.unique(np.asarray(totals, dtype=np.int64))
+        t = np.asarray(totals)
+        n = np.flatnonzero(np.bincount(t.astype(np.int64), minlength=1)) if t.shape[0] else np.zeros(0, np.int64)
         table = np.zeros(max_total + 1, np.uint32)
         if n.shape[0]:
-            table[n] = _critical_values_at(n, p, cc_threshold)
+            table[n] = _critical_values_at(n.astype(np.int64), p, cc_threshold)
         return table
     n = np.arange(0, max_total + 1, dtype=np.int64)
     return _critical_values_at(n, p, cc_threshold)
 
 
+def _binom_cdf(k, n, p):
+    """binom.cdf for 0 <= k <= n: the same Boost-backed ufunc scipy's public method ends in
+    (scipy/stats/_discrete_distns.py: binom._cdf), without the per-call argument plumbing."""
+    from scipy.stats import binom
+    try:
+        out = binom._cdf(k.astype(np.float64), n, p)
+        return np.where(k >= n, 1.0, out)
+    except Exception:
+        return binom.cdf(k, n, p)
+
+
 def _critical_values_at(n, p, cc_threshold):
     from scipy.stats import binom
-    k = np.nan_to_num(binom.ppf(cc_threshold, n, p), nan=0.0).astype(np.int64)
-    k = np.clip(k, 0, n)
+    try:
+        k = binom._ppf(cc_threshold, n, p)
+    except Exception:
+        k = binom.ppf(cc_threshold, n, p)
+    k = np.clip(np.nan_to_num(k, nan=0.0).astype(np.int64), 0, n)
     for _ in range(64):
-        low = binom.cdf(k, n, p) < cc_threshold            # k too small
+        low = _binom_cdf(k, n, p) < cc_threshold            # k too small
         k = np.where(low & (k < n), k + 1, k)
         km = np.maximum(k - 1, 0)
-        high = (k > 0) & (binom.cdf(km, n, p) >= cc_threshold)   # k-1 already passes
+        high = (k > 0) & (_binom_cdf(km, n, p) >= cc_threshold)   # k-1 already passes
         k = np.where(high, km, k)
         if not (low & (k < n)).any() and not high.any():
             break
