@@ -37,6 +37,54 @@ def compiled_available():
     return all(os.path.isfile(os.path.join(COMPILED_DIR, f)) for f in ("phaser.so", "read_variant_map.so", "run_phaser.py"))
 
 
+def split_sam_per_contig(sam_path, out_dir, vcf_gz=None):
+    """Pre-split a SAM text file per contig for the fast shim (header repeated in every part).  With
+    `vcf_gz`, records overlapping no VCF position are dropped here, outside any timing -- what the
+    reference's `samtools view -L bed` stage (phaser.py:1346) does in C."""
+    import bisect
+    os.makedirs(out_dir, exist_ok=True)
+    sites = None
+    if vcf_gz:
+        sites = {}
+        with gzip.open(vcf_gz, "rt") as f:
+            for line in f:
+                if line[0] != "#":
+                    c = line.split("\t", 2)
+                    sites.setdefault(c[0], []).append(int(c[1]))
+        for k in sites:
+            sites[k].sort()
+    header = []; outs = {}
+    with open(sam_path) as f:
+        for line in f:
+            if line[0] == "@":
+                header.append(line); continue
+            c = line.split("\t", 6)
+            chrom = c[2]
+            if sites is not None:
+                n = 0; span = 0
+                for ch in c[5]:
+                    if ch.isdigit():
+                        n = n * 10 + ord(ch) - 48
+                    else:
+                        if ch in "MDN=X":
+                            span += n
+                        n = 0
+                lo = int(c[3]); s = sites.get(chrom)
+                if not s:
+                    continue
+                j = bisect.bisect_left(s, lo)
+                if j >= len(s) or s[j] >= lo + max(span, 1):
+                    continue
+            o = outs.get(chrom)
+            if o is None:
+                o = outs[chrom] = open(os.path.join(out_dir, chrom + ".sam"), "w")
+                o.writelines(header)
+            o.write(line)
+    for o in outs.values():
+        o.close()
+    return out_dir
+
+
 def _env(hashseed):
     env = dict(os.environ)
     env["PATH"] = os.path.join(HERE, "bin") + os.pathsep + env.get("PATH", "")
@@ -56,7 +104,7 @@ def run_mapper(sam_path, variant_table, out_path, baseq=10, isize_cutoff=0, hash
 
 
 def run_reference(vcf_gz, bams, out_prefix, sample, mapq="255", baseq=10, paired_end="1",
-                  extra_args=(), hashseed=0, threads=1, quiet=True, timeout=None, compiled=False):
+                  extra_args=(), hashseed=0, threads=1, quiet=True, timeout=None, compiled=False, fast_shim_dir=None):
     """L2/L3 oracle: the whole reference phaser.py (phaser/phaser.py:26-178).
 
     `bams` are SAM text files (coordinate sorted, with @SQ lines).  Empty `.bai` / `.tbi` files are
@@ -82,8 +130,10 @@ def run_reference(vcf_gz, bams, out_prefix, sample, mapq="255", baseq=10, paired
            "--vcf", vcf_gz, "--bam", ",".join(bams), "--sample", sample,
            "--mapq", str(mapq), "--baseq", str(baseq), "--paired_end", str(paired_end),
            "--o", out_prefix, "--threads", str(threads)] + [str(a) for a in extra_args]
-    res = subprocess.run(cmd, env=_env(hashseed), stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
-                         timeout=timeout)
+    env = _env(hashseed)
+    if fast_shim_dir:
+        env["PHZ_FAST_SHIM_DIR"] = fast_shim_dir
+    res = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout)
     log = res.stdout.decode("utf-8", "replace")
     if not quiet:
         sys.stdout.write(log)

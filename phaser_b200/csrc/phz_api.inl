@@ -182,6 +182,7 @@ int phz_set_option(phz_ctx* ctx, const char* name, int64_t value) {
   PHZ_TRY
   std::string n(name);
   if (n == "k1_mode") ctx->p.k1_mode = (int)value;
+  else if (n == "k1_min_ctas") ctx->p.k1_min_ctas = (int)value;
   else throw PhzError("unknown option: " + n);
   PHZ_CATCH
 }

@@ -11,6 +11,7 @@
 #include <thread>
 #include <atomic>
 #include <fstream>
+#include <chrono>
 
 namespace phzio {
 
@@ -335,18 +336,25 @@ phz_host_reads* phz_read_alignments(const char* path, const char* const* contigs
                                     int remove_dups, int proper_pair, int min_mapq, int n_threads) {
   try {
     std::vector<u8> raw;
+    const bool timing = std::getenv("PHZ_IO_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now();
     if (!phzio::read_file(path, raw)) throw PhzError(std::string("cannot read ") + path);
+    double t1 = now();
     std::vector<u8> data;
     bool gz = raw.size() >= 18 && raw[0] == 0x1f && raw[1] == 0x8b;
     bool bgzf = gz && (raw[3] & 4) && raw[12] == 'B' && raw[13] == 'C';
     if (bgzf) phzio::inflate_bgzf(raw, data, n_threads);
     else if (gz) phzio::inflate_gzip_stream(raw, data);
     else data.swap(raw);
+    double t2 = now();
     phz_host_reads* out = new phz_host_reads();
     if (data.size() >= 4 && std::memcmp(data.data(), "BAM\1", 4) == 0)
       out->h = phzio::parse_bam(data, contigs, n_contigs, &fd->d, remove_dups, proper_pair, min_mapq);
     else
       out->h = phzio::parse_sam(data, contigs, n_contigs, &fd->d, remove_dups, proper_pair, min_mapq);
+    if (timing) std::fprintf(stderr, "[phz_io] read %.3fs inflate %.3fs parse+build %.3fs (%lld records)\n", t1 - t0, t2 - t1,
+                             now() - t2, (long long)out->h->pos.size());
     return out;
   } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
 }

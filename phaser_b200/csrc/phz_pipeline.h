@@ -292,7 +292,8 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, in
                ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
 }
 
-__global__ void __launch_bounds__(KF_THREADS) k1_tile_kernel(ReadsView rv, VariantsView vv, const TileInfo* __restrict__ tiles,
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView rv, VariantsView vv, const TileInfo* __restrict__ tiles,
                                                             int baseq, double isize_cutoff, u32* __restrict__ s_rec,
                                                             u32* __restrict__ s_var, u32* __restrict__ s_misc, u64 capacity,
                                                             unsigned long long* cursor, u32* __restrict__ tile_base,
@@ -397,6 +398,7 @@ __global__ void __launch_bounds__(KF_THREADS) k1_tile_kernel(ReadsView rv, Varia
 template <class B>
 struct Pipeline {
   B be;
+  int k1_min_ctas = 8;        // register budget of the tile kernel: 8 -> 32 regs, 6 -> 40 regs, else unconstrained
   int k1_mode = 3;            // 3: tile kernel + permute (default), 2: fused look-back, 1: windowed two-pass, 0: generic two-pass
   Buf<B, u32> s_rec, s_var, s_misc, tile_base, tile_cnt, tile_canon;
   Buf<B, TileInfo> tile_info; Buf<B, u64> tile_status; Buf<B, u32> k1_ticket;
@@ -532,8 +534,12 @@ struct Pipeline {
       total = 0;
 #ifdef __CUDACC__
       u64* cur = tile_status.ensure(2); be.memset0(cur, 2 * sizeof(u64));
-      k1_tile_kernel<<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, sr, sv, sm, (u64)cap,
-                                                                     cur, tb, tc);
+      if (k1_min_ctas >= 8)
+        k1_tile_kernel<8><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, sr, sv, sm, (u64)cap, cur, tb, tc);
+      else if (k1_min_ctas >= 6)
+        k1_tile_kernel<6><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, sr, sv, sm, (u64)cap, cur, tb, tc);
+      else
+        k1_tile_kernel<1><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, sr, sv, sm, (u64)cap, cur, tb, tc);
       PHZ_CUDA(cudaGetLastError());
       be.launches++;
       be.d2h(&total, cur, sizeof(u64));
