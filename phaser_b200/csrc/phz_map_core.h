@@ -38,6 +38,7 @@ struct ReadsView {
 
 // The same record fields, served from the shared-memory slabs a tile's TMA bulk copies filled
 // (records [r0, r0+256)); CIGAR words beyond the staged slab fall back to global memory.
+template <bool ALL_CIGAR_STAGED>
 struct TileRV {
   int64_t r0;
   const int32_t* s_pos; const int32_t* s_tlen; const u32* s_coff; const u32* s_cig; const u64* s_soff; const int16_t* s_as;
@@ -47,7 +48,11 @@ struct TileRV {
   PHZ_HD int32_t tlen_at(int64_t r) const { return s_tlen[r - r0]; }
   PHZ_HD u32 cig_lo(int64_t r) const { return s_coff[r - r0]; }
   PHZ_HD u32 cig_hi(int64_t r) const { return s_coff[r - r0 + 1]; }
-  PHZ_HD u32 cigar_at(u32 k) const { u32 i = k - cig_base; return i < cig_n ? s_cig[i] : cigar[k]; }
+  PHZ_HD u32 cigar_at(u32 k) const {
+    u32 i = k - cig_base;
+    if (ALL_CIGAR_STAGED) return s_cig[i];
+    return i < cig_n ? s_cig[i] : cigar[k];
+  }
   PHZ_HD u64 seq_off_at(int64_t r) const { return s_soff[r - r0]; }
   PHZ_HD int aln_at(int64_t r) const { return s_as[r - r0]; }
 };

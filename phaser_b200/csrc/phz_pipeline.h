@@ -10,6 +10,7 @@
 //                  edge drop (integer critical value), components, block order, phasing, counts
 //   read_lists     phaser.py:1105-1115                  per (block, BAM, haplotype, variant) read lists
 #pragma once
+#include <type_traits>
 #include "phz_map_core.h"
 #include "phz_phase_core.h"
 
@@ -286,6 +287,7 @@ __global__ void __launch_bounds__(KF_THREADS) k1_fused_kernel(ReadsView rv, Vari
 // moves each tile's block into (record, segment, variant) order.
 #ifdef __CUDACC__
 constexpr int KT_CIG = 1024;          // CIGAR words staged per tile (4 KB); tiles with more fall back to global loads
+constexpr int KT_OWN = 1024;          // candidate slots with a direct owner entry; beyond that a search over the offsets
 
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, int bytes, unsigned long long* mbar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -308,6 +310,7 @@ __global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView
   __shared__ __align__(8) unsigned long long mbar;
   __shared__ u32 warp_sum[KF_THREADS / 32];
   __shared__ u32 excl_of[KF_THREADS + 1];
+  __shared__ u8 sh_owner[KT_OWN];                     // candidate slot -> record of the tile that owns it
   __shared__ unsigned long long s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t tile = blockIdx.x;
@@ -359,39 +362,50 @@ __global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView
                    : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0) : "memory");
     }
   }
-  const TileRV trv{r0, sh_pos, sh_tlen, sh_coff, sh_cig, sh_soff, sh_as, cig_al, cig_n, rv.cigar, rv.seq, rv.qual};
-  const WindowVP vp = window_of(ti, vv.pos, win, contig == contig0);
-  const u32 cnt = live ? map_record<0>(trv, vv, vp, r, contig, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr) : 0u;
-  // ---- CTA exclusive scan of the counts
-  u32 incl = cnt;
-  #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-  if (lane == 31) warp_sum[warp] = incl;
-  __syncthreads();
-  u32 warp_base = 0, cta_total = 0;
-  #pragma unroll
-  for (int w = 0; w < KF_THREADS / 32; ++w) { u32 v = warp_sum[w]; if (w < warp) warp_base += v; cta_total += v; }
-  excl_of[tid] = warp_base + incl - cnt;
-  if (tid == 0) {
-    excl_of[KF_THREADS] = cta_total;
-    unsigned long long b = cta_total ? atomicAdd(cursor, (unsigned long long)cta_total) : 0ull;
-    s_base = b;
-    tile_base[tile] = (u32)b; tile_cnt[tile] = cta_total;
-  }
-  __syncthreads();
-  const u64 base = s_base;
-  if (cta_total == 0 || base + cta_total > capacity) return;
-  // ---- dense emission: candidate i of the tile -> thread i
-  for (u32 i = (u32)tid; i < cta_total; i += KF_THREADS) {
-    int lo = 0, hi = KF_THREADS;                      // last record index with excl_of <= i
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (excl_of[mid] <= i) lo = mid; else hi = mid; }
-    const int64_t rr = r0 + lo;
-    int c = contig0;
-    if (rr >= contig0_end) c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, rr);
-    const WindowVP vpk = window_of(ti, vv.pos, win, c == contig0);
-    map_record<2>(trv, vv, vpk, rr, c, baseq, isize_cutoff, (u64)(i - excl_of[lo]), s_rec + base + i, s_var + base + i,
-                  s_misc + base + i);
-  }
+  // Everything after the slabs have landed, instantiated twice: for all but pathological tiles the whole
+  // CIGAR range of the tile is in shared memory and is read unconditionally.
+  auto body = [&](auto staged) {
+    const TileRV<decltype(staged)::value> trv{r0, sh_pos, sh_tlen, sh_coff, sh_cig, sh_soff, sh_as, cig_al, cig_n, rv.cigar, rv.seq, rv.qual};
+    const WindowVP vp = window_of(ti, vv.pos, win, contig == contig0);
+    const u32 cnt = live ? map_record<0>(trv, vv, vp, r, contig, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr) : 0u;
+    // ---- CTA exclusive scan of the counts
+    u32 incl = cnt;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    u32 warp_base = 0, cta_total = 0;
+    #pragma unroll
+    for (int w = 0; w < KF_THREADS / 32; ++w) { u32 v = warp_sum[w]; if (w < warp) warp_base += v; cta_total += v; }
+    const u32 my_excl = warp_base + incl - cnt;
+    excl_of[tid] = my_excl;
+    for (u32 k = 0; k < cnt && my_excl + k < KT_OWN; ++k) sh_owner[my_excl + k] = (u8)tid;
+    if (tid == 0) {
+      excl_of[KF_THREADS] = cta_total;
+      unsigned long long b = cta_total ? atomicAdd(cursor, (unsigned long long)cta_total) : 0ull;
+      s_base = b;
+      tile_base[tile] = (u32)b; tile_cnt[tile] = cta_total;
+    }
+    __syncthreads();
+    const u64 base = s_base;
+    if (cta_total == 0 || base + cta_total > capacity) return;
+    // ---- dense emission: candidate i of the tile -> thread i
+    for (u32 i = (u32)tid; i < cta_total; i += KF_THREADS) {
+      int lo;
+      if (i < KT_OWN) lo = sh_owner[i];
+      else {                                            // last record index with excl_of <= i
+        lo = 0; int hi = KF_THREADS;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (excl_of[mid] <= i) lo = mid; else hi = mid; }
+      }
+      const int64_t rr = r0 + lo;
+      int c = contig0;
+      if (rr >= contig0_end) c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, rr);
+      const WindowVP vpk = window_of(ti, vv.pos, win, c == contig0);
+      map_record<2>(trv, vv, vpk, rr, c, baseq, isize_cutoff, (u64)(i - excl_of[lo]), s_rec + base + i, s_var + base + i,
+                    s_misc + base + i);
+    }
+  };
+  if ((u64)sh_coff[nrec] <= (u64)cig_al + cig_n) body(std::true_type{}); else body(std::false_type{});
 }
 #endif
 
