@@ -9,6 +9,8 @@
 // shared by all BAMs of a run (exact: names are compared, not just hashed).
 #include <zlib.h>
 #include <thread>
+#include <mutex>
+#include <exception>
 #include <atomic>
 #include <fstream>
 #include <chrono>
@@ -17,40 +19,100 @@ namespace phzio {
 
 using phz::u64; using phz::u32; using phz::u8; using phz::PhzError;
 
+template <class F>
+static void parallel_for(size_t n, int n_threads, F f) {      // f(i) for i in [0, n), dynamic schedule
+  if (n_threads < 1) n_threads = 1;
+  if ((size_t)n_threads > n) n_threads = (int)(n ? n : 1);
+  std::atomic<size_t> next(0);
+  std::exception_ptr err; std::mutex em;
+  auto work = [&]() {
+    try { while (true) { size_t i = next.fetch_add(1); if (i >= n) break; f(i); } }
+    catch (...) { std::lock_guard<std::mutex> g(em); if (!err) err = std::current_exception(); next = n; }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+  if (err) std::rethrow_exception(err);
+}
+
+static u64 name_hash(const char* s, size_t n) {
+  u64 h = 1469598103934665603ull;
+  for (size_t i = 0; i < n; ++i) { h ^= (u8)s[i]; h *= 1099511628211ull; }
+  h ^= h >> 29; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 32;
+  return h;
+}
+
+// QNAME -> dense fragment id.  64 independent shards (by hash) so that one BAM's names are inserted by
+// many threads at once; ids are handed out in order of first appearance in the file, which keeps the
+// fragments of one locus numerically close (the device code aggregates on that).
 struct FragDict {
-  // open addressing over (hash, arena offset); names live in one arena
-  std::vector<u64> slot_hash; std::vector<u32> slot_id;
-  std::vector<u64> name_off; std::string arena;
-  size_t mask = 0, count = 0;
-  FragDict() { resize(1 << 16); }
-  void resize(size_t n) {
-    std::vector<u64> oh(n, 0); std::vector<u32> oi(n, 0xFFFFFFFFu);
-    for (size_t i = 0; i < slot_hash.size(); ++i)
-      if (slot_id[i] != 0xFFFFFFFFu) { size_t p = slot_hash[i] & (n - 1); while (oi[p] != 0xFFFFFFFFu) p = (p + 1) & (n - 1); oh[p] = slot_hash[i]; oi[p] = slot_id[i]; }
-    slot_hash.swap(oh); slot_id.swap(oi); mask = n - 1;
-  }
-  static u64 hash(const char* s, size_t n) {
-    u64 h = 1469598103934665603ull;
-    for (size_t i = 0; i < n; ++i) { h ^= (u8)s[i]; h *= 1099511628211ull; }
-    h ^= h >> 29; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 32;
-    return h;
-  }
-  u32 get(const char* s, size_t n) {
-    u64 h = hash(s, n);
-    size_t p = h & mask;
-    while (slot_id[p] != 0xFFFFFFFFu) {
-      if (slot_hash[p] == h) {
-        u32 id = slot_id[p]; u64 o = name_off[id]; size_t len = (size_t)(name_off[id + 1] - o);
-        if (len == n && std::memcmp(arena.data() + o, s, n) == 0) return id;
-      }
-      p = (p + 1) & mask;
+  static constexpr int NS = 64;
+  struct Shard {
+    std::vector<u64> slot_hash; std::vector<u32> slot_ent;       // open addressing -> entry index
+    std::vector<u64> name_off; std::string arena;                // entry -> name
+    std::vector<u32> gid; std::vector<u64> first_rec;            // entry -> global id / first record of the current file
+    size_t mask = 0;
+    Shard() { name_off.push_back(0); resize(1 << 12); }
+    void resize(size_t n) {
+      std::vector<u64> oh(n, 0); std::vector<u32> oe(n, 0xFFFFFFFFu);
+      for (size_t i = 0; i < slot_hash.size(); ++i)
+        if (slot_ent[i] != 0xFFFFFFFFu) { size_t p = slot_hash[i] & (n - 1); while (oe[p] != 0xFFFFFFFFu) p = (p + 1) & (n - 1); oh[p] = slot_hash[i]; oe[p] = slot_ent[i]; }
+      slot_hash.swap(oh); slot_ent.swap(oe); mask = n - 1;
     }
-    u32 id = (u32)count++;
-    if (name_off.empty()) name_off.push_back(0);
-    arena.append(s, n); name_off.push_back(arena.size());
-    slot_hash[p] = h; slot_id[p] = id;
-    if (count * 2 > mask + 1) resize((mask + 1) * 2);
-    return id;
+    // entry index of the name, inserting it (gid unknown yet, first seen at record `rec`) when new
+    u32 find_or_add(u64 h, const char* s, size_t n, u64 rec) {
+      size_t p = h & mask;
+      while (slot_ent[p] != 0xFFFFFFFFu) {
+        if (slot_hash[p] == h) {
+          u32 e = slot_ent[p]; u64 o = name_off[e];
+          if ((size_t)(name_off[e + 1] - o) == n && std::memcmp(arena.data() + o, s, n) == 0) return e;
+        }
+        p = (p + 1) & mask;
+      }
+      u32 e = (u32)gid.size();
+      arena.append(s, n); name_off.push_back(arena.size());
+      gid.push_back(0xFFFFFFFFu); first_rec.push_back(rec);
+      slot_hash[p] = h; slot_ent[p] = e;
+      if (gid.size() * 2 > mask + 1) resize((mask + 1) * 2);
+      return e;
+    }
+  };
+  Shard sh[NS];
+  std::vector<u8> id_shard; std::vector<u32> id_ent;             // global id -> (shard, entry)
+  size_t count = 0;
+  static int shard_of(u64 h) { return (int)(h >> 58); }
+
+  // ids for the kept records of one file (names[i], lens[i], hashes[i] in file order) -> out[i]
+  void assign(const std::vector<const char*>& names, const std::vector<u32>& lens, const std::vector<u64>& hashes,
+              std::vector<u32>& out, int n_threads) {
+    size_t n = names.size();
+    out.resize(n);
+    std::vector<u32> ent(n);
+    parallel_for(NS, n_threads, [&](size_t s) {
+      Shard& S = sh[s];
+      for (size_t i = 0; i < n; ++i)
+        if ((size_t)shard_of(hashes[i]) == s) ent[i] = S.find_or_add(hashes[i], names[i], lens[i], (u64)i);
+    });
+    // new names get ids in order of first appearance: exclusive count of "first" records
+    size_t base = count, fresh = 0;
+    for (size_t i = 0; i < n; ++i) {
+      Shard& S = sh[shard_of(hashes[i])]; u32 e = ent[i];
+      if (S.gid[e] == 0xFFFFFFFFu && S.first_rec[e] == (u64)i) {
+        S.gid[e] = (u32)(base + fresh); fresh++;
+        id_shard.push_back((u8)shard_of(hashes[i])); id_ent.push_back(e);
+      }
+    }
+    count = base + fresh;
+    parallel_for((n + 65535) / 65536, n_threads, [&](size_t c) {
+      size_t i1 = std::min(n, (c + 1) * 65536);
+      for (size_t i = c * 65536; i < i1; ++i) out[i] = sh[shard_of(hashes[i])].gid[ent[i]];
+    });
+  }
+  u32 get(const char* s, size_t n) {      // single lookup (tests / small inputs)
+    std::vector<const char*> a{s}; std::vector<u32> l{(u32)n}; std::vector<u64> h{name_hash(s, n)}; std::vector<u32> o;
+    assign(a, l, h, o, 1);
+    return o[0];
   }
 };
 
@@ -133,6 +195,7 @@ static void inflate_gzip_stream(const std::vector<u8>& in, std::vector<u8>& out)
 
 struct Rec {              // one alignment that passed the filters, as offsets into the raw buffer
   int contig; int32_t pos, tlen; int16_t aln; u32 frag;
+  const char* qname; u32 l_qname;
   const u8* cig; u32 n_cig;        // BAM: packed words; SAM: text
   const u8* seq; const u8* qual; u32 l_seq;
   bool text;
@@ -175,7 +238,26 @@ static int16_t as_from_aux(const u8* p, const u8* end, std::string& err) {
   return -32768;
 }
 
-static HostReads* build(std::vector<Rec>& recs, int nc) {
+static void assign_fragments(std::vector<Rec>& recs, FragDict* fd, int n_threads) {
+  size_t n = recs.size();
+  std::vector<const char*> names(n); std::vector<u32> lens(n); std::vector<u64> hashes(n); std::vector<u32> ids;
+  parallel_for((n + 65535) / 65536, n_threads, [&](size_t c) {
+    size_t i1 = std::min(n, (c + 1) * 65536);
+    for (size_t i = c * 65536; i < i1; ++i) { names[i] = recs[i].qname; lens[i] = recs[i].l_qname; hashes[i] = name_hash(recs[i].qname, recs[i].l_qname); }
+  });
+  fd->assign(names, lens, hashes, ids, n_threads);
+  for (size_t i = 0; i < n; ++i) recs[i].frag = ids[i];
+}
+
+static u32 count_cigar_ops(const Rec& r) {
+  if (!r.text) return r.n_cig;
+  if (r.n_cig == 1 && r.cig[0] == '*') return 0;
+  u32 nops = 0;
+  for (u32 i = 0; i < r.n_cig; ++i) if (r.cig[i] < '0' || r.cig[i] > '9') nops++;
+  return nops;
+}
+
+static HostReads* build(std::vector<Rec>& recs, int nc, int n_threads) {
   HostReads* H = new HostReads();
   H->n_contigs = nc;
   size_t R = recs.size();
@@ -188,41 +270,47 @@ static HostReads* build(std::vector<Rec>& recs, int nc) {
   for (size_t i = 0; i < R; ++i) order[cur[recs[i].contig]++] = (u32)i;      // stable: file order inside a contig
   H->pos.resize(R); H->tlen.resize(R); H->aln.resize(R); H->frag.resize(R);
   H->cigar_off.assign(R + 1, 0); H->seq_off.assign(R + 1, 0);
-  // sizes
-  for (size_t k = 0; k < R; ++k) {
-    const Rec& r = recs[order[k]];
-    u32 nops = r.n_cig;
-    if (r.text) { nops = 0; for (u32 i = 0; i < r.n_cig; ++i) if (r.cig[i] < '0' || r.cig[i] > '9') nops++; if (r.n_cig == 1 && r.cig[0] == '*') nops = 0; }
-    H->cigar_off[k + 1] = H->cigar_off[k] + nops;
-    H->seq_off[k + 1] = H->seq_off[k] + r.l_seq;
-  }
+  const size_t CH = 16384, n_chunks = (R + CH - 1) / CH;
+  // sizes: per-record counts in parallel, running sums serially
+  parallel_for(n_chunks, n_threads, [&](size_t c) {
+    size_t k1 = std::min(R, (c + 1) * CH);
+    for (size_t k = c * CH; k < k1; ++k) { const Rec& r = recs[order[k]]; H->cigar_off[k + 1] = count_cigar_ops(r); H->seq_off[k + 1] = r.l_seq; }
+  });
+  for (size_t k = 0; k < R; ++k) { H->cigar_off[k + 1] += H->cigar_off[k]; H->seq_off[k + 1] += H->seq_off[k]; }
+  if (R && (u64)H->cigar_off[R] < (u64)H->cigar_off[R - 1]) throw PhzError("more than 2^32 CIGAR operations in one file");
   H->cigar.resize(H->cigar_off[R]);
   u64 nb = H->seq_off[R];
   H->qual.resize(nb); H->seq.assign((nb + 1) / 2, 0);
   static const char* OPS = "MIDNSHP=X";
-  for (size_t k = 0; k < R; ++k) {
-    const Rec& r = recs[order[k]];
-    H->pos[k] = r.pos; H->tlen[k] = r.tlen; H->aln[k] = r.aln; H->frag[k] = r.frag;
-    u32* co = H->cigar.data() + H->cigar_off[k];
-    if (!r.text) {
-      std::memcpy(co, r.cig, (size_t)r.n_cig * 4);
-    } else if (!(r.n_cig == 1 && r.cig[0] == '*')) {
-      u32 n = 0, w = 0;
-      for (u32 i = 0; i < r.n_cig; ++i) {
-        u8 ch = r.cig[i];
-        if (ch >= '0' && ch <= '9') n = n * 10 + (ch - '0');
-        else { const char* q = std::strchr(OPS, ch); co[w++] = (n << 4) | (u32)(q ? q - OPS : 0); n = 0; }
+  parallel_for(n_chunks, n_threads, [&](size_t c) {
+    size_t k1 = std::min(R, (c + 1) * CH);
+    for (size_t k = c * CH; k < k1; ++k) {
+      const Rec& r = recs[order[k]];
+      H->pos[k] = r.pos; H->tlen[k] = r.tlen; H->aln[k] = r.aln; H->frag[k] = r.frag;
+      u32* co = H->cigar.data() + H->cigar_off[k];
+      if (!r.text) {
+        std::memcpy(co, r.cig, (size_t)r.n_cig * 4);
+      } else if (!(r.n_cig == 1 && r.cig[0] == '*')) {
+        u32 n = 0, w = 0;
+        for (u32 i = 0; i < r.n_cig; ++i) {
+          u8 ch = r.cig[i];
+          if (ch >= '0' && ch <= '9') n = n * 10 + (ch - '0');
+          else { const char* q = std::strchr(OPS, ch); co[w++] = (n << 4) | (u32)(q ? q - OPS : 0); n = 0; }
+        }
+      }
+      u64 b0 = H->seq_off[k];
+      for (u32 j = 0; j < r.l_seq; ++j) {
+        u8 code = r.text ? BASE_OF_TABLE.t[r.seq[j]] : ((j & 1) ? (r.seq[j >> 1] & 15) : (r.seq[j >> 1] >> 4));
+        u64 i = b0 + j;
+        u8 val = (i & 1) ? code : (u8)(code << 4);
+        // the first / last byte of a record can be shared with a neighbour handled by another thread
+        if (j == 0 || j + 1 == r.l_seq) __atomic_fetch_or(&H->seq[i >> 1], val, __ATOMIC_RELAXED);
+        else H->seq[i >> 1] |= val;
+        int q = r.text ? (int)r.qual[j] - 33 : (int)r.qual[j];
+        H->qual[i] = (u8)(q < 0 ? 0 : q);
       }
     }
-    u64 b0 = H->seq_off[k];
-    for (u32 j = 0; j < r.l_seq; ++j) {
-      u8 code = r.text ? BASE_OF_TABLE.t[r.seq[j]] : ((j & 1) ? (r.seq[j >> 1] & 15) : (r.seq[j >> 1] >> 4));
-      u64 i = b0 + j;
-      H->seq[i >> 1] |= (i & 1) ? code : (u8)(code << 4);
-      int q = r.text ? (int)r.qual[j] - 33 : (int)r.qual[j];
-      H->qual[i] = (u8)(q < 0 ? 0 : q);
-    }
-  }
+  });
   for (int c = 0; c < nc; ++c)
     for (int64_t k = H->contig_rec_off[c] + 1; k < H->contig_rec_off[c + 1]; ++k)
       if (H->pos[k] < H->pos[k - 1]) { H->sorted = 0; break; }
@@ -230,7 +318,7 @@ static HostReads* build(std::vector<Rec>& recs, int nc) {
 }
 
 static HostReads* parse_bam(const std::vector<u8>& d, const char* const* contigs, int nc, FragDict* fd, int remove_dups,
-                            int proper_pair, int min_mapq) {
+                            int proper_pair, int min_mapq, int n_threads) {
   auto rd32 = [&](size_t o) { return (int32_t)(d[o] | (d[o + 1] << 8) | (d[o + 2] << 16) | ((u32)d[o + 3] << 24)); };
   if (d.size() < 12 || std::memcmp(d.data(), "BAM\1", 4) != 0) throw PhzError("not a BAM file");
   size_t p = 8 + (size_t)rd32(4);
@@ -241,77 +329,119 @@ static HostReads* parse_bam(const std::vector<u8>& d, const char* const* contigs
     std::string name((const char*)d.data() + p, ln > 0 ? ln - 1 : 0); p += ln + 4;
     for (int c = 0; c < nc; ++c) if (name == contigs[c]) ref_to_contig[i] = c;
   }
-  std::vector<Rec> recs;
-  std::string err;
+  // record boundaries (serial pointer chase), then filter + decode headers in parallel chunks
+  std::vector<size_t> starts;
   while (p + 4 <= d.size()) {
-    int32_t bs = rd32(p); size_t s = p + 4; p = s + (size_t)bs;
-    if (p > d.size()) throw PhzError("truncated BAM record");
-    int ref = rd32(s); if (ref < 0 || ref >= n_ref) continue;
-    int ci = ref_to_contig[ref]; if (ci < 0) continue;
-    u32 l_rn = d[s + 8], mapq = d[s + 9], n_cig = d[s + 12] | (d[s + 13] << 8), flag = d[s + 14] | (d[s + 15] << 8);
-    int32_t l_seq = rd32(s + 16);
-    if (remove_dups && (flag & 0x400)) continue;
-    if (proper_pair && !(flag & 2)) continue;
-    if ((int)mapq < min_mapq) continue;
-    size_t o = s + 32;
-    Rec r; r.text = false; r.contig = ci; r.pos = rd32(s + 4) + 1; r.tlen = rd32(s + 28);
-    r.frag = fd->get((const char*)d.data() + o, l_rn ? l_rn - 1 : 0); o += l_rn;
-    r.cig = d.data() + o; r.n_cig = n_cig; o += (size_t)n_cig * 4;
-    r.seq = d.data() + o; o += ((size_t)l_seq + 1) / 2; r.qual = d.data() + o; r.l_seq = (u32)l_seq; o += l_seq;
-    if (l_seq > 0 && r.qual[0] == 0xFF) throw PhzError("record without QUAL (unsupported)");
-    r.aln = as_from_aux(d.data() + o, d.data() + p, err);
-    if (!err.empty()) throw PhzError(err);
-    recs.push_back(r);
+    int32_t bs = rd32(p);
+    if (bs < 32 || p + 4 + (size_t)bs > d.size()) throw PhzError("truncated or corrupt BAM record");
+    starts.push_back(p + 4); p += 4 + (size_t)bs;
   }
-  return build(recs, nc);
+  const size_t CH = 16384, n_chunks = (starts.size() + CH - 1) / CH;
+  std::vector<std::vector<Rec>> parts(n_chunks);
+  parallel_for(n_chunks, n_threads, [&](size_t c) {
+    size_t i1 = std::min(starts.size(), (c + 1) * CH);
+    std::vector<Rec>& out = parts[c];
+    std::string err;
+    for (size_t i = c * CH; i < i1; ++i) {
+      size_t s = starts[i]; size_t e = s + (size_t)rd32(s - 4);
+      int ref = rd32(s); if (ref < 0 || ref >= n_ref) continue;
+      int ci = ref_to_contig[ref]; if (ci < 0) continue;
+      u32 l_rn = d[s + 8], mapq = d[s + 9], n_cig = d[s + 12] | (d[s + 13] << 8), flag = d[s + 14] | (d[s + 15] << 8);
+      int32_t l_seq = rd32(s + 16);
+      if (remove_dups && (flag & 0x400)) continue;
+      if (proper_pair && !(flag & 2)) continue;
+      if ((int)mapq < min_mapq) continue;
+      size_t o = s + 32;
+      Rec r; r.text = false; r.contig = ci; r.pos = rd32(s + 4) + 1; r.tlen = rd32(s + 28); r.frag = 0;
+      r.qname = (const char*)d.data() + o; r.l_qname = l_rn ? l_rn - 1 : 0; o += l_rn;
+      r.cig = d.data() + o; r.n_cig = n_cig; o += (size_t)n_cig * 4;
+      r.seq = d.data() + o; o += ((size_t)l_seq + 1) / 2; r.qual = d.data() + o; r.l_seq = (u32)l_seq; o += l_seq;
+      if (o > e) throw PhzError("corrupt BAM record (fields exceed block_size)");
+      if (l_seq > 0 && r.qual[0] == 0xFF) throw PhzError("record without QUAL (unsupported)");
+      r.aln = as_from_aux(d.data() + o, d.data() + e, err);
+      if (!err.empty()) throw PhzError(err);
+      out.push_back(r);
+    }
+  });
+  std::vector<Rec> recs;
+  size_t total = 0; for (auto& v : parts) total += v.size();
+  recs.reserve(total);
+  for (auto& v : parts) { recs.insert(recs.end(), v.begin(), v.end()); std::vector<Rec>().swap(v); }
+  assign_fragments(recs, fd, n_threads);
+  return build(recs, nc, n_threads);
+}
+
+static void parse_sam_line(const u8* p, const u8* le, const char* const* contigs, int nc, int remove_dups, int proper_pair,
+                           int min_mapq, std::vector<Rec>& out) {
+  const u8* f[12]; int nf = 0; const u8* q = p; f[nf++] = q;
+  while (q < le && nf < 12) { if (*q == '\t') f[nf++] = q + 1; ++q; }
+  if (nf < 11) return;
+  auto len = [&](int i) { return (size_t)((i + 1 < nf ? f[i + 1] - 1 : le) - f[i]); };
+  auto toint = [&](int i) { char b[24]; size_t n = len(i); if (n > 23) n = 23; std::memcpy(b, f[i], n); b[n] = 0; return std::strtol(b, nullptr, 10); };
+  int ci = -1;
+  for (int c = 0; c < nc; ++c) if (std::strlen(contigs[c]) == len(2) && std::memcmp(contigs[c], f[2], len(2)) == 0) { ci = c; break; }
+  if (ci < 0) return;
+  long flag = toint(1), mapq = toint(4);
+  if ((remove_dups && (flag & 0x400)) || (proper_pair && !(flag & 2)) || mapq < min_mapq) return;
+  Rec r; r.text = true; r.contig = ci; r.pos = (int32_t)toint(3); r.tlen = (int32_t)toint(8); r.frag = 0;
+  r.qname = (const char*)f[0]; r.l_qname = (u32)len(0);
+  r.cig = f[5]; r.n_cig = (u32)len(5);
+  r.seq = f[9]; r.l_seq = (u32)len(9);
+  const u8* qe = le; if (nf > 11) qe = f[11] - 1;
+  r.qual = f[10]; size_t lq = (size_t)(qe - f[10]);
+  if (r.l_seq == 1 && r.seq[0] == '*') r.l_seq = 0;
+  if (lq != r.l_seq) throw PhzError("SAM record with QUAL missing or not the length of SEQ (unsupported)");
+  r.aln = -32768;
+  if (nf > 11) {          // first AS: tag from column 12 on (read_variant_map.py:56-59)
+    const u8* t = f[11];
+    while (t < le) {
+      const u8* te = (const u8*)std::memchr(t, '\t', le - t); if (!te) te = le;
+      if (te - t > 5 && t[0] == 'A' && t[1] == 'S' && t[2] == ':') {
+        const u8* c2 = (const u8*)std::memchr(t + 3, ':', te - t - 3);
+        if (c2) {
+          char b[24]; size_t n = (size_t)(te - c2 - 1); if (n > 23) n = 23; std::memcpy(b, c2 + 1, n); b[n] = 0;
+          long v = std::strtol(b, nullptr, 10);
+          if (v < -32767 || v > 32767) throw PhzError("AS:i value outside the int16 range of the packed layout");
+          r.aln = (int16_t)v; break;
+        }
+      }
+      t = te + 1;
+    }
+  }
+  out.push_back(r);
 }
 
 static HostReads* parse_sam(const std::vector<u8>& d, const char* const* contigs, int nc, FragDict* fd, int remove_dups,
-                            int proper_pair, int min_mapq) {
-  std::vector<Rec> recs;
-  const u8* p = d.data(); const u8* end = p + d.size();
-  while (p < end) {
-    const u8* eol = (const u8*)std::memchr(p, '\n', end - p); if (!eol) eol = end;
-    const u8* le = eol; if (le > p && le[-1] == '\r') --le;
-    if (p < le && *p != '@') {
-      const u8* f[12]; int nf = 0; const u8* q = p; f[nf++] = q;
-      while (q < le && nf < 12) { if (*q == '\t') f[nf++] = q + 1; ++q; }
-      if (nf >= 11) {
-        auto len = [&](int i) { return (size_t)((i + 1 < nf ? f[i + 1] - 1 : le) - f[i]); };
-        auto toint = [&](int i) { return std::strtol(std::string((const char*)f[i], len(i)).c_str(), nullptr, 10); };
-        std::string rname((const char*)f[2], len(2));
-        int ci = -1; for (int c = 0; c < nc; ++c) if (rname == contigs[c]) { ci = c; break; }
-        long flag = toint(1), mapq = toint(4);
-        if (ci >= 0 && !(remove_dups && (flag & 0x400)) && !(proper_pair && !(flag & 2)) && mapq >= min_mapq) {
-          Rec r; r.text = true; r.contig = ci; r.pos = (int32_t)toint(3); r.tlen = (int32_t)toint(8);
-          r.frag = fd->get((const char*)f[0], len(0));
-          r.cig = f[5]; r.n_cig = (u32)len(5);
-          r.seq = f[9]; r.l_seq = (u32)len(9);
-          const u8* qe = le; if (nf > 11) qe = f[11] - 1;
-          r.qual = f[10]; size_t lq = (size_t)(qe - f[10]);
-          if (r.l_seq == 1 && r.seq[0] == '*') r.l_seq = 0;
-          if (lq != r.l_seq) throw PhzError("SAM record with QUAL missing or not the length of SEQ (unsupported)");
-          r.aln = -32768;
-          if (nf > 11) {          // first AS: tag from column 12 on (read_variant_map.py:56-59)
-            const u8* t = f[11];
-            while (t < le) {
-              const u8* te = (const u8*)std::memchr(t, '\t', le - t); if (!te) te = le;
-              if (te - t > 5 && t[0] == 'A' && t[1] == 'S' && t[2] == ':') {
-                const u8* c2 = (const u8*)std::memchr(t + 3, ':', te - t - 3);
-                if (c2) { long v = std::strtol(std::string((const char*)c2 + 1, te - c2 - 1).c_str(), nullptr, 10);
-                          if (v < -32767 || v > 32767) throw PhzError("AS:i value outside the int16 range of the packed layout");
-                          r.aln = (int16_t)v; break; }
-              }
-              t = te + 1;
-            }
-          }
-          recs.push_back(r);
-        }
-      }
-    }
-    p = eol + 1;
+                            int proper_pair, int min_mapq, int n_threads) {
+  // chunk boundaries at line starts
+  const u8* base = d.data(); const u8* end = base + d.size();
+  size_t want = (size_t)(n_threads < 1 ? 1 : n_threads) * 8;
+  size_t step = d.size() / want + 1;
+  std::vector<const u8*> cuts{base};
+  for (size_t k = 1; k < want; ++k) {
+    const u8* q = base + std::min(d.size(), k * step);
+    if (q <= cuts.back()) continue;
+    const u8* nl = (const u8*)std::memchr(q, '\n', end - q);
+    if (!nl) break;
+    if (nl + 1 > cuts.back()) cuts.push_back(nl + 1);
   }
-  return build(recs, nc);
+  cuts.push_back(end);
+  std::vector<std::vector<Rec>> parts(cuts.size() - 1);
+  parallel_for(parts.size(), n_threads, [&](size_t c) {
+    const u8* p = cuts[c]; const u8* e = cuts[c + 1];
+    while (p < e) {
+      const u8* eol = (const u8*)std::memchr(p, '\n', e - p); if (!eol) eol = e;
+      const u8* le = eol; if (le > p && le[-1] == '\r') --le;
+      if (p < le && *p != '@') parse_sam_line(p, le, contigs, nc, remove_dups, proper_pair, min_mapq, parts[c]);
+      p = eol + 1;
+    }
+  });
+  std::vector<Rec> recs;
+  size_t total = 0; for (auto& v : parts) total += v.size();
+  recs.reserve(total);
+  for (auto& v : parts) { recs.insert(recs.end(), v.begin(), v.end()); std::vector<Rec>().swap(v); }
+  assign_fragments(recs, fd, n_threads);
+  return build(recs, nc, n_threads);
 }
 
 }  // namespace phzio
@@ -326,9 +456,10 @@ void phz_fragdict_destroy(phz_fragdict* d) { delete d; }
 int64_t phz_fragdict_size(phz_fragdict* d) { return (int64_t)d->d.count; }
 int64_t phz_fragdict_name(phz_fragdict* d, int64_t id, char* buf, int64_t buflen) {
   if (id < 0 || (size_t)id >= d->d.count) return -1;
-  u64 o = d->d.name_off[id]; int64_t n = (int64_t)(d->d.name_off[id + 1] - o);
+  const phzio::FragDict::Shard& S = d->d.sh[d->d.id_shard[id]]; u32 e = d->d.id_ent[id];
+  u64 o = S.name_off[e]; int64_t n = (int64_t)(S.name_off[e + 1] - o);
   if (n + 1 > buflen) return -(n + 1);
-  std::memcpy(buf, d->d.arena.data() + o, n); buf[n] = 0;
+  std::memcpy(buf, S.arena.data() + o, n); buf[n] = 0;
   return n;
 }
 
@@ -350,9 +481,9 @@ phz_host_reads* phz_read_alignments(const char* path, const char* const* contigs
     double t2 = now();
     phz_host_reads* out = new phz_host_reads();
     if (data.size() >= 4 && std::memcmp(data.data(), "BAM\1", 4) == 0)
-      out->h = phzio::parse_bam(data, contigs, n_contigs, &fd->d, remove_dups, proper_pair, min_mapq);
+      out->h = phzio::parse_bam(data, contigs, n_contigs, &fd->d, remove_dups, proper_pair, min_mapq, n_threads);
     else
-      out->h = phzio::parse_sam(data, contigs, n_contigs, &fd->d, remove_dups, proper_pair, min_mapq);
+      out->h = phzio::parse_sam(data, contigs, n_contigs, &fd->d, remove_dups, proper_pair, min_mapq, n_threads);
     if (timing) std::fprintf(stderr, "[phz_io] read %.3fs inflate %.3fs parse+build %.3fs (%lld records)\n", t1 - t0, t2 - t1,
                              now() - t2, (long long)out->h->pos.size());
     return out;
