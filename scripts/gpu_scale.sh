@@ -1,0 +1,8 @@
+#!/bin/bash
+# scaling preview: the bench at N = 8 and N = 4 exactly as the driver launches it
+mkdir -p gpurun_out
+nvidia-smi -L | wc -l; free -g | head -2
+for n in 8 4; do
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2961$n bench.py --gpus $n --steps 5 --warmup 3 > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err; python -c "
+import json;d=json.load(open('gpurun_out/bench_n$n.json'));print('N',$n,'value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e'])"; tail -2 gpurun_out/bench_n$n.err | cut -c1-200
+done
