@@ -387,7 +387,24 @@ def run_reference(a):
     print(json.dumps(out))
 
 
+def _claim_stdout():
+    """Exactly ONE line may reach stdout (the JSON result).  Libraries (NCCL's version banner, torchrun
+    hints) also write to fd 1, so everything is diverted to stderr and the result goes to the saved fd."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 if __name__ == "__main__":
+    _RESULT_OUT = _claim_stdout()
+    _orig_print = print
+
+    def print(*a, **k):          # noqa: A001 -- the two result prints below are the only stdout writers
+        k.setdefault("file", _RESULT_OUT)
+        _orig_print(*a, **k)
+        _RESULT_OUT.flush()
+
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
