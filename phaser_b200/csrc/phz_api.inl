@@ -103,7 +103,7 @@ int phz_as_histogram(phz_ctx* ctx, uint64_t* d_hist) { PHZ_TRY ctx->p.as_histogr
 int phz_commit_bam(phz_ctx* ctx, int bam_index, int32_t as_cutoff, const uint32_t* d_frag, int64_t* n_kept) {
   PHZ_TRY
   const u32* f = d_frag ? d_frag : ctx->st_frag.p;
-  if (!f) throw PhzError("phz_commit_bam: no fragment ids");
+  if (!f && ctx->p.n_cand > 0) throw PhzError("phz_commit_bam: no fragment ids");
   *n_kept = ctx->p.commit_bam(bam_index, as_cutoff, f);
   PHZ_CATCH
 }

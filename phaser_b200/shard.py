@@ -192,3 +192,77 @@ def run_sharded(engine, vt: VariantTable, batches: List[ReadBatch], params: Phas
     if rank != 0:
         return None
     return merge_results(gathered, vt, len(batches))
+
+
+class ThreadComm:
+    """The same reductions between N logical shards that run as threads of ONE process (one engine each,
+    possibly on one GPU): used to check that the merged output does not depend on the sharding."""
+
+    def __init__(self, world):
+        import threading
+        self.world_size = world
+        self._barrier = threading.Barrier(world)
+        self._slots = [None] * world
+        self._lock = threading.Lock()
+
+    def view(self, rank):
+        parent = self
+
+        class _View:
+            world_size = parent.world_size
+
+            def __init__(self):
+                self.rank = rank
+
+            def _exchange(self, value):
+                parent._slots[rank] = value
+                parent._barrier.wait()
+                vals = list(parent._slots)
+                parent._barrier.wait()
+                return vals
+
+            def allreduce_sum(self, t):
+                vals = self._exchange(t.detach().cpu().clone())
+                out = vals[0].clone()
+                for v in vals[1:]:
+                    out += v
+                return out.to(t.device)
+
+            def allreduce_sum_ints(self, xs):
+                vals = self._exchange(list(xs))
+                return [sum(v[i] for v in vals) for i in range(len(xs))]
+
+            def allreduce_max_int(self, x):
+                return max(self._exchange(int(x)))
+
+        return _View()
+
+
+def run_logical_shards(make_engine, vt: VariantTable, batches: List[ReadBatch], params: PhaseParams, n_fragments: int,
+                       n_shards: int) -> PhaseResult:
+    """N logical shards (threads, one engine each) + merge: must equal the unsharded run."""
+    import threading
+    weights = [int(sum(b.contig_rec_off[c + 1] - b.contig_rec_off[c] for b in batches)) + 1 for c in range(len(vt.contigs))]
+    plan = plan_shards(weights, n_shards)
+    comm = ThreadComm(n_shards)
+    parts = [None] * n_shards
+    errors = []
+
+    def work(r):
+        try:
+            engine = make_engine()
+            svt, gid = sub_variant_table(vt, plan[r])
+            dev = [engine.upload_reads(sub_read_batch(b, plan[r])) for b in batches]
+            parts[r] = (run_path(engine, svt, dev, params, n_fragments, comm=comm.view(r)), gid, plan[r])
+        except BaseException as e:          # noqa: BLE001 -- re-raised in the caller; never leave the others at the barrier
+            errors.append(e)
+            comm._barrier.abort()
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(n_shards)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return merge_results(parts, vt, len(batches))

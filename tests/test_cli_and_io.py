@@ -149,3 +149,14 @@ def test_native_reader_equals_python_readers(tmp_path):
                 for k in ("contig_rec_off", "pos", "tlen", "aln_score", "frag", "cigar_off", "cigar", "seq_off", "seq", "qual"):
                     assert np.array_equal(getattr(ref_batch, k), getattr(b, k)), (path, k)
                 assert fd.names == ref_batch.qnames
+
+
+def test_cli_empty_bam_is_the_reference_fatal_error(hostsim, tmp_path, capsys):
+    c = G.load_case("rna_small")
+    empty = str(tmp_path / "empty.bam")
+    open(empty, "w").writelines(l for l in open(c["sams"][0]) if l[0] == "@")
+    base = ["--vcf", c["vcf"], "--sample", "S1", "--mapq", "255", "--baseq", "10", "--paired_end", "1", "--o", str(tmp_path / "x")]
+    with pytest.raises(SystemExit) as e:
+        cli.run(cli.build_parser().parse_args(base + ["--bam", empty]), engine=hostsim)
+    assert e.value.code == 1 and "No reads could be matched to variants" in capsys.readouterr().out
+    cli.run(cli.build_parser().parse_args(base + ["--bam", empty + "," + c["sams"][0]]), engine=hostsim)   # an empty BAM beside a real one

@@ -129,3 +129,26 @@ def test_wgs_plus_rna_joint_matches_oracle(gpu, tmp_path):
     bad = compare.diff_outputs(exp, got)
     assert not bad, "\n".join(bad)
     assert res.counters["n_tuples"] == ores.total_tuples > 3000
+
+
+def test_output_does_not_depend_on_the_sharding_gpu(gpu, tmp_path):
+    """Shard-merge invariance at a size the oracle cannot reach: 1 shard vs 4 logical shards (4 contexts on this
+    GPU, threads, exact reductions in between) over 24 contigs -> identical result arrays after the merge."""
+    from phaser_b200 import synth, pipeline, shard, engine as eng
+    g = synth.make_genome(91, 60000, exonic_frac=0.4, n_genes=5000)
+    vt = synth.to_variant_table_arrays(g)
+    batches = []
+    nfrag = 0
+    for b in range(2):
+        rb = synth.to_read_batch(synth.make_reads(g, 9100 + b, 300000), len(vt.contigs), "b%d" % b)
+        rb.frag = (rb.frag + nfrag).astype(np.uint32); nfrag += len(rb.qnames)
+        batches.append(rb)
+    P = pipeline.PhaseParams()
+    one = pipeline.run_path(gpu, vt, [gpu.upload_reads(b) for b in batches], P, n_fragments=nfrag)
+    many = shard.run_logical_shards(lambda: eng.Engine(device="cuda:0"), vt, batches, P, nfrag, 4)
+    merged_one = shard.merge_results([(one, np.arange(vt.n_variants, dtype=np.int64), list(range(len(vt.contigs))))], vt, 2)
+    for k in ("ncls", "setsize", "vb_cnt", "v_final", "v_hap", "members", "fb_first", "fb_len", "fb_sup", "fb_tot", "fb_cnt",
+              "fb_bcnt", "rl_row", "rl_var", "rl_frag"):
+        assert np.array_equal(merged_one.arrays[k], many.arrays[k]), k
+    assert np.array_equal(np.argsort(merged_one.vfirst, kind="stable"), np.argsort(many.vfirst, kind="stable"))
+    assert many.counters["final_blocks"] == one.counters["final_blocks"] > 500

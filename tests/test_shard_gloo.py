@@ -30,3 +30,33 @@ def test_two_rank_sharded_run_matches_reference(case):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
     assert "SHARDED PARITY OK" in outs[0]
+
+
+def _result_files(res, vt, sams, P, vcf, col):
+    import gzip
+    from phaser_b200 import writer
+    from tests import util
+    o = writer.Outputs(res, vt, util.bam_display_names(sams), P)
+    got = dict(allelic_counts=o.allelic_counts(), variant_connections=o.variant_connections())
+    got["haplotypes"], got["haplotypic_counts"], got["allele_config"] = o.block_tables()
+    with gzip.open(vcf, "rt") as f:
+        got["vcf"], _, _ = o.vcf_text(f.readlines(), col)
+    return got
+
+
+def test_output_does_not_depend_on_the_sharding(tmp_path):
+    """1 shard vs 3 logical shards (threads, one host-simulation engine each) over 4 contigs and 2 BAMs:
+    identical files after the merge."""
+    from oracle import compare
+    from phaser_b200 import pipeline
+    from tests import util
+    contigs = [("19", 120000), ("20", 90000), ("21", 70000), ("22", 50000)]
+    vcf, sams = util.make_case(tmp_path, 81, 300, 2500, n_bams=2, contigs=contigs, switch_per_base=0.01)
+    vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+    P = pipeline.PhaseParams()
+    e = util.hostsim_engine()
+    one = pipeline.run_path(e, vt, [e.upload_reads(b) for b in batches], P, n_fragments=len(fd.names))
+    many = shard.run_logical_shards(util.hostsim_engine, vt, batches, P, len(fd.names), 3)
+    a = _result_files(one, vt, sams, P, vcf, col); b = _result_files(many, vt, sams, P, vcf, col)
+    assert not compare.diff_outputs(a, b)
+    assert a["haplotypic_counts"] == b["haplotypic_counts"] and a["vcf"] == b["vcf"]
