@@ -223,6 +223,37 @@ def blacklist_cases():
     json.dump(m, open(os.path.join(CASES, "opt_blacklists", "case.json"), "w"), indent=1)
 
 
+def config1_inputs(tmp):
+    """BASELINE.json configs[0] shape: one contig (chr22 length), ~10k het SNVs, 300k read pairs.  The inputs are
+    NOT stored (180 MB of SAM text): they are regenerated from the seed (torch CPU generator) and checked by hash."""
+    import hashlib
+    from phaser_b200 import engine as eng
+    g = synth.make_genome(1000, 10000, contigs=[("22", 50818468)], n_genes=1250)
+    vcf = synth.write_vcf(g, os.path.join(tmp, "c1.vcf.gz"))
+    rec = synth.make_reads(g, 100000, 300000, dup_frac=0.05)
+    sam = eng.write_sam_native(rec, g.contigs, os.path.join(tmp, "c1.bam"), "c1")     # host-only entry point of _phz.so
+    h = hashlib.sha256()
+    h.update(gzip.open(vcf, "rb").read()); h.update(open(sam, "rb").read())
+    return vcf, sam, h.hexdigest()
+
+
+def config1_case():
+    tmp = tempfile.mkdtemp()
+    vcf, sam, digest = config1_inputs(tmp)
+    r = rr.run_reference(vcf, [sam], os.path.join(tmp, "ref"), "S1", hashseed=0)
+    if r["returncode"] != 0:
+        raise RuntimeError(r["log"][-2000:])
+    d = os.path.join(HERE, "config1")
+    os.makedirs(d, exist_ok=True)
+    for suf in rr.OUTPUT_SUFFIXES:
+        with gzip.open(os.path.join(d, "ref." + suf.replace(".gz", "") + ".gz"), "wt") as f:
+            f.write(rr.read_text(r[suf]))
+    json.dump({"sha256_inputs": digest, "note": "reference outputs for the seeded configs[0]-shape sample; inputs regenerated by "
+               "make_golden.config1_inputs"}, open(os.path.join(d, "case.json"), "w"), indent=1)
+    shutil.rmtree(tmp)
+    print("golden config1 ok", digest[:12])
+
+
 def main():
     os.makedirs(CASES, exist_ok=True)
     v, s = quirk_case()
@@ -238,6 +269,7 @@ def main():
                 paired_end="0")
     option_case("opt_quirks_baseq", "quirks", ["--as_q_cutoff", "0", "--max_block_size", "3"], mapq="0")
     blacklist_cases()
+    config1_case()
 
 
 if __name__ == "__main__":

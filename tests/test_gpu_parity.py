@@ -152,3 +152,23 @@ def test_output_does_not_depend_on_the_sharding_gpu(gpu, tmp_path):
         assert np.array_equal(merged_one.arrays[k], many.arrays[k]), k
     assert np.array_equal(np.argsort(merged_one.vfirst, kind="stable"), np.argsort(many.vfirst, kind="stable"))
     assert many.counters["final_blocks"] == one.counters["final_blocks"] > 500
+
+
+def test_config1_shape_matches_reference_outputs(gpu, tmp_path):
+    """BASELINE.json configs[0] shape (chr22, ~10k het SNVs, 300k read pairs = 600k SAM records) against the
+    outputs of the UNMODIFIED reference (tests/golden/config1, made by tests/golden/make_golden.py).  The inputs
+    are regenerated from the seed and checked by hash; ~80 blocks go through the exhaustive phase_v3 path."""
+    import gzip, json, os, sys
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, here)
+    import make_golden
+    meta = json.load(open(os.path.join(here, "config1", "case.json")))
+    vcf, sam, digest = make_golden.config1_inputs(str(tmp_path))
+    if digest != meta["sha256_inputs"]:
+        pytest.skip("seeded generator produced different inputs on this box (torch CPU generator drift)")
+    ref = {k: gzip.open(os.path.join(here, "config1", "ref." + k + (".txt.gz" if k != "vcf" else ".gz")), "rt").read()
+           for k in ("allelic_counts", "allele_config", "haplotypes", "haplotypic_counts", "variant_connections", "vcf")}
+    got, res, _ = util.product_outputs(gpu, vcf, [sam])
+    bad = compare.diff_outputs(ref, got)
+    assert not bad, "\n".join(bad)
+    assert res.counters["hard_blocks"] > 20
