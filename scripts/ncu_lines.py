@@ -4,11 +4,12 @@ usage: ncu_lines.py report.ncu-rep <kernel substring> [top]"""
 import collections, csv, os, re, subprocess, sys, tempfile
 rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+sect = sys.argv[4] if len(sys.argv) > 4 else kern      # mangled-name substring selecting ONE instantiation in the cubin
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
 subprocess.run("cd %s && cuobjdump -xelf all %s/phaser_b200/_phz.so >/dev/null 2>&1 && nvdisasm --print-line-info *.cubin > all.sass" % (tmp, ROOT), shell=True, check=True)
 lines = open(os.path.join(tmp, "all.sass")).read().split("\n")
-start = next(i for i, l in enumerate(lines) if ".section" in l and ".text." in l and kern in l)
+start = next(i for i, l in enumerate(lines) if ".section" in l and ".text." in l and sect in l)
 end = next(i for i in range(start + 1, len(lines)) if ".section" in lines[i])
 cur = None; a2l = {}
 for l in lines[start + 1:end]:

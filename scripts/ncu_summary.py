@@ -33,7 +33,7 @@ rep = os.path.join(G, "k1_tile_full.ncu-rep")
 if not os.path.exists(rep):
     rep = os.path.join(G, "k1_tile.ncu-rep")
 if os.path.exists(rep):
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_lines.py"), rep, "k1_tile_kernel", "30"],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_lines.py"), rep, "k1_tile_kernel", "30", "k1_tile_kernelILi8"],
                          capture_output=True, text=True).stdout
     with open(os.path.join(P, "%s_k1_tile_ncu_summary.txt" % tag), "w") as f:
         f.write("# ncu --set full --clock-control none --import-source on -k regex:k1_tile (report: %s)\n" % os.path.basename(rep))
