@@ -82,11 +82,15 @@ int phz_as_histogram(phz_ctx* ctx, uint64_t* d_hist);
  * (phaser.py:1287-1328, 558-581).  d_frag: the BAM's fragment-id array (NULL after phz_map_reads_host). */
 int phz_commit_bam(phz_ctx* ctx, int bam_index, int32_t as_cutoff, const uint32_t* d_frag, int64_t* n_kept);
 
-/* Per-variant read lists/sets, noise sums (phaser.py:610-632), generate_connectivity_map
- * (phaser.py:1265-1285), pair enumeration (:667-678) and the count part of test_variant_connection
- * (:1594-1642).  h_noise[2] receives (base_match_count, base_mismatch_count). */
-int phz_build_graph(phz_ctx* ctx, uint64_t n_fragments, uint64_t bam_exclude_mask, uint64_t* h_noise,
-                    int64_t* n_edges, uint32_t* max_c_total);
+/* Per-variant read lists and the noise sums (phaser.py:610-632): h_noise[2] receives
+ * (base_match_count, base_mismatch_count).  Separate from phz_build_graph so that the host can compute the
+ * critical values (which need only the noise level) while the graph is being built. */
+int phz_variant_stats(phz_ctx* ctx, uint64_t* h_noise);
+
+/* Unique read sets, generate_connectivity_map (phaser.py:1265-1285), pair enumeration (:667-678) and the
+ * count part of test_variant_connection (:1594-1642). */
+int phz_build_graph(phz_ctx* ctx, uint64_t n_fragments, uint64_t bam_exclude_mask, int64_t* n_edges,
+                    uint32_t* max_c_total);
 
 /* Edge drop (phaser.py:696-707) through the integer critical values h_kstar[c_total] computed on the
  * host with scipy (so the binomial test of phaser.py:1649 agrees bit for bit), build_haplotypes

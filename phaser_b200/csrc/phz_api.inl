@@ -108,11 +108,17 @@ int phz_commit_bam(phz_ctx* ctx, int bam_index, int32_t as_cutoff, const uint32_
   PHZ_CATCH
 }
 
-int phz_build_graph(phz_ctx* ctx, uint64_t n_fragments, uint64_t excl, uint64_t* h_noise, int64_t* n_edges, uint32_t* max_c_total) {
+int phz_variant_stats(phz_ctx* ctx, uint64_t* h_noise) {
   PHZ_TRY
   u64 nz[2] = {0, 0};
-  ctx->p.build_graph(n_fragments, excl, nz);
+  ctx->p.variant_stats(nz);
   h_noise[0] = nz[0]; h_noise[1] = nz[1];
+  PHZ_CATCH
+}
+
+int phz_build_graph(phz_ctx* ctx, uint64_t n_fragments, uint64_t excl, int64_t* n_edges, uint32_t* max_c_total) {
+  PHZ_TRY
+  ctx->p.build_graph(n_fragments, excl);
   *n_edges = ctx->p.E; *max_c_total = ctx->p.max_tot;
   PHZ_CATCH
 }

@@ -412,6 +412,7 @@ __global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView
 template <class B>
 struct Pipeline {
   B be;
+  bool stats_done = false;
   int k1_min_ctas = 8;        // register budget of the tile kernel: 8 -> 32 regs, 6 -> 40 regs, else unconstrained
   int k1_mode = 3;            // 3: tile kernel + permute (default), 2: fused look-back, 1: windowed two-pass, 0: generic two-pass
   Buf<B, u32> s_rec, s_var, s_misc, tile_base, tile_cnt, tile_canon;
@@ -736,9 +737,12 @@ struct Pipeline {
 
   // =================================================================== graph
   // n_frag: number of fragment ids (max id + 1).  excl_mask: bit b set = BAM b excluded from haplotypic counts.
-  void build_graph(u64 n_frag, u64 excl_mask, u64* noise_out /*host [2]: match, mismatch*/) {
-    const int64_t n = n_tuples; const int64_t Vn = V; const int nb = n_bams > 0 ? n_bams : 1;
-    const u32* gf = g_frag.p; const u32* gv = g_var.p; const u8* gc = g_cb.p; const u32* vc = vcontig.p;
+  // Per-variant lists and the two noise sums (phaser.py:610-632).  Split from build_graph so that the host
+  // can start on the critical-value table (which only needs the noise level) while the graph is being built.
+  void variant_stats(u64* noise_out /*host [2]: match, mismatch*/) {
+    const int64_t n = n_tuples; const int64_t Vn = V;
+    const u32* gv = g_var.p; const u8* gc = g_cb.p; const u32* vc = vcontig.p;
+    stats_done = true;
     be.stage("graph.variant_lists");
     // ---- per-variant lists: first-seen rank (phaser.py:1310), list lengths with duplicates (Q17)
     u32* vf = vfirst.ensure(Vn); be.memset_ff(vf, Vn * sizeof(u32));
@@ -774,7 +778,6 @@ struct Pipeline {
         atomic_add((unsigned long long*)&nz[1], (unsigned long long)mis);
       }
     });
-    be.d2h(noise_out, nz, 2 * sizeof(u64));
     {   // contig order of first appearance (read_vars key order, phaser.py:573-574)
       u32* cr = crank.ensure(nc + 1); int ncg = nc;
       be.for_each(nc, PHZ_LAMBDA(int64_t c) {
@@ -783,6 +786,15 @@ struct Pipeline {
         cr[c] = r;
       });
     }
+    be.d2h(noise_out, nz, 2 * sizeof(u64));
+    be.stage("graph.variant_lists.end");
+  }
+
+  void build_graph(u64 n_frag, u64 excl_mask) {
+    if (!stats_done) { u64 tmp[2]; variant_stats(tmp); }
+    stats_done = false;
+    const int64_t n = n_tuples; const int64_t Vn = V; const int nb = n_bams > 0 ? n_bams : 1;
+    const u32* gf = g_frag.p; const u32* gv = g_var.p; const u8* gc = g_cb.p; const u32* vc = vcontig.p;
     be.stage("graph.sort_tuples");
     // ---- (fragment, variant, bam) entries: sort tuples by (fragment, variant); t ascending inside
     const int fb = ceil_log2_host(n_frag > 1 ? n_frag : 2); const int vb = vbits;

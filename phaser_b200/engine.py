@@ -32,7 +32,7 @@ class phz_reads(ctypes.Structure):
 
 
 EXPORTS = ["phz_last_error", "phz_backend_name", "phz_create", "phz_destroy", "phz_sync", "phz_set_variants",
-           "phz_map_reads", "phz_map_reads_host", "phz_as_histogram", "phz_commit_bam", "phz_build_graph",
+           "phz_map_reads", "phz_map_reads_host", "phz_as_histogram", "phz_commit_bam", "phz_variant_stats", "phz_build_graph",
            "phz_phase", "phz_read_lists", "phz_array", "phz_download", "phz_counters", "phz_launch_counts",
            "phz_set_profiling", "phz_map_times", "phz_stage_report", "phz_set_option",
            "phz_fragdict_create", "phz_fragdict_destroy", "phz_fragdict_size", "phz_fragdict_name", "phz_read_alignments",
@@ -51,7 +51,8 @@ def _declare(lib):
     lib.phz_map_reads_host.argtypes = [c_void_p, POINTER(phz_reads), c_int, c_double, POINTER(c_int64)]
     lib.phz_as_histogram.argtypes = [c_void_p, c_void_p]
     lib.phz_commit_bam.argtypes = [c_void_p, c_int, c_int32, c_void_p, POINTER(c_int64)]
-    lib.phz_build_graph.argtypes = [c_void_p, c_uint64, c_uint64, POINTER(c_uint64), POINTER(c_int64), POINTER(c_uint32)]
+    lib.phz_variant_stats.argtypes = [c_void_p, POINTER(c_uint64)]
+    lib.phz_build_graph.argtypes = [c_void_p, c_uint64, c_uint64, POINTER(c_int64), POINTER(c_uint32)]
     lib.phz_phase.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_uint64, POINTER(c_int64), POINTER(c_int)]
     lib.phz_read_lists.argtypes = [c_void_p, c_uint64, POINTER(c_int64)]
     lib.phz_array.argtypes = [c_void_p, c_char_p, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int)]
@@ -294,10 +295,15 @@ class Engine:
                                             frag, byref(n)))
         return n.value
 
+    def variant_stats(self):
+        noise = (c_uint64 * 2)()
+        self._check(self.lib.phz_variant_stats(self.ctx, noise))
+        return int(noise[0]), int(noise[1])
+
     def build_graph(self, n_fragments, exclude_mask=0):
-        noise = (c_uint64 * 2)(); e = c_int64(0); mt = c_uint32(0)
-        self._check(self.lib.phz_build_graph(self.ctx, int(n_fragments), int(exclude_mask), noise, byref(e), byref(mt)))
-        return int(noise[0]), int(noise[1]), e.value, mt.value
+        e = c_int64(0); mt = c_uint32(0)
+        self._check(self.lib.phz_build_graph(self.ctx, int(n_fragments), int(exclude_mask), byref(e), byref(mt)))
+        return e.value, mt.value
 
     def phase(self, kstar: np.ndarray, max_block_size, exclude_mask=0):
         k = np.ascontiguousarray(kstar, np.uint32)

@@ -10,6 +10,7 @@ Multi-GPU: contigs are sharded over ranks (shard.py); `comm` carries the three e
 (histogram, noise sums, max c_total).  Everything else is rank-local.
 """
 import math
+import threading
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -35,6 +36,9 @@ class PhaseParams:
         for b in self.haplo_count_bam_exclude:
             m |= 1 << b
         return m
+
+
+PRECOMPUTED_TOTALS = 2048      # c_total values whose critical value is computed while the graph is being built
 
 
 class NullComm:
@@ -194,15 +198,29 @@ def run_path(engine: Engine, vt: VariantTable, batches, params: PhaseParams, n_f
                                   "(the reference fails on int('') at phaser.py:1304); use --as_q_cutoff 0" % n_missing)
         cutoffs.append(cutoff)
         kept.append(engine.commit_bam(b, None if cutoff is None else int(math.ceil(cutoff))))
-    match, mism, n_edges, max_tot = engine.build_graph(n_fragments, excl)
+    match, mism = engine.variant_stats()
     match, mism = comm.allreduce_sum_ints([match, mism])
     if match == 0:
         raise PhaserFatal("No reads could be matched to variants. Please double check your settings and input files. "
                           "Common reasons for this occurring include: 1) MAPQ or BASEQ set too conservatively 2) BAM "
                           "and VCF have different chromosome names (IE 'chr1' vs '1').")
     noise_e = noise_level(match, mism)
-    totals = engine.download("ed_tot") if n_edges > 0 else np.zeros(0, np.uint32)
-    kstar = critical_values(int(max_tot), noise_e, params.cc_threshold, totals=totals)
+    # the critical values of the small totals (the bulk of the edges) are computed on a host thread while the
+    # GPU builds the graph; both scipy's ufuncs and the C call release the GIL
+    pre = {}
+    worker = threading.Thread(target=lambda: pre.setdefault("k", critical_values(PRECOMPUTED_TOTALS, noise_e, params.cc_threshold)))
+    worker.start()
+    try:
+        n_edges, max_tot = engine.build_graph(n_fragments, excl)
+    finally:
+        worker.join()
+    kstar = np.zeros(int(max_tot) + 1, np.uint32)
+    m = min(int(max_tot), PRECOMPUTED_TOTALS)
+    kstar[:m + 1] = pre["k"][:m + 1]
+    if max_tot > PRECOMPUTED_TOTALS and n_edges > 0:
+        totals = engine.download("ed_tot")
+        big = totals[totals > PRECOMPUTED_TOTALS]
+        kstar = np.maximum(kstar, critical_values(int(max_tot), noise_e, params.cc_threshold, totals=big))
     nf, flags = engine.phase(kstar, params.max_block_size, excl)
     if flags & 2:
         raise PhaserFatal("a haplotype block cannot be split down to --max_block_size (the reference does not "
