@@ -10,7 +10,10 @@ Multi-GPU: contigs are sharded over ranks (shard.py); `comm` carries the three e
 (histogram, noise sums, max c_total).  Everything else is rank-local.
 """
 import math
+import os
+import sys
 import threading
+import time
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -38,6 +41,7 @@ class PhaseParams:
         return m
 
 
+_TRACE = bool(os.environ.get("PHZ_TRACE"))
 PRECOMPUTED_TOTALS = 2048      # c_total values whose critical value is computed while the graph is being built
 
 
@@ -210,10 +214,13 @@ def run_path(engine: Engine, vt: VariantTable, batches, params: PhaseParams, n_f
     pre = {}
     worker = threading.Thread(target=lambda: pre.setdefault("k", critical_values(PRECOMPUTED_TOTALS, noise_e, params.cc_threshold)))
     worker.start()
+    _t = time.perf_counter() if _TRACE else 0.0
     try:
         n_edges, max_tot = engine.build_graph(n_fragments, excl)
     finally:
+        _t1 = time.perf_counter() if _TRACE else 0.0
         worker.join()
+    _t2 = time.perf_counter() if _TRACE else 0.0
     kstar = np.zeros(int(max_tot) + 1, np.uint32)
     m = min(int(max_tot), PRECOMPUTED_TOTALS)
     kstar[:m + 1] = pre["k"][:m + 1]
@@ -221,6 +228,10 @@ def run_path(engine: Engine, vt: VariantTable, batches, params: PhaseParams, n_f
         totals = engine.download("ed_tot")
         big = totals[totals > PRECOMPUTED_TOTALS]
         kstar = np.maximum(kstar, critical_values(int(max_tot), noise_e, params.cc_threshold, totals=big))
+    if _TRACE:
+        _t3 = time.perf_counter()
+        print("[run_path] build_graph %.2f ms, join wait %.2f ms, kstar assembly %.2f ms (max_tot %d)" % (
+            (_t1 - _t) * 1e3, (_t2 - _t1) * 1e3, (_t3 - _t2) * 1e3, max_tot), file=sys.stderr)
     nf, flags = engine.phase(kstar, params.max_block_size, excl)
     if flags & 2:
         raise PhaserFatal("a haplotype block cannot be split down to --max_block_size (the reference does not "
