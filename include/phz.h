@@ -60,6 +60,13 @@ int phz_sync(phz_ctx* ctx);
 int phz_set_variants(phz_ctx* ctx, int n_contigs, const int64_t* h_contig_var_off, const int32_t* d_pos,
                      const uint8_t* d_a0, const uint8_t* d_a1, int64_t n_variants);
 
+/* Optional, after phz_set_variants: --include_indels 1 (phaser.py:1398-1408).  Sites whose REF is longer than one
+ * base or whose alleles are multi-base strings carry a0 = a1 = 0xFE in phz_set_variants and are resolved by
+ * identify_allele's general rule (read_variant_map.py:236-258) against these tables: d_ref_len[V] = len(REF);
+ * the two allele strings of site j are d_al_codes[d_al_off[2j] .. d_al_off[2j+1]) and [d_al_off[2j+1] ..
+ * d_al_off[2j+2]), one 4-bit base code per character (0xFF = matches no read base).  NULL clears. */
+int phz_set_indel_alleles(phz_ctx* ctx, const int32_t* d_ref_len, const uint32_t* d_al_off, const uint8_t* d_al_codes);
+
 /* Optional, after phz_set_variants: one byte per het site, 1 = the site lies in a --haplo_count_blacklist
  * interval and is left out of the per-BAM haplotypic counts and read lists (phaser.py:1070, 1189).  NULL clears. */
 int phz_set_haplo_blacklist(phz_ctx* ctx, const uint8_t* d_flags);

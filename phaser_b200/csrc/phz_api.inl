@@ -61,6 +61,13 @@ int phz_set_variants(phz_ctx* ctx, int n_contigs, const int64_t* h_off, const in
   PHZ_TRY ctx->p.set_variants(n_contigs, h_off, d_pos, d_a0, d_a1, n_variants); PHZ_CATCH
 }
 
+int phz_set_indel_alleles(phz_ctx* ctx, const int32_t* d_ref_len, const uint32_t* d_al_off, const uint8_t* d_al_codes) {
+  PHZ_TRY
+  if (d_ref_len && (!d_al_off || !d_al_codes)) throw PhzError("phz_set_indel_alleles: all three tables are needed");
+  ctx->p.v_ref_len = d_ref_len; ctx->p.v_al_off = d_ref_len ? d_al_off : nullptr; ctx->p.v_al_codes = d_ref_len ? d_al_codes : nullptr;
+  PHZ_CATCH
+}
+
 int phz_set_haplo_blacklist(phz_ctx* ctx, const uint8_t* d_flags) { PHZ_TRY ctx->p.vblack = d_flags; PHZ_CATCH }
 
 static ReadsView view_of(const phz_reads* r, int nc) {

@@ -64,7 +64,18 @@ struct VariantsView {
   const int32_t* pos;
   const u8* a0;
   const u8* a1;
+  static constexpr bool kIndels = false;
 };
+
+// --include_indels 1 (phaser.py:1398-1408): sites whose REF is longer than one base or whose alleles are
+// multi-base strings carry a0 == ALLELE_MULTI and are resolved against these side tables.
+struct VariantsViewIndels : VariantsView {
+  const int32_t* ref_len;          // [V] len(REF) (read_variant_map.py:130, 240)
+  const u32* al_off;               // [2V+1] allele strings of site j: [al_off[2j], al_off[2j+1]) and [al_off[2j+1], al_off[2j+2])
+  const u8* al_codes;              // 4-bit base code per character, 0xFF = a character no read base can equal
+  static constexpr bool kIndels = true;
+};
+constexpr u8 ALLELE_MULTI = 0xFE;
 
 enum { CLS_A0 = 0, CLS_A1 = 1, CLS_OTHER = 2, CLS_NONE = 3 };
 enum { OP_M = 0, OP_I = 1, OP_D = 2, OP_N = 3, OP_S = 4, OP_H = 5, OP_P = 6, OP_EQ = 7, OP_X = 8 };
@@ -152,13 +163,73 @@ struct WindowVP {
   }
 };
 
+// pseudo_read[st] of the segment made of CIGAR ops [kseg, kend) and the insertion whose key equals st
+// (read_variant_map.py:191-232).  base: 4-bit code, 16 = deletion placeholder, -1 = outside the segment.
+template <class RV>
+PHZ_HD void locate_in_segment(const RV& rv, u32 kseg, u32 kend, int32_t seg_start, int32_t q_start, u64 boff, int baseq,
+                              int32_t st, int& base, int32_t& ins_q, int32_t& ins_n) {
+  int32_t g = seg_start, q = q_start;
+  base = -1; ins_q = -1; ins_n = 0;
+  for (u32 x = kseg; x < kend; ++x) {
+    u32 c = rv.cigar_at(x); int op = c & 15; int32_t n = (int32_t)(c >> 4);
+    if (op == OP_M || op == OP_EQ || op == OP_X) {
+      int32_t sp = g - seg_start;
+      if (st >= sp && st < sp + n) base = masked_base(rv, boff, q + (st - sp), baseq);
+      g += n; q += n;
+    } else if (op == OP_D) {
+      int32_t sp = g - seg_start;
+      if (st >= sp && st < sp + n) base = 16;
+      g += n;
+    } else if (op == OP_I) {
+      if (g - 1 == st) { ins_q = q; ins_n = n; }         // whole-read key, segment-relative lookup (Q3)
+      q += n;
+    } else if (op == OP_S) {
+      q += n;
+    }
+  }
+}
+
+// identify_allele (read_variant_map.py:236-258) for a site with multi-base REF / alleles: the string is
+// pseudo_read[st : st+ref_len] with the inserted bases spliced in after their key offsets and every 'D'
+// removed; it is compared on the fly with the sample's two allele strings.  Returns the packed t_misc word.
+template <class RV>
+PHZ_HD u32 call_indel_site(const RV& rv, const VariantsViewIndels& vv, int64_t j, u32 kseg, u32 kend, int32_t seg_start,
+                           int32_t q_start, int32_t seg_len, u64 boff, int baseq, int32_t st, int seg, int as16) {
+  const int32_t L = vv.ref_len[j];
+  if ((int64_t)st + L > (int64_t)seg_len) return pack_misc(CLS_NONE, 0, 0, seg, as16);     // read_end > len(pseudo_read)
+  const u32 o0 = vv.al_off[2 * j], o1 = vv.al_off[2 * j + 1], o2 = vv.al_off[2 * j + 2];
+  const u32 len0 = o1 - o0, len1 = o2 - o1;
+  u32 n_chars = 0; int first = 0; bool eq0 = true, eq1 = true;
+  auto push = [&](int b) {
+    if (b == BASE_D) return;
+    if (n_chars == 0) first = b;
+    eq0 = eq0 && n_chars < len0 && vv.al_codes[o0 + n_chars] == (u8)b;
+    eq1 = eq1 && n_chars < len1 && vv.al_codes[o1 + n_chars] == (u8)b;
+    n_chars++;
+  };
+  for (int32_t x = st; x < st + L; ++x) {
+    int base; int32_t ins_q, ins_n;
+    locate_in_segment(rv, kseg, kend, seg_start, q_start, boff, baseq, x, base, ins_q, ins_n);
+    if (base >= 0 && base != 16) push(base);
+    for (int32_t z = 0; z < ins_n; ++z) push(masked_base(rv, boff, ins_q + z, baseq));
+  }
+  eq0 = eq0 && n_chars == len0; eq1 = eq1 && n_chars == len1;
+  int cls;
+  if (n_chars == 0) cls = CLS_NONE;
+  else if (n_chars == 1 && first == BASE_N) cls = CLS_NONE;
+  else if (eq0) cls = CLS_A0;
+  else if (eq1) cls = CLS_A1;
+  else cls = CLS_OTHER;
+  return pack_misc(cls, n_chars > 1 ? 1 : 0, first, seg, as16);
+}
+
 // Walks one record.
 // MODE 0 (count): returns the number of candidate (segment, variant) pairs.
 // MODE 1 (emit):  writes one tuple per candidate starting at out index `o` (class CLS_NONE when the
 //                 reference would print nothing) and returns the number written.
 // MODE 2 (k-th):  `o` is the ordinal of ONE candidate of this record; writes that tuple at out index 0.
-template <int MODE, class RV, class VP>
-PHZ_HD u32 map_record(const RV& rv, const VariantsView& vv, const VP& vp, int64_t r, int contig, int baseq,
+template <int MODE, class RV, class VP, class VV>
+PHZ_HD u32 map_record(const RV& rv, const VV& vv, const VP& vp, int64_t r, int contig, int baseq,
                       double isize_cutoff, u64 o, u32* t_rec, u32* t_var, u32* t_misc) {
   constexpr bool EMIT = MODE != 0;
   if (!isize_ok(rv.tlen_at(r), isize_cutoff)) return 0;
@@ -202,6 +273,16 @@ PHZ_HD u32 map_record(const RV& rv, const VariantsView& vv, const VP& vp, int64_
           if (MODE == 2) { lo += (int64_t)(o - n_out); hi = lo + 1; }
           for (int64_t j = lo; j < hi; ++j) {
             const int32_t st = (int32_t)((int64_t)vp.at(j) - lo_pos);       // offset in pseudo_read
+            if constexpr (VV::kIndels) {
+              if (vv.a0[j] == ALLELE_MULTI) {
+                const u64 w = (MODE == 2) ? 0 : o + n_out;
+                t_rec[w] = (u32)r;
+                t_var[w] = (u32)j;
+                t_misc[w] = call_indel_site(rv, vv, j, kseg, kend, seg_start, q_start, seg_len, boff, baseq, st, seg, as16);
+                n_out++;
+                continue;
+              }
+            }
             // locate pseudo_read[st] and the insertion keyed st (keys are whole-read offsets: Q3)
             int32_t g = seg_start, q = q_start;
             int base = -1;            // 16: deletion placeholder

@@ -294,8 +294,8 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, in
                ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
 }
 
-template <int MIN_CTAS>
-__global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView rv, VariantsView vv, const TileInfo* __restrict__ tiles,
+template <int MIN_CTAS, class VV>
+__global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView rv, VV vv, const TileInfo* __restrict__ tiles,
                                                             int baseq, double isize_cutoff, u32* __restrict__ s_rec,
                                                             u32* __restrict__ s_var, u32* __restrict__ s_misc, u64 capacity,
                                                             unsigned long long* cursor, u32* __restrict__ tile_base,
@@ -422,6 +422,7 @@ struct Pipeline {
   std::vector<int64_t> h_cvoff;
   Buf<B, int64_t> d_cvoff, d_croff;
   const int32_t* vpos = nullptr; const u8* va0 = nullptr; const u8* va1 = nullptr;
+  const int32_t* v_ref_len = nullptr; const u32* v_al_off = nullptr; const u8* v_al_codes = nullptr;   // --include_indels side tables
   const u8* vblack = nullptr;      // per het site: 1 = left out of the haplotypic counts (phaser.py:1070)
   Buf<B, u32> vcontig;
   // ------------------------------------------------------------------ K1 candidates of the current BAM
@@ -499,6 +500,7 @@ struct Pipeline {
     h_cvoff.assign(contig_var_off_host, contig_var_off_host + nc + 1);
     be.h2d(d_cvoff.ensure(nc + 1), h_cvoff.data(), (nc + 1) * sizeof(int64_t));
     vpos = d_pos; va0 = d_a0; va1 = d_a1; vblack = nullptr;
+    v_ref_len = nullptr; v_al_off = nullptr; v_al_codes = nullptr;
     u32* vc = vcontig.ensure(V);
     const int64_t* off = d_cvoff.p; int n = nc;
     be.for_each(V, PHZ_LAMBDA(int64_t v) { vc[v] = (u32)upper_slot_i64(off, n, v); });
@@ -514,6 +516,11 @@ struct Pipeline {
     VariantsView vv{V, nc, d_cvoff.p, vpos, va0, va1};
     const int64_t R = rv.n_records;
     if (R >= (int64_t)0x7FFFFFFF) throw PhzError("more than 2^31-1 records in one map_reads call; split the BAM");
+    if (v_ref_len) {                    // sites with multi-base alleles: tile kernel, indel instantiation
+      VariantsViewIndels vi; static_cast<VariantsView&>(vi) = vv;
+      vi.ref_len = v_ref_len; vi.al_off = v_al_off; vi.al_codes = v_al_codes;
+      return map_reads_tiles(rv, vi, baseq, isize_cutoff);
+    }
     if (k1_mode == 3) return map_reads_tiles(rv, vv, baseq, isize_cutoff);
     if (k1_mode == 2) return map_reads_fused(rv, vv, baseq, isize_cutoff);
     u32* cnt = cand_cnt.ensure(R + 1);
@@ -532,7 +539,8 @@ struct Pipeline {
 
   // Tile kernel + permute (see k1_tile_kernel).  Scratch capacity is what the buffers already hold (or a
   // first guess); if the exact total turns out larger the buffers grow and the kernel runs once more.
-  int64_t map_reads_tiles(const ReadsView& rv, const VariantsView& vv, int baseq, double isize_cutoff) {
+  template <class VV>
+  int64_t map_reads_tiles(const ReadsView& rv, const VV& vv, int baseq, double isize_cutoff) {
     const int64_t R = rv.n_records;
     if (R <= 0) { n_cand = 0; be.mark(0); be.mark(1); be.mark(2); be.mark(3); return 0; }
     const int64_t n_tiles = (R + KF_THREADS - 1) / KF_THREADS;
@@ -549,12 +557,14 @@ struct Pipeline {
       total = 0;
 #ifdef __CUDACC__
       u64* cur = tile_status.ensure(2); be.memset0(cur, 2 * sizeof(u64));
-      if (k1_min_ctas >= 8)
-        k1_tile_kernel<8><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, sr, sv, sm, (u64)cap, cur, tb, tc);
+      if constexpr (VV::kIndels)      // the indel instantiation is not register-capped: its string walk would spill at 32 registers
+        k1_tile_kernel<1, VV><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, sr, sv, sm, (u64)cap, cur, tb, tc);
+      else if (k1_min_ctas >= 8)
+        k1_tile_kernel<8, VV><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, sr, sv, sm, (u64)cap, cur, tb, tc);
       else if (k1_min_ctas >= 6)
-        k1_tile_kernel<6><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, sr, sv, sm, (u64)cap, cur, tb, tc);
+        k1_tile_kernel<6, VV><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, sr, sv, sm, (u64)cap, cur, tb, tc);
       else
-        k1_tile_kernel<1><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, sr, sv, sm, (u64)cap, cur, tb, tc);
+        k1_tile_kernel<1, VV><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, sr, sv, sm, (u64)cap, cur, tb, tc);
       PHZ_CUDA(cudaGetLastError());
       be.launches++;
       be.d2h(&total, cur, sizeof(u64));

@@ -12,7 +12,7 @@ from ctypes import c_int, c_int32, c_int64, c_uint32, c_uint64, c_double, c_void
 import numpy as np
 import torch
 
-from .layout import ReadBatch, VariantTable
+from .layout import ReadBatch, VariantTable, indel_tables
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_phz.so")
@@ -36,7 +36,8 @@ EXPORTS = ["phz_last_error", "phz_backend_name", "phz_create", "phz_destroy", "p
            "phz_phase", "phz_read_lists", "phz_array", "phz_download", "phz_counters", "phz_launch_counts",
            "phz_set_profiling", "phz_map_times", "phz_stage_report", "phz_set_option",
            "phz_fragdict_create", "phz_fragdict_destroy", "phz_fragdict_size", "phz_fragdict_name", "phz_read_alignments",
-           "phz_host_reads_view", "phz_host_reads_free", "phz_set_haplo_blacklist", "phz_write_sam"]
+           "phz_host_reads_view", "phz_host_reads_free", "phz_set_haplo_blacklist", "phz_write_sam",
+           "phz_set_indel_alleles"]
 
 
 def _declare(lib):
@@ -74,6 +75,7 @@ def _declare(lib):
     lib.phz_host_reads_view.argtypes = [c_void_p, POINTER(phz_reads), POINTER(c_int)]
     lib.phz_host_reads_free.argtypes = [c_void_p]
     lib.phz_set_haplo_blacklist.argtypes = [c_void_p, c_void_p]
+    lib.phz_set_indel_alleles.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
     return lib
 
 
@@ -237,12 +239,17 @@ class Engine:
         if self._keep.get("vt_id") != id(vt):          # the table stays resident across calls
             self._keep["v"] = (_as_torch(vt.pos, d), _as_torch(vt.a0, d), _as_torch(vt.a1, d))
             self._keep["vt_id"] = id(vt); self._keep["vt"] = vt
+            it = indel_tables(vt)                       # --include_indels: multi-base sites
+            self._keep["indel"] = None if it is None else tuple(_as_torch(a, d) for a in it)
         off = np.ascontiguousarray(vt.contig_var_off, np.int64)
         self._keep["voff"] = off
         self.n_contigs = len(vt.contigs)
         p, a0, a1 = self._keep["v"]
         self._check(self.lib.phz_set_variants(self.ctx, self.n_contigs, off.ctypes.data, p.data_ptr(), a0.data_ptr(),
                                               a1.data_ptr(), vt.n_variants))
+        it = self._keep.get("indel")
+        if it is not None:
+            self._check(self.lib.phz_set_indel_alleles(self.ctx, it[0].data_ptr(), it[1].data_ptr(), it[2].data_ptr()))
         bl = getattr(vt, "haplo_blacklisted", None)
         if bl is not None and bl.any():
             self._keep["vblack"] = _as_torch(np.ascontiguousarray(bl, np.uint8), d)

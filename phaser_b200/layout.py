@@ -21,6 +21,7 @@ BASE_CODE = {c: i for i, c in enumerate(BASE_ALPHABET)}
 CODE_N = 15
 CODE_D = 13          # IUPAC 'D' -- the reference strips it like a deletion placeholder (read_variant_map.py:254)
 ALLELE_NONE = 0xFF   # an allele string that no single read base can equal
+ALLELE_MULTI = 0xFE  # --include_indels: multi-base REF or allele string, resolved through the indel side tables
 
 # CIGAR op codes as in BAM: MIDNSHP=X
 CIGAR_OPS = "MIDNSHP=X"
@@ -79,6 +80,36 @@ class VariantTable:
     @property
     def n_variants(self) -> int:
         return int(self.pos.shape[0])
+
+
+def is_indel_site(ref: str, sample_alleles) -> bool:
+    """A site the SNV fast path cannot call: REF spans several bases or one of the sample's alleles is a string."""
+    return len(ref) != 1 or any(len(a) != 1 for a in sample_alleles)
+
+
+def sample_alleles(all_alleles, gt: str):
+    """The alleles the sample carries, in allele-index order (phaser.py:1431-1435)."""
+    g = [ch for ch in gt if ch not in "|/"]
+    return [all_alleles[i] for i in range(len(all_alleles)) if str(i) in g]
+
+
+def indel_tables(vt: "VariantTable"):
+    """(ref_len i32[V], al_off u32[2V+1], al_codes u8[]) for phz_set_indel_alleles, or None when every site is a
+    plain SNV.  Strings are stored only for the sites flagged ALLELE_MULTI."""
+    if not bool(np.any(vt.a0 == ALLELE_MULTI)):
+        return None
+    V = vt.n_variants
+    off = np.zeros(2 * V + 1, np.uint32)
+    codes = []
+    for v in np.nonzero(vt.a0 == ALLELE_MULTI)[0].tolist():
+        ind = sample_alleles(vt.all_alleles[v], vt.gt[v])
+        off[2 * v + 1] = len(ind[0]); off[2 * v + 2] = len(ind[1])
+    lens = off[1:].copy()
+    off[1:] = np.cumsum(lens, dtype=np.uint64).astype(np.uint32)
+    for v in np.nonzero(vt.a0 == ALLELE_MULTI)[0].tolist():
+        for a in sample_alleles(vt.all_alleles[v], vt.gt[v]):
+            codes.extend(BASE_CODE.get(ch, ALLELE_NONE) for ch in a)
+    return (np.ascontiguousarray(vt.ref_len, np.int32), off, np.asarray(codes if codes else [0], np.uint8))
 
 
 def pack_nibbles(codes: np.ndarray) -> np.ndarray:

@@ -5,7 +5,7 @@ Same flags, file formats and fatal-error behaviour as the reference CLI (phaser/
 the work between "het sites loaded" and "files written" runs on the GPU through the C ABI
 (include/phz.h).  Differences a user can see:
   * no samtools / bgzip / tabix / bedtools / bcftools are needed (BAM or SAM text is read directly);
-  * not yet supported, rejected with a FATAL ERROR instead of being silently ignored: --include_indels 1,
+  * not yet supported, rejected with a FATAL ERROR instead of being silently ignored:
     --process_slow 1, --output_network, --output_read_ids 1 (SURVEY.md section 8f, "next" rows);
   * fields the reference prints in CPython-set order come out in a canonical order
     (SURVEY.md section 8c).
@@ -128,8 +128,7 @@ def run(args, engine=None):
     say("  B200-native read->variant->haplotype path (phaser_b200)")
     say("##################################################")
     say("")
-    for flag, bad, why in (("--include_indels 1", args.include_indels == 1, "multi-base alleles"),
-                           ("--process_slow 1", args.process_slow == 1, "per-contig mode changes results in the reference"),
+    for flag, bad, why in (("--process_slow 1", args.process_slow == 1, "per-contig mode changes results in the reference"),
                            ("--output_network", args.output_network != "", "debug dump"),
                            ("--output_read_ids 1", args.output_read_ids == 1, "read-id columns")):
         if bad:

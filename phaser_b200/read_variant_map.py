@@ -13,7 +13,7 @@ import sys
 
 import numpy as np
 
-from .layout import VariantTable, ReadBatch, BASE_ALPHABET, AS_MISSING, allele_code
+from .layout import VariantTable, ReadBatch, BASE_ALPHABET, AS_MISSING, allele_code, is_indel_site, ALLELE_MULTI
 from . import samio
 
 _ENGINE = None
@@ -54,9 +54,13 @@ def read_variant_table(path):
                 if sep in g:
                     g.remove(sep)
             ind = [alleles[i] for i in range(len(alleles)) if str(i) in g]
-            if int(c[5]) != 1 or max(len(x) for x in alleles) != 1 or len(ind) != 2:
-                raise NotImplementedError("only single-base variants of diploid het sites are supported (variant %s)" % c[2])
-            pos.append(int(c[1])); a0.append(allele_code(ind[0])); a1.append(allele_code(ind[1])); rl.append(1)
+            if len(ind) != 2:
+                raise NotImplementedError("only diploid het sites with two distinct alleles are supported (variant %s)" % c[2])
+            pos.append(int(c[1])); rl.append(int(c[5]))
+            if int(c[5]) != 1 or is_indel_site(alleles[0], ind):        # --include_indels 1 tables (phaser.py:1398-1404)
+                a0.append(ALLELE_MULTI); a1.append(ALLELE_MULTI)
+            else:
+                a0.append(allele_code(ind[0])); a1.append(allele_code(ind[1]))
             ids.append(c[2]); rs.append(c[3]); alls.append(alleles); gts.append(c[6]); mafs.append(c[7])
     off.append(len(pos))
     if not contigs:
@@ -65,8 +69,8 @@ def read_variant_table(path):
                         np.asarray(a1, np.uint8), np.asarray(rl, np.int32), ids, rs, alls, gts, mafs)
 
 
-def allele_string(batch: ReadBatch, r, seg_index, vpos, baseq):
-    """Text of a multi-base call (base + inserted bases, read_variant_map.py:245-258) for the TSV."""
+def allele_string(batch: ReadBatch, r, seg_index, vpos, baseq, ref_len=1):
+    """Text of a multi-base call (bases + inserted bases, read_variant_map.py:245-258) for the TSV."""
     lo = int(batch.seq_off[r])
     n_b = int(batch.seq_off[r + 1]) - lo
     codes = [(int(batch.seq[(lo + j) >> 1]) >> 4) if ((lo + j) & 1) == 0 else (int(batch.seq[(lo + j) >> 1]) & 15) for j in range(n_b)]
@@ -87,7 +91,7 @@ def allele_string(batch: ReadBatch, r, seg_index, vpos, baseq):
                 break
             g += n; seg += 1; seg_start = g; pseudo = []; ins = {}
     st = vpos - (int(batch.pos[r]) + seg_start)
-    s = pseudo[st] + ins.get(st, "")
+    s = "".join(pseudo[x] + ins.get(x, "") for x in range(st, st + ref_len))
     return s.replace("D", "")
 
 
@@ -107,7 +111,7 @@ def do_read_variant_map(variant_table, baseq, o, splice, isize_cutoff):
     with open(o, "w") as out:
         for r, v, m in zip(rec[keep].tolist(), var[keep].tolist(), misc[keep].tolist()):
             if (m >> 2) & 1:
-                allele = allele_string(batch, r, (m >> 8) & 0xFF, int(vt.pos[v]), int(baseq))
+                allele = allele_string(batch, r, (m >> 8) & 0xFF, int(vt.pos[v]), int(baseq), int(vt.ref_len[v]))
             else:
                 allele = BASE_ALPHABET[(m >> 4) & 15]
             a = np.int16(np.uint16(m >> 16))

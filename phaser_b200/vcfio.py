@@ -14,7 +14,7 @@ from typing import List, Optional
 
 import numpy as np
 
-from .layout import VariantTable, allele_code
+from .layout import VariantTable, allele_code, is_indel_site, ALLELE_MULTI
 
 
 class PhaserFatal(Exception):
@@ -90,8 +90,6 @@ def parse_vcf(path, sample_column: int, pass_only=1, chrom_of_interest="", chr_p
     bl = BedIntervals(blacklist) if blacklist else None
     hbl = BedIntervals(haplo_count_blacklist) if haplo_count_blacklist else None
     haplo_set = set()
-    if include_indels:
-        raise NotImplementedError("--include_indels 1 is not supported by the B200 mapper yet (multi-base alleles)")
     contig_ban = [id_separator, ":"]
     pool = OrderedDict()
     st = VcfStats()
@@ -155,13 +153,16 @@ def parse_vcf(path, sample_column: int, pass_only=1, chrom_of_interest="", chr_p
                         use = [int(a) - 1 for a in xgeno if a != "." and int(a) != 0]
                         if use:
                             maf = min(min(afs[x], 1 - afs[x]) for x in use)
-            if max(len(x) for x in all_alleles) == 1:
+            if max(len(x) for x in all_alleles) == 1 or include_indels == 1:        # phaser.py:1398-1400
                 ind = [all_alleles[i] for i in range(len(all_alleles)) if str(i) in xgeno]
                 if len(ind) != 2 or len(xgeno) != 2:
                     raise PhaserFatal("Variant %s:%s: only diploid genotypes with two distinct alleles are supported."
                                       % (chrom, cut[1]))
                 pos.append(int(cut[1]))
-                a0.append(allele_code(ind[0])); a1.append(allele_code(ind[1]))
+                if is_indel_site(cut[3], ind):
+                    a0.append(ALLELE_MULTI); a1.append(ALLELE_MULTI)
+                else:
+                    a0.append(allele_code(ind[0])); a1.append(allele_code(ind[1]))
                 rl.append(len(cut[3]))
                 ids.append(cname + id_separator + cut[1] + id_separator + id_separator.join(all_alleles))
                 rsids.append(cut[2]); alls.append(all_alleles); gts.append(geno_string); mafs.append(str(maf))

@@ -116,6 +116,180 @@ def quirk_case():
     return VCF_HEAD + "".join(V), SAM_HEAD + "".join(x[2] for x in S)
 
 
+def indel_case():
+    """--include_indels 1 (phaser.py:1398-1408, read_variant_map.py:236-258 with ref_length > 1): deletions, insertions,
+    an MNP, a multi-allelic indel site, reads carrying each allele through D / I CIGAR ops, a deletion that ends at a
+    segment edge, a site cut by a splice junction, low-quality and N bases inside a multi-base call."""
+    V = []
+    V.append(vline("1", 105, "rs1", "A", "G", "0|1"))               # plain SNVs around the indels
+    V.append(vline("1", 110, "del2", "CAG", "C", "0|1"))            # 2-base deletion
+    V.append(vline("1", 118, "ins3", "T", "TACG", "1|0"))           # 3-base insertion
+    V.append(vline("1", 125, "mnp", "AC", "GT", "0|1"))             # MNP: ref_len 2, no length change
+    V.append(vline("1", 131, "mai", "A", "AT,ATT", "1|2"))          # multi-allelic insertion, sample carries both ALTs
+    V.append(vline("1", 136, "rs6", "C", "T", "0/1"))
+    V.append(vline("1", 140, "del1", "GA", "G", "0|1"))
+    V.append(vline("1", 146, "cpx", "ATG", "AC", "1|0"))            # complex: ref 3 -> 2
+    V.append(vline("1", 160, "rs9", "T", "C", "0|1"))
+    V.append(vline("2", 58, "edge", "AAAA", "A", "0|1"))            # REF runs over the end of short reads / the first exon
+    V.append(vline("2", 300, "rs21", "C", "G", "0|1"))
+    V.append(vline("2", 305, "ins2", "A", "AGG", "0|1"))
+    S = []
+
+    def rd(name, flag, chrom, pos, cigar, seq, qual=None, **kw):
+        S.append((chrom, pos, sline(name, flag, chrom, pos, 255, cigar, seq, qual, **kw)))
+
+    def ref1(lo, n):                       # reference sequence of contig 1 around the sites (A everywhere else)
+        g = {105: "A", 110: "C", 111: "A", 112: "G", 118: "T", 125: "A", 126: "C", 131: "A", 136: "C", 140: "G", 141: "A",
+             146: "A", 147: "T", 148: "G", 160: "T"}
+        return "".join(g.get(p, "A") for p in range(lo, lo + n))
+
+    def edit(seq, lo, changes):
+        s = list(seq)
+        for p, b in changes.items():
+            s[p - lo] = b
+        return "".join(s)
+
+    # haplotype R: reference everywhere.  60 bases from 100
+    for i in range(4):
+        rd("refhap%d" % i, 99, "1", 100, "62M", ref1(100, 62))
+    # haplotype X: every non-reference allele: SNV G@105, del CAG>C (2D after 110), ins ACG after 118, MNP GT@125-126,
+    # ATT after 131 (allele index 2), T@136, del GA>G (1D after 140), ATG>AC: 146 A, 147 C, 148 deleted, C@160
+    def alt_read(name, flag, second_ins="TT", AS=140):
+        left = edit(ref1(100, 11), 100, {105: "G"})                       # 100..110
+        mid1 = ref1(113, 6)                                               # 113..118
+        mid2 = edit(ref1(119, 13), 119, {125: "G", 126: "T"})             # 119..131
+        mid3 = edit(ref1(132, 9), 132, {136: "T"})                        # 132..140
+        mid4 = edit(ref1(142, 6), 142, {147: "C"})                        # 142..147
+        tail = edit(ref1(149, 13), 149, {160: "C"})                       # 149..161
+        seq = left + mid1 + "ACG" + mid2 + second_ins + mid3 + mid4 + tail
+        cig = "11M2D6M3I13M%dI9M1D6M1D13M" % len(second_ins)
+        rd(name, flag, "1", 100, cig, seq, AS=AS)
+    for i in range(4):
+        alt_read("althap%d" % i, 99)
+    alt_read("althapT", 99, second_ins="T")                                # allele index 1 of the multi-allelic site
+    alt_read("althapTTT", 99, second_ins="TTT")                            # neither allele -> other
+    # partial / odd carriers
+    rd("mnp_half", 99, "1", 120, "20M", edit(ref1(120, 20), 120, {125: "G"}))                  # GC: matches neither -> other
+    rd("mnp_lowq", 99, "1", 120, "20M", edit(ref1(120, 20), 120, {125: "G", 126: "T"}), "FFFFF#FFFFFFFFFFFFFF")   # NT -> other
+    rd("del_n", 99, "1", 104, "20M", edit(ref1(104, 20), 104, {111: "N"}))                     # CNG -> other
+    rd("short_end", 99, "1", 100, "12M", ref1(100, 12))                                        # 110 + 3 > read end: nothing for del2
+    rd("short_exact", 99, "1", 100, "13M", ref1(100, 13))                                      # ends exactly at 112: CAG
+    rd("del_long", 99, "1", 100, "9M6D30M", ref1(100, 9) + ref1(115, 30))                      # deletion swallows the whole del2 REF -> ""
+    rd("del_partial", 99, "1", 100, "11M1D30M", ref1(100, 11) + ref1(112, 30))                 # CAG with A deleted -> CG -> other
+    rd("ins_wrong", 99, "1", 110, "9M2I20M", ref1(110, 9) + "GG" + ref1(119, 20))              # TGG -> other
+    rd("softclip", 99, "1", 108, "4S30M", "TTTT" + ref1(108, 30))
+    # contig 2: exon 1 = 45..60, intron, exon 2 = 291..320 ; "edge" REF AAAA at 58..61 crosses the junction
+    for i in range(3):
+        rd("sp%d" % i, 99, "2", 45, "16M230N30M", "A" * 16 + edit("A" * 30, 291, {300: "C"}))
+        rd("spalt%d" % i, 99, "2", 45, "16M230N15M2I15M", "A" * 16 + edit("A" * 15, 291, {300: "G"}) + "GG" + "A" * 15)
+    rd("edge_ok", 99, "2", 50, "20M", "A" * 20)                                                # AAAA inside one segment
+    rd("edge_del", 99, "2", 50, "9M3D20M", "A" * 29)                                           # A + 3 deleted -> "A" = alt
+    rd("q3ins", 99, "2", 45, "16M230N10M2I20M", "A" * 16 + "A" * 9 + "C" + "GG" + "A" * 20)    # Q3: insertion keyed whole-read offset
+    S.sort(key=lambda t: (t[0], t[1]))
+    return VCF_HEAD + "".join(V), SAM_HEAD + "".join(x[2] for x in S)
+
+
+def fuzz_indel_case(seed=77, n_sites=140, n_reads=900):
+    """Seeded random sites (REF / ALT strings of 1-4 bases, multi-allelic, overlapping REF spans) under reads drawn from a
+    random reference with random CIGARs mixing M = X I D N S H P; reads carry one haplotype's SNV alleles, pure
+    insertions / deletions are written into the CIGAR, and a few percent of the bases are errors, N or low quality:
+    every branch of split_read / identify_allele with ref_length >= 1."""
+    import random
+    rnd = random.Random(seed)
+    G = [rnd.choice("ACGT") for _ in range(2000)]           # G[p] = reference base at 1-based position p
+    V = []; sites = []
+    # distinct positions: two sites at one position inside a multi-site block are ordered by CPython's set iteration in
+    # the reference (SURVEY.md Q29), which no canonical order can reproduce; the quirks case keeps such a pair
+    pos = sorted(rnd.sample(range(100, 1600), n_sites))
+    for i, p in enumerate(pos):
+        rl = rnd.choice([1, 1, 1, 1, 2, 3, 4])
+        ref = "".join(G[p:p + rl])
+        alts = []
+        while len(alts) < rnd.choice([1, 1, 1, 1, 2]):
+            k = rnd.random()
+            if k < 0.5:
+                a = rnd.choice("ACGT") if rl == 1 else "".join(rnd.choice("ACGT") for _ in range(rl))
+            elif k < 0.75:
+                a = ref[0]                                                      # pure deletion (or a no-op for SNVs)
+            else:
+                a = ref + "".join(rnd.choice("ACGT") for _ in range(rnd.randrange(1, 4))) if rl == 1 else ref[0] + rnd.choice("ACGT")
+            if a != ref and a not in alts:
+                alts.append(a)
+        gt = rnd.choice(["0|1", "1|0", "0/1"]) if len(alts) == 1 else rnd.choice(["1|2", "0|2", "2|1", "0/1"])
+        idx = [int(c) for c in gt if c.isdigit()]
+        alls = [ref] + alts
+        V.append(vline("1", p, "rs%d" % i if rnd.random() < 0.9 else ".", ref, ",".join(alts), gt))
+        sites.append((p, rl, [alls[idx[0]], alls[idx[1]]], [rnd.randrange(2), ]))
+    by_pos = {}
+    for st in sites:
+        by_pos.setdefault(st[0], st)
+    S = []
+    for i in range(n_reads):
+        hap = rnd.randrange(2)
+        start = rnd.randrange(60, 1600)
+        ops = []; seq = []
+        if rnd.random() < 0.1:
+            ops.append((rnd.randrange(1, 5), "H"))
+        if rnd.random() < 0.15:
+            n = rnd.randrange(1, 6); ops.append((n, "S")); seq += [rnd.choice("ACGT") for _ in range(n)]
+        g = start
+        n_blocks = rnd.choice([1, 1, 2, 2, 3, 4])
+        for b in range(n_blocks):
+            n = rnd.randrange(8, 60)
+            kind = rnd.choice("MMMM=X")
+            x = g; run = 0
+            while x < g + n:
+                st = by_pos.get(x)
+                done = False
+                if st is not None and x + st[1] <= g + n and x > g:
+                    al = st[2][hap ^ st[3][0]]
+                    ref = "".join(G[x:x + st[1]])
+                    if len(al) == st[1]:                                         # SNV / MNP: substitute
+                        seq += list(al); run += st[1]; x += st[1]; done = True
+                    elif len(al) == 1 and al == ref[0] and st[1] > 1:            # deletion
+                        seq.append(al); run += 1
+                        ops.append((run, kind)); ops.append((st[1] - 1, "D")); run = 0
+                        x += st[1]; done = True
+                    elif st[1] == 1 and al.startswith(ref) and x + 1 < g + n:    # insertion
+                        seq.append(ref); run += 1
+                        ops.append((run, kind)); ops.append((len(al) - 1, "I")); seq += list(al[1:]); run = 0
+                        x += 1; done = True
+                if not done:
+                    seq.append(G[x]); run += 1; x += 1
+            if run:
+                ops.append((run, kind))
+            g += n
+            if b + 1 < n_blocks:
+                k = rnd.random()
+                if k < 0.15:
+                    m = rnd.randrange(1, 4); ops.append((m, "I")); seq += [rnd.choice("ACGT") for _ in range(m)]
+                elif k < 0.3:
+                    m = rnd.randrange(1, 6); ops.append((m, "D")); g += m
+                elif k < 0.85:
+                    m = rnd.randrange(5, 120); ops.append((m, "N")); g += m
+                elif k < 0.93:
+                    m = rnd.randrange(1, 3); ops.append((m, "D")); g += m
+                    m = rnd.randrange(1, 3); ops.append((m, "I")); seq += [rnd.choice("ACGT") for _ in range(m)]
+                else:
+                    ops.append((1, "P"))
+        if rnd.random() < 0.15:
+            n = rnd.randrange(1, 6); ops.append((n, "S")); seq += [rnd.choice("ACGT") for _ in range(n)]
+        if rnd.random() < 0.1:
+            ops.append((rnd.randrange(1, 5), "H"))
+        merged = []
+        for n, o in ops:                                                         # M5 M3 -> M8 (same op twice in a row)
+            if merged and merged[-1][1] == o:
+                merged[-1] = (merged[-1][0] + n, o)
+            else:
+                merged.append((n, o))
+        seq = [(c if rnd.random() > 0.01 else rnd.choice("ACGTN")) for c in seq]
+        qual = "".join("F" if rnd.random() > 0.05 else "#" for _ in seq)
+        S.append((start, sline("f%d" % (i // 2), 99 if i % 2 == 0 else 147, "1", start, 255, "".join("%d%s" % x for x in merged),
+                               "".join(seq), qual, AS=rnd.randrange(100, 150), tlen=rnd.choice([0, 250, -300, 800]))))
+    S.sort(key=lambda t: t[0])
+    return VCF_HEAD + "".join(V), SAM_HEAD + "".join(x[1] for x in S)
+
+
 def run_case(name, vcf_text, sams, args, mapq="255", paired_end="1"):
     d = os.path.join(CASES, name)
     if os.path.isdir(d):
@@ -148,7 +322,7 @@ def run_case(name, vcf_text, sams, args, mapq="255", paired_end="1"):
     # mapper-level golden: the reference mapper on each BAM with the table the product's VCF parser yields
     from phaser_b200 import vcfio
     col = vcfio.sample_column_map(vcf)["S1"]
-    vt, _ = vcfio.parse_vcf(vcf, col)
+    vt, _ = vcfio.parse_vcf(vcf, col, include_indels=int(args[args.index("--include_indels") + 1]) if "--include_indels" in args else 0)
     table = os.path.join(tmp, "table.tsv")
     with open(table, "w") as f:
         for v in range(vt.n_variants):
@@ -269,6 +443,13 @@ def main():
                 paired_end="0")
     option_case("opt_quirks_baseq", "quirks", ["--as_q_cutoff", "0", "--max_block_size", "3"], mapq="0")
     blacklist_cases()
+    v, s = indel_case()
+    run_case("indels", v, [("indels.bam", s)], ["--include_indels", "1", "--as_q_cutoff", "0"])
+    vf, sf = fuzz_indel_case()
+    run_case("fuzz_indels", vf, [("fuzz.bam", sf)], ["--include_indels", "1", "--as_q_cutoff", "0", "--isize", "500"])
+    option_case("fuzz_snvs", "fuzz_indels", ["--as_q_cutoff", "0.1", "--max_block_size", "5"])
+    vq, sq = quirk_case()
+    run_case("opt_quirks_indels", vq, [("quirks.bam", sq)], ["--include_indels", "1", "--as_q_cutoff", "0"])
     config1_case()
 
 

@@ -37,7 +37,8 @@ def args_to_kw(args):
             kw["max_block_size"] = int(v)
         elif a == "--haplo_count_bam_exclude":
             kw["exclude"] = [int(x) - 1 for x in v.split(",")]
-        elif a in ("--gw_phase_method", "--gw_phase_vcf", "--unphased_vars", "--unique_ids", "--pass_only", "--remove_dups"):
+        elif a in ("--gw_phase_method", "--gw_phase_vcf", "--unphased_vars", "--unique_ids", "--pass_only", "--remove_dups",
+                   "--include_indels"):
             kw[a[2:]] = int(v)
         elif a in ("--gw_phase_vcf_min_confidence", "--cc_threshold"):
             kw[a[2:]] = float(v)

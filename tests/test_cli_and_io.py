@@ -23,7 +23,8 @@ def _run_cli(engine, case, tmp_path, extra=()):
     return c, got
 
 
-@pytest.mark.parametrize("case", ["quirks", "rna_two_bams", "opt_blacklists", "opt_maf_gwvcf2", "opt_nounphased_uid", "opt_filters"])
+@pytest.mark.parametrize("case", ["quirks", "rna_two_bams", "opt_blacklists", "opt_maf_gwvcf2", "opt_nounphased_uid", "opt_filters",
+                                  "indels", "fuzz_indels"])
 def test_cli_writes_reference_identical_files(hostsim, tmp_path, case):
     c, got = _run_cli(hostsim, case, tmp_path)
     bad = compare.diff_outputs(c["ref"], got)
@@ -37,7 +38,7 @@ def test_cli_fatal_errors_exit_1(hostsim, tmp_path, capsys):
                        (["--sample", "S1", "--id_separator", ":"], "ID separator must not be"),
                        (["--sample", "S1", "--mapq", "1,2"], "Number of mapq values"),
                        (["--sample", "S1", "--blacklist", "x.bed"], "File: x.bed not found"),
-                       (["--sample", "S1", "--include_indels", "1"], "not supported")):
+                       (["--sample", "S1", "--process_slow", "1"], "not supported")):
         with pytest.raises(SystemExit) as e:
             cli.run(cli.build_parser().parse_args(base + extra), engine=hostsim)
         assert e.value.code == 1
@@ -84,7 +85,7 @@ def test_bgzf_roundtrip_and_gzip_compat(tmp_path):
     assert raw.endswith(bgzf.EOF_BLOCK) and raw[12:14] == b"BC"
 
 
-@pytest.mark.parametrize("case", ["quirks", "rna_small"])
+@pytest.mark.parametrize("case", ["quirks", "rna_small", "indels", "fuzz_indels"])
 def test_read_variant_map_seam_writes_the_reference_tsv(hostsim, tmp_path, monkeypatch, case):
     """Seam S1: do_read_variant_map(variant_table, baseq, o, splice, isize_cutoff) with SAM text on stdin
     produces byte for byte the TSV of the reference mapper (committed golden)."""
@@ -92,13 +93,13 @@ def test_read_variant_map_seam_writes_the_reference_tsv(hostsim, tmp_path, monke
     from phaser_b200 import read_variant_map as rvm, vcfio
     c = G.load_case(case)
     col = vcfio.sample_column_map(c["vcf"])["S1"]
-    vt, _ = vcfio.parse_vcf(c["vcf"], col)
+    vt, _ = vcfio.parse_vcf(c["vcf"], col, include_indels=G.args_to_kw(c["meta"]["args"]).get("include_indels", 0))
     table = tmp_path / "table.tsv"
     with open(table, "w") as f:
         for v in range(vt.n_variants):
             ci = int(np.searchsorted(vt.contig_var_off, v, side="right") - 1)
             f.write("\t".join([vt.contigs[ci], str(int(vt.pos[v])), vt.ids[v], vt.rsids[v], ",".join(vt.all_alleles[v]),
-                               "1", vt.gt[v], vt.maf[v]]) + "\n")
+                               str(int(vt.ref_len[v])), vt.gt[v], vt.maf[v]]) + "\n")
     lines = []
     for ln in open(c["sams"][0]):          # what the two samtools stages would let through
         if ln[0] != "@":

@@ -22,7 +22,8 @@ def test_mapper_tuples_match_oracle(hostsim, name):
     kw = G.args_to_kw(c["meta"]["args"])
     vt, st, batches, col, fd = util.load_inputs(c["vcf"], c["sams"], mapq=c["meta"]["mapq"], paired_end=c["meta"]["paired_end"],
                                                 remove_dups=kw.get("remove_dups", 1), pass_only=kw.get("pass_only", 1),
-                                                id_separator=kw.get("id_separator", "_"), gw_phase_method=kw.get("gw_phase_method", 0))
+                                                id_separator=kw.get("id_separator", "_"), gw_phase_method=kw.get("gw_phase_method", 0),
+                                                include_indels=kw.get("include_indels", 0))
     for batch in batches:
         got, exp = util.compare_tuples(hostsim, vt, batch)
         assert got == exp

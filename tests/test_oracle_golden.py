@@ -20,7 +20,8 @@ def test_port_mapper_matches_reference_tsv(name):
     kw = G.args_to_kw(c["meta"]["args"])
     vt, st, batches, col, fd = util.load_inputs(c["vcf"], c["sams"], mapq=c["meta"]["mapq"], paired_end=c["meta"]["paired_end"],
                                                 remove_dups=1, pass_only=kw.get("pass_only", 1),   # the golden TSVs were made without duplicates
-                                                id_separator="_", gw_phase_method=0)   # ... and with the default table
+                                                id_separator="_", gw_phase_method=0,   # ... and with the default table
+                                                include_indels=kw.get("include_indels", 0))
     for b, batch in zip(c["meta"]["bams"], batches):
         tup = port.map_reads(batch, vt, 10, 0.0)      # the golden TSV was made with isize 0
         assert port.tuples_tsv(batch, vt, tup) == c["mapper"][b]

@@ -60,10 +60,10 @@ def bam_display_names(paths):
 
 
 def load_inputs(vcf_gz, sams, sample="S1", mapq="255", paired_end="1", remove_dups=1, pass_only=1, id_separator="_",
-                gw_phase_method=0, blacklist="", haplo_count_blacklist=""):
+                gw_phase_method=0, blacklist="", haplo_count_blacklist="", include_indels=0):
     col = vcfio.sample_column_map(vcf_gz)[sample]
     vt, st = vcfio.parse_vcf(vcf_gz, col, pass_only=pass_only, id_separator=id_separator, gw_phase_method=gw_phase_method,
-                             blacklist=blacklist, haplo_count_blacklist=haplo_count_blacklist)
+                             blacklist=blacklist, haplo_count_blacklist=haplo_count_blacklist, include_indels=include_indels)
     fd = samio.FragmentDictionary()
     mq = [int(x) for x in str(mapq).split(",")]; pe = [int(x) for x in str(paired_end).split(",")]
     if len(mq) == 1:
@@ -77,9 +77,9 @@ def load_inputs(vcf_gz, sams, sample="S1", mapq="255", paired_end="1", remove_du
 def product_outputs(engine, vcf_gz, sams, sample="S1", mapq="255", paired_end="1", max_block_size=15,
                     as_q_cutoff=0.05, cc_threshold=0.01, exclude=(), isize=(0.0,), baseq=10, unphased_vars=1,
                     gw_phase_vcf=0, gw_phase_method=0, gw_phase_vcf_min_confidence=0.90, unique_ids=0, pass_only=1,
-                    remove_dups=1, id_separator="_", blacklist="", haplo_count_blacklist=""):
+                    remove_dups=1, id_separator="_", blacklist="", haplo_count_blacklist="", include_indels=0):
     vt, st, batches, col, fd = load_inputs(vcf_gz, sams, sample, mapq, paired_end, remove_dups, pass_only, id_separator,
-                                           gw_phase_method, blacklist, haplo_count_blacklist)
+                                           gw_phase_method, blacklist, haplo_count_blacklist, include_indels)
     P = pipeline.PhaseParams(baseq=baseq, isize=list(isize), as_q_cutoff=as_q_cutoff, cc_threshold=cc_threshold,
                              max_block_size=max_block_size, haplo_count_bam_exclude=list(exclude))
     dev = [engine.upload_reads(b) for b in batches]
@@ -96,10 +96,10 @@ def product_outputs(engine, vcf_gz, sams, sample="S1", mapq="255", paired_end="1
 
 
 def oracle_outputs(vcf_gz, sams, sample="S1", mapq="255", paired_end="1", pass_only=1, remove_dups=1, exclude=None,
-                   blacklist="", haplo_count_blacklist="", **kw):
+                   blacklist="", haplo_count_blacklist="", include_indels=0, **kw):
     vt, st, batches, col, fd = load_inputs(vcf_gz, sams, sample, mapq, paired_end, remove_dups, pass_only,
                                            kw.get("id_separator", "_"), kw.get("gw_phase_method", 0), blacklist,
-                                           haplo_count_blacklist)
+                                           haplo_count_blacklist, include_indels)
     if exclude is not None:
         kw["haplo_count_bam_exclude"] = list(exclude)
     P = port.Params(bam_names=bam_display_names(sams), **kw)
