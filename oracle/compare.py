@@ -32,15 +32,22 @@ def _relabel(col):
 def canon_haplotypic_counts(text):
     lines = text.split("\n")
     header = lines[0]
+    with_ids = header.endswith("read_ids_a\tread_ids_b")
     blocks, singles = [], []
     for ln in lines[1:]:
         if ln == "":
             continue
         c = ln.split("\t")
+        ids = []
+        if with_ids and len(c) >= 20:
+            # --output_read_ids 1: rows carry the two id lists BEFORE max_haplo_maf (phaser.py:1120-1123, 1216-1219) although
+            # the header names them last (phaser.py:837-838); both are list(set(...)) -> compared as sorted sets
+            ids = [",".join(sorted(x.split(","))) for x in c[14:16]]
+            c = c[:14] + c[16:]
         if len(c) >= 18:
             c[16] = _relabel(c[16]); c[17] = _relabel(c[17])
         c[5] = ",".join(sorted(c[5].split(","))) if c[5] else c[5]     # variantsBlacklisted is printed from a set (phaser.py:1119)
-        row = "\t".join(c)
+        row = "\t".join(c + ids)
         # singleton rows: variantCount == 1, nothing blacklisted, empty aReads/bReads (phaser.py:1214-1220)
         if c[4] == "1" and c[6] == "0" and c[16] == "" and c[17] == "" and c[13] == "1" and "," not in c[3]:
             singles.append(row)
@@ -121,4 +128,11 @@ def diff_outputs(ref, got, files=("allelic_counts", "allele_config", "haplotypes
                 only_r = sorted(rr - rg)[:3]; only_g = sorted(rg - rr)[:3]
                 bad.append("variant_connections: ref %d rows, got %d rows; only in ref %s; only in got %s" % (
                     nr, ng, only_r, only_g))
+    # --output_network dump (phaser.py:1128-1157): link rows in order; node rows come from set(nodes) -> compared as a set
+    if "network_links" in ref or "network_links" in got:
+        if ref.get("network_links") != got.get("network_links"):
+            first_diff(ref.get("network_links", ""), got.get("network_links", ""), "network.links")
+        if sorted(ref.get("network_nodes", "").split("\n")[1:]) != sorted(got.get("network_nodes", "").split("\n")[1:]) or \
+                ref.get("network_nodes", "").split("\n")[0] != got.get("network_nodes", "").split("\n")[0]:
+            bad.append("network.nodes differ (as sets)")
     return bad

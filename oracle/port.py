@@ -139,6 +139,8 @@ class Params:
         self.id_separator = "_"
         self.unique_ids = 0
         self.output_read_ids = 0
+        self.read_names = None                # QNAME per fragment id, needed with output_read_ids = 1
+        self.output_network = ""              # variant id whose block is dumped as a network
         self.pass_only = 1
         self.remove_dups = 1
         for k, v in kw.items():
@@ -538,7 +540,16 @@ def _relabel_first_occurrence(lists):
 def _outputs(res, vt, var, sets, links, final, contig_of, vinfo, P, nb):
     hc = ["\t".join(["contig", "start", "stop", "variants", "variantCount", "variantsBlacklisted",
                      "variantCountBlacklisted", "haplotypeA", "haplotypeB", "aCount", "bCount", "totalCount",
-                     "blockGWPhase", "gwStat", "max_haplo_maf", "bam", "aReads", "bReads"]) + "\n"]
+                     "blockGWPhase", "gwStat", "max_haplo_maf", "bam", "aReads", "bReads"] +
+                    (["read_ids_a", "read_ids_b"] if P.output_read_ids == 1 else [])) + "\n"]     # phaser.py:837-838
+
+    def read_ids(lists):
+        # phaser.py:1087-1088 prints list(set(...)); the canonical form is first-occurrence order (oracle/compare.py sorts)
+        seen = {}
+        for lst in lists:
+            for f in lst:
+                seen.setdefault(f, None)
+        return _lts(P.read_names[f] for f in seen)
     hp = ["\t".join(['contig', 'start', 'stop', 'length', 'variants', 'variant_ids', 'variant_alleles', 'reads_hap_a',
                      'reads_hap_b', 'reads_total', 'edges_supporting', 'edges_total', 'annotated_phase',
                      'phase_concordant', 'gw_phase', 'gw_confidence']) + "\n"]
@@ -665,9 +676,38 @@ def _outputs(res, vt, var, sets, links, final, contig_of, vinfo, P, nb):
                 hc.append("\t".join(map(str, [chrom, min(positions), max(positions), _lts(vt.ids[variants[i]] for i in used),
                                               len(used), _lts(sorted(blacklisted)), len(blacklisted),
                                               _lts(alleles[0][i] for i in used), _lts(alleles[1][i] for i in used), cnt[0], cnt[1],
-                                              sum(cnt), gwp, stat, str(max_maf), P.bam_names[b],
+                                              sum(cnt), gwp, stat] +
+                                        ([read_ids(vreads[0]), read_ids(vreads[1])] if P.output_read_ids == 1 else []) +   # phaser.py:1120-1121
+                                        [str(max_maf), P.bam_names[b],
                                               _relabel_first_occurrence(vreads[0]),
                                               _relabel_first_occurrence(vreads[1])])) + "\n")
+        if P.output_network != "" and P.output_network in [vt.ids[v] for v in variants]:
+            # generate_hap_network_all (phaser.py:1928-1949) + writers (phaser.py:1128-1157)
+            counted = set(); junctions = []
+            for i in range(len(variants)):
+                for j in range(len(variants)):
+                    if i == j:
+                        continue
+                    for a in (0, 1):
+                        for oa in (0, 1):
+                            if (i, a, j, oa) in counted or (j, oa, i, a) in counted:
+                                continue
+                            k = len(sets[variants[i]][a] & sets[variants[j]][oa])
+                            junctions.append([vt.ids[variants[i]] + ":" + vis[i]["alleles"][a],
+                                              vt.ids[variants[j]] + ":" + vis[j]["alleles"][oa], k, 0])
+                            junctions.append([vt.ids[variants[i]] + ":" + vis[i]["alleles"][1 - a],
+                                              vt.ids[variants[j]] + ":" + vis[j]["alleles"][1 - oa], k, 1])
+                            counted.add((i, a, j, oa))
+            lk = ["variantA\tvariantB\tconnections\tinferred\n"]; nodes = []
+            for item in junctions:
+                if item[2] > 0:
+                    lk.append(_lts(item, "\t") + "\n"); nodes += [item[0], item[1]]
+            nd = ["id\tindex\tassigned_hap\n"]
+            for item in dict.fromkeys(nodes):          # a set in the reference: compared as a set
+                xv, xa = item.split(":")[0], item.split(":")[1]
+                vi_ = [vt.ids[v] for v in variants].index(xv)
+                nd.append(item + "\t" + str(vi_) + "\t" + ("A" if alleles[0][vi_] == xa else "B") + "\n")
+            res.network_links = "".join(lk); res.network_nodes = "".join(nd)
         for i, va in enumerate(variants):
             for j, vb in enumerate(variants):
                 if va != vb:
@@ -694,7 +734,9 @@ def _outputs(res, vt, var, sets, links, final, contig_of, vinfo, P, nb):
                         pstr = "0/1"
                     hc.append("\t".join([vt.contigs[contig_of[v]], str(int(vt.pos[v])), str(int(vt.pos[v])), vt.ids[v],
                                          "1", "", "0", vi["alleles"][0], vi["alleles"][1], str(ca), str(cb), str(ca + cb),
-                                         pstr, "1", str(vi["maf"]), P.bam_names[b], "", ""]) + "\n")
+                                         pstr, "1"] +
+                                        ([read_ids([var[v]["haplo"][h].get(b, [])]) for h in (0, 1)] if P.output_read_ids == 1 else []) +   # phaser.py:1216-1217
+                                        [str(vi["maf"]), P.bam_names[b], "", ""]) + "\n")
         for v in singles:
             vi = vinfo(v)
             if "-" not in vi["phase"]:

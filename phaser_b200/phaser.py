@@ -6,7 +6,7 @@ the work between "het sites loaded" and "files written" runs on the GPU through 
 (include/phz.h).  Differences a user can see:
   * no samtools / bgzip / tabix / bedtools / bcftools are needed (BAM or SAM text is read directly);
   * not yet supported, rejected with a FATAL ERROR instead of being silently ignored:
-    --process_slow 1, --output_network, --output_read_ids 1 (SURVEY.md section 8f, "next" rows);
+    --process_slow 1 (per-contig noise changes the results in the reference and is broken on python 3);
   * fields the reference prints in CPython-set order come out in a canonical order
     (SURVEY.md section 8c).
 """
@@ -128,9 +128,7 @@ def run(args, engine=None):
     say("  B200-native read->variant->haplotype path (phaser_b200)")
     say("##################################################")
     say("")
-    for flag, bad, why in (("--process_slow 1", args.process_slow == 1, "per-contig mode changes results in the reference"),
-                           ("--output_network", args.output_network != "", "debug dump"),
-                           ("--output_read_ids 1", args.output_read_ids == 1, "read-id columns")):
+    for flag, bad, why in (("--process_slow 1", args.process_slow == 1, "per-contig mode changes results in the reference"),):
         if bad:
             fatal_error("%s is not supported by the B200 path yet (%s)." % (flag, why))
     if args.id_separator == ":" or args.id_separator == "":
@@ -191,7 +189,8 @@ def run(args, engine=None):
         batches.append(engine.upload_reads(rb))
         del rb
     P = pipeline.PhaseParams(baseq=args.baseq, isize=isize, as_q_cutoff=args.as_q_cutoff, cc_threshold=args.cc_threshold,
-                             max_block_size=args.max_block_size, haplo_count_bam_exclude=exclude)
+                             max_block_size=args.max_block_size, haplo_count_bam_exclude=exclude,
+                             want_read_ids=(args.output_read_ids == 1), want_kept_tuples=(args.output_network != ""))
     try:
         res = pipeline.run_path(engine, vt, batches, P, n_fragments=len(fd))
     except PhaserFatal as e:
@@ -203,7 +202,8 @@ def run(args, engine=None):
     say("#3. Identifying connected variants...")
     say("     sequencing noise level estimated at %f" % res.noise_e)
     out = writer.Outputs(res, vt, bam_names, P, unphased_vars=args.unphased_vars, gw_phase_method=args.gw_phase_method,
-                         unique_ids=args.unique_ids)
+                         unique_ids=args.unique_ids, read_names=fd.names if args.output_read_ids == 1 else None,
+                         output_network=args.output_network)
     with open(args.o + ".variant_connections.txt", "w") as f:
         f.write(out.variant_connections())
     say("     %d variant connections dropped because of conflicting configurations (threshold = %f)" % (
@@ -221,6 +221,11 @@ def run(args, engine=None):
         f.write(hc)
     with open(args.o + ".allele_config.txt", "w") as f:
         f.write(cfg)
+    if out.network is not None:                      # phaser.py:1128-1157
+        with open(args.o + ".network.links.txt", "w") as f:
+            f.write(out.network[0])
+        with open(args.o + ".network.nodes.txt", "w") as f:
+            f.write(out.network[1])
     unphased_phased = phase_corrected = 0
     if args.write_vcf == 1:
         say("#7. Outputting phased VCF...")

@@ -33,6 +33,8 @@ class PhaseParams:
     max_block_size: int = 15
     haplo_count_bam_exclude: List[int] = field(default_factory=list)   # 0-based
     want_read_lists: bool = True
+    want_read_ids: bool = False        # --output_read_ids 1: kept tuples of un-blocked variants come back too
+    want_kept_tuples: bool = False     # --output_network: all kept (fragment, variant, class|bam) tuples come back
 
     def exclude_mask(self):
         m = 0
@@ -244,4 +246,12 @@ def run_path(engine: Engine, vt: VariantTable, batches, params: PhaseParams, n_f
     if download:
         for name in RESULT_ARRAYS + (["rl_frag", "rl_var", "rl_row"] if params.want_read_lists else []):
             arrays[name] = engine.download(name)
+        if params.want_kept_tuples:
+            for name in ("g_var", "g_cb", "g_frag"):
+                arrays[name] = engine.download(name)
+        if params.want_read_ids:
+            # read_ids of singleton rows (phaser.py:1194-1218): the kept allele tuples of variants outside every block
+            gv = engine.download("g_var"); gc = engine.download("g_cb")
+            sel = np.nonzero((arrays["v_final"][gv] == 0xFFFFFFFF) & ((gc & 3) < 2))[0]
+            arrays["sg_var"] = gv[sel]; arrays["sg_cb"] = gc[sel]; arrays["sg_frag"] = engine.download("g_frag")[sel]
     return PhaseResult(nb, cutoffs, kept, cands, noise_e, match, mism, engine.counters(), flags, arrays)

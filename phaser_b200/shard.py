@@ -106,6 +106,7 @@ def merge_results(parts, vt: VariantTable, n_bams: int) -> PhaseResult:
     ed = {k: [] for k in ("ed_a", "ed_b", "ed_sup", "ed_tot", "ed_cfg", "ed_keep")}
     blocks = []          # (order key, rank index, local final block)
     rl = {k: [] for k in ("rl_frag", "rl_var", "rl_row")}
+    sg = {k: [] for k in ("sg_var", "sg_cb", "sg_frag", "g_var", "g_cb", "g_frag")}
     counters = {}
     bb = max(1, int(np.ceil(np.log2(max(n_bams, 2)))))
     for ri, (res, gid, gcontigs) in enumerate(parts):
@@ -126,6 +127,12 @@ def merge_results(parts, vt: VariantTable, n_bams: int) -> PhaseResult:
         ed["ed_a"].append(gid[res.ed_a.astype(np.int64)].astype(np.uint32)); ed["ed_b"].append(gid[res.ed_b.astype(np.int64)].astype(np.uint32))
         for k in ("ed_sup", "ed_tot", "ed_cfg", "ed_keep"):
             ed[k].append(res.arrays[k])
+        if "sg_var" in res.arrays:
+            sg["sg_var"].append(gid[res.sg_var.astype(np.int64)].astype(np.uint32))
+            sg["sg_cb"].append(res.sg_cb); sg["sg_frag"].append(res.sg_frag)
+        if "g_var" in res.arrays:
+            sg["g_var"].append(gid[res.g_var.astype(np.int64)].astype(np.uint32))
+            sg["g_cb"].append(res.g_cb); sg["g_frag"].append(res.g_frag)
         # contig order of first appearance (phaser.py:573-574): first BAM with a tuple on the contig, then VCF order
         first_bam_of_contig = {}
         for v in np.nonzero(seen)[0].tolist():
@@ -171,6 +178,10 @@ def merge_results(parts, vt: VariantTable, n_bams: int) -> PhaseResult:
         arrays["rl_row"] = row[order]; arrays["rl_var"] = np.concatenate(rl["rl_var"])[order]; arrays["rl_frag"] = np.concatenate(rl["rl_frag"])[order]
     else:
         arrays["rl_row"] = np.zeros(0, np.uint32); arrays["rl_var"] = np.zeros(0, np.uint32); arrays["rl_frag"] = np.zeros(0, np.uint32)
+    for pre in ("sg_", "g_"):
+        if sg[pre + "var"]:
+            for k, dt in (("var", np.uint32), ("cb", np.uint8), ("frag", np.uint32)):
+                arrays[pre + k] = cat(sg[pre + k], dt)
     first = next(p[0] for p in parts if p[0] is not None)
     return PhaseResult(n_bams, first.as_cutoff, [sum(p[0].tuples_per_bam[b] for p in parts if p[0] is not None) for b in range(n_bams)],
                        [sum(p[0].candidates_per_bam[b] for p in parts if p[0] is not None) for b in range(n_bams)],

@@ -47,8 +47,14 @@ class VariantMeta:
 
 
 class Outputs:
-    def __init__(self, res: PhaseResult, vt, bam_names, params, unphased_vars=1, gw_phase_method=0, unique_ids=0):
+    def __init__(self, res: PhaseResult, vt, bam_names, params, unphased_vars=1, gw_phase_method=0, unique_ids=0,
+                 read_names=None, output_network=""):
+        """`read_names` (QNAME per fragment id) switches the --output_read_ids 1 columns on (phaser.py:837-838);
+        `output_network` names the variant whose block is dumped as a network (phaser.py:1128-1157)."""
+        self.output_network = output_network
+        self.network = None        # (links text, nodes text) once block_tables() met the block
         self.res = res; self.vt = vt; self.bam_names = bam_names; self.P = params
+        self.read_names = read_names
         self.unphased_vars = unphased_vars; self.gw_phase_method = gw_phase_method; self.unique_ids = unique_ids
         self._meta = {}
         self.contig_of = np.zeros(vt.n_variants, np.int64)
@@ -119,6 +125,59 @@ class Outputs:
             rows.setdefault(int(row[s]), OrderedDict())[int(var[s])] = frag[s:e].tolist()
         return rows
 
+    def _read_id_columns(self, frag_lists):
+        """read_ids_a / read_ids_b of one row: the distinct QNAMEs of `frag_lists` in first-occurrence order, i.e.
+        the list the aReads/bReads indices point into (phaser.py:1087-1105; the reference's order is list(set()))"""
+        seen = {}
+        for lst in frag_lists:
+            for f in lst:
+                if f not in seen:
+                    seen[f] = len(seen)
+        return ",".join(self.read_names[f] for f in seen)
+
+    def _network_tables(self, variants, ms, alleles_a):
+        """generate_hap_network_all + the two writers (phaser.py:1928-1949, 1128-1157): junction = number of reads shared by
+        two allele read sets (all BAMs).  Node rows come from a set in the reference; here in first-mention order."""
+        r = self.res
+        if "g_var" not in r.arrays:
+            raise RuntimeError("--output_network needs the kept tuples (PhaseParams.want_kept_tuples)")
+        pos_of = {v: i for i, v in enumerate(variants)}
+        sets = [[set(), set()] for _ in variants]
+        sel = np.nonzero(np.isin(r.g_var, np.asarray(variants, r.g_var.dtype)) & ((r.g_cb & 3) < 2))[0]
+        for v, cb, f in zip(r.g_var[sel].tolist(), r.g_cb[sel].tolist(), r.g_frag[sel].tolist()):
+            sets[pos_of[v]][cb & 3].add(f)
+        links = ["\t".join(["variantA", "variantB", "connections", "inferred\n"])]
+        nodes = []
+        n = len(variants)
+        for i in range(n):
+            for j in range(n):
+                if j <= i:
+                    continue          # (j, oa, i, a) was counted when the roles were swapped (phaser.py:1943)
+                for a in (0, 1):
+                    for oa in (0, 1):
+                        k = len(sets[i][a] & sets[j][oa])
+                        if k > 0:
+                            for x, y, inf in ((a, oa, 0), (1 - a, 1 - oa, 1)):
+                                na = ms[i].id + ":" + ms[i].alleles[x]; nb_ = ms[j].id + ":" + ms[j].alleles[y]
+                                links.append("\t".join([na, nb_, str(k), str(inf)]) + "\n")
+                                nodes += [na, nb_]
+        out = ["id\tindex\tassigned_hap\n"]
+        for item in dict.fromkeys(nodes):
+            xvar, xallele = item.split(":")[0], item.split(":")[1]
+            vi = [m.id for m in ms].index(xvar)
+            out.append(item + "\t" + str(vi) + "\t" + ("A" if alleles_a[vi] == xallele else "B") + "\n")
+        return "".join(links), "".join(out)
+
+    def _singleton_read_sets(self):
+        """(variant, bam, allele) -> fragment ids in tuple order, for the variants outside every block"""
+        r = self.res
+        out = {}
+        if "sg_var" not in r.arrays:
+            return out
+        for v, cb, f in zip(r.sg_var.tolist(), r.sg_cb.tolist(), r.sg_frag.tolist()):
+            out.setdefault((v, cb >> 2, cb & 3), []).append(f)
+        return out
+
     @staticmethod
     def _relabel(lists):
         ids = {}
@@ -139,7 +198,8 @@ class Outputs:
         excl = set(self.P.haplo_count_bam_exclude)
         hc = ["\t".join(["contig", "start", "stop", "variants", "variantCount", "variantsBlacklisted",
                          "variantCountBlacklisted", "haplotypeA", "haplotypeB", "aCount", "bCount", "totalCount",
-                         "blockGWPhase", "gwStat", "max_haplo_maf", "bam", "aReads", "bReads"]) + "\n"]
+                         "blockGWPhase", "gwStat", "max_haplo_maf", "bam", "aReads", "bReads"] +
+                        (["read_ids_a", "read_ids_b"] if self.read_names is not None else [])) + "\n"]
         hp = ["\t".join(['contig', 'start', 'stop', 'length', 'variants', 'variant_ids', 'variant_alleles',
                          'reads_hap_a', 'reads_hap_b', 'reads_total', 'edges_supporting', 'edges_total',
                          'annotated_phase', 'phase_concordant', 'gw_phase', 'gw_confidence']) + "\n"]
@@ -227,16 +287,21 @@ class Outputs:
                     continue
                 a_cnt, b_cnt = int(fbc[f, b, 0]), int(fbc[f, b, 1])
                 if a_cnt + b_cnt > 0:
-                    cols = []
+                    cols = []; ids = []
                     for h in (0, 1):
                         key = (((f << bb) | b) << 1) | h
                         per_var = rl.get(key, {})
-                        cols.append(self._relabel([per_var.get(variants[i], []) for i in used]))
+                        lists = [per_var.get(variants[i], []) for i in used]
+                        cols.append(self._relabel(lists))
+                        if self.read_names is not None:       # the row's own order: ids BEFORE maf/bam (phaser.py:1120-1123)
+                            ids.append(self._read_id_columns(lists))
                     hc.append("\t".join(map(str, [ms[0].chrom, min(positions), max(positions),
                                                   ",".join(ms[i].id for i in used), len(used), ",".join(blacklisted),
                                                   len(blacklisted), ",".join(alleles[0][i] for i in used),
-                                                  ",".join(alleles[1][i] for i in used), a_cnt, b_cnt, a_cnt + b_cnt, gwp, stat,
-                                                  str(max_maf), self.bam_names[b], cols[0], cols[1]])) + "\n")
+                                                  ",".join(alleles[1][i] for i in used), a_cnt, b_cnt, a_cnt + b_cnt, gwp, stat] +
+                                             ids + [str(max_maf), self.bam_names[b], cols[0], cols[1]])) + "\n")
+            if self.output_network != "" and self.output_network in [m.id for m in ms]:
+                self.network = self._network_tables(variants, ms, alleles[0])
             for i, ma in enumerate(ms):
                 for j, mb in enumerate(ms):
                     if i != j:
@@ -249,6 +314,7 @@ class Outputs:
             singles = [v for v in self.first_seen_order().tolist()
                        if int(ncls[v, 0]) + int(ncls[v, 1]) > 0 and r.v_final[v] == NONE32]
             black = getattr(self.vt, "haplo_blacklisted", None)
+            sg = self._singleton_read_sets() if self.read_names is not None else None
             for v in singles:
                 m = self.meta(v)
                 if black is not None and black[v]:
@@ -262,9 +328,10 @@ class Outputs:
                             pstr = str(m.phase.index(m.alleles[0])) + "|" + str(m.phase.index(m.alleles[1]))
                         else:
                             pstr = "0/1"
+                        ids = [] if sg is None else [self._read_id_columns([sg.get((v, b, h), [])]) for h in (0, 1)]
                         hc.append("\t".join([m.chrom, str(m.pos), str(m.pos), m.id, "1", "", "0", m.alleles[0], m.alleles[1],
-                                             str(ca), str(cb), str(ca + cb), pstr, "1", str(m.maf), self.bam_names[b],
-                                             "", ""]) + "\n")
+                                             str(ca), str(cb), str(ca + cb), pstr, "1"] + ids +
+                                            [str(m.maf), self.bam_names[b], "", ""]) + "\n")
             for v in singles:
                 m = self.meta(v)
                 if "-" not in m.phase:

@@ -313,6 +313,9 @@ def run_case(name, vcf_text, sams, args, mapq="255", paired_end="1"):
         text = rr.read_text(r[suf])
         with open(os.path.join(d, "ref." + suf.replace(".gz", "")), "w") as f:
             f.write(text)
+    if "--output_network" in args:                       # phaser.py:1128-1157
+        for suf in ("network.links.txt", "network.nodes.txt"):
+            shutil.copy(os.path.join(tmp, "ref." + suf), os.path.join(d, "ref." + suf))
     for p in paths:
         os.remove(p + ".bai")
     os.remove(vcf + ".tbi")
@@ -443,6 +446,8 @@ def main():
                 paired_end="0")
     option_case("opt_quirks_baseq", "quirks", ["--as_q_cutoff", "0", "--max_block_size", "3"], mapq="0")
     blacklist_cases()
+    option_case("opt_read_ids", "rna_two_bams", ["--output_read_ids", "1"])
+    option_case("opt_network", "rna_two_bams", ["--output_network", "21_24913_A_C"])
     v, s = indel_case()
     run_case("indels", v, [("indels.bam", s)], ["--include_indels", "1", "--as_q_cutoff", "0"])
     vf, sf = fuzz_indel_case()

@@ -17,6 +17,10 @@ def load_case(name):
     with open(os.path.join(d, "case.json")) as f:
         meta = json.load(f)
     ref = {k: open(os.path.join(d, fn)).read() for k, fn in FILES.items()}
+    for k in ("network_links", "network_nodes"):        # --output_network cases only
+        fn = os.path.join(d, "ref." + k.replace("_", ".") + ".txt")
+        if os.path.exists(fn):
+            ref[k] = open(fn).read()
     src = os.path.join(CASES, meta["inputs"]) if "inputs" in meta else d
     sams = [os.path.join(src, b) for b in meta["bams"]]
     mapper = {b: open(os.path.join(d, "ref.mapper.%s.tsv" % b)).read() for b in meta["bams"]}
@@ -38,12 +42,12 @@ def args_to_kw(args):
         elif a == "--haplo_count_bam_exclude":
             kw["exclude"] = [int(x) - 1 for x in v.split(",")]
         elif a in ("--gw_phase_method", "--gw_phase_vcf", "--unphased_vars", "--unique_ids", "--pass_only", "--remove_dups",
-                   "--include_indels"):
+                   "--include_indels", "--output_read_ids"):
             kw[a[2:]] = int(v)
         elif a in ("--gw_phase_vcf_min_confidence", "--cc_threshold"):
             kw[a[2:]] = float(v)
-        elif a == "--id_separator":
-            kw["id_separator"] = v
+        elif a in ("--id_separator", "--output_network"):
+            kw[a[2:]] = v
         elif a in ("--blacklist", "--haplo_count_blacklist"):
             kw[a[2:]] = os.path.join(os.path.dirname(CASES), v)
         else:

@@ -20,11 +20,15 @@ def _run_cli(engine, case, tmp_path, extra=()):
     got = {k: open(o + "." + k + ".txt").read() for k in ("allelic_counts", "allele_config", "haplotypes", "haplotypic_counts",
                                                           "variant_connections")}
     got["vcf"] = gzip.open(o + ".vcf.gz", "rt").read()
+    for k in ("network_links", "network_nodes"):
+        fn = o + "." + k.replace("_", ".") + ".txt"
+        if os.path.exists(fn):
+            got[k] = open(fn).read()
     return c, got
 
 
 @pytest.mark.parametrize("case", ["quirks", "rna_two_bams", "opt_blacklists", "opt_maf_gwvcf2", "opt_nounphased_uid", "opt_filters",
-                                  "indels", "fuzz_indels"])
+                                  "indels", "fuzz_indels", "opt_read_ids", "opt_network"])
 def test_cli_writes_reference_identical_files(hostsim, tmp_path, case):
     c, got = _run_cli(hostsim, case, tmp_path)
     bad = compare.diff_outputs(c["ref"], got)

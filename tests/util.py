@@ -77,22 +77,27 @@ def load_inputs(vcf_gz, sams, sample="S1", mapq="255", paired_end="1", remove_du
 def product_outputs(engine, vcf_gz, sams, sample="S1", mapq="255", paired_end="1", max_block_size=15,
                     as_q_cutoff=0.05, cc_threshold=0.01, exclude=(), isize=(0.0,), baseq=10, unphased_vars=1,
                     gw_phase_vcf=0, gw_phase_method=0, gw_phase_vcf_min_confidence=0.90, unique_ids=0, pass_only=1,
-                    remove_dups=1, id_separator="_", blacklist="", haplo_count_blacklist="", include_indels=0):
+                    remove_dups=1, id_separator="_", blacklist="", haplo_count_blacklist="", include_indels=0,
+                    output_read_ids=0, output_network=""):
     vt, st, batches, col, fd = load_inputs(vcf_gz, sams, sample, mapq, paired_end, remove_dups, pass_only, id_separator,
                                            gw_phase_method, blacklist, haplo_count_blacklist, include_indels)
     P = pipeline.PhaseParams(baseq=baseq, isize=list(isize), as_q_cutoff=as_q_cutoff, cc_threshold=cc_threshold,
-                             max_block_size=max_block_size, haplo_count_bam_exclude=list(exclude))
+                             max_block_size=max_block_size, haplo_count_bam_exclude=list(exclude),
+                             want_read_ids=(output_read_ids == 1), want_kept_tuples=(output_network != ""))
     dev = [engine.upload_reads(b) for b in batches]
     res = pipeline.run_path(engine, vt, dev, P, n_fragments=len(fd.names))
     o = writer.Outputs(res, vt, bam_display_names(sams), P, unphased_vars=unphased_vars, gw_phase_method=gw_phase_method,
-                       unique_ids=unique_ids)
+                       unique_ids=unique_ids, read_names=fd.names if output_read_ids == 1 else None,
+                       output_network=output_network)
     ac = o.allelic_counts(); vc = o.variant_connections()
     hp, hc, cfg = o.block_tables()
     with gzip.open(vcf_gz, "rt") as f:
         vcf_text, _, _ = o.vcf_text(f.readlines(), col, id_separator=id_separator, gw_phase_vcf=gw_phase_vcf,
                                     min_conf=gw_phase_vcf_min_confidence)
-    return dict(allelic_counts=ac, allele_config=cfg, haplotypes=hp, haplotypic_counts=hc, variant_connections=vc,
-                vcf=vcf_text), res, (vt, batches)
+    out = dict(allelic_counts=ac, allele_config=cfg, haplotypes=hp, haplotypic_counts=hc, variant_connections=vc, vcf=vcf_text)
+    if o.network is not None:
+        out["network_links"], out["network_nodes"] = o.network
+    return out, res, (vt, batches)
 
 
 def oracle_outputs(vcf_gz, sams, sample="S1", mapq="255", paired_end="1", pass_only=1, remove_dups=1, exclude=None,
@@ -102,13 +107,17 @@ def oracle_outputs(vcf_gz, sams, sample="S1", mapq="255", paired_end="1", pass_o
                                            haplo_count_blacklist, include_indels)
     if exclude is not None:
         kw["haplo_count_bam_exclude"] = list(exclude)
+    if kw.get("output_read_ids", 0) == 1:
+        kw["read_names"] = fd.names
     P = port.Params(bam_names=bam_display_names(sams), **kw)
     res = port.run(vt, batches, P)
     with gzip.open(vcf_gz, "rt") as f:
         vcf_text, _, _ = port.write_vcf_text(res, vt, f.readlines(), col, P)
-    return dict(allelic_counts=res.allelic_counts, allele_config=res.allele_config, haplotypes=res.haplotypes,
-                haplotypic_counts=res.haplotypic_counts, variant_connections=res.variant_connections,
-                vcf=vcf_text), res
+    out = dict(allelic_counts=res.allelic_counts, allele_config=res.allele_config, haplotypes=res.haplotypes,
+               haplotypic_counts=res.haplotypic_counts, variant_connections=res.variant_connections, vcf=vcf_text)
+    if hasattr(res, "network_links"):
+        out["network_links"] = res.network_links; out["network_nodes"] = res.network_nodes
+    return out, res
 
 
 def compare_tuples(engine, vt, batch, baseq=10, isize=0.0):
