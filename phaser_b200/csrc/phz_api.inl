@@ -155,7 +155,7 @@ static bool find_array(phz_ctx* ctx, const std::string& name, ArrRef* out) {
   A("vrank", vrank, p.V) A("cfirst", cfirst, p.nc) A("crank", crank, p.nc)
   A("e_key", e_key, p.NE) A("e_bam", e_bam, p.NE) A("e_mask", e_mask, p.NE) A("e_tmin", e_tmin, p.NE) A("grp_off", grp_off, p.NG + 1)
   A("ed_a", ed_a, p.E) A("ed_b", ed_b, p.E) A("ed_sup", ed_sup, p.E) A("ed_tot", ed_tot, p.E) A("ed_n9", ed_n9, p.E * 9)
-  A("ed_cfg", ed_cfg, p.E) A("ed_keep", ed_keep, p.E)
+  A("ed_cfg", ed_cfg, p.E) A("ed_keep", ed_keep, p.E) A("big_tot", big_tot, p.NBT)
   A("members", members, p.NM) A("blk_off", blk_off, p.NB + 1) A("blk_order", blk_order, p.NB) A("blk_status", blk_status, p.NB)
   A("blk_nfinal", blk_nfinal, p.NB) A("blk_rank", blk_rank, p.NB)
   A("fb_first", fb_first, p.NF) A("fb_len", fb_len, p.NF) A("fb_blk", fb_blk, p.NF) A("fb_sup", fb_sup, p.NF) A("fb_tot", fb_tot, p.NF)
@@ -196,6 +196,7 @@ int phz_set_option(phz_ctx* ctx, const char* name, int64_t value) {
   std::string n(name);
   if (n == "k1_mode") ctx->p.k1_mode = (int)value;
   else if (n == "k1_min_ctas") ctx->p.k1_min_ctas = (int)value;
+  else if (n == "big_total_threshold") ctx->p.big_total_thr = (u32)value;
   else throw PhzError("unknown option: " + n);
   PHZ_CATCH
 }

@@ -443,8 +443,9 @@ struct Pipeline {
   Buf<B, u64> p_key, p_key2; Buf<B, u32> p_val, p_val2, p_flag, p_scan, pe_start;
   Buf<B, u32> x_flag, x_scan, x_acc;
   Buf<B, u32> ed_a, ed_b, ed_sup, ed_tot, ed_n9; Buf<B, u8> ed_cfg, ed_keep;
-  Buf<B, u32> scalars, kstar_d;                     // scalars: [0]=max_tot [1]=err flags [2]=dropped
-  int64_t NX = 0, E = 0; u32 max_tot = 0;
+  Buf<B, u32> scalars, kstar_d;                     // scalars: [0]=max_tot [1]=err flags [2]=dropped [3]=n_big_tot
+  Buf<B, u32> big_tot;                              // c_total values above big_total_thr (unordered, with repeats)
+  int64_t NX = 0, E = 0; u32 max_tot = 0; int64_t NBT = 0; u32 big_total_thr = 2048;
   // ------------------------------------------------------------------ blocks
   Buf<B, u32> parent, deg, root, m_flag, m_scan, m_list, m_key, m_key2, m_val2, members;
   Buf<B, u32> b_flag, b_scan, blk_off, blk_of, pos_in_blk, blk_contig_rank, blk_order, blk_pos;
@@ -949,6 +950,8 @@ struct Pipeline {
     u32* ea_ = ed_a.ensure(E); u32* eb_ = ed_b.ensure(E); u32* esup = ed_sup.ensure(E); u32* etot = ed_tot.ensure(E);
     u32* en9 = ed_n9.ensure(E * 9); u8* ecfg = ed_cfg.ensure(E); ed_keep.ensure(E);
     u32* sc = scalars.ensure(8); be.memset0(sc, 8 * sizeof(u32));
+    // totals above the threshold go to a side list: the host needs a critical value for each distinct one
+    u32* bt = big_tot.ensure(E); const u32 bthr = big_total_thr;
     be.for_each(NX, PHZ_LAMBDA(int64_t x) {
       if (!xf[x]) return;
       u32 e = xs[x];
@@ -962,8 +965,11 @@ struct Pipeline {
       esup[e] = sup; etot[e] = tot;
       ecfg[e] = (u8)(cis > trans ? EDGE_CIS : (cis < trans ? EDGE_TRANS : EDGE_TIE));
       if (tot > load_volatile(&sc[0])) atomic_max(&sc[0], tot);
+      if (tot > bthr) bt[atomic_add(&sc[3], 1u)] = tot;
     });
-    max_tot = E > 0 ? fetch_u32(sc) : 0;
+    u32 hsc[4] = {0, 0, 0, 0};
+    if (E > 0) be.d2h(hsc, sc, sizeof(hsc));
+    max_tot = hsc[0]; NBT = hsc[3];
     be.stage("graph.end");
   }
 

@@ -217,6 +217,7 @@ def run_path(engine: Engine, vt: VariantTable, batches, params: PhaseParams, n_f
     worker = threading.Thread(target=lambda: pre.setdefault("k", critical_values(PRECOMPUTED_TOTALS, noise_e, params.cc_threshold)))
     worker.start()
     _t = time.perf_counter() if _TRACE else 0.0
+    engine.set_option("big_total_threshold", PRECOMPUTED_TOTALS)
     try:
         n_edges, max_tot = engine.build_graph(n_fragments, excl)
     finally:
@@ -226,14 +227,17 @@ def run_path(engine: Engine, vt: VariantTable, batches, params: PhaseParams, n_f
     kstar = np.zeros(int(max_tot) + 1, np.uint32)
     m = min(int(max_tot), PRECOMPUTED_TOTALS)
     kstar[:m + 1] = pre["k"][:m + 1]
+    n_big = 0
     if max_tot > PRECOMPUTED_TOTALS and n_edges > 0:
-        totals = engine.download("ed_tot")
-        big = totals[totals > PRECOMPUTED_TOTALS]
-        kstar = np.maximum(kstar, critical_values(int(max_tot), noise_e, params.cc_threshold, totals=big))
+        # the device kept the (few) totals above the precomputed range on a side list
+        big = np.unique(engine.download("big_tot")).astype(np.int64)
+        n_big = int(big.shape[0])
+        p = 1 - ((6 * noise_e) + (10 * math.pow(noise_e, 2)))
+        kstar[big] = _critical_values_at(big, p, params.cc_threshold)
     if _TRACE:
         _t3 = time.perf_counter()
-        print("[run_path] build_graph %.2f ms, join wait %.2f ms, kstar assembly %.2f ms (max_tot %d)" % (
-            (_t1 - _t) * 1e3, (_t2 - _t1) * 1e3, (_t3 - _t2) * 1e3, max_tot), file=sys.stderr)
+        print("[run_path] build_graph %.2f ms, join wait %.2f ms, kstar assembly %.2f ms (max_tot %d, %d distinct totals above %d)" % (
+            (_t1 - _t) * 1e3, (_t2 - _t1) * 1e3, (_t3 - _t2) * 1e3, max_tot, n_big, PRECOMPUTED_TOTALS), file=sys.stderr)
     nf, flags = engine.phase(kstar, params.max_block_size, excl)
     if flags & 2:
         raise PhaserFatal("a haplotype block cannot be split down to --max_block_size (the reference does not "

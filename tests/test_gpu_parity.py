@@ -173,3 +173,16 @@ def test_config1_shape_matches_reference_outputs(gpu, tmp_path):
     bad = compare.diff_outputs(ref, got)
     assert not bad, "\n".join(bad)
     assert res.counters["hard_blocks"] > 20
+
+
+def test_totals_above_the_precomputed_range_take_the_side_list(gpu, tmp_path, monkeypatch):
+    """Critical values of c_total values above pipeline.PRECOMPUTED_TOTALS come from the device's side list
+    (big_tot); with the range shrunk to 3 nearly every tested edge goes that way and nothing may change."""
+    from phaser_b200 import pipeline
+    vcf, sams = util.make_case(tmp_path, 36, 250, 2500, n_bams=2, switch_per_base=0.03)
+    exp, _ = util.oracle_outputs(vcf, sams, max_block_size=5)
+    monkeypatch.setattr(pipeline, "PRECOMPUTED_TOTALS", 3)
+    got, res, _ = util.product_outputs(gpu, vcf, sams, max_block_size=5)
+    bad = compare.diff_outputs(exp, got)
+    assert not bad, "\n".join(bad)
+    assert res.counters["edges"] > 0

@@ -41,6 +41,19 @@ def test_seeded_cases_match_oracle(hostsim, tmp_path, seed, n_bams, switch, mbs)
     assert abs(res.noise_e - ores.noise_e) == 0.0
 
 
+def test_totals_above_the_precomputed_range_take_the_side_list(hostsim, tmp_path, monkeypatch):
+    """Critical values of c_total values above pipeline.PRECOMPUTED_TOTALS come from the device's side list
+    (big_tot); with the range shrunk to 3 nearly every tested edge goes that way and nothing may change."""
+    from phaser_b200 import pipeline
+    vcf, sams = util.make_case(tmp_path, 36, 250, 2500, n_bams=2, switch_per_base=0.03)
+    exp, _ = util.oracle_outputs(vcf, sams, max_block_size=5)
+    monkeypatch.setattr(pipeline, "PRECOMPUTED_TOTALS", 3)
+    got, res, _ = util.product_outputs(hostsim, vcf, sams, max_block_size=5)
+    bad = compare.diff_outputs(exp, got)
+    assert not bad, "\n".join(bad)
+    assert res.counters["edges"] > 0
+
+
 def test_windowed_k1_logic_equals_generic(hostsim):
     """Slab selection + in-slab range search (shared with the CUDA kernel) against plain global search."""
     import numpy as np
