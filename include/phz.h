@@ -80,6 +80,42 @@ int phz_map_reads(phz_ctx* ctx, const phz_reads* reads, int baseq, double isize_
  * stream first.  This is the end-to-end entry point bench.py times. */
 int phz_map_reads_host(phz_ctx* ctx, const phz_reads* host_reads, int baseq, double isize_cutoff, int64_t* n_candidates);
 
+/* Lossless transport form of phz_reads for the host -> device copy (the copy is PCIe-bound: 146 bytes per 2x76 bp
+ * record as plain SoA, ~53 packed).  What shrinks: offsets become per-record counts (scanned on the device), bases
+ * become 2 bits (A C G T = 0..3) plus a sparse exception list for every other 4-bit code, base qualities become
+ * indices into the BAM's own table of distinct phred values (1, 2, 4 or 8 bits, whatever the data needs).
+ * Everything is expanded again on the device into the phz_reads layout K1 reads; nothing is thresholded or dropped. */
+typedef struct phz_packed_reads {
+  int64_t n_records;
+  int64_t n_cigar_ops;
+  int64_t n_bases;
+  const int64_t* h_contig_rec_off; /* n_contigs+1 */
+  const int32_t* pos;
+  const int32_t* tlen;
+  const int16_t* aln_score;
+  const uint32_t* frag;
+  const uint16_t* n_cigar;         /* CIGAR ops per record */
+  const uint16_t* l_seq;           /* bases per record */
+  const uint32_t* cigar;
+  const uint8_t* seq2;             /* (n_bases+3)/4 bytes; base i at bits 2*(i&3) of byte i>>2 */
+  int64_t n_exceptions;            /* bases whose code is not A/C/G/T (N, IUPAC, '='), ascending base index */
+  const uint64_t* exc_index;
+  const uint8_t* exc_code;         /* the original 4-bit code */
+  int32_t qual_bits;               /* 1, 2, 4 or 8 */
+  uint8_t qual_table[256];         /* index -> phred */
+  const uint8_t* qualp;            /* (n_bases*qual_bits+7)/8 bytes; base i at bit i*qual_bits, little-endian */
+} phz_packed_reads;
+typedef struct phz_packed_host phz_packed_host;
+/* Packs HOST arrays (n_threads host threads; output in page-locked memory when a CUDA device is present).  NULL +
+ * phz_last_error() when a record has more than 65535 CIGAR ops or bases: use phz_map_reads_host for such data. */
+phz_packed_host* phz_pack_reads(const phz_reads* host_reads, int n_contigs, int n_threads);
+int phz_packed_view(phz_packed_host* p, phz_packed_reads* out);
+int64_t phz_packed_bytes(phz_packed_host* p);
+void phz_packed_free(phz_packed_host* p);
+/* phz_map_reads with the packed HOST form: copies it to the device on the context's stream, expands it there and
+ * runs K1.  The end-to-end entry point bench.py times and the one the command line uses. */
+int phz_map_reads_packed(phz_ctx* ctx, const phz_packed_reads* packed, int baseq, double isize_cutoff, int64_t* n_candidates);
+
 /* Exact histogram of the alignment scores of the tuples the reference mapper would print; the host
  * derives numpy.percentile from it (phaser.py:545-553).  d_hist: PHZ_AS_BINS uint64 on the device. */
 int phz_as_histogram(phz_ctx* ctx, uint64_t* d_hist);

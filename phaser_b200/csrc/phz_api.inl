@@ -12,8 +12,11 @@ struct phz_ctx {
   // staging for phz_map_reads_host
   Buf<PHZ_BACKEND, int32_t> st_pos, st_tlen; Buf<PHZ_BACKEND, int16_t> st_as; Buf<PHZ_BACKEND, u32> st_frag, st_coff, st_cig;
   Buf<PHZ_BACKEND, u64> st_soff; Buf<PHZ_BACKEND, u8> st_seq, st_qual;
+  // packed transport (phz_map_reads_packed): what arrives over PCIe before it is expanded into st_*
+  Buf<PHZ_BACKEND, uint16_t> pk_ncg, pk_lsq; Buf<PHZ_BACKEND, u8> pk_seq2, pk_qualp, pk_exc, pk_qtab; Buf<PHZ_BACKEND, u64> pk_exi;
   phz_ctx() {
     PHZ_BACKEND* b = &p.be;
+    pk_ncg.bind(b); pk_lsq.bind(b); pk_seq2.bind(b); pk_qualp.bind(b); pk_exc.bind(b); pk_qtab.bind(b); pk_exi.bind(b);
     st_pos.bind(b); st_tlen.bind(b); st_as.bind(b); st_frag.bind(b); st_coff.bind(b); st_cig.bind(b); st_soff.bind(b);
     st_seq.bind(b); st_qual.bind(b);
   }
@@ -100,6 +103,71 @@ int phz_map_reads_host(phz_ctx* ctx, const phz_reads* h, int baseq, double isize
   be.h2d(ctx->st_soff.ensure(R + 1), h->seq_off, (R + 1) * 8); d.seq_off = (const uint64_t*)ctx->st_soff.p;
   be.h2d(ctx->st_seq.ensure((h->n_bases + 1) / 2), h->seq, (h->n_bases + 1) / 2); d.seq = ctx->st_seq.p;
   be.h2d(ctx->st_qual.ensure(h->n_bases), h->qual, h->n_bases); d.qual = ctx->st_qual.p;
+  ReadsView v = view_of(&d, ctx->p.nc);
+  *n_candidates = ctx->p.map_reads(v, h->h_contig_rec_off, baseq, isize_cutoff);
+  PHZ_CATCH
+}
+
+int phz_map_reads_packed(phz_ctx* ctx, const phz_packed_reads* h, int baseq, double isize_cutoff, int64_t* n_candidates) {
+  PHZ_TRY
+  auto& be = ctx->p.be;
+  const int64_t R = h->n_records, NB = h->n_bases, NC = h->n_cigar_ops, NX = h->n_exceptions;
+  const int bits = h->qual_bits;
+  if (bits != 1 && bits != 2 && bits != 4 && bits != 8) throw PhzError("phz_map_reads_packed: qual_bits must be 1, 2, 4 or 8");
+  phz_reads d; std::memset(&d, 0, sizeof(d));
+  d.n_records = R; d.n_cigar_ops = NC; d.n_bases = NB; d.h_contig_rec_off = h->h_contig_rec_off;
+  // ---- host -> device, packed
+  be.h2d(ctx->st_pos.ensure(R), h->pos, R * 4); d.pos = ctx->st_pos.p;
+  be.h2d(ctx->st_tlen.ensure(R), h->tlen, R * 4); d.tlen = ctx->st_tlen.p;
+  be.h2d(ctx->st_as.ensure(R), h->aln_score, R * 2); d.aln_score = ctx->st_as.p;
+  be.h2d(ctx->st_frag.ensure(R), h->frag, R * 4); d.frag = ctx->st_frag.p;
+  be.h2d(ctx->st_cig.ensure(NC), h->cigar, NC * 4); d.cigar = ctx->st_cig.p;
+  const uint16_t* ncg = ctx->pk_ncg.ensure(R); be.h2d(ctx->pk_ncg.p, h->n_cigar, R * 2);
+  const uint16_t* lsq = ctx->pk_lsq.ensure(R); be.h2d(ctx->pk_lsq.p, h->l_seq, R * 2);
+  const int64_t n2 = (NB + 3) / 4, nq = (NB * bits + 7) / 8;
+  const u8* s2 = ctx->pk_seq2.ensure(n2 + 16); be.h2d(ctx->pk_seq2.p, h->seq2, n2);
+  const u8* qp = ctx->pk_qualp.ensure(nq + 16); be.h2d(ctx->pk_qualp.p, h->qualp, nq);
+  const u64* exi = ctx->pk_exi.ensure(NX); be.h2d(ctx->pk_exi.p, h->exc_index, NX * 8);
+  const u8* exc = ctx->pk_exc.ensure(NX); be.h2d(ctx->pk_exc.p, h->exc_code, NX);
+  const u8* qt = ctx->pk_qtab.ensure(256); be.h2d(ctx->pk_qtab.p, h->qual_table, 256);
+  // ---- expand on the device into the phz_reads layout
+  be.stage("unpack");
+  be.exclusive_scan_u16_to_u32(ncg, ctx->st_coff.ensure(R + 1), R); d.cigar_off = ctx->st_coff.p;
+  be.exclusive_scan_u16_to_u64(lsq, ctx->st_soff.ensure(R + 1), R); d.seq_off = (const uint64_t*)ctx->st_soff.p;
+  {   // bases: one logical thread per 16 bases = 4 packed bytes in, 8 bytes out (A C G T -> 1 2 4 8, even index = high nibble)
+    const int64_t nw = (NB + 15) / 16;
+    u64* out = (u64*)ctx->st_seq.ensure((size_t)nw * 8 + 16);
+    const u32* in32 = (const u32*)s2;
+    be.for_each(nw, PHZ_LAMBDA(int64_t w) {
+      u32 in = in32[w]; u64 o = 0;
+      for (int k = 0; k < 16; ++k) {
+        u64 nib = (u64)1 << ((in >> (2 * k)) & 3);
+        o |= nib << ((k >> 1) * 8 + ((k & 1) ? 0 : 4));
+      }
+      out[w] = o;
+    });
+    u32* words = (u32*)ctx->st_seq.p;
+    be.for_each(NX, PHZ_LAMBDA(int64_t e) {      // every other code (N, IUPAC, '='): patch the nibble
+      u64 i = exi[e]; u32 sh = (u32)(((i >> 1) & 3) * 8 + ((i & 1) ? 0 : 4));
+      atomic_and(&words[i >> 3], ~(0xFu << sh));
+      atomic_or(&words[i >> 3], (u32)exc[e] << sh);
+    });
+    d.seq = ctx->st_seq.p;
+  }
+  {   // base qualities: one logical thread per 8 bases = `bits` packed bytes in, 8 phred bytes out
+    const int64_t nw = (NB + 7) / 8;
+    u64* out = (u64*)ctx->st_qual.ensure((size_t)nw * 8 + 16);
+    const u32 mask = (1u << bits) - 1;
+    be.for_each(nw, PHZ_LAMBDA(int64_t w) {
+      u64 in = 0;
+      for (int j = 0; j < bits; ++j) in |= (u64)qp[w * bits + j] << (8 * j);
+      u64 o = 0;
+      for (int k = 0; k < 8; ++k) o |= (u64)qt[(in >> (k * bits)) & mask] << (8 * k);
+      out[w] = o;
+    });
+    d.qual = ctx->st_qual.p;
+  }
+  be.stage("unpack.end");
   ReadsView v = view_of(&d, ctx->p.nc);
   *n_candidates = ctx->p.map_reads(v, h->h_contig_rec_off, baseq, isize_cutoff);
   PHZ_CATCH

@@ -32,6 +32,7 @@ PHZ_HD uint32_t atomic_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
 PHZ_HD unsigned long long atomic_min(unsigned long long* p, unsigned long long v) { return atomicMin(p, v); }
 PHZ_HD uint32_t atomic_max(uint32_t* p, uint32_t v) { return atomicMax(p, v); }
 PHZ_HD uint32_t atomic_or(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
+PHZ_HD uint32_t atomic_and(uint32_t* p, uint32_t v) { return atomicAnd(p, v); }
 PHZ_HD uint32_t atomic_cas(uint32_t* p, uint32_t cmp, uint32_t v) { return atomicCAS(p, cmp, v); }
 PHZ_HD uint32_t load_volatile(const uint32_t* p) { return *((const volatile uint32_t*)p); }
 #else
@@ -39,6 +40,7 @@ template <class T> inline T atomic_add(T* p, T v) { T o = *p; *p = o + v; return
 template <class T> inline T atomic_min(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
 template <class T> inline T atomic_max(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
 inline uint32_t atomic_or(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
+inline uint32_t atomic_and(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o & v; return o; }
 inline uint32_t atomic_cas(uint32_t* p, uint32_t cmp, uint32_t v) { uint32_t o = *p; if (o == cmp) *p = v; return o; }
 inline uint32_t load_volatile(const uint32_t* p) { return *p; }
 #endif
@@ -88,8 +90,11 @@ struct PhzError : public std::runtime_error {
 // =============================================================================== CUDA backend
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
+#include <thrust/iterator/transform_iterator.h>
 
 namespace phz {
+
+template <class T> struct Widen { __host__ __device__ T operator()(uint16_t x) const { return (T)x; } };
 
 #define PHZ_CUDA(call)                                                                      \
   do {                                                                                      \
@@ -162,6 +167,16 @@ struct DeviceBackend {
     return p;
   }
   void free(void* p) { if (p) cudaFree(p); }
+  // page-locked host memory for transport buffers; plain malloc when no device is usable (ingest-only use of the library)
+  static void* host_alloc(size_t bytes, bool* pinned) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 16;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) { *pinned = true; return p; }
+    cudaGetLastError();
+    *pinned = false;
+    return std::malloc(bytes);
+  }
+  static void host_free(void* p, bool pinned) { if (!p) return; if (pinned) cudaFreeHost(p); else std::free(p); }
   void memset0(void* p, size_t bytes) { if (bytes) PHZ_CUDA(cudaMemsetAsync(p, 0, bytes, stream)); }
   void memset_ff(void* p, size_t bytes) { if (bytes) PHZ_CUDA(cudaMemsetAsync(p, 0xFF, bytes, stream)); }
   void h2d(void* dst, const void* src, size_t bytes) {
@@ -213,6 +228,32 @@ struct DeviceBackend {
     PHZ_CUDA(cub::DeviceScan::ExclusiveSum(t, bytes, in, out, (int)n, stream));
     lib_launches += 2;
     const u32* in_c = in; u32* out_c = out; int64_t nn = n;
+    for_each(1, [=] __device__(int64_t) { out_c[nn] = out_c[nn - 1] + in_c[nn - 1]; });
+  }
+
+  // out[i] = sum_{j<i} (u64)in[j] for i in [0, n]; out has n+1 slots
+  void exclusive_scan_u16_to_u64(const uint16_t* in, u64* out, int64_t n) {
+    memset0(out + n, sizeof(u64));
+    if (n <= 0) return;
+    thrust::transform_iterator<Widen<u64>, const uint16_t*> it(in, Widen<u64>());
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, out, (int)n, stream);
+    void* t = tmp(bytes + 16);
+    PHZ_CUDA(cub::DeviceScan::ExclusiveSum(t, bytes, it, out, (int)n, stream));
+    lib_launches += 2;
+    const uint16_t* in_c = in; u64* out_c = out; int64_t nn = n;
+    for_each(1, [=] __device__(int64_t) { out_c[nn] = out_c[nn - 1] + in_c[nn - 1]; });
+  }
+  void exclusive_scan_u16_to_u32(const uint16_t* in, u32* out, int64_t n) {
+    memset0(out + n, sizeof(u32));
+    if (n <= 0) return;
+    thrust::transform_iterator<Widen<u32>, const uint16_t*> it(in, Widen<u32>());
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, out, (int)n, stream);
+    void* t = tmp(bytes + 16);
+    PHZ_CUDA(cub::DeviceScan::ExclusiveSum(t, bytes, it, out, (int)n, stream));
+    lib_launches += 2;
+    const uint16_t* in_c = in; u32* out_c = out; int64_t nn = n;
     for_each(1, [=] __device__(int64_t) { out_c[nn] = out_c[nn - 1] + in_c[nn - 1]; });
   }
 
@@ -279,6 +320,18 @@ struct HostSimBackend {
     for (int64_t i = 0; i < n; ++i) { u32 v = in[i]; out[i] = s; s += v; }
     out[n] = s;
   }
+  void exclusive_scan_u16_to_u64(const uint16_t* in, u64* out, int64_t n) {
+    u64 s = 0;
+    for (int64_t i = 0; i < n; ++i) { out[i] = s; s += in[i]; }
+    out[n] = s;
+  }
+  void exclusive_scan_u16_to_u32(const uint16_t* in, u32* out, int64_t n) {
+    u32 s = 0;
+    for (int64_t i = 0; i < n; ++i) { out[i] = s; s += in[i]; }
+    out[n] = s;
+  }
+  static void* host_alloc(size_t bytes, bool* pinned) { *pinned = false; return std::malloc(bytes ? bytes : 16); }
+  static void host_free(void* p, bool) { std::free(p); }
   template <class K, class V>
   void sort_impl(K* keys_in, K* keys_out, V* vals_in, V* vals_out, int64_t n, int begin_bit, int end_bit) {
     std::vector<int64_t> idx(n);

@@ -8,6 +8,7 @@
 // VCF, -F 0x400 iff remove_dups, -f 2 iff paired_end, -q MAPQ.  Fragment ids: one per distinct QNAME,
 // shared by all BAMs of a run (exact: names are compared, not just hashed).
 #include <zlib.h>
+#include <array>
 #include <thread>
 #include <mutex>
 #include <exception>
@@ -531,5 +532,112 @@ int phz_write_sam(const char* path, const char* const* contig_names, const int64
   std::fclose(f);
   PHZ_CATCH
 }
+
+}  // extern "C"
+
+// =============================================================================== packed transport (include/phz.h)
+// Host side of phz_packed_reads: offsets -> per-record counts, 4-bit bases -> 2 bits + exception list, phred bytes ->
+// indices into the table of distinct values.  Lossless; expanded again on the device by phz_map_reads_packed.
+struct phz_packed_host {
+  phz_packed_reads v;
+  std::vector<std::pair<void*, bool>> bufs;      // (pointer, page-locked)
+  std::vector<int64_t> contig_off;
+  int64_t bytes = 0;
+  template <class T> T* alloc(size_t n) {
+    bool pinned = false;
+    void* p = PHZ_BACKEND::host_alloc((n ? n : 1) * sizeof(T), &pinned);
+    if (!p) throw PhzError("out of host memory for the packed transport buffers");
+    bufs.emplace_back(p, pinned);
+    bytes += (int64_t)(n * sizeof(T));
+    return (T*)p;
+  }
+  ~phz_packed_host() { for (auto& b : bufs) PHZ_BACKEND::host_free(b.first, b.second); }
+};
+
+extern "C" {
+
+phz_packed_host* phz_pack_reads(const phz_reads* h, int n_contigs, int n_threads) {
+  phz_packed_host* P = nullptr;
+  try {
+    if (n_threads < 1) n_threads = 1;
+    const int64_t R = h->n_records, NB = h->n_bases, NCG = h->n_cigar_ops;
+    for (int64_t r = 0; r < R; ++r) {
+      if (h->cigar_off[r + 1] - h->cigar_off[r] > 65535u || h->seq_off[r + 1] - h->seq_off[r] > 65535ull)
+        throw PhzError("record " + std::to_string(r) + " has more than 65535 CIGAR operations or bases: not packable");
+    }
+    P = new phz_packed_host();
+    phz_packed_reads& v = P->v;
+    std::memset(&v, 0, sizeof(v));
+    v.n_records = R; v.n_cigar_ops = NCG; v.n_bases = NB;
+    P->contig_off.assign(h->h_contig_rec_off, h->h_contig_rec_off + n_contigs + 1);
+    v.h_contig_rec_off = P->contig_off.data();
+    int32_t* pos = P->alloc<int32_t>(R); int32_t* tlen = P->alloc<int32_t>(R); int16_t* as = P->alloc<int16_t>(R);
+    uint32_t* frag = P->alloc<uint32_t>(R); uint16_t* ncg = P->alloc<uint16_t>(R); uint16_t* lsq = P->alloc<uint16_t>(R);
+    uint32_t* cig = P->alloc<uint32_t>(NCG);
+    const size_t CH = 1 << 20;
+    phzio::parallel_for((R + CH - 1) / CH, n_threads, [&](size_t c) {
+      int64_t r0 = (int64_t)(c * CH), r1 = std::min<int64_t>(R, r0 + CH);
+      std::memcpy(pos + r0, h->pos + r0, (r1 - r0) * 4); std::memcpy(tlen + r0, h->tlen + r0, (r1 - r0) * 4);
+      std::memcpy(as + r0, h->aln_score + r0, (r1 - r0) * 2); std::memcpy(frag + r0, h->frag + r0, (r1 - r0) * 4);
+      for (int64_t r = r0; r < r1; ++r) {
+        ncg[r] = (uint16_t)(h->cigar_off[r + 1] - h->cigar_off[r]); lsq[r] = (uint16_t)(h->seq_off[r + 1] - h->seq_off[r]);
+      }
+    });
+    phzio::parallel_for((NCG + CH - 1) / CH, n_threads, [&](size_t c) {
+      int64_t i0 = (int64_t)(c * CH), i1 = std::min<int64_t>(NCG, i0 + CH);
+      std::memcpy(cig + i0, h->cigar + i0, (i1 - i0) * 4);
+    });
+    v.pos = pos; v.tlen = tlen; v.aln_score = as; v.frag = frag; v.n_cigar = ncg; v.l_seq = lsq; v.cigar = cig;
+    // ---- bases: 2 bits + exceptions.  Chunks are multiples of 4 bases so that no output byte is shared.
+    const size_t nchunks = (size_t)((NB + (int64_t)CH - 1) / (int64_t)CH);
+    uint8_t* s2 = P->alloc<uint8_t>((NB + 3) / 4);
+    std::vector<std::vector<std::pair<u64, u8>>> exc(nchunks);
+    std::vector<std::array<u64, 256>> hist(nchunks);
+    phzio::parallel_for(nchunks, n_threads, [&](size_t c) {
+      int64_t b0 = (int64_t)(c * CH), b1 = std::min<int64_t>(NB, b0 + (int64_t)CH);
+      auto& hh = hist[c]; hh.fill(0);
+      auto& ex = exc[c];
+      for (int64_t b = b0; b < b1; b += 4) {
+        u8 out = 0;
+        for (int k = 0; k < 4 && b + k < b1; ++k) {
+          int64_t i = b + k;
+          u8 code = (h->seq[i >> 1] >> ((i & 1) ? 0 : 4)) & 15;
+          u8 two;
+          switch (code) { case 1: two = 0; break; case 2: two = 1; break; case 4: two = 2; break; case 8: two = 3; break;
+                          default: two = 0; ex.emplace_back((u64)i, code); }
+          out |= (u8)(two << (2 * k));
+        }
+        s2[b >> 2] = out;
+      }
+      for (int64_t b = b0; b < b1; ++b) hh[h->qual[b]]++;
+    });
+    int64_t nex = 0; for (auto& e : exc) nex += (int64_t)e.size();
+    uint64_t* exi = P->alloc<uint64_t>(nex); uint8_t* exc_code = P->alloc<uint8_t>(nex);
+    { int64_t o = 0; for (auto& e : exc) for (auto& x : e) { exi[o] = x.first; exc_code[o] = x.second; ++o; } }
+    v.seq2 = s2; v.n_exceptions = nex; v.exc_index = exi; v.exc_code = exc_code;
+    // ---- base qualities: table of distinct values, index width = what the data needs
+    u64 tot[256]; for (int q = 0; q < 256; ++q) { tot[q] = 0; for (auto& hh : hist) tot[q] += hh[q]; }
+    u8 index_of[256]; int nd = 0;
+    for (int q = 0; q < 256; ++q) { index_of[q] = 0; if (tot[q]) { index_of[q] = (u8)nd; v.qual_table[nd] = (u8)q; nd++; } }
+    int bits = nd <= 2 ? 1 : nd <= 4 ? 2 : nd <= 16 ? 4 : 8;
+    v.qual_bits = bits;
+    uint8_t* qp = P->alloc<uint8_t>((size_t)((NB * bits + 7) / 8));
+    const int per = 8 / bits;                   // bases per packed byte
+    phzio::parallel_for(nchunks, n_threads, [&](size_t c) {
+      int64_t b0 = (int64_t)(c * CH), b1 = std::min<int64_t>(NB, b0 + (int64_t)CH);     // CH is a multiple of 8
+      for (int64_t b = b0; b < b1; b += per) {
+        u8 out = 0;
+        for (int k = 0; k < per && b + k < b1; ++k) out |= (u8)(index_of[h->qual[b + k]] << (k * bits));
+        qp[b / per] = out;
+      }
+    });
+    v.qualp = qp;
+    return P;
+  } catch (const std::exception& e) { g_err = e.what(); delete P; return nullptr; }
+}
+
+int phz_packed_view(phz_packed_host* p, phz_packed_reads* out) { PHZ_TRY *out = p->v; PHZ_CATCH }
+int64_t phz_packed_bytes(phz_packed_host* p) { return p->bytes; }
+void phz_packed_free(phz_packed_host* p) { delete p; }
 
 }  // extern "C"

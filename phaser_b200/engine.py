@@ -31,13 +31,22 @@ class phz_reads(ctypes.Structure):
                 ("seq", c_void_p), ("qual", c_void_p)]
 
 
+class phz_packed_reads(ctypes.Structure):
+    _fields_ = [("n_records", c_int64), ("n_cigar_ops", c_int64), ("n_bases", c_int64), ("h_contig_rec_off", c_void_p),
+                ("pos", c_void_p), ("tlen", c_void_p), ("aln_score", c_void_p), ("frag", c_void_p), ("n_cigar", c_void_p),
+                ("l_seq", c_void_p), ("cigar", c_void_p), ("seq2", c_void_p), ("n_exceptions", c_int64),
+                ("exc_index", c_void_p), ("exc_code", c_void_p), ("qual_bits", c_int32), ("qual_table", ctypes.c_uint8 * 256),
+                ("qualp", c_void_p)]
+
+
 EXPORTS = ["phz_last_error", "phz_backend_name", "phz_create", "phz_destroy", "phz_sync", "phz_set_variants",
            "phz_map_reads", "phz_map_reads_host", "phz_as_histogram", "phz_commit_bam", "phz_variant_stats", "phz_build_graph",
            "phz_phase", "phz_read_lists", "phz_array", "phz_download", "phz_counters", "phz_launch_counts",
            "phz_set_profiling", "phz_map_times", "phz_stage_report", "phz_set_option",
            "phz_fragdict_create", "phz_fragdict_destroy", "phz_fragdict_size", "phz_fragdict_name", "phz_read_alignments",
            "phz_host_reads_view", "phz_host_reads_free", "phz_set_haplo_blacklist", "phz_write_sam",
-           "phz_set_indel_alleles"]
+           "phz_set_indel_alleles", "phz_pack_reads", "phz_packed_view", "phz_packed_bytes", "phz_packed_free",
+           "phz_map_reads_packed"]
 
 
 def _declare(lib):
@@ -76,6 +85,13 @@ def _declare(lib):
     lib.phz_host_reads_free.argtypes = [c_void_p]
     lib.phz_set_haplo_blacklist.argtypes = [c_void_p, c_void_p]
     lib.phz_set_indel_alleles.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.phz_pack_reads.restype = c_void_p
+    lib.phz_pack_reads.argtypes = [POINTER(phz_reads), c_int, c_int]
+    lib.phz_packed_view.argtypes = [c_void_p, POINTER(phz_packed_reads)]
+    lib.phz_packed_bytes.restype = c_int64
+    lib.phz_packed_bytes.argtypes = [c_void_p]
+    lib.phz_packed_free.argtypes = [c_void_p]
+    lib.phz_map_reads_packed.argtypes = [c_void_p, POINTER(phz_packed_reads), c_int, c_double, POINTER(c_int64)]
     return lib
 
 
@@ -149,6 +165,43 @@ def write_sam_native(rec, contigs, path, bam_name="bam0", lib=None):
     if rc != 0:
         raise PhzError(lib.phz_last_error().decode())
     return path
+
+
+class PackedReads:
+    """One BAM in the packed transport form (include/phz.h: phz_packed_reads), in page-locked host memory owned by
+    the native library.  Built once at ingest; phz_map_reads_packed copies it to the device and expands it there."""
+
+    def __init__(self, lib, handle):
+        self.lib = lib; self.h = handle
+        self.view = phz_packed_reads()
+        if lib.phz_packed_view(handle, byref(self.view)) != 0:
+            raise PhzError(lib.phz_last_error().decode())
+        self.nbytes = int(lib.phz_packed_bytes(handle))
+        self.n_records = int(self.view.n_records)
+        self.qual_bits = int(self.view.qual_bits)
+        self.n_exceptions = int(self.view.n_exceptions)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.phz_packed_free(self.h); self.h = None
+        except Exception:
+            pass
+
+
+def pack_reads(reads, n_contigs, threads=0, lib=None) -> PackedReads:
+    """`reads`: ReadBatch or dict of host arrays (numpy / CPU tensors) in the phz_reads layout."""
+    lib = lib if lib is not None else load_library()
+    if isinstance(reads, ReadBatch):
+        reads = dict(contig_rec_off=np.ascontiguousarray(reads.contig_rec_off, dtype=np.int64), pos=reads.pos, tlen=reads.tlen,
+                     aln_score=reads.aln_score, frag=reads.frag, cigar_off=reads.cigar_off, cigar=reads.cigar,
+                     seq_off=reads.seq_off, seq=reads.seq, qual=reads.qual)
+    reads = {k: (np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v) for k, v in reads.items()}
+    r = Engine._reads_struct(reads)
+    h = lib.phz_pack_reads(byref(r), int(n_contigs), int(threads or (os.cpu_count() or 1)))
+    if not h:
+        raise PhzError(lib.phz_last_error().decode())
+    return PackedReads(lib, h)
 
 
 class _NativeReads:
@@ -288,6 +341,13 @@ class Engine:
         r = self._reads_struct(host_reads)
         n = c_int64(0)
         self._check(self.lib.phz_map_reads_host(self.ctx, byref(r), int(baseq), float(isize_cutoff), byref(n)))
+        return n.value
+
+    def map_reads_packed(self, packed: PackedReads, baseq, isize_cutoff):
+        """packed host form -> device (copies + expansion inside the call) -> K1"""
+        self._cur = None
+        n = c_int64(0)
+        self._check(self.lib.phz_map_reads_packed(self.ctx, byref(packed.view), int(baseq), float(isize_cutoff), byref(n)))
         return n.value
 
     def as_histogram(self):

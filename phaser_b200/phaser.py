@@ -175,7 +175,7 @@ def run(args, engine=None):
     if engine is None:
         from phaser_b200.engine import Engine
         engine = Engine(device=args.device)
-    from phaser_b200.engine import NativeFragmentDictionary, read_alignments_native, PhzError
+    from phaser_b200.engine import NativeFragmentDictionary, read_alignments_native, PhzError, pack_reads
     fd = NativeFragmentDictionary(engine.lib)
     batches = []
     for i, bam in enumerate(bam_list):
@@ -186,7 +186,10 @@ def run(args, engine=None):
                                         min_mapq=mapq[i], threads=max(1, args.threads), lib=engine.lib)
         except PhzError as e:
             fatal_error(str(e))
-        batches.append(engine.upload_reads(rb))
+        try:        # packed transport form (page-locked): copied and expanded on the device inside run_path
+            batches.append(pack_reads(rb, len(vt.contigs), threads=max(1, args.threads), lib=engine.lib))
+        except PhzError:            # a record beyond 65535 CIGAR ops / bases: plain arrays
+            batches.append(engine.upload_reads(rb))
         del rb
     P = pipeline.PhaseParams(baseq=args.baseq, isize=isize, as_q_cutoff=args.as_q_cutoff, cc_threshold=args.cc_threshold,
                              max_block_size=args.max_block_size, haplo_count_bam_exclude=exclude,

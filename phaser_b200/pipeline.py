@@ -19,7 +19,7 @@ from typing import List, Optional
 
 import numpy as np
 
-from .engine import Engine, AS_BINS
+from .engine import Engine, AS_BINS, PackedReads
 from .layout import ReadBatch, VariantTable, AS_MISSING
 from .vcfio import PhaserFatal
 
@@ -182,8 +182,9 @@ RESULT_ARRAYS = ["vfirst", "ncls", "setsize", "vb_cnt", "ed_a", "ed_b", "ed_sup"
 
 def run_path(engine: Engine, vt: VariantTable, batches, params: PhaseParams, n_fragments: int, comm=None,
              host_inputs=False, download=True) -> PhaseResult:
-    """`batches`: per BAM either a dict of device tensors (Engine.upload_reads) or, with host_inputs,
-    a dict of host arrays that phz_map_reads_host copies to the device itself."""
+    """`batches`: per BAM a dict of device tensors (Engine.upload_reads), a PackedReads (host, packed transport
+    form: phz_map_reads_packed copies and expands it) or, with host_inputs, a dict of plain host arrays
+    (phz_map_reads_host copies them)."""
     comm = comm or NullComm()
     nb = len(batches)
     isz = list(params.isize) * nb if len(params.isize) == 1 else list(params.isize)
@@ -191,8 +192,12 @@ def run_path(engine: Engine, vt: VariantTable, batches, params: PhaseParams, n_f
     engine.set_variants(vt)
     cutoffs, kept, cands = [], [], []
     for b, reads in enumerate(batches):
-        n_cand = engine.map_reads_host(reads, params.baseq, isz[b]) if host_inputs else \
-            engine.map_reads(reads, params.baseq, isz[b])
+        if isinstance(reads, PackedReads):          # packed transport form in host memory
+            n_cand = engine.map_reads_packed(reads, params.baseq, isz[b])
+        elif host_inputs:
+            n_cand = engine.map_reads_host(reads, params.baseq, isz[b])
+        else:
+            n_cand = engine.map_reads(reads, params.baseq, isz[b])
         cands.append(n_cand)
         cutoff = None
         if params.as_q_cutoff > 0:

@@ -186,3 +186,32 @@ def test_totals_above_the_precomputed_range_take_the_side_list(gpu, tmp_path, mo
     bad = compare.diff_outputs(exp, got)
     assert not bad, "\n".join(bad)
     assert res.counters["edges"] > 0
+
+
+@pytest.mark.parametrize("n_quals,expect_bits", [(2, 1), (4, 2), (11, 4), (40, 8)])
+def test_packed_transport_is_lossless(gpu, tmp_path, n_quals, expect_bits):
+    """phz_map_reads_packed (H2D of the packed form + expansion kernels + K1) == phz_map_reads on the plain arrays."""
+    vcf, sams = util.make_case(tmp_path, 41, 300, 20000, n_bams=1)
+    vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+    b = batches[0]
+    rng = np.random.default_rng(n_quals)
+    b.qual = rng.choice(np.arange(2, 2 + 2 * n_quals, 2), size=b.qual.shape[0]).astype(np.uint8)
+    seq = b.seq.copy()
+    hit = rng.random(seq.shape[0]) < 0.02
+    seq[hit] = rng.integers(0, 256, size=int(hit.sum()), dtype=np.uint8)
+    b.seq = seq
+    p = util.packed_vs_plain(gpu, vt, b, len(vt.contigs))
+    assert p.qual_bits == expect_bits and p.n_exceptions > 0
+
+
+def test_packed_host_form_through_the_whole_path(gpu, tmp_path):
+    """run_path fed with PackedReads (what the command line does) == run_path on uploaded arrays."""
+    from phaser_b200 import pipeline, engine as eng
+    vcf, sams = util.make_case(tmp_path, 42, 300, 6000, n_bams=2, switch_per_base=0.02)
+    vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+    P = pipeline.PhaseParams()
+    a = pipeline.run_path(gpu, vt, [gpu.upload_reads(b) for b in batches], P, n_fragments=len(fd.names))
+    b = pipeline.run_path(gpu, vt, [eng.pack_reads(x, len(vt.contigs), lib=gpu.lib) for x in batches], P, n_fragments=len(fd.names))
+    assert a.counters == b.counters
+    for k in a.arrays:
+        assert np.array_equal(a.arrays[k], b.arrays[k]), k

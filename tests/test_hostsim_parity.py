@@ -1,6 +1,7 @@
 """Build-container logic tests: the product's pipeline source compiled against the host-simulation
 backend (tests/hostsim) must reproduce the reference fixtures and the oracle on seeded inputs.
 The same assertions run on the real CUDA library in tests/test_gpu_parity.py."""
+import numpy as np
 import pytest
 
 from oracle import compare
@@ -91,3 +92,32 @@ def test_wgs_plus_rna_joint_matches_oracle(hostsim, tmp_path):
     bad = compare.diff_outputs(exp, got)
     assert not bad, "\n".join(bad)
     assert res.counters["n_tuples"] == ores.total_tuples > 3000
+
+
+@pytest.mark.parametrize("n_quals,expect_bits", [(2, 1), (3, 2), (4, 2), (11, 4), (16, 4), (40, 8)])
+def test_packed_transport_is_lossless(hostsim, tmp_path, n_quals, expect_bits):
+    """Every index width of the quality table, bases outside A/C/G/T (N, IUPAC, '=') through the exception list."""
+    vcf, sams = util.make_case(tmp_path, 41, 200, 1500, n_bams=1)
+    vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+    b = batches[0]
+    rng = np.random.default_rng(n_quals)
+    b.qual = rng.choice(np.arange(2, 2 + 2 * n_quals, 2), size=b.qual.shape[0]).astype(np.uint8)     # around baseq = 10
+    seq = b.seq.copy()
+    hit = rng.random(seq.shape[0]) < 0.02
+    seq[hit] = rng.integers(0, 256, size=int(hit.sum()), dtype=np.uint8)                           # any pair of 4-bit codes
+    b.seq = seq
+    p = util.packed_vs_plain(hostsim, vt, b, len(vt.contigs))
+    assert p.qual_bits == expect_bits and p.n_exceptions > 0
+    plain_bytes = sum(a.nbytes for a in (b.pos, b.tlen, b.aln_score, b.frag, b.cigar_off, b.cigar, b.seq_off, b.seq, b.qual))
+    assert p.nbytes < plain_bytes * (0.5 if expect_bits == 1 else 1.0)      # 4 % exceptions here cost 9 bytes each
+
+
+def test_packed_transport_refuses_oversized_records(hostsim):
+    from phaser_b200 import engine as eng
+    from phaser_b200.layout import ReadBatch
+    n = 70000
+    b = ReadBatch(1, np.array([0, 1], np.int64), np.array([5], np.int32), np.zeros(1, np.int32), np.zeros(1, np.int16),
+                  np.zeros(1, np.uint32), np.array([0, 1], np.uint32), np.array([n << 4], np.uint32), np.array([0, n], np.uint64),
+                  np.full((n + 1) // 2, 0x11, np.uint8), np.full(n, 30, np.uint8), None)
+    with pytest.raises(eng.PhzError, match="not packable"):
+        eng.pack_reads(b, 1, lib=hostsim.lib)

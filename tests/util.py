@@ -137,3 +137,18 @@ def compare_tuples(engine, vt, batch, baseq=10, isize=0.0):
         c = info["alleles"].index(s) if s in info["alleles"] else 2
         exp.append((r, min(si, 255), v, c, 1 if len(s) > 1 else 0, port.BASES.index(s[0]), a))
     return got, exp
+
+
+def packed_vs_plain(engine, vt, batch, n_contigs):
+    """K1 through the packed transport form must emit exactly the tuples of the plain arrays."""
+    from phaser_b200 import engine as eng
+    engine.set_variants(vt)
+    engine.map_reads(engine.upload_reads(batch), 10, 0.0)
+    plain = [engine.download(k).copy() for k in ("t_rec", "t_var", "t_misc")]
+    packed = eng.pack_reads(batch, n_contigs, threads=3, lib=engine.lib)
+    n = engine.map_reads_packed(packed, 10, 0.0)
+    got = [engine.download(k).copy() for k in ("t_rec", "t_var", "t_misc")]
+    assert n == plain[0].shape[0]
+    for a, b in zip(plain, got):
+        assert np.array_equal(a, b)
+    return packed
