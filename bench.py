@@ -236,6 +236,12 @@ def run_ours(a):
                "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3,
                "host_form": "packed transport (lossless): per-record counts instead of offsets, 2-bit bases + %d exceptions, "
                             "%d-bit base-quality indices; expanded on the device" % (packed.n_exceptions, packed.qual_bits)}
+        if a.profile:
+            E.set_profiling(2)
+            t0 = time.perf_counter(); step(True, packed); torch.cuda.synchronize(); wall = (time.perf_counter() - t0) * 1e3
+            e2e["stages_ms"] = {k: round(v, 3) for k, v in E.stage_report().items()}
+            e2e["stages_ms"]["wall_ms"] = round(wall, 3)
+            E.set_profiling(1)
         del packed
         # for comparison: the same call with the plain SoA arrays (phz_map_reads_host), 2 timed steps
         def to_host(v):

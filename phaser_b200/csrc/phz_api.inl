@@ -117,6 +117,7 @@ int phz_map_reads_packed(phz_ctx* ctx, const phz_packed_reads* h, int baseq, dou
   phz_reads d; std::memset(&d, 0, sizeof(d));
   d.n_records = R; d.n_cigar_ops = NC; d.n_bases = NB; d.h_contig_rec_off = h->h_contig_rec_off;
   // ---- host -> device, packed
+  be.stage("h2d");
   be.h2d(ctx->st_pos.ensure(R), h->pos, R * 4); d.pos = ctx->st_pos.p;
   be.h2d(ctx->st_tlen.ensure(R), h->tlen, R * 4); d.tlen = ctx->st_tlen.p;
   be.h2d(ctx->st_as.ensure(R), h->aln_score, R * 2); d.aln_score = ctx->st_as.p;

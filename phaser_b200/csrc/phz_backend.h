@@ -368,6 +368,7 @@ struct Buf {
   // contents are NOT preserved
   T* ensure(size_t n) {
     if (n > cap) {
+      if (!be) throw PhzError("internal: buffer used before it was bound to a backend");
       if (p) { be->sync(); be->free(p); }
       cap = n + n / 8 + 64;
       p = (T*)be->alloc(cap * sizeof(T));
@@ -377,6 +378,7 @@ struct Buf {
   // contents preserved
   T* grow(size_t n, size_t used) {
     if (n > cap) {
+      if (!be) throw PhzError("internal: buffer used before it was bound to a backend");
       size_t ncap = n + n / 4 + 64;
       T* q = (T*)be->alloc(ncap * sizeof(T));
       if (p && used) be->d2d(q, p, used * sizeof(T));

@@ -473,7 +473,7 @@ struct Pipeline {
     grp_off.bind(b); pair_cnt.bind(b); pair_off.bind(b);
     p_key.bind(b); p_key2.bind(b); p_val.bind(b); p_val2.bind(b); p_flag.bind(b); p_scan.bind(b); pe_start.bind(b);
     x_flag.bind(b); x_scan.bind(b); x_acc.bind(b);
-    ed_a.bind(b); ed_b.bind(b); ed_sup.bind(b); ed_tot.bind(b); ed_n9.bind(b); ed_cfg.bind(b); ed_keep.bind(b); scalars.bind(b); kstar_d.bind(b);
+    ed_a.bind(b); ed_b.bind(b); ed_sup.bind(b); ed_tot.bind(b); ed_n9.bind(b); ed_cfg.bind(b); ed_keep.bind(b); scalars.bind(b); kstar_d.bind(b); big_tot.bind(b);
     parent.bind(b); deg.bind(b); root.bind(b); m_flag.bind(b); m_scan.bind(b); m_list.bind(b); m_key.bind(b); m_key2.bind(b);
     m_val2.bind(b); members.bind(b);
     b_flag.bind(b); b_scan.bind(b); blk_off.bind(b); blk_of.bind(b); pos_in_blk.bind(b); blk_contig_rank.bind(b);

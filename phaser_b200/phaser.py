@@ -119,6 +119,15 @@ def per_bam_lists(args, bam_list):
     return [int(x) for x in mapq], isize, [int(x) for x in paired]
 
 
+_TRACE = bool(os.environ.get("PHZ_TRACE"))
+
+
+def _trace(t0, what):
+    if _TRACE:
+        print("[phaser.py] %-28s %8.1f ms" % (what, (time.perf_counter() - t0) * 1e3), file=sys.stderr)
+    return time.perf_counter()
+
+
 def run(args, engine=None):
     say("")
     say("##################################################")
@@ -156,6 +165,7 @@ def run(args, engine=None):
     say('STARTED "Read backed phasing and ASE/haplotype analyses" ... ')
     say("    DATE, TIME : %s" % datetime.datetime.now().strftime('%Y-%m-%d, %H:%M:%S'))
     say("#1. Loading heterozygous variants into intervals...")
+    _t = time.perf_counter()
     try:
         vt, st = vcfio.parse_vcf(args.vcf, sample_column, pass_only=args.pass_only, chrom_of_interest=args.chr,
                                  chr_prefix=args.chr_prefix, id_separator=args.id_separator,
@@ -170,6 +180,7 @@ def run(args, engine=None):
     if st.het_count == 0:
         fatal_error("No heterozygous sites that passed all filters were included in the analysis, phASER cannot continue. Check blacklist and pass_only arguments.")
     say("#2. Retrieving reads that overlap heterozygous sites...")
+    _t = _trace(_t, "parse_vcf")
     mapq, isize, paired = per_bam_lists(args, bam_list)
     bam_names = bam_display_names(bam_list)
     if engine is None:
@@ -186,11 +197,15 @@ def run(args, engine=None):
                                         min_mapq=mapq[i], threads=max(1, args.threads), lib=engine.lib)
         except PhzError as e:
             fatal_error(str(e))
+        _t = _trace(_t, "read_alignments_native")
         try:        # packed transport form (page-locked): copied and expanded on the device inside run_path
+            if os.environ.get("PHZ_NO_PACK"):
+                raise PhzError("packing disabled")
             batches.append(pack_reads(rb, len(vt.contigs), threads=max(1, args.threads), lib=engine.lib))
         except PhzError:            # a record beyond 65535 CIGAR ops / bases: plain arrays
             batches.append(engine.upload_reads(rb))
         del rb
+        _t = _trace(_t, "pack / upload")
     P = pipeline.PhaseParams(baseq=args.baseq, isize=isize, as_q_cutoff=args.as_q_cutoff, cc_threshold=args.cc_threshold,
                              max_block_size=args.max_block_size, haplo_count_bam_exclude=exclude,
                              want_read_ids=(args.output_read_ids == 1), want_kept_tuples=(args.output_network != ""))
@@ -198,6 +213,7 @@ def run(args, engine=None):
         res = pipeline.run_path(engine, vt, batches, P, n_fragments=len(fd))
     except PhaserFatal as e:
         fatal_error(str(e))
+    _t = _trace(_t, "run_path (device)")
     for i, bam in enumerate(bam_list):
         if res.as_cutoff[i] is not None:
             say("          using alignment score cutoff of %d" % res.as_cutoff[i])
@@ -230,6 +246,7 @@ def run(args, engine=None):
         with open(args.o + ".network.nodes.txt", "w") as f:
             f.write(out.network[1])
     unphased_phased = phase_corrected = 0
+    _t = _trace(_t, "text tables")
     if args.write_vcf == 1:
         say("#7. Outputting phased VCF...")
         with gzip.open(args.vcf, "rt") as f:
@@ -238,6 +255,7 @@ def run(args, engine=None):
                 min_conf=args.gw_phase_vcf_min_confidence, chrom_of_interest=args.chr)
         with bgzf.BGZFWriter(args.o + ".vcf.gz") as f:       # what `bgzip -f` writes (phaser.py:1851)
             f.write(text)
+    _t = _trace(_t, "vcf out")
     total_time = time.time() - start_time
     say('')
     say("     COMPLETED using %d reads in %d seconds on %s" % (sum(res.tuples_per_bam), total_time, engine.backend))
