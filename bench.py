@@ -159,7 +159,7 @@ def run_ours(a):
 
     def step(host_inputs=False, src=None):
         return pipeline.run_path(E, vt, [src if src is not None else reads], P, n_fragments=n_pairs,
-                                 host_inputs=host_inputs, download=host_inputs)
+                                 host_inputs=host_inputs, download=host_inputs, reuse_result_buffer=True)
 
     E.set_profiling(1)
     for _ in range(a.warmup):

@@ -149,6 +149,10 @@ int phz_read_lists(phz_ctx* ctx, uint64_t bam_exclude_mask, int64_t* n_entries);
 /* Result / intermediate arrays by name (DESIGN.md lists them). */
 int phz_array(phz_ctx* ctx, const char* name, const void** d_ptr, int64_t* count, int* elem_bytes);
 int phz_download(phz_ctx* ctx, const char* name, void* h_dst, int64_t dst_bytes);
+/* Same without the final wait: enqueues the copy on the context's stream (h_dst should be page-locked, otherwise
+ * the copy is synchronous anyway); phz_sync() makes the bytes visible.  Lets the caller fetch all result arrays
+ * of a run with one wait. */
+int phz_download_async(phz_ctx* ctx, const char* name, void* h_dst, int64_t dst_bytes);
 /* counters[16]: n_tuples, entries, groups, pairs, distinct pairs, edges, dropped, members, blocks,
  * hard blocks, final blocks, read-list entries, n_candidates, n_bams, 0, 0 */
 int phz_counters(phz_ctx* ctx, int64_t* counters);

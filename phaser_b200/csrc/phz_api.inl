@@ -116,36 +116,53 @@ int phz_map_reads_packed(phz_ctx* ctx, const phz_packed_reads* h, int baseq, dou
   if (bits != 1 && bits != 2 && bits != 4 && bits != 8) throw PhzError("phz_map_reads_packed: qual_bits must be 1, 2, 4 or 8");
   phz_reads d; std::memset(&d, 0, sizeof(d));
   d.n_records = R; d.n_cigar_ops = NC; d.n_bases = NB; d.h_contig_rec_off = h->h_contig_rec_off;
-  // ---- host -> device, packed
-  be.stage("h2d");
-  be.h2d(ctx->st_pos.ensure(R), h->pos, R * 4); d.pos = ctx->st_pos.p;
-  be.h2d(ctx->st_tlen.ensure(R), h->tlen, R * 4); d.tlen = ctx->st_tlen.p;
-  be.h2d(ctx->st_as.ensure(R), h->aln_score, R * 2); d.aln_score = ctx->st_as.p;
-  be.h2d(ctx->st_frag.ensure(R), h->frag, R * 4); d.frag = ctx->st_frag.p;
-  be.h2d(ctx->st_cig.ensure(NC), h->cigar, NC * 4); d.cigar = ctx->st_cig.p;
-  const uint16_t* ncg = ctx->pk_ncg.ensure(R); be.h2d(ctx->pk_ncg.p, h->n_cigar, R * 2);
-  const uint16_t* lsq = ctx->pk_lsq.ensure(R); be.h2d(ctx->pk_lsq.p, h->l_seq, R * 2);
+  // ---- host -> device on the copy stream, in the order the expansion needs it: counts, qualities, bases, then the
+  // arrays K1 reads as they are.  Each expansion kernel starts as soon as ITS input has landed and runs under the
+  // copies that follow, so only the PCIe time is on the critical path.
+  be.stage("h2d+unpack");
   const int64_t n2 = (NB + 3) / 4, nq = (NB * bits + 7) / 8;
-  const u8* s2 = ctx->pk_seq2.ensure(n2 + 16); be.h2d(ctx->pk_seq2.p, h->seq2, n2);
-  const u8* qp = ctx->pk_qualp.ensure(nq + 16); be.h2d(ctx->pk_qualp.p, h->qualp, nq);
-  const u64* exi = ctx->pk_exi.ensure(NX); be.h2d(ctx->pk_exi.p, h->exc_index, NX * 8);
-  const u8* exc = ctx->pk_exc.ensure(NX); be.h2d(ctx->pk_exc.p, h->exc_code, NX);
-  const u8* qt = ctx->pk_qtab.ensure(256); be.h2d(ctx->pk_qtab.p, h->qual_table, 256);
-  // ---- expand on the device into the phz_reads layout
-  be.stage("unpack");
-  be.exclusive_scan_u16_to_u32(ncg, ctx->st_coff.ensure(R + 1), R); d.cigar_off = ctx->st_coff.p;
-  be.exclusive_scan_u16_to_u64(lsq, ctx->st_soff.ensure(R + 1), R); d.seq_off = (const uint64_t*)ctx->st_soff.p;
+  const uint16_t* ncg = ctx->pk_ncg.ensure(R); const uint16_t* lsq = ctx->pk_lsq.ensure(R);
+  const u8* qp = ctx->pk_qualp.ensure(nq + 16); const u8* qt = ctx->pk_qtab.ensure(256);
+  const u8* s2 = ctx->pk_seq2.ensure(n2 + 16); const u64* exi = ctx->pk_exi.ensure(NX); const u8* exc = ctx->pk_exc.ensure(NX);
+  ctx->st_coff.ensure(R + 1); ctx->st_soff.ensure(R + 1);
+  const int64_t nwq = (NB + 7) / 8, nws = (NB + 15) / 16;
+  u64* qout = (u64*)ctx->st_qual.ensure((size_t)nwq * 8 + 16);
+  u64* sout = (u64*)ctx->st_seq.ensure((size_t)nws * 8 + 16);
+  ctx->st_cig.ensure(NC); ctx->st_pos.ensure(R); ctx->st_tlen.ensure(R); ctx->st_as.ensure(R); ctx->st_frag.ensure(R);
+  be.copy_begin();
+  be.h2d_copy(ctx->pk_ncg.p, h->n_cigar, R * 2); be.h2d_copy(ctx->pk_lsq.p, h->l_seq, R * 2);
+  be.copy_fence();
+  be.h2d_copy(ctx->pk_qualp.p, h->qualp, nq); be.h2d_copy(ctx->pk_qtab.p, h->qual_table, 256);
+  be.exclusive_scan_u16_to_u32(ncg, ctx->st_coff.p, R); d.cigar_off = ctx->st_coff.p;
+  be.exclusive_scan_u16_to_u64(lsq, ctx->st_soff.p, R); d.seq_off = (const uint64_t*)ctx->st_soff.p;
+  be.copy_fence();
+  be.h2d_copy(ctx->pk_seq2.p, h->seq2, n2); be.h2d_copy(ctx->pk_exi.p, h->exc_index, NX * 8); be.h2d_copy(ctx->pk_exc.p, h->exc_code, NX);
+  {   // base qualities: one logical thread per 8 bases = `bits` packed bytes in, 8 phred bytes out
+    const u32 mask = (1u << bits) - 1;
+    be.for_each(nwq, PHZ_LAMBDA(int64_t w) {
+      u64 in = 0;
+      for (int j = 0; j < bits; ++j) in |= (u64)qp[w * bits + j] << (8 * j);
+      u64 o = 0;
+      for (int k = 0; k < 8; ++k) o |= (u64)qt[(in >> (k * bits)) & mask] << (8 * k);
+      qout[w] = o;
+    });
+    d.qual = ctx->st_qual.p;
+  }
+  be.copy_fence();
+  be.h2d_copy(ctx->st_cig.p, h->cigar, NC * 4); d.cigar = ctx->st_cig.p;
+  be.h2d_copy(ctx->st_pos.p, h->pos, R * 4); d.pos = ctx->st_pos.p;
+  be.h2d_copy(ctx->st_tlen.p, h->tlen, R * 4); d.tlen = ctx->st_tlen.p;
+  be.h2d_copy(ctx->st_as.p, h->aln_score, R * 2); d.aln_score = ctx->st_as.p;
+  be.h2d_copy(ctx->st_frag.p, h->frag, R * 4); d.frag = ctx->st_frag.p;
   {   // bases: one logical thread per 16 bases = 4 packed bytes in, 8 bytes out (A C G T -> 1 2 4 8, even index = high nibble)
-    const int64_t nw = (NB + 15) / 16;
-    u64* out = (u64*)ctx->st_seq.ensure((size_t)nw * 8 + 16);
     const u32* in32 = (const u32*)s2;
-    be.for_each(nw, PHZ_LAMBDA(int64_t w) {
+    be.for_each(nws, PHZ_LAMBDA(int64_t w) {
       u32 in = in32[w]; u64 o = 0;
       for (int k = 0; k < 16; ++k) {
         u64 nib = (u64)1 << ((in >> (2 * k)) & 3);
         o |= nib << ((k >> 1) * 8 + ((k & 1) ? 0 : 4));
       }
-      out[w] = o;
+      sout[w] = o;
     });
     u32* words = (u32*)ctx->st_seq.p;
     be.for_each(NX, PHZ_LAMBDA(int64_t e) {      // every other code (N, IUPAC, '='): patch the nibble
@@ -155,20 +172,8 @@ int phz_map_reads_packed(phz_ctx* ctx, const phz_packed_reads* h, int baseq, dou
     });
     d.seq = ctx->st_seq.p;
   }
-  {   // base qualities: one logical thread per 8 bases = `bits` packed bytes in, 8 phred bytes out
-    const int64_t nw = (NB + 7) / 8;
-    u64* out = (u64*)ctx->st_qual.ensure((size_t)nw * 8 + 16);
-    const u32 mask = (1u << bits) - 1;
-    be.for_each(nw, PHZ_LAMBDA(int64_t w) {
-      u64 in = 0;
-      for (int j = 0; j < bits; ++j) in |= (u64)qp[w * bits + j] << (8 * j);
-      u64 o = 0;
-      for (int k = 0; k < 8; ++k) o |= (u64)qt[(in >> (k * bits)) & mask] << (8 * k);
-      out[w] = o;
-    });
-    d.qual = ctx->st_qual.p;
-  }
-  be.stage("unpack.end");
+  be.copy_fence();
+  be.stage("h2d+unpack.end");
   ReadsView v = view_of(&d, ctx->p.nc);
   *n_candidates = ctx->p.map_reads(v, h->h_contig_rec_off, baseq, isize_cutoff);
   PHZ_CATCH
@@ -248,6 +253,15 @@ int phz_download(phz_ctx* ctx, const char* name, void* h_dst, int64_t dst_bytes)
   if (!find_array(ctx, name, &r)) throw PhzError(std::string("unknown array: ") + name);
   if (r.n * r.eb > dst_bytes) throw PhzError(std::string("destination too small for array ") + name);
   if (r.n > 0) ctx->p.be.d2h(h_dst, r.p, (size_t)(r.n * r.eb)); else ctx->p.be.sync();
+  PHZ_CATCH
+}
+
+int phz_download_async(phz_ctx* ctx, const char* name, void* h_dst, int64_t dst_bytes) {
+  PHZ_TRY
+  ArrRef r;
+  if (!find_array(ctx, name, &r)) throw PhzError(std::string("unknown array: ") + name);
+  if (r.n * r.eb > dst_bytes) throw PhzError(std::string("destination too small for array ") + name);
+  if (r.n > 0) ctx->p.be.d2h_async(h_dst, r.p, (size_t)(r.n * r.eb));
   PHZ_CATCH
 }
 

@@ -186,8 +186,32 @@ struct DeviceBackend {
     if (bytes) PHZ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
     PHZ_CUDA(cudaStreamSynchronize(stream));
   }
+  void d2h_async(void* dst, const void* src, size_t bytes) {
+    if (bytes) PHZ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
+  }
   void d2d(void* dst, const void* src, size_t bytes) {
     if (bytes) PHZ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream));
+  }
+  // ---- second stream for host->device copies that overlap kernels of the main stream (phz_map_reads_packed):
+  // copy_begin() orders the copy stream after everything already queued on the main stream (the staging buffers
+  // may still be read by it), h2d_copy() enqueues on the copy stream, copy_fence() makes the main stream wait for
+  // the copies enqueued so far.
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_ev[2] = {nullptr, nullptr};
+  void copy_begin() {
+    if (!copy_stream) {
+      PHZ_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+      for (auto& e : copy_ev) PHZ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    PHZ_CUDA(cudaEventRecord(copy_ev[0], stream));
+    PHZ_CUDA(cudaStreamWaitEvent(copy_stream, copy_ev[0], 0));
+  }
+  void h2d_copy(void* dst, const void* src, size_t bytes) {
+    if (bytes) PHZ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, copy_stream));
+  }
+  void copy_fence() {
+    PHZ_CUDA(cudaEventRecord(copy_ev[1], copy_stream));
+    PHZ_CUDA(cudaStreamWaitEvent(stream, copy_ev[1], 0));
   }
   void sync() { PHZ_CUDA(cudaStreamSynchronize(stream)); }
 
@@ -275,7 +299,11 @@ struct DeviceBackend {
     PHZ_CUDA(cub::DeviceRadixSort::SortPairs(t, bytes, keys_in, keys_out, vals_in, vals_out, (int)n, begin_bit, end_bit, stream));
     lib_launches += 1 + (end_bit - begin_bit + 7) / 8;
   }
-  ~DeviceBackend() { if (cub_tmp) cudaFree(cub_tmp); }
+  ~DeviceBackend() {
+    if (cub_tmp) cudaFree(cub_tmp);
+    for (auto& e : copy_ev) if (e) cudaEventDestroy(e);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+  }
 };
 
 }  // namespace phz
@@ -302,7 +330,11 @@ struct HostSimBackend {
   void memset_ff(void* p, size_t bytes) { std::memset(p, 0xFF, bytes); }
   void h2d(void* dst, const void* src, size_t bytes) { if (bytes) std::memcpy(dst, src, bytes); }
   void d2h(void* dst, const void* src, size_t bytes) { if (bytes) std::memcpy(dst, src, bytes); }
+  void d2h_async(void* dst, const void* src, size_t bytes) { if (bytes) std::memcpy(dst, src, bytes); }
   void d2d(void* dst, const void* src, size_t bytes) { if (bytes) std::memmove(dst, src, bytes); }
+  void copy_begin() {}
+  void h2d_copy(void* dst, const void* src, size_t bytes) { if (bytes) std::memcpy(dst, src, bytes); }
+  void copy_fence() {}
   void sync() {}
 
   template <class F>

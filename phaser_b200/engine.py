@@ -41,7 +41,7 @@ class phz_packed_reads(ctypes.Structure):
 
 EXPORTS = ["phz_last_error", "phz_backend_name", "phz_create", "phz_destroy", "phz_sync", "phz_set_variants",
            "phz_map_reads", "phz_map_reads_host", "phz_as_histogram", "phz_commit_bam", "phz_variant_stats", "phz_build_graph",
-           "phz_phase", "phz_read_lists", "phz_array", "phz_download", "phz_counters", "phz_launch_counts",
+           "phz_phase", "phz_read_lists", "phz_array", "phz_download", "phz_download_async", "phz_counters", "phz_launch_counts",
            "phz_set_profiling", "phz_map_times", "phz_stage_report", "phz_set_option",
            "phz_fragdict_create", "phz_fragdict_destroy", "phz_fragdict_size", "phz_fragdict_name", "phz_read_alignments",
            "phz_host_reads_view", "phz_host_reads_free", "phz_set_haplo_blacklist", "phz_write_sam",
@@ -67,6 +67,7 @@ def _declare(lib):
     lib.phz_read_lists.argtypes = [c_void_p, c_uint64, POINTER(c_int64)]
     lib.phz_array.argtypes = [c_void_p, c_char_p, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int)]
     lib.phz_download.argtypes = [c_void_p, c_char_p, c_void_p, c_int64]
+    lib.phz_download_async.argtypes = [c_void_p, c_char_p, c_void_p, c_int64]
     lib.phz_counters.argtypes = [c_void_p, POINTER(c_int64)]
     lib.phz_launch_counts.argtypes = [c_void_p, POINTER(c_uint64), POINTER(c_uint64)]
     lib.phz_set_profiling.argtypes = [c_void_p, c_int]
@@ -390,6 +391,36 @@ class Engine:
         self._check(self.lib.phz_array(self.ctx, name.encode(), byref(p), byref(n), byref(eb)))
         out = np.empty(n.value, dtype or _DT[eb.value])
         self._check(self.lib.phz_download(self.ctx, name.encode(), out.ctypes.data, out.nbytes))
+        return out
+
+    def download_many(self, names):
+        """All `names` with ONE wait: copies are enqueued into a page-locked result buffer owned by the engine
+        (grow-only), then the stream is synchronised once.  The returned arrays are VIEWS of that buffer: they are
+        overwritten by the next download_many on this engine."""
+        info = []
+        total = 0
+        for name in names:
+            p = c_void_p(); n = c_int64(0); eb = c_int(0)
+            self._check(self.lib.phz_array(self.ctx, name.encode(), byref(p), byref(n), byref(eb)))
+            off = (total + 63) // 64 * 64
+            info.append((name, off, n.value, eb.value))
+            total = off + n.value * eb.value
+        buf = getattr(self, "_result_buf", None)
+        if buf is None or buf.numel() < total:
+            buf = torch.empty(int(total * 1.25) + 4096, dtype=torch.uint8)
+            if self.device.type == "cuda":
+                try:
+                    buf = buf.pin_memory()
+                except RuntimeError:
+                    pass
+            self._result_buf = buf
+        base = buf.data_ptr()
+        host = buf.numpy()
+        out = {}
+        for name, off, n, eb in info:
+            self._check(self.lib.phz_download_async(self.ctx, name.encode(), base + off, n * eb))
+            out[name] = host[off:off + n * eb].view(_DT[eb])
+        self.sync()
         return out
 
     def counters(self):

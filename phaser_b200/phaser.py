@@ -210,7 +210,7 @@ def run(args, engine=None):
                              max_block_size=args.max_block_size, haplo_count_bam_exclude=exclude,
                              want_read_ids=(args.output_read_ids == 1), want_kept_tuples=(args.output_network != ""))
     try:
-        res = pipeline.run_path(engine, vt, batches, P, n_fragments=len(fd))
+        res = pipeline.run_path(engine, vt, batches, P, n_fragments=len(fd), reuse_result_buffer=True)
     except PhaserFatal as e:
         fatal_error(str(e))
     _t = _trace(_t, "run_path (device)")

@@ -181,10 +181,12 @@ RESULT_ARRAYS = ["vfirst", "ncls", "setsize", "vb_cnt", "ed_a", "ed_b", "ed_sup"
 
 
 def run_path(engine: Engine, vt: VariantTable, batches, params: PhaseParams, n_fragments: int, comm=None,
-             host_inputs=False, download=True) -> PhaseResult:
+             host_inputs=False, download=True, reuse_result_buffer=False) -> PhaseResult:
     """`batches`: per BAM a dict of device tensors (Engine.upload_reads), a PackedReads (host, packed transport
     form: phz_map_reads_packed copies and expands it) or, with host_inputs, a dict of plain host arrays
-    (phz_map_reads_host copies them)."""
+    (phz_map_reads_host copies them).  `reuse_result_buffer`: the result arrays are views of the engine's
+    page-locked result buffer (one wait for all of them, no pageable copies) and stay valid until the next run on
+    this engine; otherwise they are private copies."""
     comm = comm or NullComm()
     nb = len(batches)
     isz = list(params.isize) * nb if len(params.isize) == 1 else list(params.isize)
@@ -253,8 +255,12 @@ def run_path(engine: Engine, vt: VariantTable, batches, params: PhaseParams, n_f
     if params.want_read_lists:
         engine.read_lists(excl)
     if download:
-        for name in RESULT_ARRAYS + (["rl_frag", "rl_var", "rl_row"] if params.want_read_lists else []):
-            arrays[name] = engine.download(name)
+        names = RESULT_ARRAYS + (["rl_frag", "rl_var", "rl_row"] if params.want_read_lists else [])
+        if reuse_result_buffer:
+            arrays.update(engine.download_many(names))
+        else:
+            for name in names:
+                arrays[name] = engine.download(name)
         if params.want_kept_tuples:
             for name in ("g_var", "g_cb", "g_frag"):
                 arrays[name] = engine.download(name)

@@ -215,3 +215,17 @@ def test_packed_host_form_through_the_whole_path(gpu, tmp_path):
     assert a.counters == b.counters
     for k in a.arrays:
         assert np.array_equal(a.arrays[k], b.arrays[k]), k
+
+
+def test_result_buffer_views_equal_private_copies(gpu, tmp_path):
+    """download_many (page-locked buffer, async copies, one wait) returns what the per-array downloads return."""
+    from phaser_b200 import pipeline, engine as eng
+    vcf, sams = util.make_case(tmp_path, 43, 300, 6000, n_bams=1)
+    vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+    P = pipeline.PhaseParams()
+    a = pipeline.run_path(gpu, vt, [gpu.upload_reads(b) for b in batches], P, n_fragments=len(fd.names))
+    b = pipeline.run_path(gpu, vt, [eng.pack_reads(x, len(vt.contigs), lib=gpu.lib) for x in batches], P,
+                          n_fragments=len(fd.names), reuse_result_buffer=True)
+    assert set(a.arrays) == set(b.arrays)
+    for k in a.arrays:
+        assert a.arrays[k].dtype == b.arrays[k].dtype and np.array_equal(a.arrays[k], b.arrays[k]), k

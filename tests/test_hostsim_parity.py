@@ -121,3 +121,16 @@ def test_packed_transport_refuses_oversized_records(hostsim):
                   np.full((n + 1) // 2, 0x11, np.uint8), np.full(n, 30, np.uint8), None)
     with pytest.raises(eng.PhzError, match="not packable"):
         eng.pack_reads(b, 1, lib=hostsim.lib)
+
+
+def test_result_buffer_views_equal_private_copies(hostsim, tmp_path):
+    from phaser_b200 import pipeline
+    vcf, sams = util.make_case(tmp_path, 43, 200, 1500, n_bams=1)
+    vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+    P = pipeline.PhaseParams()
+    a = pipeline.run_path(hostsim, vt, [hostsim.upload_reads(b) for b in batches], P, n_fragments=len(fd.names))
+    b = pipeline.run_path(hostsim, vt, [hostsim.upload_reads(b) for b in batches], P, n_fragments=len(fd.names),
+                          reuse_result_buffer=True)
+    assert set(a.arrays) == set(b.arrays)
+    for k in a.arrays:
+        assert a.arrays[k].dtype == b.arrays[k].dtype and np.array_equal(a.arrays[k], b.arrays[k]), k
