@@ -230,7 +230,7 @@ def run_ours(a):
         # the ingest's host form: packed transport buffers in page-locked memory (include/phz.h: phz_packed_reads),
         # built ONCE here like a BAM is parsed once; phz_map_reads_packed copies + expands them inside the timed region
         host_np = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in reads.items()}
-        packed = eng.pack_reads(host_np, len(g.contigs), lib=E.lib)
+        packed = eng.pack_reads(host_np, len(g.contigs), lib=E.lib, page_locked=True)
         dt, d2h = timed_e2e(packed, a.steps)
         e2e = {"value": V * world / dt, "unit": "het-SNVs/s", "h2d_bytes_per_step": int(packed.nbytes),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3,

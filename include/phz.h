@@ -106,9 +106,11 @@ typedef struct phz_packed_reads {
   const uint8_t* qualp;            /* (n_bases*qual_bits+7)/8 bytes; base i at bit i*qual_bits, little-endian */
 } phz_packed_reads;
 typedef struct phz_packed_host phz_packed_host;
-/* Packs HOST arrays (n_threads host threads; output in page-locked memory when a CUDA device is present).  NULL +
- * phz_last_error() when a record has more than 65535 CIGAR ops or bases: use phz_map_reads_host for such data. */
-phz_packed_host* phz_pack_reads(const phz_reads* host_reads, int n_contigs, int n_threads);
+/* Packs HOST arrays on n_threads host threads.  page_locked != 0: the output lives in page-locked memory (worth its
+ * allocation cost when the buffers are copied more than once or the copy must overlap kernels; a one-shot run is
+ * faster from pageable memory).  NULL + phz_last_error() when a record has more than 65535 CIGAR ops or bases: use
+ * phz_map_reads_host for such data. */
+phz_packed_host* phz_pack_reads(const phz_reads* host_reads, int n_contigs, int n_threads, int page_locked);
 int phz_packed_view(phz_packed_host* p, phz_packed_reads* out);
 int64_t phz_packed_bytes(phz_packed_host* p);
 void phz_packed_free(phz_packed_host* p);

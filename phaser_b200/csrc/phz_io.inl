@@ -543,20 +543,21 @@ struct phz_packed_host {
   std::vector<std::pair<void*, bool>> bufs;      // (pointer, page-locked)
   std::vector<int64_t> contig_off;
   int64_t bytes = 0;
+  bool want_pinned = false;
   template <class T> T* alloc(size_t n) {
     bool pinned = false;
-    void* p = PHZ_BACKEND::host_alloc((n ? n : 1) * sizeof(T), &pinned);
+    void* p = want_pinned ? PHZ_BACKEND::host_alloc((n ? n : 1) * sizeof(T), &pinned) : std::malloc((n ? n : 1) * sizeof(T));
     if (!p) throw PhzError("out of host memory for the packed transport buffers");
     bufs.emplace_back(p, pinned);
     bytes += (int64_t)(n * sizeof(T));
     return (T*)p;
   }
-  ~phz_packed_host() { for (auto& b : bufs) PHZ_BACKEND::host_free(b.first, b.second); }
+  ~phz_packed_host() { for (auto& b : bufs) { if (b.second) PHZ_BACKEND::host_free(b.first, true); else std::free(b.first); } }
 };
 
 extern "C" {
 
-phz_packed_host* phz_pack_reads(const phz_reads* h, int n_contigs, int n_threads) {
+phz_packed_host* phz_pack_reads(const phz_reads* h, int n_contigs, int n_threads, int page_locked) {
   phz_packed_host* P = nullptr;
   try {
     if (n_threads < 1) n_threads = 1;
@@ -566,6 +567,7 @@ phz_packed_host* phz_pack_reads(const phz_reads* h, int n_contigs, int n_threads
         throw PhzError("record " + std::to_string(r) + " has more than 65535 CIGAR operations or bases: not packable");
     }
     P = new phz_packed_host();
+    P->want_pinned = page_locked != 0;
     phz_packed_reads& v = P->v;
     std::memset(&v, 0, sizeof(v));
     v.n_records = R; v.n_cigar_ops = NCG; v.n_bases = NB;

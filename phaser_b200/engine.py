@@ -87,7 +87,7 @@ def _declare(lib):
     lib.phz_set_haplo_blacklist.argtypes = [c_void_p, c_void_p]
     lib.phz_set_indel_alleles.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
     lib.phz_pack_reads.restype = c_void_p
-    lib.phz_pack_reads.argtypes = [POINTER(phz_reads), c_int, c_int]
+    lib.phz_pack_reads.argtypes = [POINTER(phz_reads), c_int, c_int, c_int]
     lib.phz_packed_view.argtypes = [c_void_p, POINTER(phz_packed_reads)]
     lib.phz_packed_bytes.restype = c_int64
     lib.phz_packed_bytes.argtypes = [c_void_p]
@@ -169,8 +169,8 @@ def write_sam_native(rec, contigs, path, bam_name="bam0", lib=None):
 
 
 class PackedReads:
-    """One BAM in the packed transport form (include/phz.h: phz_packed_reads), in page-locked host memory owned by
-    the native library.  Built once at ingest; phz_map_reads_packed copies it to the device and expands it there."""
+    """One BAM in the packed transport form (include/phz.h: phz_packed_reads) in host memory owned by the native
+    library.  Built once at ingest; phz_map_reads_packed copies it to the device and expands it there."""
 
     def __init__(self, lib, handle):
         self.lib = lib; self.h = handle
@@ -190,8 +190,9 @@ class PackedReads:
             pass
 
 
-def pack_reads(reads, n_contigs, threads=0, lib=None) -> PackedReads:
-    """`reads`: ReadBatch or dict of host arrays (numpy / CPU tensors) in the phz_reads layout."""
+def pack_reads(reads, n_contigs, threads=0, lib=None, page_locked=False) -> PackedReads:
+    """`reads`: ReadBatch or dict of host arrays (numpy / CPU tensors) in the phz_reads layout.  `page_locked`: put the
+    packed buffers in page-locked memory (pays off when they are copied repeatedly; a one-shot run skips the cost)."""
     lib = lib if lib is not None else load_library()
     if isinstance(reads, ReadBatch):
         reads = dict(contig_rec_off=np.ascontiguousarray(reads.contig_rec_off, dtype=np.int64), pos=reads.pos, tlen=reads.tlen,
@@ -199,7 +200,7 @@ def pack_reads(reads, n_contigs, threads=0, lib=None) -> PackedReads:
                      seq_off=reads.seq_off, seq=reads.seq, qual=reads.qual)
     reads = {k: (np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v) for k, v in reads.items()}
     r = Engine._reads_struct(reads)
-    h = lib.phz_pack_reads(byref(r), int(n_contigs), int(threads or (os.cpu_count() or 1)))
+    h = lib.phz_pack_reads(byref(r), int(n_contigs), int(threads or (os.cpu_count() or 1)), int(bool(page_locked)))
     if not h:
         raise PhzError(lib.phz_last_error().decode())
     return PackedReads(lib, h)
