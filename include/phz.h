@@ -172,6 +172,37 @@ int phz_stage_report(phz_ctx* ctx, char* buf, int64_t buf_len);
 /* kernels of this library launched so far / library (CUB) passes launched so far */
 int phz_launch_counts(phz_ctx* ctx, uint64_t* own, uint64_t* library);
 
+/* ---- feature-level haplotypic counts: the join and the distinct-read counting of
+ * phaser_gene_ae.py (phaser_gene_ae/phaser_gene_ae.py:95-101, 172-219).  All pointers are DEVICE pointers.  Rows =
+ * the rows of haplotypic_counts.txt of ONE run (all BAMs); row_contig = index into the feature contigs, -1 when the
+ * row takes no part (totalCount <= 0 or contig without features).  Read ids are renumbered densely per (row,
+ * haplotype): the lists of variant v are ids[id_off[2v] .. id_off[2v+1]) (haplotype A) and ids[id_off[2v+1] ..
+ * id_off[2v+2]) (B); row_ids_a/b = number of distinct ids of the row per haplotype.  Features are sorted by (contig,
+ * start); f_maxstop = running maximum of f_stop inside the contig; f_contig_off has n_contigs+1 entries.
+ * Result arrays (phz_array / phz_download): "ae_row", "ae_feat" (index into the sorted features), "ae_a", "ae_b" =
+ * distinct reads per haplotype among the row's variants inside the feature, one entry per (row, overlapping feature)
+ * in row order. */
+typedef struct phz_ae_input {
+  int64_t n_rows;
+  const int32_t* row_contig;
+  const int32_t* row_start;        /* 1-based, as printed */
+  const int32_t* row_stop;
+  const uint32_t* row_a;           /* aCount / bCount columns */
+  const uint32_t* row_b;
+  const uint32_t* row_ids_a;
+  const uint32_t* row_ids_b;
+  const uint32_t* var_off;         /* n_rows+1 */
+  const int32_t* var_pos;          /* position field of the variant id */
+  const uint32_t* id_off;          /* 2*n_vars+1 */
+  const uint32_t* ids;
+  int64_t n_features;
+  const int32_t* f_start;          /* BED, 0-based */
+  const int32_t* f_stop;
+  const int32_t* f_maxstop;
+  const int64_t* f_contig_off;
+} phz_ae_input;
+int phz_gene_ae_pairs(phz_ctx* ctx, const phz_ae_input* in, int64_t* n_pairs);
+
 /* ---- native host ingest (no GPU involved): BAM (BGZF, parallel inflate) or SAM text -> phz_reads with
  * HOST pointers.  Replaces `samtools view -h BAM chr: | samtools view -Sh [-F 0x400] [-f 2] -q MAPQ`
  * (phaser.py:1346) and the mapper's per-line parsing (read_variant_map.py:25-64).  Records come out

@@ -2,6 +2,7 @@
 // DeviceBackend) and by tests/hostsim/hostsim.cpp (logic-test double, HostSimBackend).
 #include "../../include/phz.h"
 #include "phz_pipeline.h"
+#include "phz_gene_ae.h"
 #include <climits>
 #include <map>
 
@@ -14,8 +15,10 @@ struct phz_ctx {
   Buf<PHZ_BACKEND, u64> st_soff; Buf<PHZ_BACKEND, u8> st_seq, st_qual;
   // packed transport (phz_map_reads_packed): what arrives over PCIe before it is expanded into st_*
   Buf<PHZ_BACKEND, uint16_t> pk_ncg, pk_lsq; Buf<PHZ_BACKEND, u8> pk_seq2, pk_qualp, pk_exc, pk_qtab; Buf<PHZ_BACKEND, u64> pk_exi;
+  GeneAE<PHZ_BACKEND> ae;
   phz_ctx() {
     PHZ_BACKEND* b = &p.be;
+    ae.bind(b);
     pk_ncg.bind(b); pk_lsq.bind(b); pk_seq2.bind(b); pk_qualp.bind(b); pk_exc.bind(b); pk_qtab.bind(b); pk_exi.bind(b);
     st_pos.bind(b); st_tlen.bind(b); st_as.bind(b); st_frag.bind(b); st_coff.bind(b); st_cig.bind(b); st_soff.bind(b);
     st_seq.bind(b); st_qual.bind(b);
@@ -213,6 +216,10 @@ int phz_phase(phz_ctx* ctx, const uint32_t* h_kstar, int64_t kstar_len, int max_
   PHZ_CATCH
 }
 
+int phz_gene_ae_pairs(phz_ctx* ctx, const phz_ae_input* in, int64_t* n_pairs) {
+  PHZ_TRY *n_pairs = ctx->ae.run(*in); PHZ_CATCH
+}
+
 int phz_read_lists(phz_ctx* ctx, uint64_t excl, int64_t* n_entries) {
   PHZ_TRY *n_entries = ctx->p.read_lists(excl); PHZ_CATCH
 }
@@ -236,6 +243,9 @@ static bool find_array(phz_ctx* ctx, const std::string& name, ArrRef* out) {
   A("fb_cnt", fb_cnt, p.NF * 2) A("fb_bcnt", fb_bcnt, p.NF * nb * 2) A("v_final", v_final, p.V) A("v_hap", v_hap, p.V)
   A("rl_frag", rl_frag, p.NRL) A("rl_var", rl_var, p.NRL) A("rl_row", rl_row, p.NRL)
 #undef A
+#define G(nm, buf) if (name == nm) { *out = ArrRef{(const void*)ctx->ae.buf.p, ctx->ae.NPAIR, (int)sizeof(u32)}; return true; }
+  G("ae_row", ae_row) G("ae_feat", ae_feat) G("ae_a", ae_a) G("ae_b", ae_b)
+#undef G
   return false;
 }
 

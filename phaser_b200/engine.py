@@ -39,6 +39,14 @@ class phz_packed_reads(ctypes.Structure):
                 ("qualp", c_void_p)]
 
 
+class phz_ae_input(ctypes.Structure):
+    _fields_ = [("n_rows", c_int64), ("row_contig", c_void_p), ("row_start", c_void_p), ("row_stop", c_void_p),
+                ("row_a", c_void_p), ("row_b", c_void_p), ("row_ids_a", c_void_p), ("row_ids_b", c_void_p),
+                ("var_off", c_void_p), ("var_pos", c_void_p), ("id_off", c_void_p), ("ids", c_void_p),
+                ("n_features", c_int64), ("f_start", c_void_p), ("f_stop", c_void_p), ("f_maxstop", c_void_p),
+                ("f_contig_off", c_void_p)]
+
+
 EXPORTS = ["phz_last_error", "phz_backend_name", "phz_create", "phz_destroy", "phz_sync", "phz_set_variants",
            "phz_map_reads", "phz_map_reads_host", "phz_as_histogram", "phz_commit_bam", "phz_variant_stats", "phz_build_graph",
            "phz_phase", "phz_read_lists", "phz_array", "phz_download", "phz_download_async", "phz_counters", "phz_launch_counts",
@@ -46,7 +54,7 @@ EXPORTS = ["phz_last_error", "phz_backend_name", "phz_create", "phz_destroy", "p
            "phz_fragdict_create", "phz_fragdict_destroy", "phz_fragdict_size", "phz_fragdict_name", "phz_read_alignments",
            "phz_host_reads_view", "phz_host_reads_free", "phz_set_haplo_blacklist", "phz_write_sam",
            "phz_set_indel_alleles", "phz_pack_reads", "phz_packed_view", "phz_packed_bytes", "phz_packed_free",
-           "phz_map_reads_packed"]
+           "phz_map_reads_packed", "phz_gene_ae_pairs"]
 
 
 def _declare(lib):
@@ -93,6 +101,7 @@ def _declare(lib):
     lib.phz_packed_bytes.argtypes = [c_void_p]
     lib.phz_packed_free.argtypes = [c_void_p]
     lib.phz_map_reads_packed.argtypes = [c_void_p, POINTER(phz_packed_reads), c_int, c_double, POINTER(c_int64)]
+    lib.phz_gene_ae_pairs.argtypes = [c_void_p, POINTER(phz_ae_input), POINTER(c_int64)]
     return lib
 
 
@@ -422,6 +431,32 @@ class Engine:
             self._check(self.lib.phz_download_async(self.ctx, name.encode(), base + off, n * eb))
             out[name] = host[off:off + n * eb].view(_DT[eb])
         self.sync()
+        return out
+
+    def gene_ae_pairs(self, rows, feats):
+        """phaser_gene_ae join + distinct-read counts (phz_gene_ae_pairs).  `rows` / `feats`: phaser_gene_ae.Rows /
+        Features.  Returns (row, sorted-feature index, aCount, bCount) per (row, overlapping feature)."""
+        d = self.device
+        keep = []
+
+        def up(a, dt):
+            t = _as_torch(np.ascontiguousarray(np.asarray(a, dt)), d)
+            keep.append(t)
+            return t.data_ptr()
+        s = phz_ae_input()
+        s.n_rows = rows.n
+        s.row_contig = up(rows.contig, np.int32); s.row_start = up(rows.start, np.int32); s.row_stop = up(rows.stop, np.int32)
+        s.row_a = up(rows.a, np.uint32); s.row_b = up(rows.b, np.uint32)
+        s.row_ids_a = up(rows.ida, np.uint32); s.row_ids_b = up(rows.idb, np.uint32)
+        s.var_off = up(rows.var_off, np.uint32); s.var_pos = up(rows.var_pos, np.int32)
+        s.id_off = up(rows.id_off, np.uint32); s.ids = up(rows.ids, np.uint32)
+        s.n_features = int(feats.f_start.shape[0])
+        s.f_start = up(feats.f_start, np.int32); s.f_stop = up(feats.f_stop, np.int32); s.f_maxstop = up(feats.f_maxstop, np.int32)
+        s.f_contig_off = up(feats.f_contig_off, np.int64)
+        n = c_int64(0)
+        self._check(self.lib.phz_gene_ae_pairs(self.ctx, byref(s), byref(n)))
+        out = tuple(self.download(k) for k in ("ae_row", "ae_feat", "ae_a", "ae_b"))
+        del keep
         return out
 
     def counters(self):

@@ -431,6 +431,42 @@ def config1_case():
     print("golden config1 ok", digest[:12])
 
 
+def gene_ae_cases():
+    """phaser_gene_ae.py (UNMODIFIED, with the stub intervaltree of oracle/harness/stub) on the reference's own
+    haplotypic_counts.txt of existing cases; features = seeded random, overlapping and nested intervals."""
+    import random
+    import subprocess
+    GA = os.path.join(HERE, "gene_ae")
+    script = os.path.join(os.path.dirname(rr.REFERENCE_DIR), "phaser_gene_ae", "phaser_gene_ae.py")
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "oracle", "harness", "stub"), PYTHONHASHSEED="0")
+    for name, base, seed, args in (("two_bams_default", "rna_two_bams", 1, []),
+                                   ("two_bams_maf_cov", "rna_two_bams", 2, ["--min_haplo_maf", "0.2", "--gw_cutoff", "0.6", "--min_cov", "3"]),
+                                   ("conflict_default", "rna_conflict", 3, []),
+                                   ("blacklists_cutoff1", "opt_blacklists", 4, ["--gw_cutoff", "1.0"])):
+        # (a file written with --output_read_ids 1 crashes the reference script: its rows and header disagree, phaser.py:837 vs 1120)
+        d = os.path.join(GA, name)
+        os.makedirs(d, exist_ok=True)
+        rnd = random.Random(seed)
+        hc = os.path.join(CASES, base, "ref.haplotypic_counts.txt")
+        feats = []
+        for c, L in (("21", 120000), ("22", 80000), ("7", 50000)):
+            for _ in range(60):
+                a = rnd.randrange(0, L - 10); ln = rnd.choice([1, 40, 300, 2500, 9000, 40000])
+                feats.append((c, a, min(L, a + ln)))
+        rnd.shuffle(feats)
+        bed = os.path.join(d, "features.bed")
+        with open(bed, "w") as f:
+            for i, (c, a, b) in enumerate(feats):
+                f.write("%s\t%d\t%d\tgene%d\n" % (c, a, b, i))
+        out = os.path.join(d, "ref.gene_ae.txt")
+        r = subprocess.run([sys.executable, script, "--haplotypic_counts", hc, "--features", bed, "--o", out] + args,
+                           env=env, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(r.stdout[-1000:] + r.stderr[-2000:])
+        json.dump(dict(base=base, args=args), open(os.path.join(d, "case.json"), "w"), indent=1)
+        print("golden gene_ae", name, "ok")
+
+
 def main():
     os.makedirs(CASES, exist_ok=True)
     v, s = quirk_case()
@@ -456,6 +492,7 @@ def main():
     vq, sq = quirk_case()
     run_case("opt_quirks_indels", vq, [("quirks.bam", sq)], ["--include_indels", "1", "--as_q_cutoff", "0"])
     config1_case()
+    gene_ae_cases()
 
 
 if __name__ == "__main__":
