@@ -25,18 +25,28 @@ class BGZFWriter:
         self.f = open(path, "wb")
         self.buf = bytearray()
         self.level = level
+        self.coffset = 0          # compressed bytes written so far = file offset of the block being filled
+
+    def tell_virtual(self):
+        """BGZF virtual file offset of the next byte written: block start << 16 | offset inside the block"""
+        return (self.coffset << 16) | len(self.buf)
+
+    def _emit(self, raw):
+        blk = compress_block(raw, self.level)
+        self.f.write(blk)
+        self.coffset += len(blk)
 
     def write(self, data):
         if isinstance(data, str):
             data = data.encode()
         self.buf += data
         while len(self.buf) >= MAX_BLOCK:
-            self.f.write(compress_block(bytes(self.buf[:MAX_BLOCK]), self.level))
+            self._emit(bytes(self.buf[:MAX_BLOCK]))
             del self.buf[:MAX_BLOCK]
 
     def close(self):
         if self.buf:
-            self.f.write(compress_block(bytes(self.buf), self.level))
+            self._emit(bytes(self.buf))
             self.buf = bytearray()
         self.f.write(EOF_BLOCK)
         self.f.close()
@@ -62,3 +72,49 @@ def read_all(path) -> bytes:
             break
         pos += used
     return b"".join(out)
+
+
+class VirtualReader:
+    """Random access through BGZF virtual offsets (what an index points at)."""
+
+    def __init__(self, path):
+        with open(path, "rb") as f:
+            self.data = f.read()
+        self.block = -1; self.raw = b""; self.within = 0; self.next_block = 0
+
+    def _load(self, coffset):
+        if coffset >= len(self.data):
+            self.block = coffset; self.raw = b""; self.next_block = coffset
+            return
+        bsize = struct.unpack_from("<H", self.data, coffset + 16)[0] + 1
+        d = zlib.decompressobj(31)
+        self.raw = d.decompress(self.data[coffset:coffset + bsize])
+        self.block = coffset; self.next_block = coffset + bsize
+
+    def seek(self, voffset):
+        c, w = voffset >> 16, voffset & 0xffff
+        if c != self.block:
+            self._load(c)
+        self.within = w
+
+    def tell(self):
+        if self.within >= len(self.raw) and self.raw:
+            return self.next_block << 16
+        return (self.block << 16) | self.within
+
+    def readline(self):
+        out = []
+        while True:
+            if self.within >= len(self.raw):
+                if self.next_block >= len(self.data) or (self.block >= 0 and not self.raw):
+                    break
+                self._load(self.next_block); self.within = 0
+                if not self.raw:
+                    break
+            i = self.raw.find(b"\n", self.within)
+            if i < 0:
+                out.append(self.raw[self.within:]); self.within = len(self.raw)
+            else:
+                out.append(self.raw[self.within:i + 1]); self.within = i + 1
+                break
+        return b"".join(out)

@@ -20,7 +20,7 @@ import time
 if __package__ in (None, ""):
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-from phaser_b200 import vcfio, samio, pipeline, writer, bgzf    # noqa: E402
+from phaser_b200 import vcfio, samio, pipeline, writer, bgzf, tabix    # noqa: E402
 from phaser_b200.vcfio import PhaserFatal                        # noqa: E402
 
 VERSION = "1.2.0"
@@ -253,8 +253,8 @@ def run(args, engine=None):
             text, unphased_phased, phase_corrected = out.vcf_text(
                 f, sample_column, id_separator=args.id_separator, gw_phase_vcf=args.gw_phase_vcf,
                 min_conf=args.gw_phase_vcf_min_confidence, chrom_of_interest=args.chr)
-        with bgzf.BGZFWriter(args.o + ".vcf.gz") as f:       # what `bgzip -f` writes (phaser.py:1851)
-            f.write(text)
+        # what `bgzip -f` + `tabix -f -p vcf [--csi]` write (phaser.py:1847-1853); --csi iff the input VCF has a .csi (:131)
+        tabix.write_vcf_with_index(args.o + ".vcf.gz", text, csi=os.path.isfile(args.vcf + ".csi"))
     _t = _trace(_t, "vcf out")
     total_time = time.time() - start_time
     say('')

@@ -165,3 +165,44 @@ def test_cli_empty_bam_is_the_reference_fatal_error(hostsim, tmp_path, capsys):
         cli.run(cli.build_parser().parse_args(base + ["--bam", empty]), engine=hostsim)
     assert e.value.code == 1 and "No reads could be matched to variants" in capsys.readouterr().out
     cli.run(cli.build_parser().parse_args(base + ["--bam", empty + "," + c["sams"][0]]), engine=hostsim)   # an empty BAM beside a real one
+
+
+@pytest.mark.parametrize("csi", [False, True])
+def test_tabix_index_finds_exactly_the_overlapping_records(tmp_path, csi):
+    """Region queries answered through the written index (bins + chunks + linear index, virtual offsets into the
+    BGZF file) == brute-force filtering of the text; spans several BGZF blocks, contigs and bin levels."""
+    import random
+    from phaser_b200 import tabix
+    rnd = random.Random(5)
+    lines = ["##fileformat=VCFv4.2\n", "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS1\n"]
+    recs = []
+    for chrom, L in (("1", 248_000_000), ("2", 3_000_000), ("X", 40_000)):
+        pos = sorted(rnd.randrange(1, L) for _ in range(4000))
+        for p in pos:
+            ref = "A" * rnd.choice([1, 1, 1, 2, 30])
+            info = "END=%d" % (p + 70000) if rnd.random() < 0.01 else "AF=0.1"
+            lines.append("%s\t%d\t.\t%s\tC\t50\tPASS\t%s\tGT\t0|1:%s\n" % (chrom, p, ref, info, "x" * rnd.randrange(0, 60)))
+            recs.append((chrom,) + tabix.record_span(lines[-1].split("\t", 8)) + (lines[-1],))
+    path = str(tmp_path / "t.vcf.gz")
+    idx_path = tabix.write_vcf_with_index(path, "".join(lines), csi=csi)
+    assert idx_path.endswith(".csi" if csi else ".tbi")
+    assert bgzf.read_all(path).decode() == "".join(lines)
+    idx = tabix.read_index(idx_path)
+    assert idx["names"] == ["1", "2", "X"] and idx["format"][:5] == (2, 1, 2, 0, ord("#"))
+    assert len("".join(lines)) > 8 * bgzf.MAX_BLOCK         # several BGZF blocks
+    for _ in range(300):
+        chrom, L = rnd.choice([("1", 248_000_000), ("2", 3_000_000), ("X", 40_000), ("Y", 1000)])
+        b = rnd.randrange(0, L); e = b + rnd.choice([1, 100, 20_000, 300_000, 50_000_000])
+        exp = [r[3] for r in recs if r[0] == chrom and r[1] < e and r[2] > b]
+        assert tabix.query(path, idx, chrom, b, e) == exp
+
+
+def test_cli_writes_a_tabix_index_for_its_vcf(hostsim, tmp_path):
+    from phaser_b200 import tabix
+    c, got = _run_cli(hostsim, "rna_two_bams", tmp_path)
+    o = str(tmp_path / "out")
+    idx = tabix.read_index(o + ".vcf.gz.tbi")
+    body = [l for l in got["vcf"].splitlines(keepends=True) if not l.startswith("#")]
+    assert sum(r["bins"][tabix.META_BIN][1][0] for r in idx["refs"]) == len(body)
+    first = body[0].split("\t")
+    assert tabix.query(o + ".vcf.gz", idx, first[0], int(first[1]) - 1, int(first[1])) == [body[0]]
