@@ -231,6 +231,8 @@ def run_ours(a):
         # built ONCE here like a BAM is parsed once; phz_map_reads_packed copies + expands them inside the timed region
         host_np = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in reads.items()}
         packed = eng.pack_reads(host_np, len(g.contigs), lib=E.lib, page_locked=True)
+        if world > 1:
+            host_np = {}                  # N ranks share one host: keep only the packed form
         dt, d2h = timed_e2e(packed, a.steps)
         e2e = {"value": V * world / dt, "unit": "het-SNVs/s", "h2d_bytes_per_step": int(packed.nbytes),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3,
@@ -243,20 +245,25 @@ def run_ours(a):
             e2e["stages_ms"]["wall_ms"] = round(wall, 3)
             E.set_profiling(1)
         del packed
-        # for comparison: the same call with the plain SoA arrays (phz_map_reads_host), 2 timed steps
-        def to_host(v):
-            h = torch.from_numpy(v) if isinstance(v, np.ndarray) else v
-            try:
-                return h.pin_memory()
-            except RuntimeError:          # not enough lockable memory: pageable copies are slower but still valid
-                return h
-        host = {k: (to_host(v) if k != "contig_rec_off" else v) for k, v in host_np.items()}
+        # for comparison (single GPU only): the same call with the plain SoA arrays (phz_map_reads_host), 2 timed steps
+        if world == 1:
+            def to_host(v):
+                h = torch.from_numpy(v) if isinstance(v, np.ndarray) else v
+                try:
+                    return h.pin_memory()
+                except RuntimeError:          # not enough lockable memory: pageable copies are slower but still valid
+                    return h
+            host = {}
+            for k in list(host_np.keys()):     # one array at a time: never two full copies of the sample in host memory
+                v = host_np.pop(k)
+                host[k] = to_host(v) if k != "contig_rec_off" else v
+                del v
+            h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
+            dt, d2h = timed_e2e(host, min(2, a.steps))
+            e2e_plain = {"value": V * world / dt, "unit": "het-SNVs/s", "h2d_bytes_per_step": int(h2d),
+                         "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "host_form": "plain SoA arrays (phz_map_reads_host)"}
+            del host
         del host_np
-        h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
-        dt, d2h = timed_e2e(host, min(2, a.steps))
-        e2e_plain = {"value": V * world / dt, "unit": "het-SNVs/s", "h2d_bytes_per_step": int(h2d),
-                     "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "host_form": "plain SoA arrays (phz_map_reads_host)"}
-        del host
     stages = None
     if a.profile:
         E.set_profiling(2)
