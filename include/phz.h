@@ -156,7 +156,8 @@ int phz_download(phz_ctx* ctx, const char* name, void* h_dst, int64_t dst_bytes)
  * of a run with one wait. */
 int phz_download_async(phz_ctx* ctx, const char* name, void* h_dst, int64_t dst_bytes);
 /* counters[16]: n_tuples, entries, groups, pairs, distinct pairs, edges, dropped, members, blocks,
- * hard blocks, final blocks, read-list entries, n_candidates, n_bams, 0, 0 */
+ * hard blocks, final blocks, read-list entries, n_candidates, n_bams, fragment runs re-sorted in place by the
+ * graph stage, 1 if that stage fell back to the full-key sort */
 int phz_counters(phz_ctx* ctx, int64_t* counters);
 /* Tuning / A-B switches.  "k1_mode": 3 = tile kernel (het-site slab staged in shared memory by a TMA
  * bulk copy, CTA scan, one atomic cursor per tile, dense coalesced emission) + streaming permute into

@@ -279,7 +279,7 @@ int phz_counters(phz_ctx* ctx, int64_t* c) {
   PHZ_TRY
   auto& p = ctx->p;
   int64_t v[16] = {p.n_tuples, p.NE, p.NG, p.NP, p.NX, p.E, (int64_t)p.n_dropped, p.NM, p.NB, p.NH, p.NF, p.NRL,
-                   p.n_cand, p.n_bams, 0, 0};
+                   p.n_cand, p.n_bams, p.n_runs_resorted, p.full_sort_fallback ? 1 : 0};
   for (int i = 0; i < 16; ++i) c[i] = v[i];
   PHZ_CATCH
 }
@@ -290,6 +290,7 @@ int phz_set_option(phz_ctx* ctx, const char* name, int64_t value) {
   if (n == "k1_mode") ctx->p.k1_mode = (int)value;
   else if (n == "k1_min_ctas") ctx->p.k1_min_ctas = (int)value;
   else if (n == "big_total_threshold") ctx->p.big_total_thr = (u32)value;
+  else if (n == "frag_run_limit") ctx->p.frag_run_limit = value < 1 ? 1 : value;
   else throw PhzError("unknown option: " + n);
   PHZ_CATCH
 }

@@ -446,6 +446,7 @@ struct Pipeline {
   Buf<B, u32> scalars, kstar_d;                     // scalars: [0]=max_tot [1]=err flags [2]=dropped [3]=n_big_tot
   Buf<B, u32> big_tot;                              // c_total values above big_total_thr (unordered, with repeats)
   int64_t NX = 0, E = 0; u32 max_tot = 0; int64_t NBT = 0; u32 big_total_thr = 2048;
+  int64_t frag_run_limit = 1024; int64_t n_runs_resorted = 0; bool full_sort_fallback = false;
   // ------------------------------------------------------------------ blocks
   Buf<B, u32> parent, deg, root, m_flag, m_scan, m_list, m_key, m_key2, m_val2, members;
   Buf<B, u32> b_flag, b_scan, blk_off, blk_of, pos_in_blk, blk_contig_rank, blk_order, blk_pos;
@@ -812,7 +813,37 @@ struct Pipeline {
     if (fb + vb > 64) throw PhzError("fragment/variant id space too large");
     u64* k1 = s_key.ensure(n); u64* k2 = s_key2.ensure(n); u32* x1 = s_val.ensure(n); u32* x2 = s_val2.ensure(n);
     be.for_each(n, PHZ_LAMBDA(int64_t t) { k1[t] = ((u64)gf[t] << vb) | (u64)gv[t]; x1[t] = (u32)t; });
-    be.sort_pairs(k1, k2, x1, x2, n, 0, fb + vb);
+    // Tuples arrive in (record, variant) order, so a STABLE sort on the fragment bits alone (4 radix passes instead
+    // of 6) already leaves a fragment's tuples variant-sorted unless its records interleave (overlapping mates, a
+    // spliced mate jumping over the other).  The first tuple of each fragment checks its run and insertion-sorts it
+    // in place when needed (stable: equal keys keep tuple order).  Runs too long for that raise a flag and the
+    // whole array is sorted on the full key instead.
+    {
+      u32* sc = scalars.ensure(8); be.memset0(sc, 8 * sizeof(u32));
+      be.sort_pairs(k1, k2, x1, x2, n, vb, fb + vb);
+      const int64_t nn = n; const int64_t MAXRUN = frag_run_limit;
+      be.for_each(n, PHZ_LAMBDA(int64_t i) {
+        const u64 f = k2[i] >> vb;
+        if (i > 0 && (load_volatile(&k2[i - 1]) >> vb) == f) return;           // not the first tuple of its fragment
+        int64_t end = i + 1; bool sorted = true;
+        while (end < nn && (load_volatile(&k2[end]) >> vb) == f) {
+          if (end - i >= MAXRUN) { atomic_max(&sc[4], 1u); return; }
+          if (k2[end] < k2[end - 1]) sorted = false;
+          ++end;
+        }
+        if (sorted) return;
+        atomic_add(&sc[5], 1u);
+        for (int64_t j = i + 1; j < end; ++j) {
+          u64 key = k2[j]; u32 val = x2[j]; int64_t m = j;
+          while (m > i && k2[m - 1] > key) { k2[m] = k2[m - 1]; x2[m] = x2[m - 1]; --m; }
+          k2[m] = key; x2[m] = val;
+        }
+      });
+      u32 h2[2] = {0, 0};
+      if (n > 0) be.d2h(h2, sc + 4, sizeof(h2));
+      n_runs_resorted = h2[1]; full_sort_fallback = h2[0] != 0;
+      if (full_sort_fallback) be.sort_pairs(k1, k2, x1, x2, n, 0, fb + vb);
+    }
     be.stage("graph.entries");
     u32* sf = s_flag.ensure(n + 1); u32* ss = s_scan.ensure(n + 2);
     be.for_each(n, PHZ_LAMBDA(int64_t i) {
@@ -1206,7 +1237,6 @@ struct Pipeline {
     be.exclusive_scan_u32(rf, rsn, n);
     NRL = n > 0 ? (int64_t)fetch_u32(rsn + n) : 0;
     u32* k32 = rl_k32.ensure(NRL); u32* k32b = rl_k32b.ensure(NRL); u32* tt = rl_t.ensure(NRL); u32* tt2 = rl_t2.ensure(NRL);
-    u64* k64 = rl_k64.ensure(NRL); u64* k64b = rl_k64b.ensure(NRL);
     be.for_each(n, PHZ_LAMBDA(int64_t t) { if (rf[t]) { k32[rsn[t]] = gv[t]; tt[rsn[t]] = (u32)t; } });
     be.sort_pairs32(k32, k32b, tt, tt2, NRL, 0, vb);          // by variant, tuple order kept
     int bb = ceil_log2_host((u64)(nb > 1 ? nb : 2));
@@ -1214,11 +1244,11 @@ struct Pipeline {
     if (fbits + bb + 1 > 32) throw PhzError("row key of read_lists does not fit 32 bits");
     be.for_each(NRL, PHZ_LAMBDA(int64_t i) {
       u32 t = tt2[i]; u32 v = gv[t]; u32 hap = (gc[t] & 3) ^ vh[v];
-      k64[i] = ((((u64)vfin[v] << bb) | (gc[t] >> 2)) << 1) | hap;
+      k32[i] = (((vfin[v] << bb) | (u32)(gc[t] >> 2)) << 1) | hap;
     });
-    be.sort_pairs(k64, k64b, tt2, tt, NRL, 0, fbits + bb + 1);
+    be.sort_pairs32(k32, k32b, tt2, tt, NRL, 0, fbits + bb + 1);      // by (block, BAM, haplotype), variant order kept
     u32* of = rl_frag.ensure(NRL); u32* ov = rl_var.ensure(NRL); u32* orow = rl_row.ensure(NRL);
-    be.for_each(NRL, PHZ_LAMBDA(int64_t i) { u32 t = tt[i]; of[i] = gf[t]; ov[i] = gv[t]; orow[i] = (u32)k64b[i]; });
+    be.for_each(NRL, PHZ_LAMBDA(int64_t i) { u32 t = tt[i]; of[i] = gf[t]; ov[i] = gv[t]; orow[i] = k32b[i]; });
     be.stage("read_lists.end");
     return NRL;
   }

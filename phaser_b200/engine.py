@@ -114,7 +114,8 @@ def load_library(path=LIB_PATH):
 
 _DT = {1: np.uint8, 2: np.int16, 4: np.uint32, 8: np.uint64}
 COUNTER_NAMES = ["n_tuples", "entries", "groups", "pairs", "distinct_pairs", "edges", "dropped", "members", "blocks",
-                 "hard_blocks", "final_blocks", "read_list_entries", "n_candidates", "n_bams"]
+                 "hard_blocks", "final_blocks", "read_list_entries", "n_candidates", "n_bams", "frag_runs_resorted",
+                 "full_sort_fallback"]
 
 
 def _as_torch(a: np.ndarray, device, pin=False):

@@ -229,3 +229,26 @@ def test_result_buffer_views_equal_private_copies(gpu, tmp_path):
     assert set(a.arrays) == set(b.arrays)
     for k in a.arrays:
         assert a.arrays[k].dtype == b.arrays[k].dtype and np.array_equal(a.arrays[k], b.arrays[k]), k
+
+
+def test_fragment_sort_fixup_and_fallback_agree(gpu, tmp_path):
+    """The graph stage sorts tuples on the fragment bits only and repairs interleaved runs in place; with
+    frag_run_limit = 1 every multi-tuple fragment takes the full-key sort instead.  Same arrays either way, and the
+    case (short inserts: overlapping mates) must exercise the in-place repair."""
+    from phaser_b200 import pipeline
+    vcf, sams = util.make_case(tmp_path, 44, 400, 8000, n_bams=2, switch_per_base=0.02, insert_lo=60, insert_hi=200)
+    vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+    P = pipeline.PhaseParams()
+    a = pipeline.run_path(gpu, vt, [gpu.upload_reads(b) for b in batches], P, n_fragments=len(fd.names))
+    assert a.counters["frag_runs_resorted"] > 0 and a.counters["full_sort_fallback"] == 0
+    gpu.set_option("frag_run_limit", 1)
+    try:
+        b = pipeline.run_path(gpu, vt, [gpu.upload_reads(b) for b in batches], P, n_fragments=len(fd.names))
+    finally:
+        gpu.set_option("frag_run_limit", 1024)
+    assert b.counters["full_sort_fallback"] == 1
+    for k in a.arrays:
+        assert np.array_equal(a.arrays[k], b.arrays[k]), k
+    exp, _ = util.oracle_outputs(vcf, sams)
+    got, _, _ = util.product_outputs(gpu, vcf, sams)
+    assert not compare.diff_outputs(exp, got)
