@@ -233,15 +233,26 @@ def run_ours(a):
     e2e_plain = None
     checks = None
     if not a.no_e2e:
-        def timed_e2e(src, n_steps):
+        def timed_e2e(src, n_steps, prefetch=False):
+            """prefetch: samples are looped GTEx-batch style -- every step first starts the copy of the NEXT sample's
+            buffers on the copy stream (phz_prefetch_packed), then runs the path on the sample whose copy was started one
+            step earlier; each timed step still contains one full host->device copy and one result read-back."""
+            if prefetch:
+                E.prefetch_packed(src)            # the first sample's copy, before the warm-up
             for _ in range(2):
+                if prefetch:
+                    E.prefetch_packed(src)
                 r2 = step(True, src)
             barrier()
             t0 = time.perf_counter()
             for _ in range(n_steps):
+                if prefetch:
+                    E.prefetch_packed(src)
                 r2 = step(True, src)
             barrier()
             dt = (time.perf_counter() - t0) / n_steps
+            if prefetch:
+                r2 = step(True, src)              # drain the last staged copy (untimed)
             tt = torch.tensor([dt], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -253,9 +264,13 @@ def run_ours(a):
         packed = eng.pack_reads(host_np, len(g.contigs), lib=E.lib, page_locked=True)
         if world > 1:
             host_np = {}                  # N ranks share one host: keep only the packed form
-        dt, d2h = timed_e2e(packed, a.steps)
+        dt1, d2h = timed_e2e(packed, a.steps)                      # one sample at a time: copy, then path
+        dt, d2h = timed_e2e(packed, a.steps, prefetch=True)        # samples looped, next copy under the current path
         e2e = {"value": V * world / dt, "unit": "het-SNVs/s", "h2d_bytes_per_step": int(packed.nbytes),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3,
+               "mode": "samples looped; the copy of sample i+1 (phz_prefetch_packed, copy stream) runs under the path of sample i; "
+                       "every step holds one full copy in and one result read-back",
+               "single_sample_ms": dt1 * 1e3, "single_sample_value": V * world / dt1,
                "host_form": "packed transport (lossless): per-record counts instead of offsets, 2-bit bases + %d exceptions, "
                             "%d-bit base-quality indices; expanded on the device" % (packed.n_exceptions, packed.qual_bits)}
         checks = full_size_checks(E, pipeline, vt, reads, packed, P, n_pairs) if rank == 0 else None

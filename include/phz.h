@@ -117,6 +117,12 @@ void phz_packed_free(phz_packed_host* p);
 /* phz_map_reads with the packed HOST form: copies it to the device on the context's stream, expands it there and
  * runs K1.  The end-to-end entry point bench.py times and the one the command line uses. */
 int phz_map_reads_packed(phz_ctx* ctx, const phz_packed_reads* packed, int baseq, double isize_cutoff, int64_t* n_candidates);
+/* Optional: starts the copy of a sample's packed buffers on the context's copy stream and returns at once.  A later
+ * phz_map_reads_packed with the same buffers waits for that copy instead of issuing its own, so a loop over samples
+ * (the GTEx-style batch) hides the path of sample i under the copy of sample i+1.  The context has two transport
+ * slots: at most one prefetch may be outstanding while another sample is being mapped.  The host buffers must stay
+ * untouched until the matching phz_map_reads_packed has returned. */
+int phz_prefetch_packed(phz_ctx* ctx, const phz_packed_reads* packed);
 
 /* Exact histogram of the alignment scores of the tuples the reference mapper would print; the host
  * derives numpy.percentile from it (phaser.py:545-553).  d_hist: PHZ_AS_BINS uint64 on the device. */

@@ -8,20 +8,34 @@
 
 using namespace phz;
 
+// What one sample's host -> device copy lands in.  Two slots: while K1 and the rest of the path work on one, the
+// copy stream can already fill the other with the next sample (phz_prefetch_packed).
+struct TransportSlot {
+  Buf<PHZ_BACKEND, int32_t> pos, tlen; Buf<PHZ_BACKEND, int16_t> as; Buf<PHZ_BACKEND, u32> frag, cig;      // copied as they are
+  Buf<PHZ_BACKEND, uint16_t> ncg, lsq; Buf<PHZ_BACKEND, u8> seq2, qualp, exc, qtab; Buf<PHZ_BACKEND, u64> exi;  // packed form
+  const void* tag = nullptr;      // host buffer the staged copy came from
+  bool staged = false;
+  u64 seq = 0;
+  void* ready = nullptr;          // backend event: all copies of the staged sample have landed
+  void bind(PHZ_BACKEND* b) {
+    pos.bind(b); tlen.bind(b); as.bind(b); frag.bind(b); cig.bind(b); ncg.bind(b); lsq.bind(b); seq2.bind(b); qualp.bind(b);
+    exc.bind(b); qtab.bind(b); exi.bind(b);
+  }
+};
+
 struct phz_ctx {
   Pipeline<PHZ_BACKEND> p;
-  // staging for phz_map_reads_host
-  Buf<PHZ_BACKEND, int32_t> st_pos, st_tlen; Buf<PHZ_BACKEND, int16_t> st_as; Buf<PHZ_BACKEND, u32> st_frag, st_coff, st_cig;
-  Buf<PHZ_BACKEND, u64> st_soff; Buf<PHZ_BACKEND, u8> st_seq, st_qual;
-  // packed transport (phz_map_reads_packed): what arrives over PCIe before it is expanded into st_*
-  Buf<PHZ_BACKEND, uint16_t> pk_ncg, pk_lsq; Buf<PHZ_BACKEND, u8> pk_seq2, pk_qualp, pk_exc, pk_qtab; Buf<PHZ_BACKEND, u64> pk_exi;
   GeneAE<PHZ_BACKEND> ae;
+  TransportSlot slot[2];
+  int last_slot = 1;
+  u64 stage_seq = 0;
+  const u32* cur_frag = nullptr;   // fragment ids of the sample mapped last through a host entry point
+  // expanded arrays (device layout of phz_reads) that the copies / expansion kernels produce for K1
+  Buf<PHZ_BACKEND, u32> st_coff; Buf<PHZ_BACKEND, u64> st_soff; Buf<PHZ_BACKEND, u8> st_seq, st_qual;
   phz_ctx() {
     PHZ_BACKEND* b = &p.be;
-    ae.bind(b);
-    pk_ncg.bind(b); pk_lsq.bind(b); pk_seq2.bind(b); pk_qualp.bind(b); pk_exc.bind(b); pk_qtab.bind(b); pk_exi.bind(b);
-    st_pos.bind(b); st_tlen.bind(b); st_as.bind(b); st_frag.bind(b); st_coff.bind(b); st_cig.bind(b); st_soff.bind(b);
-    st_seq.bind(b); st_qual.bind(b);
+    ae.bind(b); slot[0].bind(b); slot[1].bind(b);
+    st_coff.bind(b); st_soff.bind(b); st_seq.bind(b); st_qual.bind(b);
   }
 };
 
@@ -97,12 +111,14 @@ int phz_map_reads_host(phz_ctx* ctx, const phz_reads* h, int baseq, double isize
   auto& be = ctx->p.be;
   int64_t R = h->n_records;
   phz_reads d = *h;
-  be.h2d(ctx->st_pos.ensure(R), h->pos, R * 4); d.pos = ctx->st_pos.p;
-  be.h2d(ctx->st_tlen.ensure(R), h->tlen, R * 4); d.tlen = ctx->st_tlen.p;
-  be.h2d(ctx->st_as.ensure(R), h->aln_score, R * 2); d.aln_score = ctx->st_as.p;
-  be.h2d(ctx->st_frag.ensure(R), h->frag, R * 4); d.frag = ctx->st_frag.p;
+  TransportSlot& S = ctx->slot[ctx->slot[0].staged ? 1 : 0];
+  if (S.staged) throw PhzError("phz_map_reads_host: both transport slots hold prefetched samples");
+  be.h2d(S.pos.ensure(R), h->pos, R * 4); d.pos = S.pos.p;
+  be.h2d(S.tlen.ensure(R), h->tlen, R * 4); d.tlen = S.tlen.p;
+  be.h2d(S.as.ensure(R), h->aln_score, R * 2); d.aln_score = S.as.p;
+  be.h2d(S.frag.ensure(R), h->frag, R * 4); d.frag = S.frag.p; ctx->cur_frag = S.frag.p;
   be.h2d(ctx->st_coff.ensure(R + 1), h->cigar_off, (R + 1) * 4); d.cigar_off = ctx->st_coff.p;
-  be.h2d(ctx->st_cig.ensure(h->n_cigar_ops), h->cigar, h->n_cigar_ops * 4); d.cigar = ctx->st_cig.p;
+  be.h2d(S.cig.ensure(h->n_cigar_ops), h->cigar, h->n_cigar_ops * 4); d.cigar = S.cig.p;
   be.h2d(ctx->st_soff.ensure(R + 1), h->seq_off, (R + 1) * 8); d.seq_off = (const uint64_t*)ctx->st_soff.p;
   be.h2d(ctx->st_seq.ensure((h->n_bases + 1) / 2), h->seq, (h->n_bases + 1) / 2); d.seq = ctx->st_seq.p;
   be.h2d(ctx->st_qual.ensure(h->n_bases), h->qual, h->n_bases); d.qual = ctx->st_qual.p;
@@ -111,35 +127,85 @@ int phz_map_reads_host(phz_ctx* ctx, const phz_reads* h, int baseq, double isize
   PHZ_CATCH
 }
 
+static void check_packed(const phz_packed_reads* h) {
+  const int bits = h->qual_bits;
+  if (bits != 1 && bits != 2 && bits != 4 && bits != 8) throw PhzError("packed reads: qual_bits must be 1, 2, 4 or 8");
+}
+
+// sizes the slot's buffers for `h` (may reallocate: call before any copy is enqueued)
+static void size_slot(TransportSlot& S, const phz_packed_reads* h) {
+  const int64_t R = h->n_records, NB = h->n_bases, NC = h->n_cigar_ops, NX = h->n_exceptions;
+  S.ncg.ensure(R); S.lsq.ensure(R); S.qualp.ensure((NB * h->qual_bits + 7) / 8 + 16); S.qtab.ensure(256);
+  S.seq2.ensure((NB + 3) / 4 + 16); S.exi.ensure(NX); S.exc.ensure(NX);
+  S.cig.ensure(NC); S.pos.ensure(R); S.tlen.ensure(R); S.as.ensure(R); S.frag.ensure(R);
+}
+
+int phz_prefetch_packed(phz_ctx* ctx, const phz_packed_reads* h) {
+  PHZ_TRY
+  auto& be = ctx->p.be;
+  check_packed(h);
+  int si = ctx->slot[0].staged ? 1 : (ctx->slot[1].staged ? 0 : 1 - ctx->last_slot);
+  TransportSlot& S = ctx->slot[si];
+  if (S.staged) throw PhzError("phz_prefetch_packed: both transport slots are already staged");
+  const int64_t R = h->n_records, NB = h->n_bases, NC = h->n_cigar_ops, NX = h->n_exceptions;
+  size_slot(S, h);
+  if (!S.ready) S.ready = be.new_event();
+  be.copy_begin();        // the slot may still be read by kernels queued on the main stream
+  be.h2d_copy(S.ncg.p, h->n_cigar, R * 2); be.h2d_copy(S.lsq.p, h->l_seq, R * 2);
+  be.h2d_copy(S.qualp.p, h->qualp, (NB * h->qual_bits + 7) / 8); be.h2d_copy(S.qtab.p, h->qual_table, 256);
+  be.h2d_copy(S.seq2.p, h->seq2, (NB + 3) / 4); be.h2d_copy(S.exi.p, h->exc_index, NX * 8); be.h2d_copy(S.exc.p, h->exc_code, NX);
+  be.h2d_copy(S.cig.p, h->cigar, NC * 4); be.h2d_copy(S.pos.p, h->pos, R * 4); be.h2d_copy(S.tlen.p, h->tlen, R * 4);
+  be.h2d_copy(S.as.p, h->aln_score, R * 2); be.h2d_copy(S.frag.p, h->frag, R * 4);
+  be.copy_record(S.ready);
+  S.tag = (const void*)h->seq2; S.staged = true; S.seq = ++ctx->stage_seq;
+  PHZ_CATCH
+}
+
 int phz_map_reads_packed(phz_ctx* ctx, const phz_packed_reads* h, int baseq, double isize_cutoff, int64_t* n_candidates) {
   PHZ_TRY
   auto& be = ctx->p.be;
+  check_packed(h);
   const int64_t R = h->n_records, NB = h->n_bases, NC = h->n_cigar_ops, NX = h->n_exceptions;
   const int bits = h->qual_bits;
-  if (bits != 1 && bits != 2 && bits != 4 && bits != 8) throw PhzError("phz_map_reads_packed: qual_bits must be 1, 2, 4 or 8");
   phz_reads d; std::memset(&d, 0, sizeof(d));
   d.n_records = R; d.n_cigar_ops = NC; d.n_bases = NB; d.h_contig_rec_off = h->h_contig_rec_off;
-  // ---- host -> device on the copy stream, in the order the expansion needs it: counts, qualities, bases, then the
-  // arrays K1 reads as they are.  Each expansion kernel starts as soon as ITS input has landed and runs under the
-  // copies that follow, so only the PCIe time is on the critical path.
-  be.stage("h2d+unpack");
-  const int64_t n2 = (NB + 3) / 4, nq = (NB * bits + 7) / 8;
-  const uint16_t* ncg = ctx->pk_ncg.ensure(R); const uint16_t* lsq = ctx->pk_lsq.ensure(R);
-  const u8* qp = ctx->pk_qualp.ensure(nq + 16); const u8* qt = ctx->pk_qtab.ensure(256);
-  const u8* s2 = ctx->pk_seq2.ensure(n2 + 16); const u64* exi = ctx->pk_exi.ensure(NX); const u8* exc = ctx->pk_exc.ensure(NX);
+  // a sample staged by phz_prefetch_packed from these very buffers?  (oldest first)
+  int si = -1;
+  for (int k = 0; k < 2; ++k)
+    if (ctx->slot[k].staged && ctx->slot[k].tag == (const void*)h->seq2 && (si < 0 || ctx->slot[k].seq < ctx->slot[si].seq)) si = k;
+  const bool prefetched = si >= 0;
+  if (!prefetched) {
+    si = ctx->slot[0].staged ? 1 : (ctx->slot[1].staged ? 0 : 1 - ctx->last_slot);
+    if (ctx->slot[si].staged) throw PhzError("phz_map_reads_packed: both transport slots hold other prefetched samples");
+    size_slot(ctx->slot[si], h);
+  }
+  TransportSlot& S = ctx->slot[si];
+  const uint16_t* ncg = S.ncg.p; const uint16_t* lsq = S.lsq.p; const u8* qp = S.qualp.p; const u8* qt = S.qtab.p;
+  const u8* s2 = S.seq2.p; const u64* exi = S.exi.p; const u8* exc = S.exc.p;
   ctx->st_coff.ensure(R + 1); ctx->st_soff.ensure(R + 1);
   const int64_t nwq = (NB + 7) / 8, nws = (NB + 15) / 16;
   u64* qout = (u64*)ctx->st_qual.ensure((size_t)nwq * 8 + 16);
   u64* sout = (u64*)ctx->st_seq.ensure((size_t)nws * 8 + 16);
-  ctx->st_cig.ensure(NC); ctx->st_pos.ensure(R); ctx->st_tlen.ensure(R); ctx->st_as.ensure(R); ctx->st_frag.ensure(R);
-  be.copy_begin();
-  be.h2d_copy(ctx->pk_ncg.p, h->n_cigar, R * 2); be.h2d_copy(ctx->pk_lsq.p, h->l_seq, R * 2);
-  be.copy_fence();
-  be.h2d_copy(ctx->pk_qualp.p, h->qualp, nq); be.h2d_copy(ctx->pk_qtab.p, h->qual_table, 256);
+  d.cigar = S.cig.p; d.pos = S.pos.p; d.tlen = S.tlen.p; d.aln_score = S.as.p; d.frag = S.frag.p;
+  // ---- host -> device on the copy stream, in the order the expansion needs it: counts, qualities, bases, then the
+  // arrays K1 reads as they are.  Each expansion kernel starts as soon as ITS input has landed and runs under the
+  // copies that follow, so only the PCIe time is on the critical path.  With a prefetched sample the copies are
+  // already under way (or done): the main stream just waits for them.
+  be.stage("h2d+unpack");
+  const int64_t n2 = (NB + 3) / 4, nq = (NB * bits + 7) / 8;
+  if (prefetched) be.wait_event(S.ready);
+  else {
+    be.copy_begin();
+    be.h2d_copy(S.ncg.p, h->n_cigar, R * 2); be.h2d_copy(S.lsq.p, h->l_seq, R * 2);
+    be.copy_fence();
+    be.h2d_copy(S.qualp.p, h->qualp, nq); be.h2d_copy(S.qtab.p, h->qual_table, 256);
+  }
   be.exclusive_scan_u16_to_u32(ncg, ctx->st_coff.p, R); d.cigar_off = ctx->st_coff.p;
   be.exclusive_scan_u16_to_u64(lsq, ctx->st_soff.p, R); d.seq_off = (const uint64_t*)ctx->st_soff.p;
-  be.copy_fence();
-  be.h2d_copy(ctx->pk_seq2.p, h->seq2, n2); be.h2d_copy(ctx->pk_exi.p, h->exc_index, NX * 8); be.h2d_copy(ctx->pk_exc.p, h->exc_code, NX);
+  if (!prefetched) {
+    be.copy_fence();
+    be.h2d_copy(S.seq2.p, h->seq2, n2); be.h2d_copy(S.exi.p, h->exc_index, NX * 8); be.h2d_copy(S.exc.p, h->exc_code, NX);
+  }
   {   // base qualities: one logical thread per 8 bases = `bits` packed bytes in, 8 phred bytes out
     const u32 mask = (1u << bits) - 1;
     be.for_each(nwq, PHZ_LAMBDA(int64_t w) {
@@ -151,12 +217,11 @@ int phz_map_reads_packed(phz_ctx* ctx, const phz_packed_reads* h, int baseq, dou
     });
     d.qual = ctx->st_qual.p;
   }
-  be.copy_fence();
-  be.h2d_copy(ctx->st_cig.p, h->cigar, NC * 4); d.cigar = ctx->st_cig.p;
-  be.h2d_copy(ctx->st_pos.p, h->pos, R * 4); d.pos = ctx->st_pos.p;
-  be.h2d_copy(ctx->st_tlen.p, h->tlen, R * 4); d.tlen = ctx->st_tlen.p;
-  be.h2d_copy(ctx->st_as.p, h->aln_score, R * 2); d.aln_score = ctx->st_as.p;
-  be.h2d_copy(ctx->st_frag.p, h->frag, R * 4); d.frag = ctx->st_frag.p;
+  if (!prefetched) {
+    be.copy_fence();
+    be.h2d_copy(S.cig.p, h->cigar, NC * 4); be.h2d_copy(S.pos.p, h->pos, R * 4); be.h2d_copy(S.tlen.p, h->tlen, R * 4);
+    be.h2d_copy(S.as.p, h->aln_score, R * 2); be.h2d_copy(S.frag.p, h->frag, R * 4);
+  }
   {   // bases: one logical thread per 16 bases = 4 packed bytes in, 8 bytes out (A C G T -> 1 2 4 8, even index = high nibble)
     const u32* in32 = (const u32*)s2;
     be.for_each(nws, PHZ_LAMBDA(int64_t w) {
@@ -175,7 +240,8 @@ int phz_map_reads_packed(phz_ctx* ctx, const phz_packed_reads* h, int baseq, dou
     });
     d.seq = ctx->st_seq.p;
   }
-  be.copy_fence();
+  if (!prefetched) be.copy_fence();
+  S.staged = false; ctx->last_slot = si; ctx->cur_frag = S.frag.p;
   be.stage("h2d+unpack.end");
   ReadsView v = view_of(&d, ctx->p.nc);
   *n_candidates = ctx->p.map_reads(v, h->h_contig_rec_off, baseq, isize_cutoff);
@@ -186,7 +252,7 @@ int phz_as_histogram(phz_ctx* ctx, uint64_t* d_hist) { PHZ_TRY ctx->p.as_histogr
 
 int phz_commit_bam(phz_ctx* ctx, int bam_index, int32_t as_cutoff, const uint32_t* d_frag, int64_t* n_kept) {
   PHZ_TRY
-  const u32* f = d_frag ? d_frag : ctx->st_frag.p;
+  const u32* f = d_frag ? d_frag : ctx->cur_frag;
   if (!f && ctx->p.n_cand > 0) throw PhzError("phz_commit_bam: no fragment ids");
   *n_kept = ctx->p.commit_bam(bam_index, as_cutoff, f);
   PHZ_CATCH

@@ -215,6 +215,10 @@ struct DeviceBackend {
     PHZ_CUDA(cudaEventRecord(copy_ev[1], copy_stream));
     PHZ_CUDA(cudaStreamWaitEvent(stream, copy_ev[1], 0));
   }
+  // caller-owned events for copies that outlive the call that enqueued them (prefetch)
+  void* new_event() { cudaEvent_t e; PHZ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); return (void*)e; }
+  void copy_record(void* ev) { PHZ_CUDA(cudaEventRecord((cudaEvent_t)ev, copy_stream)); }
+  void wait_event(void* ev) { PHZ_CUDA(cudaStreamWaitEvent(stream, (cudaEvent_t)ev, 0)); }
   void sync() { PHZ_CUDA(cudaStreamSynchronize(stream)); }
 
   template <class F>
@@ -337,6 +341,9 @@ struct HostSimBackend {
   void copy_begin() {}
   void h2d_copy(void* dst, const void* src, size_t bytes) { if (bytes) std::memcpy(dst, src, bytes); }
   void copy_fence() {}
+  void* new_event() { return (void*)1; }
+  void copy_record(void*) {}
+  void wait_event(void*) {}
   void sync() {}
 
   template <class F>

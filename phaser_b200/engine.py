@@ -54,7 +54,7 @@ EXPORTS = ["phz_last_error", "phz_backend_name", "phz_create", "phz_destroy", "p
            "phz_fragdict_create", "phz_fragdict_destroy", "phz_fragdict_size", "phz_fragdict_name", "phz_read_alignments",
            "phz_host_reads_view", "phz_host_reads_free", "phz_set_haplo_blacklist", "phz_write_sam",
            "phz_set_indel_alleles", "phz_pack_reads", "phz_packed_view", "phz_packed_bytes", "phz_packed_free",
-           "phz_map_reads_packed", "phz_gene_ae_pairs"]
+           "phz_map_reads_packed", "phz_prefetch_packed", "phz_gene_ae_pairs"]
 
 
 def _declare(lib):
@@ -101,6 +101,7 @@ def _declare(lib):
     lib.phz_packed_bytes.argtypes = [c_void_p]
     lib.phz_packed_free.argtypes = [c_void_p]
     lib.phz_map_reads_packed.argtypes = [c_void_p, POINTER(phz_packed_reads), c_int, c_double, POINTER(c_int64)]
+    lib.phz_prefetch_packed.argtypes = [c_void_p, POINTER(phz_packed_reads)]
     lib.phz_gene_ae_pairs.argtypes = [c_void_p, POINTER(phz_ae_input), POINTER(c_int64)]
     return lib
 
@@ -361,6 +362,10 @@ class Engine:
         n = c_int64(0)
         self._check(self.lib.phz_map_reads_packed(self.ctx, byref(packed.view), int(baseq), float(isize_cutoff), byref(n)))
         return n.value
+
+    def prefetch_packed(self, packed: PackedReads):
+        """Start copying `packed` to the device in the background; the next map_reads_packed(packed) uses that copy."""
+        self._check(self.lib.phz_prefetch_packed(self.ctx, byref(packed.view)))
 
     def as_histogram(self):
         h = torch.zeros(AS_BINS, dtype=torch.int64, device=self.device)

@@ -252,3 +252,26 @@ def test_fragment_sort_fixup_and_fallback_agree(gpu, tmp_path):
     exp, _ = util.oracle_outputs(vcf, sams)
     got, _, _ = util.product_outputs(gpu, vcf, sams)
     assert not compare.diff_outputs(exp, got)
+
+
+def test_prefetched_samples_give_the_same_results(gpu, tmp_path):
+    """Loop of samples with the next copy prefetched on the copy stream == each sample run on its own."""
+    from phaser_b200 import pipeline, engine as eng
+    P = pipeline.PhaseParams()
+    samples = []
+    for seed in (46, 47):
+        vcf, sams = util.make_case(tmp_path, seed, 300, 20000, n_bams=1, switch_per_base=0.02)
+        vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+        packed = eng.pack_reads(batches[0], len(vt.contigs), lib=gpu.lib, page_locked=True)
+        alone = pipeline.run_path(gpu, vt, [gpu.upload_reads(batches[0])], P, n_fragments=len(fd.names))
+        samples.append((vt, packed, len(fd.names), alone))
+    gpu.prefetch_packed(samples[0][1])
+    for it in range(6):
+        vt, packed, nf, alone = samples[it % 2]
+        gpu.prefetch_packed(samples[(it + 1) % 2][1])
+        got = pipeline.run_path(gpu, vt, [packed], P, n_fragments=nf)
+        assert got.counters == alone.counters
+        for k in alone.arrays:
+            assert np.array_equal(alone.arrays[k], got.arrays[k]), (it, k)
+    vt, packed, nf, alone = samples[0]
+    pipeline.run_path(gpu, vt, [packed], P, n_fragments=nf)          # drain

@@ -157,3 +157,35 @@ def test_fragment_sort_fixup_and_fallback_agree(hostsim, tmp_path):
     exp, _ = util.oracle_outputs(vcf, sams)
     got, _, _ = util.product_outputs(hostsim, vcf, sams)
     assert not compare.diff_outputs(exp, got)
+
+
+def test_prefetched_packed_sample_is_the_one_mapped(hostsim, tmp_path):
+    """phz_prefetch_packed stages a sample in the free transport slot; phz_map_reads_packed with the same buffers
+    consumes the oldest staged copy; two slots, a third outstanding prefetch is refused."""
+    from phaser_b200 import engine as eng
+    vcf, sams = util.make_case(tmp_path, 45, 200, 1500, n_bams=2)
+    vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+    hostsim.set_variants(vt)
+    packs = [eng.pack_reads(b, len(vt.contigs), lib=hostsim.lib) for b in batches]
+    want = []
+    for b in batches:
+        hostsim.map_reads(hostsim.upload_reads(b), 10, 0.0)
+        want.append([hostsim.download(k).copy() for k in ("t_rec", "t_var", "t_misc")])
+    hostsim.prefetch_packed(packs[0]); hostsim.prefetch_packed(packs[1])
+    with pytest.raises(eng.PhzError, match="both transport slots"):
+        hostsim.prefetch_packed(packs[0])
+    for order in ((1, 0), (0, 1)):
+        for i in order:
+            hostsim.map_reads_packed(packs[i], 10, 0.0)
+            got = [hostsim.download(k).copy() for k in ("t_rec", "t_var", "t_misc")]
+            assert all(np.array_equal(a, b) for a, b in zip(want[i], got))
+        hostsim.prefetch_packed(packs[0]); hostsim.prefetch_packed(packs[1])
+    hostsim.map_reads_packed(packs[0], 10, 0.0); hostsim.map_reads_packed(packs[1], 10, 0.0)       # drain
+    # steady-state loop: prefetch the next while mapping the current
+    hostsim.prefetch_packed(packs[0])
+    for i in (0, 1, 0, 1):
+        hostsim.prefetch_packed(packs[1 - i])
+        hostsim.map_reads_packed(packs[i], 10, 0.0)
+        got = [hostsim.download(k).copy() for k in ("t_rec", "t_var", "t_misc")]
+        assert all(np.array_equal(a, b) for a, b in zip(want[i], got))
+    hostsim.map_reads_packed(packs[0], 10, 0.0)
