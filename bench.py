@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--variants", type=int, default=2_000_000, help="het SNVs per sample (configs[1]: 2 M)")
     ap.add_argument("--exonic_frac", type=float, default=0.10)
     ap.add_argument("--seed", type=int, default=2000)
-    ap.add_argument("--cpu_pairs", type=int, default=750_000, help="read pairs of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu_pairs", type=int, default=2_000_000, help="read pairs of the bounded CPU-baseline sample")
     ap.add_argument("--no_e2e", action="store_true")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--k1_mode", type=int, default=3, help="3 tile kernel + permute (default), 2 fused look-back, 1 windowed two-pass, 0 generic two-pass")
