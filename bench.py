@@ -271,8 +271,8 @@ def run_ours(a):
                "mode": "samples looped; the copy of sample i+1 (phz_prefetch_packed, copy stream) runs under the path of sample i; "
                        "every step holds one full copy in and one result read-back",
                "single_sample_ms": dt1 * 1e3, "single_sample_value": V * world / dt1,
-               "host_form": "packed transport (lossless): per-record counts instead of offsets, 2-bit bases + %d exceptions, "
-                            "%d-bit base-quality indices; expanded on the device" % (packed.n_exceptions, packed.qual_bits)}
+               "host_form": "packed transport (lossless, include/phz.h phz_packed_reads), expanded on the device",
+               "host_form_coding": packed.coding, "bytes_per_record": packed.nbytes / float(R)}
         checks = full_size_checks(E, pipeline, vt, reads, packed, P, n_pairs) if rank == 0 else None
         if a.profile:
             E.set_profiling(2)

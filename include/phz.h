@@ -81,22 +81,41 @@ int phz_map_reads(phz_ctx* ctx, const phz_reads* reads, int baseq, double isize_
 int phz_map_reads_host(phz_ctx* ctx, const phz_reads* host_reads, int baseq, double isize_cutoff, int64_t* n_candidates);
 
 /* Lossless transport form of phz_reads for the host -> device copy (the copy is PCIe-bound: 146 bytes per 2x76 bp
- * record as plain SoA, ~53 packed).  What shrinks: offsets become per-record counts (scanned on the device), bases
- * become 2 bits (A C G T = 0..3) plus a sparse exception list for every other 4-bit code, base qualities become
- * indices into the BAM's own table of distinct phred values (1, 2, 4 or 8 bits, whatever the data needs).
+ * record as plain SoA, ~41 packed).  Every field takes the narrowest coding that loses nothing:
+ *   offsets      -> per-record counts (u8 or u16; scanned on the device), or nothing when all reads are equally long
+ *   pos          -> u16 difference to the previous record; 65535 = look the (signed 32-bit) difference up in the
+ *                   exception list (contig starts, long gaps); an inclusive scan on the device rebuilds pos
+ *   tlen         -> i16; -32768 = look the value up in the exception list (pairs spanning long introns)
+ *   aln_score    -> u8 index into the table of distinct scores when there are at most 256, else i16
+ *   cigar        -> u16 index into the table of distinct len<<4|op words when there are at most 65536, else u32
+ *   bases        -> 2 bits (A C G T = 0..3) plus a sparse exception list for every other 4-bit code
+ *   qualities    -> index into the BAM's own table of distinct phred values (1, 2, 4 or 8 bits, whatever it needs)
  * Everything is expanded again on the device into the phz_reads layout K1 reads; nothing is thresholded or dropped. */
 typedef struct phz_packed_reads {
   int64_t n_records;
   int64_t n_cigar_ops;
   int64_t n_bases;
   const int64_t* h_contig_rec_off; /* n_contigs+1 */
-  const int32_t* pos;
-  const int32_t* tlen;
-  const int16_t* aln_score;
+  const uint16_t* pos_delta;       /* pos[r] - pos[r-1] (pos[-1] = 0), 65535 = exception */
+  int64_t n_pos_exc;
+  const uint32_t* pos_exc_index;   /* ascending record index */
+  const int32_t* pos_exc_delta;
+  const int16_t* tlen16;           /* -32768 = exception */
+  int64_t n_tlen_exc;
+  const uint32_t* tlen_exc_index;
+  const int32_t* tlen_exc_value;
+  int32_t as_bits;                 /* 8: as_data = u8 indices into as_table; 16: as_data = i16 scores */
+  const void* as_data;
+  int16_t as_table[256];
   const uint32_t* frag;
-  const uint16_t* n_cigar;         /* CIGAR ops per record */
+  int32_t n_cigar_bits;            /* 8 or 16 */
+  const void* n_cigar;             /* CIGAR ops per record */
+  int32_t l_seq_const;             /* >= 0: every record has this many bases and l_seq is NULL */
   const uint16_t* l_seq;           /* bases per record */
-  const uint32_t* cigar;
+  int32_t cigar_bits;              /* 16: cigar = u16 indices into cigar_table; 32: cigar = the words */
+  const void* cigar;
+  int32_t n_cigar_table;
+  const uint32_t* cigar_table;
   const uint8_t* seq2;             /* (n_bases+3)/4 bytes; base i at bits 2*(i&3) of byte i>>2 */
   int64_t n_exceptions;            /* bases whose code is not A/C/G/T (N, IUPAC, '='), ascending base index */
   const uint64_t* exc_index;

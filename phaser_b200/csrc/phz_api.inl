@@ -11,15 +11,18 @@ using namespace phz;
 // What one sample's host -> device copy lands in.  Two slots: while K1 and the rest of the path work on one, the
 // copy stream can already fill the other with the next sample (phz_prefetch_packed).
 struct TransportSlot {
-  Buf<PHZ_BACKEND, int32_t> pos, tlen; Buf<PHZ_BACKEND, int16_t> as; Buf<PHZ_BACKEND, u32> frag, cig;      // copied as they are
-  Buf<PHZ_BACKEND, uint16_t> ncg, lsq; Buf<PHZ_BACKEND, u8> seq2, qualp, exc, qtab; Buf<PHZ_BACKEND, u64> exi;  // packed form
+  // the packed fields as they arrive (include/phz.h: phz_packed_reads)
+  Buf<PHZ_BACKEND, uint16_t> pos_d, lsq; Buf<PHZ_BACKEND, int16_t> tl16, as_tab; Buf<PHZ_BACKEND, u32> pos_xi, tl_xi, cig_tab;
+  Buf<PHZ_BACKEND, int32_t> pos_xv, tl_xv; Buf<PHZ_BACKEND, u8> as_raw, ncg, cig_raw, seq2, qualp, exc, qtab; Buf<PHZ_BACKEND, u64> exi;
+  Buf<PHZ_BACKEND, u32> frag;       // copied as it is; read again by phz_commit_bam
   const void* tag = nullptr;      // host buffer the staged copy came from
   bool staged = false;
   u64 seq = 0;
   void* ready = nullptr;          // backend event: all copies of the staged sample have landed
   void bind(PHZ_BACKEND* b) {
-    pos.bind(b); tlen.bind(b); as.bind(b); frag.bind(b); cig.bind(b); ncg.bind(b); lsq.bind(b); seq2.bind(b); qualp.bind(b);
-    exc.bind(b); qtab.bind(b); exi.bind(b);
+    pos_d.bind(b); lsq.bind(b); tl16.bind(b); as_tab.bind(b); pos_xi.bind(b); tl_xi.bind(b); cig_tab.bind(b); pos_xv.bind(b);
+    tl_xv.bind(b); as_raw.bind(b); ncg.bind(b); cig_raw.bind(b); seq2.bind(b); qualp.bind(b); exc.bind(b); qtab.bind(b);
+    exi.bind(b); frag.bind(b);
   }
 };
 
@@ -30,12 +33,15 @@ struct phz_ctx {
   int last_slot = 1;
   u64 stage_seq = 0;
   const u32* cur_frag = nullptr;   // fragment ids of the sample mapped last through a host entry point
+  int64_t last_R = 0, last_NC = 0, last_NB = 0;     // sizes of the arrays expanded last (phz_array "st_*")
   // expanded arrays (device layout of phz_reads) that the copies / expansion kernels produce for K1
-  Buf<PHZ_BACKEND, u32> st_coff; Buf<PHZ_BACKEND, u64> st_soff; Buf<PHZ_BACKEND, u8> st_seq, st_qual;
+  Buf<PHZ_BACKEND, u32> st_coff, st_cig, st_tmp; Buf<PHZ_BACKEND, u64> st_soff; Buf<PHZ_BACKEND, u8> st_seq, st_qual;
+  Buf<PHZ_BACKEND, int32_t> st_pos, st_tlen; Buf<PHZ_BACKEND, int16_t> st_as;
   phz_ctx() {
     PHZ_BACKEND* b = &p.be;
     ae.bind(b); slot[0].bind(b); slot[1].bind(b);
-    st_coff.bind(b); st_soff.bind(b); st_seq.bind(b); st_qual.bind(b);
+    st_coff.bind(b); st_cig.bind(b); st_tmp.bind(b); st_soff.bind(b); st_seq.bind(b); st_qual.bind(b);
+    st_pos.bind(b); st_tlen.bind(b); st_as.bind(b);
   }
 };
 
@@ -113,12 +119,12 @@ int phz_map_reads_host(phz_ctx* ctx, const phz_reads* h, int baseq, double isize
   phz_reads d = *h;
   TransportSlot& S = ctx->slot[ctx->slot[0].staged ? 1 : 0];
   if (S.staged) throw PhzError("phz_map_reads_host: both transport slots hold prefetched samples");
-  be.h2d(S.pos.ensure(R), h->pos, R * 4); d.pos = S.pos.p;
-  be.h2d(S.tlen.ensure(R), h->tlen, R * 4); d.tlen = S.tlen.p;
-  be.h2d(S.as.ensure(R), h->aln_score, R * 2); d.aln_score = S.as.p;
+  be.h2d(ctx->st_pos.ensure(R), h->pos, R * 4); d.pos = ctx->st_pos.p;
+  be.h2d(ctx->st_tlen.ensure(R), h->tlen, R * 4); d.tlen = ctx->st_tlen.p;
+  be.h2d(ctx->st_as.ensure(R), h->aln_score, R * 2); d.aln_score = ctx->st_as.p;
   be.h2d(S.frag.ensure(R), h->frag, R * 4); d.frag = S.frag.p; ctx->cur_frag = S.frag.p;
   be.h2d(ctx->st_coff.ensure(R + 1), h->cigar_off, (R + 1) * 4); d.cigar_off = ctx->st_coff.p;
-  be.h2d(S.cig.ensure(h->n_cigar_ops), h->cigar, h->n_cigar_ops * 4); d.cigar = S.cig.p;
+  be.h2d(ctx->st_cig.ensure(h->n_cigar_ops), h->cigar, h->n_cigar_ops * 4); d.cigar = ctx->st_cig.p;
   be.h2d(ctx->st_soff.ensure(R + 1), h->seq_off, (R + 1) * 8); d.seq_off = (const uint64_t*)ctx->st_soff.p;
   be.h2d(ctx->st_seq.ensure((h->n_bases + 1) / 2), h->seq, (h->n_bases + 1) / 2); d.seq = ctx->st_seq.p;
   be.h2d(ctx->st_qual.ensure(h->n_bases), h->qual, h->n_bases); d.qual = ctx->st_qual.p;
@@ -130,14 +136,44 @@ int phz_map_reads_host(phz_ctx* ctx, const phz_reads* h, int baseq, double isize
 static void check_packed(const phz_packed_reads* h) {
   const int bits = h->qual_bits;
   if (bits != 1 && bits != 2 && bits != 4 && bits != 8) throw PhzError("packed reads: qual_bits must be 1, 2, 4 or 8");
+  if (h->as_bits != 8 && h->as_bits != 16) throw PhzError("packed reads: as_bits must be 8 or 16");
+  if (h->n_cigar_bits != 8 && h->n_cigar_bits != 16) throw PhzError("packed reads: n_cigar_bits must be 8 or 16");
+  if (h->cigar_bits != 16 && h->cigar_bits != 32) throw PhzError("packed reads: cigar_bits must be 16 or 32");
+  if (h->l_seq_const < 0 && !h->l_seq && h->n_records > 0) throw PhzError("packed reads: l_seq missing");
 }
 
 // sizes the slot's buffers for `h` (may reallocate: call before any copy is enqueued)
 static void size_slot(TransportSlot& S, const phz_packed_reads* h) {
   const int64_t R = h->n_records, NB = h->n_bases, NC = h->n_cigar_ops, NX = h->n_exceptions;
-  S.ncg.ensure(R); S.lsq.ensure(R); S.qualp.ensure((NB * h->qual_bits + 7) / 8 + 16); S.qtab.ensure(256);
+  S.ncg.ensure(R * 2 + 16); S.lsq.ensure(R); S.qualp.ensure((NB * h->qual_bits + 7) / 8 + 16); S.qtab.ensure(256);
   S.seq2.ensure((NB + 3) / 4 + 16); S.exi.ensure(NX); S.exc.ensure(NX);
-  S.cig.ensure(NC); S.pos.ensure(R); S.tlen.ensure(R); S.as.ensure(R); S.frag.ensure(R);
+  S.cig_raw.ensure(NC * 4 + 16); S.cig_tab.ensure(65536);
+  S.pos_d.ensure(R); S.pos_xi.ensure(h->n_pos_exc); S.pos_xv.ensure(h->n_pos_exc);
+  S.tl16.ensure(R); S.tl_xi.ensure(h->n_tlen_exc); S.tl_xv.ensure(h->n_tlen_exc);
+  S.as_raw.ensure(R * 2 + 16); S.as_tab.ensure(256); S.frag.ensure(R);
+}
+
+// the four copy groups of one sample, in the order the expansion consumes them
+static void copy_group(PHZ_BACKEND& be, TransportSlot& S, const phz_packed_reads* h, int group) {
+  const int64_t R = h->n_records, NB = h->n_bases, NC = h->n_cigar_ops, NX = h->n_exceptions;
+  if (group == 0) {
+    be.h2d_copy(S.ncg.p, h->n_cigar, R * (h->n_cigar_bits / 8));
+    if (h->l_seq_const < 0) be.h2d_copy(S.lsq.p, h->l_seq, R * 2);
+  } else if (group == 1) {
+    be.h2d_copy(S.qualp.p, h->qualp, (NB * h->qual_bits + 7) / 8); be.h2d_copy(S.qtab.p, h->qual_table, 256);
+  } else if (group == 2) {
+    be.h2d_copy(S.seq2.p, h->seq2, (NB + 3) / 4); be.h2d_copy(S.exi.p, h->exc_index, NX * 8); be.h2d_copy(S.exc.p, h->exc_code, NX);
+  } else {
+    be.h2d_copy(S.cig_raw.p, h->cigar, NC * (h->cigar_bits / 8));
+    if (h->cigar_bits == 16) be.h2d_copy(S.cig_tab.p, h->cigar_table, (size_t)h->n_cigar_table * 4);
+    be.h2d_copy(S.pos_d.p, h->pos_delta, R * 2);
+    be.h2d_copy(S.pos_xi.p, h->pos_exc_index, h->n_pos_exc * 4); be.h2d_copy(S.pos_xv.p, h->pos_exc_delta, h->n_pos_exc * 4);
+    be.h2d_copy(S.tl16.p, h->tlen16, R * 2);
+    be.h2d_copy(S.tl_xi.p, h->tlen_exc_index, h->n_tlen_exc * 4); be.h2d_copy(S.tl_xv.p, h->tlen_exc_value, h->n_tlen_exc * 4);
+    be.h2d_copy(S.as_raw.p, h->as_data, R * (h->as_bits / 8));
+    if (h->as_bits == 8) be.h2d_copy(S.as_tab.p, h->as_table, 512);
+    be.h2d_copy(S.frag.p, h->frag, R * 4);
+  }
 }
 
 int phz_prefetch_packed(phz_ctx* ctx, const phz_packed_reads* h) {
@@ -147,15 +183,10 @@ int phz_prefetch_packed(phz_ctx* ctx, const phz_packed_reads* h) {
   int si = ctx->slot[0].staged ? 1 : (ctx->slot[1].staged ? 0 : 1 - ctx->last_slot);
   TransportSlot& S = ctx->slot[si];
   if (S.staged) throw PhzError("phz_prefetch_packed: both transport slots are already staged");
-  const int64_t R = h->n_records, NB = h->n_bases, NC = h->n_cigar_ops, NX = h->n_exceptions;
   size_slot(S, h);
   if (!S.ready) S.ready = be.new_event();
   be.copy_begin();        // the slot may still be read by kernels queued on the main stream
-  be.h2d_copy(S.ncg.p, h->n_cigar, R * 2); be.h2d_copy(S.lsq.p, h->l_seq, R * 2);
-  be.h2d_copy(S.qualp.p, h->qualp, (NB * h->qual_bits + 7) / 8); be.h2d_copy(S.qtab.p, h->qual_table, 256);
-  be.h2d_copy(S.seq2.p, h->seq2, (NB + 3) / 4); be.h2d_copy(S.exi.p, h->exc_index, NX * 8); be.h2d_copy(S.exc.p, h->exc_code, NX);
-  be.h2d_copy(S.cig.p, h->cigar, NC * 4); be.h2d_copy(S.pos.p, h->pos, R * 4); be.h2d_copy(S.tlen.p, h->tlen, R * 4);
-  be.h2d_copy(S.as.p, h->aln_score, R * 2); be.h2d_copy(S.frag.p, h->frag, R * 4);
+  for (int g = 0; g < 4; ++g) copy_group(be, S, h, g);
   be.copy_record(S.ready);
   S.tag = (const void*)h->seq2; S.staged = true; S.seq = ++ctx->stage_seq;
   PHZ_CATCH
@@ -180,32 +211,29 @@ int phz_map_reads_packed(phz_ctx* ctx, const phz_packed_reads* h, int baseq, dou
     size_slot(ctx->slot[si], h);
   }
   TransportSlot& S = ctx->slot[si];
-  const uint16_t* ncg = S.ncg.p; const uint16_t* lsq = S.lsq.p; const u8* qp = S.qualp.p; const u8* qt = S.qtab.p;
-  const u8* s2 = S.seq2.p; const u64* exi = S.exi.p; const u8* exc = S.exc.p;
-  ctx->st_coff.ensure(R + 1); ctx->st_soff.ensure(R + 1);
+  const u8* qp = S.qualp.p; const u8* qt = S.qtab.p; const u8* s2 = S.seq2.p; const u64* exi = S.exi.p; const u8* exc = S.exc.p;
+  u32* coff = ctx->st_coff.ensure(R + 1); u64* soff = ctx->st_soff.ensure(R + 1); u32* tmp = ctx->st_tmp.ensure(R + 1);
   const int64_t nwq = (NB + 7) / 8, nws = (NB + 15) / 16;
   u64* qout = (u64*)ctx->st_qual.ensure((size_t)nwq * 8 + 16);
   u64* sout = (u64*)ctx->st_seq.ensure((size_t)nws * 8 + 16);
-  d.cigar = S.cig.p; d.pos = S.pos.p; d.tlen = S.tlen.p; d.aln_score = S.as.p; d.frag = S.frag.p;
+  u32* cig = ctx->st_cig.ensure(NC); int32_t* pos = ctx->st_pos.ensure(R); int32_t* tlen = ctx->st_tlen.ensure(R);
+  int16_t* as = ctx->st_as.ensure(R);
   // ---- host -> device on the copy stream, in the order the expansion needs it: counts, qualities, bases, then the
-  // arrays K1 reads as they are.  Each expansion kernel starts as soon as ITS input has landed and runs under the
-  // copies that follow, so only the PCIe time is on the critical path.  With a prefetched sample the copies are
-  // already under way (or done): the main stream just waits for them.
+  // per-record fields.  Each expansion kernel starts as soon as ITS input has landed and runs under the copies that
+  // follow, so only the PCIe time is on the critical path.  With a prefetched sample the copies are already under
+  // way (or done): the main stream just waits for them.
   be.stage("h2d+unpack");
-  const int64_t n2 = (NB + 3) / 4, nq = (NB * bits + 7) / 8;
   if (prefetched) be.wait_event(S.ready);
-  else {
-    be.copy_begin();
-    be.h2d_copy(S.ncg.p, h->n_cigar, R * 2); be.h2d_copy(S.lsq.p, h->l_seq, R * 2);
-    be.copy_fence();
-    be.h2d_copy(S.qualp.p, h->qualp, nq); be.h2d_copy(S.qtab.p, h->qual_table, 256);
+  else { be.copy_begin(); copy_group(be, S, h, 0); be.copy_fence(); copy_group(be, S, h, 1); }
+  {   // counts -> offsets
+    const u8* n8 = S.ncg.p; const uint16_t* n16 = (const uint16_t*)S.ncg.p; const int nbits = h->n_cigar_bits;
+    be.for_each(R, PHZ_LAMBDA(int64_t r) { tmp[r] = nbits == 8 ? (u32)n8[r] : (u32)n16[r]; });
+    be.exclusive_scan_u32(tmp, coff, R); d.cigar_off = coff;
+    if (h->l_seq_const >= 0) { const u64 L = (u64)h->l_seq_const; be.for_each(R + 1, PHZ_LAMBDA(int64_t r) { soff[r] = (u64)r * L; }); }
+    else be.exclusive_scan_u16_to_u64(S.lsq.p, soff, R);
+    d.seq_off = (const uint64_t*)soff;
   }
-  be.exclusive_scan_u16_to_u32(ncg, ctx->st_coff.p, R); d.cigar_off = ctx->st_coff.p;
-  be.exclusive_scan_u16_to_u64(lsq, ctx->st_soff.p, R); d.seq_off = (const uint64_t*)ctx->st_soff.p;
-  if (!prefetched) {
-    be.copy_fence();
-    be.h2d_copy(S.seq2.p, h->seq2, n2); be.h2d_copy(S.exi.p, h->exc_index, NX * 8); be.h2d_copy(S.exc.p, h->exc_code, NX);
-  }
+  if (!prefetched) { be.copy_fence(); copy_group(be, S, h, 2); }
   {   // base qualities: one logical thread per 8 bases = `bits` packed bytes in, 8 phred bytes out
     const u32 mask = (1u << bits) - 1;
     be.for_each(nwq, PHZ_LAMBDA(int64_t w) {
@@ -217,11 +245,7 @@ int phz_map_reads_packed(phz_ctx* ctx, const phz_packed_reads* h, int baseq, dou
     });
     d.qual = ctx->st_qual.p;
   }
-  if (!prefetched) {
-    be.copy_fence();
-    be.h2d_copy(S.cig.p, h->cigar, NC * 4); be.h2d_copy(S.pos.p, h->pos, R * 4); be.h2d_copy(S.tlen.p, h->tlen, R * 4);
-    be.h2d_copy(S.as.p, h->aln_score, R * 2); be.h2d_copy(S.frag.p, h->frag, R * 4);
-  }
+  if (!prefetched) { be.copy_fence(); copy_group(be, S, h, 3); }
   {   // bases: one logical thread per 16 bases = 4 packed bytes in, 8 bytes out (A C G T -> 1 2 4 8, even index = high nibble)
     const u32* in32 = (const u32*)s2;
     be.for_each(nws, PHZ_LAMBDA(int64_t w) {
@@ -241,7 +265,25 @@ int phz_map_reads_packed(phz_ctx* ctx, const phz_packed_reads* h, int baseq, dou
     d.seq = ctx->st_seq.p;
   }
   if (!prefetched) be.copy_fence();
+  {   // per-record fields: table look-ups, exception scatters, one inclusive scan for pos
+    const uint16_t* c16 = (const uint16_t*)S.cig_raw.p; const u32* c32 = (const u32*)S.cig_raw.p; const u32* ctab = S.cig_tab.p;
+    const int cbits = h->cigar_bits;
+    be.for_each(NC, PHZ_LAMBDA(int64_t i) { cig[i] = cbits == 16 ? ctab[c16[i]] : c32[i]; });
+    const uint16_t* pd = S.pos_d.p; const int16_t* t16 = S.tl16.p;
+    const u8* a8 = S.as_raw.p; const int16_t* a16 = (const int16_t*)S.as_raw.p; const int16_t* atab = S.as_tab.p; const int abits = h->as_bits;
+    be.for_each(R, PHZ_LAMBDA(int64_t r) {
+      pos[r] = pd[r] == 65535 ? 0 : (int32_t)pd[r];
+      tlen[r] = (int32_t)t16[r];
+      as[r] = abits == 8 ? atab[a8[r]] : a16[r];
+    });
+    const u32* pxi = S.pos_xi.p; const int32_t* pxv = S.pos_xv.p; const u32* txi = S.tl_xi.p; const int32_t* txv = S.tl_xv.p;
+    be.for_each(h->n_pos_exc, PHZ_LAMBDA(int64_t e) { pos[pxi[e]] = pxv[e]; });
+    be.for_each(h->n_tlen_exc, PHZ_LAMBDA(int64_t e) { tlen[txi[e]] = txv[e]; });
+    be.inclusive_scan_i32_inplace(pos, R);
+    d.cigar = cig; d.pos = pos; d.tlen = tlen; d.aln_score = as; d.frag = S.frag.p;
+  }
   S.staged = false; ctx->last_slot = si; ctx->cur_frag = S.frag.p;
+  ctx->last_R = R; ctx->last_NC = NC; ctx->last_NB = NB;
   be.stage("h2d+unpack.end");
   ReadsView v = view_of(&d, ctx->p.nc);
   *n_candidates = ctx->p.map_reads(v, h->h_contig_rec_off, baseq, isize_cutoff);
@@ -309,6 +351,12 @@ static bool find_array(phz_ctx* ctx, const std::string& name, ArrRef* out) {
   A("fb_cnt", fb_cnt, p.NF * 2) A("fb_bcnt", fb_bcnt, p.NF * nb * 2) A("v_final", v_final, p.V) A("v_hap", v_hap, p.V)
   A("rl_frag", rl_frag, p.NRL) A("rl_var", rl_var, p.NRL) A("rl_row", rl_row, p.NRL)
 #undef A
+  // the arrays phz_map_reads_packed expanded last (device layout of phz_reads): for round-trip checks
+#define S(nm, buf, cnt) if (name == nm) { *out = ArrRef{(const void*)ctx->buf.p, (int64_t)(cnt), (int)sizeof(*ctx->buf.p)}; return true; }
+  S("st_pos", st_pos, ctx->last_R) S("st_tlen", st_tlen, ctx->last_R) S("st_as", st_as, ctx->last_R) S("st_cig", st_cig, ctx->last_NC)
+  S("st_coff", st_coff, ctx->last_R + 1) S("st_soff", st_soff, ctx->last_R + 1) S("st_seq", st_seq, (ctx->last_NB + 1) / 2)
+  S("st_qual", st_qual, ctx->last_NB)
+#undef S
 #define G(nm, buf) if (name == nm) { *out = ArrRef{(const void*)ctx->ae.buf.p, ctx->ae.NPAIR, (int)sizeof(u32)}; return true; }
   G("ae_row", ae_row) G("ae_feat", ae_feat) G("ae_a", ae_a) G("ae_b", ae_b)
 #undef G

@@ -274,6 +274,14 @@ struct DeviceBackend {
     const uint16_t* in_c = in; u64* out_c = out; int64_t nn = n;
     for_each(1, [=] __device__(int64_t) { out_c[nn] = out_c[nn - 1] + in_c[nn - 1]; });
   }
+  void inclusive_scan_i32_inplace(int32_t* a, int64_t n) {
+    if (n <= 0) return;
+    size_t bytes = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, bytes, a, a, (int)n, stream);
+    void* t = tmp(bytes + 16);
+    PHZ_CUDA(cub::DeviceScan::InclusiveSum(t, bytes, a, a, (int)n, stream));
+    lib_launches += 2;
+  }
   void exclusive_scan_u16_to_u32(const uint16_t* in, u32* out, int64_t n) {
     memset0(out + n, sizeof(u32));
     if (n <= 0) return;
@@ -365,6 +373,10 @@ struct HostSimBackend {
     u64 s = 0;
     for (int64_t i = 0; i < n; ++i) { out[i] = s; s += in[i]; }
     out[n] = s;
+  }
+  void inclusive_scan_i32_inplace(int32_t* a, int64_t n) {
+    u32 s = 0;
+    for (int64_t i = 0; i < n; ++i) { s += (u32)a[i]; a[i] = (int32_t)s; }
   }
   void exclusive_scan_u16_to_u32(const uint16_t* in, u32* out, int64_t n) {
     u32 s = 0;

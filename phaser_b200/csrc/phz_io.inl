@@ -573,23 +573,116 @@ phz_packed_host* phz_pack_reads(const phz_reads* h, int n_contigs, int n_threads
     v.n_records = R; v.n_cigar_ops = NCG; v.n_bases = NB;
     P->contig_off.assign(h->h_contig_rec_off, h->h_contig_rec_off + n_contigs + 1);
     v.h_contig_rec_off = P->contig_off.data();
-    int32_t* pos = P->alloc<int32_t>(R); int32_t* tlen = P->alloc<int32_t>(R); int16_t* as = P->alloc<int16_t>(R);
-    uint32_t* frag = P->alloc<uint32_t>(R); uint16_t* ncg = P->alloc<uint16_t>(R); uint16_t* lsq = P->alloc<uint16_t>(R);
-    uint32_t* cig = P->alloc<uint32_t>(NCG);
     const size_t CH = 1 << 20;
-    phzio::parallel_for((R + CH - 1) / CH, n_threads, [&](size_t c) {
-      int64_t r0 = (int64_t)(c * CH), r1 = std::min<int64_t>(R, r0 + CH);
-      std::memcpy(pos + r0, h->pos + r0, (r1 - r0) * 4); std::memcpy(tlen + r0, h->tlen + r0, (r1 - r0) * 4);
-      std::memcpy(as + r0, h->aln_score + r0, (r1 - r0) * 2); std::memcpy(frag + r0, h->frag + r0, (r1 - r0) * 4);
+    const size_t nrc = (size_t)((R + (int64_t)CH - 1) / (int64_t)CH);
+    // ---- pos: u16 difference to the previous record, tlen: i16, each with an exception list
+    uint16_t* pd = P->alloc<uint16_t>(R); int16_t* t16 = P->alloc<int16_t>(R); uint32_t* frag = P->alloc<uint32_t>(R);
+    std::vector<std::vector<std::pair<u32, int32_t>>> pex(nrc), tex(nrc);
+    std::vector<std::vector<u32>> as_seen(nrc, std::vector<u32>(65536 / 32, 0));
+    std::vector<u32> max_ncg(nrc, 0), lmin(nrc, 0xFFFFFFFFu), lmax(nrc, 0);
+    phzio::parallel_for(nrc, n_threads, [&](size_t c) {
+      int64_t r0 = (int64_t)(c * CH), r1 = std::min<int64_t>(R, r0 + (int64_t)CH);
+      std::memcpy(frag + r0, h->frag + r0, (r1 - r0) * 4);
+      auto& seen = as_seen[c];
       for (int64_t r = r0; r < r1; ++r) {
-        ncg[r] = (uint16_t)(h->cigar_off[r + 1] - h->cigar_off[r]); lsq[r] = (uint16_t)(h->seq_off[r + 1] - h->seq_off[r]);
+        int64_t d = (int64_t)h->pos[r] - (r > 0 ? (int64_t)h->pos[r - 1] : 0);
+        if (d >= 0 && d < 65535) pd[r] = (uint16_t)d; else { pd[r] = 65535; pex[c].emplace_back((u32)r, (int32_t)d); }
+        int32_t t = h->tlen[r];
+        if (t > -32768 && t <= 32767) t16[r] = (int16_t)t; else { t16[r] = (int16_t)-32768; tex[c].emplace_back((u32)r, t); }
+        u32 a = (u32)(uint16_t)h->aln_score[r]; seen[a >> 5] |= 1u << (a & 31);
+        u32 nc = h->cigar_off[r + 1] - h->cigar_off[r]; if (nc > max_ncg[c]) max_ncg[c] = nc;
+        u32 ls = (u32)(h->seq_off[r + 1] - h->seq_off[r]); if (ls < lmin[c]) lmin[c] = ls; if (ls > lmax[c]) lmax[c] = ls;
       }
     });
-    phzio::parallel_for((NCG + CH - 1) / CH, n_threads, [&](size_t c) {
-      int64_t i0 = (int64_t)(c * CH), i1 = std::min<int64_t>(NCG, i0 + CH);
-      std::memcpy(cig + i0, h->cigar + i0, (i1 - i0) * 4);
-    });
-    v.pos = pos; v.tlen = tlen; v.aln_score = as; v.frag = frag; v.n_cigar = ncg; v.l_seq = lsq; v.cigar = cig;
+    auto flatten = [&](std::vector<std::vector<std::pair<u32, int32_t>>>& parts, const uint32_t*& oi, const int32_t*& ov) {
+      int64_t n = 0; for (auto& e : parts) n += (int64_t)e.size();
+      uint32_t* xi = P->alloc<uint32_t>(n); int32_t* xv = P->alloc<int32_t>(n);
+      int64_t o = 0; for (auto& e : parts) for (auto& x : e) { xi[o] = x.first; xv[o] = x.second; ++o; }
+      oi = xi; ov = xv; return n;
+    };
+    v.pos_delta = pd; v.n_pos_exc = flatten(pex, v.pos_exc_index, v.pos_exc_delta);
+    v.tlen16 = t16; v.n_tlen_exc = flatten(tex, v.tlen_exc_index, v.tlen_exc_value);
+    v.frag = frag;
+    // ---- alignment scores: table of distinct values when it fits a byte
+    {
+      std::vector<u32> seen(65536 / 32, 0);
+      for (auto& sc : as_seen) for (size_t k = 0; k < seen.size(); ++k) seen[k] |= sc[k];
+      std::vector<uint16_t> distinct;
+      for (u32 a = 0; a < 65536; ++a) if (seen[a >> 5] >> (a & 31) & 1) distinct.push_back((uint16_t)a);
+      if (distinct.size() <= 256) {
+        std::vector<u8> index_of(65536, 0);
+        for (size_t k = 0; k < distinct.size(); ++k) { index_of[distinct[k]] = (u8)k; v.as_table[k] = (int16_t)distinct[k]; }
+        uint8_t* a8 = P->alloc<uint8_t>(R);
+        phzio::parallel_for(nrc, n_threads, [&](size_t c) {
+          int64_t r0 = (int64_t)(c * CH), r1 = std::min<int64_t>(R, r0 + (int64_t)CH);
+          for (int64_t r = r0; r < r1; ++r) a8[r] = index_of[(uint16_t)h->aln_score[r]];
+        });
+        v.as_bits = 8; v.as_data = a8;
+      } else {
+        int16_t* a16 = P->alloc<int16_t>(R);
+        phzio::parallel_for(nrc, n_threads, [&](size_t c) {
+          int64_t r0 = (int64_t)(c * CH), r1 = std::min<int64_t>(R, r0 + (int64_t)CH);
+          std::memcpy(a16 + r0, h->aln_score + r0, (r1 - r0) * 2);
+        });
+        v.as_bits = 16; v.as_data = a16;
+      }
+    }
+    // ---- per-record counts
+    {
+      u32 mx = 0; for (u32 x : max_ncg) mx = std::max(mx, x);
+      u32 lo = 0xFFFFFFFFu, hi = 0; for (size_t c = 0; c < nrc; ++c) { lo = std::min(lo, lmin[c]); hi = std::max(hi, lmax[c]); }
+      v.n_cigar_bits = mx <= 255 ? 8 : 16;
+      void* ncg = v.n_cigar_bits == 8 ? (void*)P->alloc<uint8_t>(R) : (void*)P->alloc<uint16_t>(R);
+      const bool lconst = R > 0 && lo == hi;
+      uint16_t* lsq = lconst ? nullptr : P->alloc<uint16_t>(R);
+      v.l_seq_const = lconst ? (int32_t)lo : -1; v.l_seq = lsq;
+      const int nb = v.n_cigar_bits;
+      phzio::parallel_for(nrc, n_threads, [&](size_t c) {
+        int64_t r0 = (int64_t)(c * CH), r1 = std::min<int64_t>(R, r0 + (int64_t)CH);
+        for (int64_t r = r0; r < r1; ++r) {
+          u32 nc = h->cigar_off[r + 1] - h->cigar_off[r];
+          if (nb == 8) ((uint8_t*)ncg)[r] = (uint8_t)nc; else ((uint16_t*)ncg)[r] = (uint16_t)nc;
+          if (lsq) lsq[r] = (uint16_t)(h->seq_off[r + 1] - h->seq_off[r]);
+        }
+      });
+      v.n_cigar = ncg;
+    }
+    // ---- CIGAR words: table of distinct words when it fits 16 bits
+    {
+      const size_t ncc = (size_t)((NCG + (int64_t)CH - 1) / (int64_t)CH);
+      std::vector<std::vector<u32>> part(ncc);
+      phzio::parallel_for(ncc, n_threads, [&](size_t c) {
+        int64_t i0 = (int64_t)(c * CH), i1 = std::min<int64_t>(NCG, i0 + (int64_t)CH);
+        std::vector<u32> w(h->cigar + i0, h->cigar + i1);
+        std::sort(w.begin(), w.end()); w.erase(std::unique(w.begin(), w.end()), w.end());
+        if (w.size() > 65536) w.resize(65537);           // hopeless already: keep it short
+        part[c].swap(w);
+      });
+      std::vector<u32> table;
+      for (auto& w : part) { table.insert(table.end(), w.begin(), w.end()); if (table.size() > (1u << 22)) { std::sort(table.begin(), table.end()); table.erase(std::unique(table.begin(), table.end()), table.end()); } }
+      std::sort(table.begin(), table.end()); table.erase(std::unique(table.begin(), table.end()), table.end());
+      if (table.size() <= 65536) {
+        uint32_t* tab = P->alloc<uint32_t>(table.size()); std::memcpy(tab, table.data(), table.size() * 4);
+        uint16_t* c16 = P->alloc<uint16_t>(NCG);
+        phzio::parallel_for(ncc, n_threads, [&](size_t c) {
+          int64_t i0 = (int64_t)(c * CH), i1 = std::min<int64_t>(NCG, i0 + (int64_t)CH);
+          u32 last = 0xFFFFFFFFu; uint16_t last_ix = 0;
+          for (int64_t i = i0; i < i1; ++i) {
+            u32 w = h->cigar[i];
+            if (w != last) { last = w; last_ix = (uint16_t)(std::lower_bound(table.begin(), table.end(), w) - table.begin()); }
+            c16[i] = last_ix;
+          }
+        });
+        v.cigar_bits = 16; v.cigar = c16; v.n_cigar_table = (int32_t)table.size(); v.cigar_table = tab;
+      } else {
+        uint32_t* cig = P->alloc<uint32_t>(NCG);
+        phzio::parallel_for(ncc, n_threads, [&](size_t c) {
+          int64_t i0 = (int64_t)(c * CH), i1 = std::min<int64_t>(NCG, i0 + (int64_t)CH);
+          std::memcpy(cig + i0, h->cigar + i0, (i1 - i0) * 4);
+        });
+        v.cigar_bits = 32; v.cigar = cig; v.n_cigar_table = 0; v.cigar_table = nullptr;
+      }
+    }
     // ---- bases: 2 bits + exceptions.  Chunks are multiples of 4 bases so that no output byte is shared.
     const size_t nchunks = (size_t)((NB + (int64_t)CH - 1) / (int64_t)CH);
     uint8_t* s2 = P->alloc<uint8_t>((NB + 3) / 4);

@@ -33,10 +33,13 @@ class phz_reads(ctypes.Structure):
 
 class phz_packed_reads(ctypes.Structure):
     _fields_ = [("n_records", c_int64), ("n_cigar_ops", c_int64), ("n_bases", c_int64), ("h_contig_rec_off", c_void_p),
-                ("pos", c_void_p), ("tlen", c_void_p), ("aln_score", c_void_p), ("frag", c_void_p), ("n_cigar", c_void_p),
-                ("l_seq", c_void_p), ("cigar", c_void_p), ("seq2", c_void_p), ("n_exceptions", c_int64),
-                ("exc_index", c_void_p), ("exc_code", c_void_p), ("qual_bits", c_int32), ("qual_table", ctypes.c_uint8 * 256),
-                ("qualp", c_void_p)]
+                ("pos_delta", c_void_p), ("n_pos_exc", c_int64), ("pos_exc_index", c_void_p), ("pos_exc_delta", c_void_p),
+                ("tlen16", c_void_p), ("n_tlen_exc", c_int64), ("tlen_exc_index", c_void_p), ("tlen_exc_value", c_void_p),
+                ("as_bits", c_int32), ("as_data", c_void_p), ("as_table", ctypes.c_int16 * 256), ("frag", c_void_p),
+                ("n_cigar_bits", c_int32), ("n_cigar", c_void_p), ("l_seq_const", c_int32), ("l_seq", c_void_p),
+                ("cigar_bits", c_int32), ("cigar", c_void_p), ("n_cigar_table", c_int32), ("cigar_table", c_void_p),
+                ("seq2", c_void_p), ("n_exceptions", c_int64), ("exc_index", c_void_p), ("exc_code", c_void_p),
+                ("qual_bits", c_int32), ("qual_table", ctypes.c_uint8 * 256), ("qualp", c_void_p)]
 
 
 class phz_ae_input(ctypes.Structure):
@@ -190,8 +193,12 @@ class PackedReads:
             raise PhzError(lib.phz_last_error().decode())
         self.nbytes = int(lib.phz_packed_bytes(handle))
         self.n_records = int(self.view.n_records)
-        self.qual_bits = int(self.view.qual_bits)
-        self.n_exceptions = int(self.view.n_exceptions)
+        v = self.view
+        self.qual_bits = int(v.qual_bits)
+        self.n_exceptions = int(v.n_exceptions)
+        self.coding = dict(qual_bits=int(v.qual_bits), base_exceptions=int(v.n_exceptions), as_bits=int(v.as_bits),
+                           n_cigar_bits=int(v.n_cigar_bits), l_seq_const=int(v.l_seq_const), cigar_bits=int(v.cigar_bits),
+                           cigar_table=int(v.n_cigar_table), pos_exceptions=int(v.n_pos_exc), tlen_exceptions=int(v.n_tlen_exc))
 
     def __del__(self):
         try:

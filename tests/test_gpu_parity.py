@@ -275,3 +275,15 @@ def test_prefetched_samples_give_the_same_results(gpu, tmp_path):
             assert np.array_equal(alone.arrays[k], got.arrays[k]), (it, k)
     vt, packed, nf, alone = samples[0]
     pipeline.run_path(gpu, vt, [packed], P, n_fragments=nf)          # drain
+
+
+def test_packed_transport_wide_codings_round_trip(gpu, tmp_path):
+    """Every field of the transport form on its wide coding and on its narrow one: the device expansion returns the
+    original arrays bit for bit (st_* arrays) and K1 emits the same tuples."""
+    from tests.test_hostsim_parity import _odd_batch
+    vcf, sams = util.make_case(tmp_path, 41, 200, 300, n_bams=1)
+    vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+    c = util.packed_vs_plain(gpu, vt, _odd_batch(len(vt.contigs)), len(vt.contigs)).coding
+    assert c["cigar_bits"] == 32 and c["n_cigar_bits"] == 16 and c["l_seq_const"] == -1 and c["as_bits"] == 16
+    c = util.packed_vs_plain(gpu, vt, batches[0], len(vt.contigs)).coding
+    assert c["cigar_bits"] == 16 and c["n_cigar_bits"] == 8 and c["l_seq_const"] == 76 and c["as_bits"] == 8

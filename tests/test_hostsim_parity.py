@@ -189,3 +189,44 @@ def test_prefetched_packed_sample_is_the_one_mapped(hostsim, tmp_path):
         got = [hostsim.download(k).copy() for k in ("t_rec", "t_var", "t_misc")]
         assert all(np.array_equal(a, b) for a, b in zip(want[i], got))
     hostsim.map_reads_packed(packs[0], 10, 0.0)
+
+
+def _odd_batch(n_contigs, seed=9):
+    """Hand-made records that push every field of the transport form off its narrow coding: > 65536 distinct CIGAR
+    words, records with > 255 operations, unequal read lengths, > 256 distinct alignment scores, TLENs beyond 16 bits,
+    position gaps beyond 16 bits and a contig restart."""
+    from phaser_b200.layout import ReadBatch
+    rng = np.random.default_rng(seed)
+    nrec = 320
+    cig = []; coff = [0]; soff = [0]; counter = 0
+    for k in range(nrec):
+        first = k % 7 + 1
+        words = [(first << 4) | 0]
+        for _ in range(300 if k % 40 == 0 else 240):
+            counter += 1
+            words.append(((counter // 2 + 1) << 4) | (2 if counter % 2 else 3))      # D / N, every (op, length) pair once
+        words.append((1 << 4) | 0)
+        cig += words; coff.append(len(cig)); soff.append(soff[-1] + first + 1)
+    nb = soff[-1]
+    pos = np.cumsum(rng.choice([0, 3, 200, 70000, 900000], size=nrec)).astype(np.int64) + 1
+    half = nrec // 2
+    pos[half:] -= pos[half] - 5                                                       # second contig starts over
+    off = np.zeros(n_contigs + 1, np.int64); off[1] = half; off[2:] = nrec
+    tlen = rng.choice([0, 250, -300, 40000, -1200000, 32767, -32768, 32768], size=nrec).astype(np.int32)
+    return ReadBatch(n_contigs, off, pos.astype(np.int32), tlen, rng.integers(-400, 400, size=nrec).astype(np.int16),
+                     np.arange(nrec, dtype=np.uint32), np.asarray(coff, np.uint32), np.asarray(cig, np.uint32),
+                     np.asarray(soff, np.uint64), rng.integers(0, 256, size=(nb + 1) // 2, dtype=np.uint8),
+                     rng.integers(0, 60, size=nb).astype(np.uint8), None)
+
+
+def test_packed_transport_wide_codings_round_trip(hostsim, tmp_path):
+    vcf, sams = util.make_case(tmp_path, 41, 200, 300, n_bams=1)
+    vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+    b = _odd_batch(len(vt.contigs))
+    p = util.packed_vs_plain(hostsim, vt, b, len(vt.contigs))
+    c = p.coding
+    assert c["cigar_bits"] == 32 and c["n_cigar_bits"] == 16 and c["l_seq_const"] == -1 and c["as_bits"] == 16
+    assert c["pos_exceptions"] > 2 and c["tlen_exceptions"] > 2 and c["qual_bits"] == 8
+    # and the narrow side of the same fields on ordinary data
+    c = util.packed_vs_plain(hostsim, vt, batches[0], len(vt.contigs)).coding
+    assert c["cigar_bits"] == 16 and c["n_cigar_bits"] == 8 and c["l_seq_const"] == 76 and c["as_bits"] == 8

@@ -147,6 +147,14 @@ def packed_vs_plain(engine, vt, batch, n_contigs):
     plain = [engine.download(k).copy() for k in ("t_rec", "t_var", "t_misc")]
     packed = eng.pack_reads(batch, n_contigs, threads=3, lib=engine.lib)
     n = engine.map_reads_packed(packed, 10, 0.0)
+    # what the device expanded must be the original arrays, bit for bit
+    nb = int(batch.qual.shape[0])
+    for name, orig in (("st_pos", batch.pos), ("st_tlen", batch.tlen), ("st_as", batch.aln_score), ("st_cig", batch.cigar),
+                       ("st_coff", batch.cigar_off), ("st_soff", batch.seq_off), ("st_qual", batch.qual)):
+        back = engine.download(name)
+        assert np.array_equal(back.view(np.asarray(orig).dtype), np.asarray(orig)), name
+    seq = engine.download("st_seq"); o = np.asarray(batch.seq)
+    assert np.array_equal(seq[:nb // 2], o[:nb // 2]) and (nb % 2 == 0 or (seq[nb // 2] >> 4) == (o[nb // 2] >> 4)), "st_seq"
     got = [engine.download(k).copy() for k in ("t_rec", "t_var", "t_misc")]
     assert n == plain[0].shape[0]
     for a, b in zip(plain, got):
