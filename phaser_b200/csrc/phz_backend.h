@@ -51,6 +51,18 @@ typedef unsigned long long u64;
 typedef uint32_t u32;
 typedef uint8_t u8;
 
+// *addr += 1, combined over whatever lanes of the warp are converged here and target the same address (usable inside
+// divergent loops: the set of participants is taken as it is found)
+PHZ_HD void converged_inc(u32* addr) {
+#if defined(__CUDA_ARCH__)
+  const unsigned act = __activemask();
+  const unsigned peers = __match_any_sync(act, (unsigned long long)addr);
+  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(addr, (u32)__popc(peers));
+#else
+  *addr += 1;
+#endif
+}
+
 // counter[key] += 1 for every lane with `active`; lanes of a warp that hit the same key are combined
 // into one atomic (neighbouring items of the sorted arrays mostly belong to the same locus).  Must be
 // reached by all lanes that are active at the call site.

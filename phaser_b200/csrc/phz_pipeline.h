@@ -781,14 +781,33 @@ struct Pipeline {
     u32* cf = cfirst.ensure(nc + 1); be.memset_ff(cf, (nc + 1) * sizeof(u32));
     u64* nz = noise.ensure(2); be.memset0(nz, 2 * sizeof(u64));
     be.for_each(Vn, PHZ_LAMBDA(int64_t v) {
-      if (vf[v] == NONE32) return;
-      atomic_min(&cf[vc[v]], vf[v]);
+      const bool seen = vf[v] != NONE32;
       // noise estimate, phaser.py:614-624
-      u32 mis = nl[v * 3 + 2], mat = nl[v * 3] + nl[v * 3 + 1];
-      if (mat > 0 && ((double)mis / (double)(mis + mat)) < 0.05) {
+      u32 mis = 0, mat = 0;
+      if (seen) { mis = nl[v * 3 + 2]; mat = nl[v * 3] + nl[v * 3 + 1]; }
+      const bool counts = seen && mat > 0 && ((double)mis / (double)(mis + mat)) < 0.05;
+#if defined(__CUDA_ARCH__)
+      // all covered sites would otherwise hammer two counters and one slot per contig: reduce inside the warp first
+      const unsigned act = __activemask();
+      const u32 c = seen ? vc[v] : 0xFFFFFFFFu;
+      const unsigned peers = __match_any_sync(act, c);
+      const u32 mn = __reduce_min_sync(peers, seen ? vf[v] : NONE32);
+      if (seen && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomic_min(&cf[c], mn);
+      const u32 a = counts ? mat : 0u, b = counts ? mis : 0u;          // 16-bit halves: 32 lanes cannot overflow 32 bits
+      const u32 alo = __reduce_add_sync(act, a & 0xFFFFu), ahi = __reduce_add_sync(act, a >> 16);
+      const u32 blo = __reduce_add_sync(act, b & 0xFFFFu), bhi = __reduce_add_sync(act, b >> 16);
+      if ((int)(threadIdx.x & 31) == __ffs(act) - 1) {
+        const unsigned long long ta = ((unsigned long long)ahi << 16) + alo, tb = ((unsigned long long)bhi << 16) + blo;
+        if (ta) atomic_add((unsigned long long*)&nz[0], ta);
+        if (tb) atomic_add((unsigned long long*)&nz[1], tb);
+      }
+#else
+      if (seen) atomic_min(&cf[vc[v]], vf[v]);
+      if (counts) {
         atomic_add((unsigned long long*)&nz[0], (unsigned long long)mat);
         atomic_add((unsigned long long*)&nz[1], (unsigned long long)mis);
       }
+#endif
     });
     {   // contig order of first appearance (read_vars key order, phaser.py:573-574)
       u32* cr = crank.ensure(nc + 1); int ncg = nc;
@@ -886,11 +905,26 @@ struct Pipeline {
         bool first = (j == 0) || (ek[j] != ek[j - 1]);
         u32 mask = 0;
         if (first) for (int64_t jj = j; jj < ne && ek[jj] == ek[j]; ++jj) mask |= em[jj];
-        for (int x = 0; x < 3; ++x) warp_agg_inc(sz, v * 3 + (u32)x, first && ((mask >> x) & 1));
         bool counted = !((excl_mask >> eb[j]) & 1);          // haplo_reads, phaser.py:1320-1322 (Q25)
         u32 kb = (v * (u32)nb + eb[j]) * 2;
+#if defined(__CUDA_ARCH__)
+        // one match per key for the five counters of this entry (every lane of the launch gets here: no divergence above)
+        const unsigned act = __activemask();
+        const unsigned pv = __match_any_sync(act, v);
+        const unsigned pk = nb == 1 ? pv : __match_any_sync(act, kb);
+        const bool lead_v = (int)(threadIdx.x & 31) == __ffs(pv) - 1, lead_k = (int)(threadIdx.x & 31) == __ffs(pk) - 1;
+        for (int x = 0; x < 3; ++x) {
+          const unsigned b = __ballot_sync(act, first && ((mask >> x) & 1)) & pv;
+          if (lead_v && b) atomicAdd(&sz[v * 3 + (u32)x], (u32)__popc(b));
+        }
+        const unsigned b0 = __ballot_sync(act, counted && (em[j] & 1)) & pk, b1 = __ballot_sync(act, counted && (em[j] & 2)) & pk;
+        if (lead_k && b0) atomicAdd(&vbc[kb], (u32)__popc(b0));
+        if (lead_k && b1) atomicAdd(&vbc[kb + 1], (u32)__popc(b1));
+#else
+        for (int x = 0; x < 3; ++x) warp_agg_inc(sz, v * 3 + (u32)x, first && ((mask >> x) & 1));
         warp_agg_inc(vbc, kb, counted && (em[j] & 1));
         warp_agg_inc(vbc, kb + 1, counted && (em[j] & 2));
+#endif
       }); }
     // (b) one logical thread per (fragment, contig) group: effective BAM, overlap rank, pair count
     be.for_each(NG, PHZ_LAMBDA(int64_t g) {
@@ -1210,9 +1244,10 @@ struct Pipeline {
             if (vfin[w] != f || !((em[i] >> (vh[w] ^ h)) & 1)) continue;
             seen_any = true; if (eb[i] == eb[j] && !(vbl && vbl[w])) seen_bam = true;
           }
-          if (!seen_any) atomic_add(&fc[(int64_t)f * 2 + h], 1u);
+          // fragments of one locus sit in neighbouring lanes and hit the same block counter: combine them
+          if (!seen_any) converged_inc(&fc[(int64_t)f * 2 + h]);
           if (!seen_bam && !((excl_mask >> eb[j]) & 1) && !(vbl && vbl[v]))
-            atomic_add(&fbc[((int64_t)f * nb + eb[j]) * 2 + h], 1u);
+            converged_inc(&fbc[((int64_t)f * nb + eb[j]) * 2 + h]);
         }
       }
     });
