@@ -781,31 +781,33 @@ struct Pipeline {
     u32* cf = cfirst.ensure(nc + 1); be.memset_ff(cf, (nc + 1) * sizeof(u32));
     u64* nz = noise.ensure(2); be.memset0(nz, 2 * sizeof(u64));
     be.for_each(Vn, PHZ_LAMBDA(int64_t v) {
-      const bool seen = vf[v] != NONE32;
+      // (captures are named here, in one order, before the host/device split below: the closure type must not depend on it)
+      const u32* vf_ = vf; const u32* nl_ = nl; const u32* vc_ = vc; u32* cf_ = cf; u64* nz_ = nz;
+      const bool seen = vf_[v] != NONE32;
       // noise estimate, phaser.py:614-624
       u32 mis = 0, mat = 0;
-      if (seen) { mis = nl[v * 3 + 2]; mat = nl[v * 3] + nl[v * 3 + 1]; }
+      if (seen) { mis = nl_[v * 3 + 2]; mat = nl_[v * 3] + nl_[v * 3 + 1]; }
       const bool counts = seen && mat > 0 && ((double)mis / (double)(mis + mat)) < 0.05;
 #if defined(__CUDA_ARCH__)
       // all covered sites would otherwise hammer two counters and one slot per contig: reduce inside the warp first
       const unsigned act = __activemask();
-      const u32 c = seen ? vc[v] : 0xFFFFFFFFu;
+      const u32 c = seen ? vc_[v] : 0xFFFFFFFFu;
       const unsigned peers = __match_any_sync(act, c);
-      const u32 mn = __reduce_min_sync(peers, seen ? vf[v] : NONE32);
-      if (seen && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomic_min(&cf[c], mn);
+      const u32 mn = __reduce_min_sync(peers, seen ? vf_[v] : NONE32);
+      if (seen && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomic_min(&cf_[c], mn);
       const u32 a = counts ? mat : 0u, b = counts ? mis : 0u;          // 16-bit halves: 32 lanes cannot overflow 32 bits
       const u32 alo = __reduce_add_sync(act, a & 0xFFFFu), ahi = __reduce_add_sync(act, a >> 16);
       const u32 blo = __reduce_add_sync(act, b & 0xFFFFu), bhi = __reduce_add_sync(act, b >> 16);
       if ((int)(threadIdx.x & 31) == __ffs(act) - 1) {
         const unsigned long long ta = ((unsigned long long)ahi << 16) + alo, tb = ((unsigned long long)bhi << 16) + blo;
-        if (ta) atomic_add((unsigned long long*)&nz[0], ta);
-        if (tb) atomic_add((unsigned long long*)&nz[1], tb);
+        if (ta) atomic_add((unsigned long long*)&nz_[0], ta);
+        if (tb) atomic_add((unsigned long long*)&nz_[1], tb);
       }
 #else
-      if (seen) atomic_min(&cf[vc[v]], vf[v]);
+      if (seen) atomic_min(&cf_[vc_[v]], vf_[v]);
       if (counts) {
-        atomic_add((unsigned long long*)&nz[0], (unsigned long long)mat);
-        atomic_add((unsigned long long*)&nz[1], (unsigned long long)mis);
+        atomic_add((unsigned long long*)&nz_[0], (unsigned long long)mat);
+        atomic_add((unsigned long long*)&nz_[1], (unsigned long long)mis);
       }
 #endif
     });
