@@ -260,10 +260,14 @@ def run_ours(a):
 
         # the ingest's host form: packed transport buffers in page-locked memory (include/phz.h: phz_packed_reads),
         # built ONCE here like a BAM is parsed once; phz_map_reads_packed copies + expands them inside the timed region
-        host_np = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in reads.items()}
-        packed = eng.pack_reads(host_np, len(g.contigs), lib=E.lib, page_locked=True)
-        if world > 1:
-            host_np = {}                  # N ranks share one host: keep only the packed form
+        packed = None
+        for turn in range(world):         # N ranks share one host: one rank at a time holds the unpacked host copy
+            if turn == rank:
+                host_np = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in reads.items()}
+                packed = eng.pack_reads(host_np, len(g.contigs), lib=E.lib, page_locked=True)
+                if world > 1:
+                    host_np = {}
+            barrier()
         dt1, d2h = timed_e2e(packed, a.steps)                      # one sample at a time: copy, then path
         dt, d2h = timed_e2e(packed, a.steps, prefetch=True)        # samples looped, next copy under the current path
         e2e = {"value": V * world / dt, "unit": "het-SNVs/s", "h2d_bytes_per_step": int(packed.nbytes),
