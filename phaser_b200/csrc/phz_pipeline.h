@@ -50,6 +50,85 @@ __global__ void __launch_bounds__(256) as_hist_kernel(const u32* __restrict__ t_
 }
 #endif
 
+#ifdef __CUDACC__
+// Per-variant counters with a shared-memory window.  Consecutive tuples (record order) and consecutive entries
+// (fragment order, fragments numbered by first appearance) belong to one locus, and expression is heavy-tailed: the
+// counters of the hottest loci would otherwise take one global reduction per warp and serialise in a single L2 slice
+// (ncu: that slice's atomic unit 36-38 % busy, the average slice 2.5 %; profiles/r01_k2_ncu_summary.txt).  A CTA
+// therefore counts into a window of AGG_W variant indices around its first item in shared memory and flushes each
+// non-zero slot once; items outside the window (sparse regions: no contention there) go straight to global memory.
+constexpr int AGG_W = 512;            // variant indices per window
+constexpr int AGG_ITEMS = 8;          // items per thread
+
+// first-seen rank + list lengths with duplicates (phaser.py:1310, Q17): vf[v] = min t, nl[v*3+cls] += 1
+__global__ void __launch_bounds__(256) variant_lists_kernel(const u32* __restrict__ gv, const u8* __restrict__ gc, int64_t n,
+                                                            u32* __restrict__ vf, u32* __restrict__ nl) {
+  __shared__ u32 s_cnt[AGG_W * 3];
+  __shared__ u32 s_first[AGG_W];
+  const int64_t t0 = (int64_t)blockIdx.x * (256 * AGG_ITEMS);
+  const u32 v0 = gv[t0];
+  const u32 base = v0 > AGG_W / 4 ? v0 - AGG_W / 4 : 0;
+  for (int i = threadIdx.x; i < AGG_W * 3; i += 256) s_cnt[i] = 0;
+  for (int i = threadIdx.x; i < AGG_W; i += 256) s_first[i] = NONE32;
+  __syncthreads();
+  for (int k = 0; k < AGG_ITEMS; ++k) {
+    const int64_t t = t0 + (int64_t)k * 256 + threadIdx.x;
+    if (t >= n) break;
+    const u32 v = gv[t]; const u32 cls = gc[t] & 3; const u32 d = v - base;
+    if (d < (u32)AGG_W) { atomicAdd(&s_cnt[d * 3 + cls], 1u); atomicMin(&s_first[d], (u32)t); }
+    else { atomicAdd(&nl[(int64_t)v * 3 + cls], 1u); atomicMin(&vf[v], (u32)t); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < AGG_W; i += 256) {
+    if (s_first[i] == NONE32) continue;
+    const int64_t v = (int64_t)base + i;
+    atomicMin(&vf[v], s_first[i]);
+    for (int x = 0; x < 3; ++x) if (s_cnt[i * 3 + x]) atomicAdd(&nl[v * 3 + x], s_cnt[i * 3 + x]);
+  }
+}
+
+// unique-set sizes and per-BAM allele counts, one item per (fragment, variant, bam) entry (see build_graph)
+__global__ void __launch_bounds__(256) entry_stats_kernel(const u64* __restrict__ ek, const u32* __restrict__ em, const u8* __restrict__ eb,
+                                                          int64_t ne, u64 vmask, u64 excl_mask, int nb,
+                                                          u32* __restrict__ sz, u32* __restrict__ vbc) {
+  __shared__ u32 s_sz[AGG_W * 3];
+  __shared__ u32 s_vb[AGG_W * 2 * 4];   // per-BAM allele counts, used when there are at most 4 BAMs
+  const int64_t j0 = (int64_t)blockIdx.x * (256 * AGG_ITEMS);
+  const u32 v0 = (u32)(ek[j0] & vmask);
+  const u32 base = v0 > AGG_W / 2 ? v0 - AGG_W / 2 : 0;
+  for (int i = threadIdx.x; i < AGG_W * 3; i += 256) s_sz[i] = 0;
+  for (int i = threadIdx.x; i < AGG_W * 2 * 4; i += 256) s_vb[i] = 0;
+  __syncthreads();
+  for (int k = 0; k < AGG_ITEMS; ++k) {
+    const int64_t j = j0 + (int64_t)k * 256 + threadIdx.x;
+    if (j >= ne) break;
+    const u64 key = ek[j];
+    const u32 v = (u32)(key & vmask); const u32 d = v - base;
+    const bool first = (j == 0) || (key != ek[j - 1]);
+    u32 mask = 0;
+    if (first) for (int64_t jj = j; jj < ne && ek[jj] == key; ++jj) mask |= em[jj];
+    const u32 m = em[j]; const u32 bam = eb[j];
+    const bool counted = !((excl_mask >> bam) & 1);          // haplo_reads, phaser.py:1320-1322 (Q25)
+    const bool in_win = d < (u32)AGG_W;
+    for (int x = 0; x < 3; ++x)
+      if ((mask >> x) & 1) { if (in_win) atomicAdd(&s_sz[d * 3 + x], 1u); else atomicAdd(&sz[(int64_t)v * 3 + x], 1u); }
+    if (counted)
+      for (int a = 0; a < 2; ++a)
+        if ((m >> a) & 1) {
+          if (in_win && nb <= 4) atomicAdd(&s_vb[(d * nb + bam) * 2 + a], 1u);
+          else atomicAdd(&vbc[((int64_t)v * nb + bam) * 2 + a], 1u);
+        }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < AGG_W; i += 256) {
+    const int64_t v = (int64_t)base + i;
+    for (int x = 0; x < 3; ++x) if (s_sz[i * 3 + x]) atomicAdd(&sz[v * 3 + x], s_sz[i * 3 + x]);
+    if (nb <= 4)
+      for (int a = 0; a < nb * 2; ++a) if (s_vb[i * nb * 2 + a]) atomicAdd(&vbc[v * nb * 2 + a], s_vb[i * nb * 2 + a]);
+  }
+}
+#endif
+
 // ----------------------------------------------------------------------------- K1, windowed
 // Records are coordinate sorted, so the het sites a tile of consecutive records can touch form a
 // short contiguous slab of the position array.  A CTA walks a strip of K1_TILES tiles of K1_THREADS
@@ -446,6 +525,7 @@ struct Pipeline {
   Buf<B, u32> scalars, kstar_d;                     // scalars: [0]=max_tot [1]=err flags [2]=dropped [3]=n_big_tot
   Buf<B, u32> big_tot;                              // c_total values above big_total_thr (unordered, with repeats)
   int64_t NX = 0, E = 0; u32 max_tot = 0; int64_t NBT = 0; u32 big_total_thr = 2048;
+  int window_agg = 1;               // 1: shared-memory window kernels for the per-variant counters, 0: warp-aggregated global atomics
   int64_t frag_run_limit = 1024; int64_t n_runs_resorted = 0; bool full_sort_fallback = false;
   // ------------------------------------------------------------------ blocks
   Buf<B, u32> parent, deg, root, m_flag, m_scan, m_list, m_key, m_key2, m_val2, members;
@@ -759,6 +839,14 @@ struct Pipeline {
     // ---- per-variant lists: first-seen rank (phaser.py:1310), list lengths with duplicates (Q17)
     u32* vf = vfirst.ensure(Vn); be.memset_ff(vf, Vn * sizeof(u32));
     u32* nl = ncls.ensure(Vn * 3); be.memset0(nl, Vn * 3 * sizeof(u32));
+#ifdef __CUDACC__
+    if (window_agg && n > 0) {
+      const int64_t per = 256 * AGG_ITEMS;
+      variant_lists_kernel<<<(unsigned)((n + per - 1) / per), 256, 0, be.stream>>>(gv, gc, n, vf, nl);
+      PHZ_CUDA(cudaGetLastError());
+      be.launches++;
+    } else
+#endif
     be.for_each(n, PHZ_LAMBDA(int64_t t) {
       u32 v = gv[t]; u32 cls = gc[t] & 3;
 #if defined(__CUDA_ARCH__)
@@ -901,6 +989,14 @@ struct Pipeline {
     u32* pc = pair_cnt.ensure(NG + 1); u32* po = pair_off.ensure(NG + 2);
     // (a) one logical thread per entry: unique-set sizes (at the first entry of a (fragment, variant) run) and
     //     per-BAM allele counts, warp-aggregated because neighbouring entries sit on the same locus
+#ifdef __CUDACC__
+    if (window_agg && NE > 0) {
+      const int64_t per = 256 * AGG_ITEMS;
+      entry_stats_kernel<<<(unsigned)((NE + per - 1) / per), 256, 0, be.stream>>>(ek, em, eb, NE, vmask, excl_mask, nb, sz, vbc);
+      PHZ_CUDA(cudaGetLastError());
+      be.launches++;
+    } else
+#endif
     { int64_t ne = NE;
       be.for_each(NE, PHZ_LAMBDA(int64_t j) {
         u32 v = (u32)(ek[j] & vmask);

@@ -287,3 +287,24 @@ def test_packed_transport_wide_codings_round_trip(gpu, tmp_path):
     assert c["cigar_bits"] == 32 and c["n_cigar_bits"] == 16 and c["l_seq_const"] == -1 and c["as_bits"] == 16
     c = util.packed_vs_plain(gpu, vt, batches[0], len(vt.contigs)).coding
     assert c["cigar_bits"] == 16 and c["n_cigar_bits"] == 8 and c["l_seq_const"] == 76 and c["as_bits"] == 8
+
+
+@pytest.mark.parametrize("n_bams", [1, 3, 5])
+def test_window_aggregated_counters_equal_plain_atomics(gpu, tmp_path, n_bams):
+    """The shared-memory window kernels for the per-variant counters (vfirst / ncls, set sizes, per-BAM allele
+    counts; <= 4 BAMs windowed, more go to global memory) against the warp-aggregated global atomics."""
+    from phaser_b200 import pipeline
+    vcf, sams = util.make_case(tmp_path, 48, 600, 12000, n_bams=n_bams, switch_per_base=0.02)
+    vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+    P = pipeline.PhaseParams(haplo_count_bam_exclude=[1] if n_bams > 1 else [])
+    out = []
+    for mode in (1, 0):
+        gpu.set_option("window_agg", mode)
+        try:
+            out.append(pipeline.run_path(gpu, vt, [gpu.upload_reads(b) for b in batches], P, n_fragments=len(fd.names)))
+        finally:
+            gpu.set_option("window_agg", 1)
+    a, b = out
+    assert a.counters == b.counters
+    for k in a.arrays:
+        assert np.array_equal(a.arrays[k], b.arrays[k]), k
