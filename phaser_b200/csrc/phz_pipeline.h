@@ -519,7 +519,8 @@ struct Pipeline {
   Buf<B, u32> grp_off, pair_cnt, pair_off;
   int64_t NE = 0, NG = 0, NP = 0;
   // ------------------------------------------------------------------ pairs / edges
-  Buf<B, u64> p_key, p_key2; Buf<B, u32> p_val, p_val2, p_flag, p_scan, pe_start;
+  Buf<B, u64> p_key, p_key2; Buf<B, u32> p_val, p_val2, p_flag, p_scan, pe_start, p_k32, p_k32b, pair_dmax;
+  int wide_pair_keys = 0;           // 1: always sort the pair table on 64-bit keys (A/B switch)
   Buf<B, u32> x_flag, x_scan, x_acc;
   Buf<B, u32> ed_a, ed_b, ed_sup, ed_tot, ed_n9; Buf<B, u8> ed_cfg, ed_keep;
   Buf<B, u32> scalars, kstar_d;                     // scalars: [0]=max_tot [1]=err flags [2]=dropped [3]=n_big_tot
@@ -552,6 +553,7 @@ struct Pipeline {
     s_key.bind(b); s_key2.bind(b); s_val.bind(b); s_val2.bind(b); s_flag.bind(b); s_scan.bind(b);
     e_key.bind(b); e_bam.bind(b); e_mask.bind(b); e_tmin.bind(b); e_flag.bind(b); e_scan.bind(b);
     grp_off.bind(b); pair_cnt.bind(b); pair_off.bind(b);
+    p_k32.bind(b); p_k32b.bind(b); pair_dmax.bind(b);
     p_key.bind(b); p_key2.bind(b); p_val.bind(b); p_val2.bind(b); p_flag.bind(b); p_scan.bind(b); pe_start.bind(b);
     x_flag.bind(b); x_scan.bind(b); x_acc.bind(b);
     ed_a.bind(b); ed_b.bind(b); ed_sup.bind(b); ed_tot.bind(b); ed_n9.bind(b); ed_cfg.bind(b); ed_keep.bind(b); scalars.bind(b); kstar_d.bind(b); big_tot.bind(b);
@@ -1025,6 +1027,7 @@ struct Pipeline {
 #endif
       }); }
     // (b) one logical thread per (fragment, contig) group: effective BAM, overlap rank, pair count
+    u32* dm = pair_dmax.ensure(4); be.memset0(dm, 4 * sizeof(u32));
     be.for_each(NG, PHZ_LAMBDA(int64_t g) {
       u32 j0 = go[g], j1 = go[g + 1];
       int effbam = -1; u32 first_t = NONE32;
@@ -1038,6 +1041,10 @@ struct Pipeline {
         j = jj;
       }
       pc[g] = k * (k - 1) / 2;
+      if (k >= 2) {         // widest variant-index distance inside a fragment: sizes the pair keys below
+        u32 d = (u32)(ek[j1 - 1] & vmask) - (u32)(ek[j0] & vmask);
+        if (d > load_volatile(&dm[0])) atomic_max(&dm[0], d);
+      }
       if (kelig >= 2) {     // insertion order of dict_variant_overlap, phaser.py:1271-1283
         for (u32 j = j0; j < j1; ++j)
           if ((em[j] & 3) && (int)eb[j] == effbam) {
@@ -1050,8 +1057,17 @@ struct Pipeline {
     be.exclusive_scan_u32(pc, po, NG);
     NP = NG > 0 ? (int64_t)fetch_u32(po + NG) : 0;
     be.stage("graph.emit_pairs");
-    // ---- pairs: key (va, vb), value = 9 co-occurrence cells + eligibility
-    u64* pk = p_key.ensure(NP); u64* pk2 = p_key2.ensure(NP); u32* pv = p_val.ensure(NP); u32* pv2 = p_val2.ensure(NP);
+    // ---- pairs: key (va, vb), value = 9 co-occurrence cells + eligibility.  The key is (va << dbits) | (vb - va)
+    // with dbits sized by the widest distance seen above: same order as (va, vb), but usually <= 32 bits, i.e. 4
+    // radix passes over 8-byte pairs instead of 6 over 12-byte ones.
+    const u32 dmax = NP > 0 ? fetch_u32(dm) : 0;
+    const int dbits = ceil_log2_host((u64)dmax + 1) > 0 ? ceil_log2_host((u64)dmax + 1) : 1;
+    const int kbits = vb + dbits;
+    const bool k32 = kbits <= 32 && !wide_pair_keys;
+    u64* pk = p_key.ensure(k32 ? 1 : NP); u64* pk2 = p_key2.ensure(k32 ? 1 : NP);
+    u32* pk32 = p_k32.ensure(k32 ? NP : 1); u32* pk32b = p_k32b.ensure(k32 ? NP : 1);
+    u32* pv = p_val.ensure(NP); u32* pv2 = p_val2.ensure(NP);
+    const u64 dmask = (((u64)1) << dbits) - 1;
     be.for_each(NG, PHZ_LAMBDA(int64_t g) {
       if (pc[g] == 0) return;
       u32 j0 = go[g], j1 = go[g + 1];
@@ -1067,17 +1083,20 @@ struct Pipeline {
           u32 cells = 0;
           for (int x = 0; x < 3; ++x) for (int y = 0; y < 3; ++y) if (((ma >> x) & 1) && ((mb >> y) & 1)) cells |= 1u << (x * 3 + y);
           if (ea && ebb) cells |= 1u << 9;
-          pk[o] = ((u64)va << vb) | vbb; pv[o] = cells; o++;
+          if (k32) pk32[o] = (va << dbits) | (vbb - va); else pk[o] = ((u64)va << dbits) | (u64)(vbb - va);
+          pv[o] = cells; o++;
           b = b1;
         }
         a = a1;
       }
     });
     be.stage("graph.sort_pairs");
-    be.sort_pairs(pk, pk2, pv, pv2, NP, 0, 2 * vb);
+    if (k32) be.sort_pairs32(pk32, pk32b, pv, pv2, NP, 0, kbits); else be.sort_pairs(pk, pk2, pv, pv2, NP, 0, kbits);
     be.stage("graph.edge_table");
     u32* pf = p_flag.ensure(NP + 1); u32* ps = p_scan.ensure(NP + 2);
-    be.for_each(NP, PHZ_LAMBDA(int64_t i) { pf[i] = (i == 0 || pk2[i] != pk2[i - 1]) ? 1u : 0u; });
+    be.for_each(NP, PHZ_LAMBDA(int64_t i) {
+      pf[i] = (i == 0 || (k32 ? pk32b[i] != pk32b[i - 1] : pk2[i] != pk2[i - 1])) ? 1u : 0u;
+    });
     be.exclusive_scan_u32(pf, ps, NP);
     NX = NP > 0 ? (int64_t)fetch_u32(ps + NP) : 0;
     u32* pst = pe_start.ensure(NX + 1);
@@ -1119,8 +1138,8 @@ struct Pipeline {
       if (!xf[x]) return;
       u32 e = xs[x];
       u32 n9[9]; for (int c = 0; c < 9; ++c) n9[c] = xacc[x * 10 + c];
-      u64 key = pk2[pst[x]];
-      ea_[e] = (u32)(key >> vb); eb_[e] = (u32)(key & vmask);
+      u64 key = k32 ? (u64)pk32b[pst[x]] : pk2[pst[x]];
+      ea_[e] = (u32)(key >> dbits); eb_[e] = (u32)(key >> dbits) + (u32)(key & dmask);
       for (int c = 0; c < 9; ++c) en9[(int64_t)e * 9 + c] = n9[c];
       u32 cis = n9[0] + n9[4], trans = n9[3] + n9[1];          // n[x][y] at x*3+y
       u32 other = n9[6] + n9[7] + n9[2] + n9[5] + n9[8];

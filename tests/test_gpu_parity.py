@@ -308,3 +308,22 @@ def test_window_aggregated_counters_equal_plain_atomics(gpu, tmp_path, n_bams):
     assert a.counters == b.counters
     for k in a.arrays:
         assert np.array_equal(a.arrays[k], b.arrays[k]), k
+
+
+def test_compact_pair_keys_equal_wide_ones(gpu, tmp_path):
+    """Pair table sorted on (va << dbits | vb - va) (32-bit when it fits) == sorted on 64-bit keys."""
+    from phaser_b200 import pipeline
+    vcf, sams = util.make_case(tmp_path, 49, 500, 9000, n_bams=2, switch_per_base=0.02)
+    vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+    P = pipeline.PhaseParams()
+    out = []
+    for wide in (0, 1):
+        gpu.set_option("wide_pair_keys", wide)
+        try:
+            out.append(pipeline.run_path(gpu, vt, [gpu.upload_reads(b) for b in batches], P, n_fragments=len(fd.names)))
+        finally:
+            gpu.set_option("wide_pair_keys", 0)
+    a, b = out
+    assert a.counters == b.counters and a.counters["edges"] > 50
+    for k in a.arrays:
+        assert np.array_equal(a.arrays[k], b.arrays[k]), k

@@ -230,3 +230,22 @@ def test_packed_transport_wide_codings_round_trip(hostsim, tmp_path):
     # and the narrow side of the same fields on ordinary data
     c = util.packed_vs_plain(hostsim, vt, batches[0], len(vt.contigs)).coding
     assert c["cigar_bits"] == 16 and c["n_cigar_bits"] == 8 and c["l_seq_const"] == 76 and c["as_bits"] == 8
+
+
+def test_compact_pair_keys_equal_wide_ones(hostsim, tmp_path):
+    """Pair table sorted on (va << dbits | vb - va) (32-bit when it fits) == sorted on 64-bit keys."""
+    from phaser_b200 import pipeline
+    vcf, sams = util.make_case(tmp_path, 49, 500, 9000, n_bams=2, switch_per_base=0.02)
+    vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+    P = pipeline.PhaseParams()
+    out = []
+    for wide in (0, 1):
+        hostsim.set_option("wide_pair_keys", wide)
+        try:
+            out.append(pipeline.run_path(hostsim, vt, [hostsim.upload_reads(b) for b in batches], P, n_fragments=len(fd.names)))
+        finally:
+            hostsim.set_option("wide_pair_keys", 0)
+    a, b = out
+    assert a.counters == b.counters and a.counters["edges"] > 50
+    for k in a.arrays:
+        assert np.array_equal(a.arrays[k], b.arrays[k]), k
