@@ -520,6 +520,7 @@ struct Pipeline {
   int64_t NE = 0, NG = 0, NP = 0;
   // ------------------------------------------------------------------ pairs / edges
   Buf<B, u64> p_key, p_key2; Buf<B, u32> p_val, p_val2, p_flag, p_scan, pe_start, p_k32, p_k32b, pair_dmax;
+  Buf<B, u32> s_f32, s_f32b;
   int wide_pair_keys = 0;           // 1: always sort the pair table on 64-bit keys (A/B switch)
   Buf<B, u32> x_flag, x_scan, x_acc;
   Buf<B, u32> ed_a, ed_b, ed_sup, ed_tot, ed_n9; Buf<B, u8> ed_cfg, ed_keep;
@@ -553,7 +554,7 @@ struct Pipeline {
     s_key.bind(b); s_key2.bind(b); s_val.bind(b); s_val2.bind(b); s_flag.bind(b); s_scan.bind(b);
     e_key.bind(b); e_bam.bind(b); e_mask.bind(b); e_tmin.bind(b); e_flag.bind(b); e_scan.bind(b);
     grp_off.bind(b); pair_cnt.bind(b); pair_off.bind(b);
-    p_k32.bind(b); p_k32b.bind(b); pair_dmax.bind(b);
+    p_k32.bind(b); p_k32b.bind(b); pair_dmax.bind(b); s_f32.bind(b); s_f32b.bind(b);
     p_key.bind(b); p_key2.bind(b); p_val.bind(b); p_val2.bind(b); p_flag.bind(b); p_scan.bind(b); pe_start.bind(b);
     x_flag.bind(b); x_scan.bind(b); x_acc.bind(b);
     ed_a.bind(b); ed_b.bind(b); ed_sup.bind(b); ed_tot.bind(b); ed_n9.bind(b); ed_cfg.bind(b); ed_keep.bind(b); scalars.bind(b); kstar_d.bind(b); big_tot.bind(b);
@@ -922,8 +923,9 @@ struct Pipeline {
     // ---- (fragment, variant, bam) entries: sort tuples by (fragment, variant); t ascending inside
     const int fb = ceil_log2_host(n_frag > 1 ? n_frag : 2); const int vb = vbits;
     if (fb + vb > 64) throw PhzError("fragment/variant id space too large");
-    u64* k1 = s_key.ensure(n); u64* k2 = s_key2.ensure(n); u32* x1 = s_val.ensure(n); u32* x2 = s_val2.ensure(n);
-    be.for_each(n, PHZ_LAMBDA(int64_t t) { k1[t] = ((u64)gf[t] << vb) | (u64)gv[t]; x1[t] = (u32)t; });
+    u64* k2 = s_key2.ensure(n); u32* x1 = s_val.ensure(n); u32* x2 = s_val2.ensure(n);
+    u32* f1 = s_f32.ensure(n); u32* f2 = s_f32b.ensure(n);
+    be.for_each(n, PHZ_LAMBDA(int64_t t) { f1[t] = gf[t]; x1[t] = (u32)t; });
     // Tuples arrive in (record, variant) order, so a STABLE sort on the fragment bits alone (4 radix passes instead
     // of 6) already leaves a fragment's tuples variant-sorted unless its records interleave (overlapping mates, a
     // spliced mate jumping over the other).  The first tuple of each fragment checks its run and insertion-sorts it
@@ -931,7 +933,11 @@ struct Pipeline {
     // whole array is sorted on the full key instead.
     {
       u32* sc = scalars.ensure(8); be.memset0(sc, 8 * sizeof(u32));
-      be.sort_pairs(k1, k2, x1, x2, n, vb, fb + vb);
+      // (32-bit fragment keys: 8-byte pairs through the radix passes; the 64-bit (fragment, variant) keys the
+      // following stages compare are assembled afterwards -- the sorted tuple indices are nearly ascending, so the
+      // gather of the variant ids stays in cache)
+      be.sort_pairs32(f1, f2, x1, x2, n, 0, fb);
+      be.for_each(n, PHZ_LAMBDA(int64_t i) { k2[i] = ((u64)f2[i] << vb) | (u64)gv[x2[i]]; });
       const int64_t nn = n; const int64_t MAXRUN = frag_run_limit;
       be.for_each(n, PHZ_LAMBDA(int64_t i) {
         const u64 f = k2[i] >> vb;
@@ -953,7 +959,11 @@ struct Pipeline {
       u32 h2[2] = {0, 0};
       if (n > 0) be.d2h(h2, sc + 4, sizeof(h2));
       n_runs_resorted = h2[1]; full_sort_fallback = h2[0] != 0;
-      if (full_sort_fallback) be.sort_pairs(k1, k2, x1, x2, n, 0, fb + vb);
+      if (full_sort_fallback) {
+        u64* k1 = s_key.ensure(n);
+        be.for_each(n, PHZ_LAMBDA(int64_t t) { k1[t] = ((u64)gf[t] << vb) | (u64)gv[t]; x1[t] = (u32)t; });
+        be.sort_pairs(k1, k2, x1, x2, n, 0, fb + vb);
+      }
     }
     be.stage("graph.entries");
     u32* sf = s_flag.ensure(n + 1); u32* ss = s_scan.ensure(n + 2);
