@@ -404,6 +404,7 @@ int phz_set_option(phz_ctx* ctx, const char* name, int64_t value) {
   if (n == "k1_mode") ctx->p.k1_mode = (int)value;
   else if (n == "k1_min_ctas") ctx->p.k1_min_ctas = (int)value;
   else if (n == "big_total_threshold") ctx->p.big_total_thr = (u32)value;
+  else if (n == "two_pass_read_lists") ctx->p.two_pass_read_lists = (int)value;
   else if (n == "wide_pair_keys") ctx->p.wide_pair_keys = (int)value;
   else if (n == "window_agg") ctx->p.window_agg = (int)value;
   else if (n == "frag_run_limit") ctx->p.frag_run_limit = value < 1 ? 1 : value;

@@ -105,6 +105,7 @@ struct PhzError : public std::runtime_error {
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
 #include <thrust/iterator/transform_iterator.h>
+#include <thrust/iterator/counting_iterator.h>
 
 namespace phz {
 
@@ -286,6 +287,20 @@ struct DeviceBackend {
     const uint16_t* in_c = in; u64* out_c = out; int64_t nn = n;
     for_each(1, [=] __device__(int64_t) { out_c[nn] = out_c[nn - 1] + in_c[nn - 1]; });
   }
+  // out[i] = sum_{j<i} f(j) for i in [0, n]; f(j) in {0, 1, ...} is evaluated on the fly (no flag array in memory)
+  template <class F>
+  void exclusive_scan_fn_u32(F f, u32* out, int64_t n) {
+    memset0(out + n, sizeof(u32));
+    if (n <= 0) return;
+    auto it = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0), f);
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, out, (int)n, stream);
+    void* t = tmp(bytes + 16);
+    PHZ_CUDA(cub::DeviceScan::ExclusiveSum(t, bytes, it, out, (int)n, stream));
+    lib_launches += 2;
+    u32* out_c = out; int64_t nn = n;
+    for_each(1, [=] __device__(int64_t) { out_c[nn] = out_c[nn - 1] + f(nn - 1); });
+  }
   void inclusive_scan_i32_inplace(int32_t* a, int64_t n) {
     if (n <= 0) return;
     size_t bytes = 0;
@@ -384,6 +399,12 @@ struct HostSimBackend {
   void exclusive_scan_u16_to_u64(const uint16_t* in, u64* out, int64_t n) {
     u64 s = 0;
     for (int64_t i = 0; i < n; ++i) { out[i] = s; s += in[i]; }
+    out[n] = s;
+  }
+  template <class F>
+  void exclusive_scan_fn_u32(F f, u32* out, int64_t n) {
+    u32 s = 0;
+    for (int64_t i = 0; i < n; ++i) { out[i] = s; s += f(i); }
     out[n] = s;
   }
   void inclusive_scan_i32_inplace(int32_t* a, int64_t n) {

@@ -520,7 +520,8 @@ struct Pipeline {
   int64_t NE = 0, NG = 0, NP = 0;
   // ------------------------------------------------------------------ pairs / edges
   Buf<B, u64> p_key, p_key2; Buf<B, u32> p_val, p_val2, p_flag, p_scan, pe_start, p_k32, p_k32b, pair_dmax;
-  Buf<B, u32> s_f32, s_f32b;
+  Buf<B, u32> s_f32, s_f32b, v_member;
+  u32 max_final_len = 0; int two_pass_read_lists = 0;
   int wide_pair_keys = 0;           // 1: always sort the pair table on 64-bit keys (A/B switch)
   Buf<B, u32> x_flag, x_scan, x_acc;
   Buf<B, u32> ed_a, ed_b, ed_sup, ed_tot, ed_n9; Buf<B, u8> ed_cfg, ed_keep;
@@ -554,7 +555,7 @@ struct Pipeline {
     s_key.bind(b); s_key2.bind(b); s_val.bind(b); s_val2.bind(b); s_flag.bind(b); s_scan.bind(b);
     e_key.bind(b); e_bam.bind(b); e_mask.bind(b); e_tmin.bind(b); e_flag.bind(b); e_scan.bind(b);
     grp_off.bind(b); pair_cnt.bind(b); pair_off.bind(b);
-    p_k32.bind(b); p_k32b.bind(b); pair_dmax.bind(b); s_f32.bind(b); s_f32b.bind(b);
+    p_k32.bind(b); p_k32b.bind(b); pair_dmax.bind(b); s_f32.bind(b); s_f32b.bind(b); v_member.bind(b);
     p_key.bind(b); p_key2.bind(b); p_val.bind(b); p_val2.bind(b); p_flag.bind(b); p_scan.bind(b); pe_start.bind(b);
     x_flag.bind(b); x_scan.bind(b); x_acc.bind(b);
     ed_a.bind(b); ed_b.bind(b); ed_sup.bind(b); ed_tot.bind(b); ed_n9.bind(b); ed_cfg.bind(b); ed_keep.bind(b); scalars.bind(b); kstar_d.bind(b); big_tot.bind(b);
@@ -807,23 +808,22 @@ struct Pipeline {
     if (bam != n_bams) throw PhzError("commit_bam: BAMs must be committed in order");
     if (bam >= 64) throw PhzError("at most 64 BAMs");
     int64_t n = n_cand;
-    u32* kf = keep_flag.ensure(n + 1); u32* ko = keep_off.ensure(n + 2);
+    u32* ko = keep_off.ensure(n + 2);
     be.stage("commit_bam");
     const u32* tr = t_rec.p; const u32* tv = t_var.p; const u32* tm = t_misc.p;
-    be.for_each(n, PHZ_LAMBDA(int64_t i) {
-      u32 m = tm[i];
-      kf[i] = (misc_cls(m) != CLS_NONE && misc_as(m) >= as_cutoff) ? 1u : 0u;
-    });
-    be.exclusive_scan_u32(kf, ko, n);
+    // the keep test is one compare on t_misc: evaluated inside the scan and again in the scatter, never stored
+    auto keep = PHZ_LAMBDA(int64_t i) -> u32 { u32 m = tm[i]; return (misc_cls(m) != CLS_NONE && misc_as(m) >= as_cutoff) ? 1u : 0u; };
+    be.exclusive_scan_fn_u32(keep, ko, n);
     int64_t nk = n > 0 ? (int64_t)fetch_u32(ko + n) : 0;
     if (n_tuples + nk >= (int64_t)0xFFFFFFF0ull) throw PhzError("more than 2^32 tuples");
     u32* gf = g_frag.grow(n_tuples + nk, n_tuples); u32* gv = g_var.grow(n_tuples + nk, n_tuples);
     u8* gc = g_cb.grow(n_tuples + nk, n_tuples);
     int64_t base = n_tuples;
     be.for_each(n, PHZ_LAMBDA(int64_t i) {
-      if (!kf[i]) return;
+      u32 m = tm[i];
+      if (!(misc_cls(m) != CLS_NONE && misc_as(m) >= as_cutoff)) return;
       int64_t o = base + ko[i];
-      gf[o] = frag[tr[i]]; gv[o] = tv[i]; gc[o] = (u8)(misc_cls(tm[i]) | (bam << 2));
+      gf[o] = frag[tr[i]]; gv[o] = tv[i]; gc[o] = (u8)(misc_cls(m) | (bam << 2));
     });
     n_tuples += nk; n_bams = bam + 1; n_cand = 0;
     be.stage("commit_bam.end");
@@ -1334,12 +1334,18 @@ struct Pipeline {
     NF = NB > 0 ? (int64_t)fetch_u32(fbb + NB) : 0;
     u32* ff = fb_first.ensure(NF); u32* fl = fb_len.ensure(NF); u32* fbk = fb_blk.ensure(NF);
     u32* vfin = v_final.ensure(Vn); be.memset_ff(vfin, Vn * sizeof(u32));
+    u32* vmi = v_member.ensure(Vn);
     be.for_each(NB, PHZ_LAMBDA(int64_t i) {
-      u32 b = bord[i]; u32 o0 = bo[b];
-      for (u32 r = 0; r < bnf[b]; ++r) { u32 f = fbb[i] + r; ff[f] = o0 + rs[o0 + r]; fl[f] = rl[o0 + r]; fbk[f] = b; }
+      u32 b = bord[i]; u32 o0 = bo[b]; u32 longest = 0;
+      for (u32 r = 0; r < bnf[b]; ++r) {
+        u32 f = fbb[i] + r; ff[f] = o0 + rs[o0 + r]; fl[f] = rl[o0 + r]; fbk[f] = b;
+        if (rl[o0 + r] > longest) longest = rl[o0 + r];
+      }
+      if (longest > load_volatile(&sc[6])) atomic_max(&sc[6], longest);      // sizes the rank field of the read-list keys
     });
     be.for_each(NM, PHZ_LAMBDA(int64_t i) {
-      u32 v = mem[i]; if (vfl[v] != NONE32) vfin[v] = fbb[bpos[bof[v]]] + vfl[v];
+      u32 v = mem[i]; vmi[v] = (u32)i;
+      if (vfl[v] != NONE32) vfin[v] = fbb[bpos[bof[v]]] + vfl[v];
     });
     be.stage("phase.edge_support");
     // ---- edge support per final block (phaser.py:876-895)
@@ -1378,8 +1384,9 @@ struct Pipeline {
         }
       }
     });
-    u32 errf = fetch_u32(sc + 1);
-    *err_out = (int)errf;
+    u32 hsc8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    be.d2h(hsc8, sc, sizeof(hsc8));
+    *err_out = (int)hsc8[1]; max_final_len = hsc8[6];
     be.stage("phase.end");
   }
 
@@ -1399,18 +1406,34 @@ struct Pipeline {
     be.exclusive_scan_u32(rf, rsn, n);
     NRL = n > 0 ? (int64_t)fetch_u32(rsn + n) : 0;
     u32* k32 = rl_k32.ensure(NRL); u32* k32b = rl_k32b.ensure(NRL); u32* tt = rl_t.ensure(NRL); u32* tt2 = rl_t2.ensure(NRL);
-    be.for_each(n, PHZ_LAMBDA(int64_t t) { if (rf[t]) { k32[rsn[t]] = gv[t]; tt[rsn[t]] = (u32)t; } });
-    be.sort_pairs32(k32, k32b, tt, tt2, NRL, 0, vb);          // by variant, tuple order kept
     int bb = ceil_log2_host((u64)(nb > 1 ? nb : 2));
     int fbits = ceil_log2_host((u64)(NF > 1 ? NF : 2));
     if (fbits + bb + 1 > 32) throw PhzError("row key of read_lists does not fit 32 bits");
-    be.for_each(NRL, PHZ_LAMBDA(int64_t i) {
-      u32 t = tt2[i]; u32 v = gv[t]; u32 hap = (gc[t] & 3) ^ vh[v];
-      k32[i] = (((vfin[v] << bb) | (u32)(gc[t] >> 2)) << 1) | hap;
-    });
-    be.sort_pairs32(k32, k32b, tt2, tt, NRL, 0, fbits + bb + 1);      // by (block, BAM, haplotype), variant order kept
+    const int rbits = ceil_log2_host((u64)max_final_len + 1) > 0 ? ceil_log2_host((u64)max_final_len + 1) : 1;
+    const u32* kres = k32b;
+    int shift = 0;
+    if (fbits + bb + 1 + rbits <= 32 && !two_pass_read_lists) {
+      // one sort: key = (block, BAM, haplotype, rank of the variant inside its block); tuple order kept by stability
+      const u32* ff = fb_first.p; const u32* vmi = v_member.p;
+      be.for_each(n, PHZ_LAMBDA(int64_t t) {
+        if (!rf[t]) return;
+        u32 v = gv[t]; u32 f = vfin[v]; u32 hap = (gc[t] & 3) ^ vh[v];
+        u32 row = (((f << bb) | (u32)(gc[t] >> 2)) << 1) | hap;
+        k32[rsn[t]] = (row << rbits) | (vmi[v] - ff[f]); tt2[rsn[t]] = (u32)t;
+      });
+      be.sort_pairs32(k32, k32b, tt2, tt, NRL, 0, fbits + bb + 1 + rbits);
+      shift = rbits;
+    } else {
+      be.for_each(n, PHZ_LAMBDA(int64_t t) { if (rf[t]) { k32[rsn[t]] = gv[t]; tt[rsn[t]] = (u32)t; } });
+      be.sort_pairs32(k32, k32b, tt, tt2, NRL, 0, vb);          // by variant, tuple order kept
+      be.for_each(NRL, PHZ_LAMBDA(int64_t i) {
+        u32 t = tt2[i]; u32 v = gv[t]; u32 hap = (gc[t] & 3) ^ vh[v];
+        k32[i] = (((vfin[v] << bb) | (u32)(gc[t] >> 2)) << 1) | hap;
+      });
+      be.sort_pairs32(k32, k32b, tt2, tt, NRL, 0, fbits + bb + 1);      // by (block, BAM, haplotype), variant order kept
+    }
     u32* of = rl_frag.ensure(NRL); u32* ov = rl_var.ensure(NRL); u32* orow = rl_row.ensure(NRL);
-    be.for_each(NRL, PHZ_LAMBDA(int64_t i) { u32 t = tt[i]; of[i] = gf[t]; ov[i] = gv[t]; orow[i] = k32b[i]; });
+    be.for_each(NRL, PHZ_LAMBDA(int64_t i) { u32 t = tt[i]; of[i] = gf[t]; ov[i] = gv[t]; orow[i] = kres[i] >> shift; });
     be.stage("read_lists.end");
     return NRL;
   }

@@ -249,3 +249,22 @@ def test_compact_pair_keys_equal_wide_ones(hostsim, tmp_path):
     assert a.counters == b.counters and a.counters["edges"] > 50
     for k in a.arrays:
         assert np.array_equal(a.arrays[k], b.arrays[k]), k
+
+
+def test_single_sort_read_lists_equal_two_pass(hostsim, tmp_path):
+    """Read lists sorted once on (block, BAM, haplotype, rank of the variant in its block) == variant sort + row sort."""
+    from phaser_b200 import pipeline
+    vcf, sams = util.make_case(tmp_path, 50, 500, 9000, n_bams=3, switch_per_base=0.02)
+    vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+    P = pipeline.PhaseParams(haplo_count_bam_exclude=[2], max_block_size=6)
+    out = []
+    for two in (0, 1):
+        hostsim.set_option("two_pass_read_lists", two)
+        try:
+            out.append(pipeline.run_path(hostsim, vt, [hostsim.upload_reads(b) for b in batches], P, n_fragments=len(fd.names)))
+        finally:
+            hostsim.set_option("two_pass_read_lists", 0)
+    a, b = out
+    assert a.counters == b.counters and a.counters["read_list_entries"] > 100
+    for k in a.arrays:
+        assert np.array_equal(a.arrays[k], b.arrays[k]), k
