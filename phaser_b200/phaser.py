@@ -128,7 +128,21 @@ def _trace(t0, what):
     return time.perf_counter()
 
 
+def _warm_imports():
+    """scipy.stats takes 1-2 s to import and is first needed after the graph stage (critical values): load it on a
+    thread while the VCF and the BAMs are being read."""
+    import threading
+
+    def work():
+        try:
+            import scipy.stats  # noqa: F401
+        except Exception:
+            pass
+    threading.Thread(target=work, daemon=True).start()
+
+
 def run(args, engine=None):
+    _warm_imports()
     say("")
     say("##################################################")
     say("              Welcome to phASER v%s" % VERSION)
