@@ -1040,6 +1040,7 @@ struct Pipeline {
     u32* dm = pair_dmax.ensure(4); be.memset0(dm, 4 * sizeof(u32));
     be.for_each(NG, PHZ_LAMBDA(int64_t g) {
       u32 j0 = go[g], j1 = go[g + 1];
+      if (j1 - j0 < 2) { pc[g] = 0; return; }          // one entry = one variant: no pair, no overlap rank (most groups)
       int effbam = -1; u32 first_t = NONE32;
       for (u32 j = j0; j < j1; ++j) if (em[j] & 3) { if ((int)eb[j] > effbam) effbam = eb[j]; if (et[j] < first_t) first_t = et[j]; }
       u32 k = 0, kelig = 0;
