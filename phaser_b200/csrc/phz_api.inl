@@ -43,6 +43,7 @@ struct phz_ctx {
     st_coff.bind(b); st_cig.bind(b); st_tmp.bind(b); st_soff.bind(b); st_seq.bind(b); st_qual.bind(b);
     st_pos.bind(b); st_tlen.bind(b); st_as.bind(b);
   }
+  ~phz_ctx() { for (auto& s : slot) p.be.free_event(s.ready); }
 };
 
 static thread_local std::string g_err;

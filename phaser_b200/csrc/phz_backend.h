@@ -230,6 +230,7 @@ struct DeviceBackend {
   }
   // caller-owned events for copies that outlive the call that enqueued them (prefetch)
   void* new_event() { cudaEvent_t e; PHZ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); return (void*)e; }
+  void free_event(void* ev) { if (ev) cudaEventDestroy((cudaEvent_t)ev); }
   void copy_record(void* ev) { PHZ_CUDA(cudaEventRecord((cudaEvent_t)ev, copy_stream)); }
   void wait_event(void* ev) { PHZ_CUDA(cudaStreamWaitEvent(stream, (cudaEvent_t)ev, 0)); }
   void sync() { PHZ_CUDA(cudaStreamSynchronize(stream)); }
@@ -377,6 +378,7 @@ struct HostSimBackend {
   void h2d_copy(void* dst, const void* src, size_t bytes) { if (bytes) std::memcpy(dst, src, bytes); }
   void copy_fence() {}
   void* new_event() { return (void*)1; }
+  void free_event(void*) {}
   void copy_record(void*) {}
   void wait_event(void*) {}
   void sync() {}
