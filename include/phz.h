@@ -166,7 +166,12 @@ int phz_build_graph(phz_ctx* ctx, uint64_t n_fragments, uint64_t bam_exclude_mas
  * host with scipy (so the binomial test of phaser.py:1649 agrees bit for bit), build_haplotypes
  * (:1861-1882), phase_v3 (:2107-2324), block statistics and haplotypic counts (:876-931, 1048-1095).
  * status_flags: bit0 = a sub-block larger than 24 variants needed exhaustive phasing (unsupported),
- * bit1 = split_by_weak cannot reach max_block_size (the reference would not terminate). */
+ * bit1 = split_by_weak cannot reach max_block_size (the reference would not terminate), bit2 = a c_total had no
+ * critical value. */
+/* Optional, before phz_phase: critical values of the (few, distinct) c_total values beyond the dense table, as two
+ * host arrays with ascending totals.  With it h_kstar only has to cover the small totals; a c_total found in neither
+ * raises status bit 2.  Used once, by the next phz_phase. */
+int phz_set_big_critical_values(phz_ctx* ctx, const uint32_t* h_n, const uint32_t* h_k, int64_t count);
 int phz_phase(phz_ctx* ctx, const uint32_t* h_kstar, int64_t kstar_len, int max_block_size,
               uint64_t bam_exclude_mask, int64_t* n_final_blocks, int* status_flags);
 

@@ -316,6 +316,13 @@ int phz_build_graph(phz_ctx* ctx, uint64_t n_fragments, uint64_t excl, int64_t* 
   PHZ_CATCH
 }
 
+int phz_set_big_critical_values(phz_ctx* ctx, const uint32_t* h_n, const uint32_t* h_k, int64_t count) {
+  PHZ_TRY
+  for (int64_t i = 1; i < count; ++i) if (h_n[i] <= h_n[i - 1]) throw PhzError("phz_set_big_critical_values: totals must ascend");
+  ctx->p.set_big_critical_values(h_n, h_k, count);
+  PHZ_CATCH
+}
+
 int phz_phase(phz_ctx* ctx, const uint32_t* h_kstar, int64_t kstar_len, int max_block_size, uint64_t excl,
               int64_t* n_final_blocks, int* status_flags) {
   PHZ_TRY

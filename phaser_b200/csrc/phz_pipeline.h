@@ -87,6 +87,45 @@ __global__ void __launch_bounds__(256) variant_lists_kernel(const u32* __restric
   }
 }
 
+// Cell sums of the sorted pair table (see build_graph): every thread owns PAIR_CH consecutive pairs, accumulates its
+// runs in registers and flushes one reduction per (run, non-zero cell).  The CTA first stages run ids and cell words
+// in shared memory with coalesced loads (row stride PAIR_CH + 1: conflict-free when each thread then walks its own
+// row) -- read straight from global memory, 32 lanes x 128-byte stride thrash L1 (ncu: lg_throttle).
+constexpr int PAIR_CH = 32;
+__global__ void __launch_bounds__(256) pair_cells_kernel(const u32* __restrict__ ps, const u32* __restrict__ pf,
+                                                         const u32* __restrict__ pv2, int64_t np, u32* __restrict__ xacc) {
+  extern __shared__ u32 sh_pairs[];
+  u32* sx = sh_pairs; u32* scell = sh_pairs + 256 * (PAIR_CH + 1);
+  const int64_t base = (int64_t)blockIdx.x * (256 * PAIR_CH);
+  for (int k = 0; k < PAIR_CH; ++k) {
+    const int l = k * 256 + threadIdx.x; const int64_t i = base + l;
+    const int slot = (l / PAIR_CH) * (PAIR_CH + 1) + (l % PAIR_CH);
+    if (i < np) { sx[slot] = ps[i] + pf[i] - 1; scell[slot] = pv2[i]; }
+  }
+  __syncthreads();
+  const int64_t i0 = base + (int64_t)threadIdx.x * PAIR_CH;
+  if (i0 >= np) return;
+  const int n = (int)((np - i0) < PAIR_CH ? (np - i0) : PAIR_CH);
+  const u32* rx = sx + threadIdx.x * (PAIR_CH + 1); const u32* rc = scell + threadIdx.x * (PAIR_CH + 1);
+  u32 acc[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) acc[k] = 0;
+  u32 cur = rx[0];
+  for (int j = 0; j < n; ++j) {
+    const u32 x = rx[j];
+    if (x != cur) {
+#pragma unroll
+      for (int k = 0; k < 10; ++k) if (acc[k]) { atomicAdd(&xacc[(int64_t)cur * 10 + k], acc[k]); acc[k] = 0; }
+      cur = x;
+    }
+    const u32 cells = rc[j];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc[k] += (cells >> k) & 1u;
+  }
+#pragma unroll
+  for (int k = 0; k < 10; ++k) if (acc[k]) atomicAdd(&xacc[(int64_t)cur * 10 + k], acc[k]);
+}
+
 // unique-set sizes and per-BAM allele counts, one item per (fragment, variant, bam) entry (see build_graph)
 __global__ void __launch_bounds__(256) entry_stats_kernel(const u64* __restrict__ ek, const u32* __restrict__ em, const u8* __restrict__ eb,
                                                           int64_t ne, u64 vmask, u64 excl_mask, int nb,
@@ -520,7 +559,7 @@ struct Pipeline {
   int64_t NE = 0, NG = 0, NP = 0;
   // ------------------------------------------------------------------ pairs / edges
   Buf<B, u64> p_key, p_key2; Buf<B, u32> p_val, p_val2, p_flag, p_scan, pe_start, p_k32, p_k32b, pair_dmax;
-  Buf<B, u32> s_f32, s_f32b, v_member;
+  Buf<B, u32> s_f32, s_f32b, v_member, big_n_d, big_k_d; int64_t n_big_k = 0;
   u32 max_final_len = 0; int two_pass_read_lists = 0;
   int wide_pair_keys = 0;           // 1: always sort the pair table on 64-bit keys (A/B switch)
   Buf<B, u32> x_flag, x_scan, x_acc;
@@ -555,7 +594,7 @@ struct Pipeline {
     s_key.bind(b); s_key2.bind(b); s_val.bind(b); s_val2.bind(b); s_flag.bind(b); s_scan.bind(b);
     e_key.bind(b); e_bam.bind(b); e_mask.bind(b); e_tmin.bind(b); e_flag.bind(b); e_scan.bind(b);
     grp_off.bind(b); pair_cnt.bind(b); pair_off.bind(b);
-    p_k32.bind(b); p_k32b.bind(b); pair_dmax.bind(b); s_f32.bind(b); s_f32b.bind(b); v_member.bind(b);
+    p_k32.bind(b); p_k32b.bind(b); pair_dmax.bind(b); s_f32.bind(b); s_f32b.bind(b); v_member.bind(b); big_n_d.bind(b); big_k_d.bind(b);
     p_key.bind(b); p_key2.bind(b); p_val.bind(b); p_val2.bind(b); p_flag.bind(b); p_scan.bind(b); pe_start.bind(b);
     x_flag.bind(b); x_scan.bind(b); x_acc.bind(b);
     ed_a.bind(b); ed_b.bind(b); ed_sup.bind(b); ed_tot.bind(b); ed_n9.bind(b); ed_cfg.bind(b); ed_keep.bind(b); scalars.bind(b); kstar_d.bind(b); big_tot.bind(b);
@@ -1117,6 +1156,17 @@ struct Pipeline {
     // pair array accumulates its runs locally and flushes one atomic per (run, non-zero cell), so a pair
     // supported by a million fragments costs the same per thread as any other.
     u32* xacc = x_acc.ensure((NX + 1) * 10); be.memset0(xacc, (NX + 1) * 10 * sizeof(u32));
+#ifdef __CUDACC__
+    if (window_agg && NP > 0) {
+      const size_t smem = 2 * 256 * (PAIR_CH + 1) * sizeof(u32);
+      static bool attr_set = false;
+      if (!attr_set) { PHZ_CUDA(cudaFuncSetAttribute(pair_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+      const int64_t per = 256 * PAIR_CH;
+      pair_cells_kernel<<<(unsigned)((NP + per - 1) / per), 256, smem, be.stream>>>(ps, pf, pv2, NP, xacc);
+      PHZ_CUDA(cudaGetLastError());
+      be.launches++;
+    } else
+#endif
     {
       const int64_t CH = 32; int64_t np = NP; int64_t nchunks = (NP + CH - 1) / CH;
       be.for_each(nchunks, PHZ_LAMBDA(int64_t c) {
@@ -1170,13 +1220,22 @@ struct Pipeline {
   // kstar[n] (host, n in [0, max_tot]): smallest k with binom.cdf(k, n, p) >= cc_threshold; an edge is
   // dropped iff c_supporting == 0 or (c_total > c_supporting and c_supporting < kstar[c_total])
   // (phaser.py:1645-1652, 696).
+  // Totals beyond the dense table are looked up in the sparse list set by set_big_critical_values (ascending n).
+  void set_big_critical_values(const u32* n_host, const u32* k_host, int64_t count) {
+    n_big_k = count;
+    u32* bn = big_n_d.ensure(count + 1); u32* bk = big_k_d.ensure(count + 1);
+    be.h2d(bn, n_host, count * sizeof(u32)); be.h2d(bk, k_host, count * sizeof(u32));
+  }
+
   void phase(const u32* kstar_host, int64_t kstar_len, int max_block_size, u64 excl_mask, int* err_out) {
-    if ((int64_t)max_tot >= kstar_len && E > 0) throw PhzError("critical-value table shorter than max c_total");
+    if ((int64_t)max_tot >= kstar_len && E > 0 && n_big_k == 0) throw PhzError("critical-value table shorter than max c_total");
     const int64_t Vn = V; const int nb = n_bams > 0 ? n_bams : 1; const int vb = vbits;
     const u32* vc = vcontig.p;
     be.stage("phase.drop_union");
     u32* ks = kstar_d.ensure(kstar_len);
     be.h2d(ks, kstar_host, kstar_len * sizeof(u32));
+    const int64_t klen = kstar_len; const int64_t nbig = n_big_k; const u32* bign = big_n_d.p; const u32* bigk = big_k_d.p;
+    n_big_k = 0;                      // the sparse list belongs to this call only
     const u32* ea_ = ed_a.p; const u32* eb_ = ed_b.p; const u32* esup = ed_sup.p; const u32* etot = ed_tot.p;
     const u8* ecfg = ed_cfg.p; u8* keep = ed_keep.p;
     u32* par = parent.ensure(Vn); u32* dg = deg.ensure(Vn + 1); be.memset0(dg, (Vn + 1) * sizeof(u32));
@@ -1184,7 +1243,14 @@ struct Pipeline {
     be.for_each(Vn, PHZ_LAMBDA(int64_t v) { par[v] = (u32)v; });
     be.for_each(E, PHZ_LAMBDA(int64_t e) {
       u32 sup = esup[e], tot = etot[e];
-      bool drop = (sup == 0) || (tot > sup && sup < ks[tot]);
+      u32 kcrit;
+      if ((int64_t)tot < klen) kcrit = ks[tot];
+      else {                          // sparse tail: exact match required (the host computed one value per distinct total)
+        int64_t lo = 0, hi = nbig;
+        while (lo < hi) { int64_t m = (lo + hi) >> 1; if (bign[m] < tot) lo = m + 1; else hi = m; }
+        if (lo < nbig && bign[lo] == tot) kcrit = bigk[lo]; else { kcrit = 0; atomic_or(&sc[1], 4u); }
+      }
+      bool drop = (sup == 0) || (tot > sup && sup < kcrit);
       keep[e] = drop ? 0 : 1;
       if (drop) { atomic_add(&sc[2], 1u); return; }
       u32 a = ea_[e], b = eb_[e];

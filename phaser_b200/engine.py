@@ -57,7 +57,7 @@ EXPORTS = ["phz_last_error", "phz_backend_name", "phz_create", "phz_destroy", "p
            "phz_fragdict_create", "phz_fragdict_destroy", "phz_fragdict_size", "phz_fragdict_name", "phz_read_alignments",
            "phz_host_reads_view", "phz_host_reads_free", "phz_set_haplo_blacklist", "phz_write_sam",
            "phz_set_indel_alleles", "phz_pack_reads", "phz_packed_view", "phz_packed_bytes", "phz_packed_free",
-           "phz_map_reads_packed", "phz_prefetch_packed", "phz_gene_ae_pairs"]
+           "phz_map_reads_packed", "phz_prefetch_packed", "phz_gene_ae_pairs", "phz_set_big_critical_values"]
 
 
 def _declare(lib):
@@ -104,6 +104,7 @@ def _declare(lib):
     lib.phz_packed_bytes.argtypes = [c_void_p]
     lib.phz_packed_free.argtypes = [c_void_p]
     lib.phz_map_reads_packed.argtypes = [c_void_p, POINTER(phz_packed_reads), c_int, c_double, POINTER(c_int64)]
+    lib.phz_set_big_critical_values.argtypes = [c_void_p, c_void_p, c_void_p, c_int64]
     lib.phz_prefetch_packed.argtypes = [c_void_p, POINTER(phz_packed_reads)]
     lib.phz_gene_ae_pairs.argtypes = [c_void_p, POINTER(phz_ae_input), POINTER(c_int64)]
     return lib
@@ -396,7 +397,11 @@ class Engine:
         self._check(self.lib.phz_build_graph(self.ctx, int(n_fragments), int(exclude_mask), byref(e), byref(mt)))
         return e.value, mt.value
 
-    def phase(self, kstar: np.ndarray, max_block_size, exclude_mask=0):
+    def phase(self, kstar: np.ndarray, max_block_size, exclude_mask=0, big=None):
+        """`kstar`: dense critical values for c_total < len(kstar); `big` = (totals ascending, values) for the rest."""
+        if big is not None and len(big[0]):
+            bn = np.ascontiguousarray(big[0], np.uint32); bk = np.ascontiguousarray(big[1], np.uint32)
+            self._check(self.lib.phz_set_big_critical_values(self.ctx, bn.ctypes.data, bk.ctypes.data, bn.shape[0]))
         k = np.ascontiguousarray(kstar, np.uint32)
         nf = c_int64(0); fl = c_int(0)
         self._check(self.lib.phz_phase(self.ctx, k.ctypes.data, k.shape[0], int(max_block_size), int(exclude_mask),

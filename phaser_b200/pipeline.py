@@ -231,21 +231,23 @@ def run_path(engine: Engine, vt: VariantTable, batches, params: PhaseParams, n_f
         _t1 = time.perf_counter() if _TRACE else 0.0
         worker.join()
     _t2 = time.perf_counter() if _TRACE else 0.0
-    kstar = np.zeros(int(max_tot) + 1, np.uint32)
     m = min(int(max_tot), PRECOMPUTED_TOTALS)
-    kstar[:m + 1] = pre["k"][:m + 1]
-    n_big = 0
+    kstar = pre["k"][:m + 1]
+    n_big = 0; big_pair = None
     if max_tot > PRECOMPUTED_TOTALS and n_edges > 0:
-        # the device kept the (few) totals above the precomputed range on a side list
+        # the device kept the (few) totals above the precomputed range on a side list; their critical values go back as
+        # a sparse (total, value) list, so nothing of size max_tot is ever built or copied
         big = np.unique(engine.download("big_tot")).astype(np.int64)
         n_big = int(big.shape[0])
         p = 1 - ((6 * noise_e) + (10 * math.pow(noise_e, 2)))
-        kstar[big] = _critical_values_at(big, p, params.cc_threshold)
+        big_pair = (big.astype(np.uint32), _critical_values_at(big, p, params.cc_threshold))
     if _TRACE:
         _t3 = time.perf_counter()
         print("[run_path] build_graph %.2f ms, join wait %.2f ms, kstar assembly %.2f ms (max_tot %d, %d distinct totals above %d)" % (
             (_t1 - _t) * 1e3, (_t2 - _t1) * 1e3, (_t3 - _t2) * 1e3, max_tot, n_big, PRECOMPUTED_TOTALS), file=sys.stderr)
-    nf, flags = engine.phase(kstar, params.max_block_size, excl)
+    nf, flags = engine.phase(kstar, params.max_block_size, excl, big=big_pair)
+    if flags & 4:
+        raise PhaserFatal("internal: an edge total has no critical value")
     if flags & 2:
         raise PhaserFatal("a haplotype block cannot be split down to --max_block_size (the reference does not "
                           "terminate on this input)")
