@@ -117,21 +117,47 @@ def _binom_cdf(k, n, p):
         return binom.cdf(k, n, p)
 
 
-def _critical_values_at(n, p, cc_threshold):
+def _scipy_ppf(q, n, p):
     from scipy.stats import binom
     try:
-        k = binom._ppf(cc_threshold, n, p)
+        return binom._ppf(q, n, p)
     except Exception:
-        k = binom.ppf(cc_threshold, n, p)
-    k = np.clip(np.nan_to_num(k, nan=0.0).astype(np.int64), 0, n)
-    for _ in range(64):
-        low = _binom_cdf(k, n, p) < cc_threshold            # k too small
-        k = np.where(low & (k < n), k + 1, k)
-        km = np.maximum(k - 1, 0)
-        high = (k > 0) & (_binom_cdf(km, n, p) >= cc_threshold)   # k-1 already passes
-        k = np.where(high, km, k)
-        if not (low & (k < n)).any() and not high.any():
+        return binom.ppf(q, n, p)
+
+
+def _critical_values_at(n, p, cc_threshold):
+    """min{k : binom.cdf(k, n, p) >= cc_threshold} for every n.  Starts from the Cornish-Fisher quantile (exact for
+    ~98 % of the totals, one below otherwise) instead of scipy's inverse (an iterative root search per element), then
+    walks each element to the k with cdf(k) >= threshold > cdf(k-1) using the SAME cdf the reference's test uses,
+    re-evaluating only the elements that moved: the result does not depend on the starting point."""
+    from scipy.special import ndtri
+    n = np.asarray(n, np.int64)
+    if n.shape[0] == 0:
+        return np.zeros(0, np.uint32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        z = float(ndtri(cc_threshold)) if 0.0 < cc_threshold < 1.0 else 0.0
+        sd = np.sqrt(n * p * (1 - p))
+        w = z + (z * z - 1) * ((1 - 2 * p) / sd) / 6
+        k = np.ceil(n * p + w * sd - 0.5)
+    bad = ~np.isfinite(k)
+    if bad.any():                      # degenerate spread (p = 0 or 1, n = 0): scipy's own inverse as the start
+        k[bad] = _scipy_ppf(cc_threshold, n[bad], p)
+    k = np.clip(np.nan_to_num(k, nan=0.0, posinf=0.0, neginf=0.0).astype(np.int64), 0, n)
+    act = np.arange(n.shape[0])
+    for it in range(1 << 20):
+        if it == 8:                    # the closed form was far off for these (tiny n): restart them from the inverse
+            k[act] = np.clip(np.nan_to_num(_scipy_ppf(cc_threshold, n[act], p), nan=0.0).astype(np.int64), 0, n[act])
+        ka = k[act]; na = n[act]
+        low = (_binom_cdf(ka, na, p) < cc_threshold) & (ka < na)             # k too small
+        ka = np.where(low, ka + 1, ka)
+        km = np.maximum(ka - 1, 0)
+        high = ~low & (ka > 0) & (_binom_cdf(km, na, p) >= cc_threshold)      # k-1 already passes
+        ka = np.where(high, km, ka)
+        k[act] = ka
+        moved = low | high
+        if not moved.any():
             break
+        act = act[moved]
     # cdf(n; n, p) = 1 >= threshold always, so k <= n
     return k.astype(np.uint32)
 
