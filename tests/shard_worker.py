@@ -26,7 +26,8 @@ def main():
     kw = G.args_to_kw(c["meta"]["args"])
     vt, st, batches, col, fd = util.load_inputs(c["vcf"], c["sams"])
     P = pipeline.PhaseParams(as_q_cutoff=kw.get("as_q_cutoff", 0.05), max_block_size=kw.get("max_block_size", 15),
-                             haplo_count_bam_exclude=kw.get("exclude", []), isize=kw.get("isize", [0.0]))
+                             haplo_count_bam_exclude=kw.get("exclude", []), isize=kw.get("isize", [0.0]),
+                             want_read_ids=kw.get("output_read_ids", 0) == 1, want_kept_tuples=kw.get("output_network", "") != "")
     if on_gpu:
         from phaser_b200.engine import Engine
         e = Engine(device="cuda:%d" % int(os.environ.get("LOCAL_RANK", os.environ["RANK"])))
@@ -35,11 +36,15 @@ def main():
     res = shard.run_sharded(e, vt, batches, P, n_fragments=len(fd.names))
     rc = 0
     if dist.get_rank() == 0:
-        o = writer.Outputs(res, vt, util.bam_display_names(c["sams"]), P)
+        o = writer.Outputs(res, vt, util.bam_display_names(c["sams"]), P,
+                           read_names=fd.names if kw.get("output_read_ids", 0) == 1 else None,
+                           output_network=kw.get("output_network", ""))
         got = dict(allelic_counts=o.allelic_counts(), variant_connections=o.variant_connections())
         got["haplotypes"], got["haplotypic_counts"], got["allele_config"] = o.block_tables()
         with gzip.open(c["vcf"], "rt") as f:
             got["vcf"], _, _ = o.vcf_text(f.readlines(), col)
+        if o.network is not None:
+            got["network_links"], got["network_nodes"] = o.network
         bad = compare.diff_outputs(c["ref"], got)
         if bad:
             print("\n".join(bad)); rc = 1

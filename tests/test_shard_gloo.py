@@ -19,7 +19,7 @@ def test_lpt_plan_is_balanced_and_complete():
     assert max(loads) <= 1.15 * sum(w) / 8
 
 
-@pytest.mark.parametrize("case", ["rna_two_bams", "rna_conflict", "quirks"])
+@pytest.mark.parametrize("case", ["rna_two_bams", "rna_conflict", "quirks", "opt_read_ids", "opt_network"])
 def test_two_rank_sharded_run_matches_reference(case):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     procs = []
