@@ -60,31 +60,52 @@ class ClockSampler:
         self.proc = None
         self.index = index
 
-    def start(self):
+    def start(self, period_ms=20):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", str(period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def ensure_running(self):
+        """nvidia-smi refused the short period (it exited): fall back to 100 ms"""
+        if self.proc is not None and self.proc.poll() is not None:
+            self.start(100)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip().split(", "))
+            self.rows.append((time.time(), line.strip().split(", ")))
 
-    def stop(self):
+    def stop_rows(self, t_begin=None, t_end=None):
+        """Samples that arrived inside [t_begin, t_end] (wall clock; a 30 ms margin covers nvidia-smi's own latency).
+        The sampler is started well before the timed region so that it is already streaming when the region begins."""
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return None
+        time.sleep(0.03)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=3)
         except Exception:
             pass
+        rows = list(self.rows)
+        if t_begin is not None:
+            inside = [r for (t, r) in rows if t_begin - 0.005 <= t <= t_end + 0.03]
+            if inside:
+                return inside
+            near = sorted(rows, key=lambda x: min(abs(x[0] - t_begin), abs(x[0] - t_end)))[:1]      # nothing landed inside: the closest one
+            return [r for (_, r) in near]
+        return [r for (_, r) in rows]
+
+    @staticmethod
+    def summary(rows):
+        if rows is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for n, v in zip(names, r[3:7]):
@@ -181,12 +202,14 @@ def run_ours(a):
                                  host_inputs=host_inputs, download=host_inputs, reuse_result_buffer=True)
 
     E.set_profiling(1)
+    clocks = ClockSampler(local); clocks.start()          # streaming before the timed region starts
     for _ in range(a.warmup):
         res = step()
     own0, lib0 = E.launch_counts()
     k1_ms = []
-    clocks = ClockSampler(local); clocks.start()
+    clocks.ensure_running()
     barrier()
+    t_region0 = time.time()
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
     if a.profiler_range:
         torch.cuda.cudart().cudaProfilerStart()
@@ -198,6 +221,7 @@ def run_ours(a):
     if a.profiler_range:
         torch.cuda.synchronize(); torch.cuda.cudart().cudaProfilerStop()
     barrier()
+    clock_rows = clocks.stop_rows(t_region0, time.time())          # samples taken during the timed steps
     ms_total = ev0.elapsed_time(ev1)
     own1, lib1 = E.launch_counts()
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -303,7 +327,7 @@ def run_ours(a):
                          "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "host_form": "plain SoA arrays (phz_map_reads_host)"}
             del host
         del host_np
-    clk = clocks.stop()          # sampled through the resident-input steps AND the end-to-end legs (both are timed work)
+    clk = ClockSampler.summary(clock_rows)
     # per-stage CUDA-event times of one extra (untimed) resident step: what the K2 / K3 figures below come from
     E.set_profiling(2)
     t0 = time.perf_counter(); step(); torch.cuda.synchronize(); wall = (time.perf_counter() - t0) * 1e3
