@@ -248,7 +248,7 @@ def run_ours(a):
             traffic = tr["dram_bytes_per_launch"]
     except Exception:
         pass
-    k1_names = {3: ["tile pre-pass", "tile kernel (slab + count + scan + dense emit)", "tile-table scan + permute"],
+    k1_names = {3: ["tile pre-pass", "tile kernel (slab + count + scan + dense emit)", "tile-table scan (the commit compacts the tiles in place: no permute of the candidates)"],
                 2: ["tile pre-pass", "-", "fused look-back kernel"], 1: ["count pass", "scan + readback", "emit pass"],
                 0: ["count pass", "scan + readback", "emit pass"]}[a.k1_mode]
     # ---- end to end: pinned host arrays -> device inside the timed region -> result arrays on the host

@@ -344,6 +344,7 @@ struct ArrRef { const void* p; int64_t n; int eb; };
 
 static bool find_array(phz_ctx* ctx, const std::string& name, ArrRef* out) {
   auto& p = ctx->p;
+  if (name == "t_rec" || name == "t_var" || name == "t_misc") p.ensure_canonical();
   const int64_t nb = p.n_bams > 0 ? p.n_bams : 1;
 #define A(nm, buf, cnt) if (name == nm) { *out = ArrRef{(const void*)p.buf.p, (int64_t)(cnt), (int)sizeof(*p.buf.p)}; return true; }
   A("t_rec", t_rec, p.n_cand) A("t_var", t_var, p.n_cand) A("t_misc", t_misc, p.n_cand)
@@ -412,6 +413,7 @@ int phz_set_option(phz_ctx* ctx, const char* name, int64_t value) {
   if (n == "k1_mode") ctx->p.k1_mode = (int)value;
   else if (n == "k1_min_ctas") ctx->p.k1_min_ctas = (int)value;
   else if (n == "big_total_threshold") ctx->p.big_total_thr = (u32)value;
+  else if (n == "lazy_canonical") ctx->p.lazy_canonical = (int)value;
   else if (n == "two_pass_read_lists") ctx->p.two_pass_read_lists = (int)value;
   else if (n == "wide_pair_keys") ctx->p.wide_pair_keys = (int)value;
   else if (n == "window_agg") ctx->p.window_agg = (int)value;

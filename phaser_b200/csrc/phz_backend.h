@@ -51,6 +51,23 @@ typedef unsigned long long u64;
 typedef uint32_t u32;
 typedef uint8_t u8;
 
+// Full-warp helpers for for_each_warp bodies (all 32 lanes of a warp run the body for the same item; the host
+// simulation runs it once with one lane).
+PHZ_HD u32 warp_ballot(bool p) {
+#if defined(__CUDA_ARCH__)
+  return __ballot_sync(0xFFFFFFFFu, p);
+#else
+  return p ? 1u : 0u;
+#endif
+}
+PHZ_HD u32 popc_u32(u32 x) {
+#if defined(__CUDA_ARCH__)
+  return (u32)__popc(x);
+#else
+  return (u32)__builtin_popcount(x);
+#endif
+}
+
 // *addr += 1, combined over whatever lanes of the warp are converged here and target the same address (usable inside
 // divergent loops: the set of participants is taken as it is found)
 PHZ_HD void converged_inc(u32* addr) {

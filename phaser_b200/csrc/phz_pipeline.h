@@ -567,6 +567,8 @@ struct Pipeline {
   Buf<B, u32> scalars, kstar_d;                     // scalars: [0]=max_tot [1]=err flags [2]=dropped [3]=n_big_tot
   Buf<B, u32> big_tot;                              // c_total values above big_total_thr (unordered, with repeats)
   int64_t NX = 0, E = 0; u32 max_tot = 0; int64_t NBT = 0; u32 big_total_thr = 2048;
+  int lazy_canonical = 1;           // 1: the tile kernel's output stays in arrival order until somebody needs canonical order
+  bool tile_order = false, canonical_valid = true; int64_t tiles_cur = 0;
   int window_agg = 1;               // 1: shared-memory window kernels for the per-variant counters, 0: warp-aggregated global atomics
   int64_t frag_run_limit = 1024; int64_t n_runs_resorted = 0; bool full_sort_fallback = false;
   // ------------------------------------------------------------------ blocks
@@ -647,6 +649,7 @@ struct Pipeline {
       return map_reads_tiles(rv, vi, baseq, isize_cutoff);
     }
     if (k1_mode == 3) return map_reads_tiles(rv, vv, baseq, isize_cutoff);
+    tile_order = false; canonical_valid = true; tiles_cur = 0;
     if (k1_mode == 2) return map_reads_fused(rv, vv, baseq, isize_cutoff);
     u32* cnt = cand_cnt.ensure(R + 1);
     u32* off = cand_off.ensure(R + 2);
@@ -667,6 +670,7 @@ struct Pipeline {
   template <class VV>
   int64_t map_reads_tiles(const ReadsView& rv, const VV& vv, int baseq, double isize_cutoff) {
     const int64_t R = rv.n_records;
+    tile_order = false; tiles_cur = 0; canonical_valid = true;
     if (R <= 0) { n_cand = 0; be.mark(0); be.mark(1); be.mark(2); be.mark(3); return 0; }
     const int64_t n_tiles = (R + KF_THREADS - 1) / KF_THREADS;
     TileInfo* ti = tile_info.ensure(n_tiles);
@@ -720,22 +724,34 @@ struct Pipeline {
     }
     n_cand = (int64_t)total;
     be.mark(2);
-    // canonical order: tile t's block moves from tile_base[t] (arrival order) to the running sum of counts
+    // Tile t's block sits at tile_base[t] (arrival order); its canonical place is the running sum of the counts.
+    // The stages that follow (AS histogram, commit) read the blocks where they are, through the tile table; the
+    // canonical arrays t_rec / t_var / t_misc are only materialised when somebody asks for them (ensure_canonical).
     be.exclusive_scan_u32(tc, tn, n_tiles);
+    tiles_cur = n_tiles; tile_order = lazy_canonical != 0; canonical_valid = false;
+    if (!tile_order) ensure_canonical();
+    be.mark(3);
+    return n_cand;
+  }
+
+  // canonical (record, segment, variant) order of the candidate tuples of the last tile-kernel run
+  void ensure_canonical() {
+    if (canonical_valid || tiles_cur == 0) { canonical_valid = true; return; }
+    const u32* tb = tile_base.p; const u32* tc = tile_cnt.p; const u32* tn = tile_canon.p;
     u32* tr = t_rec.ensure(n_cand); u32* tv = t_var.ensure(n_cand); u32* tm = t_misc.ensure(n_cand);
     const u32* sr = s_rec.p; const u32* sv = s_var.p; const u32* sm = s_misc.p;
-    be.for_each_warp(n_tiles, PHZ_LAMBDA_WARP(int64_t t, int lane, int nlanes) {
+    be.for_each_warp(tiles_cur, PHZ_LAMBDA_WARP(int64_t t, int lane, int nlanes) {
       u32 n = tc[t]; u32 src = tb[t], dst = tn[t];
       for (u32 i = (u32)lane; i < n; i += (u32)nlanes) { tr[dst + i] = sr[src + i]; tv[dst + i] = sv[src + i]; tm[dst + i] = sm[src + i]; }
     });
-    be.mark(3);
-    return n_cand;
+    canonical_valid = true;
   }
 
   // Fused single-pass K1.  Output capacity is what the buffers already hold (or a first guess); if the
   // exact total turns out larger the buffers grow and the kernel runs once more.
   int64_t map_reads_fused(const ReadsView& rv, const VariantsView& vv, int baseq, double isize_cutoff) {
     const int64_t R = rv.n_records;
+    tile_order = false; tiles_cur = 0; canonical_valid = true;
     if (R <= 0) { n_cand = 0; be.mark(0); be.mark(1); be.mark(2); be.mark(3); return 0; }
     const int64_t n_tiles = (R + KF_THREADS - 1) / KF_THREADS;
     TileInfo* ti = tile_info.ensure(n_tiles);
@@ -828,7 +844,7 @@ struct Pipeline {
   void as_histogram(u64* hist) {
     be.memset0(hist, AS_BINS * sizeof(u64));
     if (n_cand == 0) return;
-    const u32* tm = t_misc.p; int64_t n = n_cand;
+    const u32* tm = tile_order ? s_misc.p : t_misc.p; int64_t n = n_cand;      // order does not matter here
 #ifdef __CUDACC__
     int blocks = (int)((n + 256 * 16 - 1) / (256 * 16)); if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
     as_hist_kernel<<<blocks, 256, 0, be.stream>>>(tm, n, hist);
@@ -842,11 +858,54 @@ struct Pipeline {
 #endif
   }
 
+  // commit straight from the tile kernel's output: per tile the number of kept tuples, a scan over the tile table
+  // (canonical order = tile order), then every warp compacts its own tile to its canonical place in the run-wide
+  // store.  Same result as permute + flag scan + scatter over all candidates, without moving the candidates twice.
+  int64_t commit_bam_tiles(int bam, int32_t as_cutoff, const u32* frag) {
+    const int64_t nt = tiles_cur;
+    be.stage("commit_bam");
+    const u32* tb = tile_base.p; const u32* tc = tile_cnt.p;
+    const u32* sr = s_rec.p; const u32* sv = s_var.p; const u32* sm = s_misc.p;
+    u32* kc = keep_flag.ensure(nt + 1); u32* ko = keep_off.ensure(nt + 2);
+    be.for_each_warp(nt, PHZ_LAMBDA_WARP(int64_t t, int lane, int nlanes) {
+      u32 n = tc[t]; u32 src = tb[t]; u32 k = 0;
+      for (u32 i0 = 0; i0 < n; i0 += (u32)nlanes) {
+        u32 i = i0 + (u32)lane; bool keep = false;
+        if (i < n) { u32 m = sm[src + i]; keep = misc_cls(m) != CLS_NONE && misc_as(m) >= as_cutoff; }
+        k += popc_u32(warp_ballot(keep));
+      }
+      if (lane == 0) kc[t] = k;
+    });
+    be.exclusive_scan_u32(kc, ko, nt);
+    int64_t nk = nt > 0 ? (int64_t)fetch_u32(ko + nt) : 0;
+    if (n_tuples + nk >= (int64_t)0xFFFFFFF0ull) throw PhzError("more than 2^32 tuples");
+    u32* gf = g_frag.grow(n_tuples + nk, n_tuples); u32* gv = g_var.grow(n_tuples + nk, n_tuples);
+    u8* gc = g_cb.grow(n_tuples + nk, n_tuples);
+    int64_t base = n_tuples;
+    be.for_each_warp(nt, PHZ_LAMBDA_WARP(int64_t t, int lane, int nlanes) {
+      u32 n = tc[t]; u32 src = tb[t]; int64_t o = base + ko[t];
+      for (u32 i0 = 0; i0 < n; i0 += (u32)nlanes) {
+        u32 i = i0 + (u32)lane; bool keep = false; u32 m = 0;
+        if (i < n) { m = sm[src + i]; keep = misc_cls(m) != CLS_NONE && misc_as(m) >= as_cutoff; }
+        u32 b = warp_ballot(keep);
+        if (keep) {
+          int64_t w = o + popc_u32(b & ((1u << lane) - 1u));
+          gf[w] = frag[sr[src + i]]; gv[w] = sv[src + i]; gc[w] = (u8)(misc_cls(m) | (bam << 2));
+        }
+        o += popc_u32(b);
+      }
+    });
+    n_tuples += nk; n_bams = bam + 1; n_cand = 0; tile_order = false; tiles_cur = 0; canonical_valid = true;
+    be.stage("commit_bam.end");
+    return nk;
+  }
+
   // keep tuples with a printed allele and AS >= cutoff (phaser.py:1304); cutoff = INT32_MIN disables it
   int64_t commit_bam(int bam, int32_t as_cutoff, const u32* frag) {
     if (bam != n_bams) throw PhzError("commit_bam: BAMs must be committed in order");
     if (bam >= 64) throw PhzError("at most 64 BAMs");
     int64_t n = n_cand;
+    if (tile_order) return commit_bam_tiles(bam, as_cutoff, frag);
     u32* ko = keep_off.ensure(n + 2);
     be.stage("commit_bam");
     const u32* tr = t_rec.p; const u32* tv = t_var.p; const u32* tm = t_misc.p;

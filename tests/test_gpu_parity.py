@@ -346,3 +346,27 @@ def test_single_sort_read_lists_equal_two_pass(gpu, tmp_path):
     assert a.counters == b.counters and a.counters["read_list_entries"] > 100
     for k in a.arrays:
         assert np.array_equal(a.arrays[k], b.arrays[k]), k
+
+
+def test_tile_order_commit_equals_canonical_commit(gpu, tmp_path):
+    """The commit that compacts each tile of the K1 output to its canonical place (no permute of the candidates)
+    against permute + scan + scatter; and the canonical candidate arrays materialised on demand are the same."""
+    from phaser_b200 import pipeline
+    vcf, sams = util.make_case(tmp_path, 52, 600, 40000, n_bams=2, switch_per_base=0.02)
+    vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+    P = pipeline.PhaseParams()
+    out = []; tup = []
+    for lazy in (1, 0):
+        gpu.set_option("lazy_canonical", lazy)
+        try:
+            gpu.set_variants(vt)
+            gpu.map_reads(gpu.upload_reads(batches[0]), 10, 0.0)
+            tup.append([gpu.download(k).copy() for k in ("t_rec", "t_var", "t_misc")])
+            out.append(pipeline.run_path(gpu, vt, [gpu.upload_reads(b) for b in batches], P, n_fragments=len(fd.names)))
+        finally:
+            gpu.set_option("lazy_canonical", 1)
+    assert tup[0][0].shape[0] > 10000 and all(np.array_equal(a, b) for a, b in zip(*tup))
+    a, b = out
+    assert a.counters == b.counters
+    for k in a.arrays:
+        assert np.array_equal(a.arrays[k], b.arrays[k]), k
