@@ -393,6 +393,12 @@ def cpu_sample_files(a, tmp):
     vcf = synth.write_vcf(g, os.path.join(tmp, "sample.vcf.gz"))
     from phaser_b200 import engine as eng
     sam = eng.write_sam_native(rec, g.contigs, os.path.join(tmp, "sample.bam"), bam_name="bam0")
+    # gene spans of the synthetic genome as BED features (for the gene-level leg)
+    ne = g.g_nexon.cpu().numpy(); es = g.exon_start.cpu().numpy(); el = g.exon_len.cpu().numpy(); gc = g.g_contig.cpu().numpy()
+    with open(os.path.join(tmp, "genes.bed"), "w") as f:
+        for i in range(ne.shape[0]):
+            a = int(es[i, 0]); b = int(es[i, ne[i] - 1] + el[i, ne[i] - 1])
+            f.write("%s\t%d\t%d\tgene%d\n" % (g.contigs[int(gc[i])][0], a, b, i))
     return g, rec, vcf, sam, n_pairs, int(g.v_pos.shape[0])
 
 
@@ -464,10 +470,34 @@ def cli_files_to_files(a, engine):
                 cli.run(cli.build_parser().parse_args(argv), engine=engine)
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
-        return {"value": n_var / best, "unit": "het-SNVs/s", "seconds": best, "records_per_sec": n_rec / best,
-                "sample": "same %d-pair files as cpu_baseline; process start-up and torch import not included" % n_pairs}
+        out = {"value": n_var / best, "unit": "het-SNVs/s", "seconds": best, "records_per_sec": n_rec / best,
+               "sample": "same %d-pair files as cpu_baseline; process start-up and torch import not included" % n_pairs}
+        try:
+            out["gene_ae"] = gene_ae_leg(engine, os.path.join(tmp, "out.haplotypic_counts.txt"),
+                                         os.path.join(os.path.dirname(vcf), "genes.bed"))
+        except Exception as e:          # the leg is a side measurement: never lose the main line over it
+            out["gene_ae"] = {"error": str(e)[:200]}
+        return out
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+def gene_ae_leg(engine, hc_path, bed_path):
+    """SURVEY 8f row N1 measured: phaser_gene_ae on the haplotypic_counts.txt the command line just wrote for the
+    bounded sample, gene spans of the synthetic genome as features.  GPU: join + distinct-read counting
+    (phz_gene_ae_pairs, CUDA-event stage times) inside the drop-in module; CPU: the oracle restatement
+    (oracle/port_gene_ae.py, interval index like the reference's intervaltree) -- and the two texts must be equal."""
+    from phaser_b200 import phaser_gene_ae as ga
+    from oracle import port_gene_ae as pg
+    hc = open(hc_path).read(); bed = open(bed_path).read()
+    ga.run_text(engine, hc, bed)                                         # warm-up (buffers)
+    engine.set_profiling(2); engine.stage_report()
+    t0 = time.perf_counter(); got = ga.run_text(engine, hc, bed); t_gpu = time.perf_counter() - t0
+    st = {k: round(v, 3) for k, v in engine.stage_report().items() if k.startswith("gene_ae")}
+    engine.set_profiling(1)
+    t0 = time.perf_counter(); exp = pg.run(hc, bed); t_cpu = time.perf_counter() - t0
+    return {"rows": hc.count("\n") - 1, "features": bed.count("\n"), "device_stage_ms": st,
+            "product_seconds_incl_parse_and_text": t_gpu, "cpu_port_seconds": t_cpu, "identical_text": got == exp}
 
 
 def run_reference(a):

@@ -68,6 +68,22 @@ def run(hc_text, features_text, id_separator="_", gw_cutoff=0.9, min_cov=0, min_
     by_chrom = {}
     for i, f in enumerate(feats):
         by_chrom.setdefault(f["chr"], []).append(i)
+    # interval index per contig (what intervaltree gives the reference): features by start + running maximum of stops
+    import bisect
+    index = {}
+    for c, ids in by_chrom.items():
+        ids = sorted(ids, key=lambda i: (feats[i]["start"], i))
+        starts = [feats[i]["start"] for i in ids]
+        mx = []; cur = -1
+        for i in ids:
+            cur = max(cur, feats[i]["stop"]); mx.append(cur)
+        index[c] = (ids, starts, mx)
+
+    def overlapping(chrom, lo, hi):
+        ids, starts, mx = index[chrom]
+        j1 = bisect.bisect_left(starts, hi)                 # features with start < hi
+        j0 = bisect.bisect_right(mx, lo, 0, j1)             # first position whose running max of stops exceeds lo
+        return sorted(ids[j] for j in range(j0, j1) if feats[ids[j]]["stop"] > lo)
     cols, rows = parse_rows(hc_text)
     if "bam" not in cols:
         raise SystemExit("ERROR - this version of phaser_gene_ae is only compatible with results from phASER v1.0.0+")
@@ -81,10 +97,8 @@ def run(hc_text, features_text, id_separator="_", gw_cutoff=0.9, min_cov=0, min_
                 continue
             if row["totalCount"] > 0 and row["contig"] in by_chrom:          # :105
                 lo, hi = row["start"] - 1, row["stop"]
-                for fi in by_chrom[row["contig"]]:
+                for fi in (overlapping(row["contig"], lo, hi) if lo < hi else []):      # IntervalTree[lo:hi]
                     f = feats[fi]
-                    if not (lo < hi and f["start"] < hi and f["stop"] > lo):  # IntervalTree[lo:hi]
-                        continue
                     m = variant_feature_reads(row, f["start"], f["stop"], id_separator)
                     s = st[fi]
                     if row["blockGWPhase"] != "0/1" and float(row["gwStat"] >= gw_cutoff):      # :113
