@@ -367,6 +367,10 @@ def run_ours(a):
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "algorithmic_bytes": bytes_k1, "ms": k1_total_ms,
                          "ms_parts": dict(zip(k1_names, [float(x) for x in k1.mean(0)])), "traffic": traffic,
+                         # what the tile kernel really moves (ncu DRAM bytes / its own launch time): it fetches only the
+                         # SEQ/QUAL sectors under het sites, so the algorithmic figure above overstates its DRAM load
+                         "dram_achieved": (traffic / (float(k1.mean(0)[1]) * 1e-3) / 1e9) if traffic else None,
+                         "dram_frac": (traffic / (float(k1.mean(0)[1]) * 1e-3) / 1e9 / peak) if traffic else None,
                          "k1_mode": a.k1_mode},
             "e2e": e2e, "e2e_plain_soa": e2e_plain, "cpu_baseline": cpu, "cli_files_to_files": cli,
             "gpu_launches": int((own1 - own0) / a.steps), "library_passes": int((lib1 - lib0) / a.steps),
