@@ -1071,20 +1071,13 @@ struct Pipeline {
     be.exclusive_scan_u32(sf, ss, n);
     NE = n > 0 ? (int64_t)fetch_u32(ss + n) : 0;
     u64* ek = e_key.ensure(NE); u8* eb = e_bam.ensure(NE); u32* em = e_mask.ensure(NE); u32* et = e_tmin.ensure(NE);
-    { int64_t nn = n;       // the first tuple of every entry folds its (short) run: class mask, first allele tuple
-      be.for_each(n, PHZ_LAMBDA(int64_t i) {
-        if (!sf[i]) return;
-        u32 mask = 0, tmin = NONE32;
-        int64_t j = i;
-        do {
-          u32 t = x2[j]; u32 cls = gc[t] & 3;
-          mask |= 1u << cls;
-          if (cls < 2 && t < tmin) tmin = t;
-          ++j;
-        } while (j < nn && !sf[j]);
-        u32 e = ss[i];
-        ek[e] = k2[i]; eb[e] = gc[x2[i]] >> 2; em[e] = mask; et[e] = tmin;
-      }); }
+    be.memset0(em, NE * sizeof(u32)); be.memset_ff(et, NE * sizeof(u32));
+    be.for_each(n, PHZ_LAMBDA(int64_t i) {
+      u32 e = ss[i] + sf[i] - 1; u32 t = x2[i]; u32 cls = gc[t] & 3;
+      if (sf[i]) { ek[e] = k2[i]; eb[e] = gc[t] >> 2; }
+      atomic_or(&em[e], 1u << cls);
+      if (cls < 2) atomic_min(&et[e], t);
+    });
     be.stage("graph.groups");
     // ---- groups = (fragment, contig) runs of entries
     u32* ef = e_flag.ensure(NE + 1); u32* es = e_scan.ensure(NE + 2);
