@@ -153,13 +153,15 @@ def parse_vcf(path, sample_column: int, pass_only=1, chrom_of_interest="", chr_p
                         use = [int(a) - 1 for a in xgeno if a != "." and int(a) != 0]
                         if use:
                             maf = min(min(afs[x], 1 - afs[x]) for x in use)
-            if max(len(x) for x in all_alleles) == 1 or include_indels == 1:        # phaser.py:1398-1400
+            # (common case first: one-base REF and one-base ALTs need none of the general length tests)
+            all_single = len(cut[3]) == 1 and (len(cut[4]) == 1 or all(len(x) == 1 for x in alt))
+            if all_single or max(len(x) for x in all_alleles) == 1 or include_indels == 1:        # phaser.py:1398-1400
                 ind = [all_alleles[i] for i in range(len(all_alleles)) if str(i) in xgeno]
                 if len(ind) != 2 or len(xgeno) != 2:
                     raise PhaserFatal("Variant %s:%s: only diploid genotypes with two distinct alleles are supported."
                                       % (chrom, cut[1]))
                 pos.append(int(cut[1]))
-                if is_indel_site(cut[3], ind):
+                if not all_single and is_indel_site(cut[3], ind):
                     a0.append(ALLELE_MULTI); a1.append(ALLELE_MULTI)
                 else:
                     a0.append(allele_code(ind[0])); a1.append(allele_code(ind[1]))

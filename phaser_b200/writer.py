@@ -353,10 +353,14 @@ class Outputs:
         fmt_text = ""
         corrections = unphased_phased = 0
         tags = ['PG', 'PB', 'PI', 'PW', 'PC', 'PM']
+        fmt_cache = {}
         for line in vcf_lines:
             cols = line.replace("\n", "").split("\t")
             cols = cols[0:9] + ([cols[sample_column]] if len(cols) > sample_column else [])
-            line = "\t".join(cols) + "\n"
+            if line[0:1] != "#" and "##FORMAT" not in line:
+                line = "d"            # a data line: none of the header tests below can match the cut line either
+            else:
+                line = "\t".join(cols) + "\n"
             if "##FORMAT" in line:
                 fmt_text += line
                 out.append(line)
@@ -375,27 +379,33 @@ class Outputs:
             else:
                 chrom = cols[0]; pos = int(cols[1])
                 if chrom_of_interest == "" or chrom == chrom_of_interest:
-                    if "GT" in cols[8]:
-                        gt_index = cols[8].split(":").index("GT")
+                    fmt = cols[8]
+                    if "GT" in fmt:
+                        info = fmt_cache.get(fmt)
+                        if info is None:          # FORMAT strings repeat line after line: split / extend them once
+                            fields = fmt.split(":")
+                            ff0 = list(fields)
+                            for t in tags:
+                                if t not in ff0:
+                                    ff0.append(t)
+                            info = (fields.index("GT"), len(fields), ff0, ":".join(ff0), [ff0.index(t) for t in tags])
+                            fmt_cache[fmt] = info
+                        gt_index, n_fields, ff0, fmt_out, (iPG, iPB, iPI, iPW, iPC, iPM) = info
                         genotype = list(cols[9].split(":")[gt_index])
                         if "|" in genotype:
                             genotype.remove("|")
                         if "/" in genotype:
                             genotype.remove("/")
                         all_alleles = [cols[3]] + cols[4].split(",")
-                        n_fields = len(cols[8].split(":"))
                         for i in range(9, len(cols)):
                             sf = len(cols[i].split(":"))
                             if sf != n_fields:
                                 cols[i] += ":" * (n_fields - sf)
-                        ff = cols[8].split(":")
-                        for t in tags:
-                            if t not in ff:
-                                ff.append(t)
-                        cols[8] = ":".join(ff)
+                        cols[8] = fmt_out
                         uid = chrom + id_separator + str(pos) + id_separator + id_separator.join(all_alleles)
                         v = id_to_v.get(uid)
                         if v is not None and v in self.lookup:
+                            ff = list(ff0)
                             members, ab, bidx, max_maf = self.lookup[v]
                             m = self.meta(v)
                             alleles_out = []; gw_out = ["", ""]
@@ -424,12 +434,12 @@ class Outputs:
                                     cols[9] = ":".join(xf)
                             sf = cols[9].split(":")
                             sf += [''] * (len(ff) - len(sf))
-                            sf[ff.index('PG')] = "|".join(alleles_out)
-                            sf[ff.index('PB')] = ",".join(names)
-                            sf[ff.index('PI')] = str(bidx)
-                            sf[ff.index('PM')] = str(max_maf)
-                            sf[ff.index('PW')] = "|".join(gw_out)
-                            sf[ff.index('PC')] = str(stat)
+                            sf[iPG] = "|".join(alleles_out)
+                            sf[iPB] = ",".join(names)
+                            sf[iPI] = str(bidx)
+                            sf[iPM] = str(max_maf)
+                            sf[iPW] = "|".join(gw_out)
+                            sf[iPC] = str(stat)
                             if gw_phase_vcf == 2 and stat < min_conf:
                                 if 'PS' not in ff:
                                     cols[8] += ":PS"; ff.append("PS"); sf.append('')
@@ -437,11 +447,12 @@ class Outputs:
                             cols[9] = ":".join(sf)
                         else:
                             sf = cols[9].split(":")
-                            sf += [''] * (len(ff) - len(sf))
-                            sf[ff.index('PG')] = "/".join(sorted(genotype))
-                            sf[ff.index('PB')] = '.'; sf[ff.index('PI')] = '.'; sf[ff.index('PM')] = '.'
-                            sf[ff.index('PW')] = cols[9].split(":")[gt_index]
-                            sf[ff.index('PC')] = '.'
+                            gt_text = sf[gt_index]
+                            sf += [''] * (len(ff0) - len(sf))
+                            sf[iPG] = "/".join(sorted(genotype))
+                            sf[iPB] = '.'; sf[iPI] = '.'; sf[iPM] = '.'
+                            sf[iPW] = gt_text
+                            sf[iPC] = '.'
                             cols[9] = ":".join(sf)
                     out.append("\t".join(cols[0:9] + [cols[9]]) + "\n")
         return "".join(out), unphased_phased, corrections
