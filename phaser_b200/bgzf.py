@@ -26,6 +26,7 @@ class BGZFWriter:
         self.buf = bytearray()
         self.level = level
         self.coffset = 0          # compressed bytes written so far = file offset of the block being filled
+        self.block_sizes = []     # compressed size of every block emitted so far (the EOF block is not listed)
 
     def tell_virtual(self):
         """BGZF virtual file offset of the next byte written: block start << 16 | offset inside the block"""
@@ -35,6 +36,7 @@ class BGZFWriter:
         blk = compress_block(raw, self.level)
         self.f.write(blk)
         self.coffset += len(blk)
+        self.block_sizes.append(len(blk))
 
     def write(self, data):
         if isinstance(data, str):

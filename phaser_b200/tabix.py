@@ -137,18 +137,39 @@ def record_span(cols):
 
 
 def write_vcf_with_index(path_vcf_gz, text, csi=False):
-    """bgzip + tabix of `text` (the whole VCF): writes path_vcf_gz and path_vcf_gz + '.tbi' (or '.csi')."""
-    ib = IndexBuilder()
+    """bgzip + tabix of `text` (the whole VCF): writes path_vcf_gz and path_vcf_gz + '.tbi' (or '.csi').
+
+    The BGZF writer cuts the byte stream into fixed 0xff00-byte blocks, so the virtual offset of every line follows
+    from its byte offset and the compressed block sizes: the file is written in one go and the offsets of all data
+    lines are computed at once; only the (chrom, pos, ref length) fields are pulled out line by line."""
+    import numpy as np
+    data = text.encode()
     with bgzf.BGZFWriter(path_vcf_gz) as w:
-        for line in text.splitlines(keepends=True):
-            if line.startswith("#") or line.strip() == "":
-                w.write(line)
-                continue
-            v0 = w.tell_virtual()
-            w.write(line)
-            cols = line.split("\t", 8)
-            beg, end = record_span(cols)
-            ib.add(cols[0], beg, end, v0, w.tell_virtual())
+        w.write(data)
+        sizes = w.block_sizes        # filled as blocks are emitted; the last partial block is emitted by close()
+    cstart = np.concatenate([[0], np.cumsum(np.asarray(sizes, np.int64))])      # compressed offset of block b
+    buf = np.frombuffer(data, np.uint8)
+    nl = np.flatnonzero(buf == 10)
+    starts = np.concatenate([[0], nl + 1])
+    if starts.shape[0] and starts[-1] >= len(data):
+        starts = starts[:-1]
+    ends = np.concatenate([nl + 1, [len(data)]])[:starts.shape[0]]
+    is_data = (buf[starts] != ord("#")) & (ends - starts > 1)
+
+    def voff(u):
+        b = u // bgzf.MAX_BLOCK
+        return (cstart[b] << 16) | (u - b * bgzf.MAX_BLOCK)
+    ds = starts[is_data]; de = ends[is_data]
+    v0 = voff(ds).tolist(); v1 = voff(de).tolist()
+    ib = IndexBuilder()
+    mv = memoryview(data)
+    for k, (a, b) in enumerate(zip(ds.tolist(), de.tolist())):
+        cols = bytes(mv[a:b]).split(b"\t", 8)
+        beg = int(cols[1]) - 1
+        end = beg + len(cols[3])
+        if len(cols) > 7 and b"END=" in cols[7]:
+            beg, end = record_span([c.decode() for c in cols])
+        ib.add(cols[0].decode(), beg, end, v0[k], v1[k])
     idx = path_vcf_gz + (".csi" if csi else ".tbi")
     with bgzf.BGZFWriter(idx) as w:
         w.write(ib.csi_bytes() if csi else ib.tbi_bytes())
