@@ -268,7 +268,8 @@ def run(args, engine=None):
                 f, sample_column, id_separator=args.id_separator, gw_phase_vcf=args.gw_phase_vcf,
                 min_conf=args.gw_phase_vcf_min_confidence, chrom_of_interest=args.chr)
         # what `bgzip -f` + `tabix -f -p vcf [--csi]` write (phaser.py:1847-1853); --csi iff the input VCF has a .csi (:131)
-        tabix.write_vcf_with_index(args.o + ".vcf.gz", text, csi=os.path.isfile(args.vcf + ".csi"))
+        tabix.write_vcf_with_index(args.o + ".vcf.gz", text, csi=os.path.isfile(args.vcf + ".csi"),
+                                   records=getattr(out, "vcf_records", None))
     _t = _trace(_t, "vcf out")
     total_time = time.time() - start_time
     say('')

@@ -76,6 +76,42 @@ class IndexBuilder:
                 lin[w] = voff_beg
         r["last"] = voff_end; r["n"] += 1
 
+    def add_many(self, chrom, beg, end, v0, v1):
+        """All records of one reference at once (numpy arrays, file order, consecutive lines): same index as add()
+        record by record."""
+        import numpy as np
+        n = int(beg.shape[0])
+        if n == 0:
+            return
+        if chrom in self.refs:             # a reference seen before (unsorted file): keep the scalar path
+            for k in range(n):
+                self.add(chrom, int(beg[k]), int(end[k]), int(v0[k]), int(v1[k]))
+            return
+        end = np.where(end <= beg, beg + 1, end)
+        e1 = end - 1
+        bins = np.zeros(n, np.int64); done = np.zeros(n, bool)
+        s = MIN_SHIFT; t = ((1 << (3 * DEPTH)) - 1) // 7
+        for level in range(DEPTH, 0, -1):
+            hit = ~done & ((beg >> s) == (e1 >> s))
+            bins[hit] = t + (beg[hit] >> s); done |= hit
+            s += 3; t -= 1 << (3 * (level - 1))
+        # consecutive records of one bin form one chunk (their lines are adjacent in the file)
+        brk = np.flatnonzero((bins[1:] != bins[:-1]) | (v0[1:] != v1[:-1])) + 1
+        rs = np.concatenate([[0], brk]); re_ = np.concatenate([brk, [n]]) - 1
+        bd = {}
+        for b, a, z in zip(bins[rs].tolist(), v0[rs].tolist(), v1[re_].tolist()):
+            bd.setdefault(b, []).append([a, z])
+        w0 = beg >> MIN_SHIFT; w1 = e1 >> MIN_SHIFT
+        lin = np.zeros(int(w1.max()) + 1, np.int64)
+        uw, first = np.unique(w0, return_index=True)
+        lin[uw] = v0[first]
+        for k in np.flatnonzero(w1 > w0).tolist():          # records spanning several 16 kb windows (rare)
+            for w in range(int(w0[k]) + 1, int(w1[k]) + 1):
+                if lin[w] == 0 or v0[k] < lin[w]:
+                    lin[w] = v0[k]
+        self.refs[chrom] = dict(bins=bd, lin=lin.tolist(), first=int(v0[0]), last=int(v1[-1]), n=n, last_bin=int(bins[-1]))
+        self.names.append(chrom)
+
     def _finish_linear(self, r):
         lin = r["lin"]
         for i in range(1, len(lin)):            # windows without a record point at the previous one (htslib)
@@ -136,17 +172,18 @@ def record_span(cols):
     return beg, end
 
 
-def write_vcf_with_index(path_vcf_gz, text, csi=False):
+def write_vcf_with_index(path_vcf_gz, text, csi=False, records=None):
     """bgzip + tabix of `text` (the whole VCF): writes path_vcf_gz and path_vcf_gz + '.tbi' (or '.csi').
 
     The BGZF writer cuts the byte stream into fixed 0xff00-byte blocks, so the virtual offset of every line follows
-    from its byte offset and the compressed block sizes: the file is written in one go and the offsets of all data
-    lines are computed at once; only the (chrom, pos, ref length) fields are pulled out line by line."""
+    from its byte offset and the compressed block sizes: the file is written in one go, the offsets of all data lines
+    are computed at once and every reference is indexed with array operations.  `records` = (chroms, begs, ends) of
+    the data lines in file order when the caller already has them (the VCF writer does); otherwise the lines are split."""
     import numpy as np
     data = text.encode()
     with bgzf.BGZFWriter(path_vcf_gz) as w:
         w.write(data)
-        sizes = w.block_sizes        # filled as blocks are emitted; the last partial block is emitted by close()
+        sizes = w.block_sizes        # a reference to the list: the last partial block is appended by close()
     cstart = np.concatenate([[0], np.cumsum(np.asarray(sizes, np.int64))])      # compressed offset of block b
     buf = np.frombuffer(data, np.uint8)
     nl = np.flatnonzero(buf == 10)
@@ -154,22 +191,31 @@ def write_vcf_with_index(path_vcf_gz, text, csi=False):
     if starts.shape[0] and starts[-1] >= len(data):
         starts = starts[:-1]
     ends = np.concatenate([nl + 1, [len(data)]])[:starts.shape[0]]
-    is_data = (buf[starts] != ord("#")) & (ends - starts > 1)
+    is_data = (buf[starts] != ord("#")) & (ends - starts > 1) if starts.shape[0] else np.zeros(0, bool)
 
     def voff(u):
         b = u // bgzf.MAX_BLOCK
         return (cstart[b] << 16) | (u - b * bgzf.MAX_BLOCK)
     ds = starts[is_data]; de = ends[is_data]
-    v0 = voff(ds).tolist(); v1 = voff(de).tolist()
+    v0 = voff(ds); v1 = voff(de)
+    if records is not None and len(records[0]) == ds.shape[0]:
+        chroms = records[0]; beg = np.asarray(records[1], np.int64); end = np.asarray(records[2], np.int64)
+    else:
+        chroms = []; b_ = []; e_ = []
+        mv = memoryview(data)
+        for a, b in zip(ds.tolist(), de.tolist()):
+            cols = bytes(mv[a:b]).decode().split("\t", 8)
+            x, y = record_span(cols)
+            chroms.append(cols[0]); b_.append(x); e_.append(y)
+        beg = np.asarray(b_, np.int64); end = np.asarray(e_, np.int64)
     ib = IndexBuilder()
-    mv = memoryview(data)
-    for k, (a, b) in enumerate(zip(ds.tolist(), de.tolist())):
-        cols = bytes(mv[a:b]).split(b"\t", 8)
-        beg = int(cols[1]) - 1
-        end = beg + len(cols[3])
-        if len(cols) > 7 and b"END=" in cols[7]:
-            beg, end = record_span([c.decode() for c in cols])
-        ib.add(cols[0].decode(), beg, end, v0[k], v1[k])
+    k = 0; n = len(chroms)
+    while k < n:                           # runs of one reference
+        c = chroms[k]; m = k + 1
+        while m < n and chroms[m] == c:
+            m += 1
+        ib.add_many(c, beg[k:m], end[k:m], v0[k:m], v1[k:m])
+        k = m
     idx = path_vcf_gz + (".csi" if csi else ".tbi")
     with bgzf.BGZFWriter(idx) as w:
         w.write(ib.csi_bytes() if csi else ib.tbi_bytes())

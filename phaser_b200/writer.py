@@ -354,6 +354,7 @@ class Outputs:
         corrections = unphased_phased = 0
         tags = ['PG', 'PB', 'PI', 'PW', 'PC', 'PM']
         fmt_cache = {}
+        rec_chrom, rec_beg, rec_end = [], [], []       # reference span of every data line written (for the index)
         for line in vcf_lines:
             cols = line.replace("\n", "").split("\t")
             cols = cols[0:9] + ([cols[sample_column]] if len(cols) > sample_column else [])
@@ -455,4 +456,14 @@ class Outputs:
                             sf[iPC] = '.'
                             cols[9] = ":".join(sf)
                     out.append("\t".join(cols[0:9] + [cols[9]]) + "\n")
+                    e = pos - 1 + len(cols[3])
+                    if "END=" in cols[7]:
+                        for kv in cols[7].split(";"):
+                            if kv.startswith("END="):
+                                try:
+                                    e = max(e, int(kv[4:]))
+                                except ValueError:
+                                    pass
+                    rec_chrom.append(chrom); rec_beg.append(pos - 1); rec_end.append(e)
+        self.vcf_records = (rec_chrom, rec_beg, rec_end)
         return "".join(out), unphased_phased, corrections
