@@ -212,11 +212,15 @@ def run(args, engine=None):
         except PhzError as e:
             fatal_error(str(e))
         _t = _trace(_t, "read_alignments_native")
-        try:        # packed transport form (page-locked): copied and expanded on the device inside run_path
-            if os.environ.get("PHZ_NO_PACK"):
-                raise PhzError("packing disabled")
-            batches.append(pack_reads(rb, len(vt.contigs), threads=max(1, args.threads), lib=engine.lib))
-        except PhzError:            # a record beyond 65535 CIGAR ops / bases: plain arrays
+        # One-shot run: the plain arrays go up as they are.  The packed transport form (engine.pack_reads) pays off
+        # when host buffers are copied more than once or prefetched (sample loops, bench.py); packing once for a
+        # single copy costs more host time than it saves on the bus.  PHZ_PACK=1 forces it.
+        if os.environ.get("PHZ_PACK"):
+            try:
+                batches.append(pack_reads(rb, len(vt.contigs), threads=max(1, args.threads), lib=engine.lib))
+            except PhzError:            # a record beyond 65535 CIGAR ops / bases: plain arrays
+                batches.append(engine.upload_reads(rb))
+        else:
             batches.append(engine.upload_reads(rb))
         del rb
         _t = _trace(_t, "pack / upload")

@@ -233,3 +233,11 @@ def test_vectorised_index_builder_equals_record_by_record():
                 A.add(chrom, int(beg[k]), int(end[k]), int(v0[k]), int(v1[k]))
             B.add_many(chrom, beg, end, v0, v1)
         assert A.tbi_bytes() == B.tbi_bytes() and A.csi_bytes() == B.csi_bytes()
+
+
+def test_cli_with_the_packed_transport_form(hostsim, tmp_path, monkeypatch):
+    """PHZ_PACK=1: the command line sends the BAMs through pack_reads / phz_map_reads_packed; same files."""
+    monkeypatch.setenv("PHZ_PACK", "1")
+    c, got = _run_cli(hostsim, "rna_two_bams", tmp_path)
+    bad = compare.diff_outputs(c["ref"], got)
+    assert not bad, "\n".join(bad)
