@@ -134,7 +134,8 @@ int phz_packed_view(phz_packed_host* p, phz_packed_reads* out);
 int64_t phz_packed_bytes(phz_packed_host* p);
 void phz_packed_free(phz_packed_host* p);
 /* phz_map_reads with the packed HOST form: copies it to the device on the context's stream, expands it there and
- * runs K1.  The end-to-end entry point bench.py times and the one the command line uses. */
+ * runs K1.  The end-to-end entry point bench.py times; the command line takes it with PHZ_PACK=1 (a one-shot run is
+ * faster with plain arrays: packing costs more host time than it saves on the bus). */
 int phz_map_reads_packed(phz_ctx* ctx, const phz_packed_reads* packed, int baseq, double isize_cutoff, int64_t* n_candidates);
 /* Optional: starts the copy of a sample's packed buffers on the context's copy stream and returns at once.  A later
  * phz_map_reads_packed with the same buffers waits for that copy instead of issuing its own, so a loop over samples
