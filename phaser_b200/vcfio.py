@@ -95,9 +95,9 @@ def parse_vcf(path, sample_column: int, pass_only=1, chrom_of_interest="", chr_p
     st = VcfStats()
     with gzip.open(path, "rt") as f:
         for line in f:
-            cols = line.rstrip("\n").split("\t")
             if line.startswith("#"):
                 continue
+            cols = line.rstrip("\n").split("\t", sample_column + 1)       # columns past the sample's are never looked at
             # cut -f 1-9,<col> ; grep -v '0|0\|1|1' acts on that cut line (anywhere in it)
             cut = cols[0:9] + ([cols[sample_column]] if sample_column < len(cols) else [])
             cut_line = "\t".join(cut)

@@ -356,7 +356,7 @@ class Outputs:
         fmt_cache = {}
         rec_chrom, rec_beg, rec_end = [], [], []       # reference span of every data line written (for the index)
         for line in vcf_lines:
-            cols = line.replace("\n", "").split("\t")
+            cols = line.replace("\n", "").split("\t", sample_column + 1)      # columns past the sample's are cut away anyway
             cols = cols[0:9] + ([cols[sample_column]] if len(cols) > sample_column else [])
             if line[0:1] != "#" and "##FORMAT" not in line:
                 line = "d"            # a data line: none of the header tests below can match the cut line either
