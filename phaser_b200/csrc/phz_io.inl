@@ -300,16 +300,20 @@ static HostReads* build(std::vector<Rec>& recs, int nc, int n_threads) {
         }
       }
       u64 b0 = H->seq_off[k];
-      for (u32 j = 0; j < r.l_seq; ++j) {
-        u8 code = r.text ? BASE_OF_TABLE.t[r.seq[j]] : ((j & 1) ? (r.seq[j >> 1] & 15) : (r.seq[j >> 1] >> 4));
-        u64 i = b0 + j;
-        u8 val = (i & 1) ? code : (u8)(code << 4);
-        // the first / last byte of a record can be shared with a neighbour handled by another thread
-        if (j == 0 || j + 1 == r.l_seq) __atomic_fetch_or(&H->seq[i >> 1], val, __ATOMIC_RELAXED);
-        else H->seq[i >> 1] |= val;
-        int q = r.text ? (int)r.qual[j] - 33 : (int)r.qual[j];
-        H->qual[i] = (u8)(q < 0 ? 0 : q);
-      }
+      const u32 L = r.l_seq;
+      auto code_at = [&](u32 j) -> u8 {
+        return r.text ? BASE_OF_TABLE.t[r.seq[j]] : ((j & 1) ? (u8)(r.seq[j >> 1] & 15) : (u8)(r.seq[j >> 1] >> 4));
+      };
+      // bases: the first / last byte of a record can be shared with a neighbour handled by another thread (atomic
+      // or of one nibble); every byte in between belongs to this record alone and is written whole
+      u32 j = 0;
+      if (L > 0 && (b0 & 1)) { __atomic_fetch_or(&H->seq[b0 >> 1], code_at(0), __ATOMIC_RELAXED); j = 1; }
+      u8* sq = H->seq.data() + ((b0 + j) >> 1);
+      for (; j + 1 < L; j += 2) *sq++ = (u8)((code_at(j) << 4) | code_at(j + 1));
+      if (j < L) __atomic_fetch_or(&H->seq[(b0 + j) >> 1], (u8)(code_at(j) << 4), __ATOMIC_RELAXED);
+      u8* qo = H->qual.data() + b0;
+      if (r.text) for (u32 t = 0; t < L; ++t) { int q = (int)r.qual[t] - 33; qo[t] = (u8)(q < 0 ? 0 : q); }
+      else std::memcpy(qo, r.qual, L);
     }
   });
   for (int c = 0; c < nc; ++c)
