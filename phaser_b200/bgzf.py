@@ -20,6 +20,19 @@ def compress_block(data: bytes, level=6) -> bytes:
     return head + body + struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data))
 
 
+def compress_all(data: bytes, level=6, threads=0):
+    """All BGZF blocks of `data` (fixed MAX_BLOCK-byte cuts, what BGZFWriter emits), compressed on a thread pool
+    (zlib releases the GIL).  Returns the list of compressed blocks in order; the EOF block is not included."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    cuts = [data[o:o + MAX_BLOCK] for o in range(0, len(data), MAX_BLOCK)]
+    n = threads or min(16, os.cpu_count() or 1)
+    if n <= 1 or len(cuts) < 4:
+        return [compress_block(c, level) for c in cuts]
+    with ThreadPoolExecutor(max_workers=n) as ex:
+        return list(ex.map(lambda c: compress_block(c, level), cuts))
+
+
 class BGZFWriter:
     def __init__(self, path, level=6):
         self.f = open(path, "wb")

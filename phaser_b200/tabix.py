@@ -181,9 +181,12 @@ def write_vcf_with_index(path_vcf_gz, text, csi=False, records=None):
     the data lines in file order when the caller already has them (the VCF writer does); otherwise the lines are split."""
     import numpy as np
     data = text.encode()
-    with bgzf.BGZFWriter(path_vcf_gz) as w:
-        w.write(data)
-        sizes = w.block_sizes        # a reference to the list: the last partial block is appended by close()
+    blocks = bgzf.compress_all(data)          # same bytes as BGZFWriter, blocks compressed in parallel
+    with open(path_vcf_gz, "wb") as f:
+        for b in blocks:
+            f.write(b)
+        f.write(bgzf.EOF_BLOCK)
+    sizes = [len(b) for b in blocks]
     cstart = np.concatenate([[0], np.cumsum(np.asarray(sizes, np.int64))])      # compressed offset of block b
     buf = np.frombuffer(data, np.uint8)
     nl = np.flatnonzero(buf == 10)

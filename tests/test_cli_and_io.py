@@ -241,3 +241,14 @@ def test_cli_with_the_packed_transport_form(hostsim, tmp_path, monkeypatch):
     c, got = _run_cli(hostsim, "rna_two_bams", tmp_path)
     bad = compare.diff_outputs(c["ref"], got)
     assert not bad, "\n".join(bad)
+
+
+def test_parallel_bgzf_blocks_equal_the_streaming_writer(tmp_path):
+    import random
+    rnd = random.Random(1)
+    data = "".join("line %d %s\n" % (i, "x" * rnd.randrange(0, 90)) for i in range(40000)).encode()
+    p = str(tmp_path / "a.gz")
+    with bgzf.BGZFWriter(p) as w:
+        w.write(data)
+    assert b"".join(bgzf.compress_all(data, threads=4)) + bgzf.EOF_BLOCK == open(p, "rb").read()
+    assert bgzf.read_all(p) == data
