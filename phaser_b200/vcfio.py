@@ -93,6 +93,7 @@ def parse_vcf(path, sample_column: int, pass_only=1, chrom_of_interest="", chr_p
     contig_ban = [id_separator, ":"]
     pool = OrderedDict()
     st = VcfStats()
+    checked_chroms = set(); fmt_gt_index = {}; geno_cache = {}; pass_cache = {}
     with gzip.open(path, "rt") as f:
         for line in f:
             if line.startswith("#"):
@@ -108,32 +109,49 @@ def parse_vcf(path, sample_column: int, pass_only=1, chrom_of_interest="", chr_p
             chrom = cut[0]
             if hbl is not None and hbl.overlaps(chrom, int(cut[1]), len(cut[3])) and (chrom_of_interest == "" or chrom_of_interest == chrom):
                 haplo_set.add(chrom + "_" + cut[1])
-            for item in contig_ban:
-                if item in chrom:
-                    raise PhaserFatal("Character '%s' must not be present in contig name. Please change id separtor "
-                                      "using --id_separator to a character not found in the contig names and try "
-                                      "again." % item)
+            if chrom not in checked_chroms:
+                for item in contig_ban:
+                    if item in chrom:
+                        raise PhaserFatal("Character '%s' must not be present in contig name. Please change id separtor "
+                                          "using --id_separator to a character not found in the contig names and try "
+                                          "again." % item)
+                checked_chroms.add(chrom)
             if chrom_of_interest == "" or chrom_of_interest == chrom:
                 if chrom not in pool:
                     pool[chrom] = []
-                fields = cut[8].split(":")
-                if "GT" in fields:
-                    geno_string = cut[9].split(":")[fields.index("GT")]
-                    xgeno = list(geno_string)
-                    unphased = False
-                    if "." not in xgeno:
-                        if "|" in xgeno:
-                            xgeno.remove("|")
-                        if "/" in xgeno:
-                            xgeno.remove("/")
-                            unphased = True
-                        if len(set(xgeno)) > 1:
-                            if pass_only == 0 or "PASS" in cut[6].split(";"):
-                                pool[chrom].append((cut, geno_string, xgeno))
-                                if unphased:
-                                    st.unphased_count += 1
-                            else:
-                                st.filter_count += 1
+                # FORMAT, genotype and FILTER strings repeat line after line: each distinct one is analysed once
+                gi = fmt_gt_index.get(cut[8])
+                if gi is None:
+                    fields = cut[8].split(":")
+                    gi = fields.index("GT") if "GT" in fields else -1
+                    fmt_gt_index[cut[8]] = gi
+                if gi >= 0:
+                    geno_string = cut[9].split(":")[gi]
+                    ginfo = geno_cache.get(geno_string)
+                    if ginfo is None:
+                        xgeno = list(geno_string)
+                        unphased = False; usable = False
+                        if "." not in xgeno:
+                            if "|" in xgeno:
+                                xgeno.remove("|")
+                            if "/" in xgeno:
+                                xgeno.remove("/")
+                                unphased = True
+                            usable = len(set(xgeno)) > 1
+                        ginfo = (xgeno, unphased, usable)
+                        geno_cache[geno_string] = ginfo
+                    xgeno, unphased, usable = ginfo
+                    if usable:
+                        ok = pass_cache.get(cut[6])
+                        if ok is None:
+                            ok = "PASS" in cut[6].split(";")
+                            pass_cache[cut[6]] = ok
+                        if pass_only == 0 or ok:
+                            pool[chrom].append((cut, geno_string, list(xgeno)))
+                            if unphased:
+                                st.unphased_count += 1
+                        else:
+                            st.filter_count += 1
     contigs: List[str] = []
     off = [0]
     pos, a0, a1, rl = [], [], [], []
