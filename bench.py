@@ -8,8 +8,12 @@ one synthetic sample of the BASELINE.json configs[1] shape: whole-genome RNA-seq
 already resident in HBM; `e2e` times the same step through the host-buffer C-ABI entry
 (phz_map_reads_packed: page-locked host buffers in the ingest's packed transport form -> device + expansion inside
 the timed region, result arrays back; `e2e_plain_soa` is the same with plain SoA arrays through phz_map_reads_host).
-N > 1: one process per GPU, every rank phases its own sample (weak scaling, GTEx-batch style,
-configs[4]); no data-path collective, max-over-ranks timing.
+N > 1: one process per GPU and ONE sample sharded by contig over the N GPUs (configs[2] style, strong scaling,
+SURVEY 8e): LPT plan over the contigs, per-BAM all-reduce of the alignment-score histogram, all-reduce of the two
+noise counters, gather of the result arrays into rank 0 (NCCL send/recv), merge there; `value` = het SNVs of the
+sample / max-over-ranks step time.  The run checks merged == single-GPU arrays at full size and reports the time of
+each collective.  `replicas` (second key) is the round-1 mode: every rank phases its own full sample, no data-path
+collective (weak scaling, GTEx-batch style, configs[4]).
 `--impl reference` times the reference's CPU implementation of the same path (oracle/_ref when it
 was built from /root/reference, else the oracle port) on a bounded sample, rank 0 only.
 """
@@ -40,6 +44,9 @@ def parse_args():
     ap.add_argument("--exonic_frac", type=float, default=0.10)
     ap.add_argument("--seed", type=int, default=2000)
     ap.add_argument("--cpu_pairs", type=int, default=2_000_000, help="read pairs of the bounded CPU-baseline sample")
+    ap.add_argument("--mode", default="auto", choices=["auto", "shard", "replicas"],
+                    help="N > 1: 'shard' = one sample sharded by contig (default), 'replicas' = one sample per GPU")
+    ap.add_argument("--no_replicas", action="store_true", help="N > 1, shard mode: skip the replica-mode second key")
     ap.add_argument("--no_e2e", action="store_true")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--k1_mode", type=int, default=3, help="3 tile kernel + permute (default), 2 fused look-back, 1 windowed two-pass, 0 generic two-pass")
@@ -170,20 +177,30 @@ def full_size_checks(E, pipeline, vt, reads, packed, P, n_pairs):
     return out
 
 
+def _peak():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s (of fallback)"
+
+
 def run_ours(a):
     import torch.distributed as dist
-    from phaser_b200 import engine as eng, pipeline
+    from phaser_b200 import engine as eng, pipeline, shard
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    sharded = world > 1 and a.mode != "replicas"
     E = eng.Engine(device=dev)
     E.set_option("k1_mode", a.k1_mode)
     E.set_option("k1_min_ctas", a.k1_min_ctas)
     t_gen = time.time()
-    g, vt, packed, n_pairs = make_sample(a.seed + rank, a.pairs, a.variants, a.exonic_frac, dev)
+    # shard mode: every rank generates the SAME sample (same seed, same generator, same GPU type) and keeps its contigs
+    g, vt, packed, n_pairs = make_sample(a.seed + (0 if sharded else rank), a.pairs, a.variants, a.exonic_frac, dev)
     torch.cuda.synchronize()
     t_gen = time.time() - t_gen
     V = vt.n_variants
@@ -197,117 +214,178 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(host_inputs=False, src=None):
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world == 1:
+            return [float(x)]
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
+    def replica_step(host_inputs=False, src=None):
         return pipeline.run_path(E, vt, [src if src is not None else reads], P, n_fragments=n_pairs,
                                  host_inputs=host_inputs, download=host_inputs, reuse_result_buffer=True)
+
+    run = None; my_reads = reads; timers = {}
+    if sharded:
+        run = shard.ShardedRun(E, vt, shard.contig_weights(vt, [reads]), P, n_pairs, 1, device=dev)
+        my_reads = shard.sub_reads_tensors(reads, run.mine)
+        torch.cuda.synchronize()
+
+    def step(host_inputs=False, src=None):
+        """one pass of the hot path over one sample: resident inputs -> results on the device (sharded: in rank 0's
+        memory); with host inputs -> result arrays on the host (sharded: merged on rank 0)"""
+        if not sharded:
+            return replica_step(host_inputs, src)
+        return run.step([src if src is not None else my_reads], host_inputs=host_inputs, merge=host_inputs)
+
+    def timed_resident(fn, steps, warmup, profile_range=False):
+        for _ in range(warmup):
+            fn()
+        k1 = []
+        barrier()
+        t0 = time.time()
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        if profile_range:
+            torch.cuda.cudart().cudaProfilerStart()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+            k1.append(E.map_times())
+        ev1.record()
+        if profile_range:
+            torch.cuda.synchronize(); torch.cuda.cudart().cudaProfilerStop()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        return max_over_ranks(ms) / steps, ms / steps, np.asarray(k1), (t0, time.time())
 
     E.set_profiling(1)
     clocks = ClockSampler(local); clocks.start()          # streaming before the timed region starts
     for _ in range(a.warmup):
-        res = step()
+        step()
     own0, lib0 = E.launch_counts()
-    k1_ms = []
     clocks.ensure_running()
-    barrier()
-    t_region0 = time.time()
-    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
-    if a.profiler_range:
-        torch.cuda.cudart().cudaProfilerStart()
-    ev0.record()
-    for _ in range(a.steps):
-        res = step()
-        k1_ms.append(E.map_times())
-    ev1.record()
-    if a.profiler_range:
-        torch.cuda.synchronize(); torch.cuda.cudart().cudaProfilerStop()
-    barrier()
-    clock_rows = clocks.stop_rows(t_region0, time.time())          # samples taken during the timed steps
-    ms_total = ev0.elapsed_time(ev1)
+    ms_step, ms_mine, k1, region = timed_resident(step, a.steps, 0, a.profiler_range)
+    clock_rows = clocks.stop_rows(*region)          # samples taken during the timed steps
     own1, lib1 = E.launch_counts()
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / a.steps
-    counters = res.counters
-    n_tuples = counters["n_tuples"]
-    k1 = np.asarray(k1_ms)           # [steps, 3] count / scan+readback / emit
+    rank_ms = all_ranks(ms_mine)
     k1_total_ms = float(k1.sum(1).mean())
-    bytes_k1 = algorithmic_bytes_k1(packed, V, sum(res.candidates_per_bam))
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = bytes_k1 / (k1_total_ms * 1e-3) / 1e9
+    my_R = int(my_reads["pos"].shape[0])
+    peak, peak_source = _peak()
+
+    # ---- counters of the whole sample (sharded: summed over ranks) and this rank's K1 roofline
+    def sum_ranks(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world > 1 and sharded:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
+    res_local = pipeline.run_path(E, run.svt if sharded else vt, [my_reads], P, n_fragments=n_pairs,
+                                  comm=run.comm if sharded else None, download=False) if (not sharded or run.mine) else \
+        shard._idle_rank(P, 1, run.comm)
+    lc = res_local.counters if res_local.counters else {k: 0 for k in eng.COUNTER_NAMES}
+    counters = {k: sum_ranks(lc[k]) for k in ("n_tuples", "edges", "final_blocks", "members")}
+    n_tuples = counters["n_tuples"]
+    cand_mine = sum(res_local.candidates_per_bam)
+    bytes_k1 = algorithmic_bytes_k1(my_reads, int(run.svt.n_variants) if sharded else V, cand_mine)
+    achieved = bytes_k1 / (k1_total_ms * 1e-3) / 1e9 if k1_total_ms > 0 else 0.0
     # DRAM traffic of the dominant kernel from the committed ncu capture of this same workload (profiles/)
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
-        if int(tr.get("records", -1)) == R:
+        if int(tr.get("records", -1)) == my_R:
             traffic = tr["dram_bytes_per_launch"]
     except Exception:
         pass
     k1_names = {3: ["tile pre-pass", "tile kernel (slab + count + scan + dense emit)", "tile-table scan (the commit compacts the tiles in place: no permute of the candidates)"],
                 2: ["tile pre-pass", "-", "fused look-back kernel"], 1: ["count pass", "scan + readback", "emit pass"],
                 0: ["count pass", "scan + readback", "emit pass"]}[a.k1_mode]
-    # ---- end to end: pinned host arrays -> device inside the timed region -> result arrays on the host
-    e2e = None
-    e2e_plain = None
-    checks = None
-    if not a.no_e2e:
-        def timed_e2e(src, n_steps, prefetch=False):
-            """prefetch: samples are looped GTEx-batch style -- every step first starts the copy of the NEXT sample's
-            buffers on the copy stream (phz_prefetch_packed), then runs the path on the sample whose copy was started one
-            step earlier; each timed step still contains one full host->device copy and one result read-back."""
-            if prefetch:
-                E.prefetch_packed(src)            # the first sample's copy, before the warm-up
-            for _ in range(max(3, a.warmup)):
-                if prefetch:
-                    E.prefetch_packed(src)
-                r2 = step(True, src)
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(n_steps):
-                if prefetch:
-                    E.prefetch_packed(src)
-                r2 = step(True, src)
-            barrier()
-            dt = (time.perf_counter() - t0) / n_steps
-            if prefetch:
-                r2 = step(True, src)              # drain the last staged copy (untimed)
-            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            return float(tt.item()), sum(int(v.nbytes) for v in r2.arrays.values())
 
+    # ---- end to end: pinned host buffers -> device inside the timed region -> result arrays on the host
+    def timed_e2e(fn, src, n_steps, prefetch=False):
+        """prefetch: samples are looped GTEx-batch style -- every step first starts the copy of the NEXT sample's
+        buffers on the copy stream (phz_prefetch_packed), then runs the path on the sample whose copy was started one
+        step earlier; each timed step still contains one full host->device copy and one result read-back."""
+        has = src is not None          # a rank without contigs copies nothing
+        if prefetch and has:
+            E.prefetch_packed(src)            # the first sample's copy, before the warm-up
+        for _ in range(max(3, a.warmup)):
+            if prefetch and has:
+                E.prefetch_packed(src)
+            r2 = fn(True, src)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_steps):
+            if prefetch and has:
+                E.prefetch_packed(src)
+            r2 = fn(True, src)
+        barrier()
+        dt = (time.perf_counter() - t0) / n_steps
+        if prefetch:
+            r2 = fn(True, src)              # drain the last staged copy (untimed)
+        out_bytes = sum(int(v.nbytes) for v in r2.arrays.values()) if r2 is not None else 0
+        return max_over_ranks(dt), out_bytes
+
+    def pack_host(tensors, n_contigs):
+        host_np = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in tensors.items()}
+        return eng.pack_reads(host_np, n_contigs, lib=E.lib, page_locked=True), host_np
+
+    e2e = None; e2e_plain = None; checks = None; sharding = None; replicas = None
+    if not a.no_e2e:
         # the ingest's host form: packed transport buffers in page-locked memory (include/phz.h: phz_packed_reads),
         # built ONCE here like a BAM is parsed once; phz_map_reads_packed copies + expands them inside the timed region
-        packed = None
+        pk = None; host_np = {}
         for turn in range(world):         # N ranks share one host: one rank at a time holds the unpacked host copy
-            if turn == rank:
-                host_np = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in reads.items()}
-                packed = eng.pack_reads(host_np, len(g.contigs), lib=E.lib, page_locked=True)
+            if turn == rank and (not sharded or run.mine):
+                pk, host_np = pack_host(my_reads, len(run.mine) if sharded else len(g.contigs))
                 if world > 1:
                     host_np = {}
             barrier()
-        dt1, d2h = timed_e2e(packed, a.steps)                      # one sample at a time: copy, then path
-        dt, d2h = timed_e2e(packed, a.steps, prefetch=True)        # samples looped, next copy under the current path
-        e2e = {"value": V * world / dt, "unit": "het-SNVs/s", "h2d_bytes_per_step": int(packed.nbytes),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3,
+        dt1, d2h = timed_e2e(step, pk, a.steps)                      # one sample at a time: copy, then path
+        dt, d2h = timed_e2e(step, pk, a.steps, prefetch=True)        # samples looped, next copy under the current path
+        h2d = sum_ranks(pk.nbytes if pk is not None else 0) if sharded else (int(pk.nbytes) * 1)
+        d2h = int(max_over_ranks(d2h))
+        units = V if sharded else V * world
+        e2e = {"value": units / dt, "unit": "het-SNVs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": dt * 1e3,
                "mode": "samples looped; the copy of sample i+1 (phz_prefetch_packed, copy stream) runs under the path of sample i; "
-                       "every step holds one full copy in and one result read-back",
-               "single_sample_ms": dt1 * 1e3, "single_sample_value": V * world / dt1,
+                       "every step holds one full copy in and one result read-back"
+                       + ("; sharded: every rank copies its contigs' packed records, rank 0 receives the result arrays over "
+                          "NCCL, reads them back and merges them" if sharded else ""),
+               "single_sample_ms": dt1 * 1e3, "single_sample_value": units / dt1,
                "host_form": "packed transport (lossless, include/phz.h phz_packed_reads), expanded on the device",
-               "host_form_coding": packed.coding, "bytes_per_record": packed.nbytes / float(R)}
-        checks = full_size_checks(E, pipeline, vt, reads, packed, P, n_pairs) if rank == 0 else None
-        if a.profile:
+               "host_form_coding": pk.coding if pk is not None else None,
+               "bytes_per_record": (pk.nbytes / float(my_R)) if pk is not None and my_R else None}
+        if sharded:
+            # ---- one extra step with every collective bracketed by device synchronisation
+            run.timers = timers; run.comm.timers = timers
+            merged = run.step([pk] if pk is not None else [], host_inputs=True, merge=True)
+            run.timers = None; run.comm.timers = None
+            if rank == 0:
+                merged = shard.PhaseResult(merged.n_bams, merged.as_cutoff, merged.tuples_per_bam, merged.candidates_per_bam,
+                                           merged.noise_e, merged.match, merged.mismatch, merged.counters, 0,
+                                           {k: np.array(v) for k, v in merged.arrays.items()})
+        if rank == 0:
+            if sharded:      # the same sample on ONE GPU (rank 0 holds all of it): the merged arrays must be identical
+                single = pipeline.run_path(E, vt, [reads], P, n_fragments=n_pairs)
+                diff = shard.results_equal(single, merged)
+                checks = {"merged_equals_single_gpu": not diff, "differences": diff,
+                          "compared": "every result array of the merged 8-shard run vs the same sample on one GPU (edge "
+                                      "table as a set of rows, vfirst through the order it defines)".replace("8-shard", "%d-shard" % world)}
+            else:
+                checks = full_size_checks(E, pipeline, vt, reads, pk, P, n_pairs)
+        if a.profile and not sharded:
             E.set_profiling(2)
-            t0 = time.perf_counter(); step(True, packed); torch.cuda.synchronize(); wall = (time.perf_counter() - t0) * 1e3
+            t0 = time.perf_counter(); step(True, pk); torch.cuda.synchronize(); wall = (time.perf_counter() - t0) * 1e3
             e2e["stages_ms"] = {k: round(v, 3) for k, v in E.stage_report().items()}
             e2e["stages_ms"]["wall_ms"] = round(wall, 3)
             E.set_profiling(1)
-        del packed
+        del pk
         # for comparison (single GPU only): the same call with the plain SoA arrays (phz_map_reads_host), 2 timed steps
         if world == 1:
             def to_host(v):
@@ -322,11 +400,40 @@ def run_ours(a):
                 host[k] = to_host(v) if k != "contig_rec_off" else v
                 del v
             h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
-            dt, d2h = timed_e2e(host, min(2, a.steps))
-            e2e_plain = {"value": V * world / dt, "unit": "het-SNVs/s", "h2d_bytes_per_step": int(h2d),
-                         "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "host_form": "plain SoA arrays (phz_map_reads_host)"}
+            dtp, d2hp = timed_e2e(step, host, min(2, a.steps))
+            e2e_plain = {"value": V * world / dtp, "unit": "het-SNVs/s", "h2d_bytes_per_step": int(h2d),
+                         "d2h_bytes_per_step": int(d2hp), "ms_per_step": dtp * 1e3, "host_form": "plain SoA arrays (phz_map_reads_host)"}
             del host
         del host_np
+    if sharded:
+        loads = run.loads()
+        coll = {k: round(v, 4) if isinstance(v, float) else v for k, v in timers.items()}
+        names = ("allreduce_as_histogram_ms", "allreduce_noise_ms", "gather_results_ms")
+        dom = max(names, key=lambda k: timers.get(k, 0.0)) if timers else None
+        sharding = {"plan_contigs_per_rank": [[vt.contigs[c] for c in p] for p in run.plan],
+                    "records_per_rank": [int(x) - len(p) for x, p in zip(loads, run.plan)],
+                    "max_load_frac": max(loads) / float(sum(loads)), "ideal_frac": 1.0 / world,
+                    "resident_ms_per_rank": [round(x, 4) for x in rank_ms],
+                    "collectives_ms_rank0_one_step_synchronised": coll, "dominant_collective": dom,
+                    "collectives": "per BAM all_reduce(sum) of int64[65536] (AS histogram, phaser.py:545-553), all_reduce(sum) "
+                                   "of int64[2] (noise counters, phaser.py:610-631), all_gather of the array sizes + grouped "
+                                   "send/recv of one packed buffer per rank into rank 0 (result gather, phaser.py:863-867)"}
+        # ---- second key: the round-1 mode, one full sample per GPU, no data-path collective
+        if not a.no_replicas:
+            rms, _, _, _ = timed_resident(replica_step, a.steps, a.warmup)
+            replicas = {"value": V * world / (rms * 1e-3), "unit": "het-SNVs/s", "ms_per_step": rms, "scaling": "weak",
+                        "mode": "every rank phases its own full sample (configs[4] batch style), no data-path collective"}
+            if not a.no_e2e:
+                pk = None
+                for turn in range(world):
+                    if turn == rank:
+                        pk, _h = pack_host(reads, len(g.contigs)); del _h
+                    barrier()
+                rdt, rd2h = timed_e2e(replica_step, pk, min(a.steps, 5), prefetch=True)
+                replicas["e2e"] = {"value": V * world / rdt, "unit": "het-SNVs/s", "ms_per_step": rdt * 1e3,
+                                   "h2d_bytes_per_step": int(pk.nbytes) * world, "d2h_bytes_per_step": int(rd2h) * world,
+                                   "aggregate_h2d_gbs": pk.nbytes * world / rdt / 1e9}
+                del pk
     clk = ClockSampler.summary(clock_rows)
     # per-stage CUDA-event times of one extra (untimed) resident step: what the K2 / K3 figures below come from
     E.set_profiling(2)
@@ -334,38 +441,43 @@ def run_ours(a):
     stages = {k: round(v, 3) for k, v in E.stage_report().items()}
     stages["wall_ms"] = round(wall, 3)
     E.set_profiling(1)
-    T = counters["n_tuples"]; Ed = counters["edges"]; Bf = counters["final_blocks"]
+    T = lc["n_tuples"]; Ed = lc["edges"]; Bf = lc["final_blocks"]; Vl = int(run.svt.n_variants) if sharded else V
     k2_ms = sum(v for k, v in stages.items() if k.startswith("graph."))
     k3_ms = sum(v for k, v in stages.items() if k.startswith("phase."))
     other = {   # B_K2 = 12 T + 44 E, B_K3 = 12 T + 44 E + 8 V + 32 B (sort / atomic traffic counts against the stage)
         "K2 graph (all launches of the stage)": {"ms": round(k2_ms, 3), "algorithmic_bytes": 12 * T + 44 * Ed,
                                                  "achieved_gbs": (12 * T + 44 * Ed) / (k2_ms * 1e-3) / 1e9 if k2_ms else None},
         "K3 blocks + phasing + counts (integer/latency bound, not an HBM figure)": {
-            "ms": round(k3_ms, 3), "algorithmic_bytes": 12 * T + 44 * Ed + 8 * V + 32 * Bf,
-            "achieved_gbs": (12 * T + 44 * Ed + 8 * V + 32 * Bf) / (k3_ms * 1e-3) / 1e9 if k3_ms else None}}
+            "ms": round(k3_ms, 3), "algorithmic_bytes": 12 * T + 44 * Ed + 8 * Vl + 32 * Bf,
+            "achieved_gbs": (12 * T + 44 * Ed + 8 * Vl + 32 * Bf) / (k3_ms * 1e-3) / 1e9 if k3_ms else None}}
     cpu = None
     cli = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu = cpu_baseline(a)
         cli = cli_files_to_files(a, E)
     if rank == 0:
+        units = V if sharded else V * world
         out = {
-            "metric": "het_snvs_phased_per_sec", "value": V * world / (ms_step * 1e-3), "unit": "het-SNVs/s",
+            "metric": "het_snvs_phased_per_sec", "value": units / (ms_step * 1e-3), "unit": "het-SNVs/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (integer and byte work; fp64 only for 3 host scalars)",
+            "scaling": "strong" if (sharded or world == 1) else "weak", "vs_baseline": None,
+            "dtype": "u8/int32 (integer and byte work; fp64 only for 3 host scalars)",
             "data": "synthetic",
             "config": {"workload": "configs[1]: whole-genome 1 RNA-seq BAM, %d read pairs (%d records after filters, 2x76 bp "
-                                   "spliced), %d het SNVs, 1 sample per GPU" % (n_pairs, R, V),
-                       "l2": "inputs (%.1f GB per step) are larger than L2" % (bytes_k1 / 1e9),
+                                   "spliced), %d het SNVs; %s" % (n_pairs, R, V,
+                                   ("ONE sample sharded by contig over %d GPUs (LPT over record counts), results gathered "
+                                    "into rank 0" % world) if sharded else "1 sample per GPU"),
+                       "l2": "inputs (%.1f GB per step%s) are larger than L2" % (bytes_k1 / 1e9, " on rank 0" if sharded else ""),
                        "records": R, "het_snvs": V, "tuples": n_tuples, "edges": counters["edges"],
-                       "blocks": counters["final_blocks"], "phased_in_blocks": int((res.counters["members"])),
+                       "blocks": counters["final_blocks"], "phased_in_blocks": counters["members"],
                        "generator_s": round(t_gen, 1)},
-            "reads_x_variants_per_sec": n_tuples * world / (ms_step * 1e-3),
-            "records_per_sec": R * world / (ms_step * 1e-3),
-            "roofline": {"bound": "hbm", "kernel": "K1 read->allele (all launches of the stage: %s)" % " + ".join(k1_names),
+            "reads_x_variants_per_sec": n_tuples * (1 if sharded else world) / (ms_step * 1e-3),
+            "records_per_sec": R * (1 if sharded else world) / (ms_step * 1e-3),
+            "roofline": {"bound": "hbm", "kernel": "K1 read->allele (all launches of the stage%s: %s)" % (
+                             " on rank 0's contigs" if sharded else "", " + ".join(k1_names)),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                         "algorithmic_bytes": bytes_k1, "ms": k1_total_ms,
+                         "peak_source": peak_source,
+                         "algorithmic_bytes": bytes_k1, "ms": k1_total_ms, "records_this_launch": my_R,
                          "ms_parts": dict(zip(k1_names, [float(x) for x in k1.mean(0)])), "traffic": traffic,
                          # what the tile kernel really moves (ncu DRAM bytes / its own launch time): it fetches only the
                          # SEQ/QUAL sectors under het sites, so the algorithmic figure above overstates its DRAM load
@@ -376,6 +488,10 @@ def run_ours(a):
             "gpu_launches": int((own1 - own0) / a.steps), "library_passes": int((lib1 - lib0) / a.steps),
             "clocks": clk,
         }
+        if sharding is not None:
+            out["sharding"] = sharding
+        if replicas is not None:
+            out["replicas"] = replicas
         out["stages_ms"] = stages
         out["roofline_other_stages"] = other
         out["full_size_checks"] = checks
@@ -431,6 +547,12 @@ def cpu_baseline(a):
             dt = time.perf_counter() - t0
             if r["returncode"] != 0:
                 raise RuntimeError("compiled reference failed: " + r["log"][-800:])
+            if "ref_out" not in _CPU_FILES:          # kept for the files-to-files parity check of the command line
+                keep_out = os.path.join(os.path.dirname(vcf), "ref_out"); os.makedirs(keep_out, exist_ok=True)
+                for suf in rr.OUTPUT_SUFFIXES:
+                    if suf in r:
+                        shutil.copy(r[suf], os.path.join(keep_out, "ref." + suf))
+                _CPU_FILES["ref_out"] = keep_out
             tuples = None
             for ln in r["log"].splitlines():
                 if "retrieved" in ln and "reads" in ln:
@@ -476,6 +598,7 @@ def cli_files_to_files(a, engine):
             best = dt if best is None else min(best, dt)
         out = {"value": n_var / best, "unit": "het-SNVs/s", "seconds": best, "records_per_sec": n_rec / best,
                "sample": "same %d-pair files as cpu_baseline; process start-up and torch import not included" % n_pairs}
+        out.update(cli_parity(os.path.join(tmp, "out"), _CPU_FILES.get("ref_out")))
         try:
             out["gene_ae"] = gene_ae_leg(engine, os.path.join(tmp, "out.haplotypic_counts.txt"),
                                          os.path.join(os.path.dirname(vcf), "genes.bed"))
@@ -484,6 +607,27 @@ def cli_files_to_files(a, engine):
         return out
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+def cli_parity(prefix, ref_dir):
+    """The six files the command line just wrote vs the six files the unmodified reference wrote from the SAME input
+    files in this run (oracle.compare.diff_outputs = the parity definition of SURVEY 8c)."""
+    if not ref_dir:
+        return {"cli_parity": None, "cli_parity_note": "no reference outputs in this run (oracle/_ref absent)"}
+    from oracle import compare
+    from oracle.harness import run_reference as rr
+    names = {"allelic_counts": "allelic_counts.txt", "allele_config": "allele_config.txt", "haplotypes": "haplotypes.txt",
+             "haplotypic_counts": "haplotypic_counts.txt", "variant_connections": "variant_connections.txt", "vcf": "vcf.gz"}
+    ref = {}; got = {}
+    for k, suf in names.items():
+        rp = os.path.join(ref_dir, "ref." + suf); gp = prefix + "." + suf
+        if os.path.exists(rp):
+            ref[k] = rr.read_text(rp)
+        if os.path.exists(gp):
+            got[k] = rr.read_text(gp)
+    bad = compare.diff_outputs(ref, got)
+    rows = {k: (ref[k].count("\n") if k in ref else None, got[k].count("\n") if k in got else None) for k in names}
+    return {"cli_parity": not bad, "cli_parity_rows_ref_vs_cli": rows, "cli_parity_differences": [b[:300] for b in bad[:5]]}
 
 
 def gene_ae_leg(engine, hc_path, bed_path):

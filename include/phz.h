@@ -186,6 +186,10 @@ int phz_download(phz_ctx* ctx, const char* name, void* h_dst, int64_t dst_bytes)
  * the copy is synchronous anyway); phz_sync() makes the bytes visible.  Lets the caller fetch all result arrays
  * of a run with one wait. */
 int phz_download_async(phz_ctx* ctx, const char* name, void* h_dst, int64_t dst_bytes);
+/* Same, but `dst` may be a DEVICE pointer as well (the copy direction follows the pointer): packs result arrays into
+ * one device buffer that a collective then moves to the rank that writes the files (the contig-sharded run's gather of
+ * formatted rows / per-variant annotations; phaser.py:863-867 needs them in one place). */
+int phz_copy_array(phz_ctx* ctx, const char* name, void* dst, int64_t dst_bytes);
 /* counters[16]: n_tuples, entries, groups, pairs, distinct pairs, edges, dropped, members, blocks,
  * hard blocks, final blocks, read-list entries, n_candidates, n_bams, fragment runs re-sorted in place by the
  * graph stage, 1 if that stage fell back to the full-key sort */

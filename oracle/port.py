@@ -178,6 +178,12 @@ class PortResult:
     pass
 
 
+# Quirk mutants (tests/test_quirk_coverage.py): naming a quirk here makes the port follow the behaviour the reference's
+# author presumably INTENDED instead of what the reference does.  A fixture produced by the unmodified reference pins a
+# quirk exactly when the mutant no longer reproduces it; the set is empty in every other use of this module.
+MUTANTS = set()
+
+
 def run(vt, batches, params, binom_cdf=None):
     """Whole path.  `batches`: one ReadBatch per BAM (fragment ids share one namespace)."""
     if binom_cdf is None:
@@ -239,6 +245,9 @@ def run(vt, batches, params, binom_cdf=None):
             if c not in read_vars:
                 read_vars[c] = OrderedDict()
             for f, lst in rv.items():
+                if "Q9" in MUTANTS and f in read_vars[c]:
+                    read_vars[c][f] = read_vars[c][f] + lst      # what phaser.py:578-581 was meant to do
+                    continue
                 read_vars[c][f] = lst          # always overwritten: stale-variable test, phaser.py:578 (Q9)
     res.var = var
 
@@ -312,6 +321,12 @@ def run(vt, batches, params, binom_cdf=None):
             for k in ((a, 0), (a, 1), (b, 0), (b, 1)):
                 if k not in links:
                     links[k] = set()
+            if chosen == -1 and "Q16" in MUTANTS:        # a tie edge that does not glue components
+                overlap[c][a].remove(b); overlap[c][b].remove(a)
+                if len(overlap[c][a]) == 0:
+                    del overlap[c][a]
+                if len(overlap[c][b]) == 0:
+                    del overlap[c][b]
             if chosen == 0:
                 links[(a, 0)].add((b, 0)); links[(b, 0)].add((a, 0)); links[(a, 1)].add((b, 1)); links[(b, 1)].add((a, 1))
             elif chosen == 1:
@@ -499,7 +514,10 @@ def phase_v3(variants, vconn, links, max_block_size):
             if "-" in new_phase[0]:
                 STATS["merge_fail"] += 1
                 split_phases.append(final_phase)
-                split_start = used                      # Q14: not an offset sum
+                if "Q14" in MUTANTS:
+                    split_start = split_start + len(final_phase[0])      # the offset of the sub-block that starts now
+                else:
+                    split_start = used                      # Q14: not an offset sum
                 final_phase = phases[i]
             else:
                 final_phase = new_phase
@@ -597,7 +615,9 @@ def _outputs(res, vt, var, sets, links, final, contig_of, vinfo, P, nb):
                 u |= sets[v][vis[i]["alleles"].index(al)]
             hap_counts[h] = len(u)
         use_phases = [x for x in phases[0] if str(x) != "nan"]
-        phase_concordant = 1 if len(set(use_phases)) <= 1 else 0
+        phase_concordant = 1 if len(set(use_phases)) <= 1 else 0            # Q22: also 1 when no phase is known
+        if "Q22" in MUTANTS:
+            phase_concordant = 1 if len(set(use_phases)) == 1 else 0
         ps = ["".join(str(x).replace("nan", "-") for x in phases[h]) for h in (0, 1)]
         nan_strip = [int(x) for x in phases[0] if x >= 0]
         corrected = [phases[0], phases[1]]
@@ -607,6 +627,8 @@ def _outputs(res, vt, var, sets, links, final, contig_of, vinfo, P, nb):
             # set() of the phase list: every float('nan') object is distinct (Q23)
             n_nan = sum(1 for x in phases[0] if x != x)
             distinct = len(set(x for x in phases[0] if x == x)) + n_nan
+            if "Q23" in MUTANTS:
+                distinct = len(set(x for x in phases[0] if x == x))          # nan-aware "all known phases agree"
             if distinct == 1:
                 stat = 1
             elif P.gw_phase_method == 0:
@@ -636,6 +658,8 @@ def _outputs(res, vt, var, sets, links, final, contig_of, vinfo, P, nb):
                     elif stat > 0.5:
                         corrected = [[1] * len(variants), [0] * len(variants)]
                     stat = max([stat, 1 - stat])
+        if "Q28" in MUTANTS:
+            stat = float(stat)                # one print format for the statistic
         gw_stat_of[block_index] = stat
         max_maf = max(mafs)
         for i, v in enumerate(variants):

@@ -398,6 +398,15 @@ int phz_download_async(phz_ctx* ctx, const char* name, void* h_dst, int64_t dst_
   PHZ_CATCH
 }
 
+int phz_copy_array(phz_ctx* ctx, const char* name, void* dst, int64_t dst_bytes) {
+  PHZ_TRY
+  ArrRef r;
+  if (!find_array(ctx, name, &r)) throw PhzError(std::string("unknown array: ") + name);
+  if (r.n * r.eb > dst_bytes) throw PhzError(std::string("destination too small for array ") + name);
+  if (r.n > 0) ctx->p.be.copy_out_async(dst, r.p, (size_t)(r.n * r.eb));
+  PHZ_CATCH
+}
+
 int phz_counters(phz_ctx* ctx, int64_t* c) {
   PHZ_TRY
   auto& p = ctx->p;

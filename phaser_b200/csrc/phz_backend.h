@@ -224,6 +224,10 @@ struct DeviceBackend {
   void d2d(void* dst, const void* src, size_t bytes) {
     if (bytes) PHZ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream));
   }
+  // device -> wherever dst lives (host or device; unified addressing decides), no wait
+  void copy_out_async(void* dst, const void* src, size_t bytes) {
+    if (bytes) PHZ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream));
+  }
   // ---- second stream for host->device copies that overlap kernels of the main stream (phz_map_reads_packed):
   // copy_begin() orders the copy stream after everything already queued on the main stream (the staging buffers
   // may still be read by it), h2d_copy() enqueues on the copy stream, copy_fence() makes the main stream wait for
@@ -391,6 +395,7 @@ struct HostSimBackend {
   void d2h(void* dst, const void* src, size_t bytes) { if (bytes) std::memcpy(dst, src, bytes); }
   void d2h_async(void* dst, const void* src, size_t bytes) { if (bytes) std::memcpy(dst, src, bytes); }
   void d2d(void* dst, const void* src, size_t bytes) { if (bytes) std::memmove(dst, src, bytes); }
+  void copy_out_async(void* dst, const void* src, size_t bytes) { if (bytes) std::memmove(dst, src, bytes); }
   void copy_begin() {}
   void h2d_copy(void* dst, const void* src, size_t bytes) { if (bytes) std::memcpy(dst, src, bytes); }
   void copy_fence() {}

@@ -57,7 +57,8 @@ EXPORTS = ["phz_last_error", "phz_backend_name", "phz_create", "phz_destroy", "p
            "phz_fragdict_create", "phz_fragdict_destroy", "phz_fragdict_size", "phz_fragdict_name", "phz_read_alignments",
            "phz_host_reads_view", "phz_host_reads_free", "phz_set_haplo_blacklist", "phz_write_sam",
            "phz_set_indel_alleles", "phz_pack_reads", "phz_packed_view", "phz_packed_bytes", "phz_packed_free",
-           "phz_map_reads_packed", "phz_prefetch_packed", "phz_gene_ae_pairs", "phz_set_big_critical_values"]
+           "phz_map_reads_packed", "phz_prefetch_packed", "phz_gene_ae_pairs", "phz_set_big_critical_values",
+           "phz_copy_array"]
 
 
 def _declare(lib):
@@ -79,6 +80,7 @@ def _declare(lib):
     lib.phz_array.argtypes = [c_void_p, c_char_p, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int)]
     lib.phz_download.argtypes = [c_void_p, c_char_p, c_void_p, c_int64]
     lib.phz_download_async.argtypes = [c_void_p, c_char_p, c_void_p, c_int64]
+    lib.phz_copy_array.argtypes = [c_void_p, c_char_p, c_void_p, c_int64]
     lib.phz_counters.argtypes = [c_void_p, POINTER(c_int64)]
     lib.phz_launch_counts.argtypes = [c_void_p, POINTER(c_uint64), POINTER(c_uint64)]
     lib.phz_set_profiling.argtypes = [c_void_p, c_int]
@@ -450,6 +452,24 @@ class Engine:
             out[name] = host[off:off + n * eb].view(_DT[eb])
         self.sync()
         return out
+
+    def pack_arrays(self, names):
+        """All `names` back to back (64-byte aligned) in ONE buffer that lives where the engine's arrays live (device
+        memory in the product) -- the send buffer of the sharded run's result gather.  Returns (uint8 tensor,
+        [(name, byte offset, count, element bytes)]).  The copies are enqueued on the engine's stream, no wait."""
+        info = []
+        total = 0
+        for name in names:
+            p = c_void_p(); n = c_int64(0); eb = c_int(0)
+            self._check(self.lib.phz_array(self.ctx, name.encode(), byref(p), byref(n), byref(eb)))
+            off = (total + 63) // 64 * 64
+            info.append((name, off, n.value, eb.value))
+            total = off + n.value * eb.value
+        buf = torch.empty(max(total, 64), dtype=torch.uint8, device=self.device)
+        base = buf.data_ptr()
+        for name, off, n, eb in info:
+            self._check(self.lib.phz_copy_array(self.ctx, name.encode(), base + off, n * eb))
+        return buf, info
 
     def gene_ae_pairs(self, rows, feats):
         """phaser_gene_ae join + distinct-read counts (phz_gene_ae_pairs).  `rows` / `feats`: phaser_gene_ae.Rows /

@@ -2,14 +2,15 @@
 
 The reference itself maps, connects and builds blocks per contig (phaser/phaser.py:442, 533, 556, 650,
 784; pairs are same-contig only, :1278-1280), so a contig never needs data of another one.  What IS
-global, and therefore exchanged exactly between ranks, is tiny:
+global, and therefore exchanged exactly between ranks, is small:
   * per BAM, the alignment-score histogram   -> all-reduce(sum)  -> same AS cutoff everywhere (phaser.py:545-553)
   * the two noise counters                   -> all-reduce(sum)  -> same noise_e / critical values (phaser.py:610-631)
-  * the result arrays                        -> gather to rank 0, which renumbers blocks in the global
-                                                output order (phaser.py:863-867) and writes the files.
-No data-path collective: reads and tuples never leave their GPU.  Backend: NCCL on GPUs, gloo in the
-CPU tests.
+  * the result arrays                        -> gather to rank 0 (one packed device buffer per rank, grouped
+                                                send/recv), which renumbers blocks in the global output order
+                                                (phaser.py:863-867) and writes the files.
+Reads and tuples never leave their GPU.  Backend: NCCL on GPUs, gloo in the CPU tests.
 """
+import time
 from typing import List
 
 import numpy as np
@@ -17,9 +18,11 @@ import torch
 import torch.distributed as dist
 
 from .layout import ReadBatch, VariantTable
-from .pipeline import PhaseParams, PhaseResult, run_path
+from .pipeline import PhaseParams, PhaseResult, run_path, RESULT_ARRAYS
 
 NONE32 = 0xFFFFFFFF
+_DT = {1: np.uint8, 2: np.int16, 4: np.uint32, 8: np.uint64}
+N_COUNTERS = 16
 
 
 def plan_shards(weights: List[int], world: int) -> List[List[int]]:
@@ -34,19 +37,34 @@ def plan_shards(weights: List[int], world: int) -> List[List[int]]:
 
 
 class DistComm:
-    """The exact cross-rank reductions of pipeline.run_path over torch.distributed."""
+    """The exact cross-rank reductions of pipeline.run_path over torch.distributed.  With `timers` (a dict) every
+    collective is bracketed by device synchronisation and its wall time accumulated under its name."""
 
-    def __init__(self, device):
-        self.rank = dist.get_rank(); self.world_size = dist.get_world_size(); self.device = device
+    def __init__(self, device, timers=None):
+        self.rank = dist.get_rank(); self.world_size = dist.get_world_size(); self.device = torch.device(device)
+        self.timers = timers
+
+    def _sync(self):
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+
+    def _timed(self, name, fn):
+        if self.timers is None:
+            return fn()
+        self._sync(); t0 = time.perf_counter()
+        out = fn()
+        self._sync()
+        self.timers[name] = self.timers.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+        return out
 
     def allreduce_sum(self, t):
         t = t.to(self.device)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        self._timed("allreduce_as_histogram_ms", lambda: dist.all_reduce(t, op=dist.ReduceOp.SUM))
         return t
 
     def allreduce_sum_ints(self, xs):
         t = torch.tensor(list(xs), dtype=torch.int64, device=self.device)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        self._timed("allreduce_noise_ms", lambda: dist.all_reduce(t, op=dist.ReduceOp.SUM))
         return [int(x) for x in t.cpu().tolist()]
 
     def allreduce_max_int(self, x):
@@ -64,6 +82,8 @@ def sub_variant_table(vt: VariantTable, contigs: List[int]):
     pick = (lambda lst: [lst[i] for i in idx.tolist()]) if vt.ids else (lambda lst: [])
     sub = VariantTable([vt.contigs[c] for c in contigs], off, vt.pos[idx], vt.a0[idx], vt.a1[idx], vt.ref_len[idx],
                        pick(vt.ids), pick(vt.rsids), pick(vt.all_alleles), pick(vt.gt), pick(vt.maf))
+    if vt.haplo_blacklisted is not None:
+        sub.haplo_blacklisted = np.ascontiguousarray(vt.haplo_blacklisted[idx])
     return sub, idx.astype(np.int64)
 
 
@@ -95,23 +115,72 @@ def sub_read_batch(rb: ReadBatch, contigs: List[int]) -> ReadBatch:
                      cig_off.astype(np.uint32), rb.cigar[ci], seq_off.astype(np.uint64), seq, rb.qual[bi], rb.qnames)
 
 
+def sub_reads_tensors(reads: dict, contigs: List[int]) -> dict:
+    """sub_read_batch for the tensor form of a BAM (Engine.upload_reads: dict of torch tensors on any device +
+    host `contig_rec_off`): the records of `contigs`, contig order kept, offsets rebased.  The records of a contig
+    are one contiguous range of every array, so this is slicing and concatenation on the device the data is on."""
+    cro = np.asarray(reads["contig_rec_off"], np.int64)
+    pos = reads["pos"]; dev = pos.device
+    coff = reads["cigar_off"]; soff = reads["seq_off"]
+    rng = [(int(cro[c]), int(cro[c + 1])) for c in contigs]
+    off = np.zeros(len(contigs) + 1, np.int64)
+    off[1:] = np.cumsum([b - a for a, b in rng])
+
+    def cut(t):
+        return torch.cat([t[a:b] for a, b in rng]) if rng else t[:0]
+
+    out = dict(contig_rec_off=off, pos=cut(pos), tlen=cut(reads["tlen"]), aln_score=cut(reads["aln_score"]), frag=cut(reads["frag"]))
+    cig_parts, qual_parts, seq_parts, co_parts, so_parts = [], [], [], [], []
+    cbase = 0; sbase = 0
+    aligned = True
+    for a, b in rng:
+        c0 = int(coff[a].item()) & 0xFFFFFFFF; c1 = int(coff[b].item()) & 0xFFFFFFFF
+        s0 = int(soff[a].item()); s1 = int(soff[b].item())
+        cig_parts.append(reads["cigar"][c0:c1]); qual_parts.append(reads["qual"][s0:s1])
+        co_parts.append(coff[a:b].to(torch.int64).bitwise_and(0xFFFFFFFF) - c0 + cbase)
+        so_parts.append(soff[a:b].to(torch.int64) - s0 + sbase)
+        if (s0 & 1) or (sbase & 1):
+            aligned = False
+        seq_parts.append((s0, s1))
+        cbase += c1 - c0; sbase += s1 - s0
+    end_c = torch.tensor([cbase], dtype=torch.int64, device=dev); end_s = torch.tensor([sbase], dtype=torch.int64, device=dev)
+    out["cigar_off"] = torch.cat(co_parts + [end_c]).to(torch.int32)           # u32 values travel as int32 bit patterns
+    out["seq_off"] = torch.cat(so_parts + [end_s]).to(soff.dtype)
+    out["cigar"] = torch.cat(cig_parts) if cig_parts else reads["cigar"][:0]
+    out["qual"] = torch.cat(qual_parts) if qual_parts else reads["qual"][:0]
+    seq = reads["seq"]
+    if aligned:      # every piece starts on a byte boundary of both the source and the destination
+        out["seq"] = torch.cat([seq[s0 >> 1:(s1 + 1) >> 1] for s0, s1 in seq_parts]) if seq_parts else seq[:0]
+    else:            # general case: through one code per base
+        codes = []
+        for s0, s1 in seq_parts:
+            by = seq[s0 >> 1:(s1 + 1) >> 1]
+            u = torch.stack([by >> 4, by & 15], 1).reshape(-1)
+            codes.append(u[(s0 & 1):(s0 & 1) + (s1 - s0)])
+        u = torch.cat(codes) if codes else seq[:0]
+        if u.shape[0] & 1:
+            u = torch.cat([u, torch.zeros(1, dtype=u.dtype, device=dev)])
+        out["seq"] = ((u[0::2] << 4) | u[1::2]).contiguous()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ merge
+
 def merge_results(parts, vt: VariantTable, n_bams: int) -> PhaseResult:
-    """parts: per rank (PhaseResult, global variant ids of the rank's table, global contig ids).  Returns one
-    PhaseResult in global variant ids with blocks in the global output order."""
+    """parts: per rank (PhaseResult, global variant ids of the rank's table, global contig ids) or None for a rank
+    without contigs.  Returns one PhaseResult in global variant ids with blocks in the global output order
+    (phaser.py:863-867).  Array work only: the cost does not depend on Python loops over blocks or variants."""
     V = vt.n_variants
+    nb = n_bams
+    nc = len(vt.contigs)
     vfirst = np.full(V, np.iinfo(np.uint64).max, np.uint64)
-    ncls = np.zeros(V * 3, np.uint32); setsize = np.zeros(V * 3, np.uint32); vb = np.zeros(V * n_bams * 2, np.uint32)
+    ncls = np.zeros(V * 3, np.uint32); setsize = np.zeros(V * 3, np.uint32); vb = np.zeros(V * nb * 2, np.uint32)
     v_final = np.full(V, NONE32, np.uint32); v_hap = np.zeros(V, np.uint8)
-    contig_of = np.searchsorted(vt.contig_var_off, np.arange(V), side="right") - 1
-    ed = {k: [] for k in ("ed_a", "ed_b", "ed_sup", "ed_tot", "ed_cfg", "ed_keep")}
-    blocks = []          # (order key, rank index, local final block)
-    rl = {k: [] for k in ("rl_frag", "rl_var", "rl_row")}
-    sg = {k: [] for k in ("sg_var", "sg_cb", "sg_frag", "g_var", "g_cb", "g_frag")}
+    contig_of = np.repeat(np.arange(nc, dtype=np.int64), np.diff(np.asarray(vt.contig_var_off, np.int64)))
+    live = [(ri, p) for ri, p in enumerate(parts) if p is not None and p[0] is not None]
     counters = {}
-    bb = max(1, int(np.ceil(np.log2(max(n_bams, 2)))))
-    for ri, (res, gid, gcontigs) in enumerate(parts):
-        if res is None:
-            continue
+    first_bam_of_contig = np.full(nc, 1 << 30, np.int64)
+    for ri, (res, gid, _c) in live:
         for k, v in res.counters.items():
             counters[k] = counters.get(k, 0) + v
         bam_start = np.concatenate([[0], np.cumsum(res.tuples_per_bam)]).astype(np.int64)
@@ -121,88 +190,341 @@ def merge_results(parts, vt: VariantTable, n_bams: int) -> PhaseResult:
         # comparable across ranks: (BAM of the first tuple, contig, tuple order inside the rank)
         key = (bam_of.astype(np.uint64) << np.uint64(56)) | (contig_of[gid].astype(np.uint64) << np.uint64(40)) | lf.astype(np.uint64)
         vfirst[gid[seen]] = key[seen]
-        for name, dst, w in (("ncls", ncls, 3), ("setsize", setsize, 3), ("vb_cnt", vb, n_bams * 2)):
+        for name, dst, w in (("ncls", ncls, 3), ("setsize", setsize, 3), ("vb_cnt", vb, nb * 2)):
             dst.reshape(V, w)[gid] = res.arrays[name].reshape(-1, w)
         v_hap[gid] = res.v_hap
-        ed["ed_a"].append(gid[res.ed_a.astype(np.int64)].astype(np.uint32)); ed["ed_b"].append(gid[res.ed_b.astype(np.int64)].astype(np.uint32))
+        # contig order of first appearance (phaser.py:573-574): first BAM with a tuple on the contig, then VCF order
+        np.minimum.at(first_bam_of_contig, contig_of[gid[seen]], bam_of[seen])
+    first_bam_of_contig[first_bam_of_contig == (1 << 30)] = 0
+    # ---- global block order: (first BAM of the contig, contig, local order); a contig lives on one rank
+    k_bam, k_contig, k_local, k_rank = [], [], [], []
+    for ri, (res, gid, _c) in live:
+        nf = int(res.fb_first.shape[0])
+        c = contig_of[gid[res.members[res.fb_first.astype(np.int64)].astype(np.int64)]] if nf else np.zeros(0, np.int64)
+        k_bam.append(first_bam_of_contig[c]); k_contig.append(c); k_local.append(np.arange(nf, dtype=np.int64))
+        k_rank.append(np.full(nf, ri, np.int64))
+    cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
+    k_bam = cat(k_bam, np.int64); k_contig = cat(k_contig, np.int64); k_local = cat(k_local, np.int64); k_rank = cat(k_rank, np.int64)
+    order = np.lexsort((k_local, k_contig, k_bam))          # global position -> index into the concatenation
+    NF = order.shape[0]
+    new_of_cat = np.empty(NF, np.int64); new_of_cat[order] = np.arange(NF)
+    cat_len = cat([p[0].fb_len for _, p in live], np.int64)
+    g_len = cat_len[order]
+    g_first = np.zeros(NF, np.int64)
+    if NF:
+        g_first[1:] = np.cumsum(g_len)[:-1]
+    members = np.zeros(int(g_len.sum()), np.uint32)
+    fb_sup = np.zeros(NF, np.uint32); fb_tot = np.zeros(NF, np.uint32)
+    fb_cnt = np.zeros((NF, 2), np.uint32); fb_bcnt = np.zeros((NF, nb, 2), np.uint32)
+    ed = {k: [] for k in ("ed_a", "ed_b", "ed_sup", "ed_tot", "ed_cfg", "ed_keep")}
+    rl = {k: [] for k in ("rl_frag", "rl_var", "rl_row")}
+    sg = {k: [] for k in ("sg_var", "sg_cb", "sg_frag", "g_var", "g_cb", "g_frag")}
+    bb = max(1, int(np.ceil(np.log2(max(nb, 2)))))
+    base = 0
+    for ri, (res, gid, _c) in live:
+        nf = int(res.fb_first.shape[0])
+        new_id = new_of_cat[base:base + nf]          # local final block -> global block index
+        base += nf
+        ln = res.fb_len.astype(np.int64); lfirst = res.fb_first.astype(np.int64)
+        tot = int(ln.sum())
+        if tot:
+            rep = np.repeat(np.arange(nf), ln)
+            within = np.arange(tot) - np.repeat(np.cumsum(ln) - ln, ln)
+            members[g_first[new_id[rep]] + within] = gid[res.members[lfirst[rep] + within].astype(np.int64)]
+        fb_sup[new_id] = res.fb_sup; fb_tot[new_id] = res.fb_tot
+        fb_cnt[new_id] = res.fb_cnt.reshape(-1, 2); fb_bcnt[new_id] = res.fb_bcnt.reshape(-1, nb, 2)
+        inb = res.v_final != NONE32
+        v_final[gid[inb]] = new_id[res.v_final[inb].astype(np.int64)]
+        ed["ed_a"].append(gid[res.ed_a.astype(np.int64)]); ed["ed_b"].append(gid[res.ed_b.astype(np.int64)])
         for k in ("ed_sup", "ed_tot", "ed_cfg", "ed_keep"):
             ed[k].append(res.arrays[k])
         if "sg_var" in res.arrays:
-            sg["sg_var"].append(gid[res.sg_var.astype(np.int64)].astype(np.uint32))
-            sg["sg_cb"].append(res.sg_cb); sg["sg_frag"].append(res.sg_frag)
+            sg["sg_var"].append(gid[res.sg_var.astype(np.int64)]); sg["sg_cb"].append(res.sg_cb); sg["sg_frag"].append(res.sg_frag)
         if "g_var" in res.arrays:
-            sg["g_var"].append(gid[res.g_var.astype(np.int64)].astype(np.uint32))
-            sg["g_cb"].append(res.g_cb); sg["g_frag"].append(res.g_frag)
-        # contig order of first appearance (phaser.py:573-574): first BAM with a tuple on the contig, then VCF order
-        first_bam_of_contig = {}
-        for v in np.nonzero(seen)[0].tolist():
-            c = int(contig_of[gid[v]])
-            b = int(bam_of[v])
-            if c not in first_bam_of_contig or b < first_bam_of_contig[c]:
-                first_bam_of_contig[c] = b
-        for f in range(res.fb_first.shape[0]):
-            first_member = int(gid[res.members[res.fb_first[f]]])
-            c = int(contig_of[first_member])
-            blocks.append(((first_bam_of_contig.get(c, 0), c, f), ri, f))
-    blocks.sort()
-    members, fb_first, fb_len, fb_sup, fb_tot, fb_cnt, fb_bcnt = [], [], [], [], [], [], []
-    new_id = {}
-    pos = 0
-    for g, (_, ri, f) in enumerate(blocks):
-        res, gid, _c = parts[ri]
-        o = int(res.fb_first[f]); n = int(res.fb_len[f])
-        m = gid[res.members[o:o + n].astype(np.int64)]
-        members.append(m.astype(np.uint32)); fb_first.append(pos); fb_len.append(n); pos += n
-        fb_sup.append(res.fb_sup[f]); fb_tot.append(res.fb_tot[f])
-        fb_cnt.append(res.fb_cnt.reshape(-1, 2)[f]); fb_bcnt.append(res.fb_bcnt.reshape(-1, n_bams, 2)[f])
-        v_final[m] = g
-        new_id[(ri, f)] = g
-    for ri, (res, gid, _c) in enumerate(parts):
-        if res is None or "rl_row" not in res.arrays or res.rl_row.shape[0] == 0:
-            continue
-        row = res.rl_row.astype(np.int64)
-        f_local = row >> (bb + 1)
-        remap = np.array([new_id[(ri, f)] for f in range(res.fb_first.shape[0])], np.int64)
-        rl["rl_row"].append(((remap[f_local] << (bb + 1)) | (row & ((1 << (bb + 1)) - 1))).astype(np.uint32))
-        rl["rl_var"].append(gid[res.rl_var.astype(np.int64)].astype(np.uint32)); rl["rl_frag"].append(res.rl_frag)
-    cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
+            sg["g_var"].append(gid[res.g_var.astype(np.int64)]); sg["g_cb"].append(res.g_cb); sg["g_frag"].append(res.g_frag)
+        if "rl_row" in res.arrays and res.rl_row.shape[0]:
+            row = res.rl_row.astype(np.int64)
+            rl["rl_row"].append((new_id[row >> (bb + 1)] << (bb + 1)) | (row & ((1 << (bb + 1)) - 1)))
+            rl["rl_var"].append(gid[res.rl_var.astype(np.int64)]); rl["rl_frag"].append(res.rl_frag)
     arrays = dict(vfirst=vfirst, ncls=ncls, setsize=setsize, vb_cnt=vb, v_final=v_final, v_hap=v_hap,
-                  members=cat(members, np.uint32), fb_first=np.asarray(fb_first, np.uint32), fb_len=np.asarray(fb_len, np.uint32),
-                  fb_sup=np.asarray(fb_sup, np.uint32), fb_tot=np.asarray(fb_tot, np.uint32),
-                  fb_cnt=cat(fb_cnt, np.uint32).reshape(-1), fb_bcnt=cat([x.reshape(-1) for x in fb_bcnt], np.uint32))
+                  members=members, fb_first=g_first.astype(np.uint32), fb_len=g_len.astype(np.uint32),
+                  fb_sup=fb_sup, fb_tot=fb_tot, fb_cnt=fb_cnt.reshape(-1), fb_bcnt=fb_bcnt.reshape(-1))
     for k, dt in (("ed_a", np.uint32), ("ed_b", np.uint32), ("ed_sup", np.uint32), ("ed_tot", np.uint32), ("ed_cfg", np.uint8), ("ed_keep", np.uint8)):
         arrays[k] = cat(ed[k], dt)
     if rl["rl_row"]:
         # rows of one block live on one rank, so a stable sort by row keeps variant / tuple order
-        row = np.concatenate(rl["rl_row"]); order = np.argsort(row, kind="stable")
-        arrays["rl_row"] = row[order]; arrays["rl_var"] = np.concatenate(rl["rl_var"])[order]; arrays["rl_frag"] = np.concatenate(rl["rl_frag"])[order]
+        row = np.concatenate(rl["rl_row"]); o = np.argsort(row, kind="stable")
+        arrays["rl_row"] = row[o].astype(np.uint32); arrays["rl_var"] = np.concatenate(rl["rl_var"])[o].astype(np.uint32)
+        arrays["rl_frag"] = np.concatenate(rl["rl_frag"])[o].astype(np.uint32)
     else:
         arrays["rl_row"] = np.zeros(0, np.uint32); arrays["rl_var"] = np.zeros(0, np.uint32); arrays["rl_frag"] = np.zeros(0, np.uint32)
     for pre in ("sg_", "g_"):
         if sg[pre + "var"]:
             for k, dt in (("var", np.uint32), ("cb", np.uint8), ("frag", np.uint32)):
                 arrays[pre + k] = cat(sg[pre + k], dt)
-    first = next(p[0] for p in parts if p[0] is not None)
-    return PhaseResult(n_bams, first.as_cutoff, [sum(p[0].tuples_per_bam[b] for p in parts if p[0] is not None) for b in range(n_bams)],
-                       [sum(p[0].candidates_per_bam[b] for p in parts if p[0] is not None) for b in range(n_bams)],
+    first = live[0][1][0]
+    return PhaseResult(nb, first.as_cutoff, [sum(p[0].tuples_per_bam[b] for _, p in live) for b in range(nb)],
+                       [sum(p[0].candidates_per_bam[b] for _, p in live) for b in range(nb)],
                        first.noise_e, first.match, first.mismatch, counters, 0, arrays)
+
+
+def results_equal(a: PhaseResult, b: PhaseResult):
+    """Array-level equality of two results of the same inputs (e.g. merged shards vs. one GPU).  The edge table is
+    compared as a set of rows (its order is the order of the variant pairs per rank) and `vfirst` through the order
+    it defines (a tuple index on one GPU, a (BAM, contig, index) key after a merge).  Returns the names that differ."""
+    bad = []
+    for k in ("ncls", "setsize", "vb_cnt", "v_final", "v_hap", "fb_len", "fb_sup", "fb_tot",
+              "fb_cnt", "fb_bcnt", "rl_row", "rl_var", "rl_frag"):
+        if (k in a.arrays) != (k in b.arrays):
+            bad.append(k)
+        elif k in a.arrays and not np.array_equal(np.asarray(a.arrays[k]).astype(np.int64), np.asarray(b.arrays[k]).astype(np.int64)):
+            bad.append(k)
+
+    def block_members(r):        # `members` may hold unused slots between the final blocks (one GPU) or none (merged)
+        ln = r.fb_len.astype(np.int64); tot = int(ln.sum())
+        if tot == 0:
+            return np.zeros(0, np.int64)
+        within = np.arange(tot) - np.repeat(np.cumsum(ln) - ln, ln)
+        return r.members[np.repeat(r.fb_first.astype(np.int64), ln) + within].astype(np.int64)
+    if not np.array_equal(a.fb_len, b.fb_len) or not np.array_equal(block_members(a), block_members(b)):
+        bad.append("members")
+
+    def edge_rows(r):
+        m = np.stack([r.ed_a.astype(np.int64), r.ed_b.astype(np.int64), r.ed_sup.astype(np.int64), r.ed_tot.astype(np.int64),
+                      r.ed_cfg.astype(np.int64), r.ed_keep.astype(np.int64)], 1)
+        return m[np.lexsort((m[:, 1], m[:, 0]))] if m.shape[0] else m
+    ea, eb = edge_rows(a), edge_rows(b)
+    if ea.shape != eb.shape or not np.array_equal(ea, eb):
+        bad.append("edges")
+
+    def order(r):
+        vf = r.vfirst
+        seen = np.nonzero(vf != np.iinfo(vf.dtype).max)[0]
+        return seen[np.argsort(vf[seen], kind="stable")]
+    if not np.array_equal(order(a), order(b)):
+        bad.append("vfirst order")
+    for k in ("n_tuples", "edges", "dropped", "members", "final_blocks", "read_list_entries"):
+        if a.counters.get(k) != b.counters.get(k):
+            bad.append("counter " + k)
+    if a.noise_e != b.noise_e or list(a.as_cutoff) != list(b.as_cutoff):
+        bad.append("noise / AS cutoff")
+    return bad
+
+
+# ------------------------------------------------------------------------------------------------ gather
+
+def gather_names(params: PhaseParams):
+    names = list(RESULT_ARRAYS)
+    if params.want_read_lists:
+        names += ["rl_frag", "rl_var", "rl_row"]
+    if params.want_kept_tuples or params.want_read_ids:
+        names += ["g_var", "g_cb", "g_frag"]
+    return names
+
+
+def gather_results(engine, res, names, n_bams, device, timers=None, to_host=True, failed=False):
+    """Every rank packs its result arrays into ONE buffer where they live (device memory: phz_copy_array), the byte
+    counts travel in a small all-gather, and a grouped send/recv moves the buffers into rank 0's memory.  Rank 0
+    returns, per rank, {name: numpy array} + (counters, tuples per BAM, candidates per BAM) read from one page-locked
+    host copy (`to_host`) -- or the raw device buffers; the other ranks return None.  `res` is None on a rank that
+    owns no contig."""
+    world = dist.get_world_size(); rank = dist.get_rank()
+    device = torch.device(device)
+
+    def sync():
+        if device.type == "cuda":
+            torch.cuda.synchronize(device)
+
+    if timers is not None:
+        sync(); t0 = time.perf_counter()
+    nn = len(names)
+    head = torch.zeros(nn * 2 + N_COUNTERS + 2 * n_bams + 1, dtype=torch.int64)
+    buf = None
+    if res is not None:
+        buf, info = engine.pack_arrays(names)
+        if buf.device != device:          # collectives on another device than the engine's (gloo between CUDA engines)
+            buf = buf.to(device)
+        for i, (_nm, _off, n, eb) in enumerate(info):
+            head[2 * i] = n; head[2 * i + 1] = eb
+        cn = list(res.counters.values())
+        head[2 * nn:2 * nn + len(cn)] = torch.tensor(cn, dtype=torch.int64)
+        head[2 * nn + N_COUNTERS:2 * nn + N_COUNTERS + n_bams] = torch.tensor(res.tuples_per_bam, dtype=torch.int64)
+        head[2 * nn + N_COUNTERS + n_bams:2 * nn + N_COUNTERS + 2 * n_bams] = torch.tensor(res.candidates_per_bam, dtype=torch.int64)
+        head[-1] = 1
+    if failed:
+        head[-1] = 2
+    heads = [torch.zeros_like(head, device=device) for _ in range(world)]
+    dist.all_gather(heads, head.to(device))
+    heads = torch.stack(heads).cpu().numpy()
+    if (heads[:, -1] == 2).any():
+        if failed:
+            return None
+        from .vcfio import PhaserFatal
+        raise PhaserFatal("rank %s failed; see its message" % ",".join(str(r) for r in np.nonzero(heads[:, -1] == 2)[0].tolist()))
+
+    def layout(h):
+        out = []; total = 0
+        for i in range(nn):
+            n = int(h[2 * i]); eb = int(h[2 * i + 1])
+            off = (total + 63) // 64 * 64
+            out.append((names[i], off, n, eb)); total = off + n * eb
+        return out, max(total, 64)
+
+    lay = [layout(h) for h in heads]
+    ops = []; recv = [None] * world
+    if rank == 0:
+        recv[0] = buf
+        for r in range(1, world):
+            if heads[r][-1] == 1:
+                recv[r] = torch.empty(lay[r][1], dtype=torch.uint8, device=device)
+                ops.append(dist.P2POp(dist.irecv, recv[r], r))
+    elif res is not None:
+        ops.append(dist.P2POp(dist.isend, buf, 0))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    if timers is not None:
+        sync(); timers["gather_results_ms"] = timers.get("gather_results_ms", 0.0) + (time.perf_counter() - t0) * 1e3
+        timers["gather_bytes_into_rank0"] = int(sum(lay[r][1] for r in range(1, world) if heads[r][-1] == 1))
+    if rank != 0:
+        return None
+    if not to_host:
+        return recv, lay, heads
+    # one page-locked host copy of everything, then views
+    total = sum(lay[r][1] for r in range(world) if recv[r] is not None)
+    host = getattr(engine, "_gather_host", None)
+    if host is None or host.numel() < total:
+        host = torch.empty(int(total * 1.25) + 4096, dtype=torch.uint8)
+        if device.type == "cuda":
+            try:
+                host = host.pin_memory()
+            except RuntimeError:
+                pass
+        engine._gather_host = host
+    o = 0; offs = []
+    for r in range(world):
+        offs.append(o)
+        if recv[r] is not None:
+            host[o:o + lay[r][1]].copy_(recv[r][:lay[r][1]], non_blocking=True)
+            o += lay[r][1]
+    sync()
+    hn = host.numpy()
+    out = []
+    for r in range(world):
+        if recv[r] is None:
+            out.append(None); continue
+        h = heads[r]
+        arrays = {nm: hn[offs[r] + off:offs[r] + off + n * eb].view(_DT[eb]) for nm, off, n, eb in lay[r][0]}
+        from .engine import COUNTER_NAMES
+        counters = {k: int(h[2 * nn + i]) for i, k in enumerate(COUNTER_NAMES)}
+        tpb = [int(x) for x in h[2 * nn + N_COUNTERS:2 * nn + N_COUNTERS + n_bams]]
+        cpb = [int(x) for x in h[2 * nn + N_COUNTERS + n_bams:2 * nn + N_COUNTERS + 2 * n_bams]]
+        out.append((arrays, counters, tpb, cpb))
+    return out
+
+
+def _idle_rank(params: PhaseParams, n_bams: int, comm):
+    """A rank that owns no contig still takes part in every collective of run_path, with zeros, and reaches the same
+    verdicts (cutoffs, noise level, fatal errors) as the ranks that do."""
+    from .engine import AS_BINS
+    from .layout import AS_MISSING
+    from .pipeline import percentile_from_histogram, noise_level
+    from .vcfio import PhaserFatal
+    cutoffs = []
+    for _ in range(n_bams):
+        cutoff = None
+        if params.as_q_cutoff > 0:
+            hist = comm.allreduce_sum(torch.zeros(AS_BINS, dtype=torch.int64)).cpu().numpy()
+            n_missing = int(hist[AS_MISSING + 32768]); hist[AS_MISSING + 32768] = 0
+            cutoff = percentile_from_histogram(hist, params.as_q_cutoff)
+            if cutoff is not None and n_missing > 0:
+                raise PhaserFatal("%d mapped reads carry no AS:i tag but an alignment-score cutoff is active" % n_missing)
+        cutoffs.append(cutoff)
+    match, mism = comm.allreduce_sum_ints([0, 0])
+    if match == 0:
+        raise PhaserFatal("No reads could be matched to variants.")
+    return PhaseResult(n_bams, cutoffs, [0] * n_bams, [0] * n_bams, noise_level(match, mism), match, mism, {}, 0, {})
+
+
+class ShardedRun:
+    """One sample over the ranks of the process group, sharded by contig.  Built once per sample (plan, this rank's
+    variant table and ids); `step(batches)` runs the path on this rank's contigs with the exact reductions, gathers
+    the result arrays into rank 0's memory and -- on rank 0 -- merges them into one PhaseResult in global ids."""
+
+    def __init__(self, engine, vt: VariantTable, weights: List[int], params: PhaseParams, n_fragments: int, n_bams: int,
+                 device=None, timers=None):
+        self.engine = engine; self.vt = vt; self.params = params; self.n_fragments = n_fragments; self.n_bams = n_bams
+        self.world = dist.get_world_size(); self.rank = dist.get_rank()
+        self.device = torch.device(device if device is not None else engine.device)
+        self.plan = plan_shards(weights, self.world)
+        self.weights = list(weights)
+        self.mine = self.plan[self.rank]
+        self.timers = timers
+        self.comm = DistComm(self.device, timers)
+        self.svt, self.gid = sub_variant_table(vt, self.mine)
+        self.gids = [sub_variant_table_ids(vt, p) for p in self.plan] if self.rank == 0 else None
+        self.names = gather_names(params)
+
+    def loads(self):
+        return [int(sum(self.weights[c] for c in p)) for p in self.plan]
+
+    def step(self, batches, host_inputs=False, merge=True, to_host=True):
+        from .vcfio import PhaserFatal
+        err = None; res = None
+        try:
+            if self.mine:
+                res = run_path(self.engine, self.svt, batches, self.params, self.n_fragments, comm=self.comm,
+                               host_inputs=host_inputs, download=False)
+            else:
+                res = _idle_rank(self.params, self.n_bams, self.comm)
+        except PhaserFatal as e:          # rank-local verdicts (phasing flags) must not leave the others in the gather
+            err = e
+        got = gather_results(self.engine, res if (self.mine and err is None) else None, self.names, self.n_bams, self.device,
+                             self.timers, to_host=to_host and merge, failed=err is not None)
+        if err is not None:
+            raise err
+        if self.rank != 0 or not merge:
+            return None
+        if self.timers is not None:
+            t0 = time.perf_counter()
+        parts = []
+        for r, g in enumerate(got):
+            if g is None:
+                parts.append(None); continue
+            arrays, counters, tpb, cpb = g
+            if {"g_var", "g_cb", "g_frag"} <= set(arrays) and self.params.want_read_ids:
+                gv = arrays["g_var"]; gc = arrays["g_cb"]
+                sel = np.nonzero((arrays["v_final"][gv] == NONE32) & ((gc & 3) < 2))[0]
+                arrays["sg_var"] = gv[sel]; arrays["sg_cb"] = gc[sel]; arrays["sg_frag"] = arrays["g_frag"][sel]
+            if not self.params.want_kept_tuples:
+                for k in ("g_var", "g_cb", "g_frag"):
+                    arrays.pop(k, None)
+            pr = PhaseResult(self.n_bams, res.as_cutoff, tpb, cpb, res.noise_e, res.match, res.mismatch, counters, 0, arrays)
+            parts.append((pr, self.gids[r], self.plan[r]))
+        out = merge_results(parts, self.vt, self.n_bams)
+        if self.timers is not None:
+            self.timers["merge_on_rank0_ms"] = self.timers.get("merge_on_rank0_ms", 0.0) + (time.perf_counter() - t0) * 1e3
+        return out
+
+
+def sub_variant_table_ids(vt: VariantTable, contigs: List[int]):
+    return (np.concatenate([np.arange(vt.contig_var_off[c], vt.contig_var_off[c + 1]) for c in contigs]) if contigs
+            else np.zeros(0, np.int64)).astype(np.int64)
+
+
+def contig_weights(vt: VariantTable, batches) -> List[int]:
+    """records per contig over all BAMs (+1 so that empty contigs still spread)"""
+    def off(b):
+        return np.asarray(b.contig_rec_off if isinstance(b, ReadBatch) else b["contig_rec_off"], np.int64)
+    return [int(sum(off(b)[c + 1] - off(b)[c] for b in batches)) + 1 for c in range(len(vt.contigs))]
 
 
 def run_sharded(engine, vt: VariantTable, batches: List[ReadBatch], params: PhaseParams, n_fragments: int, device=None):
     """Every rank calls this with the SAME host inputs (or at least its own contigs' part of them); rank 0
     gets the merged PhaseResult, the others None."""
-    world = dist.get_world_size(); rank = dist.get_rank()
-    weights = [int(sum(b.contig_rec_off[c + 1] - b.contig_rec_off[c] for b in batches)) + 1 for c in range(len(vt.contigs))]
-    mine = plan_shards(weights, world)[rank]
-    comm = DistComm(device if device is not None else engine.device)
-    svt, gid = sub_variant_table(vt, mine)
-    dev = [engine.upload_reads(sub_read_batch(b, mine)) for b in batches]
-    res = run_path(engine, svt, dev, params, n_fragments, comm=comm)
-    gathered = [None] * world if rank == 0 else None
-    dist.gather_object((res, gid, mine), gathered, dst=0)
-    if rank != 0:
-        return None
-    return merge_results(gathered, vt, len(batches))
+    run = ShardedRun(engine, vt, contig_weights(vt, batches), params, n_fragments, len(batches), device=device)
+    dev = [engine.upload_reads(sub_read_batch(b, run.mine)) for b in batches] if run.mine else []
+    return run.step(dev)
 
 
 class ThreadComm:
@@ -253,14 +575,16 @@ def run_logical_shards(make_engine, vt: VariantTable, batches: List[ReadBatch], 
                        n_shards: int) -> PhaseResult:
     """N logical shards (threads, one engine each) + merge: must equal the unsharded run."""
     import threading
-    weights = [int(sum(b.contig_rec_off[c + 1] - b.contig_rec_off[c] for b in batches)) + 1 for c in range(len(vt.contigs))]
-    plan = plan_shards(weights, n_shards)
+    plan = plan_shards(contig_weights(vt, batches), n_shards)
     comm = ThreadComm(n_shards)
     parts = [None] * n_shards
     errors = []
 
     def work(r):
         try:
+            if not plan[r]:
+                _idle_rank(params, len(batches), comm.view(r))
+                return
             engine = make_engine()
             svt, gid = sub_variant_table(vt, plan[r])
             dev = [engine.upload_reads(sub_read_batch(b, plan[r])) for b in batches]

@@ -22,3 +22,10 @@ def hostsim():
 def gpu():
     from tests import util
     return util.gpu_engine()
+
+
+@pytest.fixture(params=["hostsim", pytest.param("gpu", marks=pytest.mark.gpu)])
+def engine(request):
+    """Drop-in surface tests run twice: on the host-simulation double here (-m "not gpu") and on the CUDA library on
+    the B200 box (-m gpu)."""
+    return request.getfixturevalue(request.param)

@@ -301,6 +301,7 @@ def run_case(name, vcf_text, sams, args, mapq="255", paired_end="1"):
     paths = []
     for bn, text in sams:
         p = os.path.join(d, bn)
+        os.makedirs(os.path.dirname(p), exist_ok=True)
         with open(p, "w") as f:
             f.write(text)
         paths.append(p)
@@ -334,7 +335,7 @@ def run_case(name, vcf_text, sams, args, mapq="255", paired_end="1"):
                                str(int(vt.ref_len[v])), vt.gt[v], vt.maf[v]]) + "\n")
     for p in paths:
         # the mapper is fed what the two samtools stages would pass: here everything on the VCF's contigs
-        out = os.path.join(d, "ref.mapper." + os.path.basename(p) + ".tsv")
+        out = os.path.join(d, "ref.mapper." + os.path.relpath(p, d).replace(os.sep, "_") + ".tsv")
         filt = os.path.join(tmp, "filt.sam")
         with open(p) as fin, open(filt, "w") as fo:
             for ln in fin:
@@ -350,15 +351,18 @@ def run_case(name, vcf_text, sams, args, mapq="255", paired_end="1"):
     print("golden case", name, "ok")
 
 
-def synth_case(name, seed, n_variants, n_pairs, n_bams, args, **read_kw):
-    g = synth.make_genome(seed, n_variants, contigs=[("21", 120000), ("22", 80000)], n_genes=max(2, n_variants // 8))
+def synth_case(name, seed, n_variants, n_pairs, n_bams, args, qname=None, bam_files=None, phased_frac=0.9, **read_kw):
+    """`qname`: QNAME prefix of every BAM (default: one prefix per BAM, so no read name is shared between BAMs);
+    `bam_files`: file names inside the case directory (default b0.bam, b1.bam, ...)."""
+    g = synth.make_genome(seed, n_variants, contigs=[("21", 120000), ("22", 80000)], n_genes=max(2, n_variants // 8),
+                          phased_frac=phased_frac)
     tmp = tempfile.mkdtemp()
     vcf = synth.write_vcf(g, os.path.join(tmp, "x.vcf.gz"))
     sams = []
     for b in range(n_bams):
         rec = synth.make_reads(g, seed * 100 + b, n_pairs, dup_frac=0.05, **read_kw)
-        p = synth.write_sam(rec, g, os.path.join(tmp, "b%d.bam" % b), bam_name="b%d" % b)
-        sams.append(("b%d.bam" % b, open(p).read()))
+        p = synth.write_sam(rec, g, os.path.join(tmp, "b%d.bam" % b), bam_name=qname if qname else "b%d" % b)
+        sams.append((bam_files[b] if bam_files else "b%d.bam" % b, open(p).read()))
     with gzip.open(vcf, "rt") as f:
         vt = f.read()
     shutil.rmtree(tmp)
@@ -398,6 +402,54 @@ def blacklist_cases():
     m = json.load(open(os.path.join(CASES, "opt_blacklists", "case.json")))
     m["args"] = ["--blacklist", "beds/blacklist.bed", "--haplo_count_blacklist", "beds/haplo_blacklist.bed"]
     json.dump(m, open(os.path.join(CASES, "opt_blacklists", "case.json"), "w"), indent=1)
+
+
+def tie_case():
+    """Q16 (phaser.py:708-726): an edge whose cis and trans support tie survives the binomial test, stays in the variant
+    graph -- so it glues its variants into one component -- but adds no allele links.  Contig 1: rs1-rs2 are joined by 40
+    clean reads; rs3 hangs on rs2 by exactly one cis and one trans read.  The reference therefore sees ONE component of
+    three variants, cannot resolve it, enumerates 2^3 configurations, finds two equally supported ones and drops the whole
+    block: rs1 and rs2 end up unphased.  (Without the glue rs1-rs2 would be an ordinary phased block.)  One read with a
+    third base at rs1 gives the noise estimate the non-zero value without which the tie edge would fail the test.
+    Contig 2: the same picture on a longer chain, a tie in the middle of two clean pairs."""
+    V = [vline("1", 105, "rs1", "A", "G", "0|1"), vline("1", 112, "rs2", "C", "T", "0|1"), vline("1", 128, "rs3", "G", "A", "0|1"),
+         vline("2", 105, "rs4", "A", "G", "0|1"), vline("2", 112, "rs5", "C", "T", "1|0"), vline("2", 128, "rs6", "G", "A", "0|1"),
+         vline("2", 135, "rs7", "T", "C", "0/1")]
+    S = []
+
+    def rd(name, chrom, pos, n, edits):
+        seq = ["A"] * n
+        for k, b in edits.items():
+            seq[k] = b
+        S.append((chrom, pos, sline(name, 99, chrom, pos, 255, "%dM" % n, "".join(seq))))
+
+    for chrom in ("1", "2"):
+        for i in range(40):          # rs1/rs4 - rs2/rs5, clean cis, both haplotypes
+            rd("c%s_%d" % (chrom, i), chrom, 100, 20, {5: "A", 12: "C"} if i % 2 else {5: "G", 12: "T"})
+        rd("x%s" % chrom, chrom, 100, 20, {5: "C", 12: "C"})                      # third base at the first site -> 'other'
+        rd("t%s_cis" % chrom, chrom, 108, 26, {4: "C", 20: "G"})                  # second - third site: one cis ...
+        rd("t%s_trans" % chrom, chrom, 108, 26, {4: "C", 20: "A"})               # ... one trans read
+    for i in range(6):               # contig 2: rs6 - rs7 clean cis on the far side of the tie
+        rd("d%d" % i, "2", 120, 20, {8: "G", 15: "T"} if i % 2 else {8: "A", 15: "C"})
+    S.sort(key=lambda t: (t[0], t[1]))
+    return VCF_HEAD + "".join(V), SAM_HEAD + "".join(x[2] for x in S)
+
+
+def engine_quirk_cases():
+    """Reference runs that pin the engine-side quirks of SURVEY.md section 8a which no earlier case provably reaches
+    (tests/test_quirk_coverage.py shows, per quirk, that a port WITHOUT the quirk no longer reproduces these files)."""
+    # Q9 (phaser.py:578): both BAMs name their reads r.<i>, so hundreds of QNAMEs occur in both files, at unrelated
+    # loci; read_vars of a shared name is overwritten by the later BAM
+    synth_case("q9_shared_qnames", 300, 160, 700, 2, [], qname="r")
+    # Q22 (phaser.py:935-939) / Q21: most genotypes are unphased, so many blocks have no known phase at all
+    synth_case("q22_unphased_blocks", 301, 160, 900, 1, [], phased_frac=0.3)
+    # Q26 (phaser.py:469-480): two BAMs with the same basename in different directories -> display names x.1, x.2
+    synth_case("q26_same_basename", 302, 120, 500, 2, ["--haplo_count_bam_exclude", "1"], bam_files=["a/x.bam", "b/x.bam"])
+    # Q16: tie edges glue components
+    v, s = tie_case()
+    run_case("q16_tie_glue", v, [("tie.bam", s)], ["--as_q_cutoff", "0"])
+    # --chr (phaser.py:205-207, 1679-1680): het sites and output VCF lines of one contig only
+    option_case("opt_chr", "rna_two_bams", ["--chr", "22", "--haplo_count_bam_exclude", "2"])
 
 
 def config1_inputs(tmp):
@@ -491,9 +543,14 @@ def main():
     option_case("fuzz_snvs", "fuzz_indels", ["--as_q_cutoff", "0.1", "--max_block_size", "5"])
     vq, sq = quirk_case()
     run_case("opt_quirks_indels", vq, [("quirks.bam", sq)], ["--include_indels", "1", "--as_q_cutoff", "0"])
+    engine_quirk_cases()
     config1_case()
     gene_ae_cases()
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1:          # python make_golden.py engine_quirk_cases  -> only that group
+        for fn in sys.argv[1:]:
+            globals()[fn]()
+    else:
+        main()

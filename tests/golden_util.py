@@ -23,7 +23,7 @@ def load_case(name):
             ref[k] = open(fn).read()
     src = os.path.join(CASES, meta["inputs"]) if "inputs" in meta else d
     sams = [os.path.join(src, b) for b in meta["bams"]]
-    mapper = {b: open(os.path.join(d, "ref.mapper.%s.tsv" % b)).read() for b in meta["bams"]}
+    mapper = {b: open(os.path.join(d, "ref.mapper.%s.tsv" % b.replace("/", "_"))).read() for b in meta["bams"]}
     return dict(dir=d, vcf=os.path.join(src, "in.vcf.gz"), sams=sams, meta=meta, ref=ref, mapper=mapper)
 
 
@@ -46,7 +46,7 @@ def args_to_kw(args):
             kw[a[2:]] = int(v)
         elif a in ("--gw_phase_vcf_min_confidence", "--cc_threshold"):
             kw[a[2:]] = float(v)
-        elif a in ("--id_separator", "--output_network"):
+        elif a in ("--id_separator", "--output_network", "--chr"):
             kw[a[2:]] = v
         elif a in ("--blacklist", "--haplo_count_blacklist"):
             kw[a[2:]] = os.path.join(os.path.dirname(CASES), v)

@@ -17,10 +17,15 @@ from tests import util, golden_util as G           # noqa: E402
 def main():
     case = sys.argv[1]
     on_gpu = os.environ.get("PHZ_ENGINE", "hostsim") == "gpu"
+    # PHZ_COMM=gloo with PHZ_ENGINE=gpu: all ranks drive CUDA engines on ONE GPU and exchange through host memory
+    # (NCCL refuses two ranks on one device) -- the sharded path on the CUDA backend where only one GPU is visible
+    backend = os.environ.get("PHZ_COMM", "nccl" if on_gpu else "gloo")
+    gpu_index = 0
     if on_gpu:
         import torch
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", os.environ["RANK"])))
-    dist.init_process_group("nccl" if on_gpu else "gloo", init_method="tcp://127.0.0.1:%s" % os.environ["MASTER_PORT"],
+        gpu_index = int(os.environ.get("LOCAL_RANK", os.environ["RANK"])) if backend == "nccl" else 0
+        torch.cuda.set_device(gpu_index)
+    dist.init_process_group(backend, init_method="tcp://127.0.0.1:%s" % os.environ["MASTER_PORT"],
                             rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
     c = G.load_case(case)
     kw = G.args_to_kw(c["meta"]["args"])
@@ -30,10 +35,10 @@ def main():
                              want_read_ids=kw.get("output_read_ids", 0) == 1, want_kept_tuples=kw.get("output_network", "") != "")
     if on_gpu:
         from phaser_b200.engine import Engine
-        e = Engine(device="cuda:%d" % int(os.environ.get("LOCAL_RANK", os.environ["RANK"])))
+        e = Engine(device="cuda:%d" % gpu_index)
     else:
         e = util.hostsim_engine()
-    res = shard.run_sharded(e, vt, batches, P, n_fragments=len(fd.names))
+    res = shard.run_sharded(e, vt, batches, P, n_fragments=len(fd.names), device="cpu" if backend == "gloo" else None)
     rc = 0
     if dist.get_rank() == 0:
         o = writer.Outputs(res, vt, util.bam_display_names(c["sams"]), P,
@@ -49,7 +54,7 @@ def main():
         if bad:
             print("\n".join(bad)); rc = 1
         else:
-            print("SHARDED PARITY OK", case, res.counters)
+            print("SHARDED PARITY OK", case, "backend=%s comm=%s" % (e.backend, backend), res.counters)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(rc)

@@ -1,4 +1,5 @@
-"""CLI drop-in behaviour and BAM/BGZF ingest (host-simulation backend in the build container)."""
+"""CLI drop-in behaviour and BAM/BGZF ingest.  Tests taking `engine` run on the host-simulation double in the build
+container and on the CUDA library on the GPU box (tests/conftest.py)."""
 import gzip
 import os
 
@@ -28,14 +29,15 @@ def _run_cli(engine, case, tmp_path, extra=()):
 
 
 @pytest.mark.parametrize("case", ["quirks", "rna_two_bams", "opt_blacklists", "opt_maf_gwvcf2", "opt_nounphased_uid", "opt_filters",
-                                  "indels", "fuzz_indels", "opt_read_ids", "opt_network"])
-def test_cli_writes_reference_identical_files(hostsim, tmp_path, case):
-    c, got = _run_cli(hostsim, case, tmp_path)
+                                  "indels", "fuzz_indels", "opt_read_ids", "opt_network", "q9_shared_qnames",
+                                  "q26_same_basename", "opt_chr", "q16_tie_glue", "q22_unphased_blocks"])
+def test_cli_writes_reference_identical_files(engine, tmp_path, case):
+    c, got = _run_cli(engine, case, tmp_path)
     bad = compare.diff_outputs(c["ref"], got)
     assert not bad, "\n".join(bad)
 
 
-def test_cli_fatal_errors_exit_1(hostsim, tmp_path, capsys):
+def test_cli_fatal_errors_exit_1(engine, tmp_path, capsys):
     c = G.load_case("quirks")
     base = ["--vcf", c["vcf"], "--bam", c["sams"][0], "--mapq", "255", "--baseq", "10", "--paired_end", "1", "--o", str(tmp_path / "x")]
     for extra, msg in ((["--sample", "NOPE"], "Sample 'NOPE' not found"),
@@ -44,7 +46,7 @@ def test_cli_fatal_errors_exit_1(hostsim, tmp_path, capsys):
                        (["--sample", "S1", "--blacklist", "x.bed"], "File: x.bed not found"),
                        (["--sample", "S1", "--process_slow", "1"], "not supported")):
         with pytest.raises(SystemExit) as e:
-            cli.run(cli.build_parser().parse_args(base + extra), engine=hostsim)
+            cli.run(cli.build_parser().parse_args(base + extra), engine=engine)
         assert e.value.code == 1
         assert "FATAL ERROR: " in capsys.readouterr().out
 
@@ -90,7 +92,7 @@ def test_bgzf_roundtrip_and_gzip_compat(tmp_path):
 
 
 @pytest.mark.parametrize("case", ["quirks", "rna_small", "indels", "fuzz_indels"])
-def test_read_variant_map_seam_writes_the_reference_tsv(hostsim, tmp_path, monkeypatch, case):
+def test_read_variant_map_seam_writes_the_reference_tsv(engine, tmp_path, monkeypatch, case):
     """Seam S1: do_read_variant_map(variant_table, baseq, o, splice, isize_cutoff) with SAM text on stdin
     produces byte for byte the TSV of the reference mapper (committed golden)."""
     import io
@@ -112,7 +114,7 @@ def test_read_variant_map_seam_writes_the_reference_tsv(hostsim, tmp_path, monke
                 continue
         lines.append(ln)
     monkeypatch.setattr("sys.stdin", io.StringIO("".join(lines)))
-    rvm.set_engine(hostsim)
+    rvm.set_engine(engine)
     out = tmp_path / "out.tsv"
     rvm.do_read_variant_map(str(table), 10, str(out), 1, 0.0)
     assert open(out).read() == c["mapper"][c["meta"]["bams"][0]]
@@ -156,15 +158,15 @@ def test_native_reader_equals_python_readers(tmp_path):
                 assert fd.names == ref_batch.qnames
 
 
-def test_cli_empty_bam_is_the_reference_fatal_error(hostsim, tmp_path, capsys):
+def test_cli_empty_bam_is_the_reference_fatal_error(engine, tmp_path, capsys):
     c = G.load_case("rna_small")
     empty = str(tmp_path / "empty.bam")
     open(empty, "w").writelines(l for l in open(c["sams"][0]) if l[0] == "@")
     base = ["--vcf", c["vcf"], "--sample", "S1", "--mapq", "255", "--baseq", "10", "--paired_end", "1", "--o", str(tmp_path / "x")]
     with pytest.raises(SystemExit) as e:
-        cli.run(cli.build_parser().parse_args(base + ["--bam", empty]), engine=hostsim)
+        cli.run(cli.build_parser().parse_args(base + ["--bam", empty]), engine=engine)
     assert e.value.code == 1 and "No reads could be matched to variants" in capsys.readouterr().out
-    cli.run(cli.build_parser().parse_args(base + ["--bam", empty + "," + c["sams"][0]]), engine=hostsim)   # an empty BAM beside a real one
+    cli.run(cli.build_parser().parse_args(base + ["--bam", empty + "," + c["sams"][0]]), engine=engine)   # an empty BAM beside a real one
 
 
 @pytest.mark.parametrize("csi", [False, True])
@@ -197,9 +199,9 @@ def test_tabix_index_finds_exactly_the_overlapping_records(tmp_path, csi):
         assert tabix.query(path, idx, chrom, b, e) == exp
 
 
-def test_cli_writes_a_tabix_index_for_its_vcf(hostsim, tmp_path):
+def test_cli_writes_a_tabix_index_for_its_vcf(engine, tmp_path):
     from phaser_b200 import tabix
-    c, got = _run_cli(hostsim, "rna_two_bams", tmp_path)
+    c, got = _run_cli(engine, "rna_two_bams", tmp_path)
     o = str(tmp_path / "out")
     idx = tabix.read_index(o + ".vcf.gz.tbi")
     body = [l for l in got["vcf"].splitlines(keepends=True) if not l.startswith("#")]
@@ -235,10 +237,10 @@ def test_vectorised_index_builder_equals_record_by_record():
         assert A.tbi_bytes() == B.tbi_bytes() and A.csi_bytes() == B.csi_bytes()
 
 
-def test_cli_with_the_packed_transport_form(hostsim, tmp_path, monkeypatch):
+def test_cli_with_the_packed_transport_form(engine, tmp_path, monkeypatch):
     """PHZ_PACK=1: the command line sends the BAMs through pack_reads / phz_map_reads_packed; same files."""
     monkeypatch.setenv("PHZ_PACK", "1")
-    c, got = _run_cli(hostsim, "rna_two_bams", tmp_path)
+    c, got = _run_cli(engine, "rna_two_bams", tmp_path)
     bad = compare.diff_outputs(c["ref"], got)
     assert not bad, "\n".join(bad)
 

@@ -52,18 +52,18 @@ def test_hostsim_matches_reference_gene_ae(hostsim, name):
     assert pg.canon(ga.run_text(hostsim, open(hc).read(), open(bed).read(), **kw)) == pg.canon(ref)
 
 
-def test_gene_ae_cli_writes_the_reference_file(hostsim, tmp_path, capsys):
+def test_gene_ae_cli_writes_the_reference_file(engine, tmp_path, capsys):
     hc, bed, ref, kw, args = _load("two_bams_maf_cov")
     o = str(tmp_path / "ae.txt")
-    ga.run(ga.build_parser().parse_args(["--haplotypic_counts", hc, "--features", bed, "--o", o] + args), engine=hostsim)
+    ga.run(ga.build_parser().parse_args(["--haplotypic_counts", hc, "--features", bed, "--o", o] + args), engine=engine)
     assert pg.canon(open(o).read()) == pg.canon(ref)
     with pytest.raises(SystemExit) as e:
         ga.run(ga.build_parser().parse_args(["--haplotypic_counts", hc, "--features", bed, "--o", o, "--min_haplo_maf", "0.7"]),
-               engine=hostsim)
+               engine=engine)
     assert e.value.code == 1
     with pytest.raises(SystemExit) as e:        # wrong separator: the reference's ERROR + exit 1 (:181-184)
         ga.run(ga.build_parser().parse_args(["--haplotypic_counts", hc, "--features", bed, "--o", o, "--id_separator", "-"]),
-               engine=hostsim)
+               engine=engine)
     assert e.value.code == 1
 
 

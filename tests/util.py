@@ -60,10 +60,11 @@ def bam_display_names(paths):
 
 
 def load_inputs(vcf_gz, sams, sample="S1", mapq="255", paired_end="1", remove_dups=1, pass_only=1, id_separator="_",
-                gw_phase_method=0, blacklist="", haplo_count_blacklist="", include_indels=0):
+                gw_phase_method=0, blacklist="", haplo_count_blacklist="", include_indels=0, chr=""):
     col = vcfio.sample_column_map(vcf_gz)[sample]
     vt, st = vcfio.parse_vcf(vcf_gz, col, pass_only=pass_only, id_separator=id_separator, gw_phase_method=gw_phase_method,
-                             blacklist=blacklist, haplo_count_blacklist=haplo_count_blacklist, include_indels=include_indels)
+                             blacklist=blacklist, haplo_count_blacklist=haplo_count_blacklist, include_indels=include_indels,
+                             chrom_of_interest=chr)
     fd = samio.FragmentDictionary()
     mq = [int(x) for x in str(mapq).split(",")]; pe = [int(x) for x in str(paired_end).split(",")]
     if len(mq) == 1:
@@ -78,9 +79,9 @@ def product_outputs(engine, vcf_gz, sams, sample="S1", mapq="255", paired_end="1
                     as_q_cutoff=0.05, cc_threshold=0.01, exclude=(), isize=(0.0,), baseq=10, unphased_vars=1,
                     gw_phase_vcf=0, gw_phase_method=0, gw_phase_vcf_min_confidence=0.90, unique_ids=0, pass_only=1,
                     remove_dups=1, id_separator="_", blacklist="", haplo_count_blacklist="", include_indels=0,
-                    output_read_ids=0, output_network=""):
+                    output_read_ids=0, output_network="", chr=""):
     vt, st, batches, col, fd = load_inputs(vcf_gz, sams, sample, mapq, paired_end, remove_dups, pass_only, id_separator,
-                                           gw_phase_method, blacklist, haplo_count_blacklist, include_indels)
+                                           gw_phase_method, blacklist, haplo_count_blacklist, include_indels, chr)
     P = pipeline.PhaseParams(baseq=baseq, isize=list(isize), as_q_cutoff=as_q_cutoff, cc_threshold=cc_threshold,
                              max_block_size=max_block_size, haplo_count_bam_exclude=list(exclude),
                              want_read_ids=(output_read_ids == 1), want_kept_tuples=(output_network != ""))
@@ -93,7 +94,7 @@ def product_outputs(engine, vcf_gz, sams, sample="S1", mapq="255", paired_end="1
     hp, hc, cfg = o.block_tables()
     with gzip.open(vcf_gz, "rt") as f:
         vcf_text, _, _ = o.vcf_text(f.readlines(), col, id_separator=id_separator, gw_phase_vcf=gw_phase_vcf,
-                                    min_conf=gw_phase_vcf_min_confidence)
+                                    min_conf=gw_phase_vcf_min_confidence, chrom_of_interest=chr)
     out = dict(allelic_counts=ac, allele_config=cfg, haplotypes=hp, haplotypic_counts=hc, variant_connections=vc, vcf=vcf_text)
     if o.network is not None:
         out["network_links"], out["network_nodes"] = o.network
@@ -102,9 +103,10 @@ def product_outputs(engine, vcf_gz, sams, sample="S1", mapq="255", paired_end="1
 
 def oracle_outputs(vcf_gz, sams, sample="S1", mapq="255", paired_end="1", pass_only=1, remove_dups=1, exclude=None,
                    blacklist="", haplo_count_blacklist="", include_indels=0, **kw):
+    chrom = kw.pop("chr", "")
     vt, st, batches, col, fd = load_inputs(vcf_gz, sams, sample, mapq, paired_end, remove_dups, pass_only,
                                            kw.get("id_separator", "_"), kw.get("gw_phase_method", 0), blacklist,
-                                           haplo_count_blacklist, include_indels)
+                                           haplo_count_blacklist, include_indels, chrom)
     if exclude is not None:
         kw["haplo_count_bam_exclude"] = list(exclude)
     if kw.get("output_read_ids", 0) == 1:
@@ -112,7 +114,7 @@ def oracle_outputs(vcf_gz, sams, sample="S1", mapq="255", paired_end="1", pass_o
     P = port.Params(bam_names=bam_display_names(sams), **kw)
     res = port.run(vt, batches, P)
     with gzip.open(vcf_gz, "rt") as f:
-        vcf_text, _, _ = port.write_vcf_text(res, vt, f.readlines(), col, P)
+        vcf_text, _, _ = port.write_vcf_text(res, vt, f.readlines(), col, P, chrom_of_interest=chrom)
     out = dict(allelic_counts=res.allelic_counts, allele_config=res.allele_config, haplotypes=res.haplotypes,
                haplotypic_counts=res.haplotypic_counts, variant_connections=res.variant_connections, vcf=vcf_text)
     if hasattr(res, "network_links"):
