@@ -426,6 +426,8 @@ int phz_set_option(phz_ctx* ctx, const char* name, int64_t value) {
   else if (n == "two_pass_read_lists") ctx->p.two_pass_read_lists = (int)value;
   else if (n == "wide_pair_keys") ctx->p.wide_pair_keys = (int)value;
   else if (n == "window_agg") ctx->p.window_agg = (int)value;
+  else if (n == "graph_mode") ctx->p.graph_mode = (int)value;
+  else if (n == "pair_table_slots") { u64 s = 16; while (s < (u64)value) s <<= 1; ctx->p.pair_table_slots = s; }
   else if (n == "frag_run_limit") ctx->p.frag_run_limit = value < 1 ? 1 : value;
   else throw PhzError("unknown option: " + n);
   PHZ_CATCH

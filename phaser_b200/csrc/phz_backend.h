@@ -34,6 +34,7 @@ PHZ_HD uint32_t atomic_max(uint32_t* p, uint32_t v) { return atomicMax(p, v); }
 PHZ_HD uint32_t atomic_or(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
 PHZ_HD uint32_t atomic_and(uint32_t* p, uint32_t v) { return atomicAnd(p, v); }
 PHZ_HD uint32_t atomic_cas(uint32_t* p, uint32_t cmp, uint32_t v) { return atomicCAS(p, cmp, v); }
+PHZ_HD unsigned long long atomic_cas(unsigned long long* p, unsigned long long cmp, unsigned long long v) { return atomicCAS(p, cmp, v); }
 PHZ_HD uint32_t load_volatile(const uint32_t* p) { return *((const volatile uint32_t*)p); }
 PHZ_HD unsigned long long load_volatile(const unsigned long long* p) { return *((const volatile unsigned long long*)p); }
 #else
@@ -43,6 +44,7 @@ template <class T> inline T atomic_max(T* p, T v) { T o = *p; if (v > o) *p = v;
 inline uint32_t atomic_or(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
 inline uint32_t atomic_and(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o & v; return o; }
 inline uint32_t atomic_cas(uint32_t* p, uint32_t cmp, uint32_t v) { uint32_t o = *p; if (o == cmp) *p = v; return o; }
+inline unsigned long long atomic_cas(unsigned long long* p, unsigned long long cmp, unsigned long long v) { unsigned long long o = *p; if (o == cmp) *p = v; return o; }
 inline uint32_t load_volatile(const uint32_t* p) { return *p; }
 inline unsigned long long load_volatile(const unsigned long long* p) { return *p; }
 #endif

@@ -1,0 +1,253 @@
+// K2 graph stage, fragment-table form (graph_mode 1, the default).
+//
+// Replaces phaser.py:1287-1328, 558-581 (tuples -> per-variant lists, Q9 effective BAM), :636-640 (unique read sets),
+// :1265-1285 (connectivity map / insertion order), :667-678 (pair enumeration), :1594-1642 (3x3 co-occurrence cells).
+//
+// Fragment ids are dense (one per distinct QNAME, numbered by first appearance in the coordinate-sorted input), so
+// "group the tuples by fragment" needs no sort: a counting pass ranks every tuple inside its fragment, a scan over
+// the fragment table gives each fragment its slot range, a scatter drops (variant << 32 | tuple) keys there.  One
+// logical thread then owns one fragment: it sorts its few keys in place, folds them into (variant, BAM) entries,
+// and -- with everything of the fragment at hand -- adds to the per-variant counters, to the insertion ranks and to
+// the pair table.  Consecutive fragments sit on the same locus and expression is heavy-tailed, so a CTA first sums
+// in shared memory (a window of variant indices for the per-variant counters, a small hash table for the pairs) and
+// flushes each touched slot once; the run-wide pair table is an open-addressing hash in global memory (L2-resident:
+// a few 100 k distinct pairs) whose non-empty slots are compacted and sorted by (va, vb) into the edge table.
+// No tuple is ever sorted globally, no pair instance is ever written to HBM.
+#pragma once
+#include "phz_backend.h"
+
+namespace phz {
+
+constexpr u64 PAIR_EMPTY = ~0ull;
+constexpr int PAIR_CELLS = 10;            // 9 co-occurrence cells n[x][y] at x*3+y, [9] = eligible fragments
+constexpr int FRAG_CTA = 256;             // threads per CTA of the fragment kernel
+constexpr int FRAG_PER_THREAD = 4;        // consecutive fragment ids per CTA = FRAG_CTA * FRAG_PER_THREAD
+constexpr int FRAG_W = 256;               // variant indices per shared-memory window
+constexpr int FRAG_HS = 512;              // slots of the CTA's pair hash
+
+PHZ_HD u32 pair_hash(u64 k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 29;
+  return (u32)k;
+}
+
+struct PairTable {
+  u64* keys;          // [S], PAIR_EMPTY = free
+  u32* vals;          // [S * PAIR_CELLS]
+  u32 mask;           // S - 1
+  u32* flags;         // [0] bit 0: table full (the host grows it and runs the stage again)
+};
+
+// slot of `key`, inserting it when absent; -1 when the probe sequence is exhausted
+PHZ_HD int pair_slot(const PairTable& pt, u64 key) {
+  u32 h = pair_hash(key) & pt.mask;
+  for (int probe = 0; probe < 512; ++probe) {
+    u64 k = load_volatile((const unsigned long long*)&pt.keys[h]);
+    if (k == key) return (int)h;
+    if (k == PAIR_EMPTY) {
+      u64 old = atomic_cas((unsigned long long*)&pt.keys[h], (unsigned long long)PAIR_EMPTY, (unsigned long long)key);
+      if (old == PAIR_EMPTY || old == key) return (int)h;
+    }
+    h = (h + 1) & pt.mask;
+  }
+  atomic_or(&pt.flags[0], 1u);
+  return -1;
+}
+
+struct FragCtx {
+  const u32* vc;      // contig of every het site
+  const u8* gc;       // class | bam << 2 per kept tuple
+  u64 excl_mask;      // BAMs left out of the haplotypic counts (phaser.py:1320, Q25)
+  u64* vrank;         // per site: insertion key into the overlap dict (phaser.py:1271-1283), min wins
+  const u32* abort;   // bit 3 set by the ranking pass: a fragment does not fit the stage, its slots hold nothing valid
+};
+
+// One fragment.  k[0..n): keys (variant << 32 | tuple index) in any order, info[0..n): scratch.  On return
+// k[0..ne) / info[0..ne) hold the fragment's (variant, BAM) entries sorted by (variant, BAM):
+// k = variant << 32 | first tuple with a reference / alternative call (NONE32 if none), info = bam << 3 | class mask.
+// Returns ne; adds groups / pairs to ng / np.
+template <class Sink>
+PHZ_HD u32 process_fragment(const FragCtx& c, u64* k, uint16_t* info, u32 n, Sink& sink, u32& ng, u32& np) {
+  // tuples arrive nearly sorted (record order = position order): insertion sort, stable because keys are unique
+  for (u32 j = 1; j < n; ++j) {
+    u64 key = k[j]; u32 m = j;
+    while (m > 0 && k[m - 1] > key) { k[m] = k[m - 1]; --m; }
+    k[m] = key;
+  }
+  // (variant, BAM) entries, in place: tuple order inside a variant is BAM-major (commit order)
+  u32 ne = 0, cur_v = 0xFFFFFFFFu, cur_b = 0xFFFFFFFFu;
+  for (u32 i = 0; i < n; ++i) {
+    const u64 key = k[i]; const u32 v = (u32)(key >> 32), t = (u32)key;
+    const u32 cb = c.gc[t]; const u32 cls = cb & 3, bam = cb >> 2;
+    if (v != cur_v || bam != cur_b) { k[ne] = ((u64)v << 32) | 0xFFFFFFFFu; info[ne] = (uint16_t)(bam << 3); ++ne; cur_v = v; cur_b = bam; }
+    info[ne - 1] = (uint16_t)(info[ne - 1] | (1u << cls));
+    if (cls < 2 && (u32)k[ne - 1] == 0xFFFFFFFFu) k[ne - 1] = ((u64)v << 32) | t;
+  }
+  // unique-set sizes (phaser.py:636-640) and per-BAM allele counts (haplo_reads, phaser.py:1320-1322)
+  for (u32 j = 0; j < ne;) {
+    const u32 v = (u32)(k[j] >> 32); u32 mask = 0, j1 = j;
+    for (; j1 < ne && (u32)(k[j1] >> 32) == v; ++j1) mask |= info[j1] & 7u;
+    for (int x = 0; x < 3; ++x) if ((mask >> x) & 1) sink.set_size(v, x);
+    for (u32 i = j; i < j1; ++i) {
+      const u32 bam = info[i] >> 3;
+      if ((c.excl_mask >> bam) & 1) continue;
+      if (info[i] & 1) sink.bam_count(v, bam, 0);
+      if (info[i] & 2) sink.bam_count(v, bam, 1);
+    }
+    j = j1;
+  }
+  // (fragment, contig) groups: effective BAM (Q9), insertion ranks, pairs
+  for (u32 g0 = 0; g0 < ne;) {
+    const u32 cg = c.vc[(u32)(k[g0] >> 32)]; u32 g1 = g0 + 1;
+    while (g1 < ne && c.vc[(u32)(k[g1] >> 32)] == cg) ++g1;
+    ++ng;
+    if (g1 - g0 >= 2) {
+      int effbam = -1; u32 first_t = 0xFFFFFFFFu;
+      for (u32 j = g0; j < g1; ++j)
+        if (info[j] & 3) { const int b = (int)(info[j] >> 3); if (b > effbam) effbam = b; const u32 t = (u32)k[j]; if (t < first_t) first_t = t; }
+      u32 kk = 0, kelig = 0;
+      for (u32 j = g0; j < g1;) {
+        const u32 v = (u32)(k[j] >> 32); bool elig = false; u32 jj = j;
+        for (; jj < g1 && (u32)(k[jj] >> 32) == v; ++jj) if ((info[jj] & 3) && (int)(info[jj] >> 3) == effbam) elig = true;
+        ++kk; if (elig) ++kelig;
+        j = jj;
+      }
+      np += kk * (kk - 1) / 2;
+      if (kelig >= 2)         // insertion order of dict_variant_overlap, phaser.py:1271-1283
+        for (u32 j = g0; j < g1; ++j)
+          if ((info[j] & 3) && (int)(info[j] >> 3) == effbam) {
+            const unsigned long long key = ((unsigned long long)first_t << 32) | (u32)k[j];
+            unsigned long long* slot = (unsigned long long*)&c.vrank[(u32)(k[j] >> 32)];
+            if (key < load_volatile(slot)) atomic_min(slot, key);          // the minimum settles early
+          }
+      if (kk >= 2)
+        for (u32 a = g0; a < g1;) {
+          const u32 va = (u32)(k[a] >> 32); u32 ma = 0; bool ea = false; u32 a1 = a;
+          for (; a1 < g1 && (u32)(k[a1] >> 32) == va; ++a1) { ma |= info[a1] & 7u; if ((info[a1] & 3) && (int)(info[a1] >> 3) == effbam) ea = true; }
+          for (u32 b = a1; b < g1;) {
+            const u32 vb = (u32)(k[b] >> 32); u32 mb = 0; bool eb = false; u32 b1 = b;
+            for (; b1 < g1 && (u32)(k[b1] >> 32) == vb; ++b1) { mb |= info[b1] & 7u; if ((info[b1] & 3) && (int)(info[b1] >> 3) == effbam) eb = true; }
+            u32 cells = 0;
+            for (int x = 0; x < 3; ++x) for (int y = 0; y < 3; ++y) if (((ma >> x) & 1) && ((mb >> y) & 1)) cells |= 1u << (x * 3 + y);
+            if (ea && eb) cells |= 1u << 9;
+            sink.pair(((u64)va << 32) | vb, cells);
+            b = b1;
+          }
+          a = a1;
+        }
+    }
+    g0 = g1;
+  }
+  return ne;
+}
+
+// sink of the host simulation (and of fragments the device kernel cannot stage): straight to the run-wide arrays
+struct DirectSink {
+  u32* sz; u32* vbc; int nb; PairTable pt;
+  PHZ_HD void set_size(u32 v, int x) { atomic_add(&sz[(int64_t)v * 3 + x], 1u); }
+  PHZ_HD void bam_count(u32 v, u32 bam, int a) { atomic_add(&vbc[((int64_t)v * nb + bam) * 2 + a], 1u); }
+  PHZ_HD void pair(u64 key, u32 cells) {
+    const int s = pair_slot(pt, key);
+    if (s < 0) return;
+    for (int c = 0; c < PAIR_CELLS; ++c) if ((cells >> c) & 1) atomic_add(&pt.vals[(int64_t)s * PAIR_CELLS + c], 1u);
+  }
+};
+
+#ifdef __CUDACC__
+struct CtaSink {
+  u32* s_sz; u32* s_vb; u32 base; int nb; u32* sz; u32* vbc;
+  unsigned long long* h_keys; u32* h_vals;       // shared: FRAG_HS keys, FRAG_HS * 5 words (two 16-bit counts per word)
+  PairTable pt;
+  __device__ __forceinline__ void set_size(u32 v, int x) {
+    const u32 d = v - base;
+    if (d < (u32)FRAG_W) atomicAdd(&s_sz[d * 3 + x], 1u); else atomicAdd(&sz[(int64_t)v * 3 + x], 1u);
+  }
+  __device__ __forceinline__ void bam_count(u32 v, u32 bam, int a) {
+    const u32 d = v - base;
+    if (d < (u32)FRAG_W && nb <= 4) atomicAdd(&s_vb[(d * nb + bam) * 2 + a], 1u);
+    else atomicAdd(&vbc[((int64_t)v * nb + bam) * 2 + a], 1u);
+  }
+  __device__ __forceinline__ void pair(u64 key, u32 cells) {
+    u32 h = pair_hash(key) & (FRAG_HS - 1);
+    int found = -1;
+    for (int probe = 0; probe < 8; ++probe) {
+      const unsigned long long kk = *(volatile unsigned long long*)&h_keys[h];
+      if (kk == key) { found = (int)h; break; }
+      if (kk == PAIR_EMPTY) {
+        const unsigned long long old = atomicCAS(&h_keys[h], (unsigned long long)PAIR_EMPTY, (unsigned long long)key);
+        if (old == PAIR_EMPTY || old == key) { found = (int)h; break; }
+      }
+      h = (h + 1) & (FRAG_HS - 1);
+    }
+    if (found >= 0) {
+      for (int c = 0; c < PAIR_CELLS; ++c) if ((cells >> c) & 1) atomicAdd(&h_vals[found * 5 + (c >> 1)], 1u << (16 * (c & 1)));
+    } else {        // the CTA's table is crowded here: straight to the run-wide table
+      const int s = pair_slot(pt, key);
+      if (s >= 0) for (int c = 0; c < PAIR_CELLS; ++c) if ((cells >> c) & 1) atomicAdd(&pt.vals[(int64_t)s * PAIR_CELLS + c], 1u);
+    }
+  }
+};
+
+// f_off[f] .. f_off[f + 1]: slot range of fragment f in fk / info.  f_ne[f] receives its number of entries.
+// cnt3: [0] entries, [1] groups, [2] pairs (64-bit sums).
+__global__ void __launch_bounds__(FRAG_CTA, 4) fragment_kernel(FragCtx c, const u32* __restrict__ f_off, int64_t n_frag,
+                                                            u64* __restrict__ fk, uint16_t* __restrict__ info,
+                                                            u32* __restrict__ f_ne, int nb, u32* __restrict__ sz,
+                                                            u32* __restrict__ vbc, PairTable pt,
+                                                            unsigned long long* __restrict__ cnt3) {
+  __shared__ u32 s_sz[FRAG_W * 3];
+  __shared__ u32 s_vb[FRAG_W * 2 * 4];
+  __shared__ unsigned long long h_keys[FRAG_HS];
+  __shared__ u32 h_vals[FRAG_HS * 5];
+  __shared__ u32 s_base;
+  __shared__ unsigned long long s_cnt[3];
+  const int tid = threadIdx.x;
+  const int64_t f0 = (int64_t)blockIdx.x * (FRAG_CTA * FRAG_PER_THREAD);
+  const int64_t f1 = (f0 + FRAG_CTA * FRAG_PER_THREAD < n_frag) ? f0 + FRAG_CTA * FRAG_PER_THREAD : n_frag;
+  const u32 o_first = f_off[f0], o_last = f_off[f1];
+  if (*c.abort & 8u) return;        // the host takes the sort-based stage instead
+  if (o_first == o_last) {          // no tuple in this range of fragments (most reads touch no het site)
+    for (int64_t f = f0 + tid; f < f1; f += FRAG_CTA) f_ne[f] = 0;
+    return;
+  }
+  for (int i = tid; i < FRAG_W * 3; i += FRAG_CTA) s_sz[i] = 0;
+  for (int i = tid; i < FRAG_W * 2 * 4; i += FRAG_CTA) s_vb[i] = 0;
+  for (int i = tid; i < FRAG_HS; i += FRAG_CTA) h_keys[i] = PAIR_EMPTY;
+  for (int i = tid; i < FRAG_HS * 5; i += FRAG_CTA) h_vals[i] = 0;
+  if (tid == 0) {
+    const u32 v0 = (u32)(fk[o_first] >> 32);
+    s_base = v0 > FRAG_W / 4 ? v0 - FRAG_W / 4 : 0;
+    s_cnt[0] = s_cnt[1] = s_cnt[2] = 0;
+  }
+  __syncthreads();
+  CtaSink sink{s_sz, s_vb, s_base, nb, sz, vbc, h_keys, h_vals, pt};
+  u32 ne_sum = 0, ng = 0, np = 0;
+  for (int64_t f = f0 + tid; f < f1; f += FRAG_CTA) {
+    const u32 o0 = f_off[f], n = f_off[f + 1] - o0;
+    u32 ne = 0;
+    if (n) ne = process_fragment(c, fk + o0, info + o0, n, sink, ng, np);
+    f_ne[f] = ne; ne_sum += ne;
+  }
+  if (ne_sum) { atomicAdd(&s_cnt[0], (unsigned long long)ne_sum); atomicAdd(&s_cnt[1], (unsigned long long)ng); }
+  if (np) atomicAdd(&s_cnt[2], (unsigned long long)np);
+  __syncthreads();
+  const u32 base = s_base;
+  for (int i = tid; i < FRAG_W; i += FRAG_CTA) {
+    const int64_t v = (int64_t)base + i;
+    for (int x = 0; x < 3; ++x) if (s_sz[i * 3 + x]) atomicAdd(&sz[v * 3 + x], s_sz[i * 3 + x]);
+    if (nb <= 4) for (int a = 0; a < nb * 2; ++a) if (s_vb[i * nb * 2 + a]) atomicAdd(&vbc[v * nb * 2 + a], s_vb[i * nb * 2 + a]);
+  }
+  for (int i = tid; i < FRAG_HS; i += FRAG_CTA) {
+    const unsigned long long key = h_keys[i];
+    if (key == PAIR_EMPTY) continue;
+    const int s = pair_slot(pt, key);
+    if (s < 0) continue;
+    for (int cidx = 0; cidx < PAIR_CELLS; ++cidx) {
+      const u32 cv = (h_vals[i * 5 + (cidx >> 1)] >> (16 * (cidx & 1))) & 0xFFFFu;
+      if (cv) atomicAdd(&pt.vals[(int64_t)s * PAIR_CELLS + cidx], cv);
+    }
+  }
+  if (tid < 3 && s_cnt[tid]) atomicAdd(&cnt3[tid], s_cnt[tid]);
+}
+#endif
+
+}  // namespace phz

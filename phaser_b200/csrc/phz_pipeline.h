@@ -13,6 +13,7 @@
 #include <type_traits>
 #include "phz_map_core.h"
 #include "phz_phase_core.h"
+#include "phz_graph.h"
 
 #ifdef __CUDACC__
 #define PHZ_LAMBDA [=] __host__ __device__
@@ -569,6 +570,10 @@ struct Pipeline {
   int64_t NX = 0, E = 0; u32 max_tot = 0; int64_t NBT = 0; u32 big_total_thr = 2048;
   int lazy_canonical = 1;           // 1: the tile kernel's output stays in arrival order until somebody needs canonical order
   bool tile_order = false, canonical_valid = true; int64_t tiles_cur = 0;
+  int graph_mode = 1;               // 1: fragment-table graph stage (phz_graph.h), 0: sort-based stage (A/B switch and fallback)
+  bool frag_entries = false;        // which form of the (fragment, variant, BAM) entries the last build_graph left behind
+  Buf<B, u32> f_cnt, f_off; Buf<B, uint16_t> t_rank, f_info; Buf<B, u64> f_key, pt_keys, pt_cnt3; Buf<B, u32> pt_vals, pt_flags, pt_slot;
+  int64_t n_frag_cur = 0; u64 pair_table_slots = 1ull << 20; int64_t pair_table_grown = 0;
   int window_agg = 1;               // 1: shared-memory window kernels for the per-variant counters, 0: warp-aggregated global atomics
   int64_t frag_run_limit = 1024; int64_t n_runs_resorted = 0; bool full_sort_fallback = false;
   // ------------------------------------------------------------------ blocks
@@ -614,6 +619,8 @@ struct Pipeline {
     fb_tot.bind(b); fb_cnt.bind(b); fb_bcnt.bind(b);
     rl_flag.bind(b); rl_scan.bind(b); rl_k32.bind(b); rl_k32b.bind(b); rl_t.bind(b); rl_t2.bind(b); rl_k64.bind(b);
     rl_k64b.bind(b); rl_frag.bind(b); rl_var.bind(b); rl_row.bind(b);
+    f_cnt.bind(b); f_off.bind(b); t_rank.bind(b); f_info.bind(b); f_key.bind(b); pt_keys.bind(b); pt_cnt3.bind(b); pt_vals.bind(b);
+    pt_flags.bind(b); pt_slot.bind(b);
   }
 
   u32 fetch_u32(const u32* p) { u32 v = 0; be.d2h(&v, p, sizeof(u32)); return v; }
@@ -1012,9 +1019,124 @@ struct Pipeline {
     be.stage("graph.variant_lists.end");
   }
 
+  // ------------------------------------------------------------------ fragment-table graph stage (phz_graph.h)
+  // Returns false when the input does not fit the stage (a fragment with more than 65535 tuples, more than 2^32 - 1
+  // fragment ids): the caller then takes the sort-based stage.
+  bool build_graph_frag(u64 n_frag, u64 excl_mask) {
+    const int64_t n = n_tuples; const int64_t Vn = V; const int nb = n_bams > 0 ? n_bams : 1;
+    if (n_frag >= 0xFFFFFFF0ull) return false;
+    const int64_t F = (int64_t)(n_frag > 0 ? n_frag : 1);
+    const u32* gf = g_frag.p; const u32* gv = g_var.p; const u8* gc = g_cb.p; const u32* vc = vcontig.p;
+    be.stage("graph.frag_rank");
+    u32* sc = scalars.ensure(8); be.memset0(sc, 8 * sizeof(u32));
+    u32* fc = f_cnt.ensure(F + 1); be.memset0(fc, (F + 1) * sizeof(u32));
+    u32* fo = f_off.ensure(F + 2);
+    uint16_t* rk = t_rank.ensure(n);
+    // rank of every tuple inside its fragment (arrival order: the per-fragment sort below makes the result canonical)
+    be.for_each(n, PHZ_LAMBDA(int64_t t) {
+      const u32 r = atomic_add(&fc[gf[t]], 1u);
+      if (r >= 65535u) { atomic_or(&sc[1], 8u); rk[t] = 65535; } else rk[t] = (uint16_t)r;
+    });
+    be.exclusive_scan_u32(fc, fo, F);
+    u64* fk = f_key.ensure(n); uint16_t* fi = f_info.ensure(n);
+    u32* sz = setsize.ensure(Vn * 3); u32* vbc = vb_cnt.ensure(Vn * nb * 2); u64* vr = vrank.ensure(Vn);
+    u64* c3 = pt_cnt3.ensure(4);
+    u32 hsc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int attempt = 0;; ++attempt) {
+      const u64 S = pair_table_slots;
+      be.stage("graph.frag_scatter");
+      be.for_each(n, PHZ_LAMBDA(int64_t t) {
+        const u32 r = rk[t]; if (r == 65535u) return;
+        fk[fo[gf[t]] + r] = ((u64)gv[t] << 32) | (u64)(u32)t;
+      });
+      be.memset0(sz, Vn * 3 * sizeof(u32)); be.memset0(vbc, Vn * nb * 2 * sizeof(u32)); be.memset_ff(vr, Vn * sizeof(u64));
+      u64* pk = pt_keys.ensure(S); u32* pv = pt_vals.ensure(S * PAIR_CELLS); u32* pf = pt_flags.ensure(4);
+      be.memset_ff(pk, S * sizeof(u64)); be.memset0(pv, S * PAIR_CELLS * sizeof(u32)); be.memset0(pf, 4 * sizeof(u32));
+      be.memset0(c3, 4 * sizeof(u64));
+      PairTable pt{pk, pv, (u32)(S - 1), pf};
+      FragCtx fx{vc, gc, excl_mask, vr, sc + 1};
+      u32* fne = fc;                      // the counts are not needed any more: the slot becomes the entry count
+      be.stage("graph.fragments");
+#ifdef __CUDACC__
+      {
+        const int64_t per = (int64_t)FRAG_CTA * FRAG_PER_THREAD;
+        fragment_kernel<<<(unsigned)((F + per - 1) / per), FRAG_CTA, 0, be.stream>>>(fx, fo, F, fk, fi, fne, nb, sz, vbc, pt,
+                                                                                  (unsigned long long*)c3);
+        PHZ_CUDA(cudaGetLastError());
+        be.launches++;
+      }
+#else
+      {
+        DirectSink sink{sz, vbc, nb, pt};
+        u64 ne_sum = 0, ng_sum = 0, np_sum = 0;
+        for (int64_t f = 0; f < F && !(sc[1] & 8u); ++f) {
+          const u32 o0 = fo[f], cnt = fo[f + 1] - o0; u32 ng = 0, np = 0, ne = 0;
+          if (cnt) ne = process_fragment(fx, fk + o0, fi + o0, cnt, sink, ng, np);
+          fne[f] = ne; ne_sum += ne; ng_sum += ng; np_sum += np;
+        }
+        c3[0] = ne_sum; c3[1] = ng_sum; c3[2] = np_sum;
+        be.launches++;
+      }
+#endif
+      be.stage("graph.edge_table");
+      // ---- non-empty slots = distinct pairs; eligible ones (phaser.py:667-678) become edges, sorted by (va, vb)
+      u32* xf = x_flag.ensure(S + 1); u32* xs = x_scan.ensure(S + 2);
+      be.for_each((int64_t)S, PHZ_LAMBDA(int64_t h) {
+        const bool used = pk[h] != PAIR_EMPTY;
+        if (used) atomic_add(&pf[1], 1u);
+        xf[h] = (used && pv[h * PAIR_CELLS + 9]) ? 1u : 0u;
+      });
+      be.exclusive_scan_u32(xf, xs, (int64_t)S);
+      { const u32* xs_c = xs; int64_t ss = (int64_t)S;
+        be.for_each(1, PHZ_LAMBDA(int64_t) { pf[2] = xs_c[ss]; pf[3] = sc[1]; }); }
+      u32 h4[4] = {0, 0, 0, 0};
+      be.d2h(h4, pf, sizeof(h4));
+      if (h4[3] & 8u) return false;            // a fragment beyond the 16-bit rank: sort-based stage
+      if (h4[0] & 1u) {                        // pair table full: grow it and run the fragments again
+        if (attempt >= 8) throw PhzError("pair table keeps overflowing");
+        pair_table_slots *= 4; pair_table_grown++;
+        continue;
+      }
+      NX = h4[1]; E = h4[2];
+      if ((u64)NX * 2 > S) { pair_table_slots *= 2; }     // keep the load factor low for the next sample (no re-run needed now)
+      u64 h3[3] = {0, 0, 0};
+      be.d2h(h3, c3, sizeof(h3));
+      NE = (int64_t)h3[0]; NG = (int64_t)h3[1]; NP = (int64_t)h3[2];
+      // ---- edge table
+      u64* ek = d_key.ensure(E); u64* ek2 = d_key2.ensure(E); u32* es = pt_slot.ensure(2 * E + 2); u32* es2 = es + E + 1;
+      be.for_each((int64_t)S, PHZ_LAMBDA(int64_t h) { if (xf[h]) { ek[xs[h]] = pk[h]; es[xs[h]] = (u32)h; } });
+      be.sort_pairs(ek, ek2, es, es2, E, 0, 32 + vbits);
+      u32* ea_ = ed_a.ensure(E); u32* eb_ = ed_b.ensure(E); u32* esup = ed_sup.ensure(E); u32* etot = ed_tot.ensure(E);
+      u32* en9 = ed_n9.ensure(E * 9); u8* ecfg = ed_cfg.ensure(E); ed_keep.ensure(E);
+      be.memset0(sc, 8 * sizeof(u32));
+      u32* bt = big_tot.ensure(E); const u32 bthr = big_total_thr;
+      be.for_each(E, PHZ_LAMBDA(int64_t e) {
+        const u64 key = ek2[e]; const u32 h = es2[e];
+        u32 n9[9]; for (int c = 0; c < 9; ++c) n9[c] = pv[(int64_t)h * PAIR_CELLS + c];
+        ea_[e] = (u32)(key >> 32); eb_[e] = (u32)key;
+        for (int c = 0; c < 9; ++c) en9[e * 9 + c] = n9[c];
+        u32 cis = n9[0] + n9[4], trans = n9[3] + n9[1];          // n[x][y] at x*3+y
+        u32 other = n9[6] + n9[7] + n9[2] + n9[5] + n9[8];
+        u32 sup = cis > trans ? cis : trans, tot = cis + trans + other;
+        esup[e] = sup; etot[e] = tot;
+        ecfg[e] = (u8)(cis > trans ? EDGE_CIS : (cis < trans ? EDGE_TRANS : EDGE_TIE));
+        if (tot > load_volatile(&sc[0])) atomic_max(&sc[0], tot);
+        if (tot > bthr) bt[atomic_add(&sc[3], 1u)] = tot;
+      });
+      break;
+    }
+    if (E > 0) be.d2h(hsc, sc, 4 * sizeof(u32));
+    max_tot = hsc[0]; NBT = hsc[3];
+    n_frag_cur = F; frag_entries = true; n_runs_resorted = 0; full_sort_fallback = false;
+    be.stage("graph.end");
+    return true;
+  }
+
   void build_graph(u64 n_frag, u64 excl_mask) {
     if (!stats_done) { u64 tmp[2]; variant_stats(tmp); }
     stats_done = false;
+    if (graph_mode == 1 && build_graph_frag(n_frag, excl_mask)) return;
+    frag_entries = false;
     const int64_t n = n_tuples; const int64_t Vn = V; const int nb = n_bams > 0 ? n_bams : 1;
     const u32* gf = g_frag.p; const u32* gv = g_var.p; const u8* gc = g_cb.p; const u32* vc = vcontig.p;
     be.stage("graph.sort_tuples");
@@ -1488,8 +1610,34 @@ struct Pipeline {
     // ---- unique-fragment counts per final block x haplotype (all BAMs, and per counted BAM)
     u32* fc = fb_cnt.ensure(NF * 2); u32* fbc = fb_bcnt.ensure(NF * nb * 2);
     be.memset0(fc, NF * 2 * sizeof(u32)); be.memset0(fbc, NF * nb * 2 * sizeof(u32));
-    const u64* ek = e_key.p; const u8* eb = e_bam.p; const u32* em = e_mask.p; const u32* go = grp_off.p;
     const u8* vbl = vblack;
+    if (frag_entries) {
+      // entries as the fragment-table stage left them: fragment f owns f_key / f_info [f_off[f], f_off[f] + f_cnt[f])
+      const u32* fo = f_off.p; const u32* fne = f_cnt.p; const u64* fk = f_key.p; const uint16_t* fi = f_info.p;
+      be.for_each(n_frag_cur, PHZ_LAMBDA(int64_t fr) {
+        const u32 ne = fne[fr];
+        if (ne == 0) return;
+        const u32 j0 = fo[fr], j1 = j0 + ne;
+        for (u32 j = j0; j < j1; ++j) {
+          u32 v = (u32)(fk[j] >> 32); u32 f = vfin[v];
+          if (f == NONE32) continue;
+          const u32 mj = fi[j] & 7u, bj = fi[j] >> 3;
+          for (int h = 0; h < 2; ++h) {
+            if (!((mj >> (vh[v] ^ h)) & 1)) continue;
+            bool seen_any = false, seen_bam = false;
+            for (u32 i = j0; i < j; ++i) {
+              u32 w = (u32)(fk[i] >> 32);
+              if (vfin[w] != f || !(((fi[i] & 7u) >> (vh[w] ^ h)) & 1)) continue;
+              seen_any = true; if ((u32)(fi[i] >> 3) == bj && !(vbl && vbl[w])) seen_bam = true;
+            }
+            if (!seen_any) converged_inc(&fc[(int64_t)f * 2 + h]);
+            if (!seen_bam && !((excl_mask >> bj) & 1) && !(vbl && vbl[v]))
+              converged_inc(&fbc[((int64_t)f * nb + bj) * 2 + h]);
+          }
+        }
+      });
+    } else {
+    const u64* ek = e_key.p; const u8* eb = e_bam.p; const u32* em = e_mask.p; const u32* go = grp_off.p;
     be.for_each(NG, PHZ_LAMBDA(int64_t g) {
       u32 j0 = go[g], j1 = go[g + 1];
       for (u32 j = j0; j < j1; ++j) {
@@ -1510,6 +1658,7 @@ struct Pipeline {
         }
       }
     });
+    }
     u32 hsc8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     be.d2h(hsc8, sc, sizeof(hsc8));
     *err_out = (int)hsc8[1]; max_final_len = hsc8[6];

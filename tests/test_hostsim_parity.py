@@ -144,13 +144,14 @@ def test_fragment_sort_fixup_and_fallback_agree(hostsim, tmp_path):
     vcf, sams = util.make_case(tmp_path, 44, 400, 8000, n_bams=2, switch_per_base=0.02, insert_lo=60, insert_hi=200)
     vt, st, batches, col, fd = util.load_inputs(vcf, sams)
     P = pipeline.PhaseParams()
-    a = pipeline.run_path(hostsim, vt, [hostsim.upload_reads(b) for b in batches], P, n_fragments=len(fd.names))
-    assert a.counters["frag_runs_resorted"] > 0 and a.counters["full_sort_fallback"] == 0
-    hostsim.set_option("frag_run_limit", 1)
+    hostsim.set_option("graph_mode", 0)           # the sort-based stage (A/B switch and fallback of the fragment-table stage)
     try:
+        a = pipeline.run_path(hostsim, vt, [hostsim.upload_reads(b) for b in batches], P, n_fragments=len(fd.names))
+        assert a.counters["frag_runs_resorted"] > 0 and a.counters["full_sort_fallback"] == 0
+        hostsim.set_option("frag_run_limit", 1)
         b = pipeline.run_path(hostsim, vt, [hostsim.upload_reads(b) for b in batches], P, n_fragments=len(fd.names))
     finally:
-        hostsim.set_option("frag_run_limit", 1024)
+        hostsim.set_option("frag_run_limit", 1024); hostsim.set_option("graph_mode", 1)
     assert b.counters["full_sort_fallback"] == 1
     for k in a.arrays:
         assert np.array_equal(a.arrays[k], b.arrays[k]), k
@@ -240,11 +241,11 @@ def test_compact_pair_keys_equal_wide_ones(hostsim, tmp_path):
     P = pipeline.PhaseParams()
     out = []
     for wide in (0, 1):
-        hostsim.set_option("wide_pair_keys", wide)
+        hostsim.set_option("wide_pair_keys", wide); hostsim.set_option("graph_mode", 0)
         try:
             out.append(pipeline.run_path(hostsim, vt, [hostsim.upload_reads(b) for b in batches], P, n_fragments=len(fd.names)))
         finally:
-            hostsim.set_option("wide_pair_keys", 0)
+            hostsim.set_option("wide_pair_keys", 0); hostsim.set_option("graph_mode", 1)
     a, b = out
     assert a.counters == b.counters and a.counters["edges"] > 50
     for k in a.arrays:
@@ -268,3 +269,57 @@ def test_single_sort_read_lists_equal_two_pass(hostsim, tmp_path):
     assert a.counters == b.counters and a.counters["read_list_entries"] > 100
     for k in a.arrays:
         assert np.array_equal(a.arrays[k], b.arrays[k]), k
+
+
+def test_fragment_table_graph_equals_the_sort_based_graph(hostsim, tmp_path):
+    """graph_mode 1 (fragment table: rank, scan, scatter, one thread per fragment, pair hash) against graph_mode 0 (global
+    tuple sort, entry / group arrays, pair sort): identical result arrays and counters -- with the pair table started
+    tiny so that it overflows and is grown, and with three BAMs sharing read names."""
+    from phaser_b200 import pipeline
+    vcf, sams = util.make_case(tmp_path, 52, 500, 9000, n_bams=3, switch_per_base=0.02, insert_lo=60, insert_hi=220)
+    vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+    for b in batches[1:]:                    # the same fragment ids in every BAM: shared QNAMEs (Q9)
+        b.frag = (b.frag % np.uint32(len(batches[0].qnames))).astype(np.uint32)
+    P = pipeline.PhaseParams(haplo_count_bam_exclude=[1])
+    out = []
+    for mode, slots in ((1, 16), (1, 1 << 20), (0, 1 << 20)):
+        hostsim.set_option("graph_mode", mode); hostsim.set_option("pair_table_slots", slots)
+        try:
+            out.append(pipeline.run_path(hostsim, vt, [hostsim.upload_reads(b) for b in batches], P, n_fragments=len(fd.names)))
+        finally:
+            hostsim.set_option("graph_mode", 1); hostsim.set_option("pair_table_slots", 1 << 20)
+    a, b, c = out
+    assert a.counters["edges"] > 100
+    for x in (b, c):
+        for k in ("n_tuples", "entries", "groups", "pairs", "distinct_pairs", "edges", "dropped", "members", "final_blocks",
+                  "read_list_entries"):
+            assert a.counters[k] == x.counters[k], k
+        for k in a.arrays:
+            assert np.array_equal(a.arrays[k], x.arrays[k]), k
+
+
+def test_a_huge_fragment_takes_the_sort_based_graph(hostsim, tmp_path):
+    """More than 65535 tuples under ONE read name do not fit the 16-bit in-fragment rank: the stage falls back to the
+    sort-based graph (full-key sort), loudly in the counters, with the same arrays as asking for that stage outright."""
+    from phaser_b200 import pipeline
+    vcf, sams = util.make_case(tmp_path, 53, 600, 100000, n_bams=1, switch_per_base=0.0)
+    vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+    batches[0].frag = np.zeros_like(batches[0].frag)
+    P = pipeline.PhaseParams(max_block_size=0)
+    out = []
+    for mode in (1, 0):
+        hostsim.set_option("graph_mode", mode)
+        try:
+            hostsim.set_variants(vt)
+            for bi, rb in enumerate(batches):
+                hostsim.map_reads(hostsim.upload_reads(rb), 10, 0.0); hostsim.commit_bam(bi, None)
+            hostsim.variant_stats()
+            hostsim.build_graph(1, 0)
+            out.append((hostsim.counters(), {k: hostsim.download(k).copy() for k in ("ed_a", "ed_b", "ed_sup", "ed_tot", "ed_cfg", "setsize", "vb_cnt")}))
+        finally:
+            hostsim.set_option("graph_mode", 1)
+    (ca, a), (cb, b) = out
+    assert ca["n_tuples"] > 65535 and ca["full_sort_fallback"] == 1 and cb["full_sort_fallback"] == 1
+    assert ca == cb
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
