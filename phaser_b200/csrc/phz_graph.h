@@ -53,6 +53,11 @@ PHZ_HD int pair_slot(const PairTable& pt, u64 key) {
   return -1;
 }
 
+// 3 x 3 outer product of two class masks: bit x*3+y set iff class x at the first site and class y at the second
+PHZ_HD u32 pair_cells_of(u32 ma, u32 mb) {
+  return ((ma & 1u) ? mb : 0u) | ((ma & 2u) ? (mb << 3) : 0u) | ((ma & 4u) ? (mb << 6) : 0u);
+}
+
 struct FragCtx {
   const u32* vc;      // contig of every het site
   const u8* gc;       // class | bam << 2 per kept tuple
@@ -65,13 +70,62 @@ struct FragCtx {
 // k[0..ne) / info[0..ne) hold the fragment's (variant, BAM) entries sorted by (variant, BAM):
 // k = variant << 32 | first tuple with a reference / alternative call (NONE32 if none), info = bam << 3 | class mask.
 // Returns ne; adds groups / pairs to ng / np.
-template <class Sink>
+template <bool ONE_BAM, class Sink>
 PHZ_HD u32 process_fragment(const FragCtx& c, u64* k, uint16_t* info, u32 n, Sink& sink, u32& ng, u32& np) {
   // tuples arrive nearly sorted (record order = position order): insertion sort, stable because keys are unique
   for (u32 j = 1; j < n; ++j) {
     u64 key = k[j]; u32 m = j;
     while (m > 0 && k[m - 1] > key) { k[m] = k[m - 1]; --m; }
     k[m] = key;
+  }
+  if (ONE_BAM) {
+    // one BAM: an entry is a distinct variant; no effective-BAM bookkeeping, no re-scans of equal-variant runs
+    u32 ne = 0, cur_v = 0xFFFFFFFFu;
+    for (u32 i = 0; i < n; ++i) {
+      const u64 key = k[i]; const u32 v = (u32)(key >> 32), t = (u32)key;
+      const u32 cls = c.gc[t] & 3;
+      if (v != cur_v) { k[ne] = ((u64)v << 32) | 0xFFFFFFFFu; info[ne] = 0; ++ne; cur_v = v; }
+      info[ne - 1] = (uint16_t)(info[ne - 1] | (1u << cls));
+      if (cls < 2 && (u32)k[ne - 1] == 0xFFFFFFFFu) k[ne - 1] = ((u64)v << 32) | t;
+    }
+    const bool counted = !(c.excl_mask & 1);
+    for (u32 g0 = 0; g0 < ne;) {
+      const u32 v0 = (u32)(k[g0] >> 32); const u32 cg = c.vc[v0]; u32 g1 = g0;
+      u32 kelig = 0, first_t = 0xFFFFFFFFu;
+      for (; g1 < ne; ++g1) {
+        const u32 v = (u32)(k[g1] >> 32);
+        if (g1 > g0 && c.vc[v] != cg) break;
+        const u32 m = info[g1];
+        if (m & 1) sink.set_size(v, 0);
+        if (m & 2) sink.set_size(v, 1);
+        if (m & 4) sink.set_size(v, 2);
+        if (counted) { if (m & 1) sink.bam_count(v, 0, 0); if (m & 2) sink.bam_count(v, 0, 1); }
+        if (m & 3) { ++kelig; const u32 t = (u32)k[g1]; if (t < first_t) first_t = t; }
+      }
+      ++ng;
+      const u32 kk = g1 - g0;
+      if (kk >= 2) {
+        np += kk * (kk - 1) / 2;
+        if (kelig >= 2)
+          for (u32 j = g0; j < g1; ++j)
+            if (info[j] & 3) {
+              const unsigned long long key = ((unsigned long long)first_t << 32) | (u32)k[j];
+              unsigned long long* slot = (unsigned long long*)&c.vrank[(u32)(k[j] >> 32)];
+              if (key < load_volatile(slot)) atomic_min(slot, key);
+            }
+        for (u32 a = g0; a + 1 < g1; ++a) {
+          const u32 va = (u32)(k[a] >> 32), ma = info[a];
+          for (u32 b = a + 1; b < g1; ++b) {
+            const u32 mb = info[b];
+            u32 cells = pair_cells_of(ma, mb);
+            if ((ma & 3) && (mb & 3)) cells |= 1u << 9;
+            sink.pair(((u64)va << 32) | (u32)(k[b] >> 32), cells);
+          }
+        }
+      }
+      g0 = g1;
+    }
+    return ne;
   }
   // (variant, BAM) entries, in place: tuple order inside a variant is BAM-major (commit order)
   u32 ne = 0, cur_v = 0xFFFFFFFFu, cur_b = 0xFFFFFFFFu;
@@ -126,8 +180,7 @@ PHZ_HD u32 process_fragment(const FragCtx& c, u64* k, uint16_t* info, u32 n, Sin
           for (u32 b = a1; b < g1;) {
             const u32 vb = (u32)(k[b] >> 32); u32 mb = 0; bool eb = false; u32 b1 = b;
             for (; b1 < g1 && (u32)(k[b1] >> 32) == vb; ++b1) { mb |= info[b1] & 7u; if ((info[b1] & 3) && (int)(info[b1] >> 3) == effbam) eb = true; }
-            u32 cells = 0;
-            for (int x = 0; x < 3; ++x) for (int y = 0; y < 3; ++y) if (((ma >> x) & 1) && ((mb >> y) & 1)) cells |= 1u << (x * 3 + y);
+            u32 cells = pair_cells_of(ma, mb);
             if (ea && eb) cells |= 1u << 9;
             sink.pair(((u64)va << 32) | vb, cells);
             b = b1;
@@ -151,6 +204,7 @@ struct DirectSink {
     for (int c = 0; c < PAIR_CELLS; ++c) if ((cells >> c) & 1) atomic_add(&pt.vals[(int64_t)s * PAIR_CELLS + c], 1u);
   }
 };
+
 
 #ifdef __CUDACC__
 struct CtaSink {
@@ -179,33 +233,36 @@ struct CtaSink {
       h = (h + 1) & (FRAG_HS - 1);
     }
     if (found >= 0) {
-      for (int c = 0; c < PAIR_CELLS; ++c) if ((cells >> c) & 1) atomicAdd(&h_vals[found * 5 + (c >> 1)], 1u << (16 * (c & 1)));
+      while (cells) { const int c = __ffs(cells) - 1; cells &= cells - 1; atomicAdd(&h_vals[found * 5 + (c >> 1)], 1u << (16 * (c & 1))); }
     } else {        // the CTA's table is crowded here: straight to the run-wide table
       const int s = pair_slot(pt, key);
-      if (s >= 0) for (int c = 0; c < PAIR_CELLS; ++c) if ((cells >> c) & 1) atomicAdd(&pt.vals[(int64_t)s * PAIR_CELLS + c], 1u);
+      if (s >= 0) while (cells) { const int c = __ffs(cells) - 1; cells &= cells - 1; atomicAdd(&pt.vals[(int64_t)s * PAIR_CELLS + c], 1u); }
     }
   }
 };
 
 // f_off[f] .. f_off[f + 1]: slot range of fragment f in fk / info.  f_ne[f] receives its number of entries.
 // cnt3: [0] entries, [1] groups, [2] pairs (64-bit sums).
+// Most fragments own no tuple (most reads touch no het site), so a warp first gathers the non-empty fragments of its
+// range into a small queue and hands them out 32 at a time: every lane of a round has a fragment to work on.
+template <bool ONE_BAM>
 __global__ void __launch_bounds__(FRAG_CTA, 4) fragment_kernel(FragCtx c, const u32* __restrict__ f_off, int64_t n_frag,
-                                                            u64* __restrict__ fk, uint16_t* __restrict__ info,
-                                                            u32* __restrict__ f_ne, int nb, u32* __restrict__ sz,
-                                                            u32* __restrict__ vbc, PairTable pt,
-                                                            unsigned long long* __restrict__ cnt3) {
+                                                               u64* __restrict__ fk, uint16_t* __restrict__ info,
+                                                               u32* __restrict__ f_ne, int nb, u32* __restrict__ sz,
+                                                               u32* __restrict__ vbc, PairTable pt,
+                                                               unsigned long long* __restrict__ cnt3) {
   __shared__ u32 s_sz[FRAG_W * 3];
   __shared__ u32 s_vb[FRAG_W * 2 * 4];
   __shared__ unsigned long long h_keys[FRAG_HS];
   __shared__ u32 h_vals[FRAG_HS * 5];
   __shared__ u32 s_base;
-  __shared__ unsigned long long s_cnt[3];
-  const int tid = threadIdx.x;
+  __shared__ u32 s_q[FRAG_CTA / 32][64];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t f0 = (int64_t)blockIdx.x * (FRAG_CTA * FRAG_PER_THREAD);
   const int64_t f1 = (f0 + FRAG_CTA * FRAG_PER_THREAD < n_frag) ? f0 + FRAG_CTA * FRAG_PER_THREAD : n_frag;
   const u32 o_first = f_off[f0], o_last = f_off[f1];
   if (*c.abort & 8u) return;        // the host takes the sort-based stage instead
-  if (o_first == o_last) {          // no tuple in this range of fragments (most reads touch no het site)
+  if (o_first == o_last) {          // no tuple in this range of fragments
     for (int64_t f = f0 + tid; f < f1; f += FRAG_CTA) f_ne[f] = 0;
     return;
   }
@@ -216,19 +273,45 @@ __global__ void __launch_bounds__(FRAG_CTA, 4) fragment_kernel(FragCtx c, const 
   if (tid == 0) {
     const u32 v0 = (u32)(fk[o_first] >> 32);
     s_base = v0 > FRAG_W / 4 ? v0 - FRAG_W / 4 : 0;
-    s_cnt[0] = s_cnt[1] = s_cnt[2] = 0;
   }
   __syncthreads();
   CtaSink sink{s_sz, s_vb, s_base, nb, sz, vbc, h_keys, h_vals, pt};
   u32 ne_sum = 0, ng = 0, np = 0;
-  for (int64_t f = f0 + tid; f < f1; f += FRAG_CTA) {
-    const u32 o0 = f_off[f], n = f_off[f + 1] - o0;
-    u32 ne = 0;
-    if (n) ne = process_fragment(c, fk + o0, info + o0, n, sink, ng, np);
-    f_ne[f] = ne; ne_sum += ne;
+  // this warp's fragments: [w0, w1)
+  const int64_t w0 = f0 + (int64_t)warp * (32 * FRAG_PER_THREAD);
+  const int64_t w1 = (w0 + 32 * FRAG_PER_THREAD < f1) ? w0 + 32 * FRAG_PER_THREAD : f1;
+  u32* q = s_q[warp];
+  u32 qn = 0;
+  for (int64_t b = w0; b < w1 || qn > 0; b += 32) {
+    if (b < w1) {
+      const int64_t f = b + lane;
+      u32 n = 0;
+      if (f < w1) { n = f_off[f + 1] - f_off[f]; if (n == 0) f_ne[f] = 0; }
+      const u32 m = __ballot_sync(0xFFFFFFFFu, n > 0);
+      if (n > 0) q[qn + __popc(m & ((1u << lane) - 1u))] = (u32)(f - f0);
+      qn += __popc(m);
+      __syncwarp();
+    }
+    if (qn >= 32 || b + 32 >= w1) {
+      const u32 take = qn < 32 ? qn : 32;
+      if ((u32)lane < take) {
+        const int64_t f = f0 + q[qn - take + lane];
+        const u32 o0 = f_off[f], n = f_off[f + 1] - o0;
+        const u32 ne = process_fragment<ONE_BAM>(c, fk + o0, info + o0, n, sink, ng, np);
+        f_ne[f] = ne; ne_sum += ne;
+      }
+      qn -= take;
+      __syncwarp();
+    }
   }
-  if (ne_sum) { atomicAdd(&s_cnt[0], (unsigned long long)ne_sum); atomicAdd(&s_cnt[1], (unsigned long long)ng); }
-  if (np) atomicAdd(&s_cnt[2], (unsigned long long)np);
+  // counters: registers -> warp -> one reduction per warp
+  for (int o = 16; o > 0; o >>= 1) {
+    ne_sum += __shfl_xor_sync(0xFFFFFFFFu, ne_sum, o); ng += __shfl_xor_sync(0xFFFFFFFFu, ng, o); np += __shfl_xor_sync(0xFFFFFFFFu, np, o);
+  }
+  if (lane == 0) {
+    if (ne_sum) { atomicAdd(&cnt3[0], (unsigned long long)ne_sum); atomicAdd(&cnt3[1], (unsigned long long)ng); }
+    if (np) atomicAdd(&cnt3[2], (unsigned long long)np);
+  }
   __syncthreads();
   const u32 base = s_base;
   for (int i = tid; i < FRAG_W; i += FRAG_CTA) {
@@ -246,7 +329,6 @@ __global__ void __launch_bounds__(FRAG_CTA, 4) fragment_kernel(FragCtx c, const 
       if (cv) atomicAdd(&pt.vals[(int64_t)s * PAIR_CELLS + cidx], cv);
     }
   }
-  if (tid < 3 && s_cnt[tid]) atomicAdd(&cnt3[tid], s_cnt[tid]);
 }
 #endif
 

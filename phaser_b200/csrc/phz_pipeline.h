@@ -1060,8 +1060,12 @@ struct Pipeline {
 #ifdef __CUDACC__
       {
         const int64_t per = (int64_t)FRAG_CTA * FRAG_PER_THREAD;
-        fragment_kernel<<<(unsigned)((F + per - 1) / per), FRAG_CTA, 0, be.stream>>>(fx, fo, F, fk, fi, fne, nb, sz, vbc, pt,
-                                                                                  (unsigned long long*)c3);
+        if (nb == 1)
+          fragment_kernel<true><<<(unsigned)((F + per - 1) / per), FRAG_CTA, 0, be.stream>>>(fx, fo, F, fk, fi, fne, nb, sz, vbc, pt,
+                                                                                          (unsigned long long*)c3);
+        else
+          fragment_kernel<false><<<(unsigned)((F + per - 1) / per), FRAG_CTA, 0, be.stream>>>(fx, fo, F, fk, fi, fne, nb, sz, vbc, pt,
+                                                                                           (unsigned long long*)c3);
         PHZ_CUDA(cudaGetLastError());
         be.launches++;
       }
@@ -1071,7 +1075,8 @@ struct Pipeline {
         u64 ne_sum = 0, ng_sum = 0, np_sum = 0;
         for (int64_t f = 0; f < F && !(sc[1] & 8u); ++f) {
           const u32 o0 = fo[f], cnt = fo[f + 1] - o0; u32 ng = 0, np = 0, ne = 0;
-          if (cnt) ne = process_fragment(fx, fk + o0, fi + o0, cnt, sink, ng, np);
+          if (cnt) ne = nb == 1 ? process_fragment<true>(fx, fk + o0, fi + o0, cnt, sink, ng, np)
+                                : process_fragment<false>(fx, fk + o0, fi + o0, cnt, sink, ng, np);
           fne[f] = ne; ne_sum += ne; ng_sum += ng; np_sum += np;
         }
         c3[0] = ne_sum; c3[1] = ng_sum; c3[2] = np_sum;

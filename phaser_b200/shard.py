@@ -311,6 +311,172 @@ def results_equal(a: PhaseResult, b: PhaseResult):
     return bad
 
 
+# ------------------------------------------------------------------------------------------------ merge on the device
+
+def _typed(buf, off, n, eb):
+    """typed view of a packed byte buffer; unsigned 32-bit data travels as int32 bit patterns (torch has no uint32 maths)"""
+    t = buf[off:off + n * eb]
+    return t if eb == 1 else t.view({2: torch.int16, 4: torch.int32, 8: torch.int64}[eb])
+
+
+def merge_results_device(recv, lay, heads, names, gids, plan, vt: VariantTable, n_bams: int, meta: PhaseResult,
+                         contig_of, want_read_ids=False, want_kept_tuples=False, host_cache=None) -> PhaseResult:
+    """merge_results on the arrays as the gather left them in rank 0's memory (device tensors, or CPU tensors under
+    gloo): same result, but every step is a tensor operation where the data already is, and the merged arrays reach
+    the host in ONE copy.  recv[r]: packed byte buffer of rank r (None: no contigs); lay[r]: its layout; gids[r]:
+    global variant ids of rank r's table (int64 tensor on the same device); contig_of: int64[V] on that device."""
+    from .engine import COUNTER_NAMES
+    dev = contig_of.device
+    V = vt.n_variants; nb = n_bams; nc = len(vt.contigs); nn = len(names)
+    M32 = 0xFFFFFFFF
+    i64 = torch.int64
+    live = [r for r in range(len(recv)) if recv[r] is not None]
+
+    def arr(r, name):
+        for nm, off, n, eb in lay[r][0]:
+            if nm == name:
+                return _typed(recv[r], off, n, eb)
+        raise KeyError(name)
+
+    def u(t):          # int32 bit pattern -> non-negative int64
+        return t.to(i64) & M32
+
+    BIG = torch.iinfo(i64).max
+    vfirst = torch.full((V,), BIG, dtype=i64, device=dev)
+    ncls = torch.zeros((V, 3), dtype=torch.int32, device=dev); setsize = torch.zeros((V, 3), dtype=torch.int32, device=dev)
+    vb = torch.zeros((V, nb * 2), dtype=torch.int32, device=dev)
+    v_final = torch.full((V,), -1, dtype=torch.int32, device=dev); v_hap = torch.zeros(V, dtype=torch.uint8, device=dev)
+    first_bam = torch.full((nc,), 1 << 30, dtype=i64, device=dev)
+    counters = {}; tpb = [0] * nb; cpb = [0] * nb
+    for r in live:
+        h = heads[r]
+        for i, k in enumerate(COUNTER_NAMES):
+            counters[k] = counters.get(k, 0) + int(h[2 * nn + i])
+        t_r = [int(x) for x in h[2 * nn + N_COUNTERS:2 * nn + N_COUNTERS + nb]]
+        for b in range(nb):
+            tpb[b] += t_r[b]; cpb[b] += int(h[2 * nn + N_COUNTERS + nb + b])
+        gid = gids[r]
+        lf = u(arr(r, "vfirst")); seen = lf != M32
+        bam_start = torch.tensor(np.concatenate([[0], np.cumsum(t_r)]), dtype=i64, device=dev)
+        bam_of = torch.searchsorted(bam_start, lf, right=True) - 1
+        key = (bam_of << 56) | (contig_of[gid] << 40) | lf
+        vfirst[gid[seen]] = key[seen]
+        ncls[gid] = arr(r, "ncls").view(-1, 3); setsize[gid] = arr(r, "setsize").view(-1, 3); vb[gid] = arr(r, "vb_cnt").view(-1, nb * 2)
+        v_hap[gid] = arr(r, "v_hap")
+        first_bam.scatter_reduce_(0, contig_of[gid[seen]], bam_of[seen], "amin")
+    first_bam[first_bam == (1 << 30)] = 0
+    # ---- global block order: (first BAM of the contig, contig, local order)
+    keys = []; lens = []
+    for r in live:
+        ff = u(arr(r, "fb_first")); nf = ff.shape[0]
+        c = contig_of[gids[r][u(arr(r, "members"))[ff]]] if nf else torch.zeros(0, dtype=i64, device=dev)
+        keys.append((first_bam[c] << 48) | (c << 32) | torch.arange(nf, dtype=i64, device=dev))
+        lens.append(u(arr(r, "fb_len")))
+    keys = torch.cat(keys) if keys else torch.zeros(0, dtype=i64, device=dev)
+    cat_len = torch.cat(lens) if lens else torch.zeros(0, dtype=i64, device=dev)
+    order = torch.argsort(keys)
+    NF = int(order.shape[0])
+    new_of_cat = torch.empty(NF, dtype=i64, device=dev); new_of_cat[order] = torch.arange(NF, dtype=i64, device=dev)
+    g_len = cat_len[order]
+    g_first = torch.cumsum(g_len, 0) - g_len
+    members = torch.zeros(int(g_len.sum().item()) if NF else 0, dtype=torch.int32, device=dev)
+    fb_sup = torch.zeros(NF, dtype=torch.int32, device=dev); fb_tot = torch.zeros(NF, dtype=torch.int32, device=dev)
+    fb_cnt = torch.zeros((NF, 2), dtype=torch.int32, device=dev); fb_bcnt = torch.zeros((NF, nb * 2), dtype=torch.int32, device=dev)
+    ed = {k: [] for k in ("ed_a", "ed_b", "ed_sup", "ed_tot", "ed_cfg", "ed_keep")}
+    sg = {k: [] for k in ("sg_var", "sg_cb", "sg_frag", "g_var", "g_cb", "g_frag")}
+    bb = max(1, int(np.ceil(np.log2(max(nb, 2)))))
+    low = (1 << (bb + 1)) - 1
+    runs = []          # per rank: (new row of every run, run length, local start of every run, rl_var, rl_frag)
+    base = 0
+    for r in live:
+        gid = gids[r]
+        ff = u(arr(r, "fb_first")); ln = u(arr(r, "fb_len")); nf = int(ff.shape[0])
+        new_id = new_of_cat[base:base + nf]; base += nf
+        tot = int(ln.sum().item()) if nf else 0
+        if tot:
+            rep = torch.repeat_interleave(torch.arange(nf, dtype=i64, device=dev), ln)
+            within = torch.arange(tot, dtype=i64, device=dev) - torch.repeat_interleave(torch.cumsum(ln, 0) - ln, ln)
+            members[g_first[new_id[rep]] + within] = gid[u(arr(r, "members"))[ff[rep] + within]].to(torch.int32)
+        fb_sup[new_id] = arr(r, "fb_sup"); fb_tot[new_id] = arr(r, "fb_tot")
+        fb_cnt[new_id] = arr(r, "fb_cnt").view(-1, 2); fb_bcnt[new_id] = arr(r, "fb_bcnt").view(-1, nb * 2)
+        vfl = arr(r, "v_final"); inb = vfl != -1
+        v_final[gid[inb]] = new_id[vfl[inb].to(i64)].to(torch.int32)
+        ed["ed_a"].append(gid[u(arr(r, "ed_a"))].to(torch.int32)); ed["ed_b"].append(gid[u(arr(r, "ed_b"))].to(torch.int32))
+        for k in ("ed_sup", "ed_tot", "ed_cfg", "ed_keep"):
+            ed[k].append(arr(r, k))
+        if want_read_ids or want_kept_tuples:
+            gv = u(arr(r, "g_var")); gc = arr(r, "g_cb"); gfr = arr(r, "g_frag")
+            if want_read_ids:
+                sel = torch.nonzero((vfl[gv] == -1) & ((gc & 3) < 2))[:, 0]
+                sg["sg_var"].append(gid[gv[sel]].to(torch.int32)); sg["sg_cb"].append(gc[sel]); sg["sg_frag"].append(gfr[sel])
+            if want_kept_tuples:
+                sg["g_var"].append(gid[gv].to(torch.int32)); sg["g_cb"].append(gc); sg["g_frag"].append(gfr)
+        if any(nm == "rl_row" for nm, _o, _n, _e in lay[r][0]):
+            row = u(arr(r, "rl_row"))
+            if row.shape[0]:
+                urow, cnt = torch.unique_consecutive(row, return_counts=True)
+                runs.append(((new_id[urow >> (bb + 1)] << (bb + 1)) | (urow & low), cnt, torch.cumsum(cnt, 0) - cnt,
+                             gid[u(arr(r, "rl_var"))].to(torch.int32), arr(r, "rl_frag")))
+    cat = lambda xs, dt: torch.cat(xs) if xs else torch.zeros(0, dtype=dt, device=dev)
+    out = dict(vfirst=vfirst, ncls=ncls.reshape(-1), setsize=setsize.reshape(-1), vb_cnt=vb.reshape(-1), v_final=v_final, v_hap=v_hap,
+               members=members, fb_first=g_first.to(torch.int32), fb_len=g_len.to(torch.int32), fb_sup=fb_sup, fb_tot=fb_tot,
+               fb_cnt=fb_cnt.reshape(-1), fb_bcnt=fb_bcnt.reshape(-1))
+    for k, dt in (("ed_a", torch.int32), ("ed_b", torch.int32), ("ed_sup", torch.int32), ("ed_tot", torch.int32), ("ed_cfg", torch.uint8),
+                  ("ed_keep", torch.uint8)):
+        out[k] = cat(ed[k], dt)
+    # ---- read lists: rows of one block live on one rank and every rank's rows are already sorted, so the merged order
+    # follows from the run lengths alone (no sort of the entries): destination = start of the run in the merged order +
+    # offset inside the run
+    if runs:
+        all_rows = torch.cat([x[0] for x in runs]); all_cnt = torch.cat([x[1] for x in runs])
+        o = torch.argsort(all_rows)
+        start_sorted = torch.cumsum(all_cnt[o], 0) - all_cnt[o]
+        start = torch.empty_like(start_sorted); start[o] = start_sorted
+        total = int(all_cnt.sum().item())
+        rl_row = torch.empty(total, dtype=torch.int32, device=dev); rl_var = torch.empty(total, dtype=torch.int32, device=dev)
+        rl_frag = torch.empty(total, dtype=torch.int32, device=dev)
+        p = 0
+        for (nrow, cnt, lstart, var, frag) in runs:
+            k = int(nrow.shape[0]); n = int(var.shape[0])
+            dest = torch.repeat_interleave(start[p:p + k] - lstart, cnt) + torch.arange(n, dtype=i64, device=dev)
+            rl_row[dest] = torch.repeat_interleave(nrow, cnt).to(torch.int32)
+            rl_var[dest] = var; rl_frag[dest] = frag
+            p += k
+        out["rl_row"] = rl_row; out["rl_var"] = rl_var; out["rl_frag"] = rl_frag
+    else:
+        for k in ("rl_row", "rl_var", "rl_frag"):
+            out[k] = torch.zeros(0, dtype=torch.int32, device=dev)
+    for pre in ("sg_", "g_"):
+        if sg[pre + "var"]:
+            out[pre + "var"] = torch.cat(sg[pre + "var"]); out[pre + "cb"] = torch.cat(sg[pre + "cb"]); out[pre + "frag"] = torch.cat(sg[pre + "frag"])
+    # ---- one copy to the host
+    total = 0; place = []
+    for k, t in out.items():
+        t = t.contiguous(); out[k] = t
+        off = (total + 63) // 64 * 64
+        place.append((k, off, t.numel() * t.element_size())); total = off + place[-1][2]
+    host = host_cache.get("buf") if host_cache is not None else None
+    if host is None or host.numel() < total:          # grow-only page-locked landing buffer (the arrays returned are views)
+        host = torch.empty(int(max(total, 64) * 1.25) + 4096, dtype=torch.uint8)
+        if dev.type == "cuda":
+            try:
+                host = host.pin_memory()
+            except RuntimeError:
+                pass
+        if host_cache is not None:
+            host_cache["buf"] = host
+    for (k, off, nbytes) in place:
+        if nbytes:
+            host[off:off + nbytes].copy_(out[k].view(torch.uint8).reshape(-1) if out[k].dtype != torch.uint8 else out[k].reshape(-1),
+                                         non_blocking=True)
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+    hn = host.numpy()
+    npdt = {torch.int32: np.uint32, torch.uint8: np.uint8, torch.int64: np.int64}
+    arrays = {k: hn[off:off + nbytes].view(npdt[out[k].dtype]) for (k, off, nbytes) in place}
+    return PhaseResult(nb, meta.as_cutoff, tpb, cpb, meta.noise_e, meta.match, meta.mismatch, counters, 0, arrays)
+
+
 # ------------------------------------------------------------------------------------------------ gather
 
 def gather_names(params: PhaseParams):
@@ -464,6 +630,12 @@ class ShardedRun:
         self.svt, self.gid = sub_variant_table(vt, self.mine)
         self.gids = [sub_variant_table_ids(vt, p) for p in self.plan] if self.rank == 0 else None
         self.names = gather_names(params)
+        self.host_cache = {}
+        if self.rank == 0:          # the merge runs where the gathered arrays are
+            self.gids_dev = [torch.from_numpy(g).to(self.device) for g in self.gids]
+            nc = len(vt.contigs)
+            self.contig_of_dev = torch.from_numpy(np.repeat(np.arange(nc, dtype=np.int64),
+                                                            np.diff(np.asarray(vt.contig_var_off, np.int64)))).to(self.device)
 
     def loads(self):
         return [int(sum(self.weights[c] for c in p)) for p in self.plan]
@@ -480,28 +652,17 @@ class ShardedRun:
         except PhaserFatal as e:          # rank-local verdicts (phasing flags) must not leave the others in the gather
             err = e
         got = gather_results(self.engine, res if (self.mine and err is None) else None, self.names, self.n_bams, self.device,
-                             self.timers, to_host=to_host and merge, failed=err is not None)
+                             self.timers, to_host=False, failed=err is not None)
         if err is not None:
             raise err
         if self.rank != 0 or not merge:
             return None
         if self.timers is not None:
             t0 = time.perf_counter()
-        parts = []
-        for r, g in enumerate(got):
-            if g is None:
-                parts.append(None); continue
-            arrays, counters, tpb, cpb = g
-            if {"g_var", "g_cb", "g_frag"} <= set(arrays) and self.params.want_read_ids:
-                gv = arrays["g_var"]; gc = arrays["g_cb"]
-                sel = np.nonzero((arrays["v_final"][gv] == NONE32) & ((gc & 3) < 2))[0]
-                arrays["sg_var"] = gv[sel]; arrays["sg_cb"] = gc[sel]; arrays["sg_frag"] = arrays["g_frag"][sel]
-            if not self.params.want_kept_tuples:
-                for k in ("g_var", "g_cb", "g_frag"):
-                    arrays.pop(k, None)
-            pr = PhaseResult(self.n_bams, res.as_cutoff, tpb, cpb, res.noise_e, res.match, res.mismatch, counters, 0, arrays)
-            parts.append((pr, self.gids[r], self.plan[r]))
-        out = merge_results(parts, self.vt, self.n_bams)
+        recv, lay, heads = got
+        out = merge_results_device(recv, lay, heads, self.names, self.gids_dev, self.plan, self.vt, self.n_bams, res,
+                                   self.contig_of_dev, want_read_ids=self.params.want_read_ids,
+                                   want_kept_tuples=self.params.want_kept_tuples, host_cache=self.host_cache)
         if self.timers is not None:
             self.timers["merge_on_rank0_ms"] = self.timers.get("merge_on_rank0_ms", 0.0) + (time.perf_counter() - t0) * 1e3
         return out
