@@ -194,6 +194,8 @@ def run_ours(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from phaser_b200 import numa
+    placement = numa.bind_near_gpu(local)          # before any page-locked transport buffer is allocated and filled
     sharded = world > 1 and a.mode != "replicas"
     E = eng.Engine(device=dev)
     E.set_option("k1_mode", a.k1_mode)
@@ -359,7 +361,7 @@ def run_ours(a):
                           "NCCL, reads them back and merges them" if sharded else ""),
                "single_sample_ms": dt1 * 1e3, "single_sample_value": units / dt1,
                "host_form": "packed transport (lossless, include/phz.h phz_packed_reads), expanded on the device",
-               "host_form_coding": pk.coding if pk is not None else None,
+               "host_form_coding": pk.coding if pk is not None else None, "host_placement_rank0": placement,
                "bytes_per_record": (pk.nbytes / float(my_R)) if pk is not None and my_R else None}
         if sharded:
             # ---- one extra step with every collective bracketed by device synchronisation

@@ -241,12 +241,17 @@ struct CtaSink {
   }
 };
 
-// f_off[f] .. f_off[f + 1]: slot range of fragment f in fk / info.  f_ne[f] receives its number of entries.
+// f_off[f] .. f_off[f + 1]: slot range of fragment f in fk / info.  f_ne[f] holds the fragment's tuple count on entry
+// (0 for most fragments: those slots are never touched) and receives its number of entries.
 // cnt3: [0] entries, [1] groups, [2] pairs (64-bit sums).
-// Most fragments own no tuple (most reads touch no het site), so a warp first gathers the non-empty fragments of its
-// range into a small queue and hands them out 32 at a time: every lane of a round has a fragment to work on.
+// Most fragments own no tuple (most reads touch no het site) and most of the others own exactly one, so the CTA first
+// sorts its range into two lists in shared memory -- single-tuple fragments (no sort, no pairs: a few instructions
+// each, all lanes alike) and the rest -- and its warps then draw 32 fragments at a time from a shared cursor: every
+// lane of a round has work of the same kind, and a warp stuck on a deep fragment does not hold up the others.
+constexpr int FRAG_RANGE = FRAG_CTA * FRAG_PER_THREAD;
+
 template <bool ONE_BAM>
-__global__ void __launch_bounds__(FRAG_CTA, 4) fragment_kernel(FragCtx c, const u32* __restrict__ f_off, int64_t n_frag,
+__global__ void __launch_bounds__(FRAG_CTA, 5) fragment_kernel(FragCtx c, const u32* __restrict__ f_off, int64_t n_frag,
                                                                u64* __restrict__ fk, uint16_t* __restrict__ info,
                                                                u32* __restrict__ f_ne, int nb, u32* __restrict__ sz,
                                                                u32* __restrict__ vbc, PairTable pt,
@@ -256,16 +261,14 @@ __global__ void __launch_bounds__(FRAG_CTA, 4) fragment_kernel(FragCtx c, const 
   __shared__ unsigned long long h_keys[FRAG_HS];
   __shared__ u32 h_vals[FRAG_HS * 5];
   __shared__ u32 s_base;
-  __shared__ u32 s_q[FRAG_CTA / 32][64];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t f0 = (int64_t)blockIdx.x * (FRAG_CTA * FRAG_PER_THREAD);
-  const int64_t f1 = (f0 + FRAG_CTA * FRAG_PER_THREAD < n_frag) ? f0 + FRAG_CTA * FRAG_PER_THREAD : n_frag;
+  __shared__ uint16_t s_list[FRAG_RANGE];       // single-tuple fragments from the front, the others from the back
+  __shared__ u32 s_n1, s_nm, s_next1, s_nextm;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t f0 = (int64_t)blockIdx.x * FRAG_RANGE;
+  const int64_t f1 = (f0 + FRAG_RANGE < n_frag) ? f0 + FRAG_RANGE : n_frag;
   const u32 o_first = f_off[f0], o_last = f_off[f1];
   if (*c.abort & 8u) return;        // the host takes the sort-based stage instead
-  if (o_first == o_last) {          // no tuple in this range of fragments
-    for (int64_t f = f0 + tid; f < f1; f += FRAG_CTA) f_ne[f] = 0;
-    return;
-  }
+  if (o_first == o_last) return;    // no tuple in this range of fragments (f_ne aliases the tuple counts: already 0)
   for (int i = tid; i < FRAG_W * 3; i += FRAG_CTA) s_sz[i] = 0;
   for (int i = tid; i < FRAG_W * 2 * 4; i += FRAG_CTA) s_vb[i] = 0;
   for (int i = tid; i < FRAG_HS; i += FRAG_CTA) h_keys[i] = PAIR_EMPTY;
@@ -273,35 +276,57 @@ __global__ void __launch_bounds__(FRAG_CTA, 4) fragment_kernel(FragCtx c, const 
   if (tid == 0) {
     const u32 v0 = (u32)(fk[o_first] >> 32);
     s_base = v0 > FRAG_W / 4 ? v0 - FRAG_W / 4 : 0;
+    s_n1 = 0; s_nm = 0; s_next1 = 0; s_nextm = 0;
+  }
+  __syncthreads();
+  // ---- sort the range into the two lists (one shared-memory reduction per warp and list)
+  for (int64_t b = f0 + (tid & ~31); b < f1; b += FRAG_CTA) {
+    const int64_t f = b + lane;
+    u32 n = 0;
+    if (f < f1) n = f_off[f + 1] - f_off[f];
+    const u32 m1 = __ballot_sync(0xFFFFFFFFu, n == 1), mm = __ballot_sync(0xFFFFFFFFu, n > 1);
+    u32 b1 = 0, bm = 0;
+    if (lane == 0) { if (m1) b1 = atomicAdd(&s_n1, (u32)__popc(m1)); if (mm) bm = atomicAdd(&s_nm, (u32)__popc(mm)); }
+    b1 = __shfl_sync(0xFFFFFFFFu, b1, 0); bm = __shfl_sync(0xFFFFFFFFu, bm, 0);
+    const u32 lt = (1u << lane) - 1u;
+    if (n == 1) s_list[b1 + __popc(m1 & lt)] = (uint16_t)(f - f0);
+    else if (n > 1) s_list[FRAG_RANGE - 1 - (bm + __popc(mm & lt))] = (uint16_t)(f - f0);
   }
   __syncthreads();
   CtaSink sink{s_sz, s_vb, s_base, nb, sz, vbc, h_keys, h_vals, pt};
   u32 ne_sum = 0, ng = 0, np = 0;
-  // this warp's fragments: [w0, w1)
-  const int64_t w0 = f0 + (int64_t)warp * (32 * FRAG_PER_THREAD);
-  const int64_t w1 = (w0 + 32 * FRAG_PER_THREAD < f1) ? w0 + 32 * FRAG_PER_THREAD : f1;
-  u32* q = s_q[warp];
-  u32 qn = 0;
-  for (int64_t b = w0; b < w1 || qn > 0; b += 32) {
-    if (b < w1) {
-      const int64_t f = b + lane;
-      u32 n = 0;
-      if (f < w1) { n = f_off[f + 1] - f_off[f]; if (n == 0) f_ne[f] = 0; }
-      const u32 m = __ballot_sync(0xFFFFFFFFu, n > 0);
-      if (n > 0) q[qn + __popc(m & ((1u << lane) - 1u))] = (u32)(f - f0);
-      qn += __popc(m);
-      __syncwarp();
+  const u32 n1 = s_n1, nm = s_nm;
+  // ---- single-tuple fragments: one entry, one group, no pair
+  for (;;) {
+    u32 start = 0;
+    if (lane == 0) start = atomicAdd(&s_next1, 32u);
+    start = __shfl_sync(0xFFFFFFFFu, start, 0);
+    if (start >= n1) break;
+    const u32 i = start + lane;
+    if (i < n1) {
+      const int64_t f = f0 + s_list[i];
+      const u32 o0 = f_off[f];
+      const u64 key = fk[o0]; const u32 v = (u32)(key >> 32), t = (u32)key;
+      const u32 cb = c.gc[t]; const u32 cls = cb & 3, bam = cb >> 2;
+      fk[o0] = cls < 2 ? key : (key | 0xFFFFFFFFull);
+      info[o0] = (uint16_t)((bam << 3) | (1u << cls));
+      sink.set_size(v, (int)cls);
+      if (cls < 2 && !((c.excl_mask >> bam) & 1)) sink.bam_count(v, bam, (int)cls);
+      f_ne[f] = 1; ++ne_sum; ++ng;
     }
-    if (qn >= 32 || b + 32 >= w1) {
-      const u32 take = qn < 32 ? qn : 32;
-      if ((u32)lane < take) {
-        const int64_t f = f0 + q[qn - take + lane];
-        const u32 o0 = f_off[f], n = f_off[f + 1] - o0;
-        const u32 ne = process_fragment<ONE_BAM>(c, fk + o0, info + o0, n, sink, ng, np);
-        f_ne[f] = ne; ne_sum += ne;
-      }
-      qn -= take;
-      __syncwarp();
+  }
+  // ---- the others
+  for (;;) {
+    u32 start = 0;
+    if (lane == 0) start = atomicAdd(&s_nextm, 32u);
+    start = __shfl_sync(0xFFFFFFFFu, start, 0);
+    if (start >= nm) break;
+    const u32 i = start + lane;
+    if (i < nm) {
+      const int64_t f = f0 + s_list[FRAG_RANGE - 1 - i];
+      const u32 o0 = f_off[f], n = f_off[f + 1] - o0;
+      const u32 ne = process_fragment<ONE_BAM>(c, fk + o0, info + o0, n, sink, ng, np);
+      f_ne[f] = ne; ne_sum += ne;
     }
   }
   // counters: registers -> warp -> one reduction per warp
