@@ -48,6 +48,10 @@ def parse_args():
                     help="N > 1: 'shard' = one sample sharded by contig (default), 'replicas' = one sample per GPU")
     ap.add_argument("--no_replicas", action="store_true", help="N > 1, shard mode: skip the replica-mode second key")
     ap.add_argument("--no_e2e", action="store_true")
+    ap.add_argument("--no_wgs", action="store_true", help="skip the configs[3]-shape leg (WGS + RNA jointly, one GPU)")
+    ap.add_argument("--wgs_pairs", type=int, default=40_000_000)
+    ap.add_argument("--wgs_rna_pairs", type=int, default=10_000_000)
+    ap.add_argument("--wgs_variants", type=int, default=5_000_000)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--k1_mode", type=int, default=3, help="3 tile kernel + permute (default), 2 fused look-back, 1 windowed two-pass, 0 generic two-pass")
     ap.add_argument("--k1_min_ctas", type=int, default=8)
@@ -126,30 +130,105 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------------------- workload
 
+def make_bam(g, seed, n_pairs, wgs=False, frag_base=0):
+    """One synthetic BAM over genome `g` as packed SoA tensors on the genome's device: RNA-seq shape (2x76, spliced) or
+    WGS shape (2x150, unspliced, 5 % of the records below MAPQ 20 and filtered like `samtools view -q 20`)."""
+    from phaser_b200 import synth
+    parts = []
+    done = 0
+    chunk = 2_000_000
+    while done < n_pairs:
+        n = min(chunk, n_pairs - done)
+        if wgs:
+            rec = synth.make_wgs_reads(g, seed * 1000 + done // chunk, n, chunk_pairs=chunk, lowmapq_frac=0.05, mapq=60)
+            rec = synth.filter_raw(rec, remove_dups=True, proper_pair=True, min_mapq=20)
+        else:
+            rec = synth.make_reads(g, seed * 1000 + done // chunk, n, chunk_pairs=chunk)
+        rec["frag"] = rec["frag"] + done
+        parts.append(synth.compact_raw(rec))
+        done += n
+    rec = synth.concat_sorted(parts)
+    del parts
+    # fragment ids as the ingest assigns them: dense, in order of first appearance in the sorted BAM
+    fr = rec["frag"].to(torch.int64)
+    first = torch.full((n_pairs,), fr.shape[0], dtype=torch.int64, device=fr.device)
+    first.scatter_reduce_(0, fr, torch.arange(fr.shape[0], device=fr.device), "amin")
+    rank = torch.empty_like(first); rank[torch.argsort(first)] = torch.arange(n_pairs, device=fr.device)
+    rec["frag"] = (rank[fr] + frag_base).to(torch.int32)
+    del fr, first, rank
+    return synth.pack_records(rec, len(g.contigs))
+
+
 def make_sample(seed, n_pairs, n_variants, exonic_frac, device):
     """Synthetic sample of the configs[1] shape, generated on `device`, returned as packed SoA tensors."""
     from phaser_b200 import synth
     g = synth.make_genome(seed, n_variants, exonic_frac=exonic_frac, device=device,
                           n_genes=max(2, int(n_variants * exonic_frac) // 8))
     vt = synth.to_variant_table_arrays(g)
-    parts = []
-    done = 0
-    chunk = 2_000_000
-    while done < n_pairs:
-        n = min(chunk, n_pairs - done)
-        rec = synth.make_reads(g, seed * 1000 + done // chunk, n, chunk_pairs=chunk)
-        rec["frag"] = rec["frag"] + done
-        parts.append(synth.compact_raw(rec))
-        done += n
-    rec = synth.concat_sorted(parts)
-    # fragment ids as the ingest assigns them: dense, in order of first appearance in the sorted BAM
-    fr = rec["frag"].to(torch.int64)
-    first = torch.full((n_pairs,), fr.shape[0], dtype=torch.int64, device=fr.device)
-    first.scatter_reduce_(0, fr, torch.arange(fr.shape[0], device=fr.device), "amin")
-    rank = torch.empty_like(first); rank[torch.argsort(first)] = torch.arange(n_pairs, device=fr.device)
-    rec["frag"] = rank[fr].to(torch.int32)
-    packed = synth.pack_records(rec, len(g.contigs))
-    return g, vt, packed, n_pairs
+    return g, vt, make_bam(g, seed, n_pairs), n_pairs
+
+
+def wgs_leg(a, E, dev):
+    """BASELINE.json configs[3] shape on ONE GPU at a size that fits beside the main sample: a WGS BAM (2x150, unspliced,
+    MAPQ >= 20) and an RNA-seq BAM phased jointly over dense het SNVs, the WGS BAM excluded from the haplotypic counts
+    (--haplo_count_bam_exclude 1).  Every read covers sites here, so K1 moves its algorithmic bytes for real; blocks
+    are chains of neighbouring sites instead of exon clusters.  Resident inputs, CUDA events, stage marks."""
+    from phaser_b200 import synth, pipeline
+    t0 = time.time()
+    g = synth.make_genome(a.seed + 7, a.wgs_variants, exonic_frac=0.04, device=dev, n_genes=max(2, a.wgs_variants // 200))
+    vt = synth.to_variant_table_arrays(g)
+    wgs = make_bam(g, a.seed + 7, a.wgs_pairs, wgs=True)
+    rna = make_bam(g, a.seed + 8, a.wgs_rna_pairs, frag_base=a.wgs_pairs)
+    torch.cuda.synchronize()
+    t_gen = time.time() - t0
+    bams = []
+    for b in (wgs, rna):
+        d = dict(b); d["contig_rec_off"] = b["contig_rec_off"].cpu().numpy().astype(np.int64); bams.append(d)
+    nfrag = a.wgs_pairs + a.wgs_rna_pairs
+    P = pipeline.PhaseParams(want_read_lists=True, haplo_count_bam_exclude=[0])
+    V = vt.n_variants
+
+    def step():
+        return pipeline.run_path(E, vt, bams, P, n_fragments=nfrag, download=False)
+    for _ in range(2):
+        res = step()
+    torch.cuda.synchronize()
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    n_steps = 5
+    ev0.record()
+    for _ in range(n_steps):
+        res = step()
+    ev1.record(); torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / n_steps
+    # K1 alone on the WGS BAM (the launch the roofline is quoted on)
+    E.set_variants(vt); E.set_profiling(1)
+    k1 = []
+    for _ in range(3):
+        n_cand = E.map_reads(bams[0], P.baseq, 0.0); k1.append(E.map_times())
+    k1 = np.asarray(k1).mean(0)
+    E.commit_bam(0, None)          # leave the context consistent
+    E.set_profiling(2)
+    step(); torch.cuda.synchronize()
+    stages = {k: round(v, 3) for k, v in E.stage_report().items()}
+    E.set_profiling(1)
+    peak, _src = _peak()
+    bytes_k1 = algorithmic_bytes_k1(bams[0], V, n_cand)
+    c = res.counters
+    k2 = sum(v for k, v in stages.items() if k.startswith("graph.")); k3 = sum(v for k, v in stages.items() if k.startswith("phase."))
+    out = {"workload": "configs[3] shape on one GPU: WGS BAM %d pairs (%d records with MAPQ >= 20, 2x150 bp) + RNA-seq BAM %d pairs "
+                       "(%d records, 2x76 bp spliced), %d het SNVs, --haplo_count_bam_exclude 1" % (
+                           a.wgs_pairs, int(bams[0]["pos"].shape[0]), a.wgs_rna_pairs, int(bams[1]["pos"].shape[0]), V),
+           "value": V / (ms * 1e-3), "unit": "het-SNVs/s", "ms_per_step": ms, "generator_s": round(t_gen, 1),
+           "records_per_sec": (int(bams[0]["pos"].shape[0]) + int(bams[1]["pos"].shape[0])) / (ms * 1e-3),
+           "tuples": c["n_tuples"], "edges": c["edges"], "blocks": c["final_blocks"], "phased_in_blocks": c["members"],
+           "hard_blocks": c["hard_blocks"],
+           "k1_wgs_bam": {"ms": float(k1.sum()), "ms_parts": [float(x) for x in k1], "algorithmic_bytes": bytes_k1,
+                          "achieved": bytes_k1 / (float(k1.sum()) * 1e-3) / 1e9, "unit": "GB/s", "peak": peak,
+                          "frac": bytes_k1 / (float(k1.sum()) * 1e-3) / 1e9 / peak, "candidates": int(n_cand)},
+           "k2_graph_ms": round(k2, 3), "k3_phase_ms": round(k3, 3), "stages_ms": stages}
+    del wgs, rna, bams
+    torch.cuda.empty_cache()
+    return out
 
 
 def algorithmic_bytes_k1(packed, n_variants, n_tuples):
@@ -452,6 +531,12 @@ def run_ours(a):
         "K3 blocks + phasing + counts (integer/latency bound, not an HBM figure)": {
             "ms": round(k3_ms, 3), "algorithmic_bytes": 12 * T + 44 * Ed + 8 * Vl + 32 * Bf,
             "achieved_gbs": (12 * T + 44 * Ed + 8 * Vl + 32 * Bf) / (k3_ms * 1e-3) / 1e9 if k3_ms else None}}
+    wgs = None
+    if rank == 0 and world == 1 and not a.no_wgs:
+        try:
+            wgs = wgs_leg(a, E, dev)
+        except Exception as e:          # a side measurement: never lose the main line over it
+            wgs = {"error": repr(e)[:300]}
     cpu = None
     cli = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -495,6 +580,7 @@ def run_ours(a):
         if replicas is not None:
             out["replicas"] = replicas
         out["stages_ms"] = stages
+        out["wgs_shape"] = wgs
         out["roofline_other_stages"] = other
         out["full_size_checks"] = checks
         print(json.dumps(out))

@@ -60,13 +60,13 @@ PHZ_HD u32 pair_cells_of(u32 ma, u32 mb) {
 
 struct FragCtx {
   const u32* vc;      // contig of every het site
-  const u8* gc;       // class | bam << 2 per kept tuple
   u64 excl_mask;      // BAMs left out of the haplotypic counts (phaser.py:1320, Q25)
   u64* vrank;         // per site: insertion key into the overlap dict (phaser.py:1271-1283), min wins
   const u32* abort;   // bit 3 set by the ranking pass: a fragment does not fit the stage, its slots hold nothing valid
 };
 
-// One fragment.  k[0..n): keys (variant << 32 | tuple index) in any order, info[0..n): scratch.  On return
+// One fragment.  k[0..n): keys (variant << 32 | tuple index) in any order, info[0..n): class | bam << 2 of the same tuples
+// (written next to the keys by the scatter pass, so no dependent look-up per tuple is needed here).  On return
 // k[0..ne) / info[0..ne) hold the fragment's (variant, BAM) entries sorted by (variant, BAM):
 // k = variant << 32 | first tuple with a reference / alternative call (NONE32 if none), info = bam << 3 | class mask.
 // Returns ne; adds groups / pairs to ng / np.
@@ -74,16 +74,16 @@ template <bool ONE_BAM, class Sink>
 PHZ_HD u32 process_fragment(const FragCtx& c, u64* k, uint16_t* info, u32 n, Sink& sink, u32& ng, u32& np) {
   // tuples arrive nearly sorted (record order = position order): insertion sort, stable because keys are unique
   for (u32 j = 1; j < n; ++j) {
-    u64 key = k[j]; u32 m = j;
-    while (m > 0 && k[m - 1] > key) { k[m] = k[m - 1]; --m; }
-    k[m] = key;
+    u64 key = k[j]; uint16_t cbj = info[j]; u32 m = j;
+    while (m > 0 && k[m - 1] > key) { k[m] = k[m - 1]; info[m] = info[m - 1]; --m; }
+    k[m] = key; info[m] = cbj;
   }
   if (ONE_BAM) {
     // one BAM: an entry is a distinct variant; no effective-BAM bookkeeping, no re-scans of equal-variant runs
     u32 ne = 0, cur_v = 0xFFFFFFFFu;
     for (u32 i = 0; i < n; ++i) {
       const u64 key = k[i]; const u32 v = (u32)(key >> 32), t = (u32)key;
-      const u32 cls = c.gc[t] & 3;
+      const u32 cls = info[i] & 3u;          // read before slot ne <= i is overwritten below
       if (v != cur_v) { k[ne] = ((u64)v << 32) | 0xFFFFFFFFu; info[ne] = 0; ++ne; cur_v = v; }
       info[ne - 1] = (uint16_t)(info[ne - 1] | (1u << cls));
       if (cls < 2 && (u32)k[ne - 1] == 0xFFFFFFFFu) k[ne - 1] = ((u64)v << 32) | t;
@@ -131,7 +131,7 @@ PHZ_HD u32 process_fragment(const FragCtx& c, u64* k, uint16_t* info, u32 n, Sin
   u32 ne = 0, cur_v = 0xFFFFFFFFu, cur_b = 0xFFFFFFFFu;
   for (u32 i = 0; i < n; ++i) {
     const u64 key = k[i]; const u32 v = (u32)(key >> 32), t = (u32)key;
-    const u32 cb = c.gc[t]; const u32 cls = cb & 3, bam = cb >> 2;
+    const u32 cb = info[i]; const u32 cls = cb & 3, bam = cb >> 2;          // read before slot ne <= i is overwritten below
     if (v != cur_v || bam != cur_b) { k[ne] = ((u64)v << 32) | 0xFFFFFFFFu; info[ne] = (uint16_t)(bam << 3); ++ne; cur_v = v; cur_b = bam; }
     info[ne - 1] = (uint16_t)(info[ne - 1] | (1u << cls));
     if (cls < 2 && (u32)k[ne - 1] == 0xFFFFFFFFu) k[ne - 1] = ((u64)v << 32) | t;
@@ -207,6 +207,7 @@ struct DirectSink {
 
 
 #ifdef __CUDACC__
+template <int VB_BAMS>
 struct CtaSink {
   u32* s_sz; u32* s_vb; u32 base; int nb; u32* sz; u32* vbc;
   unsigned long long* h_keys; u32* h_vals;       // shared: FRAG_HS keys, FRAG_HS * 5 words (two 16-bit counts per word)
@@ -217,7 +218,7 @@ struct CtaSink {
   }
   __device__ __forceinline__ void bam_count(u32 v, u32 bam, int a) {
     const u32 d = v - base;
-    if (d < (u32)FRAG_W && nb <= 4) atomicAdd(&s_vb[(d * nb + bam) * 2 + a], 1u);
+    if (d < (u32)FRAG_W && nb <= VB_BAMS) atomicAdd(&s_vb[(d * nb + bam) * 2 + a], 1u);
     else atomicAdd(&vbc[((int64_t)v * nb + bam) * 2 + a], 1u);
   }
   __device__ __forceinline__ void pair(u64 key, u32 cells) {
@@ -251,17 +252,20 @@ struct CtaSink {
 constexpr int FRAG_RANGE = FRAG_CTA * FRAG_PER_THREAD;
 
 template <bool ONE_BAM>
-__global__ void __launch_bounds__(FRAG_CTA, 5) fragment_kernel(FragCtx c, const u32* __restrict__ f_off, int64_t n_frag,
+__global__ void __launch_bounds__(FRAG_CTA, 6) fragment_kernel(FragCtx c, const u32* __restrict__ f_off, int64_t n_frag,
                                                                u64* __restrict__ fk, uint16_t* __restrict__ info,
                                                                u32* __restrict__ f_ne, int nb, u32* __restrict__ sz,
                                                                u32* __restrict__ vbc, PairTable pt,
                                                                unsigned long long* __restrict__ cnt3) {
+  constexpr int VB_BAMS = ONE_BAM ? 1 : 4;      // BAMs whose per-allele counts are staged in shared memory
   __shared__ u32 s_sz[FRAG_W * 3];
-  __shared__ u32 s_vb[FRAG_W * 2 * 4];
+  __shared__ u32 s_vb[FRAG_W * 2 * VB_BAMS];
   __shared__ unsigned long long h_keys[FRAG_HS];
   __shared__ u32 h_vals[FRAG_HS * 5];
   __shared__ u32 s_base;
-  __shared__ uint16_t s_list[FRAG_RANGE];       // single-tuple fragments from the front, the others from the back
+  // work lists: slot offsets (relative to the CTA's first slot) of the single-tuple fragments from the front,
+  // fragment indices of the others from the back
+  __shared__ u32 s_list[FRAG_RANGE];
   __shared__ u32 s_n1, s_nm, s_next1, s_nextm;
   const int tid = threadIdx.x, lane = tid & 31;
   const int64_t f0 = (int64_t)blockIdx.x * FRAG_RANGE;
@@ -270,7 +274,7 @@ __global__ void __launch_bounds__(FRAG_CTA, 5) fragment_kernel(FragCtx c, const 
   if (*c.abort & 8u) return;        // the host takes the sort-based stage instead
   if (o_first == o_last) return;    // no tuple in this range of fragments (f_ne aliases the tuple counts: already 0)
   for (int i = tid; i < FRAG_W * 3; i += FRAG_CTA) s_sz[i] = 0;
-  for (int i = tid; i < FRAG_W * 2 * 4; i += FRAG_CTA) s_vb[i] = 0;
+  for (int i = tid; i < FRAG_W * 2 * VB_BAMS; i += FRAG_CTA) s_vb[i] = 0;
   for (int i = tid; i < FRAG_HS; i += FRAG_CTA) h_keys[i] = PAIR_EMPTY;
   for (int i = tid; i < FRAG_HS * 5; i += FRAG_CTA) h_vals[i] = 0;
   if (tid == 0) {
@@ -282,21 +286,21 @@ __global__ void __launch_bounds__(FRAG_CTA, 5) fragment_kernel(FragCtx c, const 
   // ---- sort the range into the two lists (one shared-memory reduction per warp and list)
   for (int64_t b = f0 + (tid & ~31); b < f1; b += FRAG_CTA) {
     const int64_t f = b + lane;
-    u32 n = 0;
-    if (f < f1) n = f_off[f + 1] - f_off[f];
+    u32 n = 0, o0 = 0;
+    if (f < f1) { o0 = f_off[f]; n = f_off[f + 1] - o0; }
     const u32 m1 = __ballot_sync(0xFFFFFFFFu, n == 1), mm = __ballot_sync(0xFFFFFFFFu, n > 1);
     u32 b1 = 0, bm = 0;
     if (lane == 0) { if (m1) b1 = atomicAdd(&s_n1, (u32)__popc(m1)); if (mm) bm = atomicAdd(&s_nm, (u32)__popc(mm)); }
     b1 = __shfl_sync(0xFFFFFFFFu, b1, 0); bm = __shfl_sync(0xFFFFFFFFu, bm, 0);
     const u32 lt = (1u << lane) - 1u;
-    if (n == 1) s_list[b1 + __popc(m1 & lt)] = (uint16_t)(f - f0);
-    else if (n > 1) s_list[FRAG_RANGE - 1 - (bm + __popc(mm & lt))] = (uint16_t)(f - f0);
+    if (n == 1) s_list[b1 + __popc(m1 & lt)] = o0 - o_first;
+    else if (n > 1) s_list[FRAG_RANGE - 1 - (bm + __popc(mm & lt))] = (u32)(f - f0);
   }
   __syncthreads();
-  CtaSink sink{s_sz, s_vb, s_base, nb, sz, vbc, h_keys, h_vals, pt};
+  CtaSink<VB_BAMS> sink{s_sz, s_vb, s_base, nb, sz, vbc, h_keys, h_vals, pt};
   u32 ne_sum = 0, ng = 0, np = 0;
   const u32 n1 = s_n1, nm = s_nm;
-  // ---- single-tuple fragments: one entry, one group, no pair
+  // ---- single-tuple fragments: one entry, one group, no pair; f_ne = 1 is the tuple count already in place
   for (;;) {
     u32 start = 0;
     if (lane == 0) start = atomicAdd(&s_next1, 32u);
@@ -304,15 +308,14 @@ __global__ void __launch_bounds__(FRAG_CTA, 5) fragment_kernel(FragCtx c, const 
     if (start >= n1) break;
     const u32 i = start + lane;
     if (i < n1) {
-      const int64_t f = f0 + s_list[i];
-      const u32 o0 = f_off[f];
-      const u64 key = fk[o0]; const u32 v = (u32)(key >> 32), t = (u32)key;
-      const u32 cb = c.gc[t]; const u32 cls = cb & 3, bam = cb >> 2;
-      fk[o0] = cls < 2 ? key : (key | 0xFFFFFFFFull);
+      const u32 o0 = o_first + s_list[i];
+      const u64 key = fk[o0]; const u32 v = (u32)(key >> 32);
+      const u32 cb = info[o0]; const u32 cls = cb & 3, bam = cb >> 2;
+      if (cls >= 2) fk[o0] = key | 0xFFFFFFFFull;
       info[o0] = (uint16_t)((bam << 3) | (1u << cls));
       sink.set_size(v, (int)cls);
       if (cls < 2 && !((c.excl_mask >> bam) & 1)) sink.bam_count(v, bam, (int)cls);
-      f_ne[f] = 1; ++ne_sum; ++ng;
+      ++ne_sum; ++ng;
     }
   }
   // ---- the others
@@ -326,7 +329,8 @@ __global__ void __launch_bounds__(FRAG_CTA, 5) fragment_kernel(FragCtx c, const 
       const int64_t f = f0 + s_list[FRAG_RANGE - 1 - i];
       const u32 o0 = f_off[f], n = f_off[f + 1] - o0;
       const u32 ne = process_fragment<ONE_BAM>(c, fk + o0, info + o0, n, sink, ng, np);
-      f_ne[f] = ne; ne_sum += ne;
+      if (ne != n) f_ne[f] = ne;
+      ne_sum += ne;
     }
   }
   // counters: registers -> warp -> one reduction per warp
@@ -342,7 +346,7 @@ __global__ void __launch_bounds__(FRAG_CTA, 5) fragment_kernel(FragCtx c, const 
   for (int i = tid; i < FRAG_W; i += FRAG_CTA) {
     const int64_t v = (int64_t)base + i;
     for (int x = 0; x < 3; ++x) if (s_sz[i * 3 + x]) atomicAdd(&sz[v * 3 + x], s_sz[i * 3 + x]);
-    if (nb <= 4) for (int a = 0; a < nb * 2; ++a) if (s_vb[i * nb * 2 + a]) atomicAdd(&vbc[v * nb * 2 + a], s_vb[i * nb * 2 + a]);
+    if (nb <= VB_BAMS) for (int a = 0; a < nb * 2; ++a) if (s_vb[i * nb * 2 + a]) atomicAdd(&vbc[v * nb * 2 + a], s_vb[i * nb * 2 + a]);
   }
   for (int i = tid; i < FRAG_HS; i += FRAG_CTA) {
     const unsigned long long key = h_keys[i];

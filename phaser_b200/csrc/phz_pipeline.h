@@ -1047,14 +1047,15 @@ struct Pipeline {
       be.stage("graph.frag_scatter");
       be.for_each(n, PHZ_LAMBDA(int64_t t) {
         const u32 r = rk[t]; if (r == 65535u) return;
-        fk[fo[gf[t]] + r] = ((u64)gv[t] << 32) | (u64)(u32)t;
+        const u32 slot = fo[gf[t]] + r;
+        fk[slot] = ((u64)gv[t] << 32) | (u64)(u32)t; fi[slot] = (uint16_t)gc[t];
       });
       be.memset0(sz, Vn * 3 * sizeof(u32)); be.memset0(vbc, Vn * nb * 2 * sizeof(u32)); be.memset_ff(vr, Vn * sizeof(u64));
       u64* pk = pt_keys.ensure(S); u32* pv = pt_vals.ensure(S * PAIR_CELLS); u32* pf = pt_flags.ensure(4);
       be.memset_ff(pk, S * sizeof(u64)); be.memset0(pv, S * PAIR_CELLS * sizeof(u32)); be.memset0(pf, 4 * sizeof(u32));
       be.memset0(c3, 4 * sizeof(u64));
       PairTable pt{pk, pv, (u32)(S - 1), pf};
-      FragCtx fx{vc, gc, excl_mask, vr, sc + 1};
+      FragCtx fx{vc, excl_mask, vr, sc + 1};
       u32* fne = fc;                      // the counts are not needed any more: the slot becomes the entry count
       be.stage("graph.fragments");
 #ifdef __CUDACC__
@@ -1077,7 +1078,8 @@ struct Pipeline {
           const u32 o0 = fo[f], cnt = fo[f + 1] - o0; u32 ng = 0, np = 0, ne = 0;
           if (cnt) ne = nb == 1 ? process_fragment<true>(fx, fk + o0, fi + o0, cnt, sink, ng, np)
                                 : process_fragment<false>(fx, fk + o0, fi + o0, cnt, sink, ng, np);
-          fne[f] = ne; ne_sum += ne; ng_sum += ng; np_sum += np;
+          if (ne != cnt) fne[f] = ne;
+          ne_sum += ne; ng_sum += ng; np_sum += np;
         }
         c3[0] = ne_sum; c3[1] = ng_sum; c3[2] = np_sum;
         be.launches++;
