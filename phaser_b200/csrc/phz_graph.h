@@ -21,9 +21,18 @@ namespace phz {
 constexpr u64 PAIR_EMPTY = ~0ull;
 constexpr int PAIR_CELLS = 10;            // 9 co-occurrence cells n[x][y] at x*3+y, [9] = eligible fragments
 constexpr int FRAG_CTA = 256;             // threads per CTA of the fragment kernel
-constexpr int FRAG_PER_THREAD = 4;        // consecutive fragment ids per CTA = FRAG_CTA * FRAG_PER_THREAD
-constexpr int FRAG_W = 256;               // variant indices per shared-memory window
-constexpr int FRAG_HS = 512;              // slots of the CTA's pair hash
+#ifndef PHZ_FRAG_PER_THREAD
+#define PHZ_FRAG_PER_THREAD 8
+#endif
+#ifndef PHZ_FRAG_HS
+#define PHZ_FRAG_HS 512
+#endif
+#ifndef PHZ_FRAG_W
+#define PHZ_FRAG_W 256
+#endif
+constexpr int FRAG_PER_THREAD = PHZ_FRAG_PER_THREAD;   // consecutive fragment ids per CTA = FRAG_CTA * FRAG_PER_THREAD
+constexpr int FRAG_W = PHZ_FRAG_W;        // variant indices per shared-memory window
+constexpr int FRAG_HS = PHZ_FRAG_HS;      // slots of the CTA's pair hash
 
 PHZ_HD u32 pair_hash(u64 k) {
   k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 29;
@@ -250,6 +259,7 @@ struct CtaSink {
 // each, all lanes alike) and the rest -- and its warps then draw 32 fragments at a time from a shared cursor: every
 // lane of a round has work of the same kind, and a warp stuck on a deep fragment does not hold up the others.
 constexpr int FRAG_RANGE = FRAG_CTA * FRAG_PER_THREAD;
+static_assert(FRAG_RANGE <= 65536, "fragment indices inside a range are 16-bit, cell counts of a CTA's pair hash too");
 
 template <bool ONE_BAM>
 __global__ void __launch_bounds__(FRAG_CTA, 6) fragment_kernel(FragCtx c, const u32* __restrict__ f_off, int64_t n_frag,
@@ -263,9 +273,8 @@ __global__ void __launch_bounds__(FRAG_CTA, 6) fragment_kernel(FragCtx c, const 
   __shared__ unsigned long long h_keys[FRAG_HS];
   __shared__ u32 h_vals[FRAG_HS * 5];
   __shared__ u32 s_base;
-  // work lists: slot offsets (relative to the CTA's first slot) of the single-tuple fragments from the front,
-  // fragment indices of the others from the back
-  __shared__ u32 s_list[FRAG_RANGE];
+  // work lists (fragment index inside the range): single-tuple fragments from the front, the others from the back
+  __shared__ uint16_t s_list[FRAG_RANGE];
   __shared__ u32 s_n1, s_nm, s_next1, s_nextm;
   const int tid = threadIdx.x, lane = tid & 31;
   const int64_t f0 = (int64_t)blockIdx.x * FRAG_RANGE;
@@ -293,8 +302,8 @@ __global__ void __launch_bounds__(FRAG_CTA, 6) fragment_kernel(FragCtx c, const 
     if (lane == 0) { if (m1) b1 = atomicAdd(&s_n1, (u32)__popc(m1)); if (mm) bm = atomicAdd(&s_nm, (u32)__popc(mm)); }
     b1 = __shfl_sync(0xFFFFFFFFu, b1, 0); bm = __shfl_sync(0xFFFFFFFFu, bm, 0);
     const u32 lt = (1u << lane) - 1u;
-    if (n == 1) s_list[b1 + __popc(m1 & lt)] = o0 - o_first;
-    else if (n > 1) s_list[FRAG_RANGE - 1 - (bm + __popc(mm & lt))] = (u32)(f - f0);
+    if (n == 1) s_list[b1 + __popc(m1 & lt)] = (uint16_t)(f - f0);
+    else if (n > 1) s_list[FRAG_RANGE - 1 - (bm + __popc(mm & lt))] = (uint16_t)(f - f0);
   }
   __syncthreads();
   CtaSink<VB_BAMS> sink{s_sz, s_vb, s_base, nb, sz, vbc, h_keys, h_vals, pt};
@@ -308,7 +317,7 @@ __global__ void __launch_bounds__(FRAG_CTA, 6) fragment_kernel(FragCtx c, const 
     if (start >= n1) break;
     const u32 i = start + lane;
     if (i < n1) {
-      const u32 o0 = o_first + s_list[i];
+      const u32 o0 = f_off[f0 + s_list[i]];
       const u64 key = fk[o0]; const u32 v = (u32)(key >> 32);
       const u32 cb = info[o0]; const u32 cls = cb & 3, bam = cb >> 2;
       if (cls >= 2) fk[o0] = key | 0xFFFFFFFFull;

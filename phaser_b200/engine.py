@@ -15,7 +15,7 @@ import torch
 from .layout import ReadBatch, VariantTable, indel_tables
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_phz.so")
+LIB_PATH = os.environ.get("PHZ_LIB") or os.path.join(HERE, "_phz.so")      # PHZ_LIB: tuning builds of the same sources
 AS_BINS = 65536
 AS_NONE = -(2 ** 31)
 
