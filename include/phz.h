@@ -254,11 +254,78 @@ phz_host_reads* phz_read_alignments(const char* path, const char* const* contigs
                                     int remove_dups, int proper_pair, int min_mapq, int n_threads);
 int phz_host_reads_view(phz_host_reads* r, phz_reads* out, int* sorted_by_coordinate);
 void phz_host_reads_free(phz_host_reads* r);
+/* ---- native host VCF ingest (no GPU involved).  phz_vcf_open inflates the file (gzip or BGZF, BGZF blocks in
+ * parallel) and keeps the text; phz_vcf_parse applies, for one sample column, the reference's het-site filter:
+ * `gunzip -c VCF | cut -f 1-9,<col> | grep -v '0|0\|1|1'` (phaser.py:205-225), the per-line het / PASS test
+ * (:396-434) and the mapping-table rules incl. the indel exclusion (:1355-1413).  The table's pointers stay valid
+ * until the next phz_vcf_parse or phz_vcf_close on the handle.  Text fields (ids, rsids, alleles, GT strings) are NOT
+ * copied: var_line_off / var_line_len locate each site's line in the text returned by phz_vcf_text. */
+typedef struct phz_vcf phz_vcf;
+typedef struct phz_vcf_table {
+  int64_t n_variants;
+  int32_t n_contigs;
+  const int64_t* contig_var_off;   /* n_contigs+1; contigs in order of first appearance (phaser.py:410-411, 437-438) */
+  const int32_t* pos;              /* VCF POS */
+  const uint8_t* a0;               /* 4-bit base codes of the sample's two alleles (allele-index order), 0xFF = no single */
+  const uint8_t* a1;               /*   base, 0xFE = multi-base site resolved through phz_set_indel_alleles */
+  const int32_t* ref_len;          /* len(REF) */
+  const int64_t* var_line_off;     /* byte offset of the site's line in the text */
+  const int32_t* var_line_len;     /* its length without the newline */
+  const char* contig_names;        /* n_contigs NUL-terminated names, back to back (as written in the VCF) */
+  int32_t n_seen;                  /* chromosomes that reached the contig-name check (phaser.py:404-408), in order */
+  const char* seen_names;
+  int64_t stats[4];                /* het sites used, filtered (not PASS), indels excluded, unphased among the kept */
+} phz_vcf_table;
+phz_vcf* phz_vcf_open(const char* path, int n_threads);
+void phz_vcf_close(phz_vcf* v);
+int phz_vcf_text(phz_vcf* v, const char** text, int64_t* n_bytes, int64_t* n_lines, int* has_carriage_returns);
+/* first line containing "#CHR" (sample_column_map, phaser.py:2326-2342); off = -1 when there is none */
+int phz_vcf_chrom_line(phz_vcf* v, int64_t* off, int64_t* len);
+int phz_vcf_parse(phz_vcf* v, int sample_column, int pass_only, const char* chrom_of_interest, int include_indels,
+                  int n_threads, phz_vcf_table* out);
+
+/* Output VCF (write_vcf, phaser.py:1661-1845) from the text phz_vcf_open holds and the sites phz_vcf_parse numbered.
+ * Per site: the final block it sits in (or -1), which allele index haplotype A carries, and the genome-wide phase of its
+ * two alleles; per block: members (PB = their rsids), printed index (PI / PS), confidence string (PC), whether that
+ * confidence reaches --gw_phase_vcf_min_confidence, maf string (PM).  ids_match = 0 when --chr_prefix renames the
+ * contigs: the reference then matches no line (its ids carry the prefix, the lines do not).  Returns the text (valid
+ * until the next write / close) and counts[2] = (unphased sites phased genome-wide, phases corrected). */
+typedef struct phz_vcf_annot {
+  int32_t gw_phase_vcf;            /* 0, 1 or 2 */
+  int32_t ids_match;
+  const char* chrom_of_interest;   /* "" = all */
+  int64_t n_variants;
+  const int32_t* v_block;          /* [V] row of the blk_* arrays, -1 = in no phased block */
+  const uint8_t* v_hap;            /* [V] allele index on haplotype A */
+  const int8_t* v_gw;              /* [V][2] genome-wide phase of allele 0 / 1: 0, 1, or -1 = none */
+  int64_t n_blocks;
+  const int64_t* blk_first;        /* [B] first member in blk_members */
+  const int64_t* blk_len;          /* [B] */
+  const int32_t* blk_members;      /* site indices, position order */
+  const int32_t* blk_index;        /* [B] */
+  const uint8_t* blk_confident;    /* [B] */
+  const char* blk_stat;            /* B NUL-terminated strings, back to back */
+  const char* blk_maf;             /* B NUL-terminated strings, back to back */
+  const char* id_separator;        /* --id_separator and --chr_prefix: a member without an rsid is named by its id */
+  const char* chr_prefix;
+} phz_vcf_annot;
+int phz_vcf_write(phz_vcf* v, const phz_vcf_annot* annot, int n_threads, const char** text, int64_t* n_bytes, int64_t* counts);
+/* data lines of the last phz_vcf_write in file order: chromosome (index into n_names NUL-terminated names), 0-based
+ * reference span [beg, end) as tabix indexes it, byte offset of the line in the text */
+int phz_vcf_records(phz_vcf* v, int64_t* n, const int32_t** chrom, const int64_t** beg, const int64_t** end,
+                    const int64_t** text_off, const char** names, int32_t* n_names);
+
 /* SAM text twin of generated records: input for the reference baseline (test / bench infrastructure). */
 int phz_write_sam(const char* path, const char* const* contig_names, const int64_t* contig_lengths, int n_contigs, int64_t n,
                   const int64_t* contig, const int64_t* pos, const int64_t* tlen, const int64_t* flag, const int64_t* mapq,
                   const int64_t* aln, const int64_t* frag, const int64_t* ops, const int64_t* opl, int n_ops,
                   const uint8_t* bases, const uint8_t* qual, int read_len, const char* bam_name);
+
+/* BAM (BGZF) twin of the same records: the product's input in the files-to-files benchmark (test / bench infrastructure). */
+int phz_write_bam(const char* path, const char* const* contig_names, const int64_t* contig_lengths, int n_contigs, int64_t n,
+                  const int64_t* contig, const int64_t* pos, const int64_t* tlen, const int64_t* flag, const int64_t* mapq,
+                  const int64_t* aln, const int64_t* frag, const int64_t* ops, const int64_t* opl, int n_ops,
+                  const uint8_t* bases, const uint8_t* qual, int read_len, const char* bam_name, int n_threads);
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,8 @@ def compress_all(data: bytes, level=6, threads=0):
     (zlib releases the GIL).  Returns the list of compressed blocks in order; the EOF block is not included."""
     import os
     from concurrent.futures import ThreadPoolExecutor
-    cuts = [data[o:o + MAX_BLOCK] for o in range(0, len(data), MAX_BLOCK)]
+    mv = memoryview(data)
+    cuts = [bytes(mv[o:o + MAX_BLOCK]) for o in range(0, len(mv), MAX_BLOCK)]
     n = threads or min(16, os.cpu_count() or 1)
     if n <= 1 or len(cuts) < 4:
         return [compress_block(c, level) for c in cuts]

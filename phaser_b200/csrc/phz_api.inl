@@ -456,3 +456,4 @@ int phz_launch_counts(phz_ctx* ctx, uint64_t* own, uint64_t* library) {
 }  // extern "C"
 
 #include "phz_io.inl"
+#include "phz_vcf.inl"

@@ -87,27 +87,60 @@ struct FragDict {
   // ids for the kept records of one file (names[i], lens[i], hashes[i] in file order) -> out[i]
   void assign(const std::vector<const char*>& names, const std::vector<u32>& lens, const std::vector<u64>& hashes,
               std::vector<u32>& out, int n_threads) {
-    size_t n = names.size();
+    const size_t n = names.size();
     out.resize(n);
     std::vector<u32> ent(n);
+    // 1. record indices bucketed by shard (counting sort over fixed chunks: file order is kept inside a bucket)
+    const size_t CH = 1 << 16, nch = (n + CH - 1) / CH;
+    std::vector<u32> cnt(nch * NS + 1, 0);
+    parallel_for(nch, n_threads, [&](size_t c) {
+      u32* k = cnt.data() + c * NS;
+      const size_t i1 = std::min(n, (c + 1) * CH);
+      for (size_t i = c * CH; i < i1; ++i) k[shard_of(hashes[i])]++;
+    });
+    std::vector<size_t> start(nch * NS + 1, 0), sh_begin(NS + 1, 0);
+    { size_t acc = 0;
+      for (int s = 0; s < NS; ++s) { sh_begin[s] = acc; for (size_t c = 0; c < nch; ++c) { start[c * NS + s] = acc; acc += cnt[c * NS + s]; } }
+      sh_begin[NS] = acc; }
+    std::vector<u32> order(n);
+    parallel_for(nch, n_threads, [&](size_t c) {
+      size_t pos[NS];
+      for (int s = 0; s < NS; ++s) pos[s] = start[c * NS + s];
+      const size_t i1 = std::min(n, (c + 1) * CH);
+      for (size_t i = c * CH; i < i1; ++i) order[pos[shard_of(hashes[i])]++] = (u32)i;
+    });
+    // 2. every shard looks its own records up (in file order: first_rec is the first record of a new name)
     parallel_for(NS, n_threads, [&](size_t s) {
       Shard& S = sh[s];
-      for (size_t i = 0; i < n; ++i)
-        if ((size_t)shard_of(hashes[i]) == s) ent[i] = S.find_or_add(hashes[i], names[i], lens[i], (u64)i);
+      for (size_t k = sh_begin[s]; k < sh_begin[s + 1]; ++k) { const u32 i = order[k]; ent[i] = S.find_or_add(hashes[i], names[i], lens[i], (u64)i); }
     });
-    // new names get ids in order of first appearance: exclusive count of "first" records
-    size_t base = count, fresh = 0;
-    for (size_t i = 0; i < n; ++i) {
-      Shard& S = sh[shard_of(hashes[i])]; u32 e = ent[i];
-      if (S.gid[e] == 0xFFFFFFFFu && S.first_rec[e] == (u64)i) {
-        S.gid[e] = (u32)(base + fresh); fresh++;
-        id_shard.push_back((u8)shard_of(hashes[i])); id_ent.push_back(e);
+    // 3. new names get ids in order of first appearance: flag the first record of every new name, scan, hand out
+    std::vector<u32> pre(n + 1, 0);
+    std::vector<size_t> chunk_new(nch + 1, 0);
+    parallel_for(nch, n_threads, [&](size_t c) {
+      const size_t i1 = std::min(n, (c + 1) * CH); size_t k = 0;
+      for (size_t i = c * CH; i < i1; ++i) {
+        const Shard& S = sh[shard_of(hashes[i])]; const u32 e = ent[i];
+        const bool fresh = S.gid[e] == 0xFFFFFFFFu && S.first_rec[e] == (u64)i;
+        pre[i] = fresh ? 1u : 0u; k += fresh;
       }
-    }
-    count = base + fresh;
-    parallel_for((n + 65535) / 65536, n_threads, [&](size_t c) {
-      size_t i1 = std::min(n, (c + 1) * 65536);
-      for (size_t i = c * 65536; i < i1; ++i) out[i] = sh[shard_of(hashes[i])].gid[ent[i]];
+      chunk_new[c + 1] = k;
+    });
+    for (size_t c = 0; c < nch; ++c) chunk_new[c + 1] += chunk_new[c];
+    const size_t base = count, fresh_total = chunk_new[nch];
+    id_shard.resize(base + fresh_total); id_ent.resize(base + fresh_total);
+    parallel_for(nch, n_threads, [&](size_t c) {
+      const size_t i1 = std::min(n, (c + 1) * CH); size_t g = base + chunk_new[c];
+      for (size_t i = c * CH; i < i1; ++i)
+        if (pre[i]) {
+          const int s = shard_of(hashes[i]); const u32 e = ent[i];
+          sh[s].gid[e] = (u32)g; id_shard[g] = (u8)s; id_ent[g] = e; ++g;      // one writer per entry: its first record
+        }
+    });
+    count = base + fresh_total;
+    parallel_for(nch, n_threads, [&](size_t c) {
+      const size_t i1 = std::min(n, (c + 1) * CH);
+      for (size_t i = c * CH; i < i1; ++i) out[i] = sh[shard_of(hashes[i])].gid[ent[i]];
     });
   }
   u32 get(const char* s, size_t n) {      // single lookup (tests / small inputs)
@@ -343,6 +376,7 @@ static HostReads* parse_bam(const std::vector<u8>& d, const char* const* contigs
   }
   const size_t CH = 16384, n_chunks = (starts.size() + CH - 1) / CH;
   std::vector<std::vector<Rec>> parts(n_chunks);
+  double tp0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
   parallel_for(n_chunks, n_threads, [&](size_t c) {
     size_t i1 = std::min(starts.size(), (c + 1) * CH);
     std::vector<Rec>& out = parts[c];
@@ -368,12 +402,24 @@ static HostReads* parse_bam(const std::vector<u8>& d, const char* const* contigs
       out.push_back(r);
     }
   });
+  const bool timing = std::getenv("PHZ_IO_TIMING") != nullptr;
+  auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t0 = now();
+  if (timing) std::fprintf(stderr, "[phz_io] records: decode %.3fs\n", t0 - tp0);
   std::vector<Rec> recs;
   size_t total = 0; for (auto& v : parts) total += v.size();
-  recs.reserve(total);
-  for (auto& v : parts) { recs.insert(recs.end(), v.begin(), v.end()); std::vector<Rec>().swap(v); }
+  recs.resize(total);
+  { std::vector<size_t> at(parts.size() + 1, 0);
+    for (size_t c = 0; c < parts.size(); ++c) at[c + 1] = at[c] + parts[c].size();
+    parallel_for(parts.size(), n_threads, [&](size_t c) {
+      std::copy(parts[c].begin(), parts[c].end(), recs.begin() + at[c]); std::vector<Rec>().swap(parts[c]);
+    }); }
+  double t1 = now();
   assign_fragments(recs, fd, n_threads);
-  return build(recs, nc, n_threads);
+  double t2 = now();
+  HostReads* H = build(recs, nc, n_threads);
+  if (timing) std::fprintf(stderr, "[phz_io] records: merge %.3fs fragment ids %.3fs build %.3fs\n", t1 - t0, t2 - t1, now() - t2);
+  return H;
 }
 
 static void parse_sam_line(const u8* p, const u8* le, const char* const* contigs, int nc, int remove_dups, int proper_pair,
@@ -432,6 +478,7 @@ static HostReads* parse_sam(const std::vector<u8>& d, const char* const* contigs
   }
   cuts.push_back(end);
   std::vector<std::vector<Rec>> parts(cuts.size() - 1);
+  double tp0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
   parallel_for(parts.size(), n_threads, [&](size_t c) {
     const u8* p = cuts[c]; const u8* e = cuts[c + 1];
     while (p < e) {
@@ -441,12 +488,24 @@ static HostReads* parse_sam(const std::vector<u8>& d, const char* const* contigs
       p = eol + 1;
     }
   });
+  const bool timing = std::getenv("PHZ_IO_TIMING") != nullptr;
+  auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t0 = now();
+  if (timing) std::fprintf(stderr, "[phz_io] records: decode %.3fs\n", t0 - tp0);
   std::vector<Rec> recs;
   size_t total = 0; for (auto& v : parts) total += v.size();
-  recs.reserve(total);
-  for (auto& v : parts) { recs.insert(recs.end(), v.begin(), v.end()); std::vector<Rec>().swap(v); }
+  recs.resize(total);
+  { std::vector<size_t> at(parts.size() + 1, 0);
+    for (size_t c = 0; c < parts.size(); ++c) at[c + 1] = at[c] + parts[c].size();
+    parallel_for(parts.size(), n_threads, [&](size_t c) {
+      std::copy(parts[c].begin(), parts[c].end(), recs.begin() + at[c]); std::vector<Rec>().swap(parts[c]);
+    }); }
+  double t1 = now();
   assign_fragments(recs, fd, n_threads);
-  return build(recs, nc, n_threads);
+  double t2 = now();
+  HostReads* H = build(recs, nc, n_threads);
+  if (timing) std::fprintf(stderr, "[phz_io] records: merge %.3fs fragment ids %.3fs build %.3fs\n", t1 - t0, t2 - t1, now() - t2);
+  return H;
 }
 
 }  // namespace phzio
@@ -542,6 +601,114 @@ int phz_write_sam(const char* path, const char* const* contig_names, const int64
 // =============================================================================== packed transport (include/phz.h)
 // Host side of phz_packed_reads: offsets -> per-record counts, 4-bit bases -> 2 bits + exception list, phred bytes ->
 // indices into the table of distinct values.  Lossless; expanded again on the device by phz_map_reads_packed.
+// BAM (BGZF) twin of generated records: what the product's command line reads in the files-to-files benchmark while the
+// reference baseline gets the SAM text twin of the same records (test / bench infrastructure).  Records are encoded on
+// n_threads threads, the byte stream is cut into 0xff00-byte BGZF blocks that are deflated in parallel.
+int phz_write_bam(const char* path, const char* const* contig_names, const int64_t* contig_lengths, int n_contigs, int64_t n,
+                  const int64_t* contig, const int64_t* pos, const int64_t* tlen, const int64_t* flag, const int64_t* mapq,
+                  const int64_t* aln, const int64_t* frag, const int64_t* ops, const int64_t* opl, int n_ops,
+                  const uint8_t* bases, const uint8_t* qual, int read_len, const char* bam_name, int n_threads) {
+  PHZ_TRY
+  auto put32 = [](std::vector<u8>& o, u32 v) { o.push_back((u8)v); o.push_back((u8)(v >> 8)); o.push_back((u8)(v >> 16)); o.push_back((u8)(v >> 24)); };
+  std::vector<u8> head;
+  { std::string text = "@HD\tVN:1.6\tSO:coordinate\n";
+    for (int c = 0; c < n_contigs; ++c) text += std::string("@SQ\tSN:") + contig_names[c] + "\tLN:" + std::to_string((long long)contig_lengths[c]) + "\n";
+    head.insert(head.end(), {'B', 'A', 'M', 1});
+    put32(head, (u32)text.size()); head.insert(head.end(), text.begin(), text.end());
+    put32(head, (u32)n_contigs);
+    for (int c = 0; c < n_contigs; ++c) {
+      u32 l = (u32)std::strlen(contig_names[c]) + 1;
+      put32(head, l); head.insert(head.end(), contig_names[c], contig_names[c] + l); put32(head, (u32)contig_lengths[c]);
+    } }
+  const size_t CH = 1 << 15, nch = ((size_t)n + CH - 1) / CH;
+  std::vector<std::vector<u8>> parts(nch);
+  const size_t name_len = std::strlen(bam_name);
+  phzio::parallel_for(nch, n_threads, [&](size_t c) {
+    std::vector<u8>& o = parts[c];
+    o.reserve(CH * (size_t)(64 + read_len * 3 / 2));
+    const int64_t i1 = std::min<int64_t>(n, (int64_t)(c + 1) * (int64_t)CH);
+    char nm[96];
+    for (int64_t i = (int64_t)c * (int64_t)CH; i < i1; ++i) {
+      const int l_name = std::snprintf(nm, sizeof(nm), "%.*s.%lld", (int)(name_len > 60 ? 60 : name_len), bam_name, (long long)frag[i]) + 1;
+      u32 cig[64]; int nc = 0; int64_t ref_span = 0;
+      for (int j = 0; j < n_ops && nc < 64; ++j) {
+        const int64_t l = opl[i * n_ops + j]; const int op = (int)ops[i * n_ops + j];
+        if (l > 0) { cig[nc++] = ((u32)l << 4) | (u32)op; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ref_span += l; }
+      }
+      const int64_t beg = pos[i] - 1, end = beg + (ref_span > 0 ? ref_span : 1);
+      auto reg2bin = [](int64_t b, int64_t e) -> u32 {
+        --e;
+        if (b >> 14 == e >> 14) return (u32)(((1 << 15) - 1) / 7 + (b >> 14));
+        if (b >> 17 == e >> 17) return (u32)(((1 << 12) - 1) / 7 + (b >> 17));
+        if (b >> 20 == e >> 20) return (u32)(((1 << 9) - 1) / 7 + (b >> 20));
+        if (b >> 23 == e >> 23) return (u32)(((1 << 6) - 1) / 7 + (b >> 23));
+        if (b >> 26 == e >> 26) return (u32)(((1 << 3) - 1) / 7 + (b >> 26));
+        return 0;
+      };
+      const int64_t pn = tlen[i] > 0 ? (pos[i] + tlen[i] > 1 ? pos[i] + tlen[i] : 1) : pos[i];
+      const bool as8 = aln[i] >= 0 && aln[i] <= 255;
+      const u32 block = 32 + (u32)l_name + 4 * (u32)nc + (u32)(read_len + 1) / 2 + (u32)read_len + 4 + (as8 ? 4 : 5);
+      auto p32 = [&](u32 v) { o.push_back((u8)v); o.push_back((u8)(v >> 8)); o.push_back((u8)(v >> 16)); o.push_back((u8)(v >> 24)); };
+      p32(block); p32((u32)contig[i]); p32((u32)beg);
+      o.push_back((u8)l_name); o.push_back((u8)mapq[i]); const u32 bin = reg2bin(beg, end); o.push_back((u8)bin); o.push_back((u8)(bin >> 8));
+      o.push_back((u8)nc); o.push_back((u8)(nc >> 8)); o.push_back((u8)flag[i]); o.push_back((u8)(flag[i] >> 8));
+      p32((u32)read_len); p32((u32)contig[i]); p32((u32)(pn - 1)); p32((u32)(int32_t)tlen[i]);
+      o.insert(o.end(), nm, nm + l_name);
+      for (int j = 0; j < nc; ++j) p32(cig[j]);
+      const u8* b = bases + i * read_len;
+      for (int j = 0; j + 1 < read_len; j += 2) o.push_back((u8)(((b[j] & 15) << 4) | (b[j + 1] & 15)));
+      if (read_len & 1) o.push_back((u8)((b[read_len - 1] & 15) << 4));
+      o.insert(o.end(), qual + i * read_len, qual + (i + 1) * read_len);
+      o.push_back('N'); o.push_back('H'); o.push_back('C'); o.push_back(1);
+      o.push_back('A'); o.push_back('S');
+      if (as8) { o.push_back('C'); o.push_back((u8)aln[i]); }
+      else { o.push_back('s'); o.push_back((u8)aln[i]); o.push_back((u8)((uint16_t)(int16_t)aln[i] >> 8)); }
+    }
+  });
+  // one logical byte stream: header + parts; cut into BGZF blocks
+  std::vector<size_t> part_off(nch + 2, 0);
+  part_off[1] = head.size();
+  for (size_t c = 0; c < nch; ++c) part_off[c + 2] = part_off[c + 1] + parts[c].size();
+  const size_t total = part_off[nch + 1];
+  auto copy_out = [&](size_t from, size_t len, u8* dst) {
+    size_t k = std::upper_bound(part_off.begin(), part_off.end(), from) - part_off.begin() - 1;      // 0 = header, 1.. = parts
+    while (len) {
+      const std::vector<u8>& src = k == 0 ? head : parts[k - 1];
+      const size_t o = from - part_off[k]; const size_t take = std::min(len, src.size() - o);
+      std::memcpy(dst, src.data() + o, take); dst += take; from += take; len -= take; ++k;
+    }
+  };
+  const size_t BS = 0xff00, nblk = (total + BS - 1) / BS;
+  std::vector<std::vector<u8>> blocks(nblk);
+  phzio::parallel_for(nblk, n_threads, [&](size_t b) {
+    const size_t from = b * BS, len = std::min(BS, total - from);
+    std::vector<u8> raw(len); copy_out(from, len, raw.data());
+    std::vector<u8>& o = blocks[b];
+    o.resize(len + 1024);
+    z_stream zs; std::memset(&zs, 0, sizeof(zs));
+    if (deflateInit2(&zs, 1, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) throw PhzError("zlib deflate init failed");
+    zs.next_in = raw.data(); zs.avail_in = (uInt)len; zs.next_out = o.data() + 18; zs.avail_out = (uInt)(o.size() - 18 - 8);
+    if (deflate(&zs, Z_FINISH) != Z_STREAM_END) { deflateEnd(&zs); throw PhzError("BGZF deflate failed"); }
+    const size_t clen = zs.total_out; deflateEnd(&zs);
+    const u8 hdr[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0, 0};
+    std::memcpy(o.data(), hdr, 18);
+    const size_t bsize = 18 + clen + 8 - 1;
+    o[16] = (u8)bsize; o[17] = (u8)(bsize >> 8);
+    const u32 crc = (u32)crc32(crc32(0L, Z_NULL, 0), raw.data(), (uInt)len);
+    u8* t = o.data() + 18 + clen;
+    t[0] = (u8)crc; t[1] = (u8)(crc >> 8); t[2] = (u8)(crc >> 16); t[3] = (u8)(crc >> 24);
+    t[4] = (u8)len; t[5] = (u8)(len >> 8); t[6] = (u8)(len >> 16); t[7] = (u8)(len >> 24);
+    o.resize(18 + clen + 8);
+  });
+  FILE* f = std::fopen(path, "wb");
+  if (!f) throw PhzError(std::string("cannot write ") + path);
+  for (auto& b : blocks) std::fwrite(b.data(), 1, b.size(), f);
+  static const u8 eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  std::fwrite(eof, 1, 28, f);
+  std::fclose(f);
+  PHZ_CATCH
+}
+
 struct phz_packed_host {
   phz_packed_reads v;
   std::vector<std::pair<void*, bool>> bufs;      // (pointer, page-locked)

@@ -42,6 +42,19 @@ class phz_packed_reads(ctypes.Structure):
                 ("qual_bits", c_int32), ("qual_table", ctypes.c_uint8 * 256), ("qualp", c_void_p)]
 
 
+class phz_vcf_table(ctypes.Structure):
+    _fields_ = [("n_variants", c_int64), ("n_contigs", c_int32), ("contig_var_off", c_void_p), ("pos", c_void_p), ("a0", c_void_p),
+                ("a1", c_void_p), ("ref_len", c_void_p), ("var_line_off", c_void_p), ("var_line_len", c_void_p),
+                ("contig_names", c_void_p), ("n_seen", c_int32), ("seen_names", c_void_p), ("stats", c_int64 * 4)]
+
+
+class phz_vcf_annot(ctypes.Structure):
+    _fields_ = [("gw_phase_vcf", c_int32), ("ids_match", c_int32), ("chrom_of_interest", c_char_p), ("n_variants", c_int64),
+                ("v_block", c_void_p), ("v_hap", c_void_p), ("v_gw", c_void_p), ("n_blocks", c_int64), ("blk_first", c_void_p),
+                ("blk_len", c_void_p), ("blk_members", c_void_p), ("blk_index", c_void_p), ("blk_confident", c_void_p),
+                ("blk_stat", c_char_p), ("blk_maf", c_char_p), ("id_separator", c_char_p), ("chr_prefix", c_char_p)]
+
+
 class phz_ae_input(ctypes.Structure):
     _fields_ = [("n_rows", c_int64), ("row_contig", c_void_p), ("row_start", c_void_p), ("row_stop", c_void_p),
                 ("row_a", c_void_p), ("row_b", c_void_p), ("row_ids_a", c_void_p), ("row_ids_b", c_void_p),
@@ -58,7 +71,8 @@ EXPORTS = ["phz_last_error", "phz_backend_name", "phz_create", "phz_destroy", "p
            "phz_host_reads_view", "phz_host_reads_free", "phz_set_haplo_blacklist", "phz_write_sam",
            "phz_set_indel_alleles", "phz_pack_reads", "phz_packed_view", "phz_packed_bytes", "phz_packed_free",
            "phz_map_reads_packed", "phz_prefetch_packed", "phz_gene_ae_pairs", "phz_set_big_critical_values",
-           "phz_copy_array"]
+           "phz_copy_array", "phz_vcf_open", "phz_vcf_close", "phz_vcf_text", "phz_vcf_chrom_line", "phz_vcf_parse",
+           "phz_vcf_write", "phz_vcf_records", "phz_write_bam"]
 
 
 def _declare(lib):
@@ -81,6 +95,15 @@ def _declare(lib):
     lib.phz_download.argtypes = [c_void_p, c_char_p, c_void_p, c_int64]
     lib.phz_download_async.argtypes = [c_void_p, c_char_p, c_void_p, c_int64]
     lib.phz_copy_array.argtypes = [c_void_p, c_char_p, c_void_p, c_int64]
+    lib.phz_vcf_open.restype = c_void_p
+    lib.phz_vcf_open.argtypes = [c_char_p, c_int]
+    lib.phz_vcf_close.argtypes = [c_void_p]
+    lib.phz_vcf_text.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64), POINTER(c_int)]
+    lib.phz_vcf_chrom_line.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_int64)]
+    lib.phz_vcf_parse.argtypes = [c_void_p, c_int, c_int, c_char_p, c_int, c_int, POINTER(phz_vcf_table)]
+    lib.phz_vcf_write.argtypes = [c_void_p, POINTER(phz_vcf_annot), c_int, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64)]
+    lib.phz_vcf_records.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                                    POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int32)]
     lib.phz_counters.argtypes = [c_void_p, POINTER(c_int64)]
     lib.phz_launch_counts.argtypes = [c_void_p, POINTER(c_uint64), POINTER(c_uint64)]
     lib.phz_set_profiling.argtypes = [c_void_p, c_int]
@@ -168,8 +191,9 @@ class NativeFragmentDictionary:
             pass
 
 
-def write_sam_native(rec, contigs, path, bam_name="bam0", lib=None):
-    """synth.make_reads records -> SAM text through the native writer (50x faster than the Python loop)."""
+def write_sam_native(rec, contigs, path, bam_name="bam0", lib=None, bam=False, threads=0):
+    """synth.make_reads records -> SAM text through the native writer (50x faster than the Python loop); bam=True writes
+    the BGZF-compressed BAM twin of the same records instead (phz_write_bam)."""
     lib = lib if lib is not None else load_library()
     g = lambda k, dt=np.int64: np.ascontiguousarray(rec[k].cpu().numpy().astype(dt))
     c, pos, tl, fl, mq, aln, fr = (g(k) for k in ("contig", "pos", "tlen", "flag", "mapq", "aln", "frag"))
@@ -178,8 +202,14 @@ def write_sam_native(rec, contigs, path, bam_name="bam0", lib=None):
     lens = np.asarray([x[1] for x in contigs], np.int64)
     p = lambda a: a.ctypes.data_as(c_void_p)
     lib.phz_write_sam.argtypes = [c_char_p, POINTER(c_char_p), c_void_p, c_int, c_int64] + [c_void_p] * 9 + [c_int, c_void_p, c_void_p, c_int, c_char_p]
-    rc = lib.phz_write_sam(path.encode(), names, p(lens), len(contigs), pos.shape[0], p(c), p(pos), p(tl), p(fl), p(mq), p(aln),
-                           p(fr), p(ops), p(opl), ops.shape[1], p(bases), p(qual), bases.shape[1], bam_name.encode())
+    lib.phz_write_bam.argtypes = lib.phz_write_sam.argtypes + [c_int]
+    if bam:
+        rc = lib.phz_write_bam(path.encode(), names, p(lens), len(contigs), pos.shape[0], p(c), p(pos), p(tl), p(fl), p(mq), p(aln),
+                               p(fr), p(ops), p(opl), ops.shape[1], p(bases), p(qual), bases.shape[1], bam_name.encode(),
+                               int(threads or (os.cpu_count() or 1)))
+    else:
+        rc = lib.phz_write_sam(path.encode(), names, p(lens), len(contigs), pos.shape[0], p(c), p(pos), p(tl), p(fl), p(mq), p(aln),
+                               p(fr), p(ops), p(opl), ops.shape[1], p(bases), p(qual), bases.shape[1], bam_name.encode())
     if rc != 0:
         raise PhzError(lib.phz_last_error().decode())
     return path

@@ -120,11 +120,14 @@ def per_bam_lists(args, bam_list):
 
 
 _TRACE = bool(os.environ.get("PHZ_TRACE"))
+LAST_STAGE_SECONDS = {}          # stage -> seconds of the last run() in this process (bench.py reports them)
 
 
 def _trace(t0, what):
+    dt = time.perf_counter() - t0
+    LAST_STAGE_SECONDS[what] = LAST_STAGE_SECONDS.get(what, 0.0) + dt
     if _TRACE:
-        print("[phaser.py] %-28s %8.1f ms" % (what, (time.perf_counter() - t0) * 1e3), file=sys.stderr)
+        print("[phaser.py] %-28s %8.1f ms" % (what, dt * 1e3), file=sys.stderr)
     return time.perf_counter()
 
 
@@ -167,7 +170,17 @@ def run(args, engine=None):
     for b in bam_list:
         if b != "" and os.path.isfile(b) is False:
             fatal_error("File: %s not found." % b)
-    cols = vcfio.sample_column_map(args.vcf)
+    # the VCF is inflated and split into lines ONCE by the native library; the site table is parsed from that text on
+    # --threads host threads and the output VCF is written from it (blacklists still take the general Python parser)
+    from phaser_b200.engine import load_library
+    lib = engine.lib if engine is not None else load_library()
+    nv = None
+    try:
+        nv = vcfio.NativeVcf(args.vcf, lib, threads=max(1, args.threads))
+        cols = nv.sample_column_map()
+    except PhaserFatal:
+        nv = None
+        cols = vcfio.sample_column_map(args.vcf)
     if args.sample not in cols:
         fatal_error("Sample '%s' not found in the input VCF file." % args.sample)
     sample_column = cols[args.sample]
@@ -179,15 +192,30 @@ def run(args, engine=None):
     say('STARTED "Read backed phasing and ASE/haplotype analyses" ... ')
     say("    DATE, TIME : %s" % datetime.datetime.now().strftime('%Y-%m-%d, %H:%M:%S'))
     say("#1. Loading heterozygous variants into intervals...")
+    LAST_STAGE_SECONDS.clear()
     _t = time.perf_counter()
-    try:
-        vt, st = vcfio.parse_vcf(args.vcf, sample_column, pass_only=args.pass_only, chrom_of_interest=args.chr,
-                                 chr_prefix=args.chr_prefix, id_separator=args.id_separator,
-                                 include_indels=args.include_indels, gw_phase_method=args.gw_phase_method,
-                                 gw_af_field=args.gw_af_field, blacklist=args.blacklist,
-                                 haplo_count_blacklist=args.haplo_count_blacklist)
-    except PhaserFatal as e:
-        fatal_error(str(e))
+    vt = None
+    native_table = False
+    if nv is not None and args.blacklist == "" and args.haplo_count_blacklist == "":
+        try:
+            vt, st = vcfio.parse_vcf_native(nv, sample_column, pass_only=args.pass_only, chrom_of_interest=args.chr,
+                                            chr_prefix=args.chr_prefix, id_separator=args.id_separator,
+                                            include_indels=args.include_indels, gw_phase_method=args.gw_phase_method,
+                                            gw_af_field=args.gw_af_field)
+            native_table = True
+        except PhaserFatal as e:
+            if not ("malformed" in str(e) or "carriage" in str(e) or "POS is not" in str(e)):
+                fatal_error(str(e))
+            vt = None          # odd input: the general parser decides (and fails the way the reference does)
+    if vt is None:
+        try:
+            vt, st = vcfio.parse_vcf(args.vcf, sample_column, pass_only=args.pass_only, chrom_of_interest=args.chr,
+                                     chr_prefix=args.chr_prefix, id_separator=args.id_separator,
+                                     include_indels=args.include_indels, gw_phase_method=args.gw_phase_method,
+                                     gw_af_field=args.gw_af_field, blacklist=args.blacklist,
+                                     haplo_count_blacklist=args.haplo_count_blacklist)
+        except PhaserFatal as e:
+            fatal_error(str(e))
     say("          %d heterozygous sites being used for phasing (%d filtered, %d indels excluded, %d unphased)" % (
         st.het_count, st.filter_count, st.indels_excluded, st.unphased_count))
     say()
@@ -267,13 +295,23 @@ def run(args, engine=None):
     _t = _trace(_t, "text tables")
     if args.write_vcf == 1:
         say("#7. Outputting phased VCF...")
-        with gzip.open(args.vcf, "rt") as f:
-            text, unphased_phased, phase_corrected = out.vcf_text(
-                f, sample_column, id_separator=args.id_separator, gw_phase_vcf=args.gw_phase_vcf,
-                min_conf=args.gw_phase_vcf_min_confidence, chrom_of_interest=args.chr)
+        text = None
+        if native_table:
+            try:
+                text, unphased_phased, phase_corrected, records = out.vcf_native(
+                    nv, gw_phase_vcf=args.gw_phase_vcf, min_conf=args.gw_phase_vcf_min_confidence, chrom_of_interest=args.chr,
+                    id_separator=args.id_separator, chr_prefix=args.chr_prefix)
+            except writer.PhzUnsupported:
+                text = None
+        if text is None:
+            with gzip.open(args.vcf, "rt") as f:
+                text, unphased_phased, phase_corrected = out.vcf_text(
+                    f, sample_column, id_separator=args.id_separator, gw_phase_vcf=args.gw_phase_vcf,
+                    min_conf=args.gw_phase_vcf_min_confidence, chrom_of_interest=args.chr)
+            records = getattr(out, "vcf_records", None)
         # what `bgzip -f` + `tabix -f -p vcf [--csi]` write (phaser.py:1847-1853); --csi iff the input VCF has a .csi (:131)
-        tabix.write_vcf_with_index(args.o + ".vcf.gz", text, csi=os.path.isfile(args.vcf + ".csi"),
-                                   records=getattr(out, "vcf_records", None))
+        tabix.write_vcf_with_index(args.o + ".vcf.gz", text, csi=os.path.isfile(args.vcf + ".csi"), records=records)
+        text = None
     _t = _trace(_t, "vcf out")
     total_time = time.time() - start_time
     say('')

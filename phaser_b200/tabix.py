@@ -180,7 +180,7 @@ def write_vcf_with_index(path_vcf_gz, text, csi=False, records=None):
     are computed at once and every reference is indexed with array operations.  `records` = (chroms, begs, ends) of
     the data lines in file order when the caller already has them (the VCF writer does); otherwise the lines are split."""
     import numpy as np
-    data = text.encode()
+    data = text.encode() if isinstance(text, str) else text          # str, bytes or a memoryview of the native writer's text
     blocks = bgzf.compress_all(data)          # same bytes as BGZFWriter, blocks compressed in parallel
     with open(path_vcf_gz, "wb") as f:
         for b in blocks:
@@ -201,7 +201,19 @@ def write_vcf_with_index(path_vcf_gz, text, csi=False, records=None):
         return (cstart[b] << 16) | (u - b * bgzf.MAX_BLOCK)
     ds = starts[is_data]; de = ends[is_data]
     v0 = voff(ds); v1 = voff(de)
-    if records is not None and len(records[0]) == ds.shape[0]:
+    if records is not None and len(records) == 4 and len(records[0]) == ds.shape[0]:
+        # (chromosome index per line, names, begs, ends) as the native writer reports them: runs by array operations
+        cidx = np.asarray(records[0], np.int64); beg = np.asarray(records[2], np.int64); end = np.asarray(records[3], np.int64)
+        ib = IndexBuilder()
+        if cidx.shape[0]:
+            cut = np.concatenate([[0], np.flatnonzero(np.diff(cidx) != 0) + 1, [cidx.shape[0]]])
+            for k, m in zip(cut[:-1].tolist(), cut[1:].tolist()):
+                ib.add_many(records[1][int(cidx[k])], beg[k:m], end[k:m], v0[k:m], v1[k:m])
+        idx = path_vcf_gz + (".csi" if csi else ".tbi")
+        with bgzf.BGZFWriter(idx) as w:
+            w.write(ib.csi_bytes() if csi else ib.tbi_bytes())
+        return idx
+    if records is not None and len(records) == 3 and len(records[0]) == ds.shape[0]:
         chroms = records[0]; beg = np.asarray(records[1], np.int64); end = np.asarray(records[2], np.int64)
     else:
         chroms = []; b_ = []; e_ = []

@@ -204,3 +204,159 @@ def parse_vcf(path, sample_column: int, pass_only=1, chrom_of_interest="", chr_p
         if p.shape[0] > 1 and np.any(np.diff(p) < 0):
             raise PhaserFatal("VCF records of contig %s are not sorted by position." % contigs[c])
     return vt, st
+
+
+# ---------------------------------------------------------------------------------------------- native ingest
+
+class NativeVcf:
+    """The VCF held by the native library (include/phz.h: phz_vcf_open): inflated once (BGZF blocks in parallel), split
+    into lines once, parsed on --threads host threads, and written back out from the same text (phz_vcf_write)."""
+
+    def __init__(self, path, lib, threads=0):
+        import ctypes
+        import os
+        self.lib = lib
+        self.threads = int(threads or (os.cpu_count() or 1))
+        self.h = lib.phz_vcf_open(path.encode(), self.threads)
+        if not self.h:
+            raise PhaserFatal(lib.phz_last_error().decode())
+        p = ctypes.c_void_p(); n = ctypes.c_int64(0); nl = ctypes.c_int64(0); cr = ctypes.c_int(0)
+        lib.phz_vcf_text(self.h, ctypes.byref(p), ctypes.byref(n), ctypes.byref(nl), ctypes.byref(cr))
+        self.n_bytes = n.value; self.n_lines = nl.value; self.has_cr = bool(cr.value)
+        self.text = (ctypes.c_char * max(1, n.value)).from_address(p.value) if n.value else b""
+        self.mv = memoryview(self.text) if n.value else memoryview(b"")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.mv = None; self.text = None
+            self.lib.phz_vcf_close(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def line(self, off, n):
+        return bytes(self.mv[off:off + n]).decode()
+
+    def sample_column_map(self, start_col=9):
+        """phaser/phaser.py:2326-2342 on the text already in memory"""
+        import ctypes
+        off = ctypes.c_int64(0); n = ctypes.c_int64(0)
+        self.lib.phz_vcf_chrom_line(self.h, ctypes.byref(off), ctypes.byref(n))
+        out = OrderedDict()
+        if off.value >= 0:
+            cols = self.line(off.value, n.value).rstrip().split("\t")
+            for i in range(start_col, len(cols)):
+                out[cols[i]] = i
+        return out
+
+
+class _LazyColumn:
+    """One text column of the variant table, produced from the site's VCF line on demand: a whole-genome table has
+    millions of sites, the outputs name a fraction of them."""
+
+    def __init__(self, owner, kind):
+        self.o = owner; self.kind = kind
+
+    def __len__(self):
+        return self.o.n
+
+    def __bool__(self):
+        return self.o.n > 0
+
+    def __getitem__(self, v):
+        if isinstance(v, slice):
+            return [self[i] for i in range(*v.indices(self.o.n))]
+        return self.o.get(int(v))[self.kind]
+
+    def __iter__(self):
+        for i in range(self.o.n):
+            yield self[i]
+
+
+class _LazyRows:
+    def __init__(self, nv: NativeVcf, line_off, line_len, contig_name_of, sample_column, id_separator, gw_phase_method, gw_af_field):
+        self.nv = nv; self.off = line_off; self.len = line_len; self.cname = contig_name_of
+        self.col = sample_column; self.sep = id_separator; self.gwm = gw_phase_method; self.af = gw_af_field
+        self.n = int(line_off.shape[0])
+        self.cache = {}
+
+    def get(self, v):
+        r = self.cache.get(v)
+        if r is None:
+            if v < 0:
+                v += self.n
+            cols = self.nv.line(int(self.off[v]), int(self.len[v])).split("\t", self.col + 1)
+            cut = cols[0:9] + [cols[self.col]]
+            gi = cut[8].split(":").index("GT")
+            geno_string = cut[9].split(":")[gi]
+            xgeno = list(geno_string)
+            if "|" in xgeno:
+                xgeno.remove("|")
+            if "/" in xgeno:
+                xgeno.remove("/")
+            alt = cut[4].split(",")
+            all_alleles = [cut[3]] + alt
+            maf = None
+            if self.gwm == 1:
+                info = _annotation_to_dict(cut[7])
+                if self.af in info:
+                    afs = list(map(float, info[self.af].split(",")))
+                    if len(afs) == len(alt):
+                        use = [int(a) - 1 for a in xgeno if a != "." and int(a) != 0]
+                        if use:
+                            maf = min(min(afs[x], 1 - afs[x]) for x in use)
+            r = (self.cname(v) + self.sep + cut[1] + self.sep + self.sep.join(all_alleles), cut[2], all_alleles, geno_string, str(maf))
+            self.cache[v] = r
+        return r
+
+
+def parse_vcf_native(nv: NativeVcf, sample_column: int, pass_only=1, chrom_of_interest="", chr_prefix="", id_separator="_",
+                     include_indels=0, gw_phase_method=0, gw_af_field="AF"):
+    """parse_vcf through the native library (no blacklists: the caller takes parse_vcf for those).  Same VariantTable and
+    VcfStats; the text columns (ids, rsids, all_alleles, gt, maf) are produced from the VCF lines on demand."""
+    import ctypes
+    from .engine import phz_vcf_table
+    if nv.has_cr:
+        raise PhaserFatal("native VCF ingest: carriage returns in the file")        # the caller falls back to parse_vcf
+    t = phz_vcf_table()
+    rc = nv.lib.phz_vcf_parse(nv.h, int(sample_column), int(pass_only), chrom_of_interest.encode(), int(include_indels),
+                              nv.threads, ctypes.byref(t))
+    if rc != 0:
+        raise PhaserFatal(nv.lib.phz_last_error().decode())
+
+    def names(ptr, n):
+        out = []; p = ptr
+        for _ in range(n):
+            s = ctypes.string_at(p); out.append(s.decode()); p += len(s) + 1
+        return out
+
+    def arr(ptr, n, dt):
+        if n == 0 or not ptr:
+            return np.zeros(0, dt)
+        return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n,)).copy()
+
+    for chrom in names(t.seen_names, t.n_seen):                # phaser.py:404-408
+        for item in (id_separator, ":"):
+            if item in chrom:
+                raise PhaserFatal("Character '%s' must not be present in contig name. Please change id separtor "
+                                  "using --id_separator to a character not found in the contig names and try again." % item)
+    V = int(t.n_variants); nc = int(t.n_contigs)
+    raw_contigs = names(t.contig_names, nc)
+    contigs = [chr_prefix + c for c in raw_contigs]
+    off = arr(t.contig_var_off, nc + 1, np.int64)
+    pos = arr(t.pos, V, np.int32)
+    line_off = arr(t.var_line_off, V, np.int64); line_len = arr(t.var_line_len, V, np.int32)
+    st = VcfStats(int(t.stats[0]), int(t.stats[1]), int(t.stats[2]), int(t.stats[3]))
+    contig_idx = np.repeat(np.arange(nc, dtype=np.int64), np.diff(off)) if V else np.zeros(0, np.int64)
+    rows = _LazyRows(nv, line_off, line_len, lambda v: contigs[int(contig_idx[v])], sample_column, id_separator, gw_phase_method, gw_af_field)
+    vt = VariantTable(contigs, off, pos, arr(t.a0, V, np.uint8), arr(t.a1, V, np.uint8), arr(t.ref_len, V, np.int32),
+                      _LazyColumn(rows, 0), _LazyColumn(rows, 1), _LazyColumn(rows, 2), _LazyColumn(rows, 3), _LazyColumn(rows, 4))
+    vt.haplo_blacklisted = np.zeros(V, np.uint8)
+    for c in range(nc):
+        p = pos[off[c]:off[c + 1]]
+        if p.shape[0] > 1 and np.any(np.diff(p) < 0):
+            raise PhaserFatal("VCF records of contig %s are not sorted by position." % contigs[c])
+    return vt, st

@@ -18,6 +18,10 @@ import numpy as np
 from .pipeline import PhaseResult, edge_pvalues
 
 NONE32 = 0xFFFFFFFF
+
+
+class PhzUnsupported(Exception):
+    """the native writer met an input it leaves to the general Python writer"""
 NAN = float("nan")
 
 
@@ -61,6 +65,7 @@ class Outputs:
         for c in range(len(vt.contigs)):
             self.contig_of[int(vt.contig_var_off[c]):int(vt.contig_var_off[c + 1])] = c
         self.lookup = {}         # v -> (members, "a|b", block_index, max_maf)
+        self.block_stats = []; self.block_mafs = []          # per final block, in output order (native VCF writer)
         self.gw_stat_of = {}
         self.gw_phase = {}
         self.all_variants = []
@@ -262,6 +267,7 @@ class Outputs:
                         stat = max([stat, 1 - stat])
             max_maf = max(mafs)
             self.gw_stat_of[block_index] = stat
+            self.block_stats.append(stat); self.block_mafs.append(max_maf)
             for i, v in enumerate(variants):
                 self.lookup[v] = (variants, "%d|%d" % (hap_a[i], 1 - hap_a[i]), block_index, max_maf)
                 ai = ms[i].alleles.index(alleles[0][i])
@@ -345,6 +351,57 @@ class Outputs:
         return "".join(hp), "".join(hc), "".join(ac)
 
     # ------------------------------------------------------------------ VCF
+    def vcf_native(self, nv, gw_phase_vcf=0, min_conf=0.90, chrom_of_interest="", id_separator="_", chr_prefix=""):
+        """write_vcf (phaser.py:1661-1845) through the native writer (include/phz.h: phz_vcf_write) over the text the
+        native parser holds.  Must run after block_tables().  Returns (text bytes view, unphased_phased, phase_corrections,
+        records) with records = (chromosome index per data line, names, begs, ends) for the index; raises PhzUnsupported when
+        the input needs the general Python writer."""
+        import ctypes
+        from .engine import phz_vcf_annot
+        r = self.res; V = self.vt.n_variants
+        B = int(r.fb_first.shape[0])
+        v_block = np.where(r.v_final == NONE32, -1, r.v_final.astype(np.int64)).astype(np.int32)
+        v_hap = np.ascontiguousarray(r.v_hap, np.uint8)
+        gw = np.full((V, 2), -1, np.int8)
+        for v, g in self.gw_phase.items():
+            for k in (0, 1):
+                if isinstance(g[k], int):
+                    gw[v, k] = g[k]
+        first = np.ascontiguousarray(r.fb_first, np.int64); ln = np.ascontiguousarray(r.fb_len, np.int64)
+        members = np.ascontiguousarray(r.members.astype(np.int64), np.int32)
+        index = np.arange(1, B + 1, dtype=np.int32)
+        conf = np.asarray([1 if s >= min_conf else 0 for s in self.block_stats], np.uint8)
+        stat_blob = b"".join(str(s).encode() + b"\0" for s in self.block_stats) + b"\0"
+        maf_blob = b"".join(str(m).encode() + b"\0" for m in self.block_mafs) + b"\0"
+        if len(self.block_stats) != B:
+            raise RuntimeError("vcf_native must run after block_tables()")
+        a = phz_vcf_annot()
+        a.gw_phase_vcf = int(gw_phase_vcf); a.ids_match = 0 if chr_prefix else 1; a.chrom_of_interest = chrom_of_interest.encode()
+        a.id_separator = id_separator.encode(); a.chr_prefix = chr_prefix.encode()
+        a.n_variants = V; a.v_block = v_block.ctypes.data; a.v_hap = v_hap.ctypes.data; a.v_gw = gw.ctypes.data
+        a.n_blocks = B; a.blk_first = first.ctypes.data; a.blk_len = ln.ctypes.data; a.blk_members = members.ctypes.data
+        a.blk_index = index.ctypes.data; a.blk_confident = conf.ctypes.data; a.blk_stat = stat_blob; a.blk_maf = maf_blob
+        text = ctypes.c_void_p(); n = ctypes.c_int64(0); counts = (ctypes.c_int64 * 2)()
+        rc = nv.lib.phz_vcf_write(nv.h, ctypes.byref(a), nv.threads, ctypes.byref(text), ctypes.byref(n), counts)
+        if rc != 0:
+            msg = nv.lib.phz_last_error().decode()
+            raise PhzUnsupported(msg)
+        buf = (ctypes.c_char * max(1, n.value)).from_address(text.value) if n.value else b""
+        nr = ctypes.c_int64(0); pc = ctypes.c_void_p(); pb = ctypes.c_void_p(); pe = ctypes.c_void_p(); po = ctypes.c_void_p()
+        pn = ctypes.c_void_p(); nn = ctypes.c_int32(0)
+        nv.lib.phz_vcf_records(nv.h, ctypes.byref(nr), ctypes.byref(pc), ctypes.byref(pb), ctypes.byref(pe), ctypes.byref(po),
+                               ctypes.byref(pn), ctypes.byref(nn))
+
+        def arr(ptr, cnt, dt):
+            if cnt == 0 or not ptr.value:
+                return np.zeros(0, dt)
+            return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(cnt,)).copy()
+        names = []; p = pn.value
+        for _ in range(nn.value):
+            sname = ctypes.string_at(p); names.append(sname.decode()); p += len(sname) + 1
+        records = (arr(pc, nr.value, np.int32), names, arr(pb, nr.value, np.int64), arr(pe, nr.value, np.int64))
+        return memoryview(buf)[:n.value] if n.value else memoryview(b""), int(counts[0]), int(counts[1]), records
+
     def vcf_text(self, vcf_lines, sample_column, id_separator="_", gw_phase_vcf=0, min_conf=0.90, chrom_of_interest=""):
         """write_vcf (phaser.py:1661-1845).  Must run after block_tables().  Returns
         (text, unphased_phased, phase_corrections)."""
