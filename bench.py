@@ -602,7 +602,9 @@ def cpu_sample_files(a, tmp):
     from phaser_b200 import engine as eng
     sam = eng.write_sam_native(rec, g.contigs, os.path.join(tmp, "sample.bam"), bam_name="bam0")
     # the BGZF-compressed BAM twin of the same records: what the product's command line reads
-    eng.write_sam_native(rec, g.contigs, os.path.join(tmp, "sample.bgzf.bam"), bam_name="bam0", bam=True)
+    # (same basename in its own directory: the BAM's display name is part of haplotypic_counts.txt, phaser.py:469-480)
+    os.makedirs(os.path.join(tmp, "bgzf"), exist_ok=True)
+    eng.write_sam_native(rec, g.contigs, os.path.join(tmp, "bgzf", "sample.bam"), bam_name="bam0", bam=True)
     # gene spans of the synthetic genome as BED features (for the gene-level leg)
     ne = g.g_nexon.cpu().numpy(); es = g.exon_start.cpu().numpy(); el = g.exon_len.cpu().numpy(); gc = g.g_contig.cpu().numpy()
     with open(os.path.join(tmp, "genes.bed"), "w") as f:
@@ -681,7 +683,7 @@ def cli_files_to_files(a, engine):
     try:
         out = {"unit": "het-SNVs/s", "threads": os.cpu_count() or 1,
                "sample": "same %d-pair sample as cpu_baseline; process start-up and torch import not included" % n_pairs}
-        for name, bam in (("from_sam_text", sam), ("from_bgzf_bam", os.path.join(os.path.dirname(sam), "sample.bgzf.bam"))):
+        for name, bam in (("from_sam_text", sam), ("from_bgzf_bam", os.path.join(os.path.dirname(sam), "bgzf", "sample.bam"))):
             if not os.path.exists(bam):
                 continue
             argv = ["--vcf", vcf, "--bam", bam, "--sample", "S1", "--mapq", "255", "--baseq", "10", "--paired_end", "1",

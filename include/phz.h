@@ -315,6 +315,18 @@ int phz_vcf_write(phz_vcf* v, const phz_vcf_annot* annot, int n_threads, const c
 int phz_vcf_records(phz_vcf* v, int64_t* n, const int32_t** chrom, const int64_t** beg, const int64_t** end,
                     const int64_t** text_off, const char** names, int32_t* n_names);
 
+/* `bgzip -f` + `tabix -f -p vcf [--csi]` of the text of the last phz_vcf_write (phaser.py:1847-1853): writes path and
+ * path + ".tbi" (or ".csi"); BGZF blocks deflated on n_threads threads. */
+int phz_vcf_save(phz_vcf* v, const char* path_vcf_gz, int csi, int n_threads);
+
+/* aReads / bReads columns of haplotypic_counts.txt (phaser.py:1105-1115) for the requested rows: rl_* are the triples of
+ * phz_read_lists on the HOST (sorted by row); row r is named by row_key[r] (the packed block / BAM / haplotype key of
+ * "rl_row") and prints the variants row_vars[row_var_off[r] .. row_var_off[r+1]) in that order.  Reads are numbered by
+ * first occurrence inside the row.  text / row_text_off (n_rows+1 offsets) stay valid until the next call on the thread. */
+int phz_format_read_lists(int64_t n, const uint32_t* rl_row, const uint32_t* rl_var, const uint32_t* rl_frag, int64_t n_rows,
+                          const uint32_t* row_key, const int64_t* row_var_off, const uint32_t* row_vars, int n_threads,
+                          const char** text, const int64_t** row_text_off);
+
 /* SAM text twin of generated records: input for the reference baseline (test / bench infrastructure). */
 int phz_write_sam(const char* path, const char* const* contig_names, const int64_t* contig_lengths, int n_contigs, int64_t n,
                   const int64_t* contig, const int64_t* pos, const int64_t* tlen, const int64_t* flag, const int64_t* mapq,

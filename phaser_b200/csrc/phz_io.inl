@@ -37,6 +37,30 @@ static void parallel_for(size_t n, int n_threads, F f) {      // f(i) for i in [
   if (err) std::rethrow_exception(err);
 }
 
+// vector whose resize() leaves new elements uninitialised: a multi-hundred-megabyte buffer that is about to be filled by
+// parallel threads must not be zero-filled (and its pages first-touched) by ONE thread beforehand
+template <class T>
+struct NoInit : std::allocator<T> {
+  template <class U> struct rebind { typedef NoInit<U> other; };
+  NoInit() = default;
+  template <class U> NoInit(const NoInit<U>&) {}
+  template <class U, class... A> void construct(U* p, A&&... a) {
+    if constexpr (sizeof...(A) == 0) ::new ((void*)p) U; else ::new ((void*)p) U(std::forward<A>(a)...);
+  }
+};
+typedef std::vector<u8, NoInit<u8>> Bytes;
+
+// read-only view of a whole file: mapped, not copied (SAM text is parsed in place, BGZF blocks are inflated from it)
+static bool read_file(const char* path, std::vector<u8>& out);
+struct FileMap {
+  const u8* p = nullptr; size_t n = 0; bool mapped = false; std::vector<u8> fallback;
+  const u8* data() const { return p; }
+  size_t size() const { return n; }
+  u8 operator[](size_t i) const { return p[i]; }
+  bool open(const char* path);
+  ~FileMap();
+};
+
 static u64 name_hash(const char* s, size_t n) {
   u64 h = 1469598103934665603ull;
   for (size_t i = 0; i < n; ++i) { h ^= (u8)s[i]; h *= 1099511628211ull; }
@@ -153,8 +177,8 @@ struct FragDict {
 struct HostReads {
   int n_contigs = 0;
   std::vector<int64_t> contig_rec_off;
-  std::vector<int32_t> pos, tlen; std::vector<int16_t> aln; std::vector<u32> frag, cigar_off, cigar;
-  std::vector<u64> seq_off; std::vector<u8> seq, qual;
+  std::vector<int32_t, NoInit<int32_t>> pos, tlen; std::vector<int16_t, NoInit<int16_t>> aln; std::vector<u32, NoInit<u32>> frag, cigar;
+  std::vector<u32> cigar_off; std::vector<u64> seq_off; std::vector<u8> seq; Bytes qual;
   int sorted = 1;
   std::string error;
 };
@@ -167,8 +191,30 @@ static bool read_file(const char* path, std::vector<u8>& out) {
   return n == 0 || (bool)f.read((char*)out.data(), n);
 }
 
+}  // namespace phzio
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <fcntl.h>
+#include <unistd.h>
+namespace phzio {
+inline bool FileMap::open(const char* path) {
+  int fd = ::open(path, O_RDONLY);
+  if (fd < 0) return false;
+  struct stat st;
+  if (fstat(fd, &st) != 0) { ::close(fd); return false; }
+  n = (size_t)st.st_size;
+  if (n == 0) { ::close(fd); p = (const u8*)""; return true; }
+  void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+  ::close(fd);
+  if (m == MAP_FAILED) { if (!read_file(path, fallback)) return false; p = fallback.data(); n = fallback.size(); return true; }
+  p = (const u8*)m; mapped = true;
+  return true;
+}
+inline FileMap::~FileMap() { if (mapped && p) munmap((void*)p, n); }
+
 // ---- BGZF: index the blocks, inflate them in parallel into one buffer
-static void inflate_bgzf(const std::vector<u8>& in, std::vector<u8>& out, int n_threads) {
+template <class In, class Out>
+static void inflate_bgzf(const In& in, Out& out, int n_threads) {
   struct Blk { size_t in_off, in_len, out_off, out_len; };
   std::vector<Blk> blks;
   size_t p = 0, total = 0;
@@ -212,7 +258,8 @@ static void inflate_bgzf(const std::vector<u8>& in, std::vector<u8>& out, int n_
   if (bad) throw PhzError("BGZF inflate failed");
 }
 
-static void inflate_gzip_stream(const std::vector<u8>& in, std::vector<u8>& out) {
+template <class In, class Out>
+static void inflate_gzip_stream(const In& in, Out& out) {
   z_stream zs; std::memset(&zs, 0, sizeof(zs));
   if (inflateInit2(&zs, 31) != Z_OK) throw PhzError("zlib init failed");
   out.clear(); std::vector<u8> buf(1 << 20);
@@ -272,7 +319,8 @@ static int16_t as_from_aux(const u8* p, const u8* end, std::string& err) {
   return -32768;
 }
 
-static void assign_fragments(std::vector<Rec>& recs, FragDict* fd, int n_threads) {
+template <class RV>
+static void assign_fragments(RV& recs, FragDict* fd, int n_threads) {
   size_t n = recs.size();
   std::vector<const char*> names(n); std::vector<u32> lens(n); std::vector<u64> hashes(n); std::vector<u32> ids;
   parallel_for((n + 65535) / 65536, n_threads, [&](size_t c) {
@@ -291,7 +339,8 @@ static u32 count_cigar_ops(const Rec& r) {
   return nops;
 }
 
-static HostReads* build(std::vector<Rec>& recs, int nc, int n_threads) {
+template <class RV>
+static HostReads* build(RV& recs, int nc, int n_threads) {
   HostReads* H = new HostReads();
   H->n_contigs = nc;
   size_t R = recs.size();
@@ -355,7 +404,8 @@ static HostReads* build(std::vector<Rec>& recs, int nc, int n_threads) {
   return H;
 }
 
-static HostReads* parse_bam(const std::vector<u8>& d, const char* const* contigs, int nc, FragDict* fd, int remove_dups,
+template <class D>
+static HostReads* parse_bam(const D& d, const char* const* contigs, int nc, FragDict* fd, int remove_dups,
                             int proper_pair, int min_mapq, int n_threads) {
   auto rd32 = [&](size_t o) { return (int32_t)(d[o] | (d[o + 1] << 8) | (d[o + 2] << 16) | ((u32)d[o + 3] << 24)); };
   if (d.size() < 12 || std::memcmp(d.data(), "BAM\1", 4) != 0) throw PhzError("not a BAM file");
@@ -406,7 +456,7 @@ static HostReads* parse_bam(const std::vector<u8>& d, const char* const* contigs
   auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double t0 = now();
   if (timing) std::fprintf(stderr, "[phz_io] records: decode %.3fs\n", t0 - tp0);
-  std::vector<Rec> recs;
+  std::vector<Rec, NoInit<Rec>> recs;
   size_t total = 0; for (auto& v : parts) total += v.size();
   recs.resize(total);
   { std::vector<size_t> at(parts.size() + 1, 0);
@@ -462,7 +512,8 @@ static void parse_sam_line(const u8* p, const u8* le, const char* const* contigs
   out.push_back(r);
 }
 
-static HostReads* parse_sam(const std::vector<u8>& d, const char* const* contigs, int nc, FragDict* fd, int remove_dups,
+template <class D>
+static HostReads* parse_sam(const D& d, const char* const* contigs, int nc, FragDict* fd, int remove_dups,
                             int proper_pair, int min_mapq, int n_threads) {
   // chunk boundaries at line starts
   const u8* base = d.data(); const u8* end = base + d.size();
@@ -492,7 +543,7 @@ static HostReads* parse_sam(const std::vector<u8>& d, const char* const* contigs
   auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double t0 = now();
   if (timing) std::fprintf(stderr, "[phz_io] records: decode %.3fs\n", t0 - tp0);
-  std::vector<Rec> recs;
+  std::vector<Rec, NoInit<Rec>> recs;
   size_t total = 0; for (auto& v : parts) total += v.size();
   recs.resize(total);
   { std::vector<size_t> at(parts.size() + 1, 0);
@@ -530,24 +581,25 @@ int64_t phz_fragdict_name(phz_fragdict* d, int64_t id, char* buf, int64_t buflen
 phz_host_reads* phz_read_alignments(const char* path, const char* const* contigs, int n_contigs, phz_fragdict* fd,
                                     int remove_dups, int proper_pair, int min_mapq, int n_threads) {
   try {
-    std::vector<u8> raw;
+    phzio::FileMap raw;
     const bool timing = std::getenv("PHZ_IO_TIMING") != nullptr;
     auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t0 = now();
-    if (!phzio::read_file(path, raw)) throw PhzError(std::string("cannot read ") + path);
+    if (!raw.open(path)) throw PhzError(std::string("cannot read ") + path);
     double t1 = now();
-    std::vector<u8> data;
+    phzio::Bytes data;
     bool gz = raw.size() >= 18 && raw[0] == 0x1f && raw[1] == 0x8b;
     bool bgzf = gz && (raw[3] & 4) && raw[12] == 'B' && raw[13] == 'C';
     if (bgzf) phzio::inflate_bgzf(raw, data, n_threads);
     else if (gz) phzio::inflate_gzip_stream(raw, data);
-    else data.swap(raw);
     double t2 = now();
     phz_host_reads* out = new phz_host_reads();
-    if (data.size() >= 4 && std::memcmp(data.data(), "BAM\1", 4) == 0)
-      out->h = phzio::parse_bam(data, contigs, n_contigs, &fd->d, remove_dups, proper_pair, min_mapq, n_threads);
-    else
-      out->h = phzio::parse_sam(data, contigs, n_contigs, &fd->d, remove_dups, proper_pair, min_mapq, n_threads);
+    auto parse = [&](const auto& d) {
+      if (d.size() >= 4 && std::memcmp(d.data(), "BAM\1", 4) == 0)
+        return phzio::parse_bam(d, contigs, n_contigs, &fd->d, remove_dups, proper_pair, min_mapq, n_threads);
+      return phzio::parse_sam(d, contigs, n_contigs, &fd->d, remove_dups, proper_pair, min_mapq, n_threads);
+    };
+    out->h = gz ? parse(data) : parse(raw);
     if (timing) std::fprintf(stderr, "[phz_io] read %.3fs inflate %.3fs parse+build %.3fs (%lld records)\n", t1 - t0, t2 - t1,
                              now() - t2, (long long)out->h->pos.size());
     return out;

@@ -13,6 +13,7 @@
 #include <vector>
 #include <cstring>
 #include <algorithm>
+#include <map>
 
 namespace phzvcf {
 
@@ -96,7 +97,7 @@ static Geno read_geno(Span g) {
 enum LineKind : u8 { L_HEADER = 0, L_GREPPED, L_OTHER_CHROM, L_NO_GT, L_UNUSABLE, L_FILTERED, L_KEPT };
 
 struct Vcf {
-  std::vector<u8> text;
+  phzio::Bytes text;
   std::vector<u64> line_off;                 // n_lines + 1
   bool has_cr = false;
   // ---- result of the last parse
@@ -148,14 +149,14 @@ extern "C" {
 
 phz_vcf* phz_vcf_open(const char* path, int n_threads) {
   try {
-    std::vector<u8> raw;
-    if (!phzio::read_file(path, raw)) throw PhzError(std::string("cannot read ") + path);
+    phzio::FileMap raw;
+    if (!raw.open(path)) throw PhzError(std::string("cannot read ") + path);
     phz_vcf* h = new phz_vcf();
     bool gz = raw.size() >= 18 && raw[0] == 0x1f && raw[1] == 0x8b;
     bool bgzf = gz && (raw[3] & 4) && raw[12] == 'B' && raw[13] == 'C';
     if (bgzf) phzio::inflate_bgzf(raw, h->v.text, n_threads);
     else if (gz) phzio::inflate_gzip_stream(raw, h->v.text);
-    else h->v.text.swap(raw);
+    else h->v.text.assign(raw.data(), raw.data() + raw.size());
     phzvcf::index_lines(h->v, n_threads);
     return h;
   } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
@@ -595,6 +596,187 @@ int phz_vcf_records(phz_vcf* h, int64_t* n, const int32_t** chrom, const int64_t
   auto& v = h->v;
   *n = (int64_t)v.rec_chrom.size(); *chrom = v.rec_chrom.data(); *beg = v.rec_beg.data(); *end = v.rec_end.data();
   *text_off = v.rec_off.data(); *names = v.rec_names_blob.data(); *n_names = (int32_t)v.rec_names.size();
+  PHZ_CATCH
+}
+
+
+// ---------------------------------------------------------------------------------------------- bgzip + tabix of the output
+// What `bgzip -f` and `tabix -f -p vcf [--csi]` leave behind (phaser.py:1847-1853): the text of the last phz_vcf_write cut
+// into 0xff00-byte BGZF blocks (deflated in parallel) and the index of its data lines -- UCSC binning with min_shift 14 and
+// depth 5, one linear-index entry per 16 kb window, the pseudo-bin 37450 per reference, exactly as htslib writes them.
+}  // extern "C"
+namespace phzvcf {
+static void bgzf_block(const u8* raw, size_t len, std::vector<u8>& o, int level) {
+  o.resize(len + len / 8 + 1024);
+  z_stream zs; std::memset(&zs, 0, sizeof(zs));
+  if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) throw PhzError("zlib deflate init failed");
+  zs.next_in = (Bytef*)raw; zs.avail_in = (uInt)len; zs.next_out = o.data() + 18; zs.avail_out = (uInt)(o.size() - 18 - 8);
+  if (deflate(&zs, Z_FINISH) != Z_STREAM_END) { deflateEnd(&zs); throw PhzError("BGZF deflate failed"); }
+  const size_t clen = zs.total_out; deflateEnd(&zs);
+  const u8 hdr[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0, 0};
+  std::memcpy(o.data(), hdr, 18);
+  const size_t bsize = 18 + clen + 8 - 1;
+  o[16] = (u8)bsize; o[17] = (u8)(bsize >> 8);
+  const u32 crc = (u32)crc32(crc32(0L, Z_NULL, 0), raw, (uInt)len);
+  u8* t = o.data() + 18 + clen;
+  t[0] = (u8)crc; t[1] = (u8)(crc >> 8); t[2] = (u8)(crc >> 16); t[3] = (u8)(crc >> 24);
+  t[4] = (u8)len; t[5] = (u8)(len >> 8); t[6] = (u8)(len >> 16); t[7] = (u8)(len >> 24);
+  o.resize(18 + clen + 8);
+}
+static const u8 BGZF_EOF[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+static void write_bgzf_file(const char* path, const u8* data, size_t n, int n_threads, std::vector<size_t>* sizes) {
+  const size_t BS = 0xff00, nblk = (n + BS - 1) / BS;
+  std::vector<std::vector<u8>> blocks(nblk);
+  phzio::parallel_for(nblk, n_threads, [&](size_t b) { bgzf_block(data + b * BS, std::min(BS, n - b * BS), blocks[b], 6); });
+  FILE* f = std::fopen(path, "wb");
+  if (!f) throw PhzError(std::string("cannot write ") + path);
+  for (auto& b : blocks) std::fwrite(b.data(), 1, b.size(), f);
+  std::fwrite(BGZF_EOF, 1, 28, f);
+  std::fclose(f);
+  if (sizes) { sizes->clear(); for (auto& b : blocks) sizes->push_back(b.size()); }
+}
+struct RefIndex { std::map<u32, std::vector<std::pair<u64, u64>>> bins; std::vector<u64> lin; u64 first = 0, last = 0, n = 0; int64_t last_bin = -1; };
+static u32 reg2bin14(int64_t beg, int64_t end) {
+  --end;
+  int s = 14; u32 t = ((1u << 15) - 1) / 7;
+  for (int level = 5; level > 0; --level) { if (beg >> s == end >> s) return t + (u32)(beg >> s); s += 3; t -= 1u << (3 * (level - 1)); }
+  return 0;
+}
+static u64 bin_start_window(u32 b) {
+  u32 t = 0;
+  for (int level = 0; level <= 5; ++level) { u32 n = 1u << (3 * level); if (b < t + n) return (u64)(b - t) << (3 * (5 - level)); t += n; }
+  return 0;
+}
+template <class T> static void put(std::vector<u8>& o, T v) { for (size_t i = 0; i < sizeof(T); ++i) o.push_back((u8)((u64)v >> (8 * i))); }
+}  // namespace phzvcf
+extern "C" {
+
+int phz_vcf_save(phz_vcf* h, const char* path_vcf_gz, int csi, int n_threads) {
+  PHZ_TRY
+  using namespace phzvcf;
+  auto& v = h->v;
+  const u8* data = (const u8*)v.out_text.data(); const size_t n = v.out_text.size();
+  std::vector<size_t> sizes;
+  write_bgzf_file(path_vcf_gz, data, n, n_threads, &sizes);
+  std::vector<u64> cstart(sizes.size() + 1, 0);
+  for (size_t b = 0; b < sizes.size(); ++b) cstart[b + 1] = cstart[b] + sizes[b];
+  auto voff = [&](u64 u) { const u64 b = u / 0xff00; return (cstart[b] << 16) | (u - b * 0xff00); };
+  std::vector<RefIndex> refs(v.rec_names.size());
+  std::vector<int> order; std::vector<char> seen(v.rec_names.size(), 0);
+  const size_t NR = v.rec_chrom.size();
+  for (size_t k = 0; k < NR; ++k) {
+    const int c = v.rec_chrom[k];
+    if (!seen[c]) { seen[c] = 1; order.push_back(c); }
+    RefIndex& r = refs[c];
+    int64_t beg = v.rec_beg[k], end = v.rec_end[k];
+    if (end <= beg) end = beg + 1;
+    const u64 o0 = (u64)v.rec_off[k];
+    const u8* nl = (const u8*)std::memchr(data + o0, '\n', n - o0);
+    const u64 o1 = nl ? (u64)(nl - data) + 1 : n;
+    const u64 v0 = voff(o0), v1 = voff(o1);
+    const u32 b = reg2bin14(beg, end);
+    auto& chunks = r.bins[b];
+    if (r.last_bin == (int64_t)b && !chunks.empty() && chunks.back().second == v0) chunks.back().second = v1;
+    else chunks.emplace_back(v0, v1);
+    r.last_bin = b;
+    const u64 w0 = (u64)beg >> 14, w1 = (u64)(end - 1) >> 14;
+    if (r.lin.size() <= w1) r.lin.resize(w1 + 1, 0);
+    for (u64 w = w0; w <= w1; ++w) if (r.lin[w] == 0) r.lin[w] = v0;
+    if (r.n == 0) r.first = v0;
+    r.last = v1; r.n++;
+  }
+  std::vector<u8> aux;
+  { std::string names; for (int c : order) { names += v.rec_names[c]; names.push_back('\0'); }
+    for (int32_t x : {2, 1, 2, 0, (int32_t)'#', 0, (int32_t)names.size()}) put<int32_t>(aux, x);
+    aux.insert(aux.end(), names.begin(), names.end()); }
+  const u32 META = ((1u << 18) - 1) / 7 + 1;
+  std::vector<u8> out;
+  if (!csi) { out.insert(out.end(), {'T', 'B', 'I', 1}); put<int32_t>(out, (int32_t)order.size()); out.insert(out.end(), aux.begin(), aux.end()); }
+  else { out.insert(out.end(), {'C', 'S', 'I', 1}); put<int32_t>(out, 14); put<int32_t>(out, 5); put<int32_t>(out, (int32_t)aux.size());
+         out.insert(out.end(), aux.begin(), aux.end()); put<int32_t>(out, (int32_t)order.size()); }
+  for (int c : order) {
+    RefIndex& r = refs[c];
+    for (size_t i = 1; i < r.lin.size(); ++i) if (r.lin[i] == 0) r.lin[i] = r.lin[i - 1];      // empty windows point at the previous one
+    put<int32_t>(out, (int32_t)r.bins.size() + 1);
+    for (auto& kv : r.bins) {
+      put<u32>(out, kv.first);
+      if (csi) { const u64 w = bin_start_window(kv.first); put<u64>(out, w < r.lin.size() ? r.lin[w] : (r.lin.empty() ? 0 : r.lin.back())); }
+      put<int32_t>(out, (int32_t)kv.second.size());
+      for (auto& ch : kv.second) { put<u64>(out, ch.first); put<u64>(out, ch.second); }
+    }
+    put<u32>(out, META); if (csi) put<u64>(out, 0); put<int32_t>(out, 2);
+    put<u64>(out, r.first); put<u64>(out, r.last); put<u64>(out, r.n); put<u64>(out, 0);
+    if (!csi) { put<int32_t>(out, (int32_t)r.lin.size()); for (u64 x : r.lin) put<u64>(out, x); }
+  }
+  put<u64>(out, 0);
+  const std::string idx = std::string(path_vcf_gz) + (csi ? ".csi" : ".tbi");
+  write_bgzf_file(idx.c_str(), out.data(), out.size(), n_threads, nullptr);
+  PHZ_CATCH
+}
+
+
+// ---------------------------------------------------------------------------------------------- aReads / bReads columns
+// haplotypic_counts.txt, columns 17-18 (phaser.py:1105-1115): per row (final block, BAM, haplotype) and per listed variant
+// the reads that carry the haplotype's allele there, as indices into the row's list of distinct reads.  The reference's
+// numbering follows CPython's set order; the canonical form is first-occurrence order inside the row, which is
+// what the only consumer needs (ids are opaque per row).  Input: the read-list triples of phz_read_lists (sorted by row,
+// then variant rank, then tuple order); for every requested row its key and the variants to print, in order.  Output: one
+// string per row, variants ';'-joined, indices ','-joined (a variant without reads in the row gives an empty field).
+static thread_local std::string g_rl_text;
+static thread_local std::vector<int64_t> g_rl_off;
+
+int phz_format_read_lists(int64_t n, const uint32_t* rl_row, const uint32_t* rl_var, const uint32_t* rl_frag, int64_t n_rows,
+                          const uint32_t* row_key, const int64_t* row_var_off, const uint32_t* row_vars, int n_threads,
+                          const char** text, const int64_t** row_text_off) {
+  PHZ_TRY
+  std::vector<std::string> out((size_t)n_rows);
+  phzio::parallel_for((size_t)((n_rows + 255) / 256), n_threads, [&](size_t blk) {
+    std::vector<u32> hk; std::vector<u32> hv;            // open addressing: fragment -> label, rebuilt per row
+    char num[16];
+    for (int64_t r = (int64_t)blk * 256; r < n_rows && r < (int64_t)(blk + 1) * 256; ++r) {
+      const u32 key = row_key[r];
+      const uint32_t* lo = std::lower_bound(rl_row, rl_row + n, key);
+      const uint32_t* hi = std::upper_bound(lo, rl_row + n, key);
+      int64_t a = lo - rl_row; const int64_t b = hi - rl_row;
+      size_t cap = 16; while (cap < (size_t)(b - a) * 2 + 2) cap <<= 1;
+      hk.assign(cap, 0xFFFFFFFFu); hv.assign(cap, 0);
+      u32 next = 0;
+      std::string& o = out[r];
+      for (int64_t k = row_var_off[r]; k < row_var_off[r + 1]; ++k) {
+        if (k > row_var_off[r]) o.push_back(';');
+        const u32 var = row_vars[k];
+        // the row's entries come in the order of the block's variants; skip variants that are not asked for
+        while (a < b && rl_var[a] != var) {
+          bool later = false;
+          for (int64_t kk = k + 1; kk < row_var_off[r + 1]; ++kk) if (row_vars[kk] == rl_var[a]) { later = true; break; }
+          if (later) break;
+          ++a;
+        }
+        bool first = true;
+        while (a < b && rl_var[a] == var) {
+          const u32 f = rl_frag[a];
+          size_t p = (size_t)(f * 2654435761u) & (cap - 1);
+          while (hk[p] != 0xFFFFFFFFu && hk[p] != f) p = (p + 1) & (cap - 1);
+          if (hk[p] == 0xFFFFFFFFu) { hk[p] = f; hv[p] = next++; }
+          if (!first) o.push_back(',');
+          first = false;
+          int len = 0; u32 x = hv[p];
+          do { num[len++] = (char)('0' + x % 10); x /= 10; } while (x);
+          while (len) o.push_back(num[--len]);
+          ++a;
+        }
+      }
+    }
+  });
+  g_rl_off.assign((size_t)n_rows + 1, 0);
+  for (int64_t r = 0; r < n_rows; ++r) g_rl_off[r + 1] = g_rl_off[r] + (int64_t)out[r].size();
+  g_rl_text.resize((size_t)g_rl_off[n_rows]);
+  char* dst = g_rl_text.data(); const int64_t* off = g_rl_off.data();      // (thread_local: the workers must not name them)
+  phzio::parallel_for((size_t)((n_rows + 255) / 256), n_threads, [&, dst, off](size_t blk) {
+    for (int64_t r = (int64_t)blk * 256; r < n_rows && r < (int64_t)(blk + 1) * 256; ++r)
+      if (!out[r].empty()) std::memcpy(dst + off[r], out[r].data(), out[r].size());
+  });
+  *text = g_rl_text.data(); *row_text_off = g_rl_off.data();
   PHZ_CATCH
 }
 

@@ -268,7 +268,7 @@ def run(args, engine=None):
     say("     sequencing noise level estimated at %f" % res.noise_e)
     out = writer.Outputs(res, vt, bam_names, P, unphased_vars=args.unphased_vars, gw_phase_method=args.gw_phase_method,
                          unique_ids=args.unique_ids, read_names=fd.names if args.output_read_ids == 1 else None,
-                         output_network=args.output_network)
+                         output_network=args.output_network, lib=engine.lib, threads=max(1, args.threads))
     with open(args.o + ".variant_connections.txt", "w") as f:
         f.write(out.variant_connections())
     say("     %d variant connections dropped because of conflicting configurations (threshold = %f)" % (
@@ -310,8 +310,12 @@ def run(args, engine=None):
                     min_conf=args.gw_phase_vcf_min_confidence, chrom_of_interest=args.chr)
             records = getattr(out, "vcf_records", None)
         # what `bgzip -f` + `tabix -f -p vcf [--csi]` write (phaser.py:1847-1853); --csi iff the input VCF has a .csi (:131)
-        tabix.write_vcf_with_index(args.o + ".vcf.gz", text, csi=os.path.isfile(args.vcf + ".csi"), records=records)
-        text = None
+        if text is not None and native_table and records is not None and len(records) == 4:
+            text = None
+            out.vcf_save_native(nv, args.o + ".vcf.gz", csi=os.path.isfile(args.vcf + ".csi"))
+        else:
+            tabix.write_vcf_with_index(args.o + ".vcf.gz", text, csi=os.path.isfile(args.vcf + ".csi"), records=records)
+            text = None
     _t = _trace(_t, "vcf out")
     total_time = time.time() - start_time
     say('')

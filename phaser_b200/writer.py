@@ -52,10 +52,11 @@ class VariantMeta:
 
 class Outputs:
     def __init__(self, res: PhaseResult, vt, bam_names, params, unphased_vars=1, gw_phase_method=0, unique_ids=0,
-                 read_names=None, output_network=""):
+                 read_names=None, output_network="", lib=None, threads=0):
         """`read_names` (QNAME per fragment id) switches the --output_read_ids 1 columns on (phaser.py:837-838);
         `output_network` names the variant whose block is dumped as a network (phaser.py:1128-1157)."""
         self.output_network = output_network
+        self.lib = lib; self.threads = int(threads or 0)         # native formatter of the aReads / bReads columns (optional)
         self.network = None        # (links text, nodes text) once block_tables() met the block
         self.res = res; self.vt = vt; self.bam_names = bam_names; self.P = params
         self.read_names = read_names
@@ -129,6 +130,28 @@ class Outputs:
         for s, e in zip(starts.tolist(), ends.tolist()):
             rows.setdefault(int(row[s]), OrderedDict())[int(var[s])] = frag[s:e].tolist()
         return rows
+
+    def _format_read_lists_native(self, keys, offs, variants):
+        """aReads / bReads columns of the requested rows through the native formatter (phz_format_read_lists)"""
+        import ctypes
+        import os
+        r = self.res
+        row = np.ascontiguousarray(r.rl_row, np.uint32); var = np.ascontiguousarray(r.rl_var, np.uint32)
+        frag = np.ascontiguousarray(r.rl_frag, np.uint32)
+        k = np.asarray(keys, np.uint32); o = np.asarray(offs, np.int64); v = np.asarray(variants if variants else [0], np.uint32)
+        text = ctypes.c_void_p(); toff = ctypes.c_void_p()
+        rc = self.lib.phz_format_read_lists(int(row.shape[0]), row.ctypes.data, var.ctypes.data, frag.ctypes.data, int(k.shape[0]),
+                                            k.ctypes.data, o.ctypes.data, v.ctypes.data, self.threads or (os.cpu_count() or 1),
+                                            ctypes.byref(text), ctypes.byref(toff))
+        if rc != 0:
+            raise RuntimeError(self.lib.phz_last_error().decode())
+        n = int(k.shape[0])
+        off = np.ctypeslib.as_array(ctypes.cast(toff, ctypes.POINTER(ctypes.c_int64)), shape=(n + 1,))
+        total = int(off[n])
+        buf = ctypes.string_at(text.value, total) if total else b""
+        s = buf.decode()
+        ol = off.tolist()
+        return [s[ol[i]:ol[i + 1]] for i in range(n)]
 
     def _read_id_columns(self, frag_lists):
         """read_ids_a / read_ids_b of one row: the distinct QNAMEs of `frag_lists` in first-occurrence order, i.e.
@@ -209,7 +232,9 @@ class Outputs:
                          'reads_hap_a', 'reads_hap_b', 'reads_total', 'edges_supporting', 'edges_total',
                          'annotated_phase', 'phase_concordant', 'gw_phase', 'gw_confidence']) + "\n"]
         ac = ["\t".join(['variant_a', 'rsid_a', 'variant_b', 'rsid_b', 'configuration']) + "\n"]
-        rl = self._read_list_rows()
+        native_rl = self.lib is not None and self.read_names is None and "rl_row" in r.arrays
+        rl = {} if native_rl else self._read_list_rows()
+        pending = []; req_keys = []; req_off = [0]; req_vars = []          # rows whose read columns the native formatter fills
         bb = max(1, int(np.ceil(np.log2(max(nb, 2)))))
         fcnt = r.fb_cnt.reshape(-1, 2); fbc = r.fb_bcnt.reshape(-1, nb, 2) if r.fb_bcnt.size else r.fb_bcnt.reshape(0, nb, 2)
         for f in range(r.fb_first.shape[0]):
@@ -296,16 +321,23 @@ class Outputs:
                     cols = []; ids = []
                     for h in (0, 1):
                         key = (((f << bb) | b) << 1) | h
+                        if native_rl:
+                            req_keys.append(key); req_vars += [variants[i] for i in used]; req_off.append(len(req_vars))
+                            continue
                         per_var = rl.get(key, {})
                         lists = [per_var.get(variants[i], []) for i in used]
                         cols.append(self._relabel(lists))
                         if self.read_names is not None:       # the row's own order: ids BEFORE maf/bam (phaser.py:1120-1123)
                             ids.append(self._read_id_columns(lists))
-                    hc.append("\t".join(map(str, [ms[0].chrom, min(positions), max(positions),
-                                                  ",".join(ms[i].id for i in used), len(used), ",".join(blacklisted),
-                                                  len(blacklisted), ",".join(alleles[0][i] for i in used),
-                                                  ",".join(alleles[1][i] for i in used), a_cnt, b_cnt, a_cnt + b_cnt, gwp, stat] +
-                                             ids + [str(max_maf), self.bam_names[b], cols[0], cols[1]])) + "\n")
+                    head = "\t".join(map(str, [ms[0].chrom, min(positions), max(positions),
+                                               ",".join(ms[i].id for i in used), len(used), ",".join(blacklisted),
+                                               len(blacklisted), ",".join(alleles[0][i] for i in used),
+                                               ",".join(alleles[1][i] for i in used), a_cnt, b_cnt, a_cnt + b_cnt, gwp, stat] +
+                                          ids + [str(max_maf), self.bam_names[b]]))
+                    if native_rl:
+                        pending.append((len(hc), head, len(req_keys) - 2)); hc.append(None)
+                    else:
+                        hc.append(head + "\t" + cols[0] + "\t" + cols[1] + "\n")
             if self.output_network != "" and self.output_network in [m.id for m in ms]:
                 self.network = self._network_tables(variants, ms, alleles[0])
             for i, ma in enumerate(ms):
@@ -313,6 +345,10 @@ class Outputs:
                     if i != j:
                         cfg = "trans" if (ma.ref == alleles[0][i]) == (mb.ref == alleles[1][j]) else "cis"
                         ac.append("\t".join([ma.id, ma.rsid, mb.id, mb.rsid, cfg]) + "\n")
+        if pending:
+            texts = self._format_read_lists_native(req_keys, req_off, req_vars)
+            for at, head, k in pending:
+                hc[at] = head + "\t" + texts[k] + "\t" + texts[k + 1] + "\n"
         # ---- singletons (phaser.py:1180-1239)
         if self.unphased_vars == 1:
             ncls = r.ncls.reshape(-1, 3); sz = r.setsize.reshape(-1, 3)
@@ -401,6 +437,12 @@ class Outputs:
             sname = ctypes.string_at(p); names.append(sname.decode()); p += len(sname) + 1
         records = (arr(pc, nr.value, np.int32), names, arr(pb, nr.value, np.int64), arr(pe, nr.value, np.int64))
         return memoryview(buf)[:n.value] if n.value else memoryview(b""), int(counts[0]), int(counts[1]), records
+
+    @staticmethod
+    def vcf_save_native(nv, path_vcf_gz, csi=False):
+        """bgzip + tabix of the text the last vcf_native() produced (phz_vcf_save): path and path + .tbi / .csi"""
+        if nv.lib.phz_vcf_save(nv.h, path_vcf_gz.encode(), int(bool(csi)), nv.threads) != 0:
+            raise RuntimeError(nv.lib.phz_last_error().decode())
 
     def vcf_text(self, vcf_lines, sample_column, id_separator="_", gw_phase_vcf=0, min_conf=0.90, chrom_of_interest=""):
         """write_vcf (phaser.py:1661-1845).  Must run after block_tables().  Returns

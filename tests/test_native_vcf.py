@@ -70,3 +70,30 @@ def test_native_vcf_writer_equals_python_writer_and_reference(lib, hostsim, name
             assert [rec[1][i] for i in rec[0].tolist()] == ch and rec[2].tolist() == beg and rec[3].tolist() == end
             if mode == kw.get("gw_phase_vcf", 0) and conf == kw.get("gw_phase_vcf_min_confidence", 0.90):
                 assert bytes(got).decode() == c["ref"]["vcf"]          # the unmodified reference's own output VCF
+
+
+@pytest.mark.parametrize("name", ["rna_two_bams", "quirks", "fuzz_indels"])
+def test_native_bgzip_and_index_equal_the_python_writers(lib, hostsim, tmp_path, name):
+    """phz_vcf_save (BGZF blocks deflated in parallel, .tbi / .csi) writes byte for byte what bgzf.py + tabix.py write --
+    which tests/test_cli_and_io.py checks by region queries through the index."""
+    from phaser_b200 import tabix, samio
+    c = G.load_case(name)
+    kw, k = _kw(c)
+    col = vcfio.sample_column_map(c["vcf"])["S1"]
+    nv = vcfio.NativeVcf(c["vcf"], lib, threads=3)
+    vt, st = vcfio.parse_vcf_native(nv, col, **k)
+    fd = samio.FragmentDictionary()
+    batches = [samio.parse_sam(s, vt.contigs, fd, True, True, int(c["meta"]["mapq"].split(",")[0])) for s in c["sams"]]
+    P = pipeline.PhaseParams(as_q_cutoff=kw.get("as_q_cutoff", 0.05), haplo_count_bam_exclude=kw.get("exclude", []))
+    res = pipeline.run_path(hostsim, vt, [hostsim.upload_reads(b) for b in batches], P, n_fragments=len(fd.names))
+    o = writer.Outputs(res, vt, util.bam_display_names(c["sams"]), P)
+    o.allelic_counts(); o.block_tables()
+    text, _, _, rec = o.vcf_native(nv)
+    text = bytes(text)
+    for csi in (False, True):
+        a = str(tmp_path / ("n%d.vcf.gz" % csi)); b = str(tmp_path / ("p%d.vcf.gz" % csi))
+        o.vcf_save_native(nv, a, csi=csi)
+        tabix.write_vcf_with_index(b, text, csi=csi)
+        ext = ".csi" if csi else ".tbi"
+        assert open(a, "rb").read() == open(b, "rb").read()
+        assert open(a + ext, "rb").read() == open(b + ext, "rb").read()
