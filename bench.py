@@ -316,7 +316,9 @@ def run_ours(a):
     run = None; my_reads = reads; timers = {}
     if sharded:
         run = shard.ShardedRun(E, vt, shard.contig_weights(vt, [reads]), P, n_pairs, 1, device=dev)
-        my_reads = shard.sub_reads_tensors(reads, run.mine)
+        my_reads = shard.sub_reads_tensors(reads, run.mine, dense_frag=True)
+        # fragment ids renumbered densely inside the shard: the fragment table of the graph stage shrinks with the shard
+        run.frag_map = my_reads.pop("frag_map"); run.n_fragments = int(run.frag_map.shape[0]) if run.mine else 1
         torch.cuda.synchronize()
 
     def step(host_inputs=False, src=None):
@@ -366,7 +368,7 @@ def run_ours(a):
         if world > 1 and sharded:
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return int(t.item())
-    res_local = pipeline.run_path(E, run.svt if sharded else vt, [my_reads], P, n_fragments=n_pairs,
+    res_local = pipeline.run_path(E, run.svt if sharded else vt, [my_reads], P, n_fragments=run.n_fragments if sharded else n_pairs,
                                   comm=run.comm if sharded else None, download=False) if (not sharded or run.mine) else \
         shard._idle_rank(P, 1, run.comm)
     lc = res_local.counters if res_local.counters else {k: 0 for k in eng.COUNTER_NAMES}

@@ -31,6 +31,22 @@ PHZ_HD int coop_bcast(const Coop& c, int v) {
   return v;
 }
 
+// any / sum over the cooperating lanes (every lane gets the result; includes the memory ordering of coop_sync)
+PHZ_HD bool coop_any(const Coop& c, bool v) {
+#if defined(__CUDA_ARCH__)
+  if (c.n > 1) return __any_sync(0xffffffffu, v);
+#endif
+  (void)c;
+  return v;
+}
+PHZ_HD int coop_sum(const Coop& c, int v) {
+#if defined(__CUDA_ARCH__)
+  if (c.n > 1) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); }
+#endif
+  (void)c;
+  return v;
+}
+
 constexpr u8 CH_DASH = 2;
 constexpr int EDGE_CIS = 0, EDGE_TRANS = 1, EDGE_TIE = 2;
 constexpr int MAX_ENUM = 24;
@@ -53,35 +69,53 @@ struct BlockEdges {
 // color[i-lo] in {0,1} for reached variants, 0xFF otherwise.  Returns the number of reached
 // VARIANTS; *conflict is set when both alleles of some variant are reachable (then every reached
 // variant has both alleles reachable, so the reference's reach set has 2*m alleles).
-PHZ_HD int reach_range(const BlockEdges& be, int lo, int hi, u8* color, bool* conflict) {
-  for (int i = lo; i < hi; ++i) color[i - lo] = 0xFF;
-  color[0] = 0;
-  int m = 1;
-  bool conf = false, changed = true;
+PHZ_HD int reach_range(const BlockEdges& be, int lo, int hi, u8* color, bool* conflict, const Coop& cp) {
+  // The cooperating lanes share the edge list (edge k -> lane k mod n): label propagation until nothing changes.  The
+  // reached SET is a closure, independent of the order of propagation; a conflict (an edge between two reached variants
+  // whose colours contradict its sign) exists at the fixed point iff the component has no consistent 2-colouring, again
+  // whatever the order -- so the parallel sweep returns what the serial one does.
+  volatile u8* col = color;
+  for (int i = lo + cp.lane; i < hi; i += cp.n) col[i - lo] = 0xFF;
+  coop_sync(cp);
+  if (cp.lane == 0) col[0] = 0;
+  coop_sync(cp);
+  bool changed = true;
   while (changed) {
-    changed = false;
-    for (u32 k = 0; k < be.n_edges; ++k) {
+    bool ch = false;
+    for (u32 k = (u32)cp.lane; k < be.n_edges; k += (u32)cp.n) {
       int i, j, s; be.get(k, i, j, s);
       if (s == EDGE_TIE || i < lo || i >= hi || j < lo || j >= hi) continue;
-      u8 ci = color[i - lo], cj = color[j - lo];
-      if (ci != 0xFF && cj == 0xFF) { color[j - lo] = ci ^ (u8)s; m++; changed = true; }
-      else if (ci == 0xFF && cj != 0xFF) { color[i - lo] = cj ^ (u8)s; m++; changed = true; }
-      else if (ci != 0xFF && cj != 0xFF && ((ci ^ cj) != (u8)s)) conf = true;
+      u8 ci = col[i - lo], cj = col[j - lo];
+      if (ci != 0xFF && cj == 0xFF) { col[j - lo] = ci ^ (u8)s; ch = true; }
+      else if (ci == 0xFF && cj != 0xFF) { col[i - lo] = cj ^ (u8)s; ch = true; }
     }
+    coop_sync(cp);
+    changed = coop_any(cp, ch);
   }
-  *conflict = conf;
-  return m;
+  int m = 0; bool conf = false;
+  for (int i = lo + cp.lane; i < hi; i += cp.n) if (col[i - lo] != 0xFF) m++;
+  for (u32 k = (u32)cp.lane; k < be.n_edges; k += (u32)cp.n) {
+    int i, j, s; be.get(k, i, j, s);
+    if (s == EDGE_TIE || i < lo || i >= hi || j < lo || j >= hi) continue;
+    u8 ci = col[i - lo], cj = col[j - lo];
+    if (ci != 0xFF && cj != 0xFF && ((ci ^ cj) != (u8)s)) conf = true;
+  }
+  *conflict = coop_any(cp, conf);
+  return coop_sum(cp, m);
 }
 
 // resolve_phase on local range [lo, hi): writes the string into out (chars 0/1), returns its
 // length, or -1 when the reference returns None.
-PHZ_HD int resolve_range(const BlockEdges& be, int lo, int hi, u8* color, u8* out) {
+// (called by every cooperating lane; the return value is the same on all of them)
+PHZ_HD int resolve_range(const BlockEdges& be, int lo, int hi, u8* color, u8* out, const Coop& cp) {
   bool conf;
   int n = hi - lo;
-  int m = reach_range(be, lo, hi, color, &conf);
-  if (!conf && m == n) { for (int i = 0; i < n; ++i) out[i] = color[i]; return n; }
-  if (conf && 2 * m == n) { for (int i = 0; i < m; ++i) out[i] = 0; return m; }   // short string quirk
-  return -1;
+  int m = reach_range(be, lo, hi, color, &conf, cp);
+  int len = -1;
+  if (!conf && m == n) { for (int i = cp.lane; i < n; i += cp.n) out[i] = color[i]; len = n; }
+  else if (conf && 2 * m == n) { for (int i = cp.lane; i < m; i += cp.n) out[i] = 0; len = m; }   // short string quirk
+  coop_sync(cp);
+  return len;
 }
 
 // 2^n enumeration of sub_block_phase on local range [lo, hi), shared by the cooperating lanes.
@@ -143,17 +177,18 @@ PHZ_HD int enumerate_range(const BlockEdges& be, int lo, int hi, u8* out, int* e
 }
 
 // support of a configuration string laid over variants[start : start+len) (zip truncation at n)
-PHZ_HD int score_config(const BlockEdges& be, int n, int start, const u8* cfg, int len) {
+// (cooperative: the lanes share the edge list, every lane gets the sum)
+PHZ_HD int score_config(const BlockEdges& be, int n, int start, const u8* cfg, int len, const Coop& cp) {
   int hi = start + len; if (hi > n) hi = n;
   int s = 0;
-  for (u32 k = 0; k < be.n_edges; ++k) {
+  for (u32 k = (u32)cp.lane; k < be.n_edges; k += (u32)cp.n) {
     int i, j, sg; be.get(k, i, j, sg);
     if (sg == EDGE_TIE || i < start || i >= hi || j < start || j >= hi) continue;
     u8 ci = cfg[i - start], cj = cfg[j - start];
     if (ci == CH_DASH || cj == CH_DASH) continue;
     if ((ci ^ cj) == (u8)sg) s += 2;
   }
-  return s;
+  return coop_sum(cp, s);
 }
 
 PHZ_HD void close_final_block(const u8* str, int len, int n, int* consumed, int* n_runs,
@@ -225,10 +260,7 @@ PHZ_HD int phase_block_hard(const BlockEdges& be, int n, int max_block_size, u32
   for (int s = 0; s < n_sub; ++s) {
     int lo = (int)sub_off[s], hi = (int)sub_off[s + 1];
     int len = -1;
-    if (n_sub > 1) {
-      if (cp.lane == 0) len = resolve_range(be, lo, hi, color, sub + used_chars);
-      len = coop_bcast(cp, len);
-    }
+    if (n_sub > 1) len = resolve_range(be, lo, hi, color, sub + used_chars, cp);
     if (len < 0) len = enumerate_range(be, lo, hi, sub + used_chars, err, cp);
     if (cp.lane == 0) { sub_pos[s] = used_chars; sub_len[s] = (u32)len; }
     used_chars += (u32)len;
@@ -238,10 +270,13 @@ PHZ_HD int phase_block_hard(const BlockEdges& be, int n, int max_block_size, u32
   // of the four concatenations only A+B and A+B' are scored (the other two are their complements,
   // phaser.py:2234) and the merge succeeds iff both are digits and the two supports differ.
   int n_runs = 0;
-  if (cp.lane == 0) {
+  {
+    // every lane runs the control flow (its scalars depend only on data all lanes read after a sync); lane 0 alone
+    // writes the strings and the runs; the two supports of a merge are summed by all lanes over the shared edge list
     int consumed = 0;
     int fin_len = (int)sub_len[0];
-    for (int i = 0; i < fin_len; ++i) fin[i] = sub[sub_pos[0] + i];
+    if (cp.lane == 0) for (int i = 0; i < fin_len; ++i) fin[i] = sub[sub_pos[0] + i];
+    coop_sync(cp);
     int split_start = 0;
     for (int s = 1; s < n_sub; ++s) {
       const u8* nb = sub + sub_pos[s];
@@ -250,24 +285,31 @@ PHZ_HD int phase_block_hard(const BlockEdges& be, int n, int max_block_size, u32
       bool a_dash = (fin_len > 0 && fin[0] == CH_DASH), b_dash = (nb_len > 0 && nb[0] == CH_DASH);
       bool ok = false, flip_b = false;
       if (!a_dash && !b_dash) {
-        for (int i = 0; i < fin_len; ++i) cand[i] = fin[i];
-        for (int i = 0; i < nb_len; ++i) cand[fin_len + i] = nb[i];
-        int s0 = score_config(be, n, split_start, cand, used);
-        for (int i = 0; i < nb_len; ++i) cand[fin_len + i] = nb[i] ^ 1;
-        int s1 = score_config(be, n, split_start, cand, used);
+        if (cp.lane == 0) {
+          for (int i = 0; i < fin_len; ++i) cand[i] = fin[i];
+          for (int i = 0; i < nb_len; ++i) cand[fin_len + i] = nb[i];
+        }
+        coop_sync(cp);
+        int s0 = score_config(be, n, split_start, cand, used, cp);
+        coop_sync(cp);
+        if (cp.lane == 0) for (int i = 0; i < nb_len; ++i) cand[fin_len + i] = nb[i] ^ 1;
+        coop_sync(cp);
+        int s1 = score_config(be, n, split_start, cand, used, cp);
         if (s0 > s1) { ok = true; flip_b = false; } else if (s1 > s0) { ok = true; flip_b = true; }
       }
+      coop_sync(cp);
       if (ok) {
-        for (int i = 0; i < nb_len; ++i) fin[fin_len + i] = flip_b ? (u8)(nb[i] ^ 1) : nb[i];
+        if (cp.lane == 0) for (int i = 0; i < nb_len; ++i) fin[fin_len + i] = flip_b ? (u8)(nb[i] ^ 1) : nb[i];
         fin_len = used;
       } else {
-        close_final_block(fin, fin_len, n, &consumed, &n_runs, run_start, run_len, hap, fin_local);
+        if (cp.lane == 0) close_final_block(fin, fin_len, n, &consumed, &n_runs, run_start, run_len, hap, fin_local);
         split_start = used;                 // Q14: not an offset sum
         fin_len = nb_len;
-        for (int i = 0; i < nb_len; ++i) fin[i] = nb[i];
+        if (cp.lane == 0) for (int i = 0; i < nb_len; ++i) fin[i] = nb[i];
       }
+      coop_sync(cp);
     }
-    close_final_block(fin, fin_len, n, &consumed, &n_runs, run_start, run_len, hap, fin_local);
+    if (cp.lane == 0) close_final_block(fin, fin_len, n, &consumed, &n_runs, run_start, run_len, hap, fin_local);
   }
   n_runs = coop_bcast(cp, n_runs);
   coop_sync(cp);

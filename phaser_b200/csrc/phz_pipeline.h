@@ -11,6 +11,7 @@
 //   read_lists     phaser.py:1105-1115                  per (block, BAM, haplotype, variant) read lists
 #pragma once
 #include <type_traits>
+#include <cmath>
 #include "phz_map_core.h"
 #include "phz_phase_core.h"
 #include "phz_graph.h"
@@ -413,9 +414,53 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, in
                ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
 }
 
+// Count pass of ONE record served entirely from the tile's shared-memory slabs, in 32-bit arithmetic: the CIGAR words,
+// POS and the het-site slab are all staged, the record lies on the tile's first contig, so the general walk's 64-bit
+// offsets, contig look-ups and global fall-backs are not needed.  Same predicate as map_record<0> (read_variant_map.py:
+// 191-232, 239-242).  Returns false when the slab does not pin a search down (the caller takes the general walk).
+__device__ __forceinline__ bool tile_count_fast(const int32_t* __restrict__ s_pos, const u32* __restrict__ s_coff,
+                                                const u32* __restrict__ s_cig, u32 cig_al, int i, const int32_t* __restrict__ win,
+                                                int a, int b, bool at_start, bool at_end, int hint_lo, int hint_hi, u32& cnt_out) {
+  const int32_t rpos = s_pos[i];
+  u32 k = s_coff[i] - cig_al; const u32 kend = s_coff[i + 1] - cig_al;
+  u32 cnt = 0; int32_t gp = 0; bool first = true;
+  while (true) {
+    int32_t g_end = gp;
+    for (; k < kend; ++k) {
+      const u32 c = s_cig[k]; const u32 op = c & 15u;
+      if (op == OP_N) break;
+      if (op == OP_M || op == OP_D || op == OP_EQ || op == OP_X) g_end += (int32_t)(c >> 4);
+    }
+    const int32_t seg_len = g_end - gp;
+    if (seg_len > 0) {
+      const int64_t lo64 = (int64_t)rpos + gp;
+      if (lo64 + seg_len > 2147483647LL) return false;
+      const int32_t lo_key = (int32_t)lo64, hi_key = lo_key + seg_len;
+      int l, len;
+      if (first && hint_hi >= 0) { l = hint_lo; len = hint_hi - hint_lo; } else { l = a; len = b - a; }
+      while (len > 0) {                          // branch-free halving inside the bracket
+        const int half = len >> 1, mid = l + half;
+        const bool p = win[mid] < lo_key;
+        l = p ? mid + 1 : l;
+        len = p ? len - half - 1 : half;
+      }
+      if (!(first && hint_hi >= 0) && !((l > a || at_start) && (l < b || at_end))) return false;
+      int h = l;
+      while (h < b && win[h] < hi_key) ++h;
+      if (h == b && !at_end) return false;
+      cnt += (u32)(h - l);
+    }
+    if (k >= kend) break;
+    gp = g_end + (int32_t)(s_cig[k] >> 4); ++k; first = false;
+  }
+  cnt_out = cnt;
+  return true;
+}
+
 template <int MIN_CTAS, class VV>
 __global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView rv, VV vv, const TileInfo* __restrict__ tiles,
-                                                            int baseq, double isize_cutoff, u32* __restrict__ s_rec,
+                                                            int baseq, double isize_cutoff, long long isize_floor, int isize_on,
+                                                            u32* __restrict__ s_rec,
                                                             u32* __restrict__ s_var, u32* __restrict__ s_misc, u64 capacity,
                                                             unsigned long long* cursor, u32* __restrict__ tile_base,
                                                             u32* __restrict__ tile_cnt) {
@@ -431,6 +476,7 @@ __global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView
   __shared__ u32 excl_of[KF_THREADS + 1];
   __shared__ u8 sh_owner[KT_OWN];                     // candidate slot -> record of the tile that owns it
   __shared__ unsigned long long s_base;
+  __shared__ int64_t s_v01[2];                        // het-site range of the tile's first contig
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t tile = blockIdx.x;
   const TileInfo ti = tiles[tile];
@@ -466,6 +512,8 @@ __global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView
     for (int i = n2; i < nrec; ++i) sh_soff[i] = rv.seq_off[r0 + i];
     for (int i = n8; i < nrec; ++i) sh_as[i] = rv.aln_score[r0 + i];
     s_base = (unsigned long long)bytes;
+    const int c0 = (int)(ti.contig_wn >> 16);
+    s_v01[0] = vv.contig_var_off[c0]; s_v01[1] = vv.contig_var_off[c0 + 1];
   }
   const int64_t r = r0 + tid;
   const bool live = tid < nrec;
@@ -485,8 +533,28 @@ __global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView
   // CIGAR range of the tile is in shared memory and is read unconditionally.
   auto body = [&](auto staged) {
     const TileRV<decltype(staged)::value> trv{r0, sh_pos, sh_tlen, sh_coff, sh_cig, sh_soff, sh_as, cig_al, cig_n, rv.cigar, rv.seq, rv.qual};
-    const WindowVP vp = window_of(ti, vv.pos, win, contig == contig0);
-    const u32 cnt = live ? map_record<0>(trv, vv, vp, r, contig, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr) : 0u;
+    u32 cnt = 0;
+    if (live) {
+      bool done = false;
+      if constexpr (!VV::kIndels && decltype(staged)::value) {
+        if (contig == contig0) {
+          // tile-uniform slab geometry: the contig's sites inside the slab are win[a, b)
+          const int64_t a64 = s_v01[0] - (int64_t)ti.wbase, b64 = s_v01[1] - (int64_t)ti.wbase;
+          const int a = a64 > 0 ? (int)a64 : 0, b = b64 < wn ? (int)b64 : wn;
+          int32_t tl = sh_tlen[tid]; const int64_t atl = tl < 0 ? -(int64_t)tl : (int64_t)tl;
+          if (isize_on && atl > isize_floor) done = true;                        // read_variant_map.py:35,51
+          else if (a < b) {
+            const u32 hn = ti.hint & 0xFFFFu; const int hlo = (int)(ti.hint >> 16);
+            done = tile_count_fast(sh_pos, sh_coff, sh_cig, cig_al, tid, win, a, b, (int64_t)ti.wbase + a == s_v01[0],
+                                   (int64_t)ti.wbase + b == s_v01[1], hlo, hn != 0xFFFFu ? hlo + (int)hn : -1, cnt);
+          } else if (s_v01[0] == s_v01[1]) done = true;                           // a contig without het sites
+        }
+      }
+      if (!done) {
+        const WindowVP vp = window_of(ti, vv.pos, win, contig == contig0);
+        cnt = map_record<0>(trv, vv, vp, r, contig, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr);
+      }
+    }
     // ---- CTA exclusive scan of the counts
     u32 incl = cnt;
     #pragma unroll
@@ -693,14 +761,17 @@ struct Pipeline {
       total = 0;
 #ifdef __CUDACC__
       u64* cur = tile_status.ensure(2); be.memset0(cur, 2 * sizeof(u64));
+      // abs(TLEN) <= cutoff with an integer TLEN  <=>  abs(TLEN) <= floor(cutoff)  (read_variant_map.py:35,51; 0 = no gate)
+      const int isz_on = isize_cutoff != 0.0 ? 1 : 0;
+      const long long isz_floor = !isz_on ? 0 : (isize_cutoff >= 9.0e18 ? (long long)9e18 : (isize_cutoff <= -9.0e18 ? -(long long)9e18 : (long long)std::floor(isize_cutoff)));
       if constexpr (VV::kIndels)      // the indel instantiation is not register-capped: its string walk would spill at 32 registers
-        k1_tile_kernel<1, VV><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, sr, sv, sm, (u64)cap, cur, tb, tc);
+        k1_tile_kernel<1, VV><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, isz_floor, isz_on, sr, sv, sm, (u64)cap, cur, tb, tc);
       else if (k1_min_ctas >= 8)
-        k1_tile_kernel<8, VV><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, sr, sv, sm, (u64)cap, cur, tb, tc);
+        k1_tile_kernel<8, VV><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, isz_floor, isz_on, sr, sv, sm, (u64)cap, cur, tb, tc);
       else if (k1_min_ctas >= 6)
-        k1_tile_kernel<6, VV><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, sr, sv, sm, (u64)cap, cur, tb, tc);
+        k1_tile_kernel<6, VV><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, isz_floor, isz_on, sr, sv, sm, (u64)cap, cur, tb, tc);
       else
-        k1_tile_kernel<1, VV><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, sr, sv, sm, (u64)cap, cur, tb, tc);
+        k1_tile_kernel<1, VV><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, isz_floor, isz_on, sr, sv, sm, (u64)cap, cur, tb, tc);
       PHZ_CUDA(cudaGetLastError());
       be.launches++;
       be.d2h(&total, cur, sizeof(u64));

@@ -238,16 +238,24 @@ def run_path(engine: Engine, vt: VariantTable, batches, params: PhaseParams, n_f
         cutoffs.append(cutoff)
         kept.append(engine.commit_bam(b, None if cutoff is None else int(math.ceil(cutoff))))
     match, mism = engine.variant_stats()
-    match, mism = comm.allreduce_sum_ints([match, mism])
-    if match == 0:
-        raise PhaserFatal("No reads could be matched to variants. Please double check your settings and input files. "
-                          "Common reasons for this occurring include: 1) MAPQ or BASEQ set too conservatively 2) BAM "
-                          "and VCF have different chromosome names (IE 'chr1' vs '1').")
-    noise_e = noise_level(match, mism)
-    # the critical values of the small totals (the bulk of the edges) are computed on a host thread while the
-    # GPU builds the graph; both scipy's ufuncs and the C call release the GIL
+    # The critical values of the small totals (the bulk of the edges) need only the noise level: a host thread computes
+    # them while the GPU builds the graph (scipy's ufuncs and the C calls release the GIL).  With several ranks the same
+    # thread first sums the two noise counters over the ranks, so that exchange is hidden under the graph stage as well
+    # (no other collective is issued meanwhile: the order of collectives stays the same on every rank).
     pre = {}
-    worker = threading.Thread(target=lambda: pre.setdefault("k", critical_values(PRECOMPUTED_TOTALS, noise_e, params.cc_threshold)))
+    overlap_reduce = comm.world_size > 1 and getattr(comm, "timers", None) is None
+    if not overlap_reduce:
+        match, mism = comm.allreduce_sum_ints([match, mism])
+
+    def noise_and_critical_values(local=(match, mism)):
+        try:
+            m_, x_ = comm.allreduce_sum_ints(list(local)) if overlap_reduce else local
+            pre["counts"] = (m_, x_)
+            if m_ > 0:
+                pre["k"] = critical_values(PRECOMPUTED_TOTALS, noise_level(m_, x_), params.cc_threshold)
+        except BaseException as e:          # noqa: BLE001 -- re-raised on the main thread
+            pre["error"] = e
+    worker = threading.Thread(target=noise_and_critical_values)
     worker.start()
     _t = time.perf_counter() if _TRACE else 0.0
     engine.set_option("big_total_threshold", PRECOMPUTED_TOTALS)
@@ -256,6 +264,14 @@ def run_path(engine: Engine, vt: VariantTable, batches, params: PhaseParams, n_f
     finally:
         _t1 = time.perf_counter() if _TRACE else 0.0
         worker.join()
+    if "error" in pre:
+        raise pre["error"]
+    match, mism = pre["counts"]
+    if match == 0:
+        raise PhaserFatal("No reads could be matched to variants. Please double check your settings and input files. "
+                          "Common reasons for this occurring include: 1) MAPQ or BASEQ set too conservatively 2) BAM "
+                          "and VCF have different chromosome names (IE 'chr1' vs '1').")
+    noise_e = noise_level(match, mism)
     _t2 = time.perf_counter() if _TRACE else 0.0
     m = min(int(max_tot), PRECOMPUTED_TOTALS)
     kstar = pre["k"][:m + 1]

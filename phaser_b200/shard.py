@@ -115,10 +115,13 @@ def sub_read_batch(rb: ReadBatch, contigs: List[int]) -> ReadBatch:
                      cig_off.astype(np.uint32), rb.cigar[ci], seq_off.astype(np.uint64), seq, rb.qual[bi], rb.qnames)
 
 
-def sub_reads_tensors(reads: dict, contigs: List[int]) -> dict:
+def sub_reads_tensors(reads: dict, contigs: List[int], dense_frag=False) -> dict:
     """sub_read_batch for the tensor form of a BAM (Engine.upload_reads: dict of torch tensors on any device +
     host `contig_rec_off`): the records of `contigs`, contig order kept, offsets rebased.  The records of a contig
-    are one contiguous range of every array, so this is slicing and concatenation on the device the data is on."""
+    are one contiguous range of every array, so this is slicing and concatenation on the device the data is on.
+    `dense_frag`: renumber the fragment ids of the shard densely (ascending global id = order of first appearance, so
+    neighbours stay neighbours) and return the local -> global table as "frag_map": the graph stage's fragment table
+    then has one slot per fragment of the SHARD instead of one per fragment of the sample."""
     cro = np.asarray(reads["contig_rec_off"], np.int64)
     pos = reads["pos"]; dev = pos.device
     coff = reads["cigar_off"]; soff = reads["seq_off"]
@@ -130,6 +133,9 @@ def sub_reads_tensors(reads: dict, contigs: List[int]) -> dict:
         return torch.cat([t[a:b] for a, b in rng]) if rng else t[:0]
 
     out = dict(contig_rec_off=off, pos=cut(pos), tlen=cut(reads["tlen"]), aln_score=cut(reads["aln_score"]), frag=cut(reads["frag"]))
+    if dense_frag:
+        uniq, inv = torch.unique(out["frag"], return_inverse=True)
+        out["frag"] = inv.to(out["frag"].dtype); out["frag_map"] = uniq
     cig_parts, qual_parts, seq_parts, co_parts, so_parts = [], [], [], [], []
     cbase = 0; sbase = 0
     aligned = True
@@ -488,7 +494,7 @@ def gather_names(params: PhaseParams):
     return names
 
 
-def gather_results(engine, res, names, n_bams, device, timers=None, to_host=True, failed=False):
+def gather_results(engine, res, names, n_bams, device, timers=None, to_host=True, failed=False, frag_map=None):
     """Every rank packs its result arrays into ONE buffer where they live (device memory: phz_copy_array), the byte
     counts travel in a small all-gather, and a grouped send/recv moves the buffers into rank 0's memory.  Rank 0
     returns, per rank, {name: numpy array} + (counters, tuples per BAM, candidates per BAM) read from one page-locked
@@ -508,6 +514,11 @@ def gather_results(engine, res, names, n_bams, device, timers=None, to_host=True
     buf = None
     if res is not None:
         buf, info = engine.pack_arrays(names)
+        if frag_map is not None:          # shard-local fragment ids -> the sample's ids, before the arrays leave the rank
+            for nm, off, n, eb in info:
+                if nm in ("rl_frag", "g_frag") and n:
+                    view = buf[off:off + n * eb].view(torch.int32)
+                    view.copy_(frag_map.to(view.device)[view.to(torch.int64) & 0xFFFFFFFF].to(torch.int32))
         if buf.device != device:          # collectives on another device than the engine's (gloo between CUDA engines)
             buf = buf.to(device)
         for i, (_nm, _off, n, eb) in enumerate(info):
@@ -630,6 +641,7 @@ class ShardedRun:
         self.svt, self.gid = sub_variant_table(vt, self.mine)
         self.gids = [sub_variant_table_ids(vt, p) for p in self.plan] if self.rank == 0 else None
         self.names = gather_names(params)
+        self.frag_map = None          # local -> global fragment ids when the shard's reads were renumbered (sub_reads_tensors)
         self.host_cache = {}
         if self.rank == 0:          # the merge runs where the gathered arrays are
             self.gids_dev = [torch.from_numpy(g).to(self.device) for g in self.gids]
@@ -652,7 +664,7 @@ class ShardedRun:
         except PhaserFatal as e:          # rank-local verdicts (phasing flags) must not leave the others in the gather
             err = e
         got = gather_results(self.engine, res if (self.mine and err is None) else None, self.names, self.n_bams, self.device,
-                             self.timers, to_host=False, failed=err is not None)
+                             self.timers, to_host=False, failed=err is not None, frag_map=self.frag_map)
         if err is not None:
             raise err
         if self.rank != 0 or not merge:

@@ -119,5 +119,9 @@ def test_tensor_form_of_a_shard_equals_the_array_form(tmp_path):
             nb = int(a.qual.shape[0])
             for k in ("pos", "tlen", "aln_score", "frag", "cigar_off", "cigar", "seq_off", "qual"):
                 assert np.array_equal(b[k].numpy().view(getattr(a, k).dtype), getattr(a, k)), (read_len, pick, k)
+            d = shard.sub_reads_tensors(t, pick, dense_frag=True)          # shard-local fragment ids + the table back
+            fm = d["frag_map"].numpy().astype(np.int64) & 0xFFFFFFFF
+            assert np.array_equal(fm[d["frag"].numpy().astype(np.int64)], a.frag.astype(np.int64))
+            assert fm.shape[0] == np.unique(a.frag).shape[0] and (np.diff(fm) > 0).all()
             sa, sb = a.seq, b["seq"].numpy()
             assert np.array_equal(sa[:nb // 2], sb[:nb // 2]) and (nb % 2 == 0 or (sa[nb // 2] >> 4) == (sb[nb // 2] >> 4))
