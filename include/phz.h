@@ -144,6 +144,10 @@ int phz_map_reads_packed(phz_ctx* ctx, const phz_packed_reads* packed, int baseq
  * untouched until the matching phz_map_reads_packed has returned. */
 int phz_prefetch_packed(phz_ctx* ctx, const phz_packed_reads* packed);
 
+/* Host -> device copy of a PAGEABLE host array through two page-locked staging buffers filled by n_threads host threads:
+ * what the command line uses to put the ingest's arrays (150 bytes per record) on the device at PCIe speed. */
+int phz_upload(phz_ctx* ctx, void* d_dst, const void* h_src, int64_t bytes, int n_threads);
+
 /* Exact histogram of the alignment scores of the tuples the reference mapper would print; the host
  * derives numpy.percentile from it (phaser.py:545-553).  d_hist: PHZ_AS_BINS uint64 on the device. */
 int phz_as_histogram(phz_ctx* ctx, uint64_t* d_hist);

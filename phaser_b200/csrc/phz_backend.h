@@ -236,6 +236,8 @@ struct DeviceBackend {
   // the copies enqueued so far.
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[2] = {nullptr, nullptr};
+  void* up_stage[2] = {nullptr, nullptr};          // page-locked staging of phz_upload
+  cudaEvent_t up_ev[2] = {nullptr, nullptr};
   void copy_begin() {
     if (!copy_stream) {
       PHZ_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
@@ -367,6 +369,8 @@ struct DeviceBackend {
   ~DeviceBackend() {
     if (cub_tmp) cudaFree(cub_tmp);
     for (auto& e : copy_ev) if (e) cudaEventDestroy(e);
+    for (auto& e : up_ev) if (e) cudaEventDestroy(e);
+    for (auto& p : up_stage) if (p) cudaFreeHost(p);
     if (copy_stream) cudaStreamDestroy(copy_stream);
   }
 };

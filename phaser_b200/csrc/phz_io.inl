@@ -11,6 +11,7 @@
 #include <array>
 #include <thread>
 #include <mutex>
+#include <memory>
 #include <exception>
 #include <atomic>
 #include <fstream>
@@ -258,6 +259,71 @@ static void inflate_bgzf(const In& in, Out& out, int n_threads) {
   if (bad) throw PhzError("BGZF inflate failed");
 }
 
+// The same inflate as a background job: worker threads take the blocks in file order and publish how far the output is
+// complete, so that the caller can start walking the BAM records behind the inflate front instead of after it.
+struct InflateJob {
+  struct Blk { size_t in_off, in_len, out_off, out_len; };
+  std::vector<Blk> blks; std::vector<std::thread> th;
+  std::unique_ptr<std::atomic<u8>[]> done;
+  std::atomic<size_t> next{0}; std::atomic<int> bad{0};
+  size_t frontier = 0, total = 0;          // frontier: only the consumer thread touches it
+  template <class In, class Out>
+  void start(const In& in, Out& out, int n_threads) {
+    size_t p = 0;
+    while (p + 18 <= in.size()) {
+      if (in[p] != 0x1f || in[p + 1] != 0x8b) throw PhzError("corrupt BGZF block header");
+      u32 xlen = in[p + 10] | (in[p + 11] << 8);
+      size_t q = p + 12, xe = q + xlen; u32 bsize = 0; bool found = false;
+      while (q + 4 <= xe) {
+        u32 slen = in[q + 2] | (in[q + 3] << 8);
+        if (in[q] == 'B' && in[q + 1] == 'C' && slen == 2) { bsize = (in[q + 4] | (in[q + 5] << 8)) + 1; found = true; }
+        q += 4 + slen;
+      }
+      if (!found || p + bsize > in.size()) throw PhzError("BGZF block without BC field or truncated file");
+      u32 isize = in[p + bsize - 4] | (in[p + bsize - 3] << 8) | (in[p + bsize - 2] << 16) | ((u32)in[p + bsize - 1] << 24);
+      blks.push_back(Blk{xe, p + bsize - 8 - xe, total, isize});
+      total += isize; p += bsize;
+    }
+    out.resize(total);
+    done.reset(new std::atomic<u8>[blks.size() + 1]);
+    for (size_t i = 0; i <= blks.size(); ++i) done[i] = 0;
+    const u8* src = in.data(); u8* dst = out.data();
+    auto work = [this, src, dst]() {
+      z_stream zs;
+      while (!bad) {
+        size_t i = next.fetch_add(1);
+        if (i >= blks.size()) break;
+        const Blk& b = blks[i];
+        if (b.out_len) {
+          std::memset(&zs, 0, sizeof(zs));
+          if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; break; }
+          zs.next_in = (Bytef*)(src + b.in_off); zs.avail_in = (uInt)b.in_len;
+          zs.next_out = dst + b.out_off; zs.avail_out = (uInt)b.out_len;
+          int rc = inflate(&zs, Z_FINISH);
+          inflateEnd(&zs);
+          if (rc != Z_STREAM_END) { bad = 1; break; }
+        }
+        done[i].store(1, std::memory_order_release);
+      }
+    };
+    int nw = n_threads > 1 ? n_threads - 1 : 1;        // the caller's thread walks the records meanwhile
+    for (int t = 0; t < nw; ++t) th.emplace_back(work);
+  }
+  // blocks until output bytes [0, off) are complete
+  void need(size_t off) {
+    if (off > total) off = total;
+    while (true) {
+      while (frontier < blks.size() && done[frontier].load(std::memory_order_acquire)) ++frontier;
+      size_t ready = frontier < blks.size() ? blks[frontier].out_off : total;
+      if (ready >= off) return;
+      if (bad) { join(); throw PhzError("BGZF inflate failed"); }
+      std::this_thread::yield();
+    }
+  }
+  void join() { for (auto& t : th) if (t.joinable()) t.join(); th.clear(); if (bad) throw PhzError("BGZF inflate failed"); }
+  ~InflateJob() { for (auto& t : th) if (t.joinable()) t.join(); }
+};
+
 template <class In, class Out>
 static void inflate_gzip_stream(const In& in, Out& out) {
   z_stream zs; std::memset(&zs, 0, sizeof(zs));
@@ -406,24 +472,32 @@ static HostReads* build(RV& recs, int nc, int n_threads) {
 
 template <class D>
 static HostReads* parse_bam(const D& d, const char* const* contigs, int nc, FragDict* fd, int remove_dups,
-                            int proper_pair, int min_mapq, int n_threads) {
+                            int proper_pair, int min_mapq, int n_threads, InflateJob* job = nullptr) {
   auto rd32 = [&](size_t o) { return (int32_t)(d[o] | (d[o + 1] << 8) | (d[o + 2] << 16) | ((u32)d[o + 3] << 24)); };
+  auto need = [&](size_t off) { if (job) job->need(off); };         // the inflate front (BGZF input inflated in the background)
+  need(12);
   if (d.size() < 12 || std::memcmp(d.data(), "BAM\1", 4) != 0) throw PhzError("not a BAM file");
+  need(8 + (size_t)rd32(4) + 4);
   size_t p = 8 + (size_t)rd32(4);
   int n_ref = rd32(p); p += 4;
   std::vector<int> ref_to_contig(n_ref, -1);
   for (int i = 0; i < n_ref; ++i) {
+    need(p + 4); need(p + 4 + (size_t)rd32(p) + 4);
     int ln = rd32(p); p += 4;
     std::string name((const char*)d.data() + p, ln > 0 ? ln - 1 : 0); p += ln + 4;
     for (int c = 0; c < nc; ++c) if (name == contigs[c]) ref_to_contig[i] = c;
   }
   // record boundaries (serial pointer chase), then filter + decode headers in parallel chunks
   std::vector<size_t> starts;
+  starts.reserve(d.size() / 96 + 16);
+  size_t have = 0;                       // bytes known to be inflated
   while (p + 4 <= d.size()) {
+    if (job && p + 4 > have) { need(p + (1 << 20)); have = p + (1 << 20); }        // wait in 1 MB strides, not per record
     int32_t bs = rd32(p);
     if (bs < 32 || p + 4 + (size_t)bs > d.size()) throw PhzError("truncated or corrupt BAM record");
     starts.push_back(p + 4); p += 4 + (size_t)bs;
   }
+  if (job) job->join();                  // the decode below reads every byte
   const size_t CH = 16384, n_chunks = (starts.size() + CH - 1) / CH;
   std::vector<std::vector<Rec>> parts(n_chunks);
   double tp0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -590,19 +664,21 @@ phz_host_reads* phz_read_alignments(const char* path, const char* const* contigs
     phzio::Bytes data;
     bool gz = raw.size() >= 18 && raw[0] == 0x1f && raw[1] == 0x8b;
     bool bgzf = gz && (raw[3] & 4) && raw[12] == 'B' && raw[13] == 'C';
-    if (bgzf) phzio::inflate_bgzf(raw, data, n_threads);
+    phzio::InflateJob job;
+    if (bgzf) { job.start(raw, data, n_threads); job.need(4); }       // the blocks inflate in the background from here on
     else if (gz) phzio::inflate_gzip_stream(raw, data);
     double t2 = now();
-    phz_host_reads* out = new phz_host_reads();
-    auto parse = [&](const auto& d) {
+    std::unique_ptr<phz_host_reads> out(new phz_host_reads());
+    auto parse = [&](const auto& d, phzio::InflateJob* j) {
       if (d.size() >= 4 && std::memcmp(d.data(), "BAM\1", 4) == 0)
-        return phzio::parse_bam(d, contigs, n_contigs, &fd->d, remove_dups, proper_pair, min_mapq, n_threads);
+        return phzio::parse_bam(d, contigs, n_contigs, &fd->d, remove_dups, proper_pair, min_mapq, n_threads, j);
+      if (j) j->join();
       return phzio::parse_sam(d, contigs, n_contigs, &fd->d, remove_dups, proper_pair, min_mapq, n_threads);
     };
-    out->h = gz ? parse(data) : parse(raw);
+    out->h = gz ? parse(data, bgzf ? &job : nullptr) : parse(raw, nullptr);
     if (timing) std::fprintf(stderr, "[phz_io] read %.3fs inflate %.3fs parse+build %.3fs (%lld records)\n", t1 - t0, t2 - t1,
                              now() - t2, (long long)out->h->pos.size());
-    return out;
+    return out.release();
   } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
 }
 
@@ -653,6 +729,45 @@ int phz_write_sam(const char* path, const char* const* contig_names, const int64
 // =============================================================================== packed transport (include/phz.h)
 // Host side of phz_packed_reads: offsets -> per-record counts, 4-bit bases -> 2 bits + exception list, phred bytes ->
 // indices into the table of distinct values.  Lossless; expanded again on the device by phz_map_reads_packed.
+// Host -> device copy of a pageable host array at PCIe speed: the bytes go through two page-locked staging buffers that
+// host threads fill (parallel memcpy) while the previous chunk is on the bus.  A plain cudaMemcpy from pageable memory
+// stages through one driver thread at ~5 GB/s; the command line uploads 150 bytes per record this way.
+int phz_upload(phz_ctx* ctx, void* d_dst, const void* h_src, int64_t bytes, int n_threads) {
+  PHZ_TRY
+  auto& be = ctx->p.be;
+  if (bytes <= 0) return 0;
+#ifdef __CUDACC__
+  static const size_t CHUNK = 32u << 20;
+  if (!be.up_stage[0]) {
+    for (int b = 0; b < 2; ++b) {
+      PHZ_CUDA(cudaHostAlloc(&be.up_stage[b], CHUNK, cudaHostAllocDefault));
+      PHZ_CUDA(cudaEventCreateWithFlags(&be.up_ev[b], cudaEventDisableTiming));
+    }
+  }
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > 8) n_threads = 8;
+  size_t off = 0; int b = 0; bool used[2] = {false, false};
+  while (off < (size_t)bytes) {
+    const size_t n = std::min(CHUNK, (size_t)bytes - off);
+    if (used[b]) PHZ_CUDA(cudaEventSynchronize(be.up_ev[b]));          // the copy that last read this buffer is done
+    const u8* src = (const u8*)h_src + off; u8* st = (u8*)be.up_stage[b];
+    const size_t piece = (n + n_threads - 1) / n_threads;
+    phzio::parallel_for((size_t)n_threads, n_threads, [&](size_t t) {
+      const size_t a = t * piece; if (a >= n) return;
+      std::memcpy(st + a, src + a, std::min(piece, n - a));
+    });
+    PHZ_CUDA(cudaMemcpyAsync((u8*)d_dst + off, st, n, cudaMemcpyHostToDevice, be.stream));
+    PHZ_CUDA(cudaEventRecord(be.up_ev[b], be.stream));
+    used[b] = true; off += n; b ^= 1;
+  }
+  for (int k = 0; k < 2; ++k) if (used[k]) PHZ_CUDA(cudaEventSynchronize(be.up_ev[k]));      // the staging buffers are free again
+#else
+  (void)n_threads;
+  std::memcpy(d_dst, h_src, (size_t)bytes);
+#endif
+  PHZ_CATCH
+}
+
 // BAM (BGZF) twin of generated records: what the product's command line reads in the files-to-files benchmark while the
 // reference baseline gets the SAM text twin of the same records (test / bench infrastructure).  Records are encoded on
 // n_threads threads, the byte stream is cut into 0xff00-byte BGZF blocks that are deflated in parallel.

@@ -72,7 +72,7 @@ EXPORTS = ["phz_last_error", "phz_backend_name", "phz_create", "phz_destroy", "p
            "phz_set_indel_alleles", "phz_pack_reads", "phz_packed_view", "phz_packed_bytes", "phz_packed_free",
            "phz_map_reads_packed", "phz_prefetch_packed", "phz_gene_ae_pairs", "phz_set_big_critical_values",
            "phz_copy_array", "phz_vcf_open", "phz_vcf_close", "phz_vcf_text", "phz_vcf_chrom_line", "phz_vcf_parse",
-           "phz_vcf_write", "phz_vcf_records", "phz_write_bam", "phz_vcf_save", "phz_format_read_lists"]
+           "phz_vcf_write", "phz_vcf_records", "phz_write_bam", "phz_vcf_save", "phz_format_read_lists", "phz_upload"]
 
 
 def _declare(lib):
@@ -105,6 +105,7 @@ def _declare(lib):
     lib.phz_vcf_records.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                     POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int32)]
     lib.phz_vcf_save.argtypes = [c_void_p, c_char_p, c_int, c_int]
+    lib.phz_upload.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int]
     lib.phz_format_read_lists.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int,
                                           POINTER(c_void_p), POINTER(c_void_p)]
     lib.phz_counters.argtypes = [c_void_p, POINTER(c_int64)]
@@ -364,9 +365,31 @@ class Engine:
             self._keep["vblack"] = _as_torch(np.ascontiguousarray(bl, np.uint8), d)
             self._check(self.lib.phz_set_haplo_blacklist(self.ctx, self._keep["vblack"].data_ptr()))
 
-    def upload_reads(self, batch: ReadBatch):
-        """ReadBatch (numpy) -> dict of device tensors (the 'inputs resident in HBM' form)."""
+    def _upload(self, a: np.ndarray, threads=8):
+        """numpy array (pageable host memory) -> device tensor through the library's page-locked staging ring"""
+        if a.dtype == np.uint32:
+            a = a.view(np.int32)
+        elif a.dtype == np.uint64:
+            a = a.view(np.int64)
+        a = np.ascontiguousarray(a)
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, device=self.device)
+        if a.nbytes:
+            self._check(self.lib.phz_upload(self.ctx, t.data_ptr(), a.ctypes.data, a.nbytes, int(threads)))
+        return t
+
+    def upload_reads(self, batch: ReadBatch, staged=None):
+        """ReadBatch (numpy) -> dict of device tensors (the 'inputs resident in HBM' form).  `staged` (default: on a
+        CUDA engine for batches above 64 MB): the big arrays go through phz_upload instead of pageable copies."""
         d = self.device
+        nbytes = batch.qual.nbytes + batch.seq.nbytes
+        if staged is None:
+            staged = self.backend != "hostsim" and nbytes > (64 << 20)
+        if staged:
+            up = self._upload
+            return dict(contig_rec_off=np.array(batch.contig_rec_off, dtype=np.int64, copy=True),
+                        pos=up(batch.pos), tlen=up(batch.tlen), aln_score=up(batch.aln_score), frag=up(batch.frag),
+                        cigar_off=up(batch.cigar_off), cigar=up(batch.cigar), seq_off=up(batch.seq_off), seq=up(batch.seq),
+                        qual=up(batch.qual))
         return dict(contig_rec_off=np.array(batch.contig_rec_off, dtype=np.int64, copy=True),
                     pos=_as_torch(batch.pos, d), tlen=_as_torch(batch.tlen, d), aln_score=_as_torch(batch.aln_score, d),
                     frag=_as_torch(batch.frag, d), cigar_off=_as_torch(batch.cigar_off, d), cigar=_as_torch(batch.cigar, d),

@@ -428,3 +428,20 @@ def test_a_huge_fragment_takes_the_sort_based_graph(gpu, tmp_path):
     assert ca == cb
     for k in a:
         assert np.array_equal(a[k], b[k]), k
+
+
+def test_staged_upload_equals_pageable_copy(gpu, tmp_path):
+    """phz_upload (page-locked staging ring filled by host threads, what the command line uses for large BAMs) puts the
+    same bytes on the device as plain pageable copies -- incl. arrays of several staging chunks and odd sizes."""
+    import torch
+    vcf, sams = util.make_case(tmp_path, 57, 300, 4000, n_bams=1)
+    vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+    a = gpu.upload_reads(batches[0], staged=False); b = gpu.upload_reads(batches[0], staged=True)
+    for k in a:
+        if k != "contig_rec_off":
+            assert torch.equal(a[k], b[k]), k
+    big = np.random.default_rng(1).integers(0, 255, size=(3 * (32 << 20) + 12345,), dtype=np.uint8)
+    assert torch.equal(gpu._upload(big).cpu(), torch.from_numpy(big))
+    got, res, _ = util.product_outputs(gpu, vcf, sams)
+    exp, _ = util.oracle_outputs(vcf, sams)
+    assert not compare.diff_outputs(exp, got)
