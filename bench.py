@@ -352,11 +352,11 @@ def run_ours(a):
     clocks = ClockSampler(local); clocks.start()          # streaming before the timed region starts
     for _ in range(a.warmup):
         step()
-    own0, lib0 = E.launch_counts()
+    own0, lib0 = E.launch_counts(); sync0 = E.sync_count()
     clocks.ensure_running()
     ms_step, ms_mine, k1, region = timed_resident(step, a.steps, 0, a.profiler_range)
     clock_rows = clocks.stop_rows(*region)          # samples taken during the timed steps
-    own1, lib1 = E.launch_counts()
+    own1, lib1 = E.launch_counts(); sync1 = E.sync_count()
     rank_ms = all_ranks(ms_mine)
     k1_total_ms = float(k1.sum(1).mean())
     my_R = int(my_reads["pos"].shape[0])
@@ -575,6 +575,7 @@ def run_ours(a):
                          "k1_mode": a.k1_mode},
             "e2e": e2e, "e2e_plain_soa": e2e_plain, "cpu_baseline": cpu, "cli_files_to_files": cli,
             "gpu_launches": int((own1 - own0) / a.steps), "library_passes": int((lib1 - lib0) / a.steps),
+            "host_syncs_per_step": round((sync1 - sync0) / a.steps, 1),
             "clocks": clk,
         }
         if sharding is not None:

@@ -211,6 +211,8 @@ int phz_map_times(phz_ctx* ctx, float* ms);
 int phz_stage_report(phz_ctx* ctx, char* buf, int64_t buf_len);
 /* kernels of this library launched so far / library (CUB) passes launched so far */
 int phz_launch_counts(phz_ctx* ctx, uint64_t* own, uint64_t* library);
+/* blocking waits of the host on the context's stream so far (device counters read back, result downloads, phz_sync) */
+int phz_sync_count(phz_ctx* ctx, uint64_t* n);
 
 /* ---- feature-level haplotypic counts: the join and the distinct-read counting of
  * phaser_gene_ae.py (phaser_gene_ae/phaser_gene_ae.py:95-101, 172-219).  All pointers are DEVICE pointers.  Rows =
@@ -254,6 +256,11 @@ phz_fragdict* phz_fragdict_create(void);
 void phz_fragdict_destroy(phz_fragdict* d);
 int64_t phz_fragdict_size(phz_fragdict* d);
 int64_t phz_fragdict_name(phz_fragdict* d, int64_t id, char* buf, int64_t buflen);
+/* bulk export / import of the dictionary in id order (names back to back, n+1 offsets): the SoA cache file keeps it
+ * beside the arrays so that a later run skips the ingest ("parse once").  Import needs an empty dictionary. */
+int64_t phz_fragdict_blob_bytes(phz_fragdict* d);
+int phz_fragdict_export(phz_fragdict* d, char* blob, int64_t* off);
+int phz_fragdict_import(phz_fragdict* d, const char* blob, const int64_t* off, int64_t n, int n_threads);
 phz_host_reads* phz_read_alignments(const char* path, const char* const* contigs, int n_contigs, phz_fragdict* d,
                                     int remove_dups, int proper_pair, int min_mapq, int n_threads);
 int phz_host_reads_view(phz_host_reads* r, phz_reads* out, int* sorted_by_coordinate);

@@ -449,6 +449,8 @@ int phz_stage_report(phz_ctx* ctx, char* buf, int64_t buf_len) {
   PHZ_CATCH
 }
 
+int phz_sync_count(phz_ctx* ctx, uint64_t* n) { PHZ_TRY *n = ctx->p.be.syncs; PHZ_CATCH }
+
 int phz_launch_counts(phz_ctx* ctx, uint64_t* own, uint64_t* library) {
   PHZ_TRY *own = ctx->p.be.launches; *library = ctx->p.be.lib_launches; PHZ_CATCH
 }

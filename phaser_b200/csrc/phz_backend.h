@@ -157,6 +157,7 @@ struct DeviceBackend {
   int device = 0;
   u64 launches = 0;          // kernels of OURS launched (for_each + hand-written); CUB passes counted separately
   u64 lib_launches = 0;
+  u64 syncs = 0;             // blocking waits of the host on this stream (device counters read back, explicit syncs)
   void* cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
   // optional per-stage CUDA-event timing on this stream (phz_set_profiling)
@@ -219,6 +220,7 @@ struct DeviceBackend {
   void d2h(void* dst, const void* src, size_t bytes) {
     if (bytes) PHZ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
     PHZ_CUDA(cudaStreamSynchronize(stream));
+    syncs++;
   }
   void d2h_async(void* dst, const void* src, size_t bytes) {
     if (bytes) PHZ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
@@ -258,7 +260,7 @@ struct DeviceBackend {
   void free_event(void* ev) { if (ev) cudaEventDestroy((cudaEvent_t)ev); }
   void copy_record(void* ev) { PHZ_CUDA(cudaEventRecord((cudaEvent_t)ev, copy_stream)); }
   void wait_event(void* ev) { PHZ_CUDA(cudaStreamWaitEvent(stream, (cudaEvent_t)ev, 0)); }
-  void sync() { PHZ_CUDA(cudaStreamSynchronize(stream)); }
+  void sync() { PHZ_CUDA(cudaStreamSynchronize(stream)); syncs++; }
 
   template <class F>
   void for_each(int64_t n, F f) {
@@ -387,6 +389,7 @@ struct HostSimBackend {
   int device = -1;
   u64 launches = 0;
   u64 lib_launches = 0;
+  u64 syncs = 0;
   int profiling = 0;
   void mark(int) {}
   float elapsed(int, int) { return -1.f; }
@@ -398,7 +401,7 @@ struct HostSimBackend {
   void memset0(void* p, size_t bytes) { std::memset(p, 0, bytes); }
   void memset_ff(void* p, size_t bytes) { std::memset(p, 0xFF, bytes); }
   void h2d(void* dst, const void* src, size_t bytes) { if (bytes) std::memcpy(dst, src, bytes); }
-  void d2h(void* dst, const void* src, size_t bytes) { if (bytes) std::memcpy(dst, src, bytes); }
+  void d2h(void* dst, const void* src, size_t bytes) { if (bytes) std::memcpy(dst, src, bytes); syncs++; }
   void d2h_async(void* dst, const void* src, size_t bytes) { if (bytes) std::memcpy(dst, src, bytes); }
   void d2d(void* dst, const void* src, size_t bytes) { if (bytes) std::memmove(dst, src, bytes); }
   void copy_out_async(void* dst, const void* src, size_t bytes) { if (bytes) std::memmove(dst, src, bytes); }

@@ -652,6 +652,40 @@ int64_t phz_fragdict_name(phz_fragdict* d, int64_t id, char* buf, int64_t buflen
   return n;
 }
 
+// Bulk export / import of the QNAME dictionary (ids in order): what the SoA cache file stores beside the arrays so that a
+// later run can skip the ingest ("parse once") and still name its reads or meet the same QNAME in
+// another BAM.
+int64_t phz_fragdict_blob_bytes(phz_fragdict* d) {
+  int64_t n = 0;
+  for (size_t g = 0; g < d->d.count; ++g) { auto& S = d->d.sh[d->d.id_shard[g]]; u32 e = d->d.id_ent[g]; n += (int64_t)(S.name_off[e + 1] - S.name_off[e]); }
+  return n;
+}
+int phz_fragdict_export(phz_fragdict* d, char* blob, int64_t* off) {
+  PHZ_TRY
+  int64_t at = 0;
+  for (size_t g = 0; g < d->d.count; ++g) {
+    auto& S = d->d.sh[d->d.id_shard[g]]; u32 e = d->d.id_ent[g];
+    const u64 o = S.name_off[e]; const int64_t n = (int64_t)(S.name_off[e + 1] - o);
+    off[g] = at; std::memcpy(blob + at, S.arena.data() + o, (size_t)n); at += n;
+  }
+  off[d->d.count] = at;
+  PHZ_CATCH
+}
+int phz_fragdict_import(phz_fragdict* d, const char* blob, const int64_t* off, int64_t n, int n_threads) {
+  PHZ_TRY
+  if (d->d.count != 0) throw PhzError("phz_fragdict_import: the dictionary must be empty");
+  std::vector<const char*> names((size_t)n); std::vector<u32> lens((size_t)n); std::vector<u64> hashes((size_t)n); std::vector<u32> ids;
+  phzio::parallel_for((size_t)((n + 65535) / 65536), n_threads, [&](size_t c) {
+    const int64_t i1 = std::min<int64_t>(n, (int64_t)(c + 1) * 65536);
+    for (int64_t i = (int64_t)c * 65536; i < i1; ++i) {
+      names[i] = blob + off[i]; lens[i] = (u32)(off[i + 1] - off[i]); hashes[i] = phzio::name_hash(names[i], lens[i]);
+    }
+  });
+  d->d.assign(names, lens, hashes, ids, n_threads);
+  for (int64_t i = 0; i < n; ++i) if (ids[i] != (u32)i) throw PhzError("phz_fragdict_import: duplicate names in the cache");
+  PHZ_CATCH
+}
+
 phz_host_reads* phz_read_alignments(const char* path, const char* const* contigs, int n_contigs, phz_fragdict* fd,
                                     int remove_dups, int proper_pair, int min_mapq, int n_threads) {
   try {

@@ -1111,7 +1111,7 @@ struct Pipeline {
     be.exclusive_scan_u32(fc, fo, F);
     u64* fk = f_key.ensure(n); uint16_t* fi = f_info.ensure(n);
     u32* sz = setsize.ensure(Vn * 3); u32* vbc = vb_cnt.ensure(Vn * nb * 2); u64* vr = vrank.ensure(Vn);
-    u64* c3 = pt_cnt3.ensure(4);
+    u64* c3 = pt_cnt3.ensure(8);
     u32 hsc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int attempt = 0;; ++attempt) {
       const u64 S = pair_table_slots;
@@ -1124,7 +1124,7 @@ struct Pipeline {
       be.memset0(sz, Vn * 3 * sizeof(u32)); be.memset0(vbc, Vn * nb * 2 * sizeof(u32)); be.memset_ff(vr, Vn * sizeof(u64));
       u64* pk = pt_keys.ensure(S); u32* pv = pt_vals.ensure(S * PAIR_CELLS); u32* pf = pt_flags.ensure(4);
       be.memset_ff(pk, S * sizeof(u64)); be.memset0(pv, S * PAIR_CELLS * sizeof(u32)); be.memset0(pf, 4 * sizeof(u32));
-      be.memset0(c3, 4 * sizeof(u64));
+      be.memset0(c3, 8 * sizeof(u64));
       PairTable pt{pk, pv, (u32)(S - 1), pf};
       FragCtx fx{vc, excl_mask, vr, sc + 1};
       u32* fne = fc;                      // the counts are not needed any more: the slot becomes the entry count
@@ -1165,21 +1165,21 @@ struct Pipeline {
         xf[h] = (used && pv[h * PAIR_CELLS + 9]) ? 1u : 0u;
       });
       be.exclusive_scan_u32(xf, xs, (int64_t)S);
+      // ONE wait for everything the host needs from the stage so far: table-full flag, distinct pairs, edges, the ranking
+      // pass's verdict, and the entry / group / pair totals
       { const u32* xs_c = xs; int64_t ss = (int64_t)S;
-        be.for_each(1, PHZ_LAMBDA(int64_t) { pf[2] = xs_c[ss]; pf[3] = sc[1]; }); }
-      u32 h4[4] = {0, 0, 0, 0};
-      be.d2h(h4, pf, sizeof(h4));
-      if (h4[3] & 8u) return false;            // a fragment beyond the 16-bit rank: sort-based stage
-      if (h4[0] & 1u) {                        // pair table full: grow it and run the fragments again
+        be.for_each(1, PHZ_LAMBDA(int64_t) { c3[3] = pf[0]; c3[4] = pf[1]; c3[5] = xs_c[ss]; c3[6] = sc[1]; }); }
+      u64 h7[7] = {0, 0, 0, 0, 0, 0, 0};
+      be.d2h(h7, c3, sizeof(h7));
+      if (h7[6] & 8u) return false;            // a fragment beyond the 16-bit rank: sort-based stage
+      if (h7[3] & 1u) {                        // pair table full: grow it and run the fragments again
         if (attempt >= 8) throw PhzError("pair table keeps overflowing");
         pair_table_slots *= 4; pair_table_grown++;
         continue;
       }
-      NX = h4[1]; E = h4[2];
+      NX = (int64_t)h7[4]; E = (int64_t)h7[5];
       if ((u64)NX * 2 > S) { pair_table_slots *= 2; }     // keep the load factor low for the next sample (no re-run needed now)
-      u64 h3[3] = {0, 0, 0};
-      be.d2h(h3, c3, sizeof(h3));
-      NE = (int64_t)h3[0]; NG = (int64_t)h3[1]; NP = (int64_t)h3[2];
+      NE = (int64_t)h7[0]; NG = (int64_t)h7[1]; NP = (int64_t)h7[2];
       // ---- edge table
       u64* ek = d_key.ensure(E); u64* ek2 = d_key2.ensure(E); u32* es = pt_slot.ensure(2 * E + 2); u32* es2 = es + E + 1;
       be.for_each((int64_t)S, PHZ_LAMBDA(int64_t h) { if (xf[h]) { ek[xs[h]] = pk[h]; es[xs[h]] = (u32)h; } });
@@ -1523,9 +1523,10 @@ struct Pipeline {
         if (atomic_cas(&par[b], b, a) == b) break;
       }
     });
-    n_dropped = E > 0 ? fetch_u32(sc + 2) : 0;
     be.stage("phase.members");
-    // ---- members of the kept-edge graph, grouped by component root, ascending variant index inside
+    // ---- members of the kept-edge graph, grouped by component root, ascending variant index inside.  The member flags
+    // (over the sites) and the directed-adjacency flags (over the edges) are scanned back to back and their totals read
+    // with the number of dropped edges in ONE wait.
     u32* rt = root.ensure(Vn); u32* mf = m_flag.ensure(Vn + 1); u32* ms = m_scan.ensure(Vn + 2);
     be.for_each(Vn, PHZ_LAMBDA(int64_t v) {
       if (dg[v] == 0) { mf[v] = 0; rt[v] = NONE32; return; }
@@ -1533,13 +1534,34 @@ struct Pipeline {
       rt[v] = a; mf[v] = 1;
     });
     be.exclusive_scan_u32(mf, ms, Vn);
-    NM = Vn > 0 ? (int64_t)fetch_u32(ms + Vn) : 0;
+    u32* af = x_flag.ensure(E + 1 > NX + 1 ? E + 1 : NX + 1); u32* as_ = x_scan.ensure(E + 2 > NX + 2 ? E + 2 : NX + 2);
+    be.for_each(E, PHZ_LAMBDA(int64_t e) { af[e] = (keep[e] && ecfg[e] != EDGE_TIE) ? 2u : 0u; });
+    be.exclusive_scan_u32(af, as_, E);
+    { const int64_t vn = Vn, ee = E;
+      be.for_each(1, PHZ_LAMBDA(int64_t) { sc[4] = vn > 0 ? ms[vn] : 0u; sc[5] = ee > 0 ? as_[ee] : 0u; }); }
+    u32 h3[6] = {0, 0, 0, 0, 0, 0};
+    be.d2h(h3, sc, sizeof(h3));
+    n_dropped = h3[2]; NM = h3[4]; const int64_t ND = h3[5];
     u32* ml = m_list.ensure(NM); u32* mk = m_key.ensure(NM); u32* mk2 = m_key2.ensure(NM); u32* mem = members.ensure(NM);
     be.for_each(Vn, PHZ_LAMBDA(int64_t v) { if (mf[v]) { ml[ms[v]] = (u32)v; mk[ms[v]] = rt[v]; } });
     be.sort_pairs32(mk, mk2, ml, mem, NM, 0, vb);
     u32* bf = b_flag.ensure(NM + 1); u32* bs = b_scan.ensure(NM + 2);
     be.for_each(NM, PHZ_LAMBDA(int64_t i) { bf[i] = (i == 0 || mk2[i] != mk2[i - 1]) ? 1u : 0u; });
     be.exclusive_scan_u32(bf, bs, NM);
+    // ---- adjacency (kept, non-tie) by source variant: independent of the block count, so it is queued before that is read
+    u64* dk = d_key.ensure(ND); u64* dk2 = d_key2.ensure(ND); u32* dsg = d_sign.ensure(ND); u32* dsg2 = d_sign2.ensure(ND);
+    u32* ao = adj_off.ensure(Vn + 2);
+    u32* dcnt = m_flag.p;      // reuse (the member flags were consumed above): per-variant directed degree
+    be.memset0(dcnt, (Vn + 1) * sizeof(u32));
+    be.for_each(E, PHZ_LAMBDA(int64_t e) {
+      if (!af[e]) return;
+      u32 o = as_[e]; u32 a = ea_[e], b = eb_[e];
+      dk[o] = ((u64)a << vb) | b; dsg[o] = ecfg[e];
+      dk[o + 1] = ((u64)b << vb) | a; dsg[o + 1] = ecfg[e];
+      atomic_add(&dcnt[a], 1u); atomic_add(&dcnt[b], 1u);
+    });
+    be.sort_pairs(dk, dk2, dsg, dsg2, ND, 0, 2 * vb);
+    be.exclusive_scan_u32(dcnt, ao, Vn);
     NB = NM > 0 ? (int64_t)fetch_u32(bs + NM) : 0;
     u32* bo = blk_off.ensure(NB + 1); u32* bof = blk_of.ensure(Vn); u32* pib = pos_in_blk.ensure(Vn);
     be.memset_ff(bof, Vn * sizeof(u32));
@@ -1563,25 +1585,6 @@ struct Pipeline {
     be.for_each(NB, PHZ_LAMBDA(int64_t i) { b32[i] = cr[vc[mem[bo[bv2[i]]]]]; });
     be.sort_pairs32(b32, b32b, bv2, bord, NB, 0, ceil_log2_host((u64)(nc > 1 ? nc : 2)));
     be.for_each(NB, PHZ_LAMBDA(int64_t i) { bpos[bord[i]] = (u32)i; });
-    be.stage("phase.adjacency");
-    // ---- adjacency (kept, non-tie) by source variant
-    u32* af = x_flag.ensure(E + 1 > NX + 1 ? E + 1 : NX + 1); u32* as_ = x_scan.ensure(E + 2 > NX + 2 ? E + 2 : NX + 2);
-    be.for_each(E, PHZ_LAMBDA(int64_t e) { af[e] = (keep[e] && ecfg[e] != EDGE_TIE) ? 2u : 0u; });
-    be.exclusive_scan_u32(af, as_, E);
-    int64_t ND = E > 0 ? (int64_t)fetch_u32(as_ + E) : 0;
-    u64* dk = d_key.ensure(ND); u64* dk2 = d_key2.ensure(ND); u32* dsg = d_sign.ensure(ND); u32* dsg2 = d_sign2.ensure(ND);
-    u32* ao = adj_off.ensure(Vn + 2);
-    u32* dcnt = m_flag.p;      // reuse: per-variant directed degree
-    be.memset0(dcnt, (Vn + 1) * sizeof(u32));
-    be.for_each(E, PHZ_LAMBDA(int64_t e) {
-      if (!af[e]) return;
-      u32 o = as_[e]; u32 a = ea_[e], b = eb_[e];
-      dk[o] = ((u64)a << vb) | b; dsg[o] = ecfg[e];
-      dk[o + 1] = ((u64)b << vb) | a; dsg[o + 1] = ecfg[e];
-      atomic_add(&dcnt[a], 1u); atomic_add(&dcnt[b], 1u);
-    });
-    be.sort_pairs(dk, dk2, dsg, dsg2, ND, 0, 2 * vb);
-    be.exclusive_scan_u32(dcnt, ao, Vn);
     be.stage("phase.fast_bfs");
     // ---- fast path: 2-colouring from the leftmost variant (resolve_phase, phaser.py:2172-2207)
     u8* col = color.ensure(Vn); be.memset_ff(col, Vn);
@@ -1609,21 +1612,27 @@ struct Pipeline {
       } else if (conflict && 2 * m == n) {       // reaches n alleles on m variants: short all-zero string
         bst[b] = 1; bnf[b] = 1; rs[o0] = 0; rl[o0] = m;
         for (u32 i = o0; i < o0 + m; ++i) { u32 v = mem[i]; vh[v] = 0; vfl[v] = 0; }
-      } else { bst[b] = 2; bnf[b] = 0; }
+      } else { bst[b] = 2; bnf[b] = 0; atomic_add(&sc[7], n); }       // sc[7]: members of hard blocks (sizes their scratch)
     });
     be.stage("phase.hard_prepare");
     // ---- hard path: phase_v3 proper, one logical thread per block
     u32* hf = h_flag.ensure(NB + 1); u32* hs = h_scan.ensure(NB + 2);
     be.for_each(NB, PHZ_LAMBDA(int64_t b) { hf[b] = bst[b] == 2 ? 1u : 0u; });
     be.exclusive_scan_u32(hf, hs, NB);
-    NH = NB > 0 ? (int64_t)fetch_u32(hs + NB) : 0;
+    u32 h8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (NB > 0) {
+      const int64_t nbk = NB;
+      be.for_each(1, PHZ_LAMBDA(int64_t) { sc[3] = hs[nbk]; });
+      be.d2h(h8, sc, sizeof(h8));            // ONE wait: number of hard blocks + their members (kept edges = E - dropped is known)
+    }
+    NH = h8[3];
     if (NH > 0) {
       // per-block lists of kept edges (ties included: they count as connections in find_weak_points)
       u32* ec = ebk_cnt.ensure(NB + 1); u32* eo = ebk_off.ensure(NB + 2); be.memset0(ec, (NB + 1) * sizeof(u32));
       be.for_each(E, PHZ_LAMBDA(int64_t e) { af[e] = keep[e] ? 1u : 0u; if (keep[e]) atomic_add(&ec[bof[ea_[e]]], 1u); });
       be.exclusive_scan_u32(ec, eo, NB);
       be.exclusive_scan_u32(af, as_, E);
-      int64_t NK = E > 0 ? (int64_t)fetch_u32(as_ + E) : 0;
+      const int64_t NK = E - (int64_t)n_dropped;
       u32* kk = ebk_key.ensure(NK); u32* kk2 = ebk_key2.ensure(NK); u32* kv = ebk_val.ensure(NK); u32* kl = ebk_list.ensure(NK);
       be.for_each(E, PHZ_LAMBDA(int64_t e) { if (af[e]) { kk[as_[e]] = bof[ea_[e]]; kv[as_[e]] = (u32)e; } });
       be.sort_pairs32(kk, kk2, kv, kl, NK, 0, ceil_log2_host((u64)(NB > 1 ? NB : 2)));
@@ -1633,7 +1642,8 @@ struct Pipeline {
         hl[hs[b]] = (u32)b; hw[hs[b]] = (u32)hard_scratch_words(bo[b + 1] - bo[b]);
       });
       be.exclusive_scan_u32(hw, hwo, NH);
-      u32 words = fetch_u32(hwo + NH);
+      const size_t words = hard_scratch_words(0) * (size_t)NH + (hard_scratch_words(1) - hard_scratch_words(0)) * (size_t)h8[7];
+      if (words >= 0xFFFFFFF0ull) throw PhzError("hard-block scratch beyond 2^32 words");
       u32* scr = h_scratch.ensure(words);
       int mbs = max_block_size;
       be.stage("phase.hard_kernel");
@@ -1657,8 +1667,11 @@ struct Pipeline {
     u32* nfo = nf_ord.ensure(NB + 1); u32* fbb = fb_base.ensure(NB + 2);
     be.for_each(NB, PHZ_LAMBDA(int64_t i) { nfo[i] = bnf[bord[i]]; });
     be.exclusive_scan_u32(nfo, fbb, NB);
-    NF = NB > 0 ? (int64_t)fetch_u32(fbb + NB) : 0;
-    u32* ff = fb_first.ensure(NF); u32* fl = fb_len.ensure(NF); u32* fbk = fb_blk.ensure(NF);
+    // the number of final blocks is read with the closing counters: until then every array is sized by its bound (a final
+    // block has at least one member) and no launch depends on it
+    const int64_t NFmax = NM > 0 ? NM : 1;
+    { const int64_t nbk = NB; be.for_each(1, PHZ_LAMBDA(int64_t) { sc[0] = nbk > 0 ? fbb[nbk] : 0u; }); }
+    u32* ff = fb_first.ensure(NFmax); u32* fl = fb_len.ensure(NFmax); u32* fbk = fb_blk.ensure(NFmax);
     u32* vfin = v_final.ensure(Vn); be.memset_ff(vfin, Vn * sizeof(u32));
     u32* vmi = v_member.ensure(Vn);
     be.for_each(NB, PHZ_LAMBDA(int64_t i) {
@@ -1675,8 +1688,8 @@ struct Pipeline {
     });
     be.stage("phase.edge_support");
     // ---- edge support per final block (phaser.py:876-895)
-    u32* fsup = fb_sup.ensure(NF); u32* ftot = fb_tot.ensure(NF);
-    be.memset0(fsup, NF * sizeof(u32)); be.memset0(ftot, NF * sizeof(u32));
+    u32* fsup = fb_sup.ensure(NFmax); u32* ftot = fb_tot.ensure(NFmax);
+    be.memset0(fsup, NFmax * sizeof(u32)); be.memset0(ftot, NFmax * sizeof(u32));
     be.for_each(E, PHZ_LAMBDA(int64_t e) {
       if (!keep[e] || ecfg[e] == EDGE_TIE) return;
       u32 a = ea_[e], b = eb_[e]; u32 fa = vfin[a];
@@ -1686,8 +1699,8 @@ struct Pipeline {
     });
     be.stage("phase.hap_counts");
     // ---- unique-fragment counts per final block x haplotype (all BAMs, and per counted BAM)
-    u32* fc = fb_cnt.ensure(NF * 2); u32* fbc = fb_bcnt.ensure(NF * nb * 2);
-    be.memset0(fc, NF * 2 * sizeof(u32)); be.memset0(fbc, NF * nb * 2 * sizeof(u32));
+    u32* fc = fb_cnt.ensure(NFmax * 2); u32* fbc = fb_bcnt.ensure(NFmax * nb * 2);
+    be.memset0(fc, NFmax * 2 * sizeof(u32)); be.memset0(fbc, NFmax * nb * 2 * sizeof(u32));
     const u8* vbl = vblack;
     if (frag_entries) {
       // entries as the fragment-table stage left them: fragment f owns f_key / f_info [f_off[f], f_off[f] + f_cnt[f])
@@ -1739,7 +1752,7 @@ struct Pipeline {
     }
     u32 hsc8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     be.d2h(hsc8, sc, sizeof(hsc8));
-    *err_out = (int)hsc8[1]; max_final_len = hsc8[6];
+    *err_out = (int)hsc8[1]; max_final_len = hsc8[6]; NF = hsc8[0];
     be.stage("phase.end");
   }
 

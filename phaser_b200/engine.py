@@ -72,7 +72,8 @@ EXPORTS = ["phz_last_error", "phz_backend_name", "phz_create", "phz_destroy", "p
            "phz_set_indel_alleles", "phz_pack_reads", "phz_packed_view", "phz_packed_bytes", "phz_packed_free",
            "phz_map_reads_packed", "phz_prefetch_packed", "phz_gene_ae_pairs", "phz_set_big_critical_values",
            "phz_copy_array", "phz_vcf_open", "phz_vcf_close", "phz_vcf_text", "phz_vcf_chrom_line", "phz_vcf_parse",
-           "phz_vcf_write", "phz_vcf_records", "phz_write_bam", "phz_vcf_save", "phz_format_read_lists", "phz_upload"]
+           "phz_vcf_write", "phz_vcf_records", "phz_write_bam", "phz_vcf_save", "phz_format_read_lists", "phz_upload", "phz_sync_count",
+           "phz_fragdict_blob_bytes", "phz_fragdict_export", "phz_fragdict_import"]
 
 
 def _declare(lib):
@@ -106,6 +107,7 @@ def _declare(lib):
                                     POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int32)]
     lib.phz_vcf_save.argtypes = [c_void_p, c_char_p, c_int, c_int]
     lib.phz_upload.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int]
+    lib.phz_sync_count.argtypes = [c_void_p, POINTER(c_uint64)]
     lib.phz_format_read_lists.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int,
                                           POINTER(c_void_p), POINTER(c_void_p)]
     lib.phz_counters.argtypes = [c_void_p, POINTER(c_int64)]
@@ -120,6 +122,10 @@ def _declare(lib):
     lib.phz_fragdict_size.argtypes = [c_void_p]
     lib.phz_fragdict_name.restype = c_int64
     lib.phz_fragdict_name.argtypes = [c_void_p, c_int64, c_char_p, c_int64]
+    lib.phz_fragdict_blob_bytes.restype = c_int64
+    lib.phz_fragdict_blob_bytes.argtypes = [c_void_p]
+    lib.phz_fragdict_export.argtypes = [c_void_p, c_void_p, c_void_p]
+    lib.phz_fragdict_import.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int]
     lib.phz_read_alignments.restype = c_void_p
     lib.phz_read_alignments.argtypes = [c_char_p, POINTER(c_char_p), c_int, c_void_p, c_int, c_int, c_int, c_int]
     lib.phz_host_reads_view.argtypes = [c_void_p, POINTER(phz_reads), POINTER(c_int)]
@@ -158,7 +164,10 @@ def _as_torch(a: np.ndarray, device, pin=False):
         a = a.view(np.int32)
     elif a.dtype == np.uint64:
         a = a.view(np.int64)
-    t = torch.from_numpy(np.ascontiguousarray(a))
+    import warnings
+    with warnings.catch_warnings():          # memory-mapped cache arrays are read-only: the tensor is only ever copied from
+        warnings.simplefilter("ignore", UserWarning)
+        t = torch.from_numpy(np.ascontiguousarray(a))
     if pin and torch.cuda.is_available():
         t = t.pin_memory()
     if device is None:
@@ -177,6 +186,21 @@ class NativeFragmentDictionary:
 
     def __len__(self):
         return int(self.lib.phz_fragdict_size(self.h))
+
+    def export(self):
+        """(names back to back as uint8, int64 offsets[n+1]) in id order"""
+        n = len(self)
+        blob = np.empty(max(1, int(self.lib.phz_fragdict_blob_bytes(self.h))), np.uint8); off = np.zeros(n + 1, np.int64)
+        if self.lib.phz_fragdict_export(self.h, blob.ctypes.data, off.ctypes.data) != 0:
+            raise PhzError(self.lib.phz_last_error().decode())
+        return blob[:int(off[n])], off
+
+    def load(self, blob, off, threads=0):
+        """fill the (empty) dictionary with names in id order"""
+        blob = np.ascontiguousarray(blob, np.uint8); off = np.ascontiguousarray(off, np.int64)
+        if self.lib.phz_fragdict_import(self.h, blob.ctypes.data, off.ctypes.data, int(off.shape[0] - 1),
+                                        int(threads or (os.cpu_count() or 1))) != 0:
+            raise PhzError(self.lib.phz_last_error().decode())
 
     @property
     def names(self):
@@ -562,6 +586,11 @@ class Engine:
         a = c_uint64(0); b = c_uint64(0)
         self._check(self.lib.phz_launch_counts(self.ctx, byref(a), byref(b)))
         return a.value, b.value
+
+    def sync_count(self):
+        n = c_uint64(0)
+        self._check(self.lib.phz_sync_count(self.ctx, byref(n)))
+        return n.value
 
     def set_profiling(self, level=1):
         """0 off, 1 CUDA events around the K1 passes, 2 additionally named stage marks."""

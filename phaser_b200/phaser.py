@@ -71,6 +71,9 @@ def build_parser():
     p.add_argument("--process_slow", type=int, default=0, required=False)
     # this implementation only
     p.add_argument("--device", default="cuda:0", help="CUDA device to run on")
+    p.add_argument("--soa_cache", default=os.environ.get("PHZ_SOA_CACHE", ""),
+                   help="directory of the SoA cache (parse once): the first BAM's packed arrays are kept there and mapped back "
+                        "in by later runs on the same BAM, contigs and read filters")
     return p
 
 
@@ -231,14 +234,27 @@ def run(args, engine=None):
     from phaser_b200.engine import NativeFragmentDictionary, read_alignments_native, PhzError, pack_reads
     fd = NativeFragmentDictionary(engine.lib)
     batches = []
+    n_frag_cached = 0
     for i, bam in enumerate(bam_list):
         say("     file: %s" % bam)
         say("          minimum mapq: %s" % mapq[i])
-        try:        # native reader: BGZF blocks inflated on --threads host threads, records decoded straight into SoA
-            rb = read_alignments_native(bam, vt.contigs, fd, remove_dups=(args.remove_dups == 1), proper_pair=(paired[i] == 1),
-                                        min_mapq=mapq[i], threads=max(1, args.threads), lib=engine.lib)
-        except PhzError as e:
-            fatal_error(str(e))
+        rb = None; ckey = None
+        if args.soa_cache and i == 0:          # parse once: the first BAM's arrays may already sit in the cache
+            from phaser_b200 import soacache
+            ckey = soacache.cache_key(bam, vt.contigs, args.remove_dups == 1, paired[i] == 1, mapq[i])
+            rb = soacache.load(args.soa_cache, ckey, fd, need_names=(len(bam_list) > 1 or args.output_read_ids == 1),
+                               threads=max(1, args.threads))
+            if rb is not None:
+                n_frag_cached = rb.n_fragments
+                say("          (packed arrays from the SoA cache)")
+        if rb is None:
+            try:        # native reader: BGZF blocks inflated on --threads host threads, records decoded straight into SoA
+                rb = read_alignments_native(bam, vt.contigs, fd, remove_dups=(args.remove_dups == 1), proper_pair=(paired[i] == 1),
+                                            min_mapq=mapq[i], threads=max(1, args.threads), lib=engine.lib)
+            except PhzError as e:
+                fatal_error(str(e))
+            if ckey is not None:
+                soacache.save(args.soa_cache, ckey, rb, fd)
         _t = _trace(_t, "read_alignments_native")
         # One-shot run: the plain arrays go up as they are.  The packed transport form (engine.pack_reads) pays off
         # when host buffers are copied more than once or prefetched (sample loops, bench.py); packing once for a
@@ -256,7 +272,7 @@ def run(args, engine=None):
                              max_block_size=args.max_block_size, haplo_count_bam_exclude=exclude,
                              want_read_ids=(args.output_read_ids == 1), want_kept_tuples=(args.output_network != ""))
     try:
-        res = pipeline.run_path(engine, vt, batches, P, n_fragments=len(fd), reuse_result_buffer=True)
+        res = pipeline.run_path(engine, vt, batches, P, n_fragments=max(len(fd), n_frag_cached), reuse_result_buffer=True)
     except PhaserFatal as e:
         fatal_error(str(e))
     _t = _trace(_t, "run_path (device)")

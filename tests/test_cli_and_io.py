@@ -254,3 +254,20 @@ def test_parallel_bgzf_blocks_equal_the_streaming_writer(tmp_path):
         w.write(data)
     assert b"".join(bgzf.compress_all(data, threads=4)) + bgzf.EOF_BLOCK == open(p, "rb").read()
     assert bgzf.read_all(p) == data
+
+
+@pytest.mark.parametrize("case", ["rna_two_bams", "opt_read_ids", "rna_small"])
+def test_soa_cache_gives_the_same_files(engine, tmp_path, case):
+    """--soa_cache: the second run maps the first BAM's packed arrays back in instead of parsing (and refills the QNAME
+    dictionary when a second BAM or --output_read_ids needs the names); same files as the reference either way."""
+    cache = str(tmp_path / "cache")
+    c, got1 = _run_cli(engine, case, tmp_path, extra=["--soa_cache", cache])
+    assert not compare.diff_outputs(c["ref"], got1)
+    assert any(os.path.isfile(os.path.join(cache, d, "done")) for d in os.listdir(cache))
+    import io, contextlib
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        c, got2 = _run_cli(engine, case, tmp_path, extra=["--soa_cache", cache])
+    assert "from the SoA cache" in buf.getvalue()
+    assert not compare.diff_outputs(c["ref"], got2)
+    assert got1 == got2
