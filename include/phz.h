@@ -203,6 +203,9 @@ int phz_counters(phz_ctx* ctx, int64_t* counters);
  * canonical order (default); 2 = fused single pass with decoupled look-back; 1 = windowed two-pass
  * (count, scan, emit); 0 = generic two-pass (searches in global memory).  All four emit identical tuples. */
 int phz_set_option(phz_ctx* ctx, const char* name, int64_t value);
+/* Reads a switch back, or one of the read-only facts about the last run: "graph_ranked_in_commit" (1 when the graph
+ * stage used the in-fragment ranks the commits took, see "n_fragments"), "pair_table_slots" (after any growth). */
+int phz_get_option(phz_ctx* ctx, const char* name, int64_t* value);
 /* CUDA-event timing of the K1 passes of the LAST phz_map_reads call on the context's stream:
  * ms[0] = count pass, ms[1] = scan + size readback, ms[2] = emit pass (-1 when profiling is off). */
 int phz_set_profiling(phz_ctx* ctx, int level);   /* 0 off, 1 K1 pass events, 2 + named stage marks */

@@ -640,8 +640,11 @@ struct Pipeline {
   bool tile_order = false, canonical_valid = true; int64_t tiles_cur = 0;
   int graph_mode = 1;               // 1: fragment-table graph stage (phz_graph.h), 0: sort-based stage (A/B switch and fallback)
   bool frag_entries = false;        // which form of the (fragment, variant, BAM) entries the last build_graph left behind
-  Buf<B, u32> f_cnt, f_off; Buf<B, uint16_t> t_rank, f_info; Buf<B, u64> f_key, pt_keys, pt_cnt3; Buf<B, u32> pt_vals, pt_flags, pt_slot;
+  Buf<B, u32> f_cnt, f_off; Buf<B, uint16_t> t_rank, f_info; Buf<B, u64> f_key, pt_keys, pt_cnt3; Buf<B, u32> pt_vals, pt_flags, pt_slot, rank_flag;
   int64_t n_frag_cur = 0; u64 pair_table_slots = 1ull << 20; int64_t pair_table_grown = 0;
+  // the fragment count announced before the commits (option "n_fragments"): the commit then ranks every kept tuple inside
+  // its fragment while it writes it, and the graph stage skips its own ranking pass over the tuples
+  int64_t n_frag_hint = 0; bool ranks_valid = false; bool graph_ranked_in_commit = false;
   int window_agg = 1;               // 1: shared-memory window kernels for the per-variant counters, 0: warp-aggregated global atomics
   int64_t frag_run_limit = 1024; int64_t n_runs_resorted = 0; bool full_sort_fallback = false;
   // ------------------------------------------------------------------ blocks
@@ -687,7 +690,7 @@ struct Pipeline {
     fb_tot.bind(b); fb_cnt.bind(b); fb_bcnt.bind(b);
     rl_flag.bind(b); rl_scan.bind(b); rl_k32.bind(b); rl_k32b.bind(b); rl_t.bind(b); rl_t2.bind(b); rl_k64.bind(b);
     rl_k64b.bind(b); rl_frag.bind(b); rl_var.bind(b); rl_row.bind(b);
-    f_cnt.bind(b); f_off.bind(b); t_rank.bind(b); f_info.bind(b); f_key.bind(b); pt_keys.bind(b); pt_cnt3.bind(b); pt_vals.bind(b);
+    f_cnt.bind(b); f_off.bind(b); t_rank.bind(b); rank_flag.bind(b); f_info.bind(b); f_key.bind(b); pt_keys.bind(b); pt_cnt3.bind(b); pt_vals.bind(b);
     pt_flags.bind(b); pt_slot.bind(b);
   }
 
@@ -706,7 +709,7 @@ struct Pipeline {
     u32* vc = vcontig.ensure(V);
     const int64_t* off = d_cvoff.p; int n = nc;
     be.for_each(V, PHZ_LAMBDA(int64_t v) { vc[v] = (u32)upper_slot_i64(off, n, v); });
-    n_tuples = 0; n_bams = 0; n_cand = 0;
+    n_tuples = 0; n_bams = 0; n_cand = 0; ranks_valid = false;
   }
 
   // =================================================================== K1
@@ -960,6 +963,15 @@ struct Pipeline {
     u32* gf = g_frag.grow(n_tuples + nk, n_tuples); u32* gv = g_var.grow(n_tuples + nk, n_tuples);
     u8* gc = g_cb.grow(n_tuples + nk, n_tuples);
     int64_t base = n_tuples;
+    // rank inside the fragment (what the graph stage's counting sort needs), taken while the tuple is written
+    const bool rank_here = n_frag_hint > 0 && (bam == 0 || ranks_valid);
+    u32* fcn = nullptr; uint16_t* rk = nullptr; u32* rf = nullptr;
+    const int64_t F = n_frag_hint;
+    if (rank_here) {
+      fcn = f_cnt.ensure(F + 1); rk = t_rank.grow(n_tuples + nk, n_tuples); rf = rank_flag.ensure(2);
+      if (bam == 0) { be.memset0(fcn, (F + 1) * sizeof(u32)); be.memset0(rf, 2 * sizeof(u32)); }
+    }
+    ranks_valid = rank_here;
     be.for_each_warp(nt, PHZ_LAMBDA_WARP(int64_t t, int lane, int nlanes) {
       u32 n = tc[t]; u32 src = tb[t]; int64_t o = base + ko[t];
       for (u32 i0 = 0; i0 < n; i0 += (u32)nlanes) {
@@ -968,7 +980,14 @@ struct Pipeline {
         u32 b = warp_ballot(keep);
         if (keep) {
           int64_t w = o + popc_u32(b & ((1u << lane) - 1u));
-          gf[w] = frag[sr[src + i]]; gv[w] = sv[src + i]; gc[w] = (u8)(misc_cls(m) | (bam << 2));
+          const u32 f = frag[sr[src + i]];
+          gf[w] = f; gv[w] = sv[src + i]; gc[w] = (u8)(misc_cls(m) | (bam << 2));
+          if (rank_here) {
+            if ((int64_t)f < F) {
+              const u32 r = atomic_add(&fcn[f], 1u);
+              if (r >= 65535u) { atomic_or(&rf[0], 8u); rk[w] = 65535; } else rk[w] = (uint16_t)r;
+            } else { atomic_or(&rf[0], 16u); rk[w] = 65535; }         // id beyond the announced count: sort-based graph stage
+          }
         }
         o += popc_u32(b);
       }
@@ -1100,14 +1119,24 @@ struct Pipeline {
     const u32* gf = g_frag.p; const u32* gv = g_var.p; const u8* gc = g_cb.p; const u32* vc = vcontig.p;
     be.stage("graph.frag_rank");
     u32* sc = scalars.ensure(8); be.memset0(sc, 8 * sizeof(u32));
-    u32* fc = f_cnt.ensure(F + 1); be.memset0(fc, (F + 1) * sizeof(u32));
+    // rank of every tuple inside its fragment (arrival order: the per-fragment sort below makes the result canonical);
+    // already taken by the commits when the fragment count was announced to them
+    const bool ranked = ranks_valid && n_frag_hint == F && n > 0;
+    ranks_valid = false;                  // the fragment kernel reuses the count array: a second call ranks again
+    graph_ranked_in_commit = ranked;
+    u32* fc = f_cnt.ensure(F + 1);
     u32* fo = f_off.ensure(F + 2);
-    uint16_t* rk = t_rank.ensure(n);
-    // rank of every tuple inside its fragment (arrival order: the per-fragment sort below makes the result canonical)
-    be.for_each(n, PHZ_LAMBDA(int64_t t) {
-      const u32 r = atomic_add(&fc[gf[t]], 1u);
-      if (r >= 65535u) { atomic_or(&sc[1], 8u); rk[t] = 65535; } else rk[t] = (uint16_t)r;
-    });
+    uint16_t* rk = ranked ? t_rank.p : t_rank.ensure(n);
+    if (ranked) {
+      const u32* rf = rank_flag.p;
+      be.for_each(1, PHZ_LAMBDA(int64_t) { if (rf[0]) sc[1] |= 8u; });
+    } else {
+      be.memset0(fc, (F + 1) * sizeof(u32));
+      be.for_each(n, PHZ_LAMBDA(int64_t t) {
+        const u32 r = atomic_add(&fc[gf[t]], 1u);
+        if (r >= 65535u) { atomic_or(&sc[1], 8u); rk[t] = 65535; } else rk[t] = (uint16_t)r;
+      });
+    }
     be.exclusive_scan_u32(fc, fo, F);
     u64* fk = f_key.ensure(n); uint16_t* fi = f_info.ensure(n);
     u32* sz = setsize.ensure(Vn * 3); u32* vbc = vb_cnt.ensure(Vn * nb * 2); u64* vr = vrank.ensure(Vn);
@@ -1213,7 +1242,9 @@ struct Pipeline {
   void build_graph(u64 n_frag, u64 excl_mask) {
     if (!stats_done) { u64 tmp[2]; variant_stats(tmp); }
     stats_done = false;
+    graph_ranked_in_commit = false;
     if (graph_mode == 1 && build_graph_frag(n_frag, excl_mask)) return;
+    ranks_valid = false;
     frag_entries = false;
     const int64_t n = n_tuples; const int64_t Vn = V; const int nb = n_bams > 0 ? n_bams : 1;
     const u32* gf = g_frag.p; const u32* gv = g_var.p; const u8* gc = g_cb.p; const u32* vc = vcontig.p;

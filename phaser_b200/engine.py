@@ -66,7 +66,7 @@ class phz_ae_input(ctypes.Structure):
 EXPORTS = ["phz_last_error", "phz_backend_name", "phz_create", "phz_destroy", "phz_sync", "phz_set_variants",
            "phz_map_reads", "phz_map_reads_host", "phz_as_histogram", "phz_commit_bam", "phz_variant_stats", "phz_build_graph",
            "phz_phase", "phz_read_lists", "phz_array", "phz_download", "phz_download_async", "phz_counters", "phz_launch_counts",
-           "phz_set_profiling", "phz_map_times", "phz_stage_report", "phz_set_option",
+           "phz_set_profiling", "phz_map_times", "phz_stage_report", "phz_set_option", "phz_get_option",
            "phz_fragdict_create", "phz_fragdict_destroy", "phz_fragdict_size", "phz_fragdict_name", "phz_read_alignments",
            "phz_host_reads_view", "phz_host_reads_free", "phz_set_haplo_blacklist", "phz_write_sam",
            "phz_set_indel_alleles", "phz_pack_reads", "phz_packed_view", "phz_packed_bytes", "phz_packed_free",
@@ -116,6 +116,7 @@ def _declare(lib):
     lib.phz_map_times.argtypes = [c_void_p, POINTER(ctypes.c_float)]
     lib.phz_stage_report.argtypes = [c_void_p, c_char_p, c_int64]
     lib.phz_set_option.argtypes = [c_void_p, c_char_p, c_int64]
+    lib.phz_get_option.argtypes = [c_void_p, c_char_p, POINTER(c_int64)]
     lib.phz_fragdict_create.restype = c_void_p
     lib.phz_fragdict_destroy.argtypes = [c_void_p]
     lib.phz_fragdict_size.restype = c_int64
@@ -604,6 +605,11 @@ class Engine:
 
     def set_option(self, name, value):
         self._check(self.lib.phz_set_option(self.ctx, name.encode(), int(value)))
+
+    def get_option(self, name):
+        v = c_int64()
+        self._check(self.lib.phz_get_option(self.ctx, name.encode(), byref(v)))
+        return int(v.value)
 
     def stage_report(self):
         """{stage: ms} accumulated since the last call (CUDA events; needs set_profiling(True))."""

@@ -218,6 +218,7 @@ def run_path(engine: Engine, vt: VariantTable, batches, params: PhaseParams, n_f
     isz = list(params.isize) * nb if len(params.isize) == 1 else list(params.isize)
     excl = params.exclude_mask()
     engine.set_variants(vt)
+    engine.set_option("n_fragments", int(n_fragments))      # lets the commits rank the tuples inside their fragments
     cutoffs, kept, cands = [], [], []
     for b, reads in enumerate(batches):
         if isinstance(reads, PackedReads):          # packed transport form in host memory

@@ -43,6 +43,7 @@ class DistComm:
     def __init__(self, device, timers=None):
         self.rank = dist.get_rank(); self.world_size = dist.get_world_size(); self.device = torch.device(device)
         self.timers = timers
+        self._side = None
 
     def _sync(self):
         if self.device.type == "cuda":
@@ -63,6 +64,17 @@ class DistComm:
         return t
 
     def allreduce_sum_ints(self, xs):
+        import threading
+        if self.device.type == "cuda" and threading.current_thread() is not threading.main_thread():
+            # called from the critical-value thread while the main thread queues the graph stage: a stream of its own, so
+            # the exchange is ordered after nothing but its own upload (on the engine's stream it would queue behind
+            # every graph kernel launched so far and the thread would wait for all of them)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            with torch.cuda.stream(self._side):
+                t = torch.tensor(list(xs), dtype=torch.int64, device=self.device)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                return [int(x) for x in t.cpu().tolist()]
         t = torch.tensor(list(xs), dtype=torch.int64, device=self.device)
         self._timed("allreduce_noise_ms", lambda: dist.all_reduce(t, op=dist.ReduceOp.SUM))
         return [int(x) for x in t.cpu().tolist()]

@@ -286,6 +286,8 @@ def test_fragment_table_graph_equals_the_sort_based_graph(hostsim, tmp_path):
         hostsim.set_option("graph_mode", mode); hostsim.set_option("pair_table_slots", slots)
         try:
             out.append(pipeline.run_path(hostsim, vt, [hostsim.upload_reads(b) for b in batches], P, n_fragments=len(fd.names)))
+            # the three commits ranked the tuples inside their fragments; the graph stage did not have to
+            assert hostsim.get_option("graph_ranked_in_commit") == (1 if mode == 1 else 0)
         finally:
             hostsim.set_option("graph_mode", 1); hostsim.set_option("pair_table_slots", 1 << 20)
     a, b, c = out
@@ -298,6 +300,36 @@ def test_fragment_table_graph_equals_the_sort_based_graph(hostsim, tmp_path):
             assert np.array_equal(a.arrays[k], x.arrays[k]), k
 
 
+def test_ranks_taken_by_the_commits_equal_ranks_taken_by_the_graph_stage(hostsim, tmp_path):
+    """With the fragment count announced (option "n_fragments") every commit ranks its tuples inside their fragments while it
+    writes them, and the graph stage skips its ranking pass; without it the graph stage ranks.  Same graph either way, also
+    when the announced count is not the one the graph stage is then given (the stage ranks itself)."""
+    vcf, sams = util.make_case(tmp_path, 54, 400, 6000, n_bams=2, switch_per_base=0.02)
+    vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+    nf = len(fd.names)
+    out = []
+    for announced, expect in ((nf, 1), (0, 0), (nf // 2, 0)):
+        hostsim.set_variants(vt); hostsim.set_option("n_fragments", announced)
+        for bi, rb in enumerate(batches):
+            hostsim.map_reads(hostsim.upload_reads(rb), 10, 0.0); hostsim.commit_bam(bi, None)
+        hostsim.variant_stats()
+        hostsim.build_graph(nf, 0)
+        assert hostsim.get_option("graph_ranked_in_commit") == expect
+        out.append((hostsim.counters(), {k: hostsim.download(k).copy() for k in ("ed_a", "ed_b", "ed_sup", "ed_tot", "ed_cfg", "setsize", "vb_cnt")}))
+        # asking again on the same commits ranks afresh (the fragment kernel reused the count array)
+        hostsim.build_graph(nf, 0)
+        assert hostsim.get_option("graph_ranked_in_commit") == 0
+        again = {k: hostsim.download(k).copy() for k in out[-1][1]}
+        for k in again:
+            assert np.array_equal(again[k], out[-1][1][k]), k
+    assert out[0][0]["edges"] > 50 and out[0][0]["full_sort_fallback"] == 0
+    for c, a in out[1:]:
+        for k in ("n_tuples", "entries", "groups", "pairs", "distinct_pairs", "edges"):
+            assert c[k] == out[0][0][k], k
+        for k in a:
+            assert np.array_equal(a[k], out[0][1][k]), k
+
+
 def test_a_huge_fragment_takes_the_sort_based_graph(hostsim, tmp_path):
     """More than 65535 tuples under ONE read name do not fit the 16-bit in-fragment rank: the stage falls back to the
     sort-based graph (full-key sort), loudly in the counters, with the same arrays as asking for that stage outright."""
@@ -307,10 +339,10 @@ def test_a_huge_fragment_takes_the_sort_based_graph(hostsim, tmp_path):
     batches[0].frag = np.zeros_like(batches[0].frag)
     P = pipeline.PhaseParams(max_block_size=0)
     out = []
-    for mode in (1, 0):
+    for mode, announced in ((1, 1), (1, 0), (0, 0)):      # ranks taken by the commit / by the graph stage / not at all
         hostsim.set_option("graph_mode", mode)
         try:
-            hostsim.set_variants(vt)
+            hostsim.set_variants(vt); hostsim.set_option("n_fragments", announced)
             for bi, rb in enumerate(batches):
                 hostsim.map_reads(hostsim.upload_reads(rb), 10, 0.0); hostsim.commit_bam(bi, None)
             hostsim.variant_stats()
@@ -318,8 +350,8 @@ def test_a_huge_fragment_takes_the_sort_based_graph(hostsim, tmp_path):
             out.append((hostsim.counters(), {k: hostsim.download(k).copy() for k in ("ed_a", "ed_b", "ed_sup", "ed_tot", "ed_cfg", "setsize", "vb_cnt")}))
         finally:
             hostsim.set_option("graph_mode", 1)
-    (ca, a), (cb, b) = out
+    (ca, a), (cc, c), (cb, b) = out
     assert ca["n_tuples"] > 65535 and ca["full_sort_fallback"] == 1 and cb["full_sort_fallback"] == 1
-    assert ca == cb
+    assert ca == cb and cc == cb
     for k in a:
-        assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a[k], b[k]) and np.array_equal(c[k], b[k]), k
