@@ -333,6 +333,12 @@ int phz_vcf_records(phz_vcf* v, int64_t* n, const int32_t** chrom, const int64_t
  * path + ".tbi" (or ".csi"); BGZF blocks deflated on n_threads threads. */
 int phz_vcf_save(phz_vcf* v, const char* path_vcf_gz, int csi, int n_threads);
 
+/* Text-side view of `n` het sites (indices into the table of the last phz_vcf_parse) for the table writers -- what
+ * generate_variant_dict keeps per variant (phaser/phaser.py:1418-1462).  One line per site, tab-separated: POS, ID, REF, ALT
+ * as in the file, the two alleles the sample's genotype names in allele-index order, the two alleles in genotype order when
+ * the genotype is phased ("-", "-" otherwise).  A site whose genotype is not two different single digits gets the line "?"
+ * (the caller reads that line itself).  The text stays valid until the next call on the same thread. */
+int phz_vcf_site_text(phz_vcf* vcf, const int64_t* sites, int64_t n, int n_threads, const char** text, int64_t* n_bytes);
 /* aReads / bReads columns of haplotypic_counts.txt (phaser.py:1105-1115) for the requested rows: rl_* are the triples of
  * phz_read_lists on the HOST (sorted by row); row r is named by row_key[r] (the packed block / BAM / haplotype key of
  * "rl_row") and prints the variants row_vars[row_var_off[r] .. row_var_off[r+1]) in that order.  Reads are numbered by

@@ -16,6 +16,8 @@
 #include <atomic>
 #include <fstream>
 #include <chrono>
+#include <cstdlib>
+#include <sys/mman.h>
 
 namespace phzio {
 
@@ -47,6 +49,21 @@ struct NoInit : std::allocator<T> {
   template <class U> NoInit(const NoInit<U>&) {}
   template <class U, class... A> void construct(U* p, A&&... a) {
     if constexpr (sizeof...(A) == 0) ::new ((void*)p) U; else ::new ((void*)p) U(std::forward<A>(a)...);
+  }
+  // big arrays (inflated BAM, the SoA columns) are first touched by many threads at once: 2 MB pages cut the number of
+  // page faults -- and the time the threads spend queueing on the address-space lock -- by 512
+  static constexpr size_t HUGE = (size_t)2 << 20;
+  T* allocate(size_t n) {
+    const size_t bytes = n * sizeof(T);
+    if (bytes < 4 * HUGE) return std::allocator<T>::allocate(n);
+    const size_t len = (bytes + HUGE - 1) / HUGE * HUGE;
+    void* p = std::aligned_alloc(HUGE, len);
+    if (!p) throw std::bad_alloc();
+    madvise(p, len, MADV_HUGEPAGE);
+    return (T*)p;
+  }
+  void deallocate(T* p, size_t n) {
+    if (n * sizeof(T) < 4 * HUGE) std::allocator<T>::deallocate(p, n); else std::free(p);
   }
 };
 typedef std::vector<u8, NoInit<u8>> Bytes;
@@ -80,6 +97,15 @@ struct FragDict {
     std::vector<u32> gid; std::vector<u64> first_rec;            // entry -> global id / first record of the current file
     size_t mask = 0;
     Shard() { name_off.push_back(0); resize(1 << 12); }
+    // room for `extra` more names (an upper bound: every record of the bucket could be a new name)
+    void reserve_for(size_t extra) {
+      const size_t want = gid.size() + extra;
+      size_t slots = mask + 1; while (slots < want * 2 + 2) slots <<= 1;
+      if (slots != mask + 1) resize(slots);
+      gid.reserve(want); first_rec.reserve(want); name_off.reserve(want + 1);
+      const size_t per = gid.empty() ? 24 : arena.size() / gid.size() + 1;
+      arena.reserve(arena.size() + extra * per / 2);
+    }
     void resize(size_t n) {
       std::vector<u64> oh(n, 0); std::vector<u32> oe(n, 0xFFFFFFFFu);
       for (size_t i = 0; i < slot_hash.size(); ++i)
@@ -110,11 +136,8 @@ struct FragDict {
   static int shard_of(u64 h) { return (int)(h >> 58); }
 
   // ids for the kept records of one file (names[i], lens[i], hashes[i] in file order) -> out[i]
-  void assign(const std::vector<const char*>& names, const std::vector<u32>& lens, const std::vector<u64>& hashes,
-              std::vector<u32>& out, int n_threads) {
-    const size_t n = names.size();
-    out.resize(n);
-    std::vector<u32> ent(n);
+  void assign(const char* const* names, const u32* lens, const u64* hashes, size_t n, u32* out, int n_threads) {
+    std::vector<u32, NoInit<u32>> ent(n);
     // 1. record indices bucketed by shard (counting sort over fixed chunks: file order is kept inside a bucket)
     const size_t CH = 1 << 16, nch = (n + CH - 1) / CH;
     std::vector<u32> cnt(nch * NS + 1, 0);
@@ -127,7 +150,7 @@ struct FragDict {
     { size_t acc = 0;
       for (int s = 0; s < NS; ++s) { sh_begin[s] = acc; for (size_t c = 0; c < nch; ++c) { start[c * NS + s] = acc; acc += cnt[c * NS + s]; } }
       sh_begin[NS] = acc; }
-    std::vector<u32> order(n);
+    std::vector<u32, NoInit<u32>> order(n);
     parallel_for(nch, n_threads, [&](size_t c) {
       size_t pos[NS];
       for (int s = 0; s < NS; ++s) pos[s] = start[c * NS + s];
@@ -137,17 +160,18 @@ struct FragDict {
     // 2. every shard looks its own records up (in file order: first_rec is the first record of a new name)
     parallel_for(NS, n_threads, [&](size_t s) {
       Shard& S = sh[s];
+      S.reserve_for(sh_begin[s + 1] - sh_begin[s]);          // no rehash / regrowth in the middle of the file
       for (size_t k = sh_begin[s]; k < sh_begin[s + 1]; ++k) { const u32 i = order[k]; ent[i] = S.find_or_add(hashes[i], names[i], lens[i], (u64)i); }
     });
     // 3. new names get ids in order of first appearance: flag the first record of every new name, scan, hand out
-    std::vector<u32> pre(n + 1, 0);
+    std::vector<u8, NoInit<u8>> pre(n + 1);
     std::vector<size_t> chunk_new(nch + 1, 0);
     parallel_for(nch, n_threads, [&](size_t c) {
       const size_t i1 = std::min(n, (c + 1) * CH); size_t k = 0;
       for (size_t i = c * CH; i < i1; ++i) {
         const Shard& S = sh[shard_of(hashes[i])]; const u32 e = ent[i];
         const bool fresh = S.gid[e] == 0xFFFFFFFFu && S.first_rec[e] == (u64)i;
-        pre[i] = fresh ? 1u : 0u; k += fresh;
+        pre[i] = fresh ? 1 : 0; k += fresh;
       }
       chunk_new[c + 1] = k;
     });
@@ -169,9 +193,9 @@ struct FragDict {
     });
   }
   u32 get(const char* s, size_t n) {      // single lookup (tests / small inputs)
-    std::vector<const char*> a{s}; std::vector<u32> l{(u32)n}; std::vector<u64> h{name_hash(s, n)}; std::vector<u32> o;
-    assign(a, l, h, o, 1);
-    return o[0];
+    const char* a = s; u32 l = (u32)n; u64 h = name_hash(s, n); u32 o = 0;
+    assign(&a, &l, &h, 1, &o, 1);
+    return o;
   }
 };
 
@@ -179,7 +203,7 @@ struct HostReads {
   int n_contigs = 0;
   std::vector<int64_t> contig_rec_off;
   std::vector<int32_t, NoInit<int32_t>> pos, tlen; std::vector<int16_t, NoInit<int16_t>> aln; std::vector<u32, NoInit<u32>> frag, cigar;
-  std::vector<u32> cigar_off; std::vector<u64> seq_off; std::vector<u8> seq; Bytes qual;
+  std::vector<u32, NoInit<u32>> cigar_off; std::vector<u64, NoInit<u64>> seq_off; Bytes seq; Bytes qual;
   int sorted = 1;
   std::string error;
 };
@@ -388,13 +412,17 @@ static int16_t as_from_aux(const u8* p, const u8* end, std::string& err) {
 template <class RV>
 static void assign_fragments(RV& recs, FragDict* fd, int n_threads) {
   size_t n = recs.size();
-  std::vector<const char*> names(n); std::vector<u32> lens(n); std::vector<u64> hashes(n); std::vector<u32> ids;
+  std::vector<const char*, NoInit<const char*>> names(n); std::vector<u32, NoInit<u32>> lens(n), ids(n);
+  std::vector<u64, NoInit<u64>> hashes(n);
   parallel_for((n + 65535) / 65536, n_threads, [&](size_t c) {
     size_t i1 = std::min(n, (c + 1) * 65536);
     for (size_t i = c * 65536; i < i1; ++i) { names[i] = recs[i].qname; lens[i] = recs[i].l_qname; hashes[i] = name_hash(recs[i].qname, recs[i].l_qname); }
   });
-  fd->assign(names, lens, hashes, ids, n_threads);
-  for (size_t i = 0; i < n; ++i) recs[i].frag = ids[i];
+  fd->assign(names.data(), lens.data(), hashes.data(), n, ids.data(), n_threads);
+  parallel_for((n + 65535) / 65536, n_threads, [&](size_t c) {
+    size_t i1 = std::min(n, (c + 1) * 65536);
+    for (size_t i = c * 65536; i < i1; ++i) recs[i].frag = ids[i];
+  });
 }
 
 static u32 count_cigar_ops(const Rec& r) {
@@ -410,26 +438,54 @@ static HostReads* build(RV& recs, int nc, int n_threads) {
   HostReads* H = new HostReads();
   H->n_contigs = nc;
   size_t R = recs.size();
-  std::vector<int64_t> cnt(nc + 1, 0);
-  for (auto& r : recs) cnt[r.contig + 1]++;
-  H->contig_rec_off.assign(nc + 1, 0);
-  for (int c = 0; c < nc; ++c) H->contig_rec_off[c + 1] = H->contig_rec_off[c] + cnt[c + 1];
-  std::vector<int64_t> cur(H->contig_rec_off.begin(), H->contig_rec_off.end() - 1);
-  std::vector<u32> order(R);
-  for (size_t i = 0; i < R; ++i) order[cur[recs[i].contig]++] = (u32)i;      // stable: file order inside a contig
-  H->pos.resize(R); H->tlen.resize(R); H->aln.resize(R); H->frag.resize(R);
-  H->cigar_off.assign(R + 1, 0); H->seq_off.assign(R + 1, 0);
   const size_t CH = 16384, n_chunks = (R + CH - 1) / CH;
-  // sizes: per-record counts in parallel, running sums serially
+  // records grouped by contig (VCF order), file order kept inside a contig: a counting sort over fixed chunks
+  std::vector<int64_t> ccnt(n_chunks * (size_t)nc + 1, 0);
   parallel_for(n_chunks, n_threads, [&](size_t c) {
-    size_t k1 = std::min(R, (c + 1) * CH);
-    for (size_t k = c * CH; k < k1; ++k) { const Rec& r = recs[order[k]]; H->cigar_off[k + 1] = count_cigar_ops(r); H->seq_off[k + 1] = r.l_seq; }
+    int64_t* k = ccnt.data() + c * nc;
+    const size_t i1 = std::min(R, (c + 1) * CH);
+    for (size_t i = c * CH; i < i1; ++i) k[recs[i].contig]++;
   });
-  for (size_t k = 0; k < R; ++k) { H->cigar_off[k + 1] += H->cigar_off[k]; H->seq_off[k + 1] += H->seq_off[k]; }
-  if (R && (u64)H->cigar_off[R] < (u64)H->cigar_off[R - 1]) throw PhzError("more than 2^32 CIGAR operations in one file");
+  H->contig_rec_off.assign(nc + 1, 0);
+  { int64_t acc = 0;
+    for (int ci = 0; ci < nc; ++ci) {
+      H->contig_rec_off[ci] = acc;
+      for (size_t c = 0; c < n_chunks; ++c) { const int64_t k = ccnt[c * nc + ci]; ccnt[c * nc + ci] = acc; acc += k; }
+    }
+    H->contig_rec_off[nc] = acc; }
+  std::vector<u32, NoInit<u32>> order(R);
+  parallel_for(n_chunks, n_threads, [&](size_t c) {
+    int64_t* at = ccnt.data() + c * nc;
+    const size_t i1 = std::min(R, (c + 1) * CH);
+    for (size_t i = c * CH; i < i1; ++i) order[at[recs[i].contig]++] = (u32)i;
+  });
+  H->pos.resize(R); H->tlen.resize(R); H->aln.resize(R); H->frag.resize(R);
+  H->cigar_off.resize(R + 1); H->seq_off.resize(R + 1);
+  H->cigar_off[0] = 0; H->seq_off[0] = 0;
+  // sizes: per-record counts and per-chunk sums in parallel, the running sum over the chunks serially, then every chunk
+  // adds its base
+  std::vector<u64> csum(n_chunks + 1, 0), ssum(n_chunks + 1, 0);
+  parallel_for(n_chunks, n_threads, [&](size_t c) {
+    size_t k1 = std::min(R, (c + 1) * CH); u64 a = 0, b = 0;
+    for (size_t k = c * CH; k < k1; ++k) {
+      const Rec& r = recs[order[k]];
+      a += count_cigar_ops(r); b += r.l_seq;
+      H->cigar_off[k + 1] = (u32)a; H->seq_off[k + 1] = b;
+    }
+    csum[c + 1] = a; ssum[c + 1] = b;
+  });
+  for (size_t c = 0; c < n_chunks; ++c) { csum[c + 1] += csum[c]; ssum[c + 1] += ssum[c]; }
+  if (csum[n_chunks] >= 0xFFFFFFFFull) throw PhzError("more than 2^32 CIGAR operations in one file");
+  parallel_for(n_chunks, n_threads, [&](size_t c) {
+    if (c == 0) return;
+    size_t k1 = std::min(R, (c + 1) * CH); const u32 a = (u32)csum[c]; const u64 b = ssum[c];
+    for (size_t k = c * CH; k < k1; ++k) { H->cigar_off[k + 1] += a; H->seq_off[k + 1] += b; }
+  });
   H->cigar.resize(H->cigar_off[R]);
   u64 nb = H->seq_off[R];
-  H->qual.resize(nb); H->seq.assign((nb + 1) / 2, 0);
+  H->qual.resize(nb); H->seq.resize((nb + 1) / 2);
+  { const size_t ZB = (size_t)1 << 22, nz = (H->seq.size() + ZB - 1) / ZB;      // zeroed by all threads (first touch as well)
+    parallel_for(nz, n_threads, [&](size_t z) { std::memset(H->seq.data() + z * ZB, 0, std::min(ZB, H->seq.size() - z * ZB)); }); }
   static const char* OPS = "MIDNSHP=X";
   parallel_for(n_chunks, n_threads, [&](size_t c) {
     size_t k1 = std::min(R, (c + 1) * CH);
@@ -464,9 +520,17 @@ static HostReads* build(RV& recs, int nc, int n_threads) {
       else std::memcpy(qo, r.qual, L);
     }
   });
-  for (int c = 0; c < nc; ++c)
-    for (int64_t k = H->contig_rec_off[c] + 1; k < H->contig_rec_off[c + 1]; ++k)
-      if (H->pos[k] < H->pos[k - 1]) { H->sorted = 0; break; }
+  std::atomic<int> unsorted{0};
+  parallel_for(n_chunks, n_threads, [&](size_t c) {
+    if (unsorted.load(std::memory_order_relaxed)) return;
+    const size_t k0 = c * CH, k1 = std::min(R, (c + 1) * CH);
+    int ci = (int)(std::upper_bound(H->contig_rec_off.begin(), H->contig_rec_off.end(), (int64_t)k0) - H->contig_rec_off.begin()) - 1;
+    for (size_t k = k0; k < k1; ++k) {
+      while (ci + 1 <= nc && (int64_t)k >= H->contig_rec_off[ci + 1]) ++ci;
+      if ((int64_t)k > H->contig_rec_off[ci] && H->pos[k] < H->pos[k - 1]) { unsorted = 1; return; }
+    }
+  });
+  if (unsorted) H->sorted = 0;
   return H;
 }
 
@@ -674,14 +738,14 @@ int phz_fragdict_export(phz_fragdict* d, char* blob, int64_t* off) {
 int phz_fragdict_import(phz_fragdict* d, const char* blob, const int64_t* off, int64_t n, int n_threads) {
   PHZ_TRY
   if (d->d.count != 0) throw PhzError("phz_fragdict_import: the dictionary must be empty");
-  std::vector<const char*> names((size_t)n); std::vector<u32> lens((size_t)n); std::vector<u64> hashes((size_t)n); std::vector<u32> ids;
+  std::vector<const char*> names((size_t)n); std::vector<u32> lens((size_t)n); std::vector<u64> hashes((size_t)n); std::vector<u32> ids((size_t)n);
   phzio::parallel_for((size_t)((n + 65535) / 65536), n_threads, [&](size_t c) {
     const int64_t i1 = std::min<int64_t>(n, (int64_t)(c + 1) * 65536);
     for (int64_t i = (int64_t)c * 65536; i < i1; ++i) {
       names[i] = blob + off[i]; lens[i] = (u32)(off[i + 1] - off[i]); hashes[i] = phzio::name_hash(names[i], lens[i]);
     }
   });
-  d->d.assign(names, lens, hashes, ids, n_threads);
+  d->d.assign(names.data(), lens.data(), hashes.data(), (size_t)n, ids.data(), n_threads);
   for (int64_t i = 0; i < n; ++i) if (ids[i] != (u32)i) throw PhzError("phz_fragdict_import: duplicate names in the cache");
   PHZ_CATCH
 }

@@ -722,6 +722,68 @@ int phz_vcf_save(phz_vcf* h, const char* path_vcf_gz, int csi, int n_threads) {
 // what the only consumer needs (ids are opaque per row).  Input: the read-list triples of phz_read_lists (sorted by row,
 // then variant rank, then tuple order); for every requested row its key and the variants to print, in order.  Output: one
 // string per row, variants ';'-joined, indices ','-joined (a variant without reads in the row gives an empty field).
+static thread_local std::string g_site_text;
+
+// Text-side view of the requested het sites for the table writers (what generate_variant_dict keeps per variant,
+// phaser.py:1418-1462), one line per site: POS, ID, REF, ALT as in the file, then the two alleles the genotype names in
+// allele-index order, then the two alleles in genotype order when the genotype is phased ("-" twice otherwise).
+// A site whose genotype is not two single digits gets the line "?" and is left to the caller's general reading.
+int phz_vcf_site_text(phz_vcf* h, const int64_t* sites, int64_t n, int n_threads, const char** text, int64_t* n_bytes) {
+  PHZ_TRY
+  using namespace phzvcf;
+  Vcf& v = h->v;
+  if (v.sample_column < 0) throw PhzError("phz_vcf_site_text: phz_vcf_parse first");
+  const int64_t V = (int64_t)v.pos.size();
+  const size_t CH = 4096, nch = ((size_t)n + CH - 1) / CH;
+  std::vector<std::string> parts(nch);
+  std::atomic<int> bad{0};
+  const char* base = (const char*)v.text.data();
+  const int sc = v.sample_column;
+  const int64_t* voff = v.var_off.data(); const int32_t* vlen = v.var_len.data();
+  phzio::parallel_for(nch, n_threads, [&](size_t c) {
+    std::string& o = parts[c];
+    const size_t i1 = std::min((size_t)n, (c + 1) * CH);
+    o.reserve((i1 - c * CH) * 40);
+    for (size_t i = c * CH; i < i1; ++i) {
+      const int64_t s = sites[i];
+      if (s < 0 || s >= V) { bad = 1; return; }
+      const char* lp = base + voff[s]; const char* le = lp + vlen[s];
+      while (le > lp && (le[-1] == '\n' || le[-1] == '\r')) --le;
+      Cut cut; bool ok = cut_line(lp, le, sc, cut);
+      Span g{nullptr, 0}; int gi = ok ? colon_index(cut.c[8], "GT") : -1;
+      ok = ok && gi >= 0 && colon_field(cut.c[9], gi, g);
+      Geno q; if (ok) q = read_geno(g);
+      ok = ok && !q.dot && !q.overflow && q.n == 2 && q.ch[0] >= '0' && q.ch[0] <= '9' && q.ch[1] >= '0' && q.ch[1] <= '9' &&
+           q.ch[0] != q.ch[1];
+      Span al[10]; int na = 0;
+      if (ok) {
+        al[na++] = cut.c[3];
+        const char* st = cut.c[4].p; const char* e = st + cut.c[4].n;
+        for (const char* t = st;; ++t)
+          if (t == e || *t == ',') { if (na < 10) al[na] = Span{st, (size_t)(t - st)}; ++na; st = t + 1; if (t == e) break; }
+        const int d0 = q.ch[0] - '0', d1 = q.ch[1] - '0';
+        if (na > 10 || d0 >= na || d1 >= na) ok = false;      // an 11th allele would be named "10": not this simple reading
+      }
+      if (!ok) { o += "?\n"; continue; }
+      const int d0 = q.ch[0] - '0', d1 = q.ch[1] - '0';
+      const int lo = d0 < d1 ? d0 : d1, hi = d0 < d1 ? d1 : d0;
+      bool phased = false;
+      for (size_t t = 0; t < g.n; ++t) if (g.p[t] == '|') phased = true;
+      auto add = [&](Span x) { o.append(x.p, x.n); o.push_back('\t'); };
+      add(cut.c[1]); add(cut.c[2]); add(cut.c[3]); add(cut.c[4]); add(al[lo]); add(al[hi]);
+      if (phased) { add(al[d0]); o.append(al[d1].p, al[d1].n); } else o += "-\t-";
+      o.push_back('\n');
+    }
+  });
+  if (bad) throw PhzError("phz_vcf_site_text: site index out of range");
+  g_site_text.clear();
+  size_t tot = 0; for (auto& x : parts) tot += x.size();
+  g_site_text.reserve(tot);
+  for (auto& x : parts) g_site_text += x;
+  *text = g_site_text.data(); *n_bytes = (int64_t)g_site_text.size();
+  PHZ_CATCH
+}
+
 static thread_local std::string g_rl_text;
 static thread_local std::vector<int64_t> g_rl_off;
 

@@ -72,7 +72,7 @@ EXPORTS = ["phz_last_error", "phz_backend_name", "phz_create", "phz_destroy", "p
            "phz_set_indel_alleles", "phz_pack_reads", "phz_packed_view", "phz_packed_bytes", "phz_packed_free",
            "phz_map_reads_packed", "phz_prefetch_packed", "phz_gene_ae_pairs", "phz_set_big_critical_values",
            "phz_copy_array", "phz_vcf_open", "phz_vcf_close", "phz_vcf_text", "phz_vcf_chrom_line", "phz_vcf_parse",
-           "phz_vcf_write", "phz_vcf_records", "phz_write_bam", "phz_vcf_save", "phz_format_read_lists", "phz_upload", "phz_sync_count",
+           "phz_vcf_write", "phz_vcf_records", "phz_write_bam", "phz_vcf_save", "phz_format_read_lists", "phz_vcf_site_text", "phz_upload", "phz_sync_count",
            "phz_fragdict_blob_bytes", "phz_fragdict_export", "phz_fragdict_import"]
 
 
@@ -108,6 +108,7 @@ def _declare(lib):
     lib.phz_vcf_save.argtypes = [c_void_p, c_char_p, c_int, c_int]
     lib.phz_upload.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int]
     lib.phz_sync_count.argtypes = [c_void_p, POINTER(c_uint64)]
+    lib.phz_vcf_site_text.argtypes = [c_void_p, c_void_p, c_int64, c_int, POINTER(c_char_p), POINTER(c_int64)]
     lib.phz_format_read_lists.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int,
                                           POINTER(c_void_p), POINTER(c_void_p)]
     lib.phz_counters.argtypes = [c_void_p, POINTER(c_int64)]

@@ -285,6 +285,7 @@ def run(args, engine=None):
     out = writer.Outputs(res, vt, bam_names, P, unphased_vars=args.unphased_vars, gw_phase_method=args.gw_phase_method,
                          unique_ids=args.unique_ids, read_names=fd.names if args.output_read_ids == 1 else None,
                          output_network=args.output_network, lib=engine.lib, threads=max(1, args.threads))
+    out.prefetch_meta()
     with open(args.o + ".variant_connections.txt", "w") as f:
         f.write(out.variant_connections())
     say("     %d variant connections dropped because of conflicting configurations (threshold = %f)" % (

@@ -282,6 +282,25 @@ class _LazyRows:
         self.col = sample_column; self.sep = id_separator; self.gwm = gw_phase_method; self.af = gw_af_field
         self.n = int(line_off.shape[0])
         self.cache = {}
+        self.site_rows = {}        # v -> "POS\tID\tREF\tALT\tallele\tallele\tphase\tphase" (prefetch_sites)
+
+    def prefetch_sites(self, sites):
+        """One native call (phz_vcf_site_text, all host threads) for the text-side view of `sites`; the table writers then
+        build their per-variant records from one split each instead of re-reading the VCF line in Python."""
+        import ctypes
+        if self.gwm == 1 or not hasattr(self.nv.lib, "phz_vcf_site_text"):
+            return                  # the allele-frequency reading stays with get()
+        idx = np.ascontiguousarray(np.asarray(sites, np.int64))
+        idx = idx[~np.isin(idx, np.fromiter(self.site_rows.keys(), np.int64, len(self.site_rows)))] if self.site_rows else idx
+        if idx.shape[0] == 0:
+            return
+        text = ctypes.c_void_p(); nb = ctypes.c_int64(0)
+        rc = self.nv.lib.phz_vcf_site_text(self.nv.h, idx.ctypes.data, int(idx.shape[0]), self.nv.threads,
+                                           ctypes.cast(ctypes.byref(text), ctypes.POINTER(ctypes.c_char_p)), ctypes.byref(nb))
+        if rc != 0:
+            raise PhaserFatal(self.nv.lib.phz_last_error().decode())
+        rows = ctypes.string_at(text.value, nb.value).decode().split("\n")
+        self.site_rows.update(zip(idx.tolist(), rows))
 
     def get(self, v):
         r = self.cache.get(v)

@@ -49,6 +49,24 @@ class VariantMeta:
         self.chrom = chrom
         self.pos = int(vt.pos[v])
 
+    @classmethod
+    def from_site_text(cls, row, chrom, sep, pos):
+        """the same record from one line of phz_vcf_site_text (POS, ID, REF, ALT, the genotype's two alleles in index
+        order, the two alleles in genotype order or "-" twice); None when the native reader left the site alone ("?")"""
+        f = row.split("\t")
+        if len(f) != 8:
+            return None
+        m = cls.__new__(cls)
+        m.id = chrom + sep + f[0] + sep + f[2] + sep + (f[3].replace(",", sep) if "," in f[3] else f[3])
+        m.rsid = f[1] if f[1] not in (".", "") else m.id
+        m.ref = f[2]
+        m.alleles = [f[4], f[5]]
+        m.phase = [f[6], f[7]]
+        m.maf = 0                     # gw_phase_method 0: no allele frequency is read (float("None") -> 0 in __init__)
+        m.chrom = chrom
+        m.pos = pos
+        return m
+
 
 class Outputs:
     def __init__(self, res: PhaseResult, vt, bam_names, params, unphased_vars=1, gw_phase_method=0, unique_ids=0,
@@ -62,6 +80,7 @@ class Outputs:
         self.read_names = read_names
         self.unphased_vars = unphased_vars; self.gw_phase_method = gw_phase_method; self.unique_ids = unique_ids
         self._meta = {}
+        self._site_rows = None; self._site_sep = "_"
         self.contig_of = np.zeros(vt.n_variants, np.int64)
         for c in range(len(vt.contigs)):
             self.contig_of[int(vt.contig_var_off[c]):int(vt.contig_var_off[c + 1])] = c
@@ -74,9 +93,29 @@ class Outputs:
     def meta(self, v) -> VariantMeta:
         m = self._meta.get(v)
         if m is None:
-            m = VariantMeta(self.vt, v, self.vt.contigs[self.contig_of[v]])
+            chrom = self.vt.contigs[self.contig_of[v]]
+            row = self._site_rows.get(v) if self._site_rows is not None else None
+            if row is not None:
+                m = VariantMeta.from_site_text(row, chrom, self._site_sep, int(self.vt.pos[v]))
+            if m is None:
+                m = VariantMeta(self.vt, v, chrom)
             self._meta[v] = m
         return m
+
+    def prefetch_meta(self):
+        """Every variant the tables will name (edge ends, block members, covered sites), read from the VCF text in one
+        native call when the variant table is the native one."""
+        rows = getattr(getattr(self.vt.ids, "o", None), "prefetch_sites", None)
+        if rows is None:
+            return
+        r = self.res; owner = self.vt.ids.o
+        sz = r.setsize.reshape(-1, 3)
+        need = [np.asarray(r.ed_a, np.int64), np.asarray(r.ed_b, np.int64), np.nonzero(sz[:, 0] + sz[:, 1] > 0)[0].astype(np.int64)]
+        if "members" in r.arrays:
+            mem = np.asarray(r.members, np.int64)
+            need.append(mem[(mem >= 0) & (mem < self.vt.n_variants)])
+        owner.prefetch_sites(np.unique(np.concatenate(need)))
+        self._site_rows = owner.site_rows; self._site_sep = owner.sep
 
     # ------------------------------------------------------------------ simple tables
     def first_seen_order(self):
@@ -102,16 +141,19 @@ class Outputs:
         r = self.res
         out = ["variant_a\tvariant_b\tsupporting_connections\ttotal_connections\tconflicting_configuration_p\tphase_concordant\n"]
         pv = edge_pvalues(r.ed_sup, r.ed_tot, r.noise_e)
-        for e in range(r.ed_a.shape[0]):
-            a = int(r.ed_a[e]); b = int(r.ed_b[e]); cfg = int(r.ed_cfg[e])
-            ma = self.meta(a); mb = self.meta(b)
+        meta = self.meta; add = out.append
+        # (pv: python ints 0 / 1 or numpy.float64, printed by str() as the reference prints them -- Q28)
+        for a, b, sup, tot, cfg, p in zip(r.ed_a.tolist(), r.ed_b.tolist(), r.ed_sup.tolist(), r.ed_tot.tolist(),
+                                         r.ed_cfg.tolist(), pv.tolist()):
+            ma = meta(a); mb = meta(b)
             pc = "."
-            if "-" not in ma.phase and "-" not in mb.phase:       # phaser.py:1609-1620
+            pa = ma.phase; pb = mb.phase
+            if "-" not in pa and "-" not in pb:       # phaser.py:1609-1620
                 if cfg == 0:
-                    pc = 1 if ma.phase.index(ma.alleles[0]) == mb.phase.index(mb.alleles[0]) else 0
+                    pc = 1 if pa.index(ma.alleles[0]) == pb.index(mb.alleles[0]) else 0
                 elif cfg == 1:
-                    pc = 1 if ma.phase.index(ma.alleles[1]) == mb.phase.index(mb.alleles[0]) else 0
-            out.append("\t".join(map(str, [ma.id, mb.id, int(r.ed_sup[e]), int(r.ed_tot[e]), pv[e], pc])) + "\n")
+                    pc = 1 if pa.index(ma.alleles[1]) == pb.index(mb.alleles[0]) else 0
+            add("%s\t%s\t%d\t%d\t%s\t%s\n" % (ma.id, mb.id, sup, tot, p, pc))
         return "".join(out)
 
     # ------------------------------------------------------------------ blocks
@@ -236,15 +278,22 @@ class Outputs:
         rl = {} if native_rl else self._read_list_rows()
         pending = []; req_keys = []; req_off = [0]; req_vars = []          # rows whose read columns the native formatter fills
         bb = max(1, int(np.ceil(np.log2(max(nb, 2)))))
-        fcnt = r.fb_cnt.reshape(-1, 2); fbc = r.fb_bcnt.reshape(-1, nb, 2) if r.fb_bcnt.size else r.fb_bcnt.reshape(0, nb, 2)
-        for f in range(r.fb_first.shape[0]):
+        fcnt = r.fb_cnt.reshape(-1, 2).tolist()
+        fbc = (r.fb_bcnt.reshape(-1, nb, 2) if r.fb_bcnt.size else r.fb_bcnt.reshape(0, nb, 2)).tolist()
+        fb_first = r.fb_first.tolist(); fb_len = r.fb_len.tolist(); fb_sup = r.fb_sup.tolist(); fb_tot = r.fb_tot.tolist()
+        members = r.members; v_hap = r.v_hap; meta = self.meta
+        black = getattr(self.vt, "haplo_blacklisted", None)
+        if black is not None and not np.any(black):
+            black = None                                             # nothing blacklisted: every variant is used
+        for f in range(len(fb_first)):
             block_index = f + 1
-            o = int(r.fb_first[f]); n = int(r.fb_len[f])
-            variants = r.members[o:o + n].tolist()
+            o = fb_first[f]; n = fb_len[f]
+            mem = members[o:o + n]
+            variants = mem.tolist()
             self.all_variants += variants
-            hap_a = [int(r.v_hap[v]) for v in variants]
-            ms = [self.meta(v) for v in variants]
-            sup = int(r.fb_sup[f]) * 2 / 2; tot = int(r.fb_tot[f]) * 2 / 2          # floats, phaser.py:894-895
+            hap_a = v_hap[mem].tolist()
+            ms = [meta(v) for v in variants]
+            sup = fb_sup[f] * 2 / 2; tot = fb_tot[f] * 2 / 2          # floats, phaser.py:894-895
             rsids = [m.rsid for m in ms] if self.unique_ids == 0 else [m.id for m in ms]
             positions = [m.pos for m in ms]
             alleles = [[], []]; phases = [[], []]
@@ -300,7 +349,7 @@ class Outputs:
                 g[ai] = corrected[0][i]; g[1 - ai] = corrected[1][i]
                 self.gw_phase[v] = g
             cps = ["".join("-" if x != x else str(x) for x in corrected[h]) for h in (0, 1)]
-            ca, cb = int(fcnt[f, 0]), int(fcnt[f, 1])
+            ca, cb = fcnt[f]
             hp.append("\t".join(map(str, [ms[0].chrom, min(positions), max(positions), max(positions) - min(positions),
                                           n, ",".join(rsids), ",".join(alleles[0]) + "|" + ",".join(alleles[1]),
                                           ca, cb, ca + cb, sup, tot, ps[0] + "|" + ps[1], phase_concordant,
@@ -310,13 +359,15 @@ class Outputs:
                 gwp = "0|1"
             elif corrected[0][0] == 1:
                 gwp = "1|0"
-            black = getattr(self.vt, "haplo_blacklisted", None)
-            used = [i for i, v in enumerate(variants) if black is None or not black[v]]        # phaser.py:1070
-            blacklisted = sorted(ms[i].id for i in range(n) if i not in used)
+            if black is None:
+                used = list(range(n)); blacklisted = []
+            else:
+                used = [i for i, v in enumerate(variants) if not black[v]]        # phaser.py:1070
+                blacklisted = sorted(ms[i].id for i in range(n) if i not in used)
             for b in range(nb):
                 if b in excl:
                     continue
-                a_cnt, b_cnt = int(fbc[f, b, 0]), int(fbc[f, b, 1])
+                a_cnt, b_cnt = fbc[f][b]
                 if a_cnt + b_cnt > 0:
                     cols = []; ids = []
                     for h in (0, 1):
@@ -340,11 +391,12 @@ class Outputs:
                         hc.append(head + "\t" + cols[0] + "\t" + cols[1] + "\n")
             if self.output_network != "" and self.output_network in [m.id for m in ms]:
                 self.network = self._network_tables(variants, ms, alleles[0])
+            al0 = alleles[0]; al1 = alleles[1]
             for i, ma in enumerate(ms):
+                left = ma.id + "\t" + ma.rsid + "\t"; ra = ma.ref == al0[i]
                 for j, mb in enumerate(ms):
                     if i != j:
-                        cfg = "trans" if (ma.ref == alleles[0][i]) == (mb.ref == alleles[1][j]) else "cis"
-                        ac.append("\t".join([ma.id, ma.rsid, mb.id, mb.rsid, cfg]) + "\n")
+                        ac.append(left + mb.id + "\t" + mb.rsid + ("\ttrans\n" if ra == (mb.ref == al1[j]) else "\tcis\n"))
         if pending:
             texts = self._format_read_lists_native(req_keys, req_off, req_vars)
             for at, head, k in pending:
@@ -353,8 +405,8 @@ class Outputs:
         if self.unphased_vars == 1:
             ncls = r.ncls.reshape(-1, 3); sz = r.setsize.reshape(-1, 3)
             vbc = r.vb_cnt.reshape(-1, nb, 2)
-            singles = [v for v in self.first_seen_order().tolist()
-                       if int(ncls[v, 0]) + int(ncls[v, 1]) > 0 and r.v_final[v] == NONE32]
+            fso = self.first_seen_order()
+            singles = fso[((ncls[fso, 0].astype(np.int64) + ncls[fso, 1]) > 0) & (r.v_final[fso] == NONE32)].tolist()
             black = getattr(self.vt, "haplo_blacklisted", None)
             sg = self._singleton_read_sets() if self.read_names is not None else None
             for v in singles:

@@ -97,3 +97,58 @@ def test_native_bgzip_and_index_equal_the_python_writers(lib, hostsim, tmp_path,
         ext = ".csi" if csi else ".tbi"
         assert open(a, "rb").read() == open(b, "rb").read()
         assert open(a + ext, "rb").read() == open(b + ext, "rb").read()
+
+
+@pytest.mark.parametrize("name", G.case_names())
+def test_site_text_gives_the_same_variant_records(lib, name):
+    """phz_vcf_site_text (one native call for every site the tables name) -> writer.VariantMeta.from_site_text must be the
+    record writer.VariantMeta builds from the Python reading of the same VCF line, on every site of every golden input
+    (multi-allelic sites, unphased / phased genotypes, missing IDs, other id separators)."""
+    c = G.load_case(name)
+    kw, k = _kw(c)
+    if k["gw_phase_method"] == 1:
+        pytest.skip("allele frequencies are read by the Python path (prefetch_sites leaves those runs alone)")
+    col = vcfio.sample_column_map(c["vcf"])["S1"]
+    nv = vcfio.NativeVcf(c["vcf"], lib, threads=3)
+    vt, st = vcfio.parse_vcf_native(nv, col, **k)
+    rows = vt.ids.o
+    rows.prefetch_sites(np.arange(vt.n_variants)[::-1])
+    rows.prefetch_sites(np.arange(vt.n_variants))               # a second request for known sites asks for nothing
+    assert len(rows.site_rows) == vt.n_variants
+    contig_of = np.repeat(np.arange(len(vt.contigs)), np.diff(vt.contig_var_off))
+    n_native = 0
+    for v in range(vt.n_variants):
+        chrom = vt.contigs[int(contig_of[v])]
+        want = writer.VariantMeta(vt, v, chrom)
+        got = writer.VariantMeta.from_site_text(rows.site_rows[v], chrom, rows.sep, int(vt.pos[v]))
+        if got is None:
+            continue
+        n_native += 1
+        for f in writer.VariantMeta.__slots__:
+            assert getattr(got, f) == getattr(want, f), (v, f, rows.site_rows[v])
+    assert n_native > 0 or vt.n_variants == 0
+
+
+def test_site_text_on_hand_written_sites(lib, tmp_path):
+    """Missing ID, a FORMAT with GT in second place, a multi-allelic unphased site and a ninth ALT allele."""
+    alts = ",".join("ACGT"[i % 4] * (i + 2) for i in range(9))
+    lines = ["##fileformat=VCFv4.2\n", "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS1\n",
+             "1\t100\t.\tA\tG\t.\tPASS\t.\tGT\t0|1\n",
+             "1\t200\trs2\tA\t%s\t.\tPASS\t.\tGT:DP\t9|0:5\n" % alts,
+             "1\t300\trs3\tA\tC,G\t.\tPASS\t.\tDP:GT\t7:2/1\n"]
+    p = str(tmp_path / "odd.vcf.gz")
+    with gzip.open(p, "wt") as f:
+        f.writelines(lines)
+    nv = vcfio.NativeVcf(p, lib, threads=2)
+    vt, st = vcfio.parse_vcf_native(nv, 9, include_indels=1)
+    rows = vt.ids.o
+    rows.prefetch_sites(np.arange(vt.n_variants))
+    got = {int(vt.pos[v]): rows.site_rows[v] for v in range(vt.n_variants)}
+    assert got[100] == "100\t.\tA\tG\tA\tG\tA\tG"
+    last = alts.split(",")[-1]
+    assert got[200] == "200\trs2\tA\t%s\tA\t%s\t%s\tA" % (alts, last, last)
+    assert got[300] == "300\trs3\tA\tC,G\tC\tG\t-\t-"
+    for pos in (100, 200, 300):
+        m = writer.VariantMeta.from_site_text(got[pos], "1", "_", pos)
+        w = writer.VariantMeta(vt, [int(x) for x in vt.pos].index(pos), "1")
+        assert all(getattr(m, f) == getattr(w, f) for f in writer.VariantMeta.__slots__), pos
