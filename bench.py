@@ -279,6 +279,8 @@ def run_ours(a):
     E = eng.Engine(device=dev)
     E.set_option("k1_mode", a.k1_mode)
     E.set_option("k1_min_ctas", a.k1_min_ctas)
+    for kv in filter(None, os.environ.get("PHZ_OPTIONS", "").split(",")):      # A/B switches of the library, e.g. frag_stage=0
+        k, v = kv.split("="); E.set_option(k, int(v))
     t_gen = time.time()
     # shard mode: every rank generates the SAME sample (same seed, same generator, same GPU type) and keeps its contigs
     g, vt, packed, n_pairs = make_sample(a.seed + (0 if sharded else rank), a.pairs, a.variants, a.exonic_frac, dev)

@@ -427,6 +427,7 @@ int phz_set_option(phz_ctx* ctx, const char* name, int64_t value) {
   else if (n == "wide_pair_keys") ctx->p.wide_pair_keys = (int)value;
   else if (n == "window_agg") ctx->p.window_agg = (int)value;
   else if (n == "graph_mode") ctx->p.graph_mode = (int)value;
+  else if (n == "frag_stage") ctx->p.frag_stage = (int)value;
   else if (n == "n_fragments") ctx->p.n_frag_hint = value > 0 ? value : 0;
   else if (n == "pair_table_slots") { u64 s = 16; while (s < (u64)value) s <<= 1; ctx->p.pair_table_slots = s; }
   else if (n == "frag_run_limit") ctx->p.frag_run_limit = value < 1 ? 1 : value;
@@ -440,6 +441,8 @@ int phz_get_option(phz_ctx* ctx, const char* name, int64_t* value) {
   if (n == "graph_ranked_in_commit") *value = ctx->p.graph_ranked_in_commit ? 1 : 0;
   else if (n == "pair_table_slots") *value = (int64_t)ctx->p.pair_table_slots;
   else if (n == "graph_mode") *value = ctx->p.graph_mode;
+  else if (n == "frag_stage") *value = ctx->p.frag_stage;
+  else if (n == "fragments_deferred") *value = (int64_t)ctx->p.n_frag_deferred;
   else if (n == "k1_mode") *value = ctx->p.k1_mode;
   else if (n == "n_fragments") *value = ctx->p.n_frag_hint;
   else throw PhzError("unknown option: " + n);

@@ -33,6 +33,15 @@ constexpr int FRAG_CTA = 256;             // threads per CTA of the fragment ker
 constexpr int FRAG_PER_THREAD = PHZ_FRAG_PER_THREAD;   // consecutive fragment ids per CTA = FRAG_CTA * FRAG_PER_THREAD
 constexpr int FRAG_W = PHZ_FRAG_W;        // variant indices per shared-memory window
 constexpr int FRAG_HS = PHZ_FRAG_HS;      // slots of the CTA's pair hash
+#ifndef PHZ_FRAG_SLOTS
+#define PHZ_FRAG_SLOTS 2048
+#endif
+#ifndef PHZ_FRAG_SLOT_CTAS
+#define PHZ_FRAG_SLOT_CTAS 4
+#endif
+constexpr int FRAG_SLOTS = PHZ_FRAG_SLOTS;   // slot-chunk form: tuple slots per CTA (single-BAM instantiation; 3/4 of it otherwise)
+constexpr int FRAG_EXTRA = 128;           // slots staged beyond the chunk, for the tail of its last fragment
+constexpr uint16_t INFO_HEAD = 0x8000;    // f_info bit: first slot of a fragment (set by the scatter pass, kept for good)
 
 PHZ_HD u32 pair_hash(u64 k) {
   k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 29;
@@ -319,9 +328,9 @@ __global__ void __launch_bounds__(FRAG_CTA, 6) fragment_kernel(FragCtx c, const 
     if (i < n1) {
       const u32 o0 = f_off[f0 + s_list[i]];
       const u64 key = fk[o0]; const u32 v = (u32)(key >> 32);
-      const u32 cb = info[o0]; const u32 cls = cb & 3, bam = cb >> 2;
+      const u32 cb = info[o0] & 0x7FFFu; const u32 cls = cb & 3, bam = cb >> 2;
       if (cls >= 2) fk[o0] = key | 0xFFFFFFFFull;
-      info[o0] = (uint16_t)((bam << 3) | (1u << cls));
+      info[o0] = (uint16_t)((bam << 3) | (1u << cls) | INFO_HEAD);
       sink.set_size(v, (int)cls);
       if (cls < 2 && !((c.excl_mask >> bam) & 1)) sink.bam_count(v, bam, (int)cls);
       ++ne_sum; ++ng;
@@ -337,7 +346,9 @@ __global__ void __launch_bounds__(FRAG_CTA, 6) fragment_kernel(FragCtx c, const 
     if (i < nm) {
       const int64_t f = f0 + s_list[FRAG_RANGE - 1 - i];
       const u32 o0 = f_off[f], n = f_off[f + 1] - o0;
+      info[o0] &= 0x7FFFu;              // the head mark is not part of the tuple's class | bam
       const u32 ne = process_fragment<ONE_BAM>(c, fk + o0, info + o0, n, sink, ng, np);
+      info[o0] |= INFO_HEAD;
       if (ne != n) f_ne[f] = ne;
       ne_sum += ne;
     }
@@ -351,6 +362,176 @@ __global__ void __launch_bounds__(FRAG_CTA, 6) fragment_kernel(FragCtx c, const 
     if (np) atomicAdd(&cnt3[2], (unsigned long long)np);
   }
   __syncthreads();
+  const u32 base = s_base;
+  for (int i = tid; i < FRAG_W; i += FRAG_CTA) {
+    const int64_t v = (int64_t)base + i;
+    for (int x = 0; x < 3; ++x) if (s_sz[i * 3 + x]) atomicAdd(&sz[v * 3 + x], s_sz[i * 3 + x]);
+    if (nb <= VB_BAMS) for (int a = 0; a < nb * 2; ++a) if (s_vb[i * nb * 2 + a]) atomicAdd(&vbc[v * nb * 2 + a], s_vb[i * nb * 2 + a]);
+  }
+  for (int i = tid; i < FRAG_HS; i += FRAG_CTA) {
+    const unsigned long long key = h_keys[i];
+    if (key == PAIR_EMPTY) continue;
+    const int s = pair_slot(pt, key);
+    if (s < 0) continue;
+    for (int cidx = 0; cidx < PAIR_CELLS; ++cidx) {
+      const u32 cv = (h_vals[i * 5 + (cidx >> 1)] >> (16 * (cidx & 1))) & 0xFFFFu;
+      if (cv) atomicAdd(&pt.vals[(int64_t)s * PAIR_CELLS + cidx], cv);
+    }
+  }
+}
+#endif
+
+#ifdef __CUDACC__
+// ----------------------------------------------------------------------------- slot-chunk form (frag_stage 1, the default)
+// The slots of consecutive fragments are consecutive (f_off is a scan), so a CTA can own a CHUNK OF SLOTS instead of a
+// range of fragment ids: it copies its chunk of keys / info words into shared memory with coalesced loads (plus
+// FRAG_EXTRA slots for the tail of its last fragment), finds the fragments from the head marks the scatter pass left in
+// f_info (no look-up in the fragment table at all, and fragments without tuples cost nothing), runs the same
+// process_fragment on shared memory, and writes the chunk back in one coalesced sweep.  The per-fragment dependent
+// global loads (table -> key -> info) of the range form, which left it waiting on the long scoreboard, are gone; work
+// per CTA is even (slots, not fragment ids).  A fragment whose tail does not fit the staged slots (more than
+// FRAG_EXTRA tuples and badly placed) goes to a side list and is processed from global memory by a second, tiny pass
+// once no CTA is staging any more (`deferred`: pairs of head slot and fragment id; count at deferred_n).
+__device__ __forceinline__ int next_head(const u32* hb, int i, int n_st) {      // first head position > i, n_st if none
+  int w = (i + 1) >> 5;
+  const int nw = (n_st + 31) >> 5;
+  if (w >= nw) return n_st;
+  u32 m = hb[w] & (0xFFFFFFFFu << ((i + 1) & 31));
+  while (!m) { if (++w >= nw) return n_st; m = hb[w]; }
+  return (w << 5) + __ffs(m) - 1;
+}
+
+template <bool ONE_BAM>
+__global__ void __launch_bounds__(FRAG_CTA, PHZ_FRAG_SLOT_CTAS) fragment_slots_kernel(FragCtx c, int64_t n_slots, u64* __restrict__ fk,
+                                                                     uint16_t* __restrict__ info, const u32* __restrict__ gf,
+                                                                     const u32* __restrict__ f_off, u32* __restrict__ f_ne, int nb,
+                                                                     u32* __restrict__ sz, u32* __restrict__ vbc, PairTable pt,
+                                                                     unsigned long long* __restrict__ cnt3, u32* __restrict__ deferred,
+                                                                     u32* __restrict__ deferred_n) {
+  constexpr int VB_BAMS = ONE_BAM ? 1 : 4;
+  constexpr int SLOTS = ONE_BAM ? FRAG_SLOTS : FRAG_SLOTS * 3 / 4;
+  constexpr int CAP = SLOTS + FRAG_EXTRA;
+  static_assert(CAP % 32 == 0 && CAP < 32768, "staged slots: whole mark words, 15-bit positions");
+  __shared__ u32 s_sz[FRAG_W * 3];
+  __shared__ u32 s_vb[FRAG_W * 2 * VB_BAMS];
+  __shared__ unsigned long long h_keys[FRAG_HS];
+  __shared__ u32 h_vals[FRAG_HS * 5];
+  __shared__ __align__(16) u64 s_k[CAP];
+  __shared__ uint16_t s_i[CAP];
+  __shared__ u32 s_hb[CAP / 32];           // head marks of the staged slots
+  __shared__ uint16_t s_list[SLOTS];       // head positions: single-tuple fragments from the front, the others from the back
+  __shared__ u32 s_base, s_n1, s_nm, s_next1, s_nextm;
+  __shared__ int s_def;                    // head position of the fragment left to the second pass, -1 if none
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t s0 = (int64_t)blockIdx.x * SLOTS;
+  const int n_own = (int)((n_slots - s0) < SLOTS ? (n_slots - s0) : SLOTS);
+  const int n_st = (int)((n_slots - s0) < CAP ? (n_slots - s0) : CAP);
+  if (*c.abort & 8u) return;        // the host takes the sort-based stage instead
+  for (int i = tid; i < FRAG_W * 3; i += FRAG_CTA) s_sz[i] = 0;
+  for (int i = tid; i < FRAG_W * 2 * VB_BAMS; i += FRAG_CTA) s_vb[i] = 0;
+  for (int i = tid; i < FRAG_HS; i += FRAG_CTA) h_keys[i] = PAIR_EMPTY;
+  for (int i = tid; i < FRAG_HS * 5; i += FRAG_CTA) h_vals[i] = 0;
+  // ---- stage the chunk (whole warps, so that every mark word is one ballot)
+  for (int b = tid & ~31; b < n_st; b += FRAG_CTA) {
+    const int i = b + lane;
+    u32 w = 0;
+    if (i < n_st) { s_k[i] = fk[s0 + i]; w = info[s0 + i]; s_i[i] = (uint16_t)(w & 0x7FFFu); }
+    const u32 marks = __ballot_sync(0xFFFFFFFFu, (w & INFO_HEAD) != 0);
+    if (lane == 0) s_hb[b >> 5] = marks;
+  }
+  if (tid == 0) { s_n1 = 0; s_nm = 0; s_next1 = 0; s_nextm = 0; s_def = -1; }
+  __syncthreads();
+  if (tid == 0) {
+    const u32 v0 = (u32)(s_k[0] >> 32);
+    s_base = v0 > FRAG_W / 4 ? v0 - FRAG_W / 4 : 0;
+  }
+  // ---- fragments whose head lies in the chunk: two work lists (one shared-memory reduction per warp and list)
+  for (int b = tid & ~31; b < n_own; b += FRAG_CTA) {
+    const int i = b + lane;
+    u32 n = 0;
+    if (i < n_own && ((s_hb[i >> 5] >> (i & 31)) & 1u)) {
+      const int e = next_head(s_hb, i, n_st);
+      if (e == n_st && s0 + n_st < n_slots) {
+        // the tail is not staged: side list (at most one fragment per CTA: the chunk's last)
+        const u32 d = atomicAdd(deferred_n, 1u);
+        deferred[2 * d] = (u32)(s0 + i); deferred[2 * d + 1] = gf[(u32)s_k[i]];
+        s_def = i;                  // slots from here on stay as they are
+        n = 0xFFFFFFFFu;
+      } else n = (u32)(e - i);
+    }
+    const bool one = n == 1, many = n > 1 && n != 0xFFFFFFFFu;
+    const u32 m1 = __ballot_sync(0xFFFFFFFFu, one), mm = __ballot_sync(0xFFFFFFFFu, many);
+    u32 b1 = 0, bm = 0;
+    if (lane == 0) { if (m1) b1 = atomicAdd(&s_n1, (u32)__popc(m1)); if (mm) bm = atomicAdd(&s_nm, (u32)__popc(mm)); }
+    b1 = __shfl_sync(0xFFFFFFFFu, b1, 0); bm = __shfl_sync(0xFFFFFFFFu, bm, 0);
+    const u32 lt = (1u << lane) - 1u;
+    if (one) s_list[b1 + __popc(m1 & lt)] = (uint16_t)i;
+    else if (many) s_list[SLOTS - 1 - (bm + __popc(mm & lt))] = (uint16_t)i;
+  }
+  __syncthreads();
+  CtaSink<VB_BAMS> sink{s_sz, s_vb, s_base, nb, sz, vbc, h_keys, h_vals, pt};
+  u32 ne_sum = 0, ng = 0, np = 0;
+  const u32 n1 = s_n1, nm = s_nm;
+  // ---- single-tuple fragments: one entry, one group, no pair
+  for (;;) {
+    u32 start = 0;
+    if (lane == 0) start = atomicAdd(&s_next1, 32u);
+    start = __shfl_sync(0xFFFFFFFFu, start, 0);
+    if (start >= n1) break;
+    const u32 i = start + lane;
+    if (i < n1) {
+      const int p = s_list[i];
+      const u64 key = s_k[p]; const u32 v = (u32)(key >> 32);
+      const u32 cb = s_i[p]; const u32 cls = cb & 3, bam = cb >> 2;
+      if (cls >= 2) s_k[p] = key | 0xFFFFFFFFull;
+      s_i[p] = (uint16_t)((bam << 3) | (1u << cls));
+      sink.set_size(v, (int)cls);
+      if (cls < 2 && !((c.excl_mask >> bam) & 1)) sink.bam_count(v, bam, (int)cls);
+      ++ne_sum; ++ng;
+    }
+  }
+  // ---- the others
+  for (;;) {
+    u32 start = 0;
+    if (lane == 0) start = atomicAdd(&s_nextm, 32u);
+    start = __shfl_sync(0xFFFFFFFFu, start, 0);
+    if (start >= nm) break;
+    const u32 i = start + lane;
+    if (i < nm) {
+      const int p = s_list[SLOTS - 1 - i];
+      const u32 n = (u32)(next_head(s_hb, p, n_st) - p);
+      const u32 t0 = (u32)s_k[p];                 // any tuple of the fragment names it
+      const u32 ne = process_fragment<ONE_BAM>(c, s_k + p, s_i + p, n, sink, ng, np);
+      if (ne != n) f_ne[gf[t0]] = ne;
+      ne_sum += ne;
+    }
+  }
+  // counters: registers -> warp -> one reduction per warp
+  for (int o = 16; o > 0; o >>= 1) {
+    ne_sum += __shfl_xor_sync(0xFFFFFFFFu, ne_sum, o); ng += __shfl_xor_sync(0xFFFFFFFFu, ng, o); np += __shfl_xor_sync(0xFFFFFFFFu, np, o);
+  }
+  if (lane == 0) {
+    if (ne_sum) { atomicAdd(&cnt3[0], (unsigned long long)ne_sum); atomicAdd(&cnt3[1], (unsigned long long)ng); }
+    if (np) atomicAdd(&cnt3[2], (unsigned long long)np);
+  }
+  __syncthreads();
+  // ---- write the chunk back: from its first head to the end of its last fragment (a deferred fragment stays untouched)
+  {
+    int first = n_st;
+    for (int w = 0; w < (n_own + 31) >> 5; ++w) if (s_hb[w]) { first = (w << 5) + __ffs(s_hb[w]) - 1; break; }
+    int last_head = -1;
+    for (int w = ((n_own + 31) >> 5) - 1; w >= 0; --w) {
+      u32 m = s_hb[w];
+      if (w == (n_own >> 5) && (n_own & 31)) m &= (1u << (n_own & 31)) - 1u;
+      if (m) { last_head = (w << 5) + 31 - __clz(m); break; }
+    }
+    int end = 0;
+    if (last_head >= 0) end = s_def >= 0 ? s_def : next_head(s_hb, last_head, n_st);
+    for (int i = first + tid; i < end; i += FRAG_CTA) {
+      fk[s0 + i] = s_k[i];
+      info[s0 + i] = (uint16_t)(s_i[i] | (((s_hb[i >> 5] >> (i & 31)) & 1u) ? INFO_HEAD : 0));
+    }
+  }
   const u32 base = s_base;
   for (int i = tid; i < FRAG_W; i += FRAG_CTA) {
     const int64_t v = (int64_t)base + i;

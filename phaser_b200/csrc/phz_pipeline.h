@@ -639,6 +639,9 @@ struct Pipeline {
   int lazy_canonical = 1;           // 1: the tile kernel's output stays in arrival order until somebody needs canonical order
   bool tile_order = false, canonical_valid = true; int64_t tiles_cur = 0;
   int graph_mode = 1;               // 1: fragment-table graph stage (phz_graph.h), 0: sort-based stage (A/B switch and fallback)
+  int frag_stage = 1;               // fragment kernel of the fragment-table stage: 1 slot chunks staged in shared memory, 0 ranges of fragment ids
+  u64 n_frag_deferred = 0;          // fragments of the last graph stage that the slot-chunk kernel left to its second pass
+  Buf<B, u32> frag_deferred;
   bool frag_entries = false;        // which form of the (fragment, variant, BAM) entries the last build_graph left behind
   Buf<B, u32> f_cnt, f_off; Buf<B, uint16_t> t_rank, f_info; Buf<B, u64> f_key, pt_keys, pt_cnt3; Buf<B, u32> pt_vals, pt_flags, pt_slot, rank_flag;
   int64_t n_frag_cur = 0; u64 pair_table_slots = 1ull << 20; int64_t pair_table_grown = 0;
@@ -691,7 +694,7 @@ struct Pipeline {
     rl_flag.bind(b); rl_scan.bind(b); rl_k32.bind(b); rl_k32b.bind(b); rl_t.bind(b); rl_t2.bind(b); rl_k64.bind(b);
     rl_k64b.bind(b); rl_frag.bind(b); rl_var.bind(b); rl_row.bind(b);
     f_cnt.bind(b); f_off.bind(b); t_rank.bind(b); rank_flag.bind(b); f_info.bind(b); f_key.bind(b); pt_keys.bind(b); pt_cnt3.bind(b); pt_vals.bind(b);
-    pt_flags.bind(b); pt_slot.bind(b);
+    pt_flags.bind(b); pt_slot.bind(b); frag_deferred.bind(b);
   }
 
   u32 fetch_u32(const u32* p) { u32 v = 0; be.d2h(&v, p, sizeof(u32)); return v; }
@@ -1148,7 +1151,7 @@ struct Pipeline {
       be.for_each(n, PHZ_LAMBDA(int64_t t) {
         const u32 r = rk[t]; if (r == 65535u) return;
         const u32 slot = fo[gf[t]] + r;
-        fk[slot] = ((u64)gv[t] << 32) | (u64)(u32)t; fi[slot] = (uint16_t)gc[t];
+        fk[slot] = ((u64)gv[t] << 32) | (u64)(u32)t; fi[slot] = (uint16_t)(gc[t] | (r == 0 ? INFO_HEAD : 0));
       });
       be.memset0(sz, Vn * 3 * sizeof(u32)); be.memset0(vbc, Vn * nb * 2 * sizeof(u32)); be.memset_ff(vr, Vn * sizeof(u64));
       u64* pk = pt_keys.ensure(S); u32* pv = pt_vals.ensure(S * PAIR_CELLS); u32* pf = pt_flags.ensure(4);
@@ -1161,6 +1164,36 @@ struct Pipeline {
 #ifdef __CUDACC__
       {
         const int64_t per = (int64_t)FRAG_CTA * FRAG_PER_THREAD;
+        if (frag_stage == 1 && n > 0) {
+          // slot-chunk form: a CTA owns a chunk of tuple slots, staged in shared memory; fragments it cannot stage go to a
+          // side list that one more small pass works off from global memory
+          const int64_t slots = nb == 1 ? FRAG_SLOTS : FRAG_SLOTS * 3 / 4;
+          const int64_t n_cta = (n + slots - 1) / slots;
+          u32* dfl = frag_deferred.ensure(2 * n_cta + 2); u32* dfn = dfl + 2 * n_cta;
+          be.memset0(dfn, 2 * sizeof(u32));
+          if (nb == 1)
+            fragment_slots_kernel<true><<<(unsigned)n_cta, FRAG_CTA, 0, be.stream>>>(fx, n, fk, fi, gf, fo, fne, nb, sz, vbc, pt,
+                                                                                   (unsigned long long*)c3, dfl, dfn);
+          else
+            fragment_slots_kernel<false><<<(unsigned)n_cta, FRAG_CTA, 0, be.stream>>>(fx, n, fk, fi, gf, fo, fne, nb, sz, vbc, pt,
+                                                                                    (unsigned long long*)c3, dfl, dfn);
+          PHZ_CUDA(cudaGetLastError());
+          be.launches++;
+          const u32* abortp = sc + 1;
+          be.for_each(n_cta, PHZ_LAMBDA(int64_t i) {
+            if ((u32)i >= dfn[0] || (*abortp & 8u)) return;
+            const u32 o0 = dfl[2 * i], f = dfl[2 * i + 1]; const u32 cnt = fo[f + 1] - fo[f];
+            DirectSink sink{sz, vbc, nb, pt};
+            u32 ng = 0, np = 0;
+            fi[o0] &= 0x7FFFu;
+            const u32 ne = nb == 1 ? process_fragment<true>(fx, fk + o0, fi + o0, cnt, sink, ng, np)
+                                   : process_fragment<false>(fx, fk + o0, fi + o0, cnt, sink, ng, np);
+            fi[o0] |= INFO_HEAD;
+            if (ne != cnt) fne[f] = ne;
+            atomic_add((unsigned long long*)&c3[0], (unsigned long long)ne); atomic_add((unsigned long long*)&c3[1], (unsigned long long)ng);
+            atomic_add((unsigned long long*)&c3[2], (unsigned long long)np); atomic_add((unsigned long long*)&c3[7], 1ull);
+          });
+        } else
         if (nb == 1)
           fragment_kernel<true><<<(unsigned)((F + per - 1) / per), FRAG_CTA, 0, be.stream>>>(fx, fo, F, fk, fi, fne, nb, sz, vbc, pt,
                                                                                           (unsigned long long*)c3);
@@ -1176,8 +1209,12 @@ struct Pipeline {
         u64 ne_sum = 0, ng_sum = 0, np_sum = 0;
         for (int64_t f = 0; f < F && !(sc[1] & 8u); ++f) {
           const u32 o0 = fo[f], cnt = fo[f + 1] - o0; u32 ng = 0, np = 0, ne = 0;
-          if (cnt) ne = nb == 1 ? process_fragment<true>(fx, fk + o0, fi + o0, cnt, sink, ng, np)
-                                : process_fragment<false>(fx, fk + o0, fi + o0, cnt, sink, ng, np);
+          if (cnt) {
+            fi[o0] &= 0x7FFFu;            // the head mark is not part of the tuple's class | bam
+            ne = nb == 1 ? process_fragment<true>(fx, fk + o0, fi + o0, cnt, sink, ng, np)
+                         : process_fragment<false>(fx, fk + o0, fi + o0, cnt, sink, ng, np);
+            fi[o0] |= INFO_HEAD;
+          }
           if (ne != cnt) fne[f] = ne;
           ne_sum += ne; ng_sum += ng; np_sum += np;
         }
@@ -1198,8 +1235,9 @@ struct Pipeline {
       // pass's verdict, and the entry / group / pair totals
       { const u32* xs_c = xs; int64_t ss = (int64_t)S;
         be.for_each(1, PHZ_LAMBDA(int64_t) { c3[3] = pf[0]; c3[4] = pf[1]; c3[5] = xs_c[ss]; c3[6] = sc[1]; }); }
-      u64 h7[7] = {0, 0, 0, 0, 0, 0, 0};
+      u64 h7[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       be.d2h(h7, c3, sizeof(h7));
+      n_frag_deferred = h7[7];
       if (h7[6] & 8u) return false;            // a fragment beyond the 16-bit rank: sort-based stage
       if (h7[3] & 1u) {                        // pair table full: grow it and run the fragments again
         if (attempt >= 8) throw PhzError("pair table keeps overflowing");
@@ -1743,14 +1781,14 @@ struct Pipeline {
         for (u32 j = j0; j < j1; ++j) {
           u32 v = (u32)(fk[j] >> 32); u32 f = vfin[v];
           if (f == NONE32) continue;
-          const u32 mj = fi[j] & 7u, bj = fi[j] >> 3;
+          const u32 mj = fi[j] & 7u, bj = (fi[j] & 0x7FFFu) >> 3;
           for (int h = 0; h < 2; ++h) {
             if (!((mj >> (vh[v] ^ h)) & 1)) continue;
             bool seen_any = false, seen_bam = false;
             for (u32 i = j0; i < j; ++i) {
               u32 w = (u32)(fk[i] >> 32);
               if (vfin[w] != f || !(((fi[i] & 7u) >> (vh[w] ^ h)) & 1)) continue;
-              seen_any = true; if ((u32)(fi[i] >> 3) == bj && !(vbl && vbl[w])) seen_bam = true;
+              seen_any = true; if ((u32)((fi[i] & 0x7FFFu) >> 3) == bj && !(vbl && vbl[w])) seen_bam = true;
             }
             if (!seen_any) converged_inc(&fc[(int64_t)f * 2 + h]);
             if (!seen_bam && !((excl_mask >> bj) & 1) && !(vbl && vbl[v]))

@@ -405,6 +405,39 @@ def test_fragment_table_graph_equals_the_sort_based_graph(gpu, tmp_path):
             assert np.array_equal(a.arrays[k], x.arrays[k]), k
 
 
+@pytest.mark.parametrize("n_bams,fold", [(1, 0), (3, 0), (1, 11), (2, 5)])
+def test_slot_chunk_fragment_kernel_equals_the_range_form(gpu, tmp_path, n_bams, fold):
+    """frag_stage 1 (a CTA owns a chunk of tuple slots staged in shared memory, fragments found from the head marks)
+    against frag_stage 0 (a CTA owns a range of fragment ids, one thread per fragment on global memory) and the sort-based
+    stage: identical result arrays and counters over many chunks.  With the read names folded onto a handful of
+    fragments every fragment holds thousands of tuples: their tails are not staged and the second pass takes them."""
+    from phaser_b200 import pipeline
+    vcf, sams = util.make_case(tmp_path, 58 + n_bams, 700, 30000, n_bams=n_bams, switch_per_base=0.02, insert_lo=60, insert_hi=220)
+    vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+    nf = len(fd.names)
+    if fold:
+        for b in batches:
+            b.frag = (b.frag % np.uint32(fold)).astype(np.uint32)
+        nf = fold
+    P = pipeline.PhaseParams(haplo_count_bam_exclude=[1] if n_bams > 1 else [])
+    out = []
+    for graph, stage in ((1, 1), (1, 0), (0, 0)):
+        gpu.set_option("graph_mode", graph); gpu.set_option("frag_stage", stage)
+        try:
+            out.append(pipeline.run_path(gpu, vt, [gpu.upload_reads(b) for b in batches], P, n_fragments=nf))
+            if graph == 1 and stage == 1:
+                assert out[-1].counters["full_sort_fallback"] == 0
+                assert (gpu.get_option("fragments_deferred") > 0) == bool(fold)
+        finally:
+            gpu.set_option("graph_mode", 1); gpu.set_option("frag_stage", 1)
+    a, b, c = out
+    assert a.counters["n_tuples"] > 20000 and a.counters["edges"] > 100
+    for x in (b, c):
+        assert a.counters == x.counters
+        for k in a.arrays:
+            assert np.array_equal(a.arrays[k], x.arrays[k]), k
+
+
 def test_ranks_taken_by_the_commits_equal_ranks_taken_by_the_graph_stage(gpu, tmp_path):
     """With the fragment count announced (option "n_fragments") every commit ranks its tuples inside their fragments while it
     writes them, and the graph stage skips its ranking pass; without it the graph stage ranks.  Same graph either way, also
