@@ -421,6 +421,7 @@ int phz_set_option(phz_ctx* ctx, const char* name, int64_t value) {
   std::string n(name);
   if (n == "k1_mode") ctx->p.k1_mode = (int)value;
   else if (n == "k1_min_ctas") ctx->p.k1_min_ctas = (int)value;
+  else if (n == "k1_staged_emit") ctx->p.k1_staged_emit = (int)value;
   else if (n == "big_total_threshold") ctx->p.big_total_thr = (u32)value;
   else if (n == "lazy_canonical") ctx->p.lazy_canonical = (int)value;
   else if (n == "two_pass_read_lists") ctx->p.two_pass_read_lists = (int)value;

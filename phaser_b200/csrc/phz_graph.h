@@ -86,7 +86,8 @@ struct FragCtx {
 // One fragment.  k[0..n): keys (variant << 32 | tuple index) in any order, info[0..n): class | bam << 2 of the same tuples
 // (written next to the keys by the scatter pass, so no dependent look-up per tuple is needed here).  On return
 // k[0..ne) / info[0..ne) hold the fragment's (variant, BAM) entries sorted by (variant, BAM):
-// k = variant << 32 | first tuple with a reference / alternative call (NONE32 if none), info = bam << 3 | class mask.
+// k = variant << 32 | first tuple with a reference / alternative call (NONE32 if none), info = bam << 3 | class mask;
+// info[ne..n) = 0 (an empty class mask), so that a pass over the SLOTS needs neither the fragment table nor ne.
 // Returns ne; adds groups / pairs to ng / np.
 template <bool ONE_BAM, class Sink>
 PHZ_HD u32 process_fragment(const FragCtx& c, u64* k, uint16_t* info, u32 n, Sink& sink, u32& ng, u32& np) {
@@ -143,6 +144,7 @@ PHZ_HD u32 process_fragment(const FragCtx& c, u64* k, uint16_t* info, u32 n, Sin
       }
       g0 = g1;
     }
+    for (u32 x = ne; x < n; ++x) info[x] = 0;       // slots behind the entries: no class, inert for whoever walks the slots
     return ne;
   }
   // (variant, BAM) entries, in place: tuple order inside a variant is BAM-major (commit order)
@@ -208,6 +210,7 @@ PHZ_HD u32 process_fragment(const FragCtx& c, u64* k, uint16_t* info, u32 n, Sin
     }
     g0 = g1;
   }
+  for (u32 x = ne; x < n; ++x) info[x] = 0;         // slots behind the entries: no class, inert for whoever walks the slots
   return ne;
 }
 

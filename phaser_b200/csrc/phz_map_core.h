@@ -223,6 +223,51 @@ PHZ_HD u32 call_indel_site(const RV& rv, const VariantsViewIndels& vv, int64_t j
   return pack_misc(cls, n_chars > 1 ? 1 : 0, first, seg, as16);
 }
 
+// identify_allele (read_variant_map.py:236-258) for a single-base site: pseudo_read[st] of the segment made of CIGAR ops
+// [kseg, kend) (a closing N ends it early) plus the insertion keyed st, minus every 'D'.  Keys of insertions are
+// whole-read offsets looked up segment-relative (Q3).  Returns the packed t_misc word.
+template <class RV>
+PHZ_HD u32 call_snv_site(const RV& rv, u8 a0, u8 a1, u32 kseg, u32 kend, int32_t seg_start, int32_t q_start, u64 boff,
+                         int baseq, int32_t st, int seg, int as16) {
+  int32_t g = seg_start, q = q_start;
+  int base = -1;            // 16: deletion placeholder
+  int32_t ins_q = -1, ins_n = 0;
+  for (u32 x = kseg; x < kend; ++x) {
+    u32 c = rv.cigar_at(x); int op = c & 15; int32_t n = (int32_t)(c >> 4);
+    if (op == OP_N) break;
+    if (op == OP_M || op == OP_EQ || op == OP_X) {
+      int32_t sp = g - seg_start;
+      if (st >= sp && st < sp + n) base = masked_base(rv, boff, q + (st - sp), baseq);
+      g += n; q += n;
+    } else if (op == OP_D) {
+      int32_t sp = g - seg_start;
+      if (st >= sp && st < sp + n) base = 16;
+      g += n;
+    } else if (op == OP_I) {
+      if (g - 1 == st) { ins_q = q; ins_n = n; }       // later insertion with the same key wins
+      q += n;
+    } else if (op == OP_S) {
+      q += n;
+    }
+  }
+  // string = [base] + inserted bases, minus every 'D'
+  int n_chars = 0, first = 0;
+  if (base != 16 && base != BASE_D && base >= 0) { first = base; n_chars = 1; }
+  for (int32_t z = 0; z < ins_n; ++z) {
+    int b = masked_base(rv, boff, ins_q + z, baseq);
+    if (b != BASE_D) { if (n_chars == 0) first = b; n_chars++; }
+  }
+  int cls, multi = 0;
+  if (n_chars == 0) cls = CLS_NONE;                     // "" -> nothing written
+  else if (n_chars == 1) {
+    if (first == BASE_N) cls = CLS_NONE;                // "N" -> nothing written
+    else if (first == a0) cls = CLS_A0;
+    else if (first == a1) cls = CLS_A1;
+    else cls = CLS_OTHER;
+  } else { cls = CLS_OTHER; multi = 1; }
+  return pack_misc(cls, multi, first, seg, as16);
+}
+
 // Walks one record.
 // MODE 0 (count): returns the number of candidate (segment, variant) pairs.
 // MODE 1 (emit):  writes one tuple per candidate starting at out index `o` (class CLS_NONE when the
@@ -283,46 +328,10 @@ PHZ_HD u32 map_record(const RV& rv, const VV& vv, const VP& vp, int64_t r, int c
                 continue;
               }
             }
-            // locate pseudo_read[st] and the insertion keyed st (keys are whole-read offsets: Q3)
-            int32_t g = seg_start, q = q_start;
-            int base = -1;            // 16: deletion placeholder
-            int32_t ins_q = -1, ins_n = 0;
-            for (u32 x = kseg; x < kend; ++x) {
-              u32 c = rv.cigar_at(x); int op = c & 15; int32_t n = (int32_t)(c >> 4);
-              if (op == OP_M || op == OP_EQ || op == OP_X) {
-                int32_t sp = g - seg_start;
-                if (st >= sp && st < sp + n) base = masked_base(rv, boff, q + (st - sp), baseq);
-                g += n; q += n;
-              } else if (op == OP_D) {
-                int32_t sp = g - seg_start;
-                if (st >= sp && st < sp + n) base = 16;
-                g += n;
-              } else if (op == OP_I) {
-                if (g - 1 == st) { ins_q = q; ins_n = n; }       // later insertion with the same key wins
-                q += n;
-              } else if (op == OP_S) {
-                q += n;
-              }
-            }
-            // string = [base] + inserted bases, minus every 'D'
-            int n_chars = 0, first = 0;
-            if (base != 16 && base != BASE_D && base >= 0) { first = base; n_chars = 1; }
-            for (int32_t z = 0; z < ins_n; ++z) {
-              int b = masked_base(rv, boff, ins_q + z, baseq);
-              if (b != BASE_D) { if (n_chars == 0) first = b; n_chars++; }
-            }
-            int cls, multi = 0;
-            if (n_chars == 0) cls = CLS_NONE;                     // "" -> nothing written
-            else if (n_chars == 1) {
-              if (first == BASE_N) cls = CLS_NONE;                // "N" -> nothing written
-              else if (first == vv.a0[j]) cls = CLS_A0;
-              else if (first == vv.a1[j]) cls = CLS_A1;
-              else cls = CLS_OTHER;
-            } else { cls = CLS_OTHER; multi = 1; }
             const u64 w = (MODE == 2) ? 0 : o + n_out;
             t_rec[w] = (u32)r;
             t_var[w] = (u32)j;
-            t_misc[w] = pack_misc(cls, multi, first, seg, as16);
+            t_misc[w] = call_snv_site(rv, vv.a0[j], vv.a1[j], kseg, kend, seg_start, q_start, boff, baseq, st, seg, as16);
             n_out++;
           }
           if (MODE == 2) return 1;

@@ -405,26 +405,22 @@ __global__ void __launch_bounds__(KF_THREADS) k1_fused_kernel(ReadsView rv, Vari
 // running offsets in shared memory), so all lanes gather SEQ/QUAL bytes and the stores are fully
 // coalesced.  A scan over the tile table then gives the canonical offsets and a streaming permute
 // moves each tile's block into (record, segment, variant) order.
-#ifdef __CUDACC__
-constexpr int KT_CIG = 1024;          // CIGAR words staged per tile (4 KB); tiles with more fall back to global loads
-constexpr int KT_OWN = 1024;          // candidate slots with a direct owner entry; beyond that a search over the offsets
-
-__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, int bytes, unsigned long long* mbar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
-}
-
-// Count pass of ONE record served entirely from the tile's shared-memory slabs, in 32-bit arithmetic: the CIGAR words,
-// POS and the het-site slab are all staged, the record lies on the tile's first contig, so the general walk's 64-bit
-// offsets, contig look-ups and global fall-backs are not needed.  Same predicate as map_record<0> (read_variant_map.py:
-// 191-232, 239-242).  Returns false when the slab does not pin a search down (the caller takes the general walk).
-__device__ __forceinline__ bool tile_count_fast(const int32_t* __restrict__ s_pos, const u32* __restrict__ s_coff,
-                                                const u32* __restrict__ s_cig, u32 cig_al, int i, const int32_t* __restrict__ win,
-                                                int a, int b, bool at_start, bool at_end, int hint_lo, int hint_hi, u32& cnt_out) {
+// Count pass of ONE record served entirely from the tile's slabs (shared memory on the device), in 32-bit arithmetic: the
+// CIGAR words, POS and the het-site slab are all staged, the record lies on the tile's first contig, so the general walk's
+// 64-bit offsets, contig look-ups and global fall-backs are not needed.  Same predicate as map_record<0>
+// (read_variant_map.py:191-232, 239-242).  Returns false when the slab does not pin a search down (the caller takes the
+// general walk).  state_out tells the dense emission where the record's candidates are, so that it does not have to find
+// them again: (slab index of the first candidate) | (CIGAR op, counted from the record's first, that opens their segment)
+// << 16 when all candidates lie in ONE segment, EMIT_COMPLEX otherwise (the emission re-derives those).
+constexpr u32 EMIT_COMPLEX = 0xFFFFFFFFu;
+PHZ_HD bool tile_count_fast(const int32_t* __restrict__ s_pos, const u32* __restrict__ s_coff,
+                            const u32* __restrict__ s_cig, u32 cig_al, int i, const int32_t* __restrict__ win,
+                            int a, int b, bool at_start, bool at_end, int hint_lo, int hint_hi, u32& cnt_out, u32& state_out) {
   const int32_t rpos = s_pos[i];
-  u32 k = s_coff[i] - cig_al; const u32 kend = s_coff[i + 1] - cig_al;
-  u32 cnt = 0; int32_t gp = 0; bool first = true;
+  const u32 k0 = s_coff[i] - cig_al; u32 k = k0; const u32 kend = s_coff[i + 1] - cig_al;
+  u32 cnt = 0, state = EMIT_COMPLEX; int32_t gp = 0; bool first = true;
   while (true) {
+    const u32 kseg = k;
     int32_t g_end = gp;
     for (; k < kend; ++k) {
       const u32 c = s_cig[k]; const u32 op = c & 15u;
@@ -448,13 +444,52 @@ __device__ __forceinline__ bool tile_count_fast(const int32_t* __restrict__ s_po
       int h = l;
       while (h < b && win[h] < hi_key) ++h;
       if (h == b && !at_end) return false;
-      cnt += (u32)(h - l);
+      if (h > l) {
+        state = (cnt == 0 && kseg - k0 < 65536u) ? ((u32)l | ((kseg - k0) << 16)) : EMIT_COMPLEX;
+        cnt += (u32)(h - l);
+      }
     }
     if (k >= kend) break;
     gp = g_end + (int32_t)(s_cig[k] >> 4); ++k; first = false;
   }
-  cnt_out = cnt;
+  cnt_out = cnt; state_out = state;
   return true;
+}
+
+// Dense emission of ONE candidate whose place the count pass recorded (state != EMIT_COMPLEX): candidate j of record i of
+// the tile sits at slab index (state & 0xFFFF) + j, in the segment opened by the record's CIGAR op (state >> 16).  A short
+// walk over the ops in front of that segment gives its reference / query offsets and its number; no search.  Same tuple
+// as map_record<2> (the tests compare the two ways array by array).
+template <class RV>
+PHZ_HD void tile_emit_simple(const RV& trv, const int32_t* __restrict__ s_pos, const u32* __restrict__ s_coff,
+                             const u32* __restrict__ s_cig, u32 cig_al, const int32_t* __restrict__ win, u32 wbase,
+                             const u8* __restrict__ a0, const u8* __restrict__ a1, int64_t r0, int i, u32 j, u32 state, int baseq,
+                             u32* t_rec, u32* t_var, u32* t_misc) {
+  const u32 c0 = s_coff[i] - cig_al, c1 = s_coff[i + 1] - cig_al, kseg = c0 + (state >> 16);
+  int32_t gp = 0, qp = 0; int seg = 0;
+  for (u32 x = c0; x < kseg; ++x) {
+    const u32 c = s_cig[x]; const u32 op = c & 15u; const int32_t n = (int32_t)(c >> 4);
+    if (op == OP_M || op == OP_EQ || op == OP_X) { gp += n; qp += n; }
+    else if (op == OP_D) gp += n;
+    else if (op == OP_N) { gp += n; ++seg; }
+    else if (op == OP_I || op == OP_S) qp += n;
+  }
+  const u32 widx = (state & 0xFFFFu) + j;
+  const int64_t vj = (int64_t)wbase + widx;
+  const int32_t st = (int32_t)((int64_t)win[widx] - ((int64_t)s_pos[i] + gp));       // offset in pseudo_read
+  const int64_t r = r0 + i;
+  *t_rec = (u32)r;
+  *t_var = (u32)vj;
+  *t_misc = call_snv_site(trv, a0[vj], a1[vj], cig_al + kseg, cig_al + c1, gp, qp, trv.seq_off_at(r), baseq, st, seg, trv.aln_at(r));
+}
+
+#ifdef __CUDACC__
+constexpr int KT_CIG = 1024;          // CIGAR words staged per tile (4 KB); tiles with more fall back to global loads
+constexpr int KT_OWN = 1024;          // candidate slots with a direct owner entry; beyond that a search over the offsets
+
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, int bytes, unsigned long long* mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
 }
 
 template <int MIN_CTAS, class VV>
@@ -463,7 +498,7 @@ __global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView
                                                             u32* __restrict__ s_rec,
                                                             u32* __restrict__ s_var, u32* __restrict__ s_misc, u64 capacity,
                                                             unsigned long long* cursor, u32* __restrict__ tile_base,
-                                                            u32* __restrict__ tile_cnt) {
+                                                            u32* __restrict__ tile_cnt, int k1_staged_emit) {
   __shared__ __align__(128) int32_t win[KF_WIN];
   __shared__ __align__(128) int32_t sh_pos[KF_THREADS];
   __shared__ __align__(128) int32_t sh_tlen[KF_THREADS];
@@ -475,6 +510,7 @@ __global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView
   __shared__ u32 warp_sum[KF_THREADS / 32];
   __shared__ u32 excl_of[KF_THREADS + 1];
   __shared__ u8 sh_owner[KT_OWN];                     // candidate slot -> record of the tile that owns it
+  __shared__ u32 sh_state[KF_THREADS];                // where the count pass found the record's candidates (tile_count_fast)
   __shared__ unsigned long long s_base;
   __shared__ int64_t s_v01[2];                        // het-site range of the tile's first contig
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -533,7 +569,7 @@ __global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView
   // CIGAR range of the tile is in shared memory and is read unconditionally.
   auto body = [&](auto staged) {
     const TileRV<decltype(staged)::value> trv{r0, sh_pos, sh_tlen, sh_coff, sh_cig, sh_soff, sh_as, cig_al, cig_n, rv.cigar, rv.seq, rv.qual};
-    u32 cnt = 0;
+    u32 cnt = 0, state = EMIT_COMPLEX;
     if (live) {
       bool done = false;
       if constexpr (!VV::kIndels && decltype(staged)::value) {
@@ -546,7 +582,8 @@ __global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView
           else if (a < b) {
             const u32 hn = ti.hint & 0xFFFFu; const int hlo = (int)(ti.hint >> 16);
             done = tile_count_fast(sh_pos, sh_coff, sh_cig, cig_al, tid, win, a, b, (int64_t)ti.wbase + a == s_v01[0],
-                                   (int64_t)ti.wbase + b == s_v01[1], hlo, hn != 0xFFFFu ? hlo + (int)hn : -1, cnt);
+                                   (int64_t)ti.wbase + b == s_v01[1], hlo, hn != 0xFFFFu ? hlo + (int)hn : -1, cnt, state);
+            if (!done) state = EMIT_COMPLEX;
           } else if (s_v01[0] == s_v01[1]) done = true;                           // a contig without het sites
         }
       }
@@ -566,6 +603,8 @@ __global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView
     for (int w = 0; w < KF_THREADS / 32; ++w) { u32 v = warp_sum[w]; if (w < warp) warp_base += v; cta_total += v; }
     const u32 my_excl = warp_base + incl - cnt;
     excl_of[tid] = my_excl;
+    if (k1_staged_emit == 0) state = EMIT_COMPLEX;
+    sh_state[tid] = state;
     for (u32 k = 0; k < cnt && my_excl + k < KT_OWN; ++k) sh_owner[my_excl + k] = (u8)tid;
     if (tid == 0) {
       excl_of[KF_THREADS] = cta_total;
@@ -583,6 +622,14 @@ __global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView
       else {                                            // last record index with excl_of <= i
         lo = 0; int hi = KF_THREADS;
         while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (excl_of[mid] <= i) lo = mid; else hi = mid; }
+      }
+      const u32 stt = sh_state[lo];
+      if constexpr (!VV::kIndels && decltype(staged)::value) {
+        if (stt != EMIT_COMPLEX) {          // the count pass left the candidates' place behind: no second search
+          tile_emit_simple(trv, sh_pos, sh_coff, sh_cig, cig_al, win, ti.wbase, vv.a0, vv.a1, r0, lo, i - excl_of[lo], stt, baseq,
+                           s_rec + base + i, s_var + base + i, s_misc + base + i);
+          continue;
+        }
       }
       const int64_t rr = r0 + lo;
       int c = contig0;
@@ -602,6 +649,7 @@ struct Pipeline {
   bool stats_done = false;
   int k1_min_ctas = 8;        // register budget of the tile kernel: 8 -> 32 regs, 6 -> 40 regs, else unconstrained
   int k1_mode = 3;            // 3: tile kernel + permute (default), 2: fused look-back, 1: windowed two-pass, 0: generic two-pass
+  int k1_staged_emit = 1;     // tile kernel: 1 the dense emission takes the candidates' place from the count pass, 0 it re-derives every candidate
   Buf<B, u32> s_rec, s_var, s_misc, tile_base, tile_cnt, tile_canon;
   Buf<B, TileInfo> tile_info; Buf<B, u64> tile_status; Buf<B, u32> k1_ticket;
   // ------------------------------------------------------------------ variants
@@ -641,7 +689,7 @@ struct Pipeline {
   int graph_mode = 1;               // 1: fragment-table graph stage (phz_graph.h), 0: sort-based stage (A/B switch and fallback)
   int frag_stage = 1;               // fragment kernel of the fragment-table stage: 1 slot chunks staged in shared memory, 0 ranges of fragment ids
   u64 n_frag_deferred = 0;          // fragments of the last graph stage that the slot-chunk kernel left to its second pass
-  Buf<B, u32> frag_deferred;
+  Buf<B, u32> frag_deferred, v_packed;
   bool frag_entries = false;        // which form of the (fragment, variant, BAM) entries the last build_graph left behind
   Buf<B, u32> f_cnt, f_off; Buf<B, uint16_t> t_rank, f_info; Buf<B, u64> f_key, pt_keys, pt_cnt3; Buf<B, u32> pt_vals, pt_flags, pt_slot, rank_flag;
   int64_t n_frag_cur = 0; u64 pair_table_slots = 1ull << 20; int64_t pair_table_grown = 0;
@@ -694,7 +742,7 @@ struct Pipeline {
     rl_flag.bind(b); rl_scan.bind(b); rl_k32.bind(b); rl_k32b.bind(b); rl_t.bind(b); rl_t2.bind(b); rl_k64.bind(b);
     rl_k64b.bind(b); rl_frag.bind(b); rl_var.bind(b); rl_row.bind(b);
     f_cnt.bind(b); f_off.bind(b); t_rank.bind(b); rank_flag.bind(b); f_info.bind(b); f_key.bind(b); pt_keys.bind(b); pt_cnt3.bind(b); pt_vals.bind(b);
-    pt_flags.bind(b); pt_slot.bind(b); frag_deferred.bind(b);
+    pt_flags.bind(b); pt_slot.bind(b); frag_deferred.bind(b); v_packed.bind(b);
   }
 
   u32 fetch_u32(const u32* p) { u32 v = 0; be.d2h(&v, p, sizeof(u32)); return v; }
@@ -765,35 +813,64 @@ struct Pipeline {
     for (int attempt = 0; attempt < 2; ++attempt) {
       u32* sr = s_rec.ensure(cap); u32* sv = s_var.ensure(cap); u32* sm = s_misc.ensure(cap);
       total = 0;
-#ifdef __CUDACC__
-      u64* cur = tile_status.ensure(2); be.memset0(cur, 2 * sizeof(u64));
       // abs(TLEN) <= cutoff with an integer TLEN  <=>  abs(TLEN) <= floor(cutoff)  (read_variant_map.py:35,51; 0 = no gate)
       const int isz_on = isize_cutoff != 0.0 ? 1 : 0;
       const long long isz_floor = !isz_on ? 0 : (isize_cutoff >= 9.0e18 ? (long long)9e18 : (isize_cutoff <= -9.0e18 ? -(long long)9e18 : (long long)std::floor(isize_cutoff)));
+#ifdef __CUDACC__
+      u64* cur = tile_status.ensure(2); be.memset0(cur, 2 * sizeof(u64));
       if constexpr (VV::kIndels)      // the indel instantiation is not register-capped: its string walk would spill at 32 registers
-        k1_tile_kernel<1, VV><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, isz_floor, isz_on, sr, sv, sm, (u64)cap, cur, tb, tc);
+        k1_tile_kernel<1, VV><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, isz_floor, isz_on, sr, sv, sm, (u64)cap, cur, tb, tc, k1_staged_emit);
       else if (k1_min_ctas >= 8)
-        k1_tile_kernel<8, VV><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, isz_floor, isz_on, sr, sv, sm, (u64)cap, cur, tb, tc);
+        k1_tile_kernel<8, VV><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, isz_floor, isz_on, sr, sv, sm, (u64)cap, cur, tb, tc, k1_staged_emit);
       else if (k1_min_ctas >= 6)
-        k1_tile_kernel<6, VV><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, isz_floor, isz_on, sr, sv, sm, (u64)cap, cur, tb, tc);
+        k1_tile_kernel<6, VV><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, isz_floor, isz_on, sr, sv, sm, (u64)cap, cur, tb, tc, k1_staged_emit);
       else
-        k1_tile_kernel<1, VV><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, isz_floor, isz_on, sr, sv, sm, (u64)cap, cur, tb, tc);
+        k1_tile_kernel<1, VV><<<(unsigned)n_tiles, KF_THREADS, 0, be.stream>>>(rv, vv, ti, baseq, isize_cutoff, isz_floor, isz_on, sr, sv, sm, (u64)cap, cur, tb, tc, k1_staged_emit);
       PHZ_CUDA(cudaGetLastError());
       be.launches++;
       be.d2h(&total, cur, sizeof(u64));
 #else
-      // host simulation: same tile descriptors, slab logic and k-th candidate emission, tiles in sequence
+      // host simulation: same tile descriptors, slab logic, count pass and candidate emission (the slabs are the global
+      // arrays themselves), tiles in sequence
       for (int64_t t = 0; t < n_tiles; ++t) {
-        int c0 = (int)(ti[t].contig_wn >> 16);
+        const int c0 = (int)(ti[t].contig_wn >> 16); const int wn = (int)(ti[t].contig_wn & 0xFFFF);
+        const int64_t r0 = t * KF_THREADS;
+        const u32 cig_al = ti[t].cig0 & ~3u;
+        const int32_t* win = vv.pos + ti[t].wbase;
+        const int64_t cv0 = vv.contig_var_off[c0], cv1 = vv.contig_var_off[c0 + 1];
+        const int64_t a64 = cv0 - (int64_t)ti[t].wbase, b64 = cv1 - (int64_t)ti[t].wbase;
+        const int a = a64 > 0 ? (int)a64 : 0, b = b64 < wn ? (int)b64 : wn;
+        const u32 hn = ti[t].hint & 0xFFFFu; const int hlo = (int)(ti[t].hint >> 16);
         u32 tile_total = 0;
-        for (int64_t r = t * KF_THREADS; r < (t + 1) * KF_THREADS && r < R; ++r) {
+        for (int64_t r = r0; r < r0 + KF_THREADS && r < R; ++r) {
           int c = c0;
           if (r >= rv.contig_rec_off[c + 1]) c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r);
-          const WindowVP vp = window_of(ti[t], vv.pos, vv.pos + ti[t].wbase, c == c0);
-          u32 cnt = map_record<0>(rv, vv, vp, r, c, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr);
+          const WindowVP vp = window_of(ti[t], vv.pos, win, c == c0);
+          u32 cnt = 0, state = EMIT_COMPLEX; bool done = false;
+          if constexpr (!VV::kIndels) {
+            if (c == c0) {
+              const int64_t tl = rv.tlen[r]; const int64_t atl = tl < 0 ? -tl : tl;
+              if (isz_on && atl > isz_floor) done = true;
+              else if (a < b) {
+                done = tile_count_fast(rv.pos + r0, rv.cigar_off + r0, rv.cigar + cig_al, cig_al, (int)(r - r0), win, a, b,
+                                       (int64_t)ti[t].wbase + a == cv0, (int64_t)ti[t].wbase + b == cv1, hlo,
+                                       hn != 0xFFFFu ? hlo + (int)hn : -1, cnt, state);
+                if (!done) state = EMIT_COMPLEX;
+              } else if (cv0 == cv1) done = true;
+            }
+          }
+          if (!done) cnt = map_record<0>(rv, vv, vp, r, c, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr);
+          if (k1_staged_emit == 0) state = EMIT_COMPLEX;
           if (total + tile_total + cnt <= cap)
             for (u32 k = 0; k < cnt; ++k) {
               u64 w = total + tile_total + k;
+              if constexpr (!VV::kIndels) {
+                if (state != EMIT_COMPLEX) {
+                  tile_emit_simple(rv, rv.pos + r0, rv.cigar_off + r0, rv.cigar + cig_al, cig_al, win, ti[t].wbase, vv.a0, vv.a1, r0,
+                                   (int)(r - r0), k, state, baseq, sr + w, sv + w, sm + w);
+                  continue;
+                }
+              }
               map_record<2>(rv, vv, vp, r, c, baseq, isize_cutoff, k, sr + w, sv + w, sm + w);
             }
           tile_total += cnt;
@@ -1772,28 +1849,36 @@ struct Pipeline {
     be.memset0(fc, NFmax * 2 * sizeof(u32)); be.memset0(fbc, NFmax * nb * 2 * sizeof(u32));
     const u8* vbl = vblack;
     if (frag_entries) {
-      // entries as the fragment-table stage left them: fragment f owns f_key / f_info [f_off[f], f_off[f] + f_cnt[f])
-      const u32* fo = f_off.p; const u32* fne = f_cnt.p; const u64* fk = f_key.p; const uint16_t* fi = f_info.p;
-      be.for_each(n_frag_cur, PHZ_LAMBDA(int64_t fr) {
-        const u32 ne = fne[fr];
-        if (ne == 0) return;
-        const u32 j0 = fo[fr], j1 = j0 + ne;
-        for (u32 j = j0; j < j1; ++j) {
-          u32 v = (u32)(fk[j] >> 32); u32 f = vfin[v];
-          if (f == NONE32) continue;
-          const u32 mj = fi[j] & 7u, bj = (fi[j] & 0x7FFFu) >> 3;
-          for (int h = 0; h < 2; ++h) {
-            if (!((mj >> (vh[v] ^ h)) & 1)) continue;
-            bool seen_any = false, seen_bam = false;
-            for (u32 i = j0; i < j; ++i) {
-              u32 w = (u32)(fk[i] >> 32);
-              if (vfin[w] != f || !(((fi[i] & 7u) >> (vh[w] ^ h)) & 1)) continue;
-              seen_any = true; if ((u32)((fi[i] & 0x7FFFu) >> 3) == bj && !(vbl && vbl[w])) seen_bam = true;
+      // entries as the fragment-table stage left them, walked by SLOT: every fragment's entries sit at the front of its
+      // slots, the slots behind them carry an empty class mask, the first slot carries the head mark -- one thread per
+      // slot looks back over the earlier entries of its fragment (a handful); neither the fragment table nor the entry
+      // counts are read.  Per site one packed word (final block << 1 | haplotype) instead of two gathers.
+      const u64* fk = f_key.p; const uint16_t* fi = f_info.p;
+      u32* pv = v_packed.ensure(Vn);
+      be.for_each(Vn, PHZ_LAMBDA(int64_t v) { pv[v] = vfin[v] == NONE32 ? NONE32 : ((vfin[v] << 1) | (u32)(vh[v] & 1)); });
+      be.for_each(n_tuples, PHZ_LAMBDA(int64_t j) {
+        const u32 ij = fi[j]; const u32 mj = ij & 7u;
+        if (!mj) return;
+        const u32 v = (u32)(fk[j] >> 32); const u32 pj = pv[v];
+        if (pj == NONE32) return;
+        const u32 f = pj >> 1, hv = pj & 1u, bj = (ij & 0x7FFFu) >> 3;
+        for (u32 h = 0; h < 2; ++h) {
+          if (!((mj >> (hv ^ h)) & 1)) continue;
+          bool seen_any = false, seen_bam = false;
+          if (!(ij & INFO_HEAD))
+            for (int64_t i = j - 1;; --i) {
+              const u32 ii = fi[i]; const u32 mi = ii & 7u;
+              if (mi) {
+                const u32 w = (u32)(fk[i] >> 32); const u32 pw = pv[w];
+                if (pw != NONE32 && (pw >> 1) == f && ((mi >> ((pw & 1u) ^ h)) & 1)) {
+                  seen_any = true; if (((ii & 0x7FFFu) >> 3) == bj && !(vbl && vbl[w])) seen_bam = true;
+                }
+              }
+              if ((ii & INFO_HEAD) || i == 0) break;
             }
-            if (!seen_any) converged_inc(&fc[(int64_t)f * 2 + h]);
-            if (!seen_bam && !((excl_mask >> bj) & 1) && !(vbl && vbl[v]))
-              converged_inc(&fbc[((int64_t)f * nb + bj) * 2 + h]);
-          }
+          if (!seen_any) converged_inc(&fc[(int64_t)f * 2 + h]);
+          if (!seen_bam && !((excl_mask >> bj) & 1) && !(vbl && vbl[v]))
+            converged_inc(&fbc[((int64_t)f * nb + bj) * 2 + h]);
         }
       });
     } else {

@@ -101,15 +101,15 @@ def test_windowed_k1_equals_generic_k1(gpu):
     d = gpu.upload_reads(rb)
     out = {}
     try:
-        for mode in (0, 1, 2, 3):
-            gpu.set_option("k1_mode", mode)
+        for mode in (0, 1, 2, 3, 4):          # 4: the tile kernel with every candidate re-derived by the dense emission
+            gpu.set_option("k1_mode", min(mode, 3)); gpu.set_option("k1_staged_emit", 0 if mode == 4 else 1)
             gpu.set_variants(vt)
             n = gpu.map_reads(d, 10, 0.0)
             out[mode] = (n, gpu.download("t_rec"), gpu.download("t_var"), gpu.download("t_misc"))
     finally:
-        gpu.set_option("k1_mode", 3)
-    assert out[0][0] == out[1][0] == out[2][0] == out[3][0] and out[0][0] > 100000
-    for m in (1, 2, 3):
+        gpu.set_option("k1_mode", 3); gpu.set_option("k1_staged_emit", 1)
+    assert out[0][0] == out[1][0] == out[2][0] == out[3][0] == out[4][0] and out[0][0] > 100000
+    for m in (1, 2, 3, 4):
         for a, b in zip(out[0][1:], out[m][1:]):
             assert np.array_equal(a, b), m
 
@@ -432,8 +432,11 @@ def test_slot_chunk_fragment_kernel_equals_the_range_form(gpu, tmp_path, n_bams,
             gpu.set_option("graph_mode", 1); gpu.set_option("frag_stage", 1)
     a, b, c = out
     assert a.counters["n_tuples"] > 20000 and a.counters["edges"] > 100
+    assert a.counters == b.counters
     for x in (b, c):
-        assert a.counters == x.counters
+        for k in ("n_tuples", "entries", "groups", "pairs", "distinct_pairs", "edges", "dropped", "members", "final_blocks",
+                  "read_list_entries"):
+            assert a.counters[k] == x.counters[k], k
         for k in a.arrays:
             assert np.array_equal(a.arrays[k], x.arrays[k]), k
 

@@ -65,15 +65,15 @@ def test_windowed_k1_logic_equals_generic(hostsim):
     d = hostsim.upload_reads(rb)
     out = {}
     try:
-        for mode in (0, 1, 2, 3):
-            hostsim.set_option("k1_mode", mode)
+        for mode in (0, 1, 2, 3, 4):          # 4: the tile path with every candidate re-derived by the emission
+            hostsim.set_option("k1_mode", min(mode, 3)); hostsim.set_option("k1_staged_emit", 0 if mode == 4 else 1)
             hostsim.set_variants(vt)
             n = hostsim.map_reads(d, 10, 0.0)
             out[mode] = (n, hostsim.download("t_rec"), hostsim.download("t_var"), hostsim.download("t_misc"))
     finally:
-        hostsim.set_option("k1_mode", 3)
-    assert out[0][0] == out[1][0] == out[2][0] == out[3][0] and out[0][0] > 5000
-    for m in (1, 2, 3):
+        hostsim.set_option("k1_mode", 3); hostsim.set_option("k1_staged_emit", 1)
+    assert out[0][0] == out[1][0] == out[2][0] == out[3][0] == out[4][0] and out[0][0] > 5000
+    for m in (1, 2, 3, 4):
         for a, b in zip(out[0][1:], out[m][1:]):
             assert np.array_equal(a, b), m
 
