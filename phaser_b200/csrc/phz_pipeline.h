@@ -273,9 +273,15 @@ __global__ void __launch_bounds__(K1_THREADS) k1_window_kernel(ReadsView rv, Var
 // variant) order, without a second kernel, without per-record count/offset arrays in HBM.
 constexpr int KF_THREADS = 256;
 constexpr int KF_WIN = 1024;                      // het-site positions per slab (4 KB)
+constexpr int KT_CIG = 1024;                      // CIGAR words staged per tile of the tile kernel (4 KB); tiles with more fall back to global loads
 constexpr u64 KF_FLAG_AGG = 1ull << 62, KF_FLAG_PREFIX = 2ull << 62, KF_VALUE_MASK = (1ull << 62) - 1;
 
-struct TileInfo { u32 wbase; u32 contig_wn; u32 hint; u32 cig0; };    // contig << 16 | wn ; hint_lo << 16 | bracket length (0xFFFF = none) ; first CIGAR word of the tile
+// contig << 16 | wn ; hint_lo << 16 | bracket length (0xFFFF = none) ; first CIGAR word of the tile ; the sites of the
+// tile's first contig inside the slab are slab[a, b): a | b << 16 ; geo bit 0: slab[a] is the contig's first site, bit 1:
+// slab[b - 1] its last, bit 2: the contig has no site at all (tile-uniform geometry the tile kernel would otherwise
+// re-derive per thread in 64-bit arithmetic)
+// ; rec_cig: records of the tile | CIGAR words staged for it << 16 ; n_first: its records on the first contig
+struct alignas(16) TileInfo { u32 wbase; u32 contig_wn; u32 hint; u32 cig0; u32 ab; u32 geo; u32 rec_cig; u32 n_first; };
 
 PHZ_HD TileInfo tile_info_for(const ReadsView& rv, const VariantsView& vv, int64_t r0) {
   int c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r0);
@@ -293,6 +299,14 @@ PHZ_HD TileInfo tile_info_for(const ReadsView& rv, const VariantsView& vv, int64
   int64_t hint_lo = wlo - wbase, nfirst = wlast - wlo;
   TileInfo ti; ti.wbase = (u32)wbase; ti.contig_wn = ((u32)c << 16) | (u32)wn; ti.cig0 = rv.cigar_off[r0];
   ti.hint = (hint_lo + nfirst <= wn && nfirst < 0xFFFF) ? (((u32)hint_lo << 16) | (u32)nfirst) : 0xFFFFu;
+  const int64_t a64 = v0 - wbase, b64 = v1 - wbase;
+  const int64_t a = a64 > 0 ? a64 : 0, b = b64 < wn ? b64 : wn;
+  ti.ab = (u32)(a < b ? a : 0) | ((u32)(a < b ? b : 0) << 16);
+  ti.geo = ((a < b && wbase + a == v0) ? 1u : 0u) | ((a < b && wbase + b == v1) ? 2u : 0u) | (v0 == v1 ? 4u : 0u);
+  const int64_t nrec = (rv.n_records - r0) < KF_THREADS ? (rv.n_records - r0) : KF_THREADS;
+  const int64_t cig_left = rv.n_cigar_ops - (int64_t)(ti.cig0 & ~3u);
+  ti.rec_cig = (u32)nrec | ((u32)(cig_left < KT_CIG ? cig_left : KT_CIG) << 16);
+  ti.n_first = (u32)(r_last - r0 + 1);
   return ti;
 }
 
@@ -484,7 +498,6 @@ PHZ_HD void tile_emit_simple(const RV& trv, const int32_t* __restrict__ s_pos, c
 }
 
 #ifdef __CUDACC__
-constexpr int KT_CIG = 1024;          // CIGAR words staged per tile (4 KB); tiles with more fall back to global loads
 constexpr int KT_OWN = 1024;          // candidate slots with a direct owner entry; beyond that a search over the offsets
 
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, int bytes, unsigned long long* mbar) {
@@ -512,17 +525,19 @@ __global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView
   __shared__ u8 sh_owner[KT_OWN];                     // candidate slot -> record of the tile that owns it
   __shared__ u32 sh_state[KF_THREADS];                // where the count pass found the record's candidates (tile_count_fast)
   __shared__ unsigned long long s_base;
-  __shared__ int64_t s_v01[2];                        // het-site range of the tile's first contig
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t tile = blockIdx.x;
   const TileInfo ti = tiles[tile];
   const int wn = (int)(ti.contig_wn & 0xFFFF);
+  // abs(TLEN) fits 32 unsigned bits: a floor beyond that never gates, a negative one gates everything but is kept exact
+  const u32 isize_floor32 = isize_floor >= 0xFFFFFFFFll ? 0xFFFFFFFFu : (isize_floor < 0 ? 0u : (u32)isize_floor);
+  if (isize_floor >= 0xFFFFFFFFll) isize_on = 0;
   const int64_t r0 = tile * KF_THREADS;
-  const int nrec = (int)((rv.n_records - r0) < KF_THREADS ? (rv.n_records - r0) : KF_THREADS);
+  const int nrec = (int)(ti.rec_cig & 0xFFFFu);
   // CIGAR slab: words [cig_al, cig_al + cig_n) with a 16-byte aligned start
   const u32 cig_al = ti.cig0 & ~3u;
-  int64_t cig_left = rv.n_cigar_ops - (int64_t)cig_al;
-  const u32 cig_n = (u32)(cig_left < KT_CIG ? cig_left : KT_CIG);
+  const u32 cig_n = ti.rec_cig >> 16;
+  const bool gate_all = isize_on && isize_floor < 0;       // abs(TLEN) <= a negative cutoff: never
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -548,15 +563,13 @@ __global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView
     for (int i = n2; i < nrec; ++i) sh_soff[i] = rv.seq_off[r0 + i];
     for (int i = n8; i < nrec; ++i) sh_as[i] = rv.aln_score[r0 + i];
     s_base = (unsigned long long)bytes;
-    const int c0 = (int)(ti.contig_wn >> 16);
-    s_v01[0] = vv.contig_var_off[c0]; s_v01[1] = vv.contig_var_off[c0 + 1];
   }
   const int64_t r = r0 + tid;
   const bool live = tid < nrec;
   const int contig0 = (int)(ti.contig_wn >> 16);
-  const int64_t contig0_end = rv.contig_rec_off[contig0 + 1];
+  const int n_first = (int)ti.n_first;                 // records [0, n_first) of the tile lie on its first contig
   int contig = contig0;
-  if (live && r >= contig0_end) contig = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r);
+  if (live && tid >= n_first) contig = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, r);
   __syncthreads();                                   // mbarrier initialised, tail elements visible
   if (s_base > 0) {
     u32 done = 0;
@@ -574,17 +587,16 @@ __global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView
       bool done = false;
       if constexpr (!VV::kIndels && decltype(staged)::value) {
         if (contig == contig0) {
-          // tile-uniform slab geometry: the contig's sites inside the slab are win[a, b)
-          const int64_t a64 = s_v01[0] - (int64_t)ti.wbase, b64 = s_v01[1] - (int64_t)ti.wbase;
-          const int a = a64 > 0 ? (int)a64 : 0, b = b64 < wn ? (int)b64 : wn;
-          int32_t tl = sh_tlen[tid]; const int64_t atl = tl < 0 ? -(int64_t)tl : (int64_t)tl;
-          if (isize_on && atl > isize_floor) done = true;                        // read_variant_map.py:35,51
+          // tile-uniform slab geometry (from the pre-pass): the contig's sites inside the slab are win[a, b)
+          const int a = (int)(ti.ab & 0xFFFFu), b = (int)(ti.ab >> 16);
+          const int32_t tl = sh_tlen[tid]; const u32 atl = tl < 0 ? 0u - (u32)tl : (u32)tl;
+          if (isize_on && (gate_all || atl > isize_floor32)) done = true;        // read_variant_map.py:35,51
           else if (a < b) {
             const u32 hn = ti.hint & 0xFFFFu; const int hlo = (int)(ti.hint >> 16);
-            done = tile_count_fast(sh_pos, sh_coff, sh_cig, cig_al, tid, win, a, b, (int64_t)ti.wbase + a == s_v01[0],
-                                   (int64_t)ti.wbase + b == s_v01[1], hlo, hn != 0xFFFFu ? hlo + (int)hn : -1, cnt, state);
+            done = tile_count_fast(sh_pos, sh_coff, sh_cig, cig_al, tid, win, a, b, (ti.geo & 1u) != 0, (ti.geo & 2u) != 0, hlo,
+                                   hn != 0xFFFFu ? hlo + (int)hn : -1, cnt, state);
             if (!done) state = EMIT_COMPLEX;
-          } else if (s_v01[0] == s_v01[1]) done = true;                           // a contig without het sites
+          } else if (ti.geo & 4u) done = true;                                    // a contig without het sites
         }
       }
       if (!done) {
@@ -598,9 +610,11 @@ __global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView
     for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
     if (lane == 31) warp_sum[warp] = incl;
     __syncthreads();
-    u32 warp_base = 0, cta_total = 0;
+    static_assert(KF_THREADS / 32 == 8, "the warp sums are scanned by three shuffle steps");
+    u32 wv = lane < KF_THREADS / 32 ? warp_sum[lane] : 0u, wi = wv;
     #pragma unroll
-    for (int w = 0; w < KF_THREADS / 32; ++w) { u32 v = warp_sum[w]; if (w < warp) warp_base += v; cta_total += v; }
+    for (int o = 1; o < KF_THREADS / 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+    const u32 warp_base = __shfl_sync(0xffffffffu, wi - wv, warp), cta_total = __shfl_sync(0xffffffffu, wi, KF_THREADS / 32 - 1);
     const u32 my_excl = warp_base + incl - cnt;
     excl_of[tid] = my_excl;
     if (k1_staged_emit == 0) state = EMIT_COMPLEX;
@@ -633,7 +647,7 @@ __global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView
       }
       const int64_t rr = r0 + lo;
       int c = contig0;
-      if (rr >= contig0_end) c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, rr);
+      if (lo >= n_first) c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, rr);
       const WindowVP vpk = window_of(ti, vv.pos, win, c == contig0);
       map_record<2>(trv, vv, vpk, rr, c, baseq, isize_cutoff, (u64)(i - excl_of[lo]), s_rec + base + i, s_var + base + i,
                     s_misc + base + i);
@@ -689,7 +703,7 @@ struct Pipeline {
   int graph_mode = 1;               // 1: fragment-table graph stage (phz_graph.h), 0: sort-based stage (A/B switch and fallback)
   int frag_stage = 1;               // fragment kernel of the fragment-table stage: 1 slot chunks staged in shared memory, 0 ranges of fragment ids
   u64 n_frag_deferred = 0;          // fragments of the last graph stage that the slot-chunk kernel left to its second pass
-  Buf<B, u32> frag_deferred, v_packed;
+  Buf<B, u32> frag_deferred, v_packed, v_rank_in_final;
   bool frag_entries = false;        // which form of the (fragment, variant, BAM) entries the last build_graph left behind
   Buf<B, u32> f_cnt, f_off; Buf<B, uint16_t> t_rank, f_info; Buf<B, u64> f_key, pt_keys, pt_cnt3; Buf<B, u32> pt_vals, pt_flags, pt_slot, rank_flag;
   int64_t n_frag_cur = 0; u64 pair_table_slots = 1ull << 20; int64_t pair_table_grown = 0;
@@ -742,7 +756,7 @@ struct Pipeline {
     rl_flag.bind(b); rl_scan.bind(b); rl_k32.bind(b); rl_k32b.bind(b); rl_t.bind(b); rl_t2.bind(b); rl_k64.bind(b);
     rl_k64b.bind(b); rl_frag.bind(b); rl_var.bind(b); rl_row.bind(b);
     f_cnt.bind(b); f_off.bind(b); t_rank.bind(b); rank_flag.bind(b); f_info.bind(b); f_key.bind(b); pt_keys.bind(b); pt_cnt3.bind(b); pt_vals.bind(b);
-    pt_flags.bind(b); pt_slot.bind(b); frag_deferred.bind(b); v_packed.bind(b);
+    pt_flags.bind(b); pt_slot.bind(b); frag_deferred.bind(b); v_packed.bind(b); v_rank_in_final.bind(b);
   }
 
   u32 fetch_u32(const u32* p) { u32 v = 0; be.d2h(&v, p, sizeof(u32)); return v; }
@@ -833,13 +847,11 @@ struct Pipeline {
       // host simulation: same tile descriptors, slab logic, count pass and candidate emission (the slabs are the global
       // arrays themselves), tiles in sequence
       for (int64_t t = 0; t < n_tiles; ++t) {
-        const int c0 = (int)(ti[t].contig_wn >> 16); const int wn = (int)(ti[t].contig_wn & 0xFFFF);
+        const int c0 = (int)(ti[t].contig_wn >> 16);
         const int64_t r0 = t * KF_THREADS;
         const u32 cig_al = ti[t].cig0 & ~3u;
         const int32_t* win = vv.pos + ti[t].wbase;
-        const int64_t cv0 = vv.contig_var_off[c0], cv1 = vv.contig_var_off[c0 + 1];
-        const int64_t a64 = cv0 - (int64_t)ti[t].wbase, b64 = cv1 - (int64_t)ti[t].wbase;
-        const int a = a64 > 0 ? (int)a64 : 0, b = b64 < wn ? (int)b64 : wn;
+        const int a = (int)(ti[t].ab & 0xFFFFu), b = (int)(ti[t].ab >> 16);
         const u32 hn = ti[t].hint & 0xFFFFu; const int hlo = (int)(ti[t].hint >> 16);
         u32 tile_total = 0;
         for (int64_t r = r0; r < r0 + KF_THREADS && r < R; ++r) {
@@ -853,10 +865,10 @@ struct Pipeline {
               if (isz_on && atl > isz_floor) done = true;
               else if (a < b) {
                 done = tile_count_fast(rv.pos + r0, rv.cigar_off + r0, rv.cigar + cig_al, cig_al, (int)(r - r0), win, a, b,
-                                       (int64_t)ti[t].wbase + a == cv0, (int64_t)ti[t].wbase + b == cv1, hlo,
+                                       (ti[t].geo & 1u) != 0, (ti[t].geo & 2u) != 0, hlo,
                                        hn != 0xFFFFu ? hlo + (int)hn : -1, cnt, state);
                 if (!done) state = EMIT_COMPLEX;
-              } else if (cv0 == cv1) done = true;
+              } else if (ti[t].geo & 4u) done = true;
             }
           }
           if (!done) cnt = map_record<0>(rv, vv, vp, r, c, baseq, isize_cutoff, 0, nullptr, nullptr, nullptr);
@@ -1848,14 +1860,20 @@ struct Pipeline {
     u32* fc = fb_cnt.ensure(NFmax * 2); u32* fbc = fb_bcnt.ensure(NFmax * nb * 2);
     be.memset0(fc, NFmax * 2 * sizeof(u32)); be.memset0(fbc, NFmax * nb * 2 * sizeof(u32));
     const u8* vbl = vblack;
+    // per site: final block << 1 | haplotype in ONE word (NONE32 outside the final blocks), and the site's rank inside
+    // its final block -- what the haplotypic counts and the read lists would otherwise gather from three arrays
+    u32* pv = v_packed.ensure(Vn); u32* pr = v_rank_in_final.ensure(Vn);
+    be.for_each(Vn, PHZ_LAMBDA(int64_t v) {
+      const u32 f = vfin[v];
+      pv[v] = f == NONE32 ? NONE32 : ((f << 1) | (u32)(vh[v] & 1));
+      pr[v] = f == NONE32 ? 0u : vmi[v] - ff[f];
+    });
     if (frag_entries) {
       // entries as the fragment-table stage left them, walked by SLOT: every fragment's entries sit at the front of its
       // slots, the slots behind them carry an empty class mask, the first slot carries the head mark -- one thread per
       // slot looks back over the earlier entries of its fragment (a handful); neither the fragment table nor the entry
       // counts are read.  Per site one packed word (final block << 1 | haplotype) instead of two gathers.
       const u64* fk = f_key.p; const uint16_t* fi = f_info.p;
-      u32* pv = v_packed.ensure(Vn);
-      be.for_each(Vn, PHZ_LAMBDA(int64_t v) { pv[v] = vfin[v] == NONE32 ? NONE32 : ((vfin[v] << 1) | (u32)(vh[v] & 1)); });
       be.for_each(n_tuples, PHZ_LAMBDA(int64_t j) {
         const u32 ij = fi[j]; const u32 mj = ij & 7u;
         if (!mj) return;
@@ -1916,14 +1934,19 @@ struct Pipeline {
   int64_t read_lists(u64 excl_mask) {
     const int64_t n = n_tuples; const int nb = n_bams > 0 ? n_bams : 1; const int vb = vbits;
     const u32* gf = g_frag.p; const u32* gv = g_var.p; const u8* gc = g_cb.p; const u32* vfin = v_final.p; const u8* vh = v_hap.p;
-    u32* rf = rl_flag.ensure(n + 1); u32* rsn = rl_scan.ensure(n + 2);
+    u32* rsn = rl_scan.ensure(n + 2);
     const u8* vbl = vblack;
+    const u32* pv = v_packed.p; const u32* pr = v_rank_in_final.p;
     be.stage("read_lists");
-    be.for_each(n, PHZ_LAMBDA(int64_t t) {
-      u32 cls = gc[t] & 3; u32 bam = gc[t] >> 2;
-      rf[t] = (cls < 2 && vfin[gv[t]] != NONE32 && !((excl_mask >> bam) & 1) && !(vbl && vbl[gv[t]])) ? 1u : 0u;
-    });
-    be.exclusive_scan_u32(rf, rsn, n);
+    // a tuple is listed iff it is a reference / alternative call of a counted BAM at a site inside a final block; the test
+    // is evaluated inside the scan and again by the pass that writes the keys (no flag array)
+    auto listed = PHZ_LAMBDA(int64_t t) -> u32 {
+      const u32 c = gc[t];
+      if ((c & 3u) >= 2u || ((excl_mask >> (c >> 2)) & 1)) return 0u;
+      const u32 v = gv[t];
+      return (pv[v] != NONE32 && !(vbl && vbl[v])) ? 1u : 0u;
+    };
+    be.exclusive_scan_fn_u32(listed, rsn, n);
     NRL = n > 0 ? (int64_t)fetch_u32(rsn + n) : 0;
     u32* k32 = rl_k32.ensure(NRL); u32* k32b = rl_k32b.ensure(NRL); u32* tt = rl_t.ensure(NRL); u32* tt2 = rl_t2.ensure(NRL);
     int bb = ceil_log2_host((u64)(nb > 1 ? nb : 2));
@@ -1934,17 +1957,16 @@ struct Pipeline {
     int shift = 0;
     if (fbits + bb + 1 + rbits <= 32 && !two_pass_read_lists) {
       // one sort: key = (block, BAM, haplotype, rank of the variant inside its block); tuple order kept by stability
-      const u32* ff = fb_first.p; const u32* vmi = v_member.p;
       be.for_each(n, PHZ_LAMBDA(int64_t t) {
-        if (!rf[t]) return;
-        u32 v = gv[t]; u32 f = vfin[v]; u32 hap = (gc[t] & 3) ^ vh[v];
-        u32 row = (((f << bb) | (u32)(gc[t] >> 2)) << 1) | hap;
-        k32[rsn[t]] = (row << rbits) | (vmi[v] - ff[f]); tt2[rsn[t]] = (u32)t;
+        if (!listed(t)) return;
+        const u32 v = gv[t]; const u32 p = pv[v]; const u32 c = gc[t];
+        const u32 row = ((((p >> 1) << bb) | (c >> 2)) << 1) | ((c & 3u) ^ (p & 1u));
+        k32[rsn[t]] = (row << rbits) | pr[v]; tt2[rsn[t]] = (u32)t;
       });
       be.sort_pairs32(k32, k32b, tt2, tt, NRL, 0, fbits + bb + 1 + rbits);
       shift = rbits;
     } else {
-      be.for_each(n, PHZ_LAMBDA(int64_t t) { if (rf[t]) { k32[rsn[t]] = gv[t]; tt[rsn[t]] = (u32)t; } });
+      be.for_each(n, PHZ_LAMBDA(int64_t t) { if (listed(t)) { k32[rsn[t]] = gv[t]; tt[rsn[t]] = (u32)t; } });
       be.sort_pairs32(k32, k32b, tt, tt2, NRL, 0, vb);          // by variant, tuple order kept
       be.for_each(NRL, PHZ_LAMBDA(int64_t i) {
         u32 t = tt2[i]; u32 v = gv[t]; u32 hap = (gc[t] & 3) ^ vh[v];
