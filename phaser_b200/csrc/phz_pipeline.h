@@ -1315,18 +1315,23 @@ struct Pipeline {
       // ---- non-empty slots = distinct pairs; eligible ones (phaser.py:667-678) become edges, sorted by (va, vb)
       u32* xf = x_flag.ensure(S + 1); u32* xs = x_scan.ensure(S + 2);
       be.for_each((int64_t)S, PHZ_LAMBDA(int64_t h) {
-        const bool used = pk[h] != PAIR_EMPTY;
+        const u64 key = pk[h];
+        const bool used = key != PAIR_EMPTY;
         if (used) atomic_add(&pf[1], 1u);
-        xf[h] = (used && pv[h * PAIR_CELLS + 9]) ? 1u : 0u;
+        const bool edge = used && pv[h * PAIR_CELLS + 9];
+        xf[h] = edge ? 1u : 0u;
+        // the two sites of a pair are neighbours: the largest index difference sizes the sort key of the edge table
+        if (edge) { const u32 d = (u32)key - (u32)(key >> 32); if (d > load_volatile(&pf[2])) atomic_max(&pf[2], d); }
       });
       be.exclusive_scan_u32(xf, xs, (int64_t)S);
       // ONE wait for everything the host needs from the stage so far: table-full flag, distinct pairs, edges, the ranking
       // pass's verdict, and the entry / group / pair totals
       { const u32* xs_c = xs; int64_t ss = (int64_t)S;
-        be.for_each(1, PHZ_LAMBDA(int64_t) { c3[3] = pf[0]; c3[4] = pf[1]; c3[5] = xs_c[ss]; c3[6] = sc[1]; }); }
+        be.for_each(1, PHZ_LAMBDA(int64_t) { c3[3] = pf[0]; c3[4] = pf[1]; c3[5] = xs_c[ss]; c3[6] = sc[1] | ((u64)pf[2] << 32); }); }
       u64 h7[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       be.d2h(h7, c3, sizeof(h7));
       n_frag_deferred = h7[7];
+      const int dbits = ceil_log2_host((h7[6] >> 32) + 1) > 0 ? ceil_log2_host((h7[6] >> 32) + 1) : 1;
       if (h7[6] & 8u) return false;            // a fragment beyond the 16-bit rank: sort-based stage
       if (h7[3] & 1u) {                        // pair table full: grow it and run the fragments again
         if (attempt >= 8) throw PhzError("pair table keeps overflowing");
@@ -1338,8 +1343,12 @@ struct Pipeline {
       NE = (int64_t)h7[0]; NG = (int64_t)h7[1]; NP = (int64_t)h7[2];
       // ---- edge table
       u64* ek = d_key.ensure(E); u64* ek2 = d_key2.ensure(E); u32* es = pt_slot.ensure(2 * E + 2); u32* es2 = es + E + 1;
-      be.for_each((int64_t)S, PHZ_LAMBDA(int64_t h) { if (xf[h]) { ek[xs[h]] = pk[h]; es[xs[h]] = (u32)h; } });
-      be.sort_pairs(ek, ek2, es, es2, E, 0, 32 + vbits);
+      // sort key: first site << dbits | index difference (vbits + dbits bits: four radix passes instead of seven)
+      const u64 dmask = (((u64)1) << dbits) - 1;
+      be.for_each((int64_t)S, PHZ_LAMBDA(int64_t h) {
+        if (xf[h]) { const u64 key = pk[h]; ek[xs[h]] = ((key >> 32) << dbits) | (u64)((u32)key - (u32)(key >> 32)); es[xs[h]] = (u32)h; }
+      });
+      be.sort_pairs(ek, ek2, es, es2, E, 0, vbits + dbits);
       u32* ea_ = ed_a.ensure(E); u32* eb_ = ed_b.ensure(E); u32* esup = ed_sup.ensure(E); u32* etot = ed_tot.ensure(E);
       u32* en9 = ed_n9.ensure(E * 9); u8* ecfg = ed_cfg.ensure(E); ed_keep.ensure(E);
       be.memset0(sc, 8 * sizeof(u32));
@@ -1347,7 +1356,7 @@ struct Pipeline {
       be.for_each(E, PHZ_LAMBDA(int64_t e) {
         const u64 key = ek2[e]; const u32 h = es2[e];
         u32 n9[9]; for (int c = 0; c < 9; ++c) n9[c] = pv[(int64_t)h * PAIR_CELLS + c];
-        ea_[e] = (u32)(key >> 32); eb_[e] = (u32)key;
+        ea_[e] = (u32)(key >> dbits); eb_[e] = (u32)(key >> dbits) + (u32)(key & dmask);
         for (int c = 0; c < 9; ++c) en9[e * 9 + c] = n9[c];
         u32 cis = n9[0] + n9[4], trans = n9[3] + n9[1];          // n[x][y] at x*3+y
         u32 other = n9[6] + n9[7] + n9[2] + n9[5] + n9[8];
@@ -1934,20 +1943,33 @@ struct Pipeline {
   int64_t read_lists(u64 excl_mask) {
     const int64_t n = n_tuples; const int nb = n_bams > 0 ? n_bams : 1; const int vb = vbits;
     const u32* gf = g_frag.p; const u32* gv = g_var.p; const u8* gc = g_cb.p; const u32* vfin = v_final.p; const u8* vh = v_hap.p;
-    u32* rsn = rl_scan.ensure(n + 2);
     const u8* vbl = vblack;
     const u32* pv = v_packed.p; const u32* pr = v_rank_in_final.p;
     be.stage("read_lists");
-    // a tuple is listed iff it is a reference / alternative call of a counted BAM at a site inside a final block; the test
-    // is evaluated inside the scan and again by the pass that writes the keys (no flag array)
-    auto listed = PHZ_LAMBDA(int64_t t) -> u32 {
+    // a tuple is listed iff it is a reference / alternative call of a counted BAM at a site inside a final block.  The
+    // selection keeps tuple order without a per-tuple flag or offset array: one warp per tile of RL_TILE tuples counts its
+    // listed tuples, a scan over the tile counts places the tiles, and the same warps write their keys in order
+    // (ballot prefix) -- the test is evaluated twice, its one gather is the packed per-site word.
+    auto listed = PHZ_LAMBDA(int64_t t) -> bool {
       const u32 c = gc[t];
-      if ((c & 3u) >= 2u || ((excl_mask >> (c >> 2)) & 1)) return 0u;
+      if ((c & 3u) >= 2u || ((excl_mask >> (c >> 2)) & 1)) return false;
       const u32 v = gv[t];
-      return (pv[v] != NONE32 && !(vbl && vbl[v])) ? 1u : 0u;
+      return pv[v] != NONE32 && !(vbl && vbl[v]);
     };
-    be.exclusive_scan_fn_u32(listed, rsn, n);
-    NRL = n > 0 ? (int64_t)fetch_u32(rsn + n) : 0;
+    constexpr int64_t RL_TILE = 1024;
+    const int64_t n_rt = (n + RL_TILE - 1) / RL_TILE;
+    u32* tcn = rl_flag.ensure(n_rt + 1); u32* tof = rl_scan.ensure(n_rt + 2);
+    be.for_each_warp(n_rt, PHZ_LAMBDA_WARP(int64_t tile, int lane, int nlanes) {
+      const int64_t t0 = tile * RL_TILE, t1 = t0 + RL_TILE < n ? t0 + RL_TILE : n;
+      u32 k = 0;
+      for (int64_t i0 = t0; i0 < t1; i0 += nlanes) {
+        const int64_t t = i0 + lane;
+        k += popc_u32(warp_ballot(t < t1 && listed(t)));
+      }
+      if (lane == 0) tcn[tile] = k;
+    });
+    be.exclusive_scan_u32(tcn, tof, n_rt);
+    NRL = n_rt > 0 ? (int64_t)fetch_u32(tof + n_rt) : 0;
     u32* k32 = rl_k32.ensure(NRL); u32* k32b = rl_k32b.ensure(NRL); u32* tt = rl_t.ensure(NRL); u32* tt2 = rl_t2.ensure(NRL);
     int bb = ceil_log2_host((u64)(nb > 1 ? nb : 2));
     int fbits = ceil_log2_host((u64)(NF > 1 ? NF : 2));
@@ -1955,18 +1977,34 @@ struct Pipeline {
     const int rbits = ceil_log2_host((u64)max_final_len + 1) > 0 ? ceil_log2_host((u64)max_final_len + 1) : 1;
     const u32* kres = k32b;
     int shift = 0;
-    if (fbits + bb + 1 + rbits <= 32 && !two_pass_read_lists) {
-      // one sort: key = (block, BAM, haplotype, rank of the variant inside its block); tuple order kept by stability
-      be.for_each(n, PHZ_LAMBDA(int64_t t) {
-        if (!listed(t)) return;
-        const u32 v = gv[t]; const u32 p = pv[v]; const u32 c = gc[t];
-        const u32 row = ((((p >> 1) << bb) | (c >> 2)) << 1) | ((c & 3u) ^ (p & 1u));
-        k32[rsn[t]] = (row << rbits) | pr[v]; tt2[rsn[t]] = (u32)t;
-      });
+    const bool one_sort = fbits + bb + 1 + rbits <= 32 && !two_pass_read_lists;
+    // one sort: key = (block, BAM, haplotype, rank of the variant inside its block), tuple order kept by stability;
+    // otherwise first by variant, then by (block, BAM, haplotype)
+    u32* tsel = one_sort ? tt2 : tt;
+    be.for_each_warp(n_rt, PHZ_LAMBDA_WARP(int64_t tile, int lane, int nlanes) {
+      const int64_t t0 = tile * RL_TILE, t1 = t0 + RL_TILE < n ? t0 + RL_TILE : n;
+      u32 o = tof[tile];
+      for (int64_t i0 = t0; i0 < t1; i0 += nlanes) {
+        const int64_t t = i0 + lane;
+        const bool keep = t < t1 && listed(t);
+        const u32 bal = warp_ballot(keep);
+        if (keep) {
+          const u32 w = o + popc_u32(bal & ((1u << lane) - 1u));
+          const u32 v = gv[t];
+          if (one_sort) {
+            const u32 p = pv[v]; const u32 c = gc[t];
+            const u32 row = ((((p >> 1) << bb) | (c >> 2)) << 1) | ((c & 3u) ^ (p & 1u));
+            k32[w] = (row << rbits) | pr[v];
+          } else k32[w] = v;
+          tsel[w] = (u32)t;
+        }
+        o += popc_u32(bal);
+      }
+    });
+    if (one_sort) {
       be.sort_pairs32(k32, k32b, tt2, tt, NRL, 0, fbits + bb + 1 + rbits);
       shift = rbits;
     } else {
-      be.for_each(n, PHZ_LAMBDA(int64_t t) { if (listed(t)) { k32[rsn[t]] = gv[t]; tt[rsn[t]] = (u32)t; } });
       be.sort_pairs32(k32, k32b, tt, tt2, NRL, 0, vb);          // by variant, tuple order kept
       be.for_each(NRL, PHZ_LAMBDA(int64_t i) {
         u32 t = tt2[i]; u32 v = gv[t]; u32 hap = (gc[t] & 3) ^ vh[v];
