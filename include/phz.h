@@ -123,6 +123,20 @@ typedef struct phz_packed_reads {
   int32_t qual_bits;               /* 1, 2, 4 or 8 */
   uint8_t qual_table[256];         /* index -> phred */
   const uint8_t* qualp;            /* (n_bases*qual_bits+7)/8 bytes; base i at bit i*qual_bits, little-endian */
+  /* fragment ids.  frag_bits 32: `frag` holds them.  frag_bits 16 (`frag` is NULL): ids numbered by first appearance
+   * (what the ingest assigns) are implicit -- bit r of frag_first set = record r opens the next new id, i.e.
+   * frag_base + (set bits before r); a record with a clear bit refers back to an open fragment (its mate, a
+   * secondary line) with a 16-bit distance: id = frag_base + (set bits before r) - frag_back[k], k = the record's rank
+   * among the clear bits.  Any record whose id does not follow from this is listed in the exception arrays (ascending
+   * record index), which win.  Lossless for ANY id sequence; the packer takes it when it is the smaller form. */
+  int32_t frag_bits;
+  uint32_t frag_base;
+  const uint32_t* frag_first;      /* (n_records+31)/32 words */
+  int64_t n_frag_back;             /* records with a clear bit */
+  const uint16_t* frag_back;
+  int64_t n_frag_exc;
+  const uint32_t* frag_exc_index;
+  const uint32_t* frag_exc_value;
 } phz_packed_reads;
 typedef struct phz_packed_host phz_packed_host;
 /* Packs HOST arrays on n_threads host threads.  page_locked != 0: the output lives in page-locked memory (worth its

@@ -14,7 +14,8 @@ struct TransportSlot {
   // the packed fields as they arrive (include/phz.h: phz_packed_reads)
   Buf<PHZ_BACKEND, uint16_t> pos_d, lsq; Buf<PHZ_BACKEND, int16_t> tl16, as_tab; Buf<PHZ_BACKEND, u32> pos_xi, tl_xi, cig_tab;
   Buf<PHZ_BACKEND, int32_t> pos_xv, tl_xv; Buf<PHZ_BACKEND, u8> as_raw, ncg, cig_raw, seq2, qualp, exc, qtab; Buf<PHZ_BACKEND, u64> exi;
-  Buf<PHZ_BACKEND, u32> frag;       // copied as it is; read again by phz_commit_bam
+  Buf<PHZ_BACKEND, u32> frag;       // the ids (copied as they are, or rebuilt from the implicit coding); read again by phz_commit_bam
+  Buf<PHZ_BACKEND, u32> frag_fb, frag_xi, frag_xv; Buf<PHZ_BACKEND, uint16_t> frag_bk;      // implicit coding (phz.h: frag_first / frag_back)
   const void* tag = nullptr;      // host buffer the staged copy came from
   bool staged = false;
   u64 seq = 0;
@@ -22,7 +23,7 @@ struct TransportSlot {
   void bind(PHZ_BACKEND* b) {
     pos_d.bind(b); lsq.bind(b); tl16.bind(b); as_tab.bind(b); pos_xi.bind(b); tl_xi.bind(b); cig_tab.bind(b); pos_xv.bind(b);
     tl_xv.bind(b); as_raw.bind(b); ncg.bind(b); cig_raw.bind(b); seq2.bind(b); qualp.bind(b); exc.bind(b); qtab.bind(b);
-    exi.bind(b); frag.bind(b);
+    exi.bind(b); frag.bind(b); frag_fb.bind(b); frag_xi.bind(b); frag_xv.bind(b); frag_bk.bind(b);
   }
 };
 
@@ -141,6 +142,7 @@ static void check_packed(const phz_packed_reads* h) {
   if (h->n_cigar_bits != 8 && h->n_cigar_bits != 16) throw PhzError("packed reads: n_cigar_bits must be 8 or 16");
   if (h->cigar_bits != 16 && h->cigar_bits != 32) throw PhzError("packed reads: cigar_bits must be 16 or 32");
   if (h->l_seq_const < 0 && !h->l_seq && h->n_records > 0) throw PhzError("packed reads: l_seq missing");
+  if (h->frag_bits != 32 && h->frag_bits != 16) throw PhzError("packed reads: frag_bits must be 32 or 16");
 }
 
 // sizes the slot's buffers for `h` (may reallocate: call before any copy is enqueued)
@@ -152,6 +154,7 @@ static void size_slot(TransportSlot& S, const phz_packed_reads* h) {
   S.pos_d.ensure(R); S.pos_xi.ensure(h->n_pos_exc); S.pos_xv.ensure(h->n_pos_exc);
   S.tl16.ensure(R); S.tl_xi.ensure(h->n_tlen_exc); S.tl_xv.ensure(h->n_tlen_exc);
   S.as_raw.ensure(R * 2 + 16); S.as_tab.ensure(256); S.frag.ensure(R);
+  if (h->frag_bits == 16) { S.frag_fb.ensure((R + 31) / 32 + 1); S.frag_bk.ensure(h->n_frag_back + 1); S.frag_xi.ensure(h->n_frag_exc); S.frag_xv.ensure(h->n_frag_exc); }
 }
 
 // the four copy groups of one sample, in the order the expansion consumes them
@@ -160,6 +163,10 @@ static void copy_group(PHZ_BACKEND& be, TransportSlot& S, const phz_packed_reads
   if (group == 0) {
     be.h2d_copy(S.ncg.p, h->n_cigar, R * (h->n_cigar_bits / 8));
     if (h->l_seq_const < 0) be.h2d_copy(S.lsq.p, h->l_seq, R * 2);
+    if (h->frag_bits == 16) {         // implicit fragment ids travel with the counts: they are rebuilt under the copies that follow
+      be.h2d_copy(S.frag_fb.p, h->frag_first, ((R + 31) / 32) * 4); be.h2d_copy(S.frag_bk.p, h->frag_back, h->n_frag_back * 2);
+      be.h2d_copy(S.frag_xi.p, h->frag_exc_index, h->n_frag_exc * 4); be.h2d_copy(S.frag_xv.p, h->frag_exc_value, h->n_frag_exc * 4);
+    }
   } else if (group == 1) {
     be.h2d_copy(S.qualp.p, h->qualp, (NB * h->qual_bits + 7) / 8); be.h2d_copy(S.qtab.p, h->qual_table, 256);
   } else if (group == 2) {
@@ -173,7 +180,7 @@ static void copy_group(PHZ_BACKEND& be, TransportSlot& S, const phz_packed_reads
     be.h2d_copy(S.tl_xi.p, h->tlen_exc_index, h->n_tlen_exc * 4); be.h2d_copy(S.tl_xv.p, h->tlen_exc_value, h->n_tlen_exc * 4);
     be.h2d_copy(S.as_raw.p, h->as_data, R * (h->as_bits / 8));
     if (h->as_bits == 8) be.h2d_copy(S.as_tab.p, h->as_table, 512);
-    be.h2d_copy(S.frag.p, h->frag, R * 4);
+    if (h->frag_bits == 32) be.h2d_copy(S.frag.p, h->frag, R * 4);
   }
 }
 
@@ -233,6 +240,17 @@ int phz_map_reads_packed(phz_ctx* ctx, const phz_packed_reads* h, int baseq, dou
     if (h->l_seq_const >= 0) { const u64 L = (u64)h->l_seq_const; be.for_each(R + 1, PHZ_LAMBDA(int64_t r) { soff[r] = (u64)r * L; }); }
     else be.exclusive_scan_u16_to_u64(S.lsq.p, soff, R);
     d.seq_off = (const uint64_t*)soff;
+  }
+  if (h->frag_bits == 16) {   // fragment ids from the first-appearance bitmap: one scan (set bits before r), one pass, the exceptions
+    const u32* fb = S.frag_fb.p; const uint16_t* bk = S.frag_bk.p; const u32* fxi = S.frag_xi.p; const u32* fxv = S.frag_xv.p;
+    const u32 base = h->frag_base; u32* fr = S.frag.p;
+    auto opens = PHZ_LAMBDA(int64_t r) -> u32 { return (fb[r >> 5] >> (r & 31)) & 1u; };
+    be.exclusive_scan_fn_u32(opens, tmp, R);
+    be.for_each(R, PHZ_LAMBDA(int64_t r) {
+      const u32 nf = tmp[r];
+      fr[r] = ((fb[r >> 5] >> (r & 31)) & 1u) ? base + nf : base + nf - (u32)bk[r - nf];
+    });
+    be.for_each(h->n_frag_exc, PHZ_LAMBDA(int64_t e) { fr[fxi[e]] = fxv[e]; });
   }
   if (!prefetched) { be.copy_fence(); copy_group(be, S, h, 2); }
   {   // base qualities: one logical thread per 8 bases = `bits` packed bytes in, 8 phred bytes out
@@ -366,6 +384,7 @@ static bool find_array(phz_ctx* ctx, const std::string& name, ArrRef* out) {
   S("st_coff", st_coff, ctx->last_R + 1) S("st_soff", st_soff, ctx->last_R + 1) S("st_seq", st_seq, (ctx->last_NB + 1) / 2)
   S("st_qual", st_qual, ctx->last_NB)
 #undef S
+  if (name == "st_frag") { *out = ArrRef{(const void*)ctx->cur_frag, ctx->cur_frag ? ctx->last_R : 0, (int)sizeof(u32)}; return true; }
 #define G(nm, buf) if (name == nm) { *out = ArrRef{(const void*)ctx->ae.buf.p, ctx->ae.NPAIR, (int)sizeof(u32)}; return true; }
   G("ae_row", ae_row) G("ae_feat", ae_feat) G("ae_a", ae_a) G("ae_b", ae_b)
 #undef G

@@ -976,7 +976,8 @@ int phz_write_bam(const char* path, const char* const* contig_names, const int64
 
 struct phz_packed_host {
   phz_packed_reads v;
-  std::vector<std::pair<void*, bool>> bufs;      // (pointer, page-locked)
+  struct Owned { void* p; bool pinned; int64_t bytes; };
+  std::vector<Owned> bufs;
   std::vector<int64_t> contig_off;
   int64_t bytes = 0;
   bool want_pinned = false;
@@ -984,11 +985,16 @@ struct phz_packed_host {
     bool pinned = false;
     void* p = want_pinned ? PHZ_BACKEND::host_alloc((n ? n : 1) * sizeof(T), &pinned) : std::malloc((n ? n : 1) * sizeof(T));
     if (!p) throw PhzError("out of host memory for the packed transport buffers");
-    bufs.emplace_back(p, pinned);
+    bufs.push_back(Owned{p, pinned, (int64_t)(n * sizeof(T))});
     bytes += (int64_t)(n * sizeof(T));
     return (T*)p;
   }
-  ~phz_packed_host() { for (auto& b : bufs) { if (b.second) PHZ_BACKEND::host_free(b.first, true); else std::free(b.first); } }
+  static void free_one(const Owned& b) { if (b.pinned) PHZ_BACKEND::host_free(b.p, true); else std::free(b.p); }
+  void release(const void* p) {          // a buffer the packer allocated for a coding it then did not take
+    for (size_t i = 0; i < bufs.size(); ++i)
+      if (bufs[i].p == p) { bytes -= bufs[i].bytes; free_one(bufs[i]); bufs.erase(bufs.begin() + (long)i); return; }
+  }
+  ~phz_packed_host() { for (auto& b : bufs) free_one(b); }
 };
 
 extern "C" {
@@ -1012,13 +1018,12 @@ phz_packed_host* phz_pack_reads(const phz_reads* h, int n_contigs, int n_threads
     const size_t CH = 1 << 20;
     const size_t nrc = (size_t)((R + (int64_t)CH - 1) / (int64_t)CH);
     // ---- pos: u16 difference to the previous record, tlen: i16, each with an exception list
-    uint16_t* pd = P->alloc<uint16_t>(R); int16_t* t16 = P->alloc<int16_t>(R); uint32_t* frag = P->alloc<uint32_t>(R);
+    uint16_t* pd = P->alloc<uint16_t>(R); int16_t* t16 = P->alloc<int16_t>(R);
     std::vector<std::vector<std::pair<u32, int32_t>>> pex(nrc), tex(nrc);
     std::vector<std::vector<u32>> as_seen(nrc, std::vector<u32>(65536 / 32, 0));
     std::vector<u32> max_ncg(nrc, 0), lmin(nrc, 0xFFFFFFFFu), lmax(nrc, 0);
     phzio::parallel_for(nrc, n_threads, [&](size_t c) {
       int64_t r0 = (int64_t)(c * CH), r1 = std::min<int64_t>(R, r0 + (int64_t)CH);
-      std::memcpy(frag + r0, h->frag + r0, (r1 - r0) * 4);
       auto& seen = as_seen[c];
       for (int64_t r = r0; r < r1; ++r) {
         int64_t d = (int64_t)h->pos[r] - (r > 0 ? (int64_t)h->pos[r - 1] : 0);
@@ -1038,7 +1043,66 @@ phz_packed_host* phz_pack_reads(const phz_reads* h, int n_contigs, int n_threads
     };
     v.pos_delta = pd; v.n_pos_exc = flatten(pex, v.pos_exc_index, v.pos_exc_delta);
     v.tlen16 = t16; v.n_tlen_exc = flatten(tex, v.tlen_exc_index, v.tlen_exc_value);
-    v.frag = frag;
+    // ---- fragment ids numbered by first appearance are implicit (phz.h: frag_first / frag_back); taken when smaller.
+    // A record "opens" an id iff its id exceeds every id before it (a prefix maximum: chunk maxima first, then the chunks
+    // in parallel); whatever the implicit rule then gets wrong -- ids that are not dense, references further back than
+    // 16 bits -- is listed as an exception, so the coding is lossless for any input.
+    v.frag_bits = 32;
+    if (R > 0) {
+      const u32 base = h->frag[0];
+      std::vector<u32> cmax(nrc, 0); std::vector<int64_t> cfirst(nrc + 1, 0);
+      phzio::parallel_for(nrc, n_threads, [&](size_t c) {
+        int64_t r0 = (int64_t)(c * CH), r1 = std::min<int64_t>(R, r0 + (int64_t)CH);
+        u32 m = 0; for (int64_t r = r0; r < r1; ++r) m = std::max(m, h->frag[r]);
+        cmax[c] = m;
+      });
+      // exclusive prefix maximum over the chunks; "nothing seen yet" = base - 1 (64-bit: base may be 0)
+      std::vector<int64_t> pmax(nrc, (int64_t)base - 1);
+      for (size_t c = 1; c < nrc; ++c) pmax[c] = std::max(pmax[c - 1], (int64_t)cmax[c - 1]);
+      phzio::parallel_for(nrc, n_threads, [&](size_t c) {
+        int64_t r0 = (int64_t)(c * CH), r1 = std::min<int64_t>(R, r0 + (int64_t)CH);
+        int64_t m = pmax[c], k = 0;
+        for (int64_t r = r0; r < r1; ++r) if ((int64_t)h->frag[r] > m) { m = h->frag[r]; ++k; }
+        cfirst[c + 1] = k;
+      });
+      for (size_t c = 0; c < nrc; ++c) cfirst[c + 1] += cfirst[c];
+      const int64_t n_first = cfirst[nrc], n_back = R - n_first;
+      std::vector<std::vector<std::pair<u32, u32>>> fex(nrc);
+      uint32_t* fb = P->alloc<uint32_t>((R + 31) / 32); uint16_t* bk = P->alloc<uint16_t>(n_back);
+      static_assert(CH % 32 == 0, "chunks own whole words of the first-appearance bitmap");
+      phzio::parallel_for(nrc, n_threads, [&](size_t c) {
+        int64_t r0 = (int64_t)(c * CH), r1 = std::min<int64_t>(R, r0 + (int64_t)CH);
+        for (int64_t w = r0 >> 5; w < (r1 + 31) >> 5; ++w) fb[w] = 0;
+        int64_t m = pmax[c], nf = cfirst[c];          // nf: set bits before r
+        for (int64_t r = r0; r < r1; ++r) {
+          const u32 id = h->frag[r];
+          if ((int64_t)id > m) {
+            m = id; fb[r >> 5] |= 1u << (r & 31);
+            if ((int64_t)id != (int64_t)base + nf) fex[c].emplace_back((u32)r, id);
+            ++nf;
+          } else {
+            const int64_t d = (int64_t)base + nf - (int64_t)id;
+            if (d >= 1 && d <= 65535) bk[r - nf] = (uint16_t)d;
+            else { bk[r - nf] = 0; fex[c].emplace_back((u32)r, id); }
+          }
+        }
+      });
+      int64_t n_exc = 0; for (auto& e : fex) n_exc += (int64_t)e.size();
+      if (((R + 31) / 32) * 4 + n_back * 2 + n_exc * 8 < R * 4) {
+        uint32_t* xi = P->alloc<uint32_t>(n_exc); uint32_t* xv = P->alloc<uint32_t>(n_exc);
+        int64_t o = 0; for (auto& e : fex) for (auto& x : e) { xi[o] = x.first; xv[o] = x.second; ++o; }
+        v.frag_bits = 16; v.frag_base = base; v.frag_first = fb; v.n_frag_back = n_back; v.frag_back = bk;
+        v.n_frag_exc = n_exc; v.frag_exc_index = xi; v.frag_exc_value = xv;
+      } else { P->release(fb); P->release(bk); }
+    }
+    if (v.frag_bits == 32) {
+      uint32_t* frag = P->alloc<uint32_t>(R);
+      phzio::parallel_for(nrc, n_threads, [&](size_t c) {
+        int64_t r0 = (int64_t)(c * CH), r1 = std::min<int64_t>(R, r0 + (int64_t)CH);
+        std::memcpy(frag + r0, h->frag + r0, (r1 - r0) * 4);
+      });
+      v.frag = frag;
+    }
     // ---- alignment scores: table of distinct values when it fits a byte
     {
       std::vector<u32> seen(65536 / 32, 0);

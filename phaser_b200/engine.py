@@ -39,7 +39,9 @@ class phz_packed_reads(ctypes.Structure):
                 ("n_cigar_bits", c_int32), ("n_cigar", c_void_p), ("l_seq_const", c_int32), ("l_seq", c_void_p),
                 ("cigar_bits", c_int32), ("cigar", c_void_p), ("n_cigar_table", c_int32), ("cigar_table", c_void_p),
                 ("seq2", c_void_p), ("n_exceptions", c_int64), ("exc_index", c_void_p), ("exc_code", c_void_p),
-                ("qual_bits", c_int32), ("qual_table", ctypes.c_uint8 * 256), ("qualp", c_void_p)]
+                ("qual_bits", c_int32), ("qual_table", ctypes.c_uint8 * 256), ("qualp", c_void_p),
+                ("frag_bits", c_int32), ("frag_base", ctypes.c_uint32), ("frag_first", c_void_p), ("n_frag_back", c_int64),
+                ("frag_back", c_void_p), ("n_frag_exc", c_int64), ("frag_exc_index", c_void_p), ("frag_exc_value", c_void_p)]
 
 
 class phz_vcf_table(ctypes.Structure):
@@ -261,7 +263,8 @@ class PackedReads:
         self.n_exceptions = int(v.n_exceptions)
         self.coding = dict(qual_bits=int(v.qual_bits), base_exceptions=int(v.n_exceptions), as_bits=int(v.as_bits),
                            n_cigar_bits=int(v.n_cigar_bits), l_seq_const=int(v.l_seq_const), cigar_bits=int(v.cigar_bits),
-                           cigar_table=int(v.n_cigar_table), pos_exceptions=int(v.n_pos_exc), tlen_exceptions=int(v.n_tlen_exc))
+                           cigar_table=int(v.n_cigar_table), pos_exceptions=int(v.n_pos_exc), tlen_exceptions=int(v.n_tlen_exc),
+                           frag_bits=int(v.frag_bits), frag_exceptions=int(v.n_frag_exc))
 
     def __del__(self):
         try:

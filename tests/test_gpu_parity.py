@@ -291,6 +291,14 @@ def test_packed_transport_wide_codings_round_trip(gpu, tmp_path):
     assert c["cigar_bits"] == 16 and c["n_cigar_bits"] == 8 and c["l_seq_const"] == 76 and c["as_bits"] == 8
 
 
+@pytest.mark.parametrize("ids", ["first_appearance", "offset", "shuffled", "far_back", "gaps"])
+def test_packed_fragment_ids_round_trip(gpu, tmp_path, ids):
+    """The implicit fragment-id coding of the transport form (bitmap + 16-bit back references + exceptions) expanded by the
+    CUDA library: same cases as on the host-simulation backend."""
+    from tests import test_hostsim_parity as H
+    H.test_packed_fragment_ids_round_trip(gpu, tmp_path, ids)
+
+
 @pytest.mark.parametrize("n_bams", [1, 3, 5])
 def test_window_aggregated_counters_equal_plain_atomics(gpu, tmp_path, n_bams):
     """The shared-memory window kernels for the per-variant counters (vfirst / ncls, set sizes, per-BAM allele

@@ -233,6 +233,34 @@ def test_packed_transport_wide_codings_round_trip(hostsim, tmp_path):
     assert c["cigar_bits"] == 16 and c["n_cigar_bits"] == 8 and c["l_seq_const"] == 76 and c["as_bits"] == 8
 
 
+@pytest.mark.parametrize("ids", ["first_appearance", "offset", "shuffled", "far_back", "gaps"])
+def test_packed_fragment_ids_round_trip(hostsim, tmp_path, ids):
+    """Fragment ids numbered by first appearance travel as a bitmap + 16-bit back references (phz.h: frag_first /
+    frag_back); anything else must come back bit for bit too -- through the exception list or as plain 32-bit ids."""
+    vcf, sams = util.make_case(tmp_path, 43, 200, 2500, n_bams=1)
+    vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+    b = batches[0]
+    first = np.unique(b.frag, return_index=True)[1]
+    rank = np.empty(int(b.frag.max()) + 1, np.int64); rank[b.frag[np.sort(first)]] = np.arange(first.shape[0])
+    dense = rank[b.frag]                                         # ids in order of first appearance
+    rng = np.random.default_rng(7)
+    if ids == "first_appearance":
+        f = dense; expect = 16
+    elif ids == "offset":                                        # a second BAM: new names continue after the first BAM's
+        f = dense + 1_000_000; expect = 16
+    elif ids == "shuffled":                                      # arbitrary numbering: plain ids
+        f = rng.permutation(first.shape[0])[dense] * 100000; expect = 32
+    elif ids == "far_back":                                      # a few mates further back than 16 bits can say: exceptions
+        f = dense.copy(); f[-5:] = 0; f[-1] = f.max() + 70000; expect = 16
+    else:                                                        # ids with holes (a shard's view of a global numbering)
+        f = dense * 3; expect = None        # small here: either form may win, the round trip is what counts
+    b.frag = f.astype(np.uint32)
+    p = util.packed_vs_plain(hostsim, vt, b, len(vt.contigs))
+    assert expect is None or p.coding["frag_bits"] == expect, p.coding
+    if ids == "far_back":
+        assert p.coding["frag_exceptions"] >= 1
+
+
 def test_compact_pair_keys_equal_wide_ones(hostsim, tmp_path):
     """Pair table sorted on (va << dbits | vb - va) (32-bit when it fits) == sorted on 64-bit keys."""
     from phaser_b200 import pipeline

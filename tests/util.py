@@ -152,7 +152,7 @@ def packed_vs_plain(engine, vt, batch, n_contigs):
     # what the device expanded must be the original arrays, bit for bit
     nb = int(batch.qual.shape[0])
     for name, orig in (("st_pos", batch.pos), ("st_tlen", batch.tlen), ("st_as", batch.aln_score), ("st_cig", batch.cigar),
-                       ("st_coff", batch.cigar_off), ("st_soff", batch.seq_off), ("st_qual", batch.qual)):
+                       ("st_coff", batch.cigar_off), ("st_soff", batch.seq_off), ("st_qual", batch.qual), ("st_frag", batch.frag)):
         back = engine.download(name)
         assert np.array_equal(back.view(np.asarray(orig).dtype), np.asarray(orig)), name
     seq = engine.download("st_seq"); o = np.asarray(batch.seq)
