@@ -342,13 +342,24 @@ def merge_results_device(recv, lay, heads, names, gids, plan, vt: VariantTable, 
     """merge_results on the arrays as the gather left them in rank 0's memory (device tensors, or CPU tensors under
     gloo): same result, but every step is a tensor operation where the data already is, and the merged arrays reach
     the host in ONE copy.  recv[r]: packed byte buffer of rank r (None: no contigs); lay[r]: its layout; gids[r]:
-    global variant ids of rank r's table (int64 tensor on the same device); contig_of: int64[V] on that device."""
+    global variant ids of rank r's table (int64 tensor on the same device); contig_of: int64[V] on that device.
+    The arrays of all ranks are concatenated per name first and every step then runs ONCE over the concatenation (a
+    per-element rank index supplies what differs between ranks: id bases, tuples per BAM), so the number of tensor
+    operations -- what the merge costs on a GPU -- does not grow with the number of ranks, and nothing is read back
+    before the final copy (all sizes are known from the layouts)."""
     from .engine import COUNTER_NAMES
     dev = contig_of.device
     V = vt.n_variants; nb = n_bams; nc = len(vt.contigs); nn = len(names)
     M32 = 0xFFFFFFFF
     i64 = torch.int64
     live = [r for r in range(len(recv)) if recv[r] is not None]
+    nl = len(live)
+
+    def count(r, name):
+        for nm, _off, n, _eb in lay[r][0]:
+            if nm == name:
+                return int(n)
+        return 0
 
     def arr(r, name):
         for nm, off, n, eb in lay[r][0]:
@@ -356,117 +367,139 @@ def merge_results_device(recv, lay, heads, names, gids, plan, vt: VariantTable, 
                 return _typed(recv[r], off, n, eb)
         raise KeyError(name)
 
+    def has(name):
+        return nl > 0 and all(any(nm == name for nm, _o, _n, _e in lay[r][0]) for r in live)
+
+    def allr(name, dt=torch.int32):
+        xs = [arr(r, name) for r in live]
+        return torch.cat(xs) if xs else torch.zeros(0, dtype=dt, device=dev)
+
     def u(t):          # int32 bit pattern -> non-negative int64
         return t.to(i64) & M32
 
+    def per_element(counts, values):
+        """values[k] repeated counts[k] times (k = position in `live`), as an int64 tensor"""
+        return torch.repeat_interleave(torch.as_tensor(np.asarray(values, np.int64), device=dev),
+                                       torch.as_tensor(np.asarray(counts, np.int64), device=dev))
+
+    def bases(counts):
+        return np.concatenate([[0], np.cumsum(np.asarray(counts, np.int64))])[:-1]
+
+    # ---- host side: counters and the per-rank sizes (from the small headers and the layouts; no device reads)
+    counters = {}; tpb = [0] * nb; cpb = [0] * nb; t_rs = []
+    for r in live:
+        h = heads[r]
+        for i, k in enumerate(COUNTER_NAMES):
+            counters[k] = counters.get(k, 0) + int(h[2 * nn + i])
+        t_r = [int(x) for x in h[2 * nn + N_COUNTERS:2 * nn + N_COUNTERS + nb]]
+        t_rs.append(t_r)
+        for b in range(nb):
+            tpb[b] += t_r[b]; cpb[b] += int(h[2 * nn + N_COUNTERS + nb + b])
+    nv = [int(gids[r].shape[0]) for r in live]; nfb = [count(r, "fb_first") for r in live]; nm = [count(r, "members") for r in live]
+    ne = [count(r, "ed_a") for r in live]
+    vbase = bases(nv); fbase = bases(nfb); mbase = bases(nm)
+    gid = torch.cat([gids[r] for r in live]) if nl else torch.zeros(0, dtype=i64, device=dev)      # local (concatenated) -> global site
+    cgid = contig_of[gid]
+
+    # ---- per site
     BIG = torch.iinfo(i64).max
     vfirst = torch.full((V,), BIG, dtype=i64, device=dev)
     ncls = torch.zeros((V, 3), dtype=torch.int32, device=dev); setsize = torch.zeros((V, 3), dtype=torch.int32, device=dev)
     vb = torch.zeros((V, nb * 2), dtype=torch.int32, device=dev)
     v_final = torch.full((V,), -1, dtype=torch.int32, device=dev); v_hap = torch.zeros(V, dtype=torch.uint8, device=dev)
     first_bam = torch.full((nc,), 1 << 30, dtype=i64, device=dev)
-    counters = {}; tpb = [0] * nb; cpb = [0] * nb
-    for r in live:
-        h = heads[r]
-        for i, k in enumerate(COUNTER_NAMES):
-            counters[k] = counters.get(k, 0) + int(h[2 * nn + i])
-        t_r = [int(x) for x in h[2 * nn + N_COUNTERS:2 * nn + N_COUNTERS + nb]]
-        for b in range(nb):
-            tpb[b] += t_r[b]; cpb[b] += int(h[2 * nn + N_COUNTERS + nb + b])
-        gid = gids[r]
-        lf = u(arr(r, "vfirst")); seen = lf != M32
-        bam_start = torch.tensor(np.concatenate([[0], np.cumsum(t_r)]), dtype=i64, device=dev)
-        bam_of = torch.searchsorted(bam_start, lf, right=True) - 1
-        key = (bam_of << 56) | (contig_of[gid] << 40) | lf
+    if nl:
+        lf = u(allr("vfirst")); seen = lf != M32
+        if nb == 1:
+            bam_of = torch.zeros_like(lf)
+        else:          # first tuple of BAM b on each rank: a tuple rank belongs to the last BAM that starts at or before it
+            starts = np.asarray([np.cumsum(t)[:-1] for t in t_rs], np.int64).reshape(nl, nb - 1)
+            st = torch.repeat_interleave(torch.as_tensor(starts, device=dev), torch.as_tensor(np.asarray(nv, np.int64), device=dev), dim=0)
+            bam_of = (lf[:, None] >= st).sum(1)
+        key = (bam_of << 56) | (cgid << 40) | lf
         vfirst[gid[seen]] = key[seen]
-        ncls[gid] = arr(r, "ncls").view(-1, 3); setsize[gid] = arr(r, "setsize").view(-1, 3); vb[gid] = arr(r, "vb_cnt").view(-1, nb * 2)
-        v_hap[gid] = arr(r, "v_hap")
-        first_bam.scatter_reduce_(0, contig_of[gid[seen]], bam_of[seen], "amin")
+        ncls[gid] = allr("ncls").view(-1, 3); setsize[gid] = allr("setsize").view(-1, 3); vb[gid] = allr("vb_cnt").view(-1, nb * 2)
+        v_hap[gid] = allr("v_hap", torch.uint8)
+        first_bam.scatter_reduce_(0, cgid[seen], bam_of[seen], "amin")
     first_bam[first_bam == (1 << 30)] = 0
-    # ---- global block order: (first BAM of the contig, contig, local order)
-    keys = []; lens = []
-    for r in live:
-        ff = u(arr(r, "fb_first")); nf = ff.shape[0]
-        c = contig_of[gids[r][u(arr(r, "members"))[ff]]] if nf else torch.zeros(0, dtype=i64, device=dev)
-        keys.append((first_bam[c] << 48) | (c << 32) | torch.arange(nf, dtype=i64, device=dev))
-        lens.append(u(arr(r, "fb_len")))
-    keys = torch.cat(keys) if keys else torch.zeros(0, dtype=i64, device=dev)
-    cat_len = torch.cat(lens) if lens else torch.zeros(0, dtype=i64, device=dev)
-    order = torch.argsort(keys)
-    NF = int(order.shape[0])
-    new_of_cat = torch.empty(NF, dtype=i64, device=dev); new_of_cat[order] = torch.arange(NF, dtype=i64, device=dev)
-    g_len = cat_len[order]
-    g_first = torch.cumsum(g_len, 0) - g_len
-    members = torch.zeros(int(g_len.sum().item()) if NF else 0, dtype=torch.int32, device=dev)
-    fb_sup = torch.zeros(NF, dtype=torch.int32, device=dev); fb_tot = torch.zeros(NF, dtype=torch.int32, device=dev)
-    fb_cnt = torch.zeros((NF, 2), dtype=torch.int32, device=dev); fb_bcnt = torch.zeros((NF, nb * 2), dtype=torch.int32, device=dev)
-    ed = {k: [] for k in ("ed_a", "ed_b", "ed_sup", "ed_tot", "ed_cfg", "ed_keep")}
-    sg = {k: [] for k in ("sg_var", "sg_cb", "sg_frag", "g_var", "g_cb", "g_frag")}
+    # ---- global block order: (first BAM of the contig, contig, local order); ranks in `live` order, as concatenated
+    NF = int(sum(nfb))
+    if NF:
+        mem_g = gid[u(allr("members")) + per_element(nm, vbase)]                 # members as global site ids (concatenated order)
+        ff = u(allr("fb_first")) + per_element(nfb, mbase)                       # first member of every block in mem_g
+        cat_len = u(allr("fb_len"))
+        c = contig_of[mem_g[ff]]
+        local = torch.arange(NF, dtype=i64, device=dev) - per_element(nfb, fbase)
+        order = torch.argsort((first_bam[c] << 48) | (c << 32) | local)
+        new_of_cat = torch.empty(NF, dtype=i64, device=dev); new_of_cat[order] = torch.arange(NF, dtype=i64, device=dev)
+        g_len = cat_len[order]
+        g_first = torch.cumsum(g_len, 0) - g_len
+        # the final blocks need not tile the member arrays (members of dropped blocks): expand the runs from the block table
+        # (the one size of the merge that is not in the layouts: repeat_interleave reads it back)
+        rep = torch.repeat_interleave(torch.arange(NF, dtype=i64, device=dev), cat_len)
+        within = torch.arange(rep.shape[0], dtype=i64, device=dev) - torch.repeat_interleave(torch.cumsum(cat_len, 0) - cat_len, cat_len)
+        members = torch.zeros(rep.shape[0], dtype=torch.int32, device=dev)
+        members[g_first[new_of_cat[rep]] + within] = mem_g[ff[rep] + within].to(torch.int32)
+        fb_sup = torch.zeros(NF, dtype=torch.int32, device=dev); fb_tot = torch.zeros(NF, dtype=torch.int32, device=dev)
+        fb_cnt = torch.zeros((NF, 2), dtype=torch.int32, device=dev); fb_bcnt = torch.zeros((NF, nb * 2), dtype=torch.int32, device=dev)
+        fb_sup[new_of_cat] = allr("fb_sup"); fb_tot[new_of_cat] = allr("fb_tot")
+        fb_cnt[new_of_cat] = allr("fb_cnt").view(-1, 2); fb_bcnt[new_of_cat] = allr("fb_bcnt").view(-1, nb * 2)
+        vfl = allr("v_final"); inb = vfl != -1
+        v_final[gid[inb]] = new_of_cat[(vfl.to(i64) + per_element(nv, fbase))[inb]].to(torch.int32)
+    else:
+        new_of_cat = torch.zeros(0, dtype=i64, device=dev)
+        g_len = torch.zeros(0, dtype=i64, device=dev); g_first = torch.zeros(0, dtype=i64, device=dev)
+        members = torch.zeros(0, dtype=torch.int32, device=dev)
+        fb_sup = torch.zeros(0, dtype=torch.int32, device=dev); fb_tot = torch.zeros(0, dtype=torch.int32, device=dev)
+        fb_cnt = torch.zeros((0, 2), dtype=torch.int32, device=dev); fb_bcnt = torch.zeros((0, nb * 2), dtype=torch.int32, device=dev)
+    # ---- edges: the ranks' tables one after the other, sites renumbered
+    ed = {}
+    ev = per_element(ne, vbase) if nl else None
+    for k in ("ed_a", "ed_b"):
+        ed[k] = gid[u(allr(k)) + ev].to(torch.int32) if nl else torch.zeros(0, dtype=torch.int32, device=dev)
+    for k, dt in (("ed_sup", torch.int32), ("ed_tot", torch.int32), ("ed_cfg", torch.uint8), ("ed_keep", torch.uint8)):
+        ed[k] = allr(k, dt)
+    sg = {}
+    if (want_read_ids or want_kept_tuples) and nl:
+        ng = [count(r, "g_var") for r in live]
+        gvl = u(allr("g_var")) + per_element(ng, vbase); gc = allr("g_cb", torch.uint8); gfr = allr("g_frag")
+        if want_read_ids:
+            sel = torch.nonzero((allr("v_final")[gvl] == -1) & ((gc & 3) < 2))[:, 0]
+            sg["sg_var"] = gid[gvl[sel]].to(torch.int32); sg["sg_cb"] = gc[sel]; sg["sg_frag"] = gfr[sel]
+        if want_kept_tuples:
+            sg["g_var"] = gid[gvl].to(torch.int32); sg["g_cb"] = gc; sg["g_frag"] = gfr
     bb = max(1, int(np.ceil(np.log2(max(nb, 2)))))
     low = (1 << (bb + 1)) - 1
-    runs = []          # per rank: (new row of every run, run length, local start of every run, rl_var, rl_frag)
-    base = 0
-    for r in live:
-        gid = gids[r]
-        ff = u(arr(r, "fb_first")); ln = u(arr(r, "fb_len")); nf = int(ff.shape[0])
-        new_id = new_of_cat[base:base + nf]; base += nf
-        tot = int(ln.sum().item()) if nf else 0
-        if tot:
-            rep = torch.repeat_interleave(torch.arange(nf, dtype=i64, device=dev), ln)
-            within = torch.arange(tot, dtype=i64, device=dev) - torch.repeat_interleave(torch.cumsum(ln, 0) - ln, ln)
-            members[g_first[new_id[rep]] + within] = gid[u(arr(r, "members"))[ff[rep] + within]].to(torch.int32)
-        fb_sup[new_id] = arr(r, "fb_sup"); fb_tot[new_id] = arr(r, "fb_tot")
-        fb_cnt[new_id] = arr(r, "fb_cnt").view(-1, 2); fb_bcnt[new_id] = arr(r, "fb_bcnt").view(-1, nb * 2)
-        vfl = arr(r, "v_final"); inb = vfl != -1
-        v_final[gid[inb]] = new_id[vfl[inb].to(i64)].to(torch.int32)
-        ed["ed_a"].append(gid[u(arr(r, "ed_a"))].to(torch.int32)); ed["ed_b"].append(gid[u(arr(r, "ed_b"))].to(torch.int32))
-        for k in ("ed_sup", "ed_tot", "ed_cfg", "ed_keep"):
-            ed[k].append(arr(r, k))
-        if want_read_ids or want_kept_tuples:
-            gv = u(arr(r, "g_var")); gc = arr(r, "g_cb"); gfr = arr(r, "g_frag")
-            if want_read_ids:
-                sel = torch.nonzero((vfl[gv] == -1) & ((gc & 3) < 2))[:, 0]
-                sg["sg_var"].append(gid[gv[sel]].to(torch.int32)); sg["sg_cb"].append(gc[sel]); sg["sg_frag"].append(gfr[sel])
-            if want_kept_tuples:
-                sg["g_var"].append(gid[gv].to(torch.int32)); sg["g_cb"].append(gc); sg["g_frag"].append(gfr)
-        if any(nm == "rl_row" for nm, _o, _n, _e in lay[r][0]):
-            row = u(arr(r, "rl_row"))
-            if row.shape[0]:
-                urow, cnt = torch.unique_consecutive(row, return_counts=True)
-                runs.append(((new_id[urow >> (bb + 1)] << (bb + 1)) | (urow & low), cnt, torch.cumsum(cnt, 0) - cnt,
-                             gid[u(arr(r, "rl_var"))].to(torch.int32), arr(r, "rl_frag")))
-    cat = lambda xs, dt: torch.cat(xs) if xs else torch.zeros(0, dtype=dt, device=dev)
     out = dict(vfirst=vfirst, ncls=ncls.reshape(-1), setsize=setsize.reshape(-1), vb_cnt=vb.reshape(-1), v_final=v_final, v_hap=v_hap,
                members=members, fb_first=g_first.to(torch.int32), fb_len=g_len.to(torch.int32), fb_sup=fb_sup, fb_tot=fb_tot,
                fb_cnt=fb_cnt.reshape(-1), fb_bcnt=fb_bcnt.reshape(-1))
-    for k, dt in (("ed_a", torch.int32), ("ed_b", torch.int32), ("ed_sup", torch.int32), ("ed_tot", torch.int32), ("ed_cfg", torch.uint8),
-                  ("ed_keep", torch.uint8)):
-        out[k] = cat(ed[k], dt)
+    out.update(ed)
     # ---- read lists: rows of one block live on one rank and every rank's rows are already sorted, so the merged order
     # follows from the run lengths alone (no sort of the entries): destination = start of the run in the merged order +
     # offset inside the run
-    if runs:
-        all_rows = torch.cat([x[0] for x in runs]); all_cnt = torch.cat([x[1] for x in runs])
-        o = torch.argsort(all_rows)
-        start_sorted = torch.cumsum(all_cnt[o], 0) - all_cnt[o]
+    nrl = [count(r, "rl_row") for r in live] if has("rl_row") else []
+    if sum(nrl):
+        row = u(allr("rl_row")); rk = per_element(nrl, np.arange(nl))
+        urow, cnt = torch.unique_consecutive((rk << 40) | row, return_counts=True)       # runs never join across ranks
+        lrow = urow & ((1 << 40) - 1); rrun = urow >> 40
+        fb_of_run = torch.as_tensor(fbase, device=dev)[rrun]
+        nrow = (new_of_cat[(lrow >> (bb + 1)) + fb_of_run] << (bb + 1)) | (lrow & low)
+        o = torch.argsort(nrow)
+        start_sorted = torch.cumsum(cnt[o], 0) - cnt[o]
         start = torch.empty_like(start_sorted); start[o] = start_sorted
-        total = int(all_cnt.sum().item())
+        lstart = torch.cumsum(cnt, 0) - cnt                                              # where the run sits in the concatenation
+        total = int(sum(nrl))
+        dest = torch.repeat_interleave(start - lstart, cnt) + torch.arange(total, dtype=i64, device=dev)
         rl_row = torch.empty(total, dtype=torch.int32, device=dev); rl_var = torch.empty(total, dtype=torch.int32, device=dev)
         rl_frag = torch.empty(total, dtype=torch.int32, device=dev)
-        p = 0
-        for (nrow, cnt, lstart, var, frag) in runs:
-            k = int(nrow.shape[0]); n = int(var.shape[0])
-            dest = torch.repeat_interleave(start[p:p + k] - lstart, cnt) + torch.arange(n, dtype=i64, device=dev)
-            rl_row[dest] = torch.repeat_interleave(nrow, cnt).to(torch.int32)
-            rl_var[dest] = var; rl_frag[dest] = frag
-            p += k
+        rl_row[dest] = torch.repeat_interleave(nrow, cnt).to(torch.int32)
+        rl_var[dest] = gid[u(allr("rl_var")) + per_element(nrl, vbase)].to(torch.int32)
+        rl_frag[dest] = allr("rl_frag")
         out["rl_row"] = rl_row; out["rl_var"] = rl_var; out["rl_frag"] = rl_frag
     else:
         for k in ("rl_row", "rl_var", "rl_frag"):
             out[k] = torch.zeros(0, dtype=torch.int32, device=dev)
-    for pre in ("sg_", "g_"):
-        if sg[pre + "var"]:
-            out[pre + "var"] = torch.cat(sg[pre + "var"]); out[pre + "cb"] = torch.cat(sg[pre + "cb"]); out[pre + "frag"] = torch.cat(sg[pre + "frag"])
+    out.update(sg)
     # ---- one copy to the host
     total = 0; place = []
     for k, t in out.items():
