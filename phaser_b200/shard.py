@@ -10,6 +10,8 @@ global, and therefore exchanged exactly between ranks, is small:
                                                 (phaser.py:863-867) and writes the files.
 Reads and tuples never leave their GPU.  Backend: NCCL on GPUs, gloo in the CPU tests.
 """
+import os
+import sys
 import time
 from typing import List
 
@@ -354,6 +356,14 @@ def merge_results_device(recv, lay, heads, names, gids, plan, vt: VariantTable, 
     i64 = torch.int64
     live = [r for r in range(len(recv)) if recv[r] is not None]
     nl = len(live)
+    trace = [] if os.environ.get("PHZ_MERGE_TRACE") else None
+
+    def mark(what):
+        if trace is not None:
+            if dev.type == "cuda":
+                torch.cuda.synchronize(dev)
+            trace.append((what, time.perf_counter()))
+    mark("start")
 
     def count(r, name):
         for nm, _off, n, _eb in lay[r][0]:
@@ -422,6 +432,7 @@ def merge_results_device(recv, lay, heads, names, gids, plan, vt: VariantTable, 
         v_hap[gid] = allr("v_hap", torch.uint8)
         first_bam.scatter_reduce_(0, cgid[seen], bam_of[seen], "amin")
     first_bam[first_bam == (1 << 30)] = 0
+    mark("per site")
     # ---- global block order: (first BAM of the contig, contig, local order); ranks in `live` order, as concatenated
     NF = int(sum(nfb))
     if NF:
@@ -452,6 +463,7 @@ def merge_results_device(recv, lay, heads, names, gids, plan, vt: VariantTable, 
         members = torch.zeros(0, dtype=torch.int32, device=dev)
         fb_sup = torch.zeros(0, dtype=torch.int32, device=dev); fb_tot = torch.zeros(0, dtype=torch.int32, device=dev)
         fb_cnt = torch.zeros((0, 2), dtype=torch.int32, device=dev); fb_bcnt = torch.zeros((0, nb * 2), dtype=torch.int32, device=dev)
+    mark("blocks")
     # ---- edges: the ranks' tables one after the other, sites renumbered
     ed = {}
     ev = per_element(ne, vbase) if nl else None
@@ -500,6 +512,7 @@ def merge_results_device(recv, lay, heads, names, gids, plan, vt: VariantTable, 
         for k in ("rl_row", "rl_var", "rl_frag"):
             out[k] = torch.zeros(0, dtype=torch.int32, device=dev)
     out.update(sg)
+    mark("edges + read lists")
     # ---- one copy to the host
     total = 0; place = []
     for k, t in out.items():
@@ -522,6 +535,9 @@ def merge_results_device(recv, lay, heads, names, gids, plan, vt: VariantTable, 
                                          non_blocking=True)
     if dev.type == "cuda":
         torch.cuda.synchronize(dev)
+    mark("copy to the host (%d bytes)" % total)
+    if trace is not None:
+        print("[merge] " + ", ".join("%s %.2f ms" % (w, (t - trace[i][1]) * 1e3) for i, (w, t) in enumerate(trace[1:])), file=sys.stderr)
     hn = host.numpy()
     npdt = {torch.int32: np.uint32, torch.uint8: np.uint8, torch.int64: np.int64}
     arrays = {k: hn[off:off + nbytes].view(npdt[out[k].dtype]) for (k, off, nbytes) in place}
