@@ -620,17 +620,17 @@ __global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView
     if (k1_staged_emit == 0) state = EMIT_COMPLEX;
     sh_state[tid] = state;
     for (u32 k = 0; k < cnt && my_excl + k < KT_OWN; ++k) sh_owner[my_excl + k] = (u8)tid;
-    // the tile's output range comes from ONE returning atomic on the cursor; its round trip to L2 is taken off the
-    // critical path: thread 0 issues it, nobody reads the result until every thread has derived its first candidate
-    unsigned long long b_reg = 0;
     if (tid == 0) {
       excl_of[KF_THREADS] = cta_total;
-      if (cta_total) b_reg = atomicAdd(cursor, (unsigned long long)cta_total);
+      unsigned long long b = cta_total ? atomicAdd(cursor, (unsigned long long)cta_total) : 0ull;
+      s_base = b;
+      tile_base[tile] = (u32)b; tile_cnt[tile] = cta_total;
     }
-    __syncthreads();                                   // owner / state / offset tables visible
-    if (cta_total == 0) { if (tid == 0) { tile_base[tile] = 0; tile_cnt[tile] = 0; } return; }
+    __syncthreads();
+    const u64 base = s_base;
+    if (cta_total == 0 || base + cta_total > capacity) return;
     // ---- dense emission: candidate i of the tile -> thread i
-    auto derive = [&](u32 i, u32& o_rec, u32& o_var, u32& o_misc) {
+    for (u32 i = (u32)tid; i < cta_total; i += KF_THREADS) {
       int lo;
       if (i < KT_OWN) lo = sh_owner[i];
       else {                                            // last record index with excl_of <= i
@@ -641,29 +641,16 @@ __global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView
       if constexpr (!VV::kIndels && decltype(staged)::value) {
         if (stt != EMIT_COMPLEX) {          // the count pass left the candidates' place behind: no second search
           tile_emit_simple(trv, sh_pos, sh_coff, sh_cig, cig_al, win, ti.wbase, vv.a0, vv.a1, r0, lo, i - excl_of[lo], stt, baseq,
-                           &o_rec, &o_var, &o_misc);
-          return;
+                           s_rec + base + i, s_var + base + i, s_misc + base + i);
+          continue;
         }
       }
       const int64_t rr = r0 + lo;
       int c = contig0;
       if (lo >= n_first) c = upper_slot_i64(rv.contig_rec_off, rv.n_contigs, rr);
       const WindowVP vpk = window_of(ti, vv.pos, win, c == contig0);
-      map_record<2>(trv, vv, vpk, rr, c, baseq, isize_cutoff, (u64)(i - excl_of[lo]), &o_rec, &o_var, &o_misc);
-    };
-    u64 base = 0;
-    for (u32 i = (u32)tid, round = 0;; i += KF_THREADS, ++round) {
-      const bool have = i < cta_total;
-      u32 o_rec = 0, o_var = 0, o_misc = 0;
-      if (have) derive(i, o_rec, o_var, o_misc);
-      if (round == 0) {                                // every thread of the CTA passes here exactly once
-        if (tid == 0) { s_base = b_reg; tile_base[tile] = (u32)b_reg; tile_cnt[tile] = cta_total; }
-        __syncthreads();
-        base = s_base;
-        if (base + cta_total > capacity) return;       // the host grows the buffers and runs the kernel again
-      }
-      if (!have) break;
-      s_rec[base + i] = o_rec; s_var[base + i] = o_var; s_misc[base + i] = o_misc;
+      map_record<2>(trv, vv, vpk, rr, c, baseq, isize_cutoff, (u64)(i - excl_of[lo]), s_rec + base + i, s_var + base + i,
+                    s_misc + base + i);
     }
   };
   if ((u64)sh_coff[nrec] <= (u64)cig_al + cig_n) body(std::true_type{}); else body(std::false_type{});
