@@ -208,6 +208,17 @@ int phz_download_async(phz_ctx* ctx, const char* name, void* h_dst, int64_t dst_
  * one device buffer that a collective then moves to the rank that writes the files (the contig-sharded run's gather of
  * formatted rows / per-variant annotations; phaser.py:863-867 needs them in one place). */
 int phz_copy_array(phz_ctx* ctx, const char* name, void* dst, int64_t dst_bytes);
+/* Merge step of the contig-sharded run on the rank that writes the files (the per-variant read lists
+ * of phaser.py:1105-1115 brought into the run-wide block order of phaser.py:863-867).  The ranks' read lists arrive
+ * concatenated (n entries); consecutive entries of one row form a run.  Run k covers entries [d_run_first[k],
+ * d_run_first[k+1]) (d_run_first has n_runs + 1 elements, the last one = n), goes to d_run_dest[k] .. in the merged
+ * order, takes row id d_run_row[k], and its site ids (local to the sending rank) are turned into the sample's ids
+ * through d_site_map[local id + d_run_site_base[k]].  All pointers are DEVICE pointers of this context's device; one
+ * kernel on the context's stream, no wait. */
+int phz_expand_runs(phz_ctx* ctx, int64_t n_runs, const int64_t* d_run_first, const int64_t* d_run_dest,
+                    const int64_t* d_run_row, const int64_t* d_run_site_base, int64_t n, const uint32_t* d_site_local,
+                    const uint32_t* d_frag, const int64_t* d_site_map, uint32_t* d_out_row, uint32_t* d_out_site,
+                    uint32_t* d_out_frag);
 /* counters[16]: n_tuples, entries, groups, pairs, distinct pairs, edges, dropped, members, blocks,
  * hard blocks, final blocks, read-list entries, n_candidates, n_bams, fragment runs re-sorted in place by the
  * graph stage, 1 if that stage fell back to the full-key sort */

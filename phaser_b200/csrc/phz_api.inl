@@ -426,6 +426,22 @@ int phz_copy_array(phz_ctx* ctx, const char* name, void* dst, int64_t dst_bytes)
   PHZ_CATCH
 }
 
+int phz_expand_runs(phz_ctx* ctx, int64_t n_runs, const int64_t* rf, const int64_t* rd, const int64_t* rr, const int64_t* rb,
+                    int64_t n, const uint32_t* site, const uint32_t* frag, const int64_t* map, uint32_t* o_row, uint32_t* o_site,
+                    uint32_t* o_frag) {
+  PHZ_TRY
+  if (n_runs <= 0 || n <= 0) return 0;
+  ctx->p.be.for_each(n, PHZ_LAMBDA(int64_t i) {
+    int64_t lo = 0, hi = n_runs;                 // last run with first <= i
+    while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (rf[mid] <= i) lo = mid; else hi = mid; }
+    const int64_t d = rd[lo] + (i - rf[lo]);
+    o_row[d] = (u32)rr[lo];
+    o_site[d] = (u32)map[(int64_t)site[i] + rb[lo]];
+    o_frag[d] = frag[i];
+  });
+  PHZ_CATCH
+}
+
 int phz_counters(phz_ctx* ctx, int64_t* c) {
   PHZ_TRY
   auto& p = ctx->p;

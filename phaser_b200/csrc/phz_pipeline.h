@@ -716,7 +716,7 @@ struct Pipeline {
   Buf<B, u32> parent, deg, root, m_flag, m_scan, m_list, m_key, m_key2, m_val2, members;
   Buf<B, u32> b_flag, b_scan, blk_off, blk_of, pos_in_blk, blk_contig_rank, blk_order, blk_pos;
   Buf<B, u64> blk_rank, bs_key, bs_key2; Buf<B, u32> bs_val, bs_val2, bs_k32, bs_k32b;
-  Buf<B, u64> d_key, d_key2; Buf<B, u32> d_sign, d_sign2, adj_off;
+  Buf<B, u64> d_key, d_key2; Buf<B, u32> d_sign, d_sign2, adj_off, adj_list;
   Buf<B, u8> color, v_hap, blk_status; Buf<B, u32> bfsq, run_start, run_len, blk_nfinal, v_fin_local;
   Buf<B, u32> ebk_cnt, ebk_off, ebk_key, ebk_key2, ebk_val, ebk_list;
   Buf<B, u32> h_flag, h_scan, h_list, h_words, h_woff, h_scratch;
@@ -746,7 +746,7 @@ struct Pipeline {
     b_flag.bind(b); b_scan.bind(b); blk_off.bind(b); blk_of.bind(b); pos_in_blk.bind(b); blk_contig_rank.bind(b);
     blk_order.bind(b); blk_pos.bind(b); blk_rank.bind(b); bs_key.bind(b); bs_key2.bind(b); bs_val.bind(b); bs_val2.bind(b);
     bs_k32.bind(b); bs_k32b.bind(b);
-    d_key.bind(b); d_key2.bind(b); d_sign.bind(b); d_sign2.bind(b); adj_off.bind(b);
+    d_key.bind(b); d_key2.bind(b); d_sign.bind(b); d_sign2.bind(b); adj_off.bind(b); adj_list.bind(b);
     color.bind(b); v_hap.bind(b); blk_status.bind(b); bfsq.bind(b); run_start.bind(b); run_len.bind(b); blk_nfinal.bind(b);
     v_fin_local.bind(b);
     ebk_cnt.bind(b); ebk_off.bind(b); ebk_key.bind(b); ebk_key2.bind(b); ebk_val.bind(b); ebk_list.bind(b);
@@ -1691,9 +1691,8 @@ struct Pipeline {
       }
     });
     be.stage("phase.members");
-    // ---- members of the kept-edge graph, grouped by component root, ascending variant index inside.  The member flags
-    // (over the sites) and the directed-adjacency flags (over the edges) are scanned back to back and their totals read
-    // with the number of dropped edges in ONE wait.
+    // ---- members of the kept-edge graph, grouped by component root, ascending variant index inside.  Their number is
+    // read with the number of dropped edges in ONE wait.
     u32* rt = root.ensure(Vn); u32* mf = m_flag.ensure(Vn + 1); u32* ms = m_scan.ensure(Vn + 2);
     be.for_each(Vn, PHZ_LAMBDA(int64_t v) {
       if (dg[v] == 0) { mf[v] = 0; rt[v] = NONE32; return; }
@@ -1702,33 +1701,36 @@ struct Pipeline {
     });
     be.exclusive_scan_u32(mf, ms, Vn);
     u32* af = x_flag.ensure(E + 1 > NX + 1 ? E + 1 : NX + 1); u32* as_ = x_scan.ensure(E + 2 > NX + 2 ? E + 2 : NX + 2);
-    be.for_each(E, PHZ_LAMBDA(int64_t e) { af[e] = (keep[e] && ecfg[e] != EDGE_TIE) ? 2u : 0u; });
-    be.exclusive_scan_u32(af, as_, E);
-    { const int64_t vn = Vn, ee = E;
-      be.for_each(1, PHZ_LAMBDA(int64_t) { sc[4] = vn > 0 ? ms[vn] : 0u; sc[5] = ee > 0 ? as_[ee] : 0u; }); }
+    { const int64_t vn = Vn;
+      be.for_each(1, PHZ_LAMBDA(int64_t) { sc[4] = vn > 0 ? ms[vn] : 0u; }); }
     u32 h3[6] = {0, 0, 0, 0, 0, 0};
     be.d2h(h3, sc, sizeof(h3));
-    n_dropped = h3[2]; NM = h3[4]; const int64_t ND = h3[5];
+    n_dropped = h3[2]; NM = h3[4];
     u32* ml = m_list.ensure(NM); u32* mk = m_key.ensure(NM); u32* mk2 = m_key2.ensure(NM); u32* mem = members.ensure(NM);
     be.for_each(Vn, PHZ_LAMBDA(int64_t v) { if (mf[v]) { ml[ms[v]] = (u32)v; mk[ms[v]] = rt[v]; } });
     be.sort_pairs32(mk, mk2, ml, mem, NM, 0, vb);
     u32* bf = b_flag.ensure(NM + 1); u32* bs = b_scan.ensure(NM + 2);
     be.for_each(NM, PHZ_LAMBDA(int64_t i) { bf[i] = (i == 0 || mk2[i] != mk2[i - 1]) ? 1u : 0u; });
     be.exclusive_scan_u32(bf, bs, NM);
-    // ---- adjacency (kept, non-tie) by source variant: independent of the block count, so it is queued before that is read
-    u64* dk = d_key.ensure(ND); u64* dk2 = d_key2.ensure(ND); u32* dsg = d_sign.ensure(ND); u32* dsg2 = d_sign2.ensure(ND);
+    // ---- adjacency (kept, non-tie) by source variant: a counting sort (degree, scan, scatter through per-variant cursors;
+    // the 2-colouring below does not depend on the order inside a variant's list).  Independent of the block count, so
+    // it is queued before that is read.  adj[k] = neighbour | configuration << 31.
+    u32* adj = adj_list.ensure(2 * E + 1);
     u32* ao = adj_off.ensure(Vn + 2);
-    u32* dcnt = m_flag.p;      // reuse (the member flags were consumed above): per-variant directed degree
+    u32* dcnt = m_flag.p;      // reuse (the member flags were consumed above): per-variant directed degree, then cursor
     be.memset0(dcnt, (Vn + 1) * sizeof(u32));
     be.for_each(E, PHZ_LAMBDA(int64_t e) {
-      if (!af[e]) return;
-      u32 o = as_[e]; u32 a = ea_[e], b = eb_[e];
-      dk[o] = ((u64)a << vb) | b; dsg[o] = ecfg[e];
-      dk[o + 1] = ((u64)b << vb) | a; dsg[o + 1] = ecfg[e];
-      atomic_add(&dcnt[a], 1u); atomic_add(&dcnt[b], 1u);
+      if (!keep[e] || ecfg[e] == EDGE_TIE) return;
+      atomic_add(&dcnt[ea_[e]], 1u); atomic_add(&dcnt[eb_[e]], 1u);
     });
-    be.sort_pairs(dk, dk2, dsg, dsg2, ND, 0, 2 * vb);
     be.exclusive_scan_u32(dcnt, ao, Vn);
+    be.memset0(dcnt, (Vn + 1) * sizeof(u32));
+    be.for_each(E, PHZ_LAMBDA(int64_t e) {
+      if (!keep[e] || ecfg[e] == EDGE_TIE) return;
+      const u32 a = ea_[e], b = eb_[e], sgn = (u32)ecfg[e] << 31;
+      adj[ao[a] + atomic_add(&dcnt[a], 1u)] = b | sgn;
+      adj[ao[b] + atomic_add(&dcnt[b], 1u)] = a | sgn;
+    });
     NB = NM > 0 ? (int64_t)fetch_u32(bs + NM) : 0;
     u32* bo = blk_off.ensure(NB + 1); u32* bof = blk_of.ensure(Vn); u32* pib = pos_in_blk.ensure(Vn);
     be.memset_ff(bof, Vn * sizeof(u32));
@@ -1767,7 +1769,7 @@ struct Pipeline {
       while (qh < qt) {
         u32 v = q[o0 + qh++]; u8 cv = col[v];
         for (u32 k = ao[v]; k < ao[v + 1]; ++k) {
-          u32 w = (u32)(dk2[k] & vmask); u8 want = cv ^ (u8)dsg2[k];
+          const u32 x = adj[k]; u32 w = x & 0x7FFFFFFFu; u8 want = cv ^ (u8)(x >> 31);
           if (col[w] == 0xFF) { col[w] = want; q[o0 + qt++] = w; }
           else if (col[w] != want) conflict = true;
         }

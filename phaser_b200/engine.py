@@ -73,7 +73,7 @@ EXPORTS = ["phz_last_error", "phz_backend_name", "phz_create", "phz_destroy", "p
            "phz_host_reads_view", "phz_host_reads_free", "phz_set_haplo_blacklist", "phz_write_sam",
            "phz_set_indel_alleles", "phz_pack_reads", "phz_packed_view", "phz_packed_bytes", "phz_packed_free",
            "phz_map_reads_packed", "phz_prefetch_packed", "phz_gene_ae_pairs", "phz_set_big_critical_values",
-           "phz_copy_array", "phz_vcf_open", "phz_vcf_close", "phz_vcf_text", "phz_vcf_chrom_line", "phz_vcf_parse",
+           "phz_copy_array", "phz_expand_runs", "phz_vcf_open", "phz_vcf_close", "phz_vcf_text", "phz_vcf_chrom_line", "phz_vcf_parse",
            "phz_vcf_write", "phz_vcf_records", "phz_write_bam", "phz_vcf_save", "phz_format_read_lists", "phz_vcf_site_text", "phz_upload", "phz_sync_count",
            "phz_fragdict_blob_bytes", "phz_fragdict_export", "phz_fragdict_import"]
 
@@ -98,6 +98,8 @@ def _declare(lib):
     lib.phz_download.argtypes = [c_void_p, c_char_p, c_void_p, c_int64]
     lib.phz_download_async.argtypes = [c_void_p, c_char_p, c_void_p, c_int64]
     lib.phz_copy_array.argtypes = [c_void_p, c_char_p, c_void_p, c_int64]
+    lib.phz_expand_runs.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p]
     lib.phz_vcf_open.restype = c_void_p
     lib.phz_vcf_open.argtypes = [c_char_p, c_int]
     lib.phz_vcf_close.argtypes = [c_void_p]
@@ -555,6 +557,17 @@ class Engine:
         for name, off, n, eb in info:
             self._check(self.lib.phz_copy_array(self.ctx, name.encode(), base + off, n * eb))
         return buf, info
+
+    def expand_runs(self, run_first, run_dest, run_row, run_site_base, site_local, frag, site_map, out_row, out_site, out_frag):
+        """phz_expand_runs on tensors that live on the engine's device (int64 run tables, int32 entry arrays)."""
+        for t in (run_first, run_dest, run_row, run_site_base, site_map):
+            assert t.dtype == torch.int64 and t.is_contiguous() and t.device.type == self.device.type
+        for t in (site_local, frag, out_row, out_site, out_frag):
+            assert t.dtype == torch.int32 and t.is_contiguous() and t.device.type == self.device.type
+        self._check(self.lib.phz_expand_runs(self.ctx, int(run_row.shape[0]), run_first.data_ptr(), run_dest.data_ptr(),
+                                             run_row.data_ptr(), run_site_base.data_ptr(), int(site_local.shape[0]),
+                                             site_local.data_ptr(), frag.data_ptr(), site_map.data_ptr(), out_row.data_ptr(),
+                                             out_site.data_ptr(), out_frag.data_ptr()))
 
     def gene_ae_pairs(self, rows, feats):
         """phaser_gene_ae join + distinct-read counts (phz_gene_ae_pairs).  `rows` / `feats`: phaser_gene_ae.Rows /

@@ -340,7 +340,7 @@ def _typed(buf, off, n, eb):
 
 
 def merge_results_device(recv, lay, heads, names, gids, plan, vt: VariantTable, n_bams: int, meta: PhaseResult,
-                         contig_of, want_read_ids=False, want_kept_tuples=False, host_cache=None) -> PhaseResult:
+                         contig_of, want_read_ids=False, want_kept_tuples=False, host_cache=None, engine=None) -> PhaseResult:
     """merge_results on the arrays as the gather left them in rank 0's memory (device tensors, or CPU tensors under
     gloo): same result, but every step is a tensor operation where the data already is, and the merged arrays reach
     the host in ONE copy.  recv[r]: packed byte buffer of rank r (None: no contigs); lay[r]: its layout; gids[r]:
@@ -364,6 +364,37 @@ def merge_results_device(recv, lay, heads, names, gids, plan, vt: VariantTable, 
                 torch.cuda.synchronize(dev)
             trace.append((what, time.perf_counter()))
     mark("start")
+    # ---- ONE page-locked landing buffer (grow-only, the arrays returned are views of it), filled in two goes: whatever
+    # is finished before the read lists are merged leaves on a side stream and travels under that merge
+    bound = 64 * 64 + 4096 + V * (8 + 12 + 12 + 8 * nb + 4 + 1) + sum(int(recv[r].numel()) for r in live)
+    host = host_cache.get("buf") if host_cache is not None else None
+    if host is None or host.numel() < bound:
+        host = torch.empty(int(bound * 1.25), dtype=torch.uint8)
+        if dev.type == "cuda":
+            try:
+                host = host.pin_memory()
+            except RuntimeError:
+                pass
+        if host_cache is not None:
+            host_cache["buf"] = host
+    ship_state = {"total": 0, "place": [], "host": host, "done": set()}
+
+    def ship(arrays, stream=None):
+        for k, t in arrays.items():
+            if k in ship_state["done"]:
+                continue
+            t = t.contiguous(); arrays[k] = t
+            off = (ship_state["total"] + 63) // 64 * 64; nbytes = t.numel() * t.element_size()
+            if off + nbytes > host.numel():
+                raise RuntimeError("merge: landing buffer too small for " + k)
+            ship_state["place"].append((k, off, nbytes)); ship_state["total"] = off + nbytes; ship_state["done"].add(k)
+            if nbytes:
+                src = t.view(torch.uint8).reshape(-1) if t.dtype != torch.uint8 else t.reshape(-1)
+                if stream is not None:
+                    with torch.cuda.stream(stream):
+                        host[off:off + nbytes].copy_(src, non_blocking=True)
+                else:
+                    host[off:off + nbytes].copy_(src, non_blocking=True)
 
     def count(r, name):
         for nm, _off, n, _eb in lay[r][0]:
@@ -489,52 +520,53 @@ def merge_results_device(recv, lay, heads, names, gids, plan, vt: VariantTable, 
     # ---- read lists: rows of one block live on one rank and every rank's rows are already sorted, so the merged order
     # follows from the run lengths alone (no sort of the entries): destination = start of the run in the merged order +
     # offset inside the run
+    if dev.type == "cuda":
+        side = host_cache.setdefault("side_stream", torch.cuda.Stream(device=dev)) if host_cache is not None else torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        ship(out, side)
     nrl = [count(r, "rl_row") for r in live] if has("rl_row") else []
     if sum(nrl):
-        row = u(allr("rl_row")); rk = per_element(nrl, np.arange(nl))
-        urow, cnt = torch.unique_consecutive((rk << 40) | row, return_counts=True)       # runs never join across ranks
-        lrow = urow & ((1 << 40) - 1); rrun = urow >> 40
+        total = int(sum(nrl))
+        row32 = allr("rl_row")
+        # runs of equal row ids (a run never continues across two ranks' arrays): head flags on the 32-bit ids
+        head = torch.ones(total, dtype=torch.bool, device=dev)
+        head[1:] = row32[1:] != row32[:-1]
+        rstart = torch.as_tensor(bases(nrl), device=dev)
+        head[rstart[rstart < total]] = True
+        lstart = torch.nonzero(head)[:, 0]                                               # where the run sits in the concatenation
+        nrun = int(lstart.shape[0])
+        first = torch.cat([lstart, torch.full((1,), total, dtype=i64, device=dev)])
+        cnt = first[1:] - first[:-1]
+        lrow = u(row32[lstart])
+        rrun = torch.searchsorted(rstart, lstart, right=True) - 1                        # position of the run's rank in `live`
         fb_of_run = torch.as_tensor(fbase, device=dev)[rrun]
         nrow = (new_of_cat[(lrow >> (bb + 1)) + fb_of_run] << (bb + 1)) | (lrow & low)
         o = torch.argsort(nrow)
         start_sorted = torch.cumsum(cnt[o], 0) - cnt[o]
         start = torch.empty_like(start_sorted); start[o] = start_sorted
-        lstart = torch.cumsum(cnt, 0) - cnt                                              # where the run sits in the concatenation
-        total = int(sum(nrl))
-        dest = torch.repeat_interleave(start - lstart, cnt) + torch.arange(total, dtype=i64, device=dev)
         rl_row = torch.empty(total, dtype=torch.int32, device=dev); rl_var = torch.empty(total, dtype=torch.int32, device=dev)
         rl_frag = torch.empty(total, dtype=torch.int32, device=dev)
-        rl_row[dest] = torch.repeat_interleave(nrow, cnt).to(torch.int32)
-        rl_var[dest] = gid[u(allr("rl_var")) + per_element(nrl, vbase)].to(torch.int32)
-        rl_frag[dest] = allr("rl_frag")
+        vb_of_run = torch.as_tensor(vbase, device=dev)[rrun]
+        if engine is not None and engine.device.type == dev.type:
+            # one kernel of the native library: entry -> run (bisection over the run table) -> place, ids renumbered
+            engine.expand_runs(first.contiguous(), start.contiguous(), nrow.contiguous(), vb_of_run.contiguous(),
+                               allr("rl_var").contiguous(), allr("rl_frag").contiguous(), gid.contiguous(), rl_row, rl_var, rl_frag)
+        else:       # the same as tensor operations (arrays that do not live where the engine's do: gloo on a GPU box)
+            dest = torch.repeat_interleave(start - lstart, cnt) + torch.arange(total, dtype=i64, device=dev)
+            rl_row[dest] = torch.repeat_interleave(nrow, cnt).to(torch.int32)
+            rl_var[dest] = gid[u(allr("rl_var")) + torch.repeat_interleave(vb_of_run, cnt)].to(torch.int32)
+            rl_frag[dest] = allr("rl_frag")
         out["rl_row"] = rl_row; out["rl_var"] = rl_var; out["rl_frag"] = rl_frag
     else:
         for k in ("rl_row", "rl_var", "rl_frag"):
             out[k] = torch.zeros(0, dtype=torch.int32, device=dev)
     out.update(sg)
     mark("edges + read lists")
-    # ---- one copy to the host
-    total = 0; place = []
-    for k, t in out.items():
-        t = t.contiguous(); out[k] = t
-        off = (total + 63) // 64 * 64
-        place.append((k, off, t.numel() * t.element_size())); total = off + place[-1][2]
-    host = host_cache.get("buf") if host_cache is not None else None
-    if host is None or host.numel() < total:          # grow-only page-locked landing buffer (the arrays returned are views)
-        host = torch.empty(int(max(total, 64) * 1.25) + 4096, dtype=torch.uint8)
-        if dev.type == "cuda":
-            try:
-                host = host.pin_memory()
-            except RuntimeError:
-                pass
-        if host_cache is not None:
-            host_cache["buf"] = host
-    for (k, off, nbytes) in place:
-        if nbytes:
-            host[off:off + nbytes].copy_(out[k].view(torch.uint8).reshape(-1) if out[k].dtype != torch.uint8 else out[k].reshape(-1),
-                                         non_blocking=True)
+    # ---- the rest of the copy to the host (the arrays finished before the read lists are already on their way)
+    ship(out)
     if dev.type == "cuda":
         torch.cuda.synchronize(dev)
+    total = ship_state["total"]; place = ship_state["place"]; host = ship_state["host"]
     mark("copy to the host (%d bytes)" % total)
     if trace is not None:
         print("[merge] " + ", ".join("%s %.2f ms" % (w, (t - trace[i][1]) * 1e3) for i, (w, t) in enumerate(trace[1:])), file=sys.stderr)
@@ -735,7 +767,7 @@ class ShardedRun:
         recv, lay, heads = got
         out = merge_results_device(recv, lay, heads, self.names, self.gids_dev, self.plan, self.vt, self.n_bams, res,
                                    self.contig_of_dev, want_read_ids=self.params.want_read_ids,
-                                   want_kept_tuples=self.params.want_kept_tuples, host_cache=self.host_cache)
+                                   want_kept_tuples=self.params.want_kept_tuples, host_cache=self.host_cache, engine=self.engine)
         if self.timers is not None:
             self.timers["merge_on_rank0_ms"] = self.timers.get("merge_on_rank0_ms", 0.0) + (time.perf_counter() - t0) * 1e3
         return out

@@ -1,0 +1,14 @@
+#!/bin/bash
+# Round 2, visit S (2 GPUs): where the merge on rank 0 spends its time (PHZ_MERGE_TRACE: synchronised section times).
+mkdir -p gpurun_out
+PHZ_MERGE_TRACE=1 timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29663 bench.py --gpus 2 --steps 5 --warmup 3 --no_replicas > gpurun_out/r2s_bench_n2.json 2> gpurun_out/r2s_bench_n2.err
+grep "\[merge\]" gpurun_out/r2s_bench_n2.err | tail -6
+python - <<'PY'
+import json
+try:
+    d = json.loads(open("gpurun_out/r2s_bench_n2.json").read().strip().splitlines()[-1])
+    print("N=2 value %.4g ms %.3f" % (d["value"], d["ms_per_step"]), "e2e", d["e2e"]["ms_per_step"], d["e2e"]["single_sample_ms"])
+    print("  sharding", json.dumps(d.get("sharding", {}).get("collectives_ms_rank0_one_step_synchronised")), d.get("full_size_checks"))
+except Exception as e:
+    print("ERR", e)
+PY
