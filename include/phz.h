@@ -175,6 +175,11 @@ int phz_commit_bam(phz_ctx* ctx, int bam_index, int32_t as_cutoff, const uint32_
  * (base_match_count, base_mismatch_count).  Separate from phz_build_graph so that the host can compute the
  * critical values (which need only the noise level) while the graph is being built. */
 int phz_variant_stats(phz_ctx* ctx, uint64_t* h_noise);
+/* The same in two halves, so that the host does not wait between the commits and the graph stage: the first half queues the
+ * work and the copy of the two sums to a page-locked slot, the second waits for exactly that copy -- from any host thread,
+ * e.g. the one that computes the critical values while the caller's thread queues phz_build_graph. */
+int phz_variant_stats_async(phz_ctx* ctx);
+int phz_noise_wait(phz_ctx* ctx, uint64_t* h_noise);
 
 /* Unique read sets, generate_connectivity_map (phaser.py:1265-1285), pair enumeration (:667-678) and the
  * count part of test_variant_connection (:1594-1642). */

@@ -322,7 +322,25 @@ int phz_commit_bam(phz_ctx* ctx, int bam_index, int32_t as_cutoff, const uint32_
 int phz_variant_stats(phz_ctx* ctx, uint64_t* h_noise) {
   PHZ_TRY
   u64 nz[2] = {0, 0};
-  ctx->p.variant_stats(nz);
+  void* ev = ctx->p.noise_event; ctx->p.noise_event = nullptr;        // synchronous form: wait here
+  try { ctx->p.variant_stats(nz); } catch (...) { ctx->p.noise_event = ev; throw; }
+  ctx->p.noise_event = ev;
+  h_noise[0] = nz[0]; h_noise[1] = nz[1];
+  PHZ_CATCH
+}
+
+int phz_variant_stats_async(phz_ctx* ctx) {
+  PHZ_TRY
+  if (!ctx->p.noise_event) ctx->p.noise_event = ctx->p.be.new_event();
+  u64 unused[2];
+  ctx->p.variant_stats(unused);
+  PHZ_CATCH
+}
+
+int phz_noise_wait(phz_ctx* ctx, uint64_t* h_noise) {
+  PHZ_TRY
+  u64 nz[2] = {0, 0};
+  ctx->p.noise_wait(nz);
   h_noise[0] = nz[0]; h_noise[1] = nz[1];
   PHZ_CATCH
 }

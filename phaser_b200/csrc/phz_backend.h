@@ -260,6 +260,8 @@ struct DeviceBackend {
   void free_event(void* ev) { if (ev) cudaEventDestroy((cudaEvent_t)ev); }
   void copy_record(void* ev) { PHZ_CUDA(cudaEventRecord((cudaEvent_t)ev, copy_stream)); }
   void wait_event(void* ev) { PHZ_CUDA(cudaStreamWaitEvent(stream, (cudaEvent_t)ev, 0)); }
+  void record_event(void* ev) { PHZ_CUDA(cudaEventRecord((cudaEvent_t)ev, stream)); }       // on the main stream
+  void host_wait_event(void* ev) { PHZ_CUDA(cudaEventSynchronize((cudaEvent_t)ev)); }       // any host thread; the stream runs on
   void sync() { PHZ_CUDA(cudaStreamSynchronize(stream)); syncs++; }
 
   template <class F>
@@ -412,6 +414,8 @@ struct HostSimBackend {
   void free_event(void*) {}
   void copy_record(void*) {}
   void wait_event(void*) {}
+  void record_event(void*) {}
+  void host_wait_event(void*) {}
   void sync() {}
 
   template <class F>

@@ -89,6 +89,20 @@ def noise_level(match: int, mismatch: int) -> float:
     return float(mismatch) / (float(match + mismatch) * 2)
 
 
+_POOL_THREADS = 2
+_POOL = None
+
+
+def _pool():
+    """resident helper thread of run_path (critical values under the graph stage; splitting the large totals over
+    several threads was measured slower: the numpy calls around the ufunc serialise on the GIL)"""
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=_POOL_THREADS, thread_name_prefix="phz-host")
+    return _POOL
+
+
 def critical_values(max_total: int, noise_e: float, cc_threshold: float, totals=None) -> np.ndarray:
     """kstar[n] = min{k : binom.cdf(k, n, p) >= cc_threshold}, p = 1-(6e+10e^2)  (phaser.py:1649, 696).
     An edge with 0 < c_supporting < c_total is dropped iff c_supporting < kstar[c_total]; uses the same
@@ -238,33 +252,43 @@ def run_path(engine: Engine, vt: VariantTable, batches, params: PhaseParams, n_f
                                   "(the reference fails on int('') at phaser.py:1304); use --as_q_cutoff 0" % n_missing)
         cutoffs.append(cutoff)
         kept.append(engine.commit_bam(b, None if cutoff is None else int(math.ceil(cutoff))))
-    match, mism = engine.variant_stats()
+    # The two noise sums are not needed by THIS thread before the graph stage is queued: variant_stats only queues its work
+    # and the copy of the sums; the helper thread below waits for that copy (an event), so the device never idles here.
+    overlap_reduce = comm.world_size > 1 and getattr(comm, "timers", None) is None
+    async_noise = comm.world_size == 1 or overlap_reduce
+    if async_noise:
+        engine.variant_stats_async(); match = mism = None
+    else:
+        match, mism = engine.variant_stats()
     # The critical values of the small totals (the bulk of the edges) need only the noise level: a host thread computes
     # them while the GPU builds the graph (scipy's ufuncs and the C calls release the GIL).  With several ranks the same
     # thread first sums the two noise counters over the ranks, so that exchange is hidden under the graph stage as well
     # (no other collective is issued meanwhile: the order of collectives stays the same on every rank).
     pre = {}
-    overlap_reduce = comm.world_size > 1 and getattr(comm, "timers", None) is None
-    if not overlap_reduce:
+    if not async_noise:
         match, mism = comm.allreduce_sum_ints([match, mism])
 
     def noise_and_critical_values(local=(match, mism)):
         try:
+            if async_noise:
+                local = engine.noise_wait()
             m_, x_ = comm.allreduce_sum_ints(list(local)) if overlap_reduce else local
             pre["counts"] = (m_, x_)
             if m_ > 0:
                 pre["k"] = critical_values(PRECOMPUTED_TOTALS, noise_level(m_, x_), params.cc_threshold)
         except BaseException as e:          # noqa: BLE001 -- re-raised on the main thread
             pre["error"] = e
-    worker = threading.Thread(target=noise_and_critical_values)
-    worker.start()
+    if comm.world_size == 1:
+        worker = _pool().submit(noise_and_critical_values)      # a resident thread: no start-up cost on the critical path
+    else:       # its own thread: the helper takes part in a collective, and logical shards (threads) must not queue behind each other
+        worker = threading.Thread(target=noise_and_critical_values); worker.start(); worker.result = worker.join
     _t = time.perf_counter() if _TRACE else 0.0
     engine.set_option("big_total_threshold", PRECOMPUTED_TOTALS)
     try:
         n_edges, max_tot = engine.build_graph(n_fragments, excl)
     finally:
         _t1 = time.perf_counter() if _TRACE else 0.0
-        worker.join()
+        worker.result()
     if "error" in pre:
         raise pre["error"]
     match, mism = pre["counts"]
