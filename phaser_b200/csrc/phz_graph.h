@@ -228,6 +228,19 @@ struct DirectSink {
 
 
 #ifdef __CUDACC__
+// counter += v on a shared-memory word, result not needed: the shared-space reduction (the pointers reach the sink as generic
+// addresses, which would make these generic atomics)
+#ifndef PHZ_FRAG_RED_SHARED
+#define PHZ_FRAG_RED_SHARED 1
+#endif
+__device__ __forceinline__ void red_shared_add(u32* p, u32 v) {
+#if PHZ_FRAG_RED_SHARED
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+#else
+  atomicAdd(p, v);
+#endif
+}
+
 template <int VB_BAMS>
 struct CtaSink {
   u32* s_sz; u32* s_vb; u32 base; int nb; u32* sz; u32* vbc;
@@ -235,11 +248,11 @@ struct CtaSink {
   PairTable pt;
   __device__ __forceinline__ void set_size(u32 v, int x) {
     const u32 d = v - base;
-    if (d < (u32)FRAG_W) atomicAdd(&s_sz[d * 3 + x], 1u); else atomicAdd(&sz[(int64_t)v * 3 + x], 1u);
+    if (d < (u32)FRAG_W) red_shared_add(&s_sz[d * 3 + x], 1u); else atomicAdd(&sz[(int64_t)v * 3 + x], 1u);
   }
   __device__ __forceinline__ void bam_count(u32 v, u32 bam, int a) {
     const u32 d = v - base;
-    if (d < (u32)FRAG_W && nb <= VB_BAMS) atomicAdd(&s_vb[(d * nb + bam) * 2 + a], 1u);
+    if (d < (u32)FRAG_W && nb <= VB_BAMS) red_shared_add(&s_vb[(d * nb + bam) * 2 + a], 1u);
     else atomicAdd(&vbc[((int64_t)v * nb + bam) * 2 + a], 1u);
   }
   __device__ __forceinline__ void pair(u64 key, u32 cells) {
@@ -255,7 +268,7 @@ struct CtaSink {
       h = (h + 1) & (FRAG_HS - 1);
     }
     if (found >= 0) {
-      while (cells) { const int c = __ffs(cells) - 1; cells &= cells - 1; atomicAdd(&h_vals[found * 5 + (c >> 1)], 1u << (16 * (c & 1))); }
+      while (cells) { const int c = __ffs(cells) - 1; cells &= cells - 1; red_shared_add(&h_vals[found * 5 + (c >> 1)], 1u << (16 * (c & 1))); }
     } else {        // the CTA's table is crowded here: straight to the run-wide table
       const int s = pair_slot(pt, key);
       if (s >= 0) while (cells) { const int c = __ffs(cells) - 1; cells &= cells - 1; atomicAdd(&pt.vals[(int64_t)s * PAIR_CELLS + c], 1u); }

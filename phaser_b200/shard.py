@@ -71,8 +71,10 @@ class DistComm:
             # called from the critical-value thread while the main thread queues the graph stage: a stream of its own, so
             # the exchange is ordered after nothing but its own upload (on the engine's stream it would queue behind
             # every graph kernel launched so far and the thread would wait for all of them)
+            # -- and a HIGH-PRIORITY one: the collective's few CTAs must not wait until the graph kernels that fill every SM
+            # have drained (measured at N = 2..8: the helper thread got its sums ~0.7 ms late and the critical values with them)
             if self._side is None:
-                self._side = torch.cuda.Stream(device=self.device)
+                self._side = torch.cuda.Stream(device=self.device, priority=-1)
             with torch.cuda.stream(self._side):
                 t = torch.tensor(list(xs), dtype=torch.int64, device=self.device)
                 dist.all_reduce(t, op=dist.ReduceOp.SUM)
