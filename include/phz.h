@@ -180,6 +180,13 @@ int phz_variant_stats(phz_ctx* ctx, uint64_t* h_noise);
  * e.g. the one that computes the critical values while the caller's thread queues phz_build_graph. */
 int phz_variant_stats_async(phz_ctx* ctx);
 int phz_noise_wait(phz_ctx* ctx, uint64_t* h_noise);
+/* Contig-sharded runs: the two sums must be added over the ranks before anybody uses them (phaser.py:610-631 is global).
+ * phz_variant_stats_device leaves this rank's sums in the caller's DEVICE buffer (uint64[2]; no wait, no host copy), the
+ * caller all-reduces that buffer in stream order (NCCL on the context's stream: the collective runs between this stage's
+ * kernels and the graph stage's, never beside them), and phz_noise_publish queues its copy to the slot phz_noise_wait
+ * reads.  No host thread takes part in the exchange. */
+int phz_variant_stats_device(phz_ctx* ctx, uint64_t* d_noise);
+int phz_noise_publish(phz_ctx* ctx, const uint64_t* d_noise);
 
 /* Unique read sets, generate_connectivity_map (phaser.py:1265-1285), pair enumeration (:667-678) and the
  * count part of test_variant_connection (:1594-1642). */

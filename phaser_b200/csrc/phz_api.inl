@@ -337,6 +337,22 @@ int phz_variant_stats_async(phz_ctx* ctx) {
   PHZ_CATCH
 }
 
+int phz_variant_stats_device(phz_ctx* ctx, uint64_t* d_noise) {
+  PHZ_TRY
+  u64 unused[2];
+  ctx->p.noise_dev_out = (u64*)d_noise;
+  try { ctx->p.variant_stats(unused); } catch (...) { ctx->p.noise_dev_out = nullptr; throw; }
+  ctx->p.noise_dev_out = nullptr;
+  PHZ_CATCH
+}
+
+int phz_noise_publish(phz_ctx* ctx, const uint64_t* d_noise) {
+  PHZ_TRY
+  if (!ctx->p.noise_event) ctx->p.noise_event = ctx->p.be.new_event();
+  ctx->p.noise_publish((const u64*)d_noise);
+  PHZ_CATCH
+}
+
 int phz_noise_wait(phz_ctx* ctx, uint64_t* h_noise) {
   PHZ_TRY
   u64 nz[2] = {0, 0};

@@ -701,7 +701,7 @@ struct Pipeline {
   int lazy_canonical = 1;           // 1: the tile kernel's output stays in arrival order until somebody needs canonical order
   bool tile_order = false, canonical_valid = true; int64_t tiles_cur = 0;
   int graph_mode = 1;               // 1: fragment-table graph stage (phz_graph.h), 0: sort-based stage (A/B switch and fallback)
-  void* noise_event = nullptr; u64* noise_host = nullptr; bool noise_host_pinned = false, noise_pending = false;      // asynchronous variant_stats
+  u64* noise_dev_out = nullptr; void* noise_event = nullptr; u64* noise_host = nullptr; bool noise_host_pinned = false, noise_pending = false;      // asynchronous variant_stats
   int frag_stage = 1;               // fragment kernel of the fragment-table stage: 1 slot chunks staged in shared memory, 0 ranges of fragment ids
   u64 n_frag_deferred = 0;          // fragments of the last graph stage that the slot-chunk kernel left to its second pass
   Buf<B, u32> frag_deferred, v_packed, v_rank_in_final;
@@ -1198,13 +1198,22 @@ struct Pipeline {
         cr[c] = r;
       });
     }
-    if (noise_event) {      // no wait here: the two sums travel to a page-locked slot, an event tells when (noise_wait)
+    if (noise_dev_out) {    // no wait, no host copy: the two sums go to the caller's device buffer (a collective sums them over the ranks)
+      be.d2d(noise_dev_out, nz, 2 * sizeof(u64));
+    } else if (noise_event) {      // no wait here: the two sums travel to a page-locked slot, an event tells when (noise_wait)
       if (!noise_host) { bool pinned = false; noise_host = (u64*)B::host_alloc(2 * sizeof(u64), &pinned); noise_host_pinned = pinned; }
       be.d2h_async(noise_host, nz, 2 * sizeof(u64));
       be.record_event(noise_event);
       noise_pending = true;
     } else be.d2h(noise_out, nz, 2 * sizeof(u64));
     be.stage("graph.variant_lists.end");
+  }
+  // the (summed) noise counters of a device buffer -> the page-locked slot + event of noise_wait
+  void noise_publish(const u64* d_in) {
+    if (!noise_host) { bool pinned = false; noise_host = (u64*)B::host_alloc(2 * sizeof(u64), &pinned); noise_host_pinned = pinned; }
+    be.d2h_async(noise_host, d_in, 2 * sizeof(u64));
+    be.record_event(noise_event);
+    noise_pending = true;
   }
   // second half of an asynchronous variant_stats: may be called from another host thread while this one queues the graph stage
   void noise_wait(u64* noise_out) {

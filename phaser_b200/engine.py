@@ -73,7 +73,7 @@ EXPORTS = ["phz_last_error", "phz_backend_name", "phz_create", "phz_destroy", "p
            "phz_host_reads_view", "phz_host_reads_free", "phz_set_haplo_blacklist", "phz_write_sam",
            "phz_set_indel_alleles", "phz_pack_reads", "phz_packed_view", "phz_packed_bytes", "phz_packed_free",
            "phz_map_reads_packed", "phz_prefetch_packed", "phz_gene_ae_pairs", "phz_set_big_critical_values",
-           "phz_copy_array", "phz_expand_runs", "phz_variant_stats_async", "phz_noise_wait", "phz_vcf_open", "phz_vcf_close", "phz_vcf_text", "phz_vcf_chrom_line", "phz_vcf_parse",
+           "phz_copy_array", "phz_expand_runs", "phz_variant_stats_async", "phz_noise_wait", "phz_variant_stats_device", "phz_noise_publish", "phz_vcf_open", "phz_vcf_close", "phz_vcf_text", "phz_vcf_chrom_line", "phz_vcf_parse",
            "phz_vcf_write", "phz_vcf_records", "phz_write_bam", "phz_vcf_save", "phz_format_read_lists", "phz_vcf_site_text", "phz_upload", "phz_sync_count",
            "phz_fragdict_blob_bytes", "phz_fragdict_export", "phz_fragdict_import"]
 
@@ -93,6 +93,8 @@ def _declare(lib):
     lib.phz_variant_stats.argtypes = [c_void_p, POINTER(c_uint64)]
     lib.phz_variant_stats_async.argtypes = [c_void_p]
     lib.phz_noise_wait.argtypes = [c_void_p, POINTER(c_uint64)]
+    lib.phz_variant_stats_device.argtypes = [c_void_p, c_void_p]
+    lib.phz_noise_publish.argtypes = [c_void_p, c_void_p]
     lib.phz_build_graph.argtypes = [c_void_p, c_uint64, c_uint64, POINTER(c_int64), POINTER(c_uint32)]
     lib.phz_phase.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_uint64, POINTER(c_int64), POINTER(c_int)]
     lib.phz_read_lists.argtypes = [c_void_p, c_uint64, POINTER(c_int64)]
@@ -486,6 +488,15 @@ class Engine:
     def variant_stats_async(self):
         """first half of variant_stats: queues the work, does not wait (noise_wait returns the two sums)"""
         self._check(self.lib.phz_variant_stats_async(self.ctx))
+
+    def variant_stats_device(self, t):
+        """variant_stats with the two sums left in `t` (int64[2] on the engine's device): no wait, no host copy"""
+        assert t.dtype == torch.int64 and t.numel() == 2 and t.is_contiguous() and t.device.type == self.device.type
+        self._check(self.lib.phz_variant_stats_device(self.ctx, t.data_ptr()))
+
+    def noise_publish(self, t):
+        """queues the copy of `t` (the sums, e.g. after an all-reduce) to the slot noise_wait reads"""
+        self._check(self.lib.phz_noise_publish(self.ctx, t.data_ptr()))
 
     def noise_wait(self):
         noise = (c_uint64 * 2)()

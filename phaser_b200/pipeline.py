@@ -254,9 +254,18 @@ def run_path(engine: Engine, vt: VariantTable, batches, params: PhaseParams, n_f
         kept.append(engine.commit_bam(b, None if cutoff is None else int(math.ceil(cutoff))))
     # The two noise sums are not needed by THIS thread before the graph stage is queued: variant_stats only queues its work
     # and the copy of the sums; the helper thread below waits for that copy (an event), so the device never idles here.
+    # Several ranks: the sums are added over the ranks ON THE DEVICE, in stream order (comm.allreduce_sum_device: the
+    # collective runs between this stage's kernels and the graph stage's; issued from the helper thread it had to find
+    # room beside the graph kernels and came back a millisecond late).
     overlap_reduce = comm.world_size > 1 and getattr(comm, "timers", None) is None
-    async_noise = comm.world_size == 1 or overlap_reduce
-    if async_noise:
+    stream_reduce = comm.world_size > 1 and hasattr(comm, "allreduce_sum_device")
+    async_noise = comm.world_size == 1 or overlap_reduce or stream_reduce
+    if stream_reduce:
+        import torch
+        sums = torch.zeros(2, dtype=torch.int64, device=engine.device)
+        engine.variant_stats_device(sums); comm.allreduce_sum_device(sums); engine.noise_publish(sums)
+        overlap_reduce = False; match = mism = None
+    elif async_noise:
         engine.variant_stats_async(); match = mism = None
     else:
         match, mism = engine.variant_stats()
@@ -270,12 +279,18 @@ def run_path(engine: Engine, vt: VariantTable, batches, params: PhaseParams, n_f
 
     def noise_and_critical_values(local=(match, mism)):
         try:
+            w0 = time.perf_counter() if _TRACE else 0.0
             if async_noise:
                 local = engine.noise_wait()
+            w1 = time.perf_counter() if _TRACE else 0.0
             m_, x_ = comm.allreduce_sum_ints(list(local)) if overlap_reduce else local
+            w2 = time.perf_counter() if _TRACE else 0.0
             pre["counts"] = (m_, x_)
             if m_ > 0:
                 pre["k"] = critical_values(PRECOMPUTED_TOTALS, noise_level(m_, x_), params.cc_threshold)
+            if _TRACE:
+                print("[run_path helper] wait for the noise sums %.2f ms, all-reduce %.2f ms, critical values %.2f ms" % (
+                    (w1 - w0) * 1e3, (w2 - w1) * 1e3, (time.perf_counter() - w2) * 1e3), file=sys.stderr)
         except BaseException as e:          # noqa: BLE001 -- re-raised on the main thread
             pre["error"] = e
     if comm.world_size == 1:

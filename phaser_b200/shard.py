@@ -65,6 +65,17 @@ class DistComm:
         self._timed("allreduce_as_histogram_ms", lambda: dist.all_reduce(t, op=dist.ReduceOp.SUM))
         return t
 
+    def allreduce_sum_device(self, t):
+        """in-place sum over the ranks of a tensor that lives on the engine's device, in STREAM order: with NCCL the host does
+        not wait and the collective runs where it is queued (between the kernels before and after it)"""
+        if self.timers is not None:
+            self._timed("allreduce_noise_ms", lambda: dist.all_reduce(t, op=dist.ReduceOp.SUM))
+        elif t.device.type == self.device.type:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        else:           # gloo beside a CUDA engine (tests on a one-GPU box): through the collective's own device
+            u = t.to(self.device); dist.all_reduce(u, op=dist.ReduceOp.SUM); t.copy_(u)
+        return t
+
     def allreduce_sum_ints(self, xs):
         import threading
         if self.device.type == "cuda" and threading.current_thread() is not threading.main_thread():
