@@ -660,6 +660,10 @@ __global__ void __launch_bounds__(KF_THREADS, MIN_CTAS) k1_tile_kernel(ReadsView
 template <class B>
 struct Pipeline {
   B be;
+  ~Pipeline() {
+    if (noise_host) B::host_free(noise_host, noise_host_pinned);
+    if (noise_event) be.free_event(noise_event);
+  }
   bool stats_done = false;
   int k1_min_ctas = 8;        // register budget of the tile kernel: 8 -> 32 regs, 6 -> 40 regs, else unconstrained
   int k1_mode = 3;            // 3: tile kernel + permute (default), 2: fused look-back, 1: windowed two-pass, 0: generic two-pass

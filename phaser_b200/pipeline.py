@@ -294,16 +294,17 @@ def run_path(engine: Engine, vt: VariantTable, batches, params: PhaseParams, n_f
         except BaseException as e:          # noqa: BLE001 -- re-raised on the main thread
             pre["error"] = e
     if comm.world_size == 1:
-        worker = _pool().submit(noise_and_critical_values)      # a resident thread: no start-up cost on the critical path
-    else:       # its own thread: the helper takes part in a collective, and logical shards (threads) must not queue behind each other
-        worker = threading.Thread(target=noise_and_critical_values); worker.start(); worker.result = worker.join
+        wait_for_helper = _pool().submit(noise_and_critical_values).result      # a resident thread: no start-up cost on the critical path
+    else:       # its own thread: the helper may take part in a collective, and logical shards (threads) must not queue behind each other
+        helper = threading.Thread(target=noise_and_critical_values); helper.start()
+        wait_for_helper = helper.join
     _t = time.perf_counter() if _TRACE else 0.0
     engine.set_option("big_total_threshold", PRECOMPUTED_TOTALS)
     try:
         n_edges, max_tot = engine.build_graph(n_fragments, excl)
     finally:
         _t1 = time.perf_counter() if _TRACE else 0.0
-        worker.result()
+        wait_for_helper()
     if "error" in pre:
         raise pre["error"]
     match, mism = pre["counts"]
