@@ -383,3 +383,26 @@ def test_a_huge_fragment_takes_the_sort_based_graph(hostsim, tmp_path):
     assert ca == cb and cc == cb
     for k in a:
         assert np.array_equal(a[k], b[k]) and np.array_equal(c[k], b[k]), k
+
+
+def test_variant_stats_in_halves_returns_the_same_sums(hostsim, tmp_path):
+    """phz_variant_stats == phz_variant_stats_async + phz_noise_wait == phz_variant_stats_device + phz_noise_publish +
+    phz_noise_wait (the forms run_path uses on one rank / on several ranks), and a wait without a pending half fails."""
+    import torch
+    from phaser_b200 import engine as eng
+    vcf, sams = util.make_case(tmp_path, 44, 200, 2000, n_bams=1)
+    vt, st, batches, col, fd = util.load_inputs(vcf, sams)
+    hostsim.set_variants(vt)
+    hostsim.map_reads(hostsim.upload_reads(batches[0]), 10, 0.0); hostsim.commit_bam(0, None)
+    whole = hostsim.variant_stats()
+    assert whole[0] > 0
+    hostsim.variant_stats_async()
+    assert hostsim.noise_wait() == whole
+    t = torch.zeros(2, dtype=torch.int64)
+    hostsim.variant_stats_device(t)
+    assert tuple(int(x) for x in t.tolist()) == whole
+    t += 5                                   # what an all-reduce over the ranks would leave behind
+    hostsim.noise_publish(t)
+    assert hostsim.noise_wait() == (whole[0] + 5, whole[1] + 5)
+    with pytest.raises(eng.PhzError):
+        hostsim.noise_wait()
